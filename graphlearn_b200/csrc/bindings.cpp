@@ -1,0 +1,65 @@
+// pybind11 surface of the native extension `graphlearn_b200._C`.
+#include <torch/extension.h>
+
+namespace glb {
+// sampling.cu
+std::vector<at::Tensor> sample_neighbors(const at::Tensor&, const at::Tensor&, int64_t, int64_t, int64_t,
+                                         const c10::optional<at::Tensor>&, bool, int64_t, int64_t,
+                                         const at::Tensor&, int64_t, bool);
+at::Tensor get_degrees(const at::Tensor&, const at::Tensor&, int64_t);
+std::vector<at::Tensor> sample_full(const at::Tensor&, const at::Tensor&, int64_t, bool);
+void rng_advance(const at::Tensor&, int64_t);
+// gather.cu
+at::Tensor gather_rows(const at::Tensor&, const at::Tensor&, bool, double);
+at::Tensor gather_agg(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t);
+void scatter_add_rows(const at::Tensor&, const at::Tensor&, const at::Tensor&, double);
+// sage_fused.cu
+int64_t sage_pad_k(int64_t);
+int64_t sage_smem_bytes(int64_t, int64_t);
+at::Tensor pack_weight_sw128(const at::Tensor&, int64_t);
+std::vector<at::Tensor> sage_fused_forward(const at::Tensor&, const c10::optional<at::Tensor>&, const at::Tensor&,
+                                           const c10::optional<at::Tensor>&, int64_t, int64_t, int64_t,
+                                           const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t,
+                                           bool, bool, bool);
+// comm.cu
+int64_t symm_alloc(int64_t, int64_t);
+void symm_free(int64_t, int64_t);
+py::bytes ipc_get_handle(int64_t, int64_t);
+int64_t ipc_open_handle(const std::string&, int64_t);
+void ipc_close_handle(int64_t, int64_t);
+at::Tensor tensor_from_ptr(int64_t, std::vector<int64_t>, int64_t, int64_t);
+void allreduce_oneshot(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, double);
+void step_advance(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t);
+void adam_flat(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
+               double, double, double, double, double);
+// host_loader.cpp
+std::vector<at::Tensor> load_table(const std::string&, bool, bool, bool, bool, std::vector<int64_t>,
+                                   std::vector<int64_t>, const std::string&, const std::string&, int64_t);
+void save_embeddings(const std::string&, const at::Tensor&, const at::Tensor&, bool);
+}  // namespace glb
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "graphlearn_b200 native runtime: sm_100a kernels + host loader";
+  m.def("sample_neighbors", &glb::sample_neighbors);
+  m.def("get_degrees", &glb::get_degrees);
+  m.def("sample_full", &glb::sample_full);
+  m.def("rng_advance", &glb::rng_advance);
+  m.def("gather_rows", &glb::gather_rows);
+  m.def("gather_agg", &glb::gather_agg);
+  m.def("scatter_add_rows", &glb::scatter_add_rows);
+  m.def("sage_pad_k", &glb::sage_pad_k);
+  m.def("sage_smem_bytes", &glb::sage_smem_bytes);
+  m.def("pack_weight_sw128", &glb::pack_weight_sw128);
+  m.def("sage_fused_forward", &glb::sage_fused_forward);
+  m.def("symm_alloc", &glb::symm_alloc);
+  m.def("symm_free", &glb::symm_free);
+  m.def("ipc_get_handle", &glb::ipc_get_handle);
+  m.def("ipc_open_handle", &glb::ipc_open_handle);
+  m.def("ipc_close_handle", &glb::ipc_close_handle);
+  m.def("tensor_from_ptr", &glb::tensor_from_ptr);
+  m.def("allreduce_oneshot", &glb::allreduce_oneshot);
+  m.def("step_advance", &glb::step_advance);
+  m.def("adam_flat", &glb::adam_flat);
+  m.def("load_table", &glb::load_table);
+  m.def("save_embeddings", &glb::save_embeddings);
+}

@@ -1,0 +1,292 @@
+// Native host-side data loader: multi-threaded parser for the reference's
+// "name:type" tab-separated node / edge tables
+// (docs/en/gl/graph/data_loader.md:117-153; behaviour of
+// graphlearn/src/core/io/{edge_loader,node_loader,parser,slice_reader}.cc).
+//
+// Design: the file is read once into memory, cut into `threads` slices at line
+// boundaries (the reference slices per server x thread,
+// graphlearn/src/core/io/slice_reader.h:60-86), every slice is parsed by its
+// own thread straight into columnar vectors, and the columns are concatenated
+// into torch tensors ready for a pinned-host -> HBM copy.  Columnar output
+// (ids, weights, labels, timestamps, int/float attribute matrices, string
+// blob + offsets) replaces the reference's per-record AttributeValue objects.
+#include <torch/extension.h>
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace glb {
+
+namespace {
+
+struct Schema {
+  bool is_edge;
+  bool weighted, labeled, timestamped;
+  std::vector<int> attr_types;      // 0 = int, 1 = float, 2 = string
+  std::vector<int64_t> buckets;     // per attribute: >0 -> hash into buckets (becomes an int attr)
+  char attr_delim;
+  char field_delim;
+  int n_int = 0, n_float = 0, n_str = 0;
+};
+
+struct Columns {
+  std::vector<int64_t> a, b;        // id | (src, dst)
+  std::vector<float> w;
+  std::vector<int64_t> label, ts;
+  std::vector<int64_t> iattr;
+  std::vector<float> fattr;
+  std::vector<char> sblob;
+  std::vector<int64_t> soff;        // end offset of every string attr, relative to this slice
+  std::string error;
+};
+
+inline uint64_t fnv1a(const char* s, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)s[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+inline bool parse_i64(const char* s, const char* e, int64_t* out) {
+  if (s == e) return false;
+  bool neg = false;
+  if (*s == '-') { neg = true; ++s; } else if (*s == '+') { ++s; }
+  if (s == e) return false;
+  uint64_t v = 0;
+  for (; s < e; ++s) {
+    if (*s < '0' || *s > '9') {
+      if (*s == '\r' && s + 1 == e) break;
+      return false;
+    }
+    v = v * 10 + (uint64_t)(*s - '0');
+  }
+  *out = neg ? -(int64_t)v : (int64_t)v;
+  return true;
+}
+
+inline bool parse_f32(const char* s, const char* e, float* out) {
+  char buf[64];
+  size_t n = (size_t)(e - s);
+  if (n == 0 || n >= sizeof(buf)) return false;
+  std::memcpy(buf, s, n);
+  buf[n] = 0;
+  char* endp = nullptr;
+  errno = 0;
+  float v = std::strtof(buf, &endp);
+  if (endp == buf) return false;
+  while (*endp == '\r' || *endp == ' ') ++endp;
+  if (*endp != 0) return false;
+  *out = v;
+  return true;
+}
+
+// parse lines in [begin, end)
+void parse_slice(const char* begin, const char* end, const Schema& sc, Columns* out) {
+  const char* p = begin;
+  int64_t line_no = 0;
+  while (p < end) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!eol) eol = end;
+    const char* le = eol;
+    if (le > p && le[-1] == '\r') --le;
+    if (le > p) {
+      // split fields
+      const char* f = p;
+      int field = 0;
+      auto next = [&](const char** fs, const char** fe) -> bool {
+        if (f > le) return false;
+        const char* t = (const char*)memchr(f, sc.field_delim, (size_t)(le - f));
+        if (!t) t = le;
+        *fs = f; *fe = t;
+        f = t + 1;
+        ++field;
+        return true;
+      };
+      const char *fs, *fe;
+      bool ok = true;
+      int64_t v;
+      float fv;
+      if (!next(&fs, &fe) || !parse_i64(fs, fe, &v)) ok = false; else out->a.push_back(v);
+      if (ok && sc.is_edge) { if (!next(&fs, &fe) || !parse_i64(fs, fe, &v)) ok = false; else out->b.push_back(v); }
+      if (ok && sc.weighted) { if (!next(&fs, &fe) || !parse_f32(fs, fe, &fv)) ok = false; else out->w.push_back(fv); }
+      if (ok && sc.labeled) { if (!next(&fs, &fe) || !parse_i64(fs, fe, &v)) ok = false; else out->label.push_back(v); }
+      if (ok && sc.timestamped) { if (!next(&fs, &fe) || !parse_i64(fs, fe, &v)) ok = false; else out->ts.push_back(v); }
+      if (ok && !sc.attr_types.empty()) {
+        if (!next(&fs, &fe)) ok = false;
+        else {
+          // the attribute column runs to the end of the line (it may itself contain the field delimiter
+          // only if it differs from attr_delim; keep reference behaviour: one column)
+          const char* as = fs;
+          const char* ae = fe;
+          size_t na = sc.attr_types.size();
+          for (size_t i = 0; i < na && ok; ++i) {
+            const char* t = (i + 1 == na) ? ae : (const char*)memchr(as, sc.attr_delim, (size_t)(ae - as));
+            if (!t) { ok = false; break; }
+            int ty = sc.attr_types[i];
+            int64_t bucket = sc.buckets.empty() ? 0 : sc.buckets[i];
+            if (ty == 0) {
+              if (!parse_i64(as, t, &v)) { ok = false; break; }
+              out->iattr.push_back(v);   // int buckets are applied by the feature encoder, not the loader
+            } else if (ty == 1) {
+              if (!parse_f32(as, t, &fv)) { ok = false; break; }
+              out->fattr.push_back(fv);
+            } else {
+              if (bucket > 0) out->iattr.push_back((int64_t)(fnv1a(as, (size_t)(t - as)) % (uint64_t)bucket));
+              else { out->sblob.insert(out->sblob.end(), as, t); out->soff.push_back((int64_t)out->sblob.size()); }
+            }
+            as = t + 1;
+          }
+        }
+      }
+      if (!ok) {
+        if (out->error.empty())
+          out->error = "malformed record (slice line " + std::to_string(line_no) + "): " +
+                       std::string(p, std::min<size_t>((size_t)(le - p), 120));
+        return;
+      }
+    }
+    ++line_no;
+    p = eol + 1;
+  }
+}
+
+template <typename T>
+at::Tensor concat(const std::vector<Columns>& cols, std::vector<T> Columns::*field, at::ScalarType st) {
+  int64_t n = 0;
+  for (auto& c : cols) n += (int64_t)(c.*field).size();
+  auto t = at::empty({n}, at::TensorOptions().dtype(st));
+  T* dst = reinterpret_cast<T*>(t.data_ptr());
+  for (auto& c : cols) {
+    auto& v = c.*field;
+    if (!v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(T));
+    dst += v.size();
+  }
+  return t;
+}
+
+}  // namespace
+
+// returns [a, b, weights, labels, timestamps, int_attrs[n,i], float_attrs[n,f], str_blob(uint8), str_offsets(int64)]
+std::vector<at::Tensor> load_table(const std::string& path, bool is_edge, bool weighted, bool labeled,
+                                   bool timestamped, std::vector<int64_t> attr_types,
+                                   std::vector<int64_t> buckets, const std::string& attr_delim,
+                                   const std::string& field_delim, int64_t threads) {
+  Schema sc;
+  sc.is_edge = is_edge; sc.weighted = weighted; sc.labeled = labeled; sc.timestamped = timestamped;
+  for (auto t : attr_types) sc.attr_types.push_back((int)t);
+  sc.buckets = buckets;
+  TORCH_CHECK(buckets.empty() || buckets.size() == attr_types.size(), "bucket list must match attr_types");
+  sc.attr_delim = attr_delim.empty() ? ':' : attr_delim[0];
+  sc.field_delim = field_delim.empty() ? '\t' : field_delim[0];
+  for (size_t i = 0; i < sc.attr_types.size(); ++i) {
+    int64_t bk = sc.buckets.empty() ? 0 : sc.buckets[i];
+    if (sc.attr_types[i] == 0) sc.n_int++;
+    else if (sc.attr_types[i] == 1) sc.n_float++;
+    else if (bk > 0) sc.n_int++;
+    else sc.n_str++;
+  }
+
+  // slurp
+  FILE* fp = std::fopen(path.c_str(), "rb");
+  TORCH_CHECK(fp != nullptr, "cannot open data source: ", path);
+  std::fseek(fp, 0, SEEK_END);
+  long sz = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
+  std::vector<char> buf((size_t)sz);
+  size_t rd = sz > 0 ? std::fread(buf.data(), 1, (size_t)sz, fp) : 0;
+  std::fclose(fp);
+  TORCH_CHECK((long)rd == sz, "short read on ", path);
+  const char* begin = buf.data();
+  const char* end = begin + sz;
+
+  // header detection: "name:type<TAB>name:type..." (first field not numeric)
+  if (begin < end) {
+    const char* eol = (const char*)memchr(begin, '\n', (size_t)(end - begin));
+    if (!eol) eol = end;
+    const char* t = (const char*)memchr(begin, sc.field_delim, (size_t)(eol - begin));
+    if (!t) t = eol;
+    int64_t dummy;
+    const char* fe = t;
+    if (fe > begin && fe[-1] == '\r') --fe;
+    if (!parse_i64(begin, fe, &dummy)) begin = (eol < end) ? eol + 1 : end;
+  }
+
+  int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads, 64));
+  if ((end - begin) < (1 << 16)) nt = 1;
+  std::vector<const char*> cuts(nt + 1);
+  cuts[0] = begin; cuts[nt] = end;
+  for (int i = 1; i < nt; ++i) {
+    const char* c = begin + (size_t)((end - begin) / nt) * i;
+    if (c < cuts[i - 1]) c = cuts[i - 1];
+    const char* nl = (const char*)memchr(c, '\n', (size_t)(end - c));
+    cuts[i] = nl ? nl + 1 : end;
+  }
+  std::vector<Columns> cols(nt);
+  std::vector<std::thread> pool;
+  for (int i = 0; i < nt; ++i)
+    pool.emplace_back([&, i] { parse_slice(cuts[i], cuts[i + 1], sc, &cols[i]); });
+  for (auto& th : pool) th.join();
+  for (auto& c : cols) TORCH_CHECK(c.error.empty(), path, ": ", c.error);
+
+  auto a = concat<int64_t>(cols, &Columns::a, at::kLong);
+  auto b = concat<int64_t>(cols, &Columns::b, at::kLong);
+  auto w = concat<float>(cols, &Columns::w, at::kFloat);
+  auto lb = concat<int64_t>(cols, &Columns::label, at::kLong);
+  auto ts = concat<int64_t>(cols, &Columns::ts, at::kLong);
+  auto ia = concat<int64_t>(cols, &Columns::iattr, at::kLong);
+  auto fa = concat<float>(cols, &Columns::fattr, at::kFloat);
+  int64_t n = a.numel();
+  if (sc.n_int > 0) ia = ia.view({n, sc.n_int});
+  if (sc.n_float > 0) fa = fa.view({n, sc.n_float});
+  // strings: rebase per-slice offsets
+  int64_t nblob = 0, noff = 0;
+  for (auto& c : cols) { nblob += (int64_t)c.sblob.size(); noff += (int64_t)c.soff.size(); }
+  auto blob = at::empty({nblob}, at::TensorOptions().dtype(at::kByte));
+  auto off = at::zeros({noff + 1}, at::TensorOptions().dtype(at::kLong));
+  {
+    char* bd = reinterpret_cast<char*>(blob.data_ptr());
+    int64_t* od = off.data_ptr<int64_t>() + 1;
+    int64_t base = 0;
+    for (auto& c : cols) {
+      if (!c.sblob.empty()) std::memcpy(bd + base, c.sblob.data(), c.sblob.size());
+      for (auto o : c.soff) *od++ = base + o;
+      base += (int64_t)c.sblob.size();
+    }
+  }
+  return {a, b, w, lb, ts, ia, fa, blob, off};
+}
+
+// Embedding / result dump in the reference's "id:int64\temb:string" dialect
+// (graphlearn/examples/tf/trainer.py:214-279) so results can be re-ingested as a node table.
+void save_embeddings(const std::string& path, const at::Tensor& ids, const at::Tensor& emb, bool header) {
+  auto idc = ids.to(at::kCPU).to(at::kLong).contiguous();
+  auto ec = emb.to(at::kCPU).to(at::kFloat).contiguous();
+  TORCH_CHECK(ec.dim() == 2 && ec.size(0) == idc.numel(), "emb must be [n, d]");
+  FILE* fp = std::fopen(path.c_str(), "wb");
+  TORCH_CHECK(fp != nullptr, "cannot open for write: ", path);
+  if (header) std::fputs("id:int64\temb:string\n", fp);
+  const int64_t* ip = idc.data_ptr<int64_t>();
+  const float* ep = ec.data_ptr<float>();
+  int64_t n = idc.numel(), d = ec.size(1);
+  std::string line;
+  char tmp[64];
+  for (int64_t i = 0; i < n; ++i) {
+    line.clear();
+    std::snprintf(tmp, sizeof(tmp), "%lld\t", (long long)ip[i]);
+    line += tmp;
+    for (int64_t j = 0; j < d; ++j) {
+      std::snprintf(tmp, sizeof(tmp), j + 1 == d ? "%.6g" : "%.6g,", ep[i * d + j]);
+      line += tmp;
+    }
+    line += '\n';
+    std::fwrite(line.data(), 1, line.size(), fp);
+  }
+  std::fclose(fp);
+}
+
+}  // namespace glb
