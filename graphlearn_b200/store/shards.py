@@ -1,0 +1,269 @@
+"""Per-GPU graph shards: node tables and CSR adjacency in HBM.
+
+B200-native replacement for the reference's GraphStore / Graph / Noder and the
+memory storages (graphlearn/src/core/graph/graph_store.cc:185-333,
+storage/memory_adj_matrix.cc:159-225, memory_node_storage.cc:64-138):
+
+* a node type is hash partitioned by ``|id| % world`` (hash_partitioner.h:90-92);
+  local rows are addressed by *virtual ids* ``vid = row * world + owner`` so
+  that any rank can compute (owner, row) arithmetically.  For a dense id space
+  0..N-1 the vid is the id itself (row = id // world).
+* float attributes live in ONE symmetric [n_local, stride] table (fp32 or bf16)
+  that every peer maps over NVLink; labels / weights / int attrs are local
+  device tensors (also published symmetrically for remote lookups).
+* an edge type is a CSR over the source rows, stored on the source's owner:
+  ``indptr`` int64, ``indices`` = destination vids, optional in-row inclusive
+  prefix sums of the sampling weights (weighted sampling without per-call alias
+  builds) and optional timestamps (rows sorted ascending for
+  temporal graphs, otherwise by weight descending so that top-k is a prefix -
+  memory_adj_matrix.cc:60-66,105-149).  The edge id is the CSR position on the
+  owner, so no separate eid array is needed.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from ..parallel import partition as part
+from ..parallel.runtime import Runtime, SymmTensor, make_csr_desc, make_table_desc
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class IdMap:
+    """global id <-> vid for one node type."""
+
+    def __init__(self, rt: Runtime, local_ids: torch.Tensor, dense: bool):
+        self.rt = rt
+        self.dense = dense
+        self.local_ids = local_ids              # sorted ascending (general) / implicit (dense)
+        self.n_local = int(local_ids.numel())
+        self.nrows = rt.all_gather_object(self.n_local)
+
+    @staticmethod
+    def build(rt: Runtime, local_ids: torch.Tensor) -> "IdMap":
+        """`local_ids`: unique ids owned by this rank (any order)."""
+        local_ids = torch.unique(local_ids)     # sorted
+        n = int(local_ids.numel())
+        W = rt.world
+        # dense iff the owned ids are exactly {rank, rank+W, rank+2W, ...}
+        dense_local = bool(n == 0 or (int(local_ids[0]) == rt.rank and int(local_ids[-1]) == rt.rank + (n - 1) * W)) \
+            and bool(n == 0 or torch.equal(local_ids, torch.arange(n, device=local_ids.device) * W + rt.rank))
+        dense = all(rt.all_gather_object(dense_local))
+        return IdMap(rt, local_ids, dense)
+
+    def _local_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """rows of ids owned by THIS rank; -1 when unknown."""
+        W = self.rt.world
+        if self.dense:
+            rows = torch.div(ids, W, rounding_mode="floor")
+            ok = (ids >= 0) & (rows < self.n_local) & (ids % W == self.rt.rank)
+            return torch.where(ok, rows, torch.full_like(rows, -1))
+        if self.n_local == 0:
+            return torch.full_like(ids, -1)
+        pos = torch.searchsorted(self.local_ids, ids).clamp_(max=self.n_local - 1)
+        ok = self.local_ids[pos] == ids
+        return torch.where(ok, pos, torch.full_like(pos, -1))
+
+    def to_vid(self, ids: torch.Tensor) -> torch.Tensor:
+        """Collective when world > 1 and the id space is not dense."""
+        W = self.rt.world
+        ids = ids.to(torch.int64)
+        if self.dense:
+            rows = torch.div(ids, W, rounding_mode="floor")
+            nrows = torch.tensor(self.nrows, device=ids.device, dtype=torch.int64)
+            ok = (ids >= 0) & (rows < nrows[(ids.abs() % W)])
+            return torch.where(ok, ids, torch.full_like(ids, -1))
+        if W == 1:
+            return self._local_rows(ids)        # vid == row
+        flat = ids.reshape(-1)
+        (rows,) = part.remote_apply(flat, lambda x: (self._local_rows(x),), W)
+        vid = torch.where(rows >= 0, rows * W + part.owner_of(flat, W), torch.full_like(rows, -1))
+        return vid.reshape(ids.shape)
+
+    def local_vids(self) -> torch.Tensor:
+        W = self.rt.world
+        return torch.arange(self.n_local, device=self.local_ids.device, dtype=torch.int64) * W + self.rt.rank
+
+    def to_id(self, vids: torch.Tensor) -> torch.Tensor:
+        """vid -> original id (collective when not dense and world > 1)."""
+        if self.dense:
+            return vids
+        W = self.rt.world
+        flat = vids.reshape(-1)
+
+        def look(v):
+            rows = torch.div(v, W, rounding_mode="floor").clamp_(min=0, max=max(self.n_local - 1, 0))
+            out = self.local_ids[rows] if self.n_local > 0 else torch.full_like(v, -1)
+            return (torch.where(v >= 0, out, torch.full_like(out, -1)),)
+
+        if W == 1:
+            return look(flat)[0].reshape(vids.shape)
+        # route by owner = vid % W (vids are non-negative when valid)
+        (ids,) = part.remote_apply(flat.clamp(min=0), look, W)
+        return torch.where(flat >= 0, ids, torch.full_like(ids, -1)).reshape(vids.shape)
+
+
+class NodeTable:
+    def __init__(self, rt: Runtime, ntype: str, idmap: IdMap):
+        self.rt = rt
+        self.type = ntype
+        self.idmap = idmap
+        self.n_local = idmap.n_local
+        self.float_dim = 0
+        self.int_dim = 0
+        self.str_dim = 0
+        self.feats: Optional[SymmTensor] = None      # [n_local, stride]
+        self.feat_desc: Optional[torch.Tensor] = None
+        self.ints: Optional[SymmTensor] = None       # int64 [n_local, int_dim]
+        self.labels: Optional[SymmTensor] = None     # int64 [n_local]
+        self.weights: Optional[SymmTensor] = None    # float [n_local]
+        self.timestamps: Optional[SymmTensor] = None
+        self.strings: Optional[List[List[str]]] = None   # host side, [n_local][str_dim]
+        self.out_degrees: Dict[str, torch.Tensor] = {}
+        self.in_degrees: Dict[str, torch.Tensor] = {}
+        self.present: Optional[torch.Tensor] = None  # bool [n_local]: row came from a node source
+
+    @property
+    def nrows(self):
+        return self.idmap.nrows
+
+    def set_float(self, x: torch.Tensor, dtype: torch.dtype = torch.float32):
+        """x: [n_local, d] on the runtime device."""
+        d = int(x.size(1))
+        self.float_dim = d
+        stride = _round_up(max(d, 1), 4 if dtype == torch.float32 else 8)
+        st = self.rt.symm_empty((self.n_local, stride), dtype)
+        st.local.zero_()
+        st.local[:, :d] = x.to(dtype)
+        self.feats = st
+        self.rt.barrier()
+        self.feat_desc = make_table_desc(self.rt.world, d, stride, dtype, st.nrows, st.ptrs)
+
+    def _set_symm(self, name, x: torch.Tensor):
+        st = self.rt.symm_empty(tuple(x.shape), x.dtype)
+        st.local.copy_(x)
+        setattr(self, name, st)
+        self.rt.barrier()
+
+    def set_labels(self, x):
+        self._set_symm("labels", x.to(torch.int64))
+
+    def set_weights(self, x):
+        self._set_symm("weights", x.to(torch.float32))
+
+    def set_timestamps(self, x):
+        self._set_symm("timestamps", x.to(torch.int64))
+
+    def set_ints(self, x):
+        self.int_dim = int(x.size(1))
+        self._set_symm("ints", x.to(torch.int64))
+
+
+class CsrShard:
+    """CSR adjacency of one edge type on this rank (+ peer pointer tables)."""
+
+    def __init__(self, rt: Runtime, etype: str, src_type: str, dst_type: str):
+        self.rt = rt
+        self.type = etype
+        self.src_type = src_type
+        self.dst_type = dst_type
+        self.indptr: Optional[SymmTensor] = None
+        self.indices: Optional[SymmTensor] = None
+        self.cumw: Optional[SymmTensor] = None          # edge-weight prefix sums
+        self.cumw_indeg: Optional[SymmTensor] = None    # in-degree prefix sums
+        self.ts: Optional[SymmTensor] = None
+        self.weights: Optional[SymmTensor] = None       # float [E_local]
+        self.labels: Optional[SymmTensor] = None
+        self.float_attrs: Optional[SymmTensor] = None
+        self.int_attrs: Optional[SymmTensor] = None
+        self.float_dim = 0
+        self.int_dim = 0
+        self.n_src_rows = 0
+        self.n_edges = 0
+        self.desc: Optional[torch.Tensor] = None
+        self.desc_indeg: Optional[torch.Tensor] = None
+        self.directed = True
+        self.timestamped = False
+        self.dst_ids_unique: Optional[torch.Tensor] = None   # distinct dst vids on this shard (neg sampling)
+
+    @staticmethod
+    def from_coo(rt: Runtime, etype, src_type, dst_type, src_rows: torch.Tensor, dst_vids: torch.Tensor,
+                 n_src_rows: int, weights: Optional[torch.Tensor] = None, ts: Optional[torch.Tensor] = None,
+                 labels: Optional[torch.Tensor] = None, float_attrs: Optional[torch.Tensor] = None,
+                 int_attrs: Optional[torch.Tensor] = None) -> "CsrShard":
+        """K11: build the CSR on the device.  Rows are ordered by timestamp
+        ascending when `ts` is given, else by weight descending (top-k prefix)."""
+        self = CsrShard(rt, etype, src_type, dst_type)
+        E = int(src_rows.numel())
+        dev = src_rows.device
+        order = torch.arange(E, device=dev)
+        if E > 0:
+            if ts is not None:
+                order = torch.argsort(ts, stable=True)
+            elif weights is not None:
+                order = torch.argsort(weights, descending=True, stable=True)
+            order = order[torch.argsort(src_rows[order], stable=True)]
+        srt = src_rows[order]
+        counts = torch.bincount(srt, minlength=n_src_rows) if E > 0 else torch.zeros(n_src_rows, dtype=torch.int64, device=dev)
+        indptr = torch.zeros(n_src_rows + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(counts, 0)
+        self.n_src_rows = n_src_rows
+        self.n_edges = E
+        self.indptr = rt.symm_from(indptr)
+        self.indices = rt.symm_from(dst_vids[order].to(torch.int64))
+        self._order = order
+        self._row_of_edge = srt
+        if weights is not None:
+            w = weights[order].to(torch.float32)
+            self.weights = rt.symm_from(w)
+            self.cumw = rt.symm_from(self._row_cumsum(w, indptr, srt))
+        if ts is not None:
+            self.ts = rt.symm_from(ts[order].to(torch.int64))
+            self.timestamped = True
+        if labels is not None:
+            self.labels = rt.symm_from(labels[order].to(torch.int64))
+        if float_attrs is not None and float_attrs.numel() > 0:
+            self.float_dim = int(float_attrs.size(1))
+            self.float_attrs = rt.symm_from(float_attrs[order].to(torch.float32))
+        if int_attrs is not None and int_attrs.numel() > 0:
+            self.int_dim = int(int_attrs.size(1))
+            self.int_attrs = rt.symm_from(int_attrs[order].to(torch.int64))
+        self.dst_ids_unique = torch.unique(self.indices.local) if E > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
+        self._make_desc()
+        return self
+
+    @staticmethod
+    def _row_cumsum(w: torch.Tensor, indptr: torch.Tensor, row_of_edge: torch.Tensor) -> torch.Tensor:
+        if w.numel() == 0:
+            return w.clone()
+        c = torch.cumsum(w.to(torch.float64), 0)
+        base = torch.zeros(indptr.numel() - 1, dtype=torch.float64, device=w.device)
+        starts = indptr[:-1]
+        nz = starts < w.numel()
+        base[nz] = c[starts[nz]] - w[starts[nz]].to(torch.float64)
+        return (c - base[row_of_edge]).to(torch.float32)
+
+    def set_indegree_weights(self, indeg_of_dst: torch.Tensor):
+        """per-edge weight = in-degree of the destination (InDegreeSampler)."""
+        w = indeg_of_dst.to(torch.float32).clamp_(min=0)
+        self.cumw_indeg = self.rt.symm_from(self._row_cumsum(w, self.indptr.local, self._row_of_edge))
+        self._make_desc()
+
+    def _make_desc(self):
+        W = self.rt.world
+        self.desc = make_csr_desc(
+            W, self.indptr.nrows and [n - 1 for n in self.indptr.nrows], self.indptr.ptrs, self.indices.ptrs,
+            None, self.cumw.ptrs if self.cumw is not None else None,
+            self.ts.ptrs if self.ts is not None else None)
+        if self.cumw_indeg is not None:
+            self.desc_indeg = make_csr_desc(
+                W, [n - 1 for n in self.indptr.nrows], self.indptr.ptrs, self.indices.ptrs, None,
+                self.cumw_indeg.ptrs, self.ts.ptrs if self.ts is not None else None)
+
+    @property
+    def peer_ok(self) -> bool:
+        return self.rt.is_cuda
