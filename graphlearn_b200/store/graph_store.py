@@ -1,0 +1,283 @@
+"""GraphStore: load -> partition -> build the per-GPU shards of a heterogeneous graph.
+
+B200-native counterpart of GraphStore::{Load,Build,BuildStatistics}
+(graphlearn/src/core/graph/graph_store.cc:185-333) and of the server Init
+sequence (graphlearn/src/service/server_impl.cc:163-195):
+
+  load     native multi-threaded TSV parser (csrc/host_loader.cpp) or in-memory
+           arrays -> columnar tensors
+  shuffle  rows are assigned to owner = |id| % world (edges by SRC id, nodes by
+           node id - graph_update_request.cc:151-156,234-237).  Every rank
+           parses the source and keeps what it owns (no RPC shuffle needed on a
+           single box where all ranks see the same files).
+  build    id maps (id <-> virtual id), node tables and CSR shards in HBM, peer
+           pointer tables exchanged through CUDA IPC.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import config as _config
+from ..data.decoder import Decoder
+from ..parallel.runtime import Runtime, native
+from .shards import CsrShard, IdMap, NodeTable
+
+ORIGIN, REVERSED = 0, 1
+
+
+class Topology(object):
+    """edge type -> (src type, dst type)  (graphlearn/python/data/topology.py)."""
+
+    def __init__(self):
+        self._edges: Dict[str, Tuple[str, str]] = {}
+
+    def add(self, edge_type, src_type, dst_type):
+        self._edges[edge_type] = (src_type, dst_type)
+
+    def get_src_type(self, edge_type):
+        return self._edges[edge_type][0]
+
+    def get_dst_type(self, edge_type):
+        return self._edges[edge_type][1]
+
+    def is_exist(self, edge_type):
+        return edge_type in self._edges
+
+    def edge_types(self):
+        return list(self._edges)
+
+    def __str__(self):
+        return "\n".join("%s: %s -> %s" % (e, s, d) for e, (s, d) in self._edges.items())
+
+
+class Source(object):
+    def __init__(self, kind, path, types, decoder, direction=ORIGIN, option=None, data=None):
+        self.kind = kind              # 'node' | 'edge'
+        self.path = path
+        self.types = types            # node type | (src_type, dst_type, edge_type)
+        self.decoder = decoder
+        self.direction = direction
+        self.option = option
+        self.data = data              # optional in-memory dict of arrays
+
+
+def _expand_paths(path: str) -> List[str]:
+    out = []
+    for p in [x.strip() for x in path.split(",") if x.strip()]:
+        if p.startswith("file://"):
+            p = p[len("file://"):]
+        if os.path.isdir(p):
+            out.extend(sorted(os.path.join(p, f) for f in os.listdir(p) if not f.startswith(".")))
+        else:
+            out.append(p)
+    return out
+
+
+def _load_source(src: Source) -> Dict[str, object]:
+    """-> dict(a, b, w, label, ts, ia, fa, strs) of CPU tensors."""
+    dec: Decoder = src.decoder
+    if src.data is not None:
+        d = src.data
+        g = lambda k: (None if d.get(k) is None else torch.as_tensor(np.asarray(d[k]) if not isinstance(d[k], torch.Tensor) else d[k]))  # noqa: E731
+        a = g("ids") if src.kind == "node" else g("src_ids")
+        out = {"a": a.to(torch.int64), "b": None if src.kind == "node" else g("dst_ids").to(torch.int64),
+               "w": g("weights"), "label": g("labels"), "ts": g("timestamps"), "ia": g("int_attrs"),
+               "fa": g("float_attrs"), "strs": d.get("string_attrs")}
+        return out
+    C = native()
+    cfg = _config.get()
+    codes, buckets = dec.loader_schema()
+    parts = []
+    for p in _expand_paths(src.path):
+        parts.append(C.load_table(p, src.kind == "edge", dec.weighted, dec.labeled, dec.timestamped, codes, buckets,
+                                  dec.attr_delimiter, cfg.field_delimiter, int(cfg.loader_threads)))
+    if not parts:
+        raise FileNotFoundError("no data files for source %r" % (src.path,))
+    cat = [torch.cat([p[i] for p in parts]) if i < 7 else None for i in range(7)]
+    strs = None
+    if dec.string_attr_num > 0:
+        rows = []
+        for p in parts:
+            blob = p[7].numpy().tobytes()
+            off = p[8].tolist()
+            vals = [blob[off[i]:off[i + 1]].decode("utf-8", "replace") for i in range(len(off) - 1)]
+            rows.extend(vals)
+        strs = np.array(rows, dtype=object).reshape(-1, dec.string_attr_num)
+    n = cat[0].numel()
+    return {"a": cat[0], "b": cat[1] if src.kind == "edge" else None,
+            "w": cat[2] if dec.weighted else None, "label": cat[3] if dec.labeled else None,
+            "ts": cat[4] if dec.timestamped else None,
+            "ia": cat[5].view(n, -1) if dec.int_attr_num > 0 else None,
+            "fa": cat[6].view(n, -1) if dec.float_attr_num > 0 else None, "strs": strs}
+
+
+def _take(d: Dict[str, object], idx: torch.Tensor) -> Dict[str, object]:
+    out = {}
+    for k, v in d.items():
+        if v is None:
+            out[k] = None
+        elif isinstance(v, torch.Tensor):
+            out[k] = v[idx]
+        else:
+            out[k] = v[idx.numpy()]
+    return out
+
+
+class GraphStore(object):
+    def __init__(self, rt: Runtime):
+        self.rt = rt
+        self.topology = Topology()
+        self.node_decoders: Dict[str, Decoder] = {}
+        self.edge_decoders: Dict[str, Decoder] = {}
+        self.nodes: Dict[str, NodeTable] = {}
+        self.edges: Dict[str, CsrShard] = {}
+        self.reverse: Dict[str, CsrShard] = {}      # in-edge CSR (built lazily for inV / in-degree)
+        self._edge_cache: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.stats: Dict[str, List[int]] = {}
+
+    # ------------------------------------------------------------------ build
+    def build(self, node_sources: List[Source], edge_sources: List[Source]):
+        rt, W, r = self.rt, self.rt.world, self.rt.rank
+        dev = rt.device
+        cfg = _config.get()
+        fdt = torch.bfloat16 if cfg.feature_dtype == "bf16" else torch.float32
+        # ---- load + keep what this rank owns
+        nd: Dict[str, List[Dict]] = {}
+        for s in node_sources:
+            d = _load_source(s)
+            keep = (d["a"].abs() % W == r).nonzero().flatten()
+            nd.setdefault(s.types, []).append(_take(d, keep))
+        ed: Dict[str, List[Dict]] = {}
+        ends: Dict[str, List[torch.Tensor]] = {}   # node type -> owned endpoint ids seen in edges
+        for s in edge_sources:
+            d = _load_source(s)
+            st, dt, et = s.types
+            if s.direction == REVERSED:
+                d["a"], d["b"] = d["b"], d["a"]
+            own_dst = d["b"][d["b"].abs() % W == r]
+            ends.setdefault(dt, []).append(own_dst)
+            keep = (d["a"].abs() % W == r).nonzero().flatten()
+            dk = _take(d, keep)
+            ends.setdefault(st, []).append(dk["a"])
+            ed.setdefault(et, []).append(dk)
+            self.topology.add(et, st, dt)
+        # ---- node tables
+        types = sorted(set(list(nd.keys()) + list(ends.keys())))
+        types = rt.all_gather_object(types)[0] if W > 1 else types
+        for t in types:
+            parts = nd.get(t, [])
+            ids_src = torch.cat([p["a"] for p in parts]) if parts else torch.zeros(0, dtype=torch.int64)
+            ids_all = torch.cat([ids_src] + ends.get(t, [])) if (parts or t in ends) else ids_src
+            idmap = IdMap.build(rt, ids_all.to(dev))
+            tab = NodeTable(rt, t, idmap)
+            n = idmap.n_local
+            dec = self.node_decoders.get(t, Decoder())
+            rows = idmap._local_rows(ids_src.to(dev)) if ids_src.numel() else torch.zeros(0, dtype=torch.int64, device=dev)
+            present = torch.zeros(n, dtype=torch.bool, device=dev)
+            present[rows] = True
+            tab.present = present
+            merged = {k: (torch.cat([p[k] for p in parts]) if parts and parts[0][k] is not None and k != "strs" else None)
+                      for k in ("w", "label", "ts", "ia", "fa")}
+            if dec.float_attr_num > 0:
+                x = torch.full((n, dec.float_attr_num), float(cfg.default_float_attribute), device=dev)
+                if merged["fa"] is not None:
+                    x[rows] = merged["fa"].to(dev).float()
+                tab.set_float(x, fdt)
+            if dec.int_attr_num > 0:
+                x = torch.full((n, dec.int_attr_num), int(cfg.default_int_attribute), dtype=torch.int64, device=dev)
+                if merged["ia"] is not None:
+                    x[rows] = merged["ia"].to(dev)
+                tab.set_ints(x)
+            if dec.labeled:
+                x = torch.full((n,), int(cfg.default_label), dtype=torch.int64, device=dev)
+                if merged["label"] is not None:
+                    x[rows] = merged["label"].to(dev)
+                tab.set_labels(x)
+            if dec.weighted:
+                x = torch.full((n,), float(cfg.default_weight), device=dev)
+                if merged["w"] is not None:
+                    x[rows] = merged["w"].to(dev).float()
+                tab.set_weights(x)
+            if dec.timestamped:
+                x = torch.full((n,), int(cfg.default_timestamp), dtype=torch.int64, device=dev)
+                if merged["ts"] is not None:
+                    x[rows] = merged["ts"].to(dev)
+                tab.set_timestamps(x)
+            if dec.string_attr_num > 0:
+                tab.str_dim = dec.string_attr_num
+                arr = np.full((n, dec.string_attr_num), cfg.default_string_attribute, dtype=object)
+                if parts and parts[0]["strs"] is not None:
+                    arr[rows.cpu().numpy()] = np.concatenate([p["strs"] for p in parts])
+                tab.strings = arr
+            self.nodes[t] = tab
+        # ---- edge shards
+        for et in self.topology.edge_types():
+            st, dt = self.topology.get_src_type(et), self.topology.get_dst_type(et)
+            parts = ed.get(et, [])
+            cat = lambda k: (torch.cat([p[k] for p in parts]).to(dev) if parts and parts[0][k] is not None else None)  # noqa: E731
+            src = cat("a") if parts else torch.zeros(0, dtype=torch.int64, device=dev)
+            dst = cat("b") if parts else torch.zeros(0, dtype=torch.int64, device=dev)
+            src_tab, dst_tab = self.nodes[st], self.nodes[dt]
+            src_rows = src_tab.idmap._local_rows(src)
+            dst_vids = dst_tab.idmap.to_vid(dst)
+            csr = CsrShard.from_coo(rt, et, st, dt, src_rows, dst_vids, src_tab.n_local, weights=cat("w"),
+                                    ts=cat("ts"), labels=cat("label"), float_attrs=cat("fa"), int_attrs=cat("ia"))
+            strs = [p["strs"] for p in parts if p["strs"] is not None]
+            csr.strings = np.concatenate(strs)[csr._order.cpu().numpy()] if strs else None
+            self.edges[et] = csr
+            ip = csr.indptr.local
+            src_tab.out_degrees[et] = ip[1:] - ip[:-1]
+        # ---- statistics (GetCount / GetStats, graph_store.cc:278-317)
+        for t, tab in self.nodes.items():
+            self.stats[t] = rt.all_gather_object(int(tab.present.sum().item()) if tab.present is not None else tab.n_local)
+        for et, csr in self.edges.items():
+            self.stats[et] = rt.all_gather_object(csr.n_edges)
+        rt.barrier()
+
+    # ------------------------------------------------------------------ in-edges (lazy; collective)
+    def reverse_csr(self, etype: str) -> CsrShard:
+        """CSR of the in-edges of `etype`, partitioned by DESTINATION owner (for inV / in-degrees)."""
+        if etype in self.reverse:
+            return self.reverse[etype]
+        from ..parallel import partition as part
+        rt, W = self.rt, self.rt.world
+        csr = self.edges[etype]
+        st, dt = csr.src_type, csr.dst_type
+        src_vids = csr._row_of_edge * W + rt.rank
+        dst_vids = csr.indices.local
+        w = csr.weights.local if csr.weights is not None else None
+        if W > 1:
+            ok = dst_vids >= 0
+            sorted_dst, order, counts = part.partition_by_owner(dst_vids[ok], W)
+            sc = [int(x) for x in counts.tolist()]
+            rc = part.exchange_counts(counts)
+            dst_vids = part._all_to_all_v(sorted_dst, sc, rc)
+            src_vids = part._all_to_all_v(src_vids[ok][order], sc, rc)
+            if w is not None:
+                w = part._all_to_all_v(w[ok][order], sc, rc)
+        else:
+            ok = dst_vids >= 0
+            dst_vids, src_vids = dst_vids[ok], src_vids[ok]
+            w = w[ok] if w is not None else None
+        rows = torch.div(dst_vids, W, rounding_mode="floor")
+        rev = CsrShard.from_coo(rt, etype + "#in", dt, st, rows, src_vids, self.nodes[dt].n_local, weights=w)
+        self.reverse[etype] = rev
+        ip = rev.indptr.local
+        self.nodes[dt].in_degrees[etype] = ip[1:] - ip[:-1]
+        return rev
+
+    def ensure_indegree_weights(self, etype: str):
+        """Per-edge weight = in-degree(dst) for InDegreeSampler (collective)."""
+        from ..ops import gather as G
+        csr = self.edges[etype]
+        if csr.cumw_indeg is not None:
+            return
+        self.reverse_csr(etype)
+        dt = self.nodes[csr.dst_type]
+        indeg = self.rt.symm_from(dt.in_degrees[etype].to(torch.int64))
+        vals = G.gather_any(self.rt, indeg, csr.indices.local, fill=0)
+        csr.set_indegree_weights(vals)

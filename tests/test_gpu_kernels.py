@@ -189,7 +189,7 @@ def test_gather_bf16_table(rt):
     dict(M=1024, k=25, ds=100, dn=100, n_out=256, mode="mean", relu=True, bf16=True),
     dict(M=129, k=5, ds=64, dn=32, n_out=47, mode="sum", relu=False, bf16=False),
     dict(M=256, k=7, ds=100, dn=100, n_out=64, mode="gcn", relu=False, bf16=False),
-    dict(M=500, k=3, ds=200, dn=200, n_out=128, mode="mean", relu=True, bf16=False),
+    dict(M=500, k=3, ds=200, dn=200, n_out=64, mode="mean", relu=True, bf16=False),
 ])
 def test_sage_fused_store_numerics(rt, cfg):
     """tcgen05 fused layer reading a (fp32) store vs fp32 torch reference."""
