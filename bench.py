@@ -100,6 +100,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from graphlearn_b200.engine.fast_sage import FastSageTrainer
     from graphlearn_b200.engine.trainer import SageTrainer
     from graphlearn_b200.models.graphsage import EgoGraphSAGE
     from graphlearn_b200.parallel.runtime import init
@@ -118,8 +119,9 @@ def run_ours(args):
     build_s = time.time() - t0
     torch.manual_seed(0)
     model = EgoGraphSAGE(shape["feat_dim"], HIDDEN, shape["num_classes"], 2).to(rt.device)
-    tr = SageTrainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
-                     use_cuda_graph=not args.no_graph)
+    Trainer = SageTrainer if args.engine == "autograd" else FastSageTrainer
+    tr = Trainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
+                 use_cuda_graph=not args.no_graph)
     # host-side seed stream: each rank traverses (shuffled) its own nodes, like the reference's
     # V().batch().shuffle(traverse=True) root which is unsharded (node_getter.cc:64-92)
     gen = torch.Generator().manual_seed(1234 + rt.rank)
@@ -182,7 +184,7 @@ def run_ours(args):
                        "feat_dim": shape["feat_dim"], "feature_storage": args.feature_dtype,
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
                                     % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * (2 if fdt == torch.bfloat16 else 4) / 1e9),
-                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None,
+                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine,
                        "graph_build_s": round(build_s, 2)},
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": args.batch * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -213,6 +215,8 @@ def main():
     ap.add_argument("--feature-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--engine", default="fast", choices=["fast", "autograd"],
+                    help="fast = hand-scheduled fwd/bwd kernel chain; autograd = torch.autograd over the same kernels")
     ap.add_argument("--small", action="store_true", help="small graph for quick functional runs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

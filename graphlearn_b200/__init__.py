@@ -1,0 +1,46 @@
+"""graphlearn_b200 - a B200-native distributed GNN training engine with the
+capabilities and user API of alibaba/graph-learn (``import graphlearn_b200 as gl``).
+
+Public surface mirrors graphlearn/__init__.py:16-40: ``gl.Graph``, ``gl.Dataset``,
+``gl.Decoder``, ``gl.Mask``, ``gl.NODE / EDGE_SRC / EDGE_DST``, padding modes,
+``gl.KnnOption``, errors and every ``gl.set_*`` flag; ``gl.nn`` holds the
+PyTorch model layer.
+"""
+from __future__ import annotations
+
+from . import config as _config
+from .config import *  # noqa: F401,F403  (all set_* functions + constants)
+from .config import CIRCULAR, REPLICATE, enable_actor  # noqa: F401
+from .data.decoder import Decoder  # noqa: F401
+from .data.feature_spec import FeatureSpec  # noqa: F401
+from .data.values import Edges, Layer, Layers, Nodes, SparseEdges, SparseNodes, SubGraph, Values  # noqa: F401
+from .errors import *  # noqa: F401,F403
+from .errors import OutOfRangeError  # noqa: F401
+from .graph import EDGE_DST, EDGE_SRC, NODE, Graph  # noqa: F401
+from .gsl.dataset import Dataset  # noqa: F401
+from .ops.knn import KnnOption  # noqa: F401
+from .store.graph_store import Topology  # noqa: F401
+from .utils import Mask, get_mask_type, strategy2op  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+class IndexOption(object):
+    """KNN index options of the reference (graphlearn/python/c/py_export.cc); only the flat
+    (brute-force tensor-core) index exists here, the fields are kept for script parity."""
+
+    def __init__(self):
+        self.name = "knn"
+        self.index_type = "flat"
+        self.nlist = 0
+        self.nprobe = 0
+        self.m = 0
+
+
+def get_cluster(*args, **kwargs):
+    from .cluster import get_cluster as _gc
+    return _gc(*args, **kwargs)
+
+
+def get_config():
+    return _config.get()

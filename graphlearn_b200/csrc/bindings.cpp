@@ -9,6 +9,9 @@ std::vector<at::Tensor> sample_neighbors(const at::Tensor&, const at::Tensor&, i
 at::Tensor get_degrees(const at::Tensor&, const at::Tensor&, int64_t);
 std::vector<at::Tensor> sample_full(const at::Tensor&, const at::Tensor&, int64_t, bool);
 void rng_advance(const at::Tensor&, int64_t);
+// walk.cu
+at::Tensor random_walk(const at::Tensor&, const at::Tensor&, int64_t, double, double, int64_t, int64_t,
+                       const at::Tensor&, int64_t);
 // gather.cu
 at::Tensor gather_rows(const at::Tensor&, const at::Tensor&, bool, double);
 at::Tensor gather_agg(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t);
@@ -20,7 +23,14 @@ at::Tensor pack_weight_sw128(const at::Tensor&, int64_t);
 std::vector<at::Tensor> sage_fused_forward(const at::Tensor&, const c10::optional<at::Tensor>&, const at::Tensor&,
                                            const c10::optional<at::Tensor>&, int64_t, int64_t, int64_t,
                                            const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t,
-                                           bool, bool, bool);
+                                           bool, bool, bool, int64_t, const c10::optional<at::Tensor>&,
+                                           const c10::optional<at::Tensor>&);
+// train_ops.cu
+void softmax_ce(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, const at::Tensor&,
+                const at::Tensor&, const c10::optional<at::Tensor>&);
+void sage_bwd_input(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t, int64_t, double,
+                    const c10::optional<at::Tensor>&, const at::Tensor&, const c10::optional<at::Tensor>&);
+std::vector<at::Tensor> pack_weight_f32(const at::Tensor&, int64_t, bool);
 // comm.cu
 int64_t symm_alloc(int64_t, int64_t);
 void symm_free(int64_t, int64_t);
@@ -44,6 +54,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("get_degrees", &glb::get_degrees);
   m.def("sample_full", &glb::sample_full);
   m.def("rng_advance", &glb::rng_advance);
+  m.def("random_walk", &glb::random_walk);
   m.def("gather_rows", &glb::gather_rows);
   m.def("gather_agg", &glb::gather_agg);
   m.def("scatter_add_rows", &glb::scatter_add_rows);
@@ -51,6 +62,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sage_smem_bytes", &glb::sage_smem_bytes);
   m.def("pack_weight_sw128", &glb::pack_weight_sw128);
   m.def("sage_fused_forward", &glb::sage_fused_forward);
+  m.def("pack_weight_f32", &glb::pack_weight_f32);
+  m.def("softmax_ce", &glb::softmax_ce);
+  m.def("sage_bwd_input", &glb::sage_bwd_input);
   m.def("symm_alloc", &glb::symm_alloc);
   m.def("symm_free", &glb::symm_free);
   m.def("ipc_get_handle", &glb::ipc_get_handle);

@@ -50,6 +50,9 @@ struct SageParams {
   int relu;
   int out_bf16;
   int tmem_cols;
+  int rows_per_cta;           // destination rows gathered by one CTA (<= 128)
+  const char* zero_row;       // >= 2 KB of zeros: target of the loads of masked lanes / missing rows
+  int wshift_self, wshift_nbr; // log2(world) of each table when it is a power of two, else -1
 };
 
 __device__ __forceinline__ float4 load4_rt(const void* row, int c, int dtype) {
@@ -88,9 +91,70 @@ __device__ __forceinline__ void put_a(uint8_t* sA, int r, int kcol, float4 v) {
   *reinterpret_cast<uint2*>(sA + off) = u;
 }
 
-// CPL = 16-byte-lane chunks per lane for the neighbour half: kp_nbr = 128*CPL
-// (kp_nbr == 64 uses CPL = 1 with the upper half-warp idle).
-template <int CPL>
+// One 16-byte storage chunk of a feature row: 4 fp32 or 8 bf16 features.  Kept RAW
+// (unconverted) so that a whole batch of row loads is issued back to back before the first use.
+template <int DT> struct Chunk;
+template <> struct Chunk<0> {
+  static constexpr int kVec = 4;
+  float4 v;
+  __device__ __forceinline__ void load(const char* p) { v = ld_nc_f4(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void add_to(float (&a)[4]) const { a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w; }
+};
+template <> struct Chunk<1> {
+  static constexpr int kVec = 8;
+  uint4 v;
+  __device__ __forceinline__ void load(const char* p) { v = ld_nc_u4(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void add_to(float (&a)[8]) const {
+    float2 x;
+    x = unpack_bf16x2(v.x); a[0] += x.x; a[1] += x.y;
+    x = unpack_bf16x2(v.y); a[2] += x.x; a[3] += x.y;
+    x = unpack_bf16x2(v.z); a[4] += x.x; a[5] += x.y;
+    x = unpack_bf16x2(v.w); a[6] += x.x; a[7] += x.y;
+  }
+};
+
+// locator of a table row packed into 32 bits: (row << 3) | owner, 0xFFFFFFFF = missing
+__device__ __forceinline__ uint32_t make_loc(const TableView& t, int64_t vid, int wshift) {
+  if (vid < 0) return 0xFFFFFFFFu;
+  int owner; int64_t row;
+  if (wshift >= 0) { owner = (int)(vid & ((1 << wshift) - 1)); row = vid >> wshift; }
+  else { owner = (int)(vid % t.world); row = vid / t.world; }
+  if (row >= t.nrows[owner]) return 0xFFFFFFFFu;
+  return ((uint32_t)row << 3) | (uint32_t)owner;
+}
+__device__ __forceinline__ const char* loc_ptr(const TableView& t, uint32_t loc, uint32_t row_bytes) {
+  return reinterpret_cast<const char*>(t.base.p[loc & 7u]) + (size_t)(loc >> 3) * row_bytes;
+}
+
+// write VEC consecutive K elements of tile row r starting at K column kcol (multiple of VEC)
+template <int VEC>
+__device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_save, size_t a_off, int r, int kcol,
+                                          const float (&v)[VEC]) {
+  const int kb = kcol >> 6;
+  const uint32_t off = (uint32_t)kb * (kTileM * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63));
+  if constexpr (VEC == 4) {
+    uint2 u; u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(sA + off) = u;
+    if (a_save) *reinterpret_cast<uint2*>(a_save + a_off + kcol) = u;
+  } else {
+    uint4 u; u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(sA + off) = u;
+    if (a_save) *reinterpret_cast<uint4*>(a_save + a_off + kcol) = u;
+  }
+}
+
+// U  = neighbour row loads kept in flight per lane (one batch)
+// DT = storage dtype of the self AND neighbour tables (0 fp32, 1 bf16)
+//
+// Work decomposition: the CTA owns `rows_per_cta` consecutive destination rows (<= 128; a small M
+// is spread over many CTAs - the unused rows of the 128-row MMA tile are never stored).  A row
+// needs LPR = kp / VEC lanes (16-byte chunk per lane); when LPR < 32 a warp processes 32/LPR rows
+// side by side (sub-warp groups), when LPR > 32 the row is cut into 32-lane slices.  Per item a
+// lane group (1) already holds the neighbour locators (prefetched during the previous item),
+// (2) issues ALL self + neighbour chunk loads of the batch unconditionally (masked lanes read a
+// zero row), (3) reduces in fp32, (4) writes bf16 into the SW128 A tile.
+template <int U, int DT>
 __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -131,82 +195,107 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   }
 
   // --- gather + aggregate -> A tile (bf16, SW128 K-major)
-  const int m0 = blockIdx.x * kTileM;
+  constexpr int VEC = Chunk<DT>::kVec;
+  const int R = p.rows_per_cta;
+  const int m0 = blockIdx.x * R;
   const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
   const int k = p.k;
-  for (int r = warp; r < kTileM; r += kWarps) {
+  const int lanes_row = p.kp_nbr / VEC;                 // 16-byte chunks per (half) row: 8..128
+  const int lpr = lanes_row < 32 ? lanes_row : 32;      // lanes per row inside a warp
+  const int lshift = 31 - __clz(lpr);                   // log2(lpr)
+  const int rpi = 32 >> lshift;                         // rows per item
+  const int n_slices = lanes_row > 32 ? lanes_row >> 5 : 1;
+  const int row_groups = (R + rpi - 1) / rpi;
+  const int n_items = row_groups * n_slices;
+  const int sub = lane >> lshift;                       // which row of the item this lane works on
+  const int lig = lane & (lpr - 1);                     // lane index inside its row group
+  const bool has_self = p.kp_self > 0;
+  const bool need_self = has_self || p.mode == kGcnMean;
+  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+  const int wshift_n = p.wshift_nbr, wshift_s = p.wshift_self;
+  float scale = 1.f;
+  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
+  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
+
+  // locators of one item: lane `lig` < k holds neighbour `lig` of its row (first pass); every lane
+  // holds the self locator of its row
+  auto load_locs = [&](int item, uint32_t& nloc, uint32_t& sloc) {
+    nloc = 0xFFFFFFFFu; sloc = 0xFFFFFFFFu;
+    if (item >= n_items) return;
+    const int rg = n_slices == 1 ? item : item / n_slices;
+    const int r = rg * rpi + sub;
     const int m = m0 + r;
-    const bool valid = m < p.M;
-    // self row
-    const char* sp = nullptr;
-    if (valid && (p.kp_self > 0 || p.mode == kGcnMean)) {
-      int64_t sv = p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m;
-      sp = table_row(p.tself, sv);
+    if (r >= R || m >= p.M) return;
+    if (lig < k) {
+      const int64_t idx = (int64_t)m * k + lig;
+      nloc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n);
     }
-    for (int c4 = lane; c4 < (p.kp_self >> 2); c4 += 32) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (sp && 4 * c4 < d_self) v = mask_tail(load4_rt(sp, c4, p.tself.dtype), 4 * c4, d_self);
-      put_a(sA, r, 4 * c4, v);
-      if (p.a_save && valid) {
-        uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
-        *reinterpret_cast<uint2*>(p.a_save + (size_t)m * k_total + 4 * c4) = u;
-      }
-    }
-    // neighbour rows
-    float4 acc[CPL];
+    if (need_self) sloc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, wshift_s);
+  };
+
+  uint32_t nloc_next, sloc_next;
+  load_locs(warp, nloc_next, sloc_next);
+  for (int item = warp; item < n_items; item += kWarps) {
+    const int rg = n_slices == 1 ? item : item / n_slices;
+    const int sl = n_slices == 1 ? 0 : item - rg * n_slices;
+    const int r = rg * rpi + sub;
+    const int m = m0 + r;
+    const bool valid = r < R && m < p.M;
+    const uint32_t nloc0 = nloc_next, sloc = sloc_next;
+    load_locs(item + kWarps, nloc_next, sloc_next);      // prefetch: overlaps this item's row loads
+    const int chunk = lig + 32 * sl;                     // this lane's 16-byte chunk of the row
+    const int f0 = chunk * VEC;                          // first feature of the chunk
+    const bool lane_nbr = f0 < d_nbr;                    // chunk holds real neighbour features
+    const bool lane_self = need_self && f0 < d_self && sloc != 0xFFFFFFFFu;
+    const char* sptr = lane_self ? loc_ptr(p.tself, sloc, self_row_bytes) + (size_t)chunk * 16 : p.zero_row + lane * 16;
+
+    float acc[VEC];
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int jb = 0; jb < k; jb += 32) {
-      const int cnt = min(32, k - jb);
-      const char* myp = nullptr;
-      if (valid && lane < cnt) {
-        int64_t idx = (int64_t)m * k + jb + lane;
-        int64_t nv = p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx;
-        myp = table_row(p.tnbr, nv);
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    Chunk<DT> sraw;
+    bool self_loaded = false;
+    for (int jb = 0; jb < k; jb += lpr) {
+      const int cnt = min(lpr, k - jb);
+      uint32_t ploc = nloc0;
+      if (jb > 0) {        // k > lanes per row: fetch this pass's locators inline
+        ploc = 0xFFFFFFFFu;
+        if (valid && lig < cnt) {
+          const int64_t idx = (int64_t)m * k + jb + lig;
+          ploc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n);
+        }
       }
-      for (int j0 = 0; j0 < cnt; j0 += 5) {
-        float4 v[5][CPL];
+      for (int j0 = 0; j0 < cnt; j0 += U) {
+        Chunk<DT> raw[U];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int j = j0 + u;
-          const char* rp = reinterpret_cast<const char*>(
-              __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myp), j < cnt ? j : 0));
-          if (j >= cnt) rp = nullptr;
-#pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            const int c4 = lane + 32 * i;
-            v[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rp && 4 * c4 < d_nbr) v[u][i] = load4_rt(rp, c4, p.tnbr.dtype);
-          }
+          const uint32_t loc = __shfl_sync(0xffffffffu, ploc, j < cnt ? j : 0, lpr);
+          const bool use = (j < cnt) && (loc != 0xFFFFFFFFu) && lane_nbr;
+          raw[u].load(use ? loc_ptr(p.tnbr, loc, nbr_row_bytes) + (size_t)chunk * 16 : p.zero_row + lane * 16);
         }
+        if (!self_loaded) { sraw.load(sptr); self_loaded = true; }
 #pragma unroll
-        for (int u = 0; u < 5; ++u)
-#pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            acc[i].x += v[u][i].x; acc[i].y += v[u][i].y;
-            acc[i].z += v[u][i].z; acc[i].w += v[u][i].w;
-          }
+        for (int u = 0; u < U; ++u) raw[u].add_to(acc);
       }
     }
-    float scale = 1.f;
-    if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
-    else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
+    if (!self_loaded) sraw.load(sptr);                   // k == 0
+    float sv[VEC];
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < (p.kp_nbr >> 2)) {
-        float4 a = mask_tail(acc[i], 4 * c4, d_nbr);
-        if (p.mode == kGcnMean && sp && 4 * c4 < p.tself.dim) {
-          float4 s = mask_tail(load4_rt(sp, c4, p.tself.dtype), 4 * c4, p.tself.dim);
-          a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
-        }
-        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
-        put_a(sA, r, p.kp_self + 4 * c4, a);
-        if (p.a_save && valid) {
-          uint2 u; u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
-          *reinterpret_cast<uint2*>(p.a_save + (size_t)m * k_total + p.kp_self + 4 * c4) = u;
-        }
-      }
+    for (int i = 0; i < VEC; ++i) sv[i] = 0.f;
+    sraw.add_to(sv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {                      // tail masks (dims that are not multiples of VEC)
+      if (f0 + i >= d_self) sv[i] = 0.f;
+      if (f0 + i >= d_nbr) acc[i] = 0.f;
+    }
+    if (r < R) {                                         // rows beyond R belong to another CTA's tile
+      const size_t a_off = (size_t)m * k_total;
+      __nv_bfloat16* asave = (p.a_save && valid) ? p.a_save : nullptr;
+      if (has_self) put_chunk<VEC>(sA, asave, a_off, r, f0, sv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
+      put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
     }
   }
   umma::fence_proxy_async_smem();     // generic-proxy st.shared -> visible to tcgen05 (async proxy)
@@ -239,17 +328,18 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
     const int cols_per_group = p.N >> 2; // multiple of 16
     const int row = q * 32 + lane;
     const int m = m0 + row;
+    const bool row_ok = row < R && m < p.M;
     for (int c0 = 0; c0 < cols_per_group; c0 += 16) {
       const int n0 = g * cols_per_group + c0;
       uint32_t v[16];
       umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
       umma::tmem_ld_wait();
-      if (m < p.M && n0 < p.n_out) {
+      if (row_ok && n0 < p.n_out) {
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x = __uint_as_float(v[i]);
-          if (p.bias) x += __ldg(p.bias + n0 + i);
+          if (p.bias && n0 + i < p.n_out) x += __ldg(p.bias + n0 + i);
           if (p.relu) x = fmaxf(x, 0.f);
           f[i] = x;
         }
@@ -305,6 +395,28 @@ __global__ void pack_sw128_kernel(const __nv_bfloat16* __restrict__ w, int n_rea
   *reinterpret_cast<uint4*>(img + off) = val;
 }
 
+// fp32 row-major padded weight [n_real, k_total] -> (SW128 bf16 image, bf16 row-major copy) in one pass
+__global__ void pack_sw128_f32_kernel(const float* __restrict__ w, int n_real, int N, int k_total,
+                                      uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ w16) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte (8 element) chunk each
+  int nkb = k_total >> 6;
+  int total = nkb * N * 8;
+  if (idx >= total) return;
+  int c = idx & 7;
+  int n = (idx >> 3) % N;
+  int kb = (idx >> 3) / N;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (n < n_real) {
+    const float4* src = reinterpret_cast<const float4*>(w + (size_t)n * k_total + kb * 64 + c * 8);
+    float4 a = src[0], b = src[1];
+    val.x = pack_bf16x2(a.x, a.y); val.y = pack_bf16x2(a.z, a.w);
+    val.z = pack_bf16x2(b.x, b.y); val.w = pack_bf16x2(b.z, b.w);
+    if (w16) *reinterpret_cast<uint4*>(w16 + (size_t)n * k_total + kb * 64 + c * 8) = val;
+  }
+  size_t off = (size_t)kb * N * 128 + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)((c ^ (n & 7)) * 16);
+  *reinterpret_cast<uint4*>(img + off) = val;
+}
+
 // ---------------------------------------------------------------------------
 static int pad_k(int d) {
   if (d <= 0) return 0;
@@ -336,13 +448,35 @@ at::Tensor pack_weight_sw128(const at::Tensor& w_padded, int64_t N) {
   return img;
 }
 
+// returns (image, bf16 row-major copy)
+std::vector<at::Tensor> pack_weight_f32(const at::Tensor& w_padded, int64_t N, bool want_rowmajor) {
+  TORCH_CHECK(w_padded.is_cuda() && w_padded.scalar_type() == at::kFloat && w_padded.dim() == 2 &&
+              w_padded.is_contiguous(), "w_padded must be a contiguous CUDA fp32 [n, k_total] tensor");
+  int64_t n_real = w_padded.size(0), k_total = w_padded.size(1);
+  TORCH_CHECK(k_total % 64 == 0 && N % 8 == 0 && N >= n_real, "bad padded weight shape");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(w_padded.data_ptr()) & 15) == 0, "weight must be 16 B aligned");
+  c10::cuda::CUDAGuard guard(w_padded.device());
+  auto o16 = w_padded.options().dtype(at::kBFloat16);
+  auto img = at::empty({(k_total / 64) * N * 64}, o16);
+  at::Tensor w16;
+  if (want_rowmajor) w16 = at::empty({n_real, k_total}, o16);
+  int total = (int)((k_total / 64) * N * 8);
+  pack_sw128_f32_kernel<<<(total + 255) / 256, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      w_padded.data_ptr<float>(), (int)n_real, (int)N, (int)k_total, reinterpret_cast<uint8_t*>(img.data_ptr()),
+      want_rowmajor ? reinterpret_cast<__nv_bfloat16*>(w16.data_ptr()) : nullptr);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {img, want_rowmajor ? w16 : at::Tensor()};
+}
+
 std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
                                            const c10::optional<at::Tensor>& self_vids,
                                            const at::Tensor& tnbr_desc,
                                            const c10::optional<at::Tensor>& nbr_vids, int64_t M,
                                            int64_t k, int64_t mode, const at::Tensor& w_img,
                                            const c10::optional<at::Tensor>& bias, int64_t N,
-                                           int64_t n_out, bool relu, bool out_bf16, bool save_a) {
+                                           int64_t n_out, bool relu, bool out_bf16, bool save_a, int64_t rows_per_cta,
+                                           const c10::optional<at::Tensor>& out_buf,
+                                           const c10::optional<at::Tensor>& a_buf) {
   TORCH_CHECK(w_img.is_cuda() && w_img.scalar_type() == at::kBFloat16, "w_img must be CUDA bf16");
   c10::cuda::CUDAGuard guard(w_img.device());
   SageParams p;
@@ -366,32 +500,76 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   if (nbr_vids.has_value()) { nv = nbr_vids->contiguous(); check_cuda_i64(nv, "nbr_vids");
     TORCH_CHECK(nv.numel() == M * k); p.nbr_vids = nv.data_ptr<int64_t>(); }
   if (bias.has_value()) { b = bias->contiguous();
-    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() == N, "bias must be fp32 [N]");
+    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out, "bias must be fp32 [>= n_out]");
     p.bias = b.data_ptr<float>(); }
   auto opts = w_img.options();
-  auto out = at::empty({M, n_out}, opts.dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
+  at::Tensor out;
+  if (out_buf.has_value()) {
+    out = *out_buf;
+    TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.size(0) == M && out.size(1) == n_out && out.stride(1) == 1,
+                "out_buf must be [M, n_out] with unit inner stride");
+    TORCH_CHECK(out.scalar_type() == (out_bf16 ? at::kBFloat16 : at::kFloat), "out_buf dtype mismatch");
+  } else {
+    out = at::empty({M, n_out}, opts.dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
+  }
   at::Tensor a_save;
   p.a_save = nullptr;
   if (save_a) {
-    a_save = at::empty({M, (int64_t)k_total}, opts.dtype(at::kBFloat16));
+    if (a_buf.has_value()) {
+      a_save = *a_buf;
+      TORCH_CHECK(a_save.scalar_type() == at::kBFloat16 && a_save.dim() == 2 && a_save.size(0) == M &&
+                  a_save.size(1) == k_total && a_save.stride(1) == 1 && a_save.stride(0) == k_total,
+                  "a_buf must be a row-contiguous bf16 [M, K_total] view");
+    } else {
+      a_save = at::empty({M, (int64_t)k_total}, opts.dtype(at::kBFloat16));
+    }
     p.a_save = reinterpret_cast<__nv_bfloat16*>(a_save.data_ptr());
   }
   p.w_img = w_img.data_ptr();
   p.out = out.data_ptr();
-  p.out_stride = n_out;
+  p.out_stride = out.stride(0);
   p.N = (int)N; p.n_out = (int)n_out; p.relu = relu ? 1 : 0; p.out_bf16 = out_bf16 ? 1 : 0;
   p.tmem_cols = N <= 64 ? 64 : N <= 128 ? 128 : 256;
   if (M == 0) return {out, save_a ? a_save : at::Tensor()};
-  unsigned grid = (unsigned)((M + kTileM - 1) / kTileM);
+  // spread small M over the whole chip: aim for >= 2 CTAs' worth of work per SM-wave but never
+  // more than 128 rows per CTA; keep R a multiple of 8 (one 1024-byte swizzle atom)
+  int R = kTileM;
+  if (rows_per_cta > 0) R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (rows_per_cta + 7) / 8 * 8));
+  else {
+    const int64_t sms = 148;
+    int64_t want = (M + sms - 1) / sms;
+    R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (want + 7) / 8 * 8));
+  }
+  p.rows_per_cta = R;
+  TORCH_CHECK(p.tself.dtype == p.tnbr.dtype, "fused SAGE layer needs self / neighbour tables of the same dtype");
+  TORCH_CHECK(p.kp_self == 0 || p.kp_self == p.kp_nbr, "fused SAGE layer needs equally padded self / neighbour dims");
+  auto log2_or_neg = [](int w) { int s = 0; while ((1 << s) < w) ++s; return (1 << s) == w ? s : -1; };
+  p.wshift_self = log2_or_neg(p.tself.world);
+  p.wshift_nbr = log2_or_neg(p.tnbr.world);
+  TORCH_CHECK((p.tself.stride * (p.tself.dtype == 0 ? 4 : 2)) % 16 == 0 && (p.tnbr.stride * (p.tnbr.dtype == 0 ? 4 : 2)) % 16 == 0,
+              "table rows must be 16-byte aligned (stride multiple of 4 fp32 / 8 bf16 elements)");
+  {
+    static std::vector<at::Tensor> zero_rows(64);
+    int dev = w_img.get_device();
+    if (!zero_rows[dev].defined()) zero_rows[dev] = at::zeros({1024}, opts.dtype(at::kFloat));
+    p.zero_row = reinterpret_cast<const char*>(zero_rows[dev].data_ptr());
+  }
+  unsigned grid = (unsigned)((M + R - 1) / R);
   auto stream = at::cuda::getCurrentCUDAStream();
-  const int cpl = p.kp_nbr <= 128 ? 1 : p.kp_nbr / 128;
-#define LAUNCH(C)                                                                                 \
+  const int u = k <= 4 ? 4 : k <= 8 ? 8 : 13;
+  const int dt = p.tnbr.dtype;
+#define LAUNCH(UU, DD)                                                                            \
   do {                                                                                            \
-    C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_fwd_kernel<C>,                                 \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sage_fused_fwd_kernel<C><<<grid, kThreads, smem, stream>>>(p);                                \
+    static bool attr_done = false;                                                                \
+    if (!attr_done) {                                                                             \
+      C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_fwd_kernel<UU, DD>,                          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));  \
+      attr_done = true;                                                                           \
+    }                                                                                             \
+    sage_fused_fwd_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                           \
   } while (0)
-  if (cpl == 1) LAUNCH(1); else if (cpl == 2) LAUNCH(2); else LAUNCH(4);
+  if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 8) LAUNCH(8, 0); else LAUNCH(13, 0); }
+  else         { if (u == 4) LAUNCH(4, 1); else if (u == 8) LAUNCH(8, 1); else LAUNCH(13, 1); }
 #undef LAUNCH
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, save_a ? a_save : at::Tensor()};

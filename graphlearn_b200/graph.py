@@ -1,0 +1,413 @@
+"""``gl.Graph`` - the user entry point (API parity with
+graphlearn/python/graph.py:38-1119).
+
+    g = gl.Graph()
+    g.node(path, "item", decoder=gl.Decoder(labeled=True, attr_types=["float"] * 100))
+     .edge(path, ("item", "item", "sim"), decoder=gl.Decoder(weighted=True), directed=False)
+     .init()
+    q = g.V("item").batch(512).shuffle(traverse=True).alias("src") \
+         .outV("sim").sample(25).by("random").alias("h1").values()
+
+``init()`` does not start servers: it loads the sources with the native loader,
+hash-partitions them over the ranks of the box (one process per GPU, SPMD) and
+builds the HBM shards (store/graph_store.py).  "worker mode" of the reference
+== running the same script under torchrun; "server mode" (separate sampler
+servers) has no equivalent because sampling is a device kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import config as _config
+from . import errors
+from .data import values as V_
+from .data.decoder import Decoder
+from .ops import gather as G
+from .ops import sampling as S
+from .parallel import runtime as _rt
+from .store.graph_store import ORIGIN, REVERSED, GraphStore, Source, Topology
+from .utils import Mask, get_mask_type
+
+NODE = 0
+EDGE_SRC = 1
+EDGE_DST = 2
+
+
+def _as_tensor(x, device, dtype=torch.int64):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype).to(device)
+
+
+class Graph(object):
+    def __init__(self):
+        self._node_sources: List[Source] = []
+        self._edge_sources: List[Source] = []
+        self._node_decoders: Dict[str, Decoder] = {}
+        self._edge_decoders: Dict[str, Decoder] = {}
+        self._topology = Topology()
+        self._undirected_edges: List[str] = []
+        self._store: Optional[GraphStore] = None
+        self._rt = None
+        self._datasets = []
+        self._inited = False
+        self._with_vineyard = False
+
+    # ------------------------------------------------------------------ description
+    def node(self, source, node_type, decoder=None, option=None, mask=Mask.NONE):
+        """Register a node source: a path (file, dir or comma list) or an in-memory dict
+        {ids, weights, labels, timestamps, int_attrs, float_attrs, string_attrs}."""
+        if not isinstance(source, (str, dict)):
+            raise ValueError("source for node() must be a string or a dict of arrays.")
+        if not isinstance(node_type, str):
+            raise ValueError("node_type for node() must be a string.")
+        decoder = decoder or Decoder()
+        if not isinstance(decoder, Decoder):
+            raise ValueError("decoder must be an instance of Decoder, got {}".format(type(decoder)))
+        t = get_mask_type(node_type, mask)
+        self._node_decoders[t] = decoder
+        if isinstance(source, dict):
+            self._node_sources.append(Source("node", None, t, decoder, option=option, data=source))
+        else:
+            self._node_sources.append(Source("node", source, t, decoder, option=option))
+        return self
+
+    def edge(self, source, edge_type, decoder=None, directed=True, option=None, mask=Mask.NONE):
+        """edge_type = (src_type, dst_type, edge_type).  ``directed=False`` also adds the reversed
+        rows: into the same type when src_type == dst_type, otherwise as '<edge_type>_reverse'
+        (graphlearn/python/graph.py:357-381)."""
+        if not isinstance(source, (str, dict)):
+            raise ValueError("source for edge() must be a string or a dict of arrays.")
+        if not isinstance(edge_type, tuple) or len(edge_type) != 3:
+            raise ValueError("edge_type for edge() must be a tuple of (src_type, dst_tye, edge_type).")
+        decoder = decoder or Decoder()
+        if not isinstance(decoder, Decoder):
+            raise ValueError("decoder must be an instance of Decoder, got {}".format(type(decoder)))
+        st, dt, et = edge_type
+        met = get_mask_type(et, mask)
+        self._edge_decoders[met] = decoder
+        self._topology.add(met, st, dt)
+
+        def add(types, direction):
+            if isinstance(source, dict):
+                self._edge_sources.append(Source("edge", None, types, decoder, direction, option, data=source))
+            else:
+                self._edge_sources.append(Source("edge", source, types, decoder, direction, option))
+
+        add((st, dt, met), ORIGIN)
+        if not directed:
+            self._undirected_edges.append(et)
+            if st != dt:
+                rt_ = et + "_reverse"
+                self._edge_decoders[rt_] = decoder
+                self._topology.add(rt_, dt, st)
+                add((dt, st, rt_), REVERSED)
+            else:
+                add((st, dt, met), REVERSED)
+        return self
+
+    @property
+    def undirected_edges(self):
+        return self._undirected_edges
+
+    def is_directed(self, edge_type):
+        return edge_type not in self._undirected_edges
+
+    # ------------------------------------------------------------------ lifecycle
+    def init(self, task_index=0, task_count=1, cluster="", job_name="", device=None, **kwargs):
+        """Build the sharded graph on this rank's GPU.  ``task_index/task_count/cluster/job_name``
+        are accepted for script compatibility; the rank/world come from torchrun env vars."""
+        if self._inited:
+            return self
+        self._rt = _rt.init(device=device)
+        self._store = GraphStore(self._rt)
+        self._store.node_decoders = self._node_decoders
+        self._store.edge_decoders = self._edge_decoders
+        self._store.build(self._node_sources, self._edge_sources)
+        self._topology = self._store.topology
+        self._inited = True
+        return self
+
+    def close(self):
+        for ds in self._datasets:
+            try:
+                ds.close()
+            except Exception:
+                pass
+        self._inited = False
+
+    def wait_for_close(self):
+        """Server-mode blocking call of the reference; SPMD ranks simply synchronise."""
+        if self._rt is not None:
+            self._rt.barrier()
+
+    def add_dataset(self, ds):
+        self._datasets.append(ds)
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def store(self) -> GraphStore:
+        self._check_inited()
+        return self._store
+
+    @property
+    def runtime(self):
+        return self._rt
+
+    @property
+    def device(self):
+        return self._rt.device if self._rt else torch.device("cpu")
+
+    def _check_inited(self):
+        if not self._inited:
+            raise errors.FailedPreconditionError("Graph is not initialised; call g.init() first.")
+
+    def get_topology(self):
+        return self._topology
+
+    def get_node_decoder(self, node_type):
+        d = self._node_decoders.get(node_type)
+        if d is None:
+            # masked / unmasked fallback
+            for k, v in self._node_decoders.items():
+                if k.endswith("_" + node_type) and k.startswith("MASK"):
+                    return v
+            return Decoder()
+        return d
+
+    def get_edge_decoder(self, edge_type):
+        return self._edge_decoders.get(edge_type, Decoder())
+
+    def get_node_decoders(self):
+        return self._node_decoders
+
+    def get_edge_decoders(self):
+        return self._edge_decoders
+
+    def get_stats(self):
+        """{type: [count on rank 0, count on rank 1, ...]} (GetStats)."""
+        self._check_inited()
+        return dict(self._store.stats)
+
+    server_get_stats = get_stats
+
+    # ------------------------------------------------------------------ id helpers
+    def _table(self, node_type):
+        self._check_inited()
+        if node_type not in self._store.nodes:
+            raise errors.NotFoundError("unknown node type %r" % (node_type,))
+        return self._store.nodes[node_type]
+
+    def _csr(self, edge_type):
+        self._check_inited()
+        if edge_type not in self._store.edges:
+            raise errors.NotFoundError("unknown edge type %r" % (edge_type,))
+        return self._store.edges[edge_type]
+
+    def to_vids(self, node_type, ids):
+        t = self._table(node_type)
+        return t.idmap.to_vid(_as_tensor(ids, self.device))
+
+    def to_ids(self, node_type, vids):
+        return self._table(node_type).idmap.to_id(vids)
+
+    # ------------------------------------------------------------------ lookups (O18)
+    def lookup_nodes(self, node_type, ids, vids=None) -> V_.Nodes:
+        """Attributes / weights / labels / timestamps of nodes; unknown ids get the configured
+        defaults (graphlearn/src/core/graph/storage/memory_node_storage.cc:88-138)."""
+        tab = self._table(node_type)
+        dec = self.get_node_decoder(node_type)
+        cfg = _config.get()
+        ids_t = _as_tensor(ids, self.device)
+        shape = tuple(ids_t.shape)
+        flat = ids_t.reshape(-1)
+        v = vids.reshape(-1) if vids is not None else tab.idmap.to_vid(flat)
+        rt = self._rt
+        out = V_.Nodes(ids_t, node_type, shape=shape, graph=self, vids=v)
+        out._inited = True
+        if dec.float_attr_num > 0 and tab.feats is not None:
+            out._t["float_attrs"] = G.gather_rows(rt, tab.feats, tab.feat_desc, v, tab.float_dim,
+                                                  fill=cfg.default_float_attribute)
+        if dec.int_attr_num > 0 and tab.ints is not None:
+            out._t["int_attrs"] = G.gather_any(rt, tab.ints, v, fill=cfg.default_int_attribute)
+        if dec.labeled and tab.labels is not None:
+            out._t["labels"] = G.gather_any(rt, tab.labels, v, fill=cfg.default_label)
+        if dec.weighted and tab.weights is not None:
+            out._t["weights"] = G.gather_any(rt, tab.weights, v, fill=cfg.default_weight)
+        if dec.timestamped and tab.timestamps is not None:
+            out._t["timestamps"] = G.gather_any(rt, tab.timestamps, v, fill=cfg.default_timestamp)
+        if dec.string_attr_num > 0 and tab.strings is not None:
+            out._t["string_attrs"] = self._lookup_strings(tab, v)
+        return out
+
+    def _lookup_strings(self, tab, vids):
+        W = self._rt.world
+        if W > 1:
+            raise errors.UnimplementedError("string attributes are host side and only served by the owning rank")
+        rows = torch.div(vids, W, rounding_mode="floor").cpu().numpy()
+        ok = (vids >= 0).cpu().numpy() & (rows < tab.n_local)
+        arr = np.full((len(rows), tab.str_dim), _config.get().default_string_attribute, dtype=object)
+        arr[ok] = tab.strings[rows[ok]]
+        return arr
+
+    def lookup_edges(self, edge_type, src_ids, edge_ids, src_vids=None) -> V_.Edges:
+        csr = self._csr(edge_type)
+        dec = self.get_edge_decoder(edge_type)
+        cfg = _config.get()
+        src_t = _as_tensor(src_ids, self.device)
+        eid_t = _as_tensor(edge_ids, self.device)
+        shape = tuple(eid_t.shape)
+        W = self._rt.world
+        sv = src_vids.reshape(-1) if src_vids is not None else self._table(csr.src_type).idmap.to_vid(src_t.reshape(-1))
+        if sv.numel() != eid_t.numel() and sv.numel() > 0:
+            sv = sv.reshape(-1, 1).expand(-1, eid_t.numel() // sv.numel()).reshape(-1)
+        # edge rows live on the SOURCE's owner at position edge_id: address them as vid = eid * W + owner
+        key = torch.where(eid_t.reshape(-1) >= 0, eid_t.reshape(-1) * W + (sv.clamp(min=0) % W),
+                          torch.full_like(sv, -1))
+        out = V_.Edges(src_t, csr.src_type, None, csr.dst_type, edge_type, eid_t, shape=shape, graph=self)
+        out._inited = True
+        rt = self._rt
+        if dec.weighted and csr.weights is not None:
+            out._t["weights"] = G.gather_any(rt, csr.weights, key, fill=cfg.default_weight)
+        if dec.labeled and csr.labels is not None:
+            out._t["labels"] = G.gather_any(rt, csr.labels, key, fill=cfg.default_label)
+        if dec.timestamped and csr.ts is not None:
+            out._t["timestamps"] = G.gather_any(rt, csr.ts, key, fill=cfg.default_timestamp)
+        if dec.float_attr_num > 0 and csr.float_attrs is not None:
+            out._t["float_attrs"] = G.gather_any(rt, csr.float_attrs, key, fill=cfg.default_float_attribute)
+        if dec.int_attr_num > 0 and csr.int_attrs is not None:
+            out._t["int_attrs"] = G.gather_any(rt, csr.int_attrs, key, fill=cfg.default_int_attribute)
+        if dec.string_attr_num > 0 and getattr(csr, "strings", None) is not None and W == 1:
+            e = eid_t.reshape(-1).cpu().numpy()
+            arr = np.full((len(e), dec.string_attr_num), cfg.default_string_attribute, dtype=object)
+            ok = (e >= 0) & (e < len(csr.strings))
+            arr[ok] = csr.strings[e[ok]]
+            out._t["string_attrs"] = arr
+        return out
+
+    def get_nodes(self, node_type, ids, offsets=None, shape=None):
+        """Construct Nodes / SparseNodes bound to this graph (attributes are fetched lazily)."""
+        if offsets is None:
+            return V_.Nodes(ids, node_type, shape=shape, graph=self)
+        return V_.SparseNodes(ids, offsets, shape, node_type, graph=self)
+
+    def get_edges(self, edge_type, src_ids, dst_ids, edge_ids=None, offsets=None, shape=None):
+        st, dt = self._topology.get_src_type(edge_type), self._topology.get_dst_type(edge_type)
+        if offsets is None:
+            return V_.Edges(src_ids, st, dst_ids, dt, edge_type, edge_ids, shape=shape, graph=self)
+        return V_.SparseEdges(src_ids, st, dst_ids, dt, edge_type, offsets, shape, edge_ids=edge_ids, graph=self)
+
+    # ------------------------------------------------------------------ degrees / aggregation
+    def out_degrees(self, ids, edge_type):
+        csr = self._csr(edge_type)
+        v = self.to_vids(csr.src_type, ids)
+        d = S.get_degrees(csr, v.reshape(-1))
+        return d.reshape(v.shape).cpu().numpy()
+
+    def in_degrees(self, ids, edge_type):
+        """The reference returns Unimplemented for in-degrees (degree_getter.cc:48-53); here the
+        in-edge CSR is built on demand."""
+        csr = self._csr(edge_type)
+        rev = self._store.reverse_csr(edge_type)
+        v = self.to_vids(csr.dst_type, ids)
+        d = S.get_degrees(rev, v.reshape(-1))
+        return d.reshape(v.shape).cpu().numpy()
+
+    def aggregate_nodes(self, node_type, ids, func="sum", k=0, offsets=None, vids=None):
+        """Server-side segment aggregation of float attributes (Aggregator operators O16)."""
+        tab = self._table(node_type)
+        v = vids if vids is not None else tab.idmap.to_vid(_as_tensor(ids, self.device).reshape(-1))
+        return G.gather_agg(self._rt, tab.feats, tab.feat_desc, v, tab.float_dim, func, offsets=offsets, k=k)
+
+    # ------------------------------------------------------------------ GSL entry points
+    def V(self, t, feed=None, node_from=NODE, mask=Mask.NONE):
+        from .gsl.dag import Dag
+        from .gsl.dag_node import TraverseVertexDagNode
+        if feed is not None:
+            raise NotImplementedError("`feed` is not supported for V() yet (same as the reference).")
+        self._check_inited()
+        dag = Dag(self)
+        if node_from == NODE:
+            node_type = get_mask_type(t, mask)
+            if node_type not in self._store.nodes:
+                raise ValueError("node type %r not in graph" % (node_type,))
+            params = {"node_from": NODE, "node_type": node_type}
+            out_type = node_type
+            base_type = t
+        else:
+            et = get_mask_type(t, mask)
+            if not self._topology.is_exist(et):
+                raise ValueError("edge type %r not in graph" % (et,))
+            params = {"node_from": node_from, "edge_type": et}
+            out_type = self._topology.get_src_type(et) if node_from == EDGE_SRC else self._topology.get_dst_type(et)
+            base_type = out_type
+        node = TraverseVertexDagNode(dag, op_name="GetNodes", params=params)
+        node.set_output_type(out_type, base_type)
+        dag.root = node
+        return node
+
+    def E(self, edge_type, feed=None, reverse=False, mask=Mask.NONE):
+        from .gsl.dag import Dag
+        from .gsl.dag_node import TraverseSourceEdgeDagNode
+        if feed is not None:
+            raise NotImplementedError("`feed` is not supported for E() yet (same as the reference).")
+        self._check_inited()
+        et = get_mask_type(edge_type, mask)
+        if not self._topology.is_exist(et):
+            raise ValueError("edge type %r not in graph" % (et,))
+        dag = Dag(self)
+        node = TraverseSourceEdgeDagNode(dag, op_name="GetEdges", params={"edge_type": et, "reverse": reverse})
+        dag.root = node
+        return node
+
+    def SubGraph(self, seed_type, nbr_type, batch_size=64, strategy="random_node", num_nbrs=None, need_dist=False):
+        """Root of a subgraph-sampling query (graphlearn/python/graph.py:629-667)."""
+        from .gsl.dag import Dag
+        from .gsl.dag_node import SubGraphDagNode
+        self._check_inited()
+        dag = Dag(self)
+        node = SubGraphDagNode(dag, params={"seed_type": seed_type, "nbr_type": nbr_type, "batch_size": batch_size,
+                                            "strategy": strategy, "num_nbrs": list(num_nbrs or []),
+                                            "need_dist": need_dist})
+        dag.root = node
+        return node
+
+    # ------------------------------------------------------------------ imperative samplers (P4)
+    def node_sampler(self, t, batch_size=64, strategy="by_order", node_from=NODE, mask=Mask.NONE):
+        from .sampler.node_sampler import NodeSampler
+        return NodeSampler(self, get_mask_type(t, mask) if node_from == NODE else t, batch_size, strategy, node_from)
+
+    def edge_sampler(self, edge_type, batch_size=64, strategy="by_order", mask=Mask.NONE):
+        from .sampler.edge_sampler import EdgeSampler
+        return EdgeSampler(self, get_mask_type(edge_type, mask), batch_size, strategy)
+
+    def neighbor_sampler(self, meta_path, expand_factor, strategy="random"):
+        from .sampler.neighbor_sampler import FullNeighborSampler, NeighborSampler
+        if strategy == "full":
+            return FullNeighborSampler(self, meta_path, expand_factor)
+        return NeighborSampler(self, meta_path, expand_factor, strategy)
+
+    def negative_sampler(self, object_type, expand_factor, strategy="random", conditional=False, **kwargs):
+        from .sampler.negative_sampler import ConditionalNegativeSampler, NegativeSampler
+        if conditional:
+            return ConditionalNegativeSampler(self, object_type, expand_factor, strategy, **kwargs)
+        return NegativeSampler(self, object_type, expand_factor, strategy)
+
+    def subgraph_sampler(self, seed_type, nbr_type, batch_size=64, strategy="random_node", num_nbrs=None,
+                         need_dist=False):
+        from .sampler.subgraph_sampler import SubGraphSampler
+        return SubGraphSampler(self, seed_type, nbr_type, batch_size, strategy, num_nbrs, need_dist)
+
+    def search(self, node_type, inputs, option):
+        """KNN search over a node type's float attributes (KnnOperator)."""
+        from .ops import knn
+        tab = self._table(node_type)
+        q = _as_tensor(inputs, self.device, torch.float32)
+        ids, dist = knn.search(self._rt, tab, q, option.k, metric=_config.get().knn_metric)
+        return ids.cpu().numpy(), dist.cpu().numpy()
+
+    def get_client(self):
+        return self

@@ -1,0 +1,318 @@
+"""Executes a GSL query plan on the device, one batch per call.
+
+This replaces the reference's server-side continuous DAG execution
+(DagScheduler -> DagNodeRunner -> OpRunner -> Tape,
+graphlearn/src/core/runner/dag_scheduler.cc:45-86, dag_node_runner.cc:32-98):
+the plan is walked in topological (construction) order and every traversal is
+one kernel launch over the sharded store; the per-alias results are ``Nodes``
+/ ``Edges`` objects backed by device tensors.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .. import config as _config
+from .. import errors
+from ..data import values as V_
+from ..ops import negative as NEG
+from ..ops import rng as rng_ops
+from ..ops import sampling as S
+from ..ops import subgraph as SUB
+from ..ops import walk as WALK
+from .dag_node import (DagNode, FakeNode, SubGraphDagNode, TraverseEdgeDagNode, TraverseNegVertexDagNode,
+                       TraverseSourceEdgeDagNode, TraverseVertexDagNode)
+from .iterators import SeedIterator
+
+NODE, EDGE_SRC, EDGE_DST = 0, 1, 2
+
+
+class _Out(object):
+    """Per-node execution result: ids (+ vids in the node type's base table) or an edge batch."""
+    __slots__ = ("ids", "vids", "shape", "value", "src_ids", "src_vids", "eids")
+
+    def __init__(self, ids=None, vids=None, shape=None, value=None):
+        self.ids, self.vids, self.shape, self.value = ids, vids, shape, value
+        self.src_ids = self.src_vids = self.eids = None
+
+
+class QueryExecutor(object):
+    def __init__(self, dag, drop_last: bool = False, seed: Optional[int] = None):
+        if not dag.is_ready():
+            raise ValueError("query is not ready: end it with .values()")
+        self.dag = dag
+        self.g = dag.graph
+        self.store = self.g.store
+        self.rt = self.g.runtime
+        self.rng = rng_ops.DeviceRng(self.rt, _config.get().seed if seed is None else seed)
+        self.drop_last = drop_last
+        self._iter: Optional[SeedIterator] = None
+        self._order = self._toposort()
+        self._salt = 0
+
+    # ------------------------------------------------------------------ plan
+    def _toposort(self):
+        order, seen = [], set()
+
+        def visit(n: DagNode):
+            if id(n) in seen:
+                return
+            seen.add(id(n))
+            order.append(n)
+            for d in n.downstreams:
+                visit(d)
+
+        visit(self.dag.root)
+        return order
+
+    # ------------------------------------------------------------------ roots
+    def _root_nodes(self, node: DagNode) -> _Out:
+        p = node.params
+        bs = int(p.get("batch_size", 64))
+        strategy = p.get("strategy", "by_order")
+        W, r = self.rt.world, self.rt.rank
+        if p.get("node_from", NODE) == NODE:
+            tab = self.store.nodes[node.type]
+            if self._iter is None:
+                rows = tab.present.nonzero().flatten() if tab.present is not None else torch.arange(tab.n_local, device=self.rt.device)
+                self._rows = rows
+                self._iter = SeedIterator(int(rows.numel()), bs, strategy, self.rt.device, seed=_config.get().seed + 17 * r,
+                                          drop_last=self.drop_last)
+            idx = self._iter.next_index()
+            rows = self._rows[idx]
+            vids = rows * W + r
+            ids = tab.idmap.to_id(vids) if not tab.idmap.dense else vids
+            # vids must live in the BASE table (edges index the unmasked node type)
+            base = node._base_type
+            if base != node.type and base in self.store.nodes:
+                bvids = self.store.nodes[base].idmap.to_vid(ids)
+            else:
+                bvids = vids
+            out = _Out(ids=ids, vids=bvids, shape=(int(ids.numel()),))
+            out.value = V_.Nodes(ids, node.type, shape=out.shape, graph=self.g, vids=vids)
+            return out
+        # nodes from edge end points
+        csr = self.store.edges[p["edge_type"]]
+        if self._iter is None:
+            self._iter = SeedIterator(csr.n_edges, bs, strategy, self.rt.device, seed=_config.get().seed + 17 * r,
+                                      drop_last=self.drop_last)
+        idx = self._iter.next_index()
+        if p["node_from"] == EDGE_SRC:
+            vids = csr._row_of_edge[idx] * W + r
+            t = csr.src_type
+        else:
+            vids = csr.indices.local[idx]
+            t = csr.dst_type
+        ids = self.g.to_ids(t, vids)
+        out = _Out(ids=ids, vids=vids, shape=(int(ids.numel()),))
+        out.value = V_.Nodes(ids, t, shape=out.shape, graph=self.g, vids=vids)
+        return out
+
+    def _root_edges(self, node: DagNode) -> _Out:
+        p = node.params
+        csr = self.store.edges[p["edge_type"]]
+        W, r = self.rt.world, self.rt.rank
+        bs = int(p.get("batch_size", 64))
+        if self._iter is None:
+            self._iter = SeedIterator(csr.n_edges, bs, p.get("strategy", "by_order"), self.rt.device,
+                                      seed=_config.get().seed + 17 * r, drop_last=self.drop_last)
+        idx = self._iter.next_index()
+        src_v = csr._row_of_edge[idx] * W + r
+        dst_v = csr.indices.local[idx]
+        src_ids = self.g.to_ids(csr.src_type, src_v)
+        dst_ids = self.g.to_ids(csr.dst_type, dst_v)
+        st, dt = csr.src_type, csr.dst_type
+        if p.get("reverse"):
+            src_ids, dst_ids, src_v, dst_v, st, dt = dst_ids, src_ids, dst_v, src_v, dt, st
+        out = _Out(ids=dst_ids, vids=dst_v, shape=(int(idx.numel()),))
+        out.src_ids, out.src_vids, out.eids = src_ids, src_v, idx
+        out.value = V_.Edges(src_ids, st, dst_ids, dt, p["edge_type"], idx, shape=out.shape, graph=self.g,
+                             src_vids=(csr._row_of_edge[idx] * W + r))
+        return out
+
+    # ------------------------------------------------------------------ traversals
+    def _sample(self, node: DagNode, up: _Out, results) -> _Out:
+        p = node.params
+        et = p["edge_type"]
+        direction = p.get("direction", "out")
+        strategy = p.get("strategy", "random")
+        k = int(p.get("neighbor_count", 1))
+        if direction == "in":
+            csr = self.store.reverse_csr(et)
+            dst_t = self.store.edges[et].src_type
+        else:
+            csr = self.store.edges[et]
+            dst_t = csr.dst_type
+        if strategy == "in_degree" and direction == "out":
+            self.store.ensure_indegree_weights(et)
+        src_v = up.vids.reshape(-1)
+        self._salt += 1
+        want_edges = p.get("emit") == "edges"
+        if strategy == "full":
+            cap = k if k > 0 else 0
+            vals, eids, offs = S.sample_full(csr, src_v, cap=cap, want_eids=True)
+            counts = (offs[1:] - offs[:-1])
+            ids = self.g.to_ids(dst_t, vals)
+            B = int(src_v.numel())
+            maxd = int(counts.max().item()) if B > 0 else 0
+            out = _Out(ids=ids, vids=vals, shape=(int(ids.numel()),))
+            if want_edges:
+                src_ids = torch.repeat_interleave(up.ids.reshape(-1), counts)
+                out.value = V_.SparseEdges(src_ids, up.value.type if hasattr(up.value, "type") else None, ids, dst_t, et,
+                                           counts, (B, maxd), edge_ids=eids, graph=self.g)
+            else:
+                out.value = V_.SparseNodes(ids, counts, (B, maxd), dst_t, graph=self.g, vids=vals)
+            return out
+        fmode, fvals = S.FILTER_NONE, None
+        if node._filter is not None:
+            f = results[id(node._filter)]
+            fv = f.vids.reshape(-1)
+            if fv.numel() != src_v.numel():
+                fv = fv.reshape(-1, 1).expand(-1, src_v.numel() // max(fv.numel(), 1)).reshape(-1)
+            fmode, fvals = S.FILTER_ID, fv
+        elif csr.timestamped and getattr(up.value, "_t", {}).get("timestamps") is not None and p.get("temporal", True):
+            ts = up.value.tensor("timestamps")
+            if ts is not None and ts.numel() == src_v.numel():
+                fmode, fvals = S.FILTER_TS, ts.reshape(-1).to(torch.int64)
+        nbr, eid = S.sample_neighbors(csr, src_v, k, strategy, fmode, fvals, want_eids=True, rng=self.rng,
+                                      salt=self._salt)
+        B = int(src_v.numel())
+        ids = self.g.to_ids(dst_t, nbr)
+        out = _Out(ids=ids, vids=nbr, shape=(B, k))
+        if want_edges:
+            src_ids = up.ids.reshape(-1, 1).expand(B, k)
+            out.src_ids, out.src_vids, out.eids = src_ids, src_v, eid
+            topo = self.g.get_topology()
+            st = topo.get_src_type(et) if direction == "out" else topo.get_dst_type(et)
+            out.value = V_.Edges(src_ids, st, ids, dst_t, et, eid, shape=(B, k), graph=self.g,
+                                 src_vids=src_v.reshape(-1, 1).expand(B, k))
+        else:
+            out.value = V_.Nodes(ids, dst_t, shape=(B, k), graph=self.g, vids=nbr)
+        return out
+
+    def _negative(self, node: DagNode, up: _Out, results) -> _Out:
+        p = node.params
+        k = int(p.get("neighbor_count", 1))
+        strategy = p.get("strategy", "random")
+        self._salt += 1
+        src_v = up.vids.reshape(-1)
+        B = int(src_v.numel())
+        gen = self.rng.torch_generator(self._salt)
+        if p.get("conditional"):
+            dst = results[id(p["dst_node"])]
+            neg = NEG.conditional_negative(self.store, p["edge_type"], src_v, dst.vids.reshape(-1), k, strategy,
+                                           p["condition"], gen)
+            dst_t = self.store.edges[p["edge_type"]].dst_type
+        elif "node_type" in p and "edge_type" not in p:
+            dst_t = p["node_type"]
+            neg = NEG.node_weight_negative(self.store, dst_t, src_v, k, gen)
+        else:
+            et = p["edge_type"]
+            dst_t = self.store.edges[et].dst_type if p.get("direction", "out") == "out" else self.store.edges[et].src_type
+            neg = NEG.edge_negative(self.store, et, src_v, k, strategy, gen, direction=p.get("direction", "out"))
+        ids = self.g.to_ids(dst_t, neg)
+        out = _Out(ids=ids, vids=neg, shape=(B, k))
+        out.value = V_.Nodes(ids, dst_t, shape=(B, k), graph=self.g, vids=neg)
+        return out
+
+    def _walk(self, node: DagNode, up: _Out) -> _Out:
+        p = node.params
+        csr = self.store.edges[p["edge_type"]]
+        self._salt += 1
+        walks = WALK.random_walk(csr, up.vids.reshape(-1), int(p["walk_len"]), p["p"], p["q"], rng=self.rng,
+                                 salt=self._salt)
+        ids = self.g.to_ids(csr.dst_type, walks)
+        out = _Out(ids=ids, vids=walks, shape=tuple(walks.shape))
+        out.value = V_.Nodes(ids, csr.dst_type, shape=tuple(walks.shape), graph=self.g, vids=walks)
+        return out
+
+    def _subgraph(self, node: DagNode, up: Optional[_Out]) -> _Out:
+        p = node.params
+        et = p["nbr_type"]
+        csr = self.store.edges[et]
+        if up is None:
+            # root SubGraph: seeds from a node iterator over the seed type
+            if self._iter is None:
+                tab = self.store.nodes[p["seed_type"]]
+                self._iter = SeedIterator(tab.n_local, int(p["batch_size"]), "shuffle" if "random" in p["strategy"] else "by_order",
+                                          self.rt.device, seed=_config.get().seed + 17 * self.rt.rank)
+            idx = self._iter.next_index()
+            seeds = idx * self.rt.world + self.rt.rank
+            src = dst = None
+        elif p.get("from_edges"):
+            src, dst = up.src_vids.reshape(-1), up.vids.reshape(-1)
+            seeds = torch.cat([src, dst])
+        else:
+            seeds = up.vids.reshape(-1)
+            src = dst = None
+        sg = SUB.induce_subgraph(self.store, et, seeds, p.get("num_nbrs") or [], need_dist=p.get("need_dist", False),
+                                 src=src, dst=dst, rng=self.rng)
+        ids = self.g.to_ids(csr.src_type, sg["nodes"])
+        nodes = V_.Nodes(ids, csr.src_type, graph=self.g, vids=sg["nodes"])
+        edges = None
+        if sg.get("eids") is not None:
+            edges = V_.Edges(ids[sg["row"]], csr.src_type, ids[sg["col"]], csr.dst_type, et, sg["eids"], graph=self.g,
+                             src_vids=sg["nodes"][sg["row"]])
+        kw = {}
+        if sg.get("dist_to_src") is not None:
+            kw = {"dist_to_src": sg["dist_to_src"].cpu().numpy(), "dist_to_dst": sg["dist_to_dst"].cpu().numpy()}
+        out = _Out(ids=ids, vids=sg["nodes"], shape=(int(ids.numel()),))
+        out.value = V_.SubGraph(torch.stack([sg["row"], sg["col"]]), nodes, edges, **kw)
+        return out
+
+    # ------------------------------------------------------------------ run one batch
+    def run(self) -> Dict[str, object]:
+        results: Dict[int, _Out] = {}
+        for node in self._order:
+            up = results.get(id(node.upstream)) if node.upstream is not None else None
+            if node is self.dag.root:
+                if isinstance(node, SubGraphDagNode):
+                    res = self._subgraph(node, None)
+                elif isinstance(node, TraverseSourceEdgeDagNode):
+                    res = self._root_edges(node)
+                else:
+                    res = self._root_nodes(node)
+            elif isinstance(node, FakeNode):
+                which = node.params["which"]
+                if which == "src":
+                    res = _Out(ids=up.src_ids, vids=(up.src_vids.reshape(-1, 1).expand(up.shape).reshape(up.shape)
+                                                     if up.src_vids is not None and len(up.shape) == 2 else up.src_vids),
+                               shape=up.shape)
+                else:
+                    res = _Out(ids=up.ids, vids=up.vids, shape=up.shape)
+                res.value = V_.Nodes(res.ids, node.type, shape=res.shape, graph=self.g, vids=res.vids)
+            elif isinstance(node, SubGraphDagNode):
+                res = self._subgraph(node, up)
+            elif node.op_name == "RandomWalk":
+                res = self._walk(node, up)
+            elif isinstance(node, TraverseNegVertexDagNode) or node.params.get("negative"):
+                res = self._negative(node, up, results)
+            elif node.op_name == "Sampler":
+                res = self._sample(node, up, results)
+            else:
+                raise errors.UnimplementedError("unknown GSL node %r" % (node.op_name,))
+            results[id(node)] = res
+        self.rng.advance(1)
+        out = {}
+        for alias in self.dag.list_alias():
+            out[alias] = results[id(self.dag.get_node(alias))].value
+        return out
+
+    # ------------------------------------------------------------------ state
+    @property
+    def epoch(self):
+        return self._iter.epoch if self._iter is not None else 0
+
+    def state_dict(self):
+        return {"iter": None if self._iter is None else self._iter.state_dict(), "rng": self.rng.state_dict()}
+
+    def load_state_dict(self, sd):
+        if sd.get("iter") is not None:
+            if self._iter is None:
+                try:
+                    self.run()
+                except errors.OutOfRangeError:
+                    pass
+            self._iter.load_state_dict(sd["iter"])
+        self.rng.load_state_dict(sd["rng"])

@@ -32,9 +32,17 @@ class EgoSAGEConv(nn.Module):
         self.agg_type = agg_type
         assert agg_type in ("mean", "sum", "max", "gcn")
         k_in = self.in_nbr if agg_type == "gcn" else self.in_self + self.in_nbr
-        self.weight = nn.Parameter(torch.empty(out_dim, k_in))
+        self._mode = "mean" if agg_type == "max" else agg_type
+        w = torch.empty(out_dim, k_in)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        # stored in the fused kernel's padded K layout (pad columns are zero and stay zero)
+        self.weight_p = nn.Parameter(sage_ops.pad_weight(w, self.in_self, self.in_nbr, self._mode))
         self.bias = nn.Parameter(torch.zeros(out_dim)) if bias else None
-        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+
+    @property
+    def weight(self):
+        """Logical [out, in_self + in_nbr] weight (gcn: [out, in])."""
+        return sage_ops.logical_weight(self.weight_p, self.in_self, self.in_nbr, self._mode)
 
     def forward(self, x, neighbor, expand, relu=False, out_bf16=False):
         """x [M, d], neighbor [M*k, d_n], expand = k."""
@@ -43,7 +51,7 @@ class EgoSAGEConv(nn.Module):
             y = F.linear(torch.cat([x.float(), agg], 1), self.weight, self.bias)
             y = F.relu(y) if relu else y
             return y.to(torch.bfloat16) if out_bf16 else y
-        return sage_ops.sage_layer(self.weight, self.bias, k=expand, mode=self.agg_type, relu=relu,
+        return sage_ops.sage_layer(self.weight_p, self.bias, k=expand, mode=self.agg_type, relu=relu,
                                    out_bf16=out_bf16, x_self=x, x_nbr=neighbor)
 
     def forward_store(self, table, self_vids, nbr_vids, expand, relu=False, out_bf16=False, nbr_table=None):
@@ -53,6 +61,6 @@ class EgoSAGEConv(nn.Module):
             xs = G.gather_rows(table.rt, table.feats, table.feat_desc, self_vids, table.float_dim)
             xn = G.gather_rows(nt.rt, nt.feats, nt.feat_desc, nbr_vids, nt.float_dim)
             return self.forward(xs, xn, expand, relu, out_bf16)
-        return sage_ops.sage_layer(self.weight, self.bias, k=expand, mode=self.agg_type, relu=relu,
+        return sage_ops.sage_layer(self.weight_p, self.bias, k=expand, mode=self.agg_type, relu=relu,
                                    out_bf16=out_bf16, self_table=table, self_vids=self_vids.reshape(-1),
                                    nbr_table=nbr_table or table, nbr_vids=nbr_vids.reshape(-1))

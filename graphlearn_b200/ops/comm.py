@@ -101,7 +101,11 @@ def flatten_module(module: torch.nn.Module):
     n = (total + 3) // 4 * 4
     dev = params[0].device
     flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
-    flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+    # 4 spare floats behind the gradients: scratch accumulators (e.g. the loss) that must be zeroed
+    # together with the gradients by the single per-step memset of `flat_g.storage`
+    g_store = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+    flat_g = g_store[:n]
+    module._glb_grad_storage = g_store
     off = 0
     with torch.no_grad():
         for p in params:

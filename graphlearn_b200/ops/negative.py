@@ -1,0 +1,206 @@
+"""Negative samplers (K2).
+
+Semantics follow the reference operators:
+  random      uniform over the destination candidates, NOT guaranteed negative
+              (graphlearn/src/core/operator/sampler/random_negative_sampler.cc:46-58)
+  in_degree   dst drawn ~ in-degree, true neighbours of src rejected, strictness
+              dropped after `neg_sampling_retry_times` rounds
+              (in_degree_negative_sampler.cc:61-98)
+  node_weight node drawn ~ node weight, ids of the src batch rejected
+              (node_weight_negative_sampler.cc:61-92)
+  conditional negatives sharing selected attribute values with the positive dst
+              (conditional_negative_sampler.cc:37-156)
+
+B200 design: instead of Vose alias tables (alias_method.cc:57-123) the weighted
+draws use one global inclusive prefix-sum per (shard, distribution) and a
+binary search (``torch.searchsorted`` -> a single vectorised device kernel);
+rejection is a sorted-row membership test against the CSR (rows are fetched
+with the peer-memory full sampler when the source is remote).  The candidate
+universe is the WHOLE destination node type, not only the local shard's dst
+list as in the reference (its quirk listed in SURVEY Appendix B).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .. import config as _config
+from . import gather as G
+from . import sampling as S
+
+
+def _draw_global_uniform(tab, B, k, gen, device):
+    """uniform vids over all rows of all ranks of a node table."""
+    W = tab.rt.world
+    nrows = torch.tensor(tab.nrows, device=device, dtype=torch.int64)
+    cum = torch.cumsum(nrows, 0)
+    total = int(cum[-1].item())
+    if total == 0:
+        return torch.full((B, k), -1, dtype=torch.int64, device=device)
+    u = torch.randint(0, total, (B, k), device=device, generator=gen)
+    owner = torch.searchsorted(cum, u, right=True)
+    row = u - (cum[owner] - nrows[owner])
+    return row * W + owner
+
+
+class _WeightedSampler(object):
+    """draw vids ~ weight over a sharded node table (weights gathered once to every rank: they are
+    [N] floats - small next to the feature table)."""
+
+    def __init__(self, rt, weights_local: torch.Tensor):
+        W = rt.world
+        if W > 1:
+            import torch.distributed as dist
+            sizes = rt.all_gather_object(int(weights_local.numel()))
+            mx = max(sizes)
+            pad = torch.zeros(mx, device=weights_local.device, dtype=torch.float32)
+            pad[:weights_local.numel()] = weights_local.float()
+            allw = [torch.zeros_like(pad) for _ in range(W)]
+            dist.all_gather(allw, pad)
+            parts = [a[:n] for a, n in zip(allw, sizes)]
+        else:
+            sizes = [int(weights_local.numel())]
+            parts = [weights_local.float()]
+        self.sizes = sizes
+        self.W = W
+        w = torch.cat(parts).clamp(min=0).double()
+        self.cum = torch.cumsum(w, 0)
+        self.total = float(self.cum[-1].item()) if w.numel() else 0.0
+        self.offsets = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0).tolist()), device=w.device)
+
+    def draw(self, shape, gen, device):
+        if self.total <= 0:
+            return torch.full(shape, -1, dtype=torch.int64, device=device)
+        u = torch.rand(shape, device=device, generator=gen, dtype=torch.float64) * self.total
+        pos = torch.searchsorted(self.cum, u, right=True).clamp_(max=self.cum.numel() - 1)
+        owner = torch.searchsorted(self.offsets[1:], pos, right=True)
+        row = pos - self.offsets[owner]
+        return row * self.W + owner
+
+
+_CACHE: Dict[tuple, _WeightedSampler] = {}
+
+
+def _is_neighbor(csr, src_v: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
+    """[B, k] bool: cand[b, j] in adj(src[b]).  Rows come from the (peer capable) full sampler."""
+    vals, _, offs = S.sample_full(csr, src_v, cap=0, want_eids=False)
+    B, k = cand.shape
+    counts = offs[1:] - offs[:-1]
+    if vals.numel() == 0:
+        return torch.zeros_like(cand, dtype=torch.bool)
+    seg = torch.repeat_interleave(torch.arange(B, device=cand.device), counts)
+    # hash (segment, value) pairs into sortable keys
+    base = int(max(int(vals.max().item()), int(cand.max().item())) + 2)
+    keys = torch.sort(seg * base + (vals + 1))[0]
+    q = torch.arange(B, device=cand.device)[:, None] * base + (cand + 1)
+    pos = torch.searchsorted(keys, q.reshape(-1)).clamp_(max=keys.numel() - 1)
+    return (keys[pos] == q.reshape(-1)).reshape(B, k)
+
+
+def edge_negative(store, etype: str, src_v: torch.Tensor, k: int, strategy: str, gen, direction: str = "out"):
+    cfg = _config.get()
+    csr = store.edges[etype] if direction == "out" else store.reverse_csr(etype)
+    dst_tab = store.nodes[csr.dst_type]
+    B = int(src_v.numel())
+    dev = src_v.device
+    if strategy == "random":
+        return _draw_global_uniform(dst_tab, B, k, gen, dev)
+    if strategy == "in_degree":
+        key = ("indeg", etype, direction)
+        if key not in _CACHE:
+            if direction == "out":
+                store.reverse_csr(etype)
+                wloc = dst_tab.in_degrees[etype].float()
+            else:
+                wloc = store.nodes[csr.dst_type].out_degrees[etype].float()
+            _CACHE[key] = _WeightedSampler(store.rt, wloc)
+        ws = _CACHE[key]
+        neg = ws.draw((B, k), gen, dev)
+        for _ in range(max(1, cfg.neg_sampling_retry_times)):
+            bad = _is_neighbor(csr, src_v, neg)
+            if not bool(bad.any()):
+                break
+            redraw = ws.draw((B, k), gen, dev)
+            neg = torch.where(bad, redraw, neg)
+        return neg
+    raise ValueError("unknown negative sampling strategy %r" % (strategy,))
+
+
+def node_weight_negative(store, ntype: str, src_v: torch.Tensor, k: int, gen):
+    cfg = _config.get()
+    tab = store.nodes[ntype]
+    B = int(src_v.numel())
+    dev = src_v.device
+    if tab.weights is None:
+        return _draw_global_uniform(tab, B, k, gen, dev)
+    key = ("nw", ntype)
+    if key not in _CACHE:
+        _CACHE[key] = _WeightedSampler(store.rt, tab.weights.local)
+    ws = _CACHE[key]
+    neg = ws.draw((B, k), gen, dev)
+    batch = torch.sort(torch.unique(src_v))[0]
+    for _ in range(max(1, cfg.neg_sampling_retry_times)):
+        pos = torch.searchsorted(batch, neg.reshape(-1)).clamp_(max=max(batch.numel() - 1, 0))
+        bad = (batch[pos] == neg.reshape(-1)).reshape(B, k) if batch.numel() else torch.zeros_like(neg, dtype=torch.bool)
+        if not bool(bad.any()):
+            break
+        neg = torch.where(bad, ws.draw((B, k), gen, dev), neg)
+    return neg
+
+
+def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Tensor, k: int, strategy: str,
+                         cond: dict, gen):
+    """Negatives that share selected int / float attribute columns with the positive dst; each
+    selected column gets ``prop`` of the k slots, the remainder is filled by the base strategy
+    (conditional_negative_sampler.cc:37-156).  True neighbours of src and (unique=True)
+    duplicates are avoided on a best-effort basis like the reference."""
+    csr = store.edges[etype]
+    tab = store.nodes[csr.dst_type]
+    rt = store.rt
+    B = int(src_v.numel())
+    dev = src_v.device
+    base_strategy = strategy if strategy in ("random", "in_degree") else "random"
+    out = edge_negative(store, etype, src_v, k, base_strategy, gen)
+    cols = [("int", c, p) for c, p in zip(cond.get("int_cols", []), cond.get("int_props", []))] + \
+           [("float", c, p) for c, p in zip(cond.get("float_cols", []), cond.get("float_props", []))]
+    if not cols:
+        return out
+    slot = 0
+    for kind, c, prop in cols:
+        n_slots = int(round(prop * k))
+        if n_slots <= 0 or slot >= k:
+            continue
+        n_slots = min(n_slots, k - slot)
+        if kind == "int":
+            attr_all = tab.ints
+            dstv = G.gather_any(rt, attr_all, dst_v, fill=0)[:, c]
+            local_vals = attr_all.local[:, c]
+        else:
+            dstv = G.gather_rows(rt, tab.feats, tab.feat_desc, dst_v, tab.float_dim)[:, c]
+            local_vals = tab.feats.local[:, c].float()
+        # inverted index over the LOCAL shard: sort rows by attribute value, pick uniformly inside
+        # the run of equal values (the reference's AttributeNodesMap)
+        order = torch.argsort(local_vals, stable=True)
+        sv = local_vals[order]
+        lo = torch.searchsorted(sv, dstv.to(sv.dtype), right=False)
+        hi = torch.searchsorted(sv, dstv.to(sv.dtype), right=True)
+        span = (hi - lo)
+        u = torch.rand(B, n_slots, device=dev, generator=gen)
+        pick = lo[:, None] + (u * span[:, None].clamp(min=1).float()).long().clamp_(max=None)
+        pick = torch.minimum(pick, (hi - 1).clamp(min=0)[:, None]).clamp_(min=0, max=max(order.numel() - 1, 0))
+        cand = order[pick] * rt.world + rt.rank if order.numel() else torch.full((B, n_slots), -1, device=dev)
+        ok = (span > 0)[:, None].expand(B, n_slots)
+        bad_nbr = _is_neighbor(csr, src_v, cand) | (cand == dst_v[:, None])
+        use = ok & ~bad_nbr
+        out[:, slot:slot + n_slots] = torch.where(use, cand, out[:, slot:slot + n_slots])
+        slot += n_slots
+    if cond.get("unique"):
+        # replace in-row duplicates by fresh base draws (best effort, one round)
+        srt, idx = torch.sort(out, dim=1)
+        dup = torch.zeros_like(out, dtype=torch.bool)
+        dup[:, 1:] = srt[:, 1:] == srt[:, :-1]
+        dup = torch.zeros_like(out, dtype=torch.bool).scatter(1, idx, dup)
+        fresh = edge_negative(store, etype, src_v, k, base_strategy, gen)
+        out = torch.where(dup, fresh, out)
+    return out

@@ -1,0 +1,257 @@
+"""CPU tests of the public API (Graph / GSL / Dataset / samplers) on closed-form
+fixtures.  They exercise the portable torch path of every op - the same path that
+serves as the oracle for the CUDA kernels."""
+import numpy as np
+import pytest
+import torch
+
+import graphlearn_b200 as gl
+from tests import fixtures as fx
+
+
+@pytest.fixture(scope="module")
+def g(tmp_path_factory):
+    d = fx.write_graph(str(tmp_path_factory.mktemp("graph")))
+    return fx.build_graph(d)
+
+
+def test_decoder_format_bits():
+    d = gl.Decoder(weighted=True, labeled=True, timestamped=True, attr_types=["int", ("string", 10), "float", "string"])
+    assert d.data_format == 2 + 4 + 8 + 16
+    assert (d.int_attr_num, d.float_attr_num, d.string_attr_num) == (2, 1, 1)
+    assert gl.Decoder().data_format == 0
+
+
+def test_stats_and_topology(g):
+    st = g.get_stats()
+    assert st["user"] == [fx.N_USER] and st["item"] == [fx.N_ITEM]
+    assert st["buy"] == [sum((u % 5) + 1 for u in range(fx.N_USER))]
+    topo = g.get_topology()
+    assert topo.get_src_type("buy") == "user" and topo.get_dst_type("buy") == "item"
+
+
+def test_lookup_nodes_closed_form(g):
+    ids = np.array([0, 7, 39, 12])
+    n = g.lookup_nodes("user", ids)
+    assert np.allclose(n.weights, 1.0 + ids)
+    assert (n.labels == ids % 3).all()
+    assert (n.int_attrs == np.stack([ids, ids * 10], 1)).all()
+    assert np.allclose(n.float_attrs[:, 0], ids / 2.0)
+    assert list(n.string_attrs[:, 0]) == ["u%d" % i for i in ids]
+    it = g.lookup_nodes("item", np.array([[3, 4], [5, 59]]))
+    assert it.float_attrs.shape == (2, 2, 4)
+    assert np.allclose(it.float_attrs[1, 1], [fx.item_float(59, j) for j in range(4)])
+
+
+def test_lookup_unknown_id_defaults(g):
+    gl.set_default_label(-7)
+    n = g.lookup_nodes("user", np.array([5, 1000]))
+    assert n.labels[1] == -7 and n.labels[0] == 5 % 3
+    assert n.weights[1] == 0.0
+    assert (n.float_attrs[1] == 0).all()
+
+
+def test_node_sampler_epochs(g):
+    s = g.node_sampler("user", batch_size=16, strategy="by_order")
+    seen = []
+    with pytest.raises(gl.OutOfRangeError):
+        while True:
+            seen.extend(s.get().ids.tolist())
+    assert sorted(seen) == list(range(fx.N_USER))
+    assert len(s.get().ids) == 16            # next epoch restarts
+    sh = g.node_sampler("user", batch_size=10, strategy="shuffle")
+    ep = []
+    with pytest.raises(gl.OutOfRangeError):
+        while True:
+            ep.extend(sh.get().ids.tolist())
+    assert sorted(ep) == list(range(fx.N_USER)) and ep != list(range(fx.N_USER))
+    r = g.node_sampler("user", batch_size=7, strategy="random")
+    for _ in range(20):
+        assert len(r.get().ids) == 7
+
+
+def test_edge_sampler(g):
+    s = g.edge_sampler("buy", batch_size=8, strategy="by_order")
+    e = s.get()
+    adj = fx.u2i_adj()
+    for u, i in zip(e.src_ids, e.dst_ids):
+        assert i in [x[0] for x in adj[u]]
+    assert e.weights.shape == (8,)
+
+
+@pytest.mark.parametrize("strategy", ["random", "random_without_replacement", "topk", "edge_weight", "in_degree"])
+def test_neighbor_sampler_membership(g, strategy):
+    adj = fx.u2i_adj()
+    ids = np.arange(fx.N_USER)
+    layers = g.neighbor_sampler("buy", 4, strategy=strategy).get(ids)
+    n = layers.layer_nodes(1)
+    e = layers.layer_edges(1)
+    assert n.ids.shape == (fx.N_USER, 4)
+    for u in ids:
+        items = [x[0] for x in adj[u]]
+        assert set(n.ids[u].tolist()) <= set(items)
+        if strategy == "topk":       # rows sorted by weight desc; circular padding
+            exp = [x[0] for x in sorted(adj[u], key=lambda t: -t[1])]
+            assert n.ids[u].tolist() == [exp[j % len(exp)] for j in range(4)]
+        if strategy == "random_without_replacement" and len(items) >= 4:
+            assert len(set(e.edge_ids[u].tolist())) == 4
+    assert np.allclose(e.weights.shape, (fx.N_USER, 4))
+
+
+def test_padding_replicate(g):
+    gl.set_padding_mode(gl.REPLICATE)
+    gl.set_default_neighbor_id(-1)
+    layers = g.neighbor_sampler("buy", 6, strategy="topk").get(np.array([0]))     # user 0 has 1 item
+    ids = layers.layer_nodes(1).ids[0]
+    assert ids[0] == 1 and (ids[1:] == -1).all()
+
+
+def test_full_sampler_sparse(g):
+    adj = fx.u2i_adj()
+    layers = g.neighbor_sampler("buy", 0, strategy="full").get(np.array([3, 4, 9]))
+    n = layers.layer_nodes(1)
+    assert n.offsets.tolist() == [len(adj[3]), len(adj[4]), len(adj[9])]
+    parts = [x.ids.tolist() for x in n]
+    for u, p in zip([3, 4, 9], parts):
+        assert sorted(p) == sorted(x[0] for x in adj[u])
+    assert n.dense_shape[0] == 3
+
+
+def test_edge_weight_distribution(g):
+    # user 4 has 5 items with weights 1..5
+    layers = g.neighbor_sampler("buy", 2000, strategy="edge_weight").get(np.array([4]))
+    ids = layers.layer_nodes(1).ids[0]
+    adj = dict(fx.u2i_adj()[4])
+    tot = sum(adj.values())
+    for item, w in adj.items():
+        frac = (ids == item).mean()
+        assert abs(frac - w / tot) < 0.05
+
+
+def test_gsl_two_hop_query(g):
+    q = (g.V("user").batch(8).alias("src")
+          .outV("buy").sample(3).by("random").alias("h1")
+          .outV("sim").sample(2).by("topk").alias("h2").values())
+    ds = gl.Dataset(q)
+    res = ds.next()
+    assert res["src"].ids.shape == (8,)
+    assert res["h1"].ids.shape == (8, 3)
+    assert res["h2"].ids.shape == (24, 2)
+    assert res["h2"].float_attrs.shape == (24, 2, 4)
+    h1 = res["h1"].ids.reshape(-1)
+    # i2i rows are timestamp-ascending (k = 1, 2, 3): topk(2) = first two
+    assert (res["h2"].ids[:, 0] == (h1 + 1) % fx.N_ITEM).all()
+    assert (res["h2"].ids[:, 1] == (h1 + 2) % fx.N_ITEM).all()
+    assert (res["src"].labels == res["src"].ids % 3).all()
+    n = 1
+    with pytest.raises(gl.OutOfRangeError):
+        while True:
+            ds.next(); n += 1
+    assert n == fx.N_USER // 8
+    assert ds.next()["src"].ids.shape == (8,)        # new epoch
+
+
+def test_gsl_edges_and_each(g):
+    q = (g.E("buy").batch(5).alias("e")
+          .each(lambda e: (e.outV().alias("u"), e.inV().alias("i").outV("sim").sample(2).by("random").alias("ii")))
+          .values())
+    res = gl.Dataset(q).next()
+    assert res["e"].src_ids.shape == (5,) and res["e"].weights.shape == (5,)
+    assert (res["u"].ids == res["e"].src_ids).all() and (res["i"].ids == res["e"].dst_ids).all()
+    assert res["ii"].ids.shape == (5, 2)
+
+
+def test_gsl_negative_and_filter(g):
+    q = (g.E("buy").batch(6).alias("e").each(lambda e: (
+        e.outV().alias("u").outNeg("buy").sample(4).by("in_degree").alias("neg"),
+        e.inV().alias("i"))).values())
+    res = gl.Dataset(q).next()
+    adj = fx.u2i_adj()
+    for u, negs in zip(res["u"].ids, res["neg"].ids):
+        assert not (set(negs.tolist()) & {x[0] for x in adj[u]})
+    q2 = g.V("item").batch(10).alias("a").outV("sim").sample(2).by("random").filter("a").alias("b").values()
+    r2 = gl.Dataset(q2).next()
+    assert (r2["b"].ids != r2["a"].ids[:, None]).all()
+
+
+def test_random_walk_and_node2vec(g):
+    for p, qq in ((1.0, 1.0), (0.25, 4.0)):
+        q = g.V("item").batch(12).alias("s").random_walk("sim", 5, p=p, q=qq).alias("w").values()
+        res = gl.Dataset(q).next()
+        w = res["w"].ids
+        assert w.shape == (12, 5)
+        cur = res["s"].ids
+        for s in range(5):
+            d = (w[:, s] - cur) % fx.N_ITEM
+            assert ((d >= 1) & (d <= 3)).all()
+            cur = w[:, s]
+
+
+def test_subgraph_induce(g):
+    sg = g.subgraph_sampler("item", "sim", batch_size=10, strategy="by_order").get()
+    ids = sg.nodes.ids
+    assert ids.tolist() == list(range(10))
+    ei = sg.edge_index
+    pairs = set(zip(ids[ei[0]].tolist(), ids[ei[1]].tolist()))
+    for a in range(10):
+        for k in (1, 2, 3):
+            b = a + k
+            if b < 10:
+                assert (a, b) in pairs and (b, a) in pairs
+    assert ei.shape[1] == 2 * sum(1 for a in range(10) for k in (1, 2, 3) if a + k < 10)
+
+
+def test_degrees_and_aggregation(g):
+    adj = fx.u2i_adj()
+    od = g.out_degrees(np.arange(10), "buy")
+    assert od.tolist() == [len(adj[u]) for u in range(10)]
+    indeg = g.in_degrees(np.arange(fx.N_ITEM), "buy")
+    exp = np.zeros(fx.N_ITEM, int)
+    for u in adj:
+        for i, _ in adj[u]:
+            exp[i] += 1
+    assert indeg.tolist() == exp.tolist()
+    nodes = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
+    for func, f in (("sum", np.sum), ("mean", np.mean), ("max", np.max), ("min", np.min)):
+        got = nodes.embedding_agg(func)
+        ref = f(nodes.float_attrs, axis=1)
+        assert np.allclose(got, ref, atol=1e-5), func
+
+
+def test_undirected_and_masks(tmp_path):
+    d = fx.write_graph(str(tmp_path))
+    g2 = gl.Graph()
+    g2.node(d + "/item.tsv", "item", decoder=gl.Decoder(attr_types=["float"] * 4))
+    g2.node(d + "/item.tsv", "item", decoder=gl.Decoder(attr_types=["float"] * 4), mask=gl.Mask.TRAIN)
+    g2.edge(d + "/i2i.tsv", ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True), directed=False)
+    g2.init(device="cpu")
+    assert g2.get_stats()["sim"] == [2 * 3 * fx.N_ITEM]
+    assert g2.out_degrees(np.array([5]), "sim").tolist() == [6]
+    q = g2.V("item", mask=gl.Mask.TRAIN).batch(4).alias("s").outV("sim").sample(3).by("random").alias("n").values()
+    res = gl.Dataset(q).next()
+    assert res["s"].type == "MASKTRAIN_item" and res["n"].ids.shape == (4, 3)
+    d1 = (res["n"].ids - res["s"].ids[:, None]) % fx.N_ITEM
+    assert (np.isin(d1, [1, 2, 3, fx.N_ITEM - 1, fx.N_ITEM - 2, fx.N_ITEM - 3])).all()
+
+
+def test_in_memory_sources_and_knn():
+    g3 = gl.Graph()
+    n = 200
+    x = np.random.RandomState(0).randn(n, 16).astype(np.float32)
+    g3.node({"ids": np.arange(n), "float_attrs": x}, "p", decoder=gl.Decoder(attr_types=["float"] * 16))
+    g3.edge({"src_ids": np.arange(n), "dst_ids": (np.arange(n) + 1) % n}, ("p", "p", "next"))
+    g3.init(device="cpu")
+    ids, dist = g3.search("p", x[:5], gl.KnnOption(k=3))
+    assert (ids[:, 0] == np.arange(5)).all() and np.allclose(dist[:, 0], 0, atol=1e-4)
+
+
+def test_non_dense_ids(tmp_path):
+    """ids that are not 0..N-1: the id <-> virtual-id map must be transparent."""
+    g4 = gl.Graph()
+    ids = np.array([1000, 5, 77, 123456789012, 42])
+    g4.node({"ids": ids, "labels": np.arange(5)}, "n", decoder=gl.Decoder(labeled=True))
+    g4.edge({"src_ids": ids, "dst_ids": np.roll(ids, 1)}, ("n", "n", "e"))
+    g4.init(device="cpu")
+    lay = g4.neighbor_sampler("e", 2).get(ids)
+    assert (lay.layer_nodes(1).ids[:, 0] == np.roll(ids, 1)).all()
+    assert (g4.lookup_nodes("n", ids).labels == np.arange(5)).all()

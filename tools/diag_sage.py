@@ -16,7 +16,7 @@ def run(M, k, d, n_out, mode="mean", w=None, xs=None, xn=None, tag=""):
     xn = torch.randn(M * k, d, device=dev) if xn is None else xn
     kin = d if mode == "gcn" else 2 * d
     w = torch.randn(n_out, kin, device=dev) / math.sqrt(kin) if w is None else w
-    y = SG.sage_layer(w, None, k=k, mode=mode, relu=False, x_self=xs, x_nbr=xn).float()
+    y = SG.sage_layer(SG.pad_weight(w, d, d, mode), None, k=k, mode=mode, relu=False, x_self=xs, x_nbr=xn).float()
     torch.cuda.synchronize()
     ref = SG.sage_layer_reference(w, None, xs.to(torch.bfloat16).float(), xn, k, mode, False)
     err = (y - ref).abs()
