@@ -27,7 +27,8 @@
 namespace glb {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 512;
+constexpr int kThreads = 1024;         // 32 warps: the gather needs warps in flight, not registers
+constexpr int kEpiWarps = 16;          // warps that drain TMEM in the epilogue
 constexpr int kWarps = kThreads / 32;
 
 enum SageMode : int { kConcatMean = 0, kConcatSum = 1, kGcnMean = 2 };
@@ -53,6 +54,7 @@ struct SageParams {
   int rows_per_cta;           // destination rows gathered by one CTA (<= 128)
   const char* zero_row;       // >= 2 KB of zeros: target of the loads of masked lanes / missing rows
   int wshift_self, wshift_nbr; // log2(world) of each table when it is a power of two, else -1
+  long long* debug_ts;        // optional [grid][16] phase timestamps (clock64) written by thread 0
 };
 
 __device__ __forceinline__ float4 load4_rt(const void* row, int c, int dtype) {
@@ -154,10 +156,15 @@ __device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_save, si
 // lane group (1) already holds the neighbour locators (prefetched during the previous item),
 // (2) issues ALL self + neighbour chunk loads of the batch unconditionally (masked lanes read a
 // zero row), (3) reduces in fp32, (4) writes bf16 into the SW128 A tile.
+#define GLB_TS(i) do { if (p.debug_ts && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
+
 template <int U, int DT>
 __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  GLB_TS(0);
+  // keep every pointer derived from the __shared__ symbol by plain integer offsets so that the
+  // compiler emits LDS/STS (a uintptr_t round trip would demote them to generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int k_total = p.kp_self + p.kp_nbr;
   const int nkb = k_total >> 6;
   uint8_t* sA = smem;
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GLB_TS(1);
 
   // --- weights: TMA bulk copies of the pre-swizzled image, overlapped with the gather
   if (tid == 0) {
@@ -194,12 +202,40 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
       umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
   }
 
-  // --- gather + aggregate -> A tile (bf16, SW128 K-major)
+  // --- phase 0: resolve the tile's neighbour / self ids into ROW POINTERS staged in shared memory
+  //     (coalesced read of nbr_vids[m0*k .. (m0+R)*k); missing rows point at a zero row).  The
+  //     hot loop below is then just  LDS.64 + IADD + LDG  per row chunk.
   constexpr int VEC = Chunk<DT>::kVec;
   const int R = p.rows_per_cta;
   const int m0 = blockIdx.x * R;
-  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
   const int k = p.k;
+  const char** sPtrN = reinterpret_cast<const char**>(bars + 4);       // [R * k]
+  const char** sPtrS = sPtrN + (size_t)R * k;                          // [R]
+  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
+  {
+    const int wshift_n = p.wshift_nbr, wshift_s = p.wshift_self;
+    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+    const int64_t base = (int64_t)m0 * k;
+    const int64_t lim = (int64_t)p.M * k;
+    for (int i = tid; i < R * k; i += kThreads) {
+      const int64_t idx = base + i;
+      uint32_t loc = 0xFFFFFFFFu;
+      if (idx < lim) loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n);
+      sPtrN[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) : p.zero_row;
+    }
+    for (int i = tid; i < R; i += kThreads) {
+      const int m = m0 + i;
+      uint32_t loc = 0xFFFFFFFFu;
+      if (need_self && m < p.M) loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, wshift_s);
+      sPtrS[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) : p.zero_row;
+    }
+  }
+  __syncthreads();
+  GLB_TS(2);
+
+  // --- phase 1: gather + aggregate -> A tile (bf16, SW128 K-major)
+  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
   const int lanes_row = p.kp_nbr / VEC;                 // 16-byte chunks per (half) row: 8..128
   const int lpr = lanes_row < 32 ? lanes_row : 32;      // lanes per row inside a warp
   const int lshift = 31 - __clz(lpr);                   // log2(lpr)
@@ -210,100 +246,69 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   const int sub = lane >> lshift;                       // which row of the item this lane works on
   const int lig = lane & (lpr - 1);                     // lane index inside its row group
   const bool has_self = p.kp_self > 0;
-  const bool need_self = has_self || p.mode == kGcnMean;
-  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
-  const int wshift_n = p.wshift_nbr, wshift_s = p.wshift_self;
   float scale = 1.f;
   if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
   else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
 
-  // locators of one item: lane `lig` < k holds neighbour `lig` of its row (first pass); every lane
-  // holds the self locator of its row
-  auto load_locs = [&](int item, uint32_t& nloc, uint32_t& sloc) {
-    nloc = 0xFFFFFFFFu; sloc = 0xFFFFFFFFu;
-    if (item >= n_items) return;
-    const int rg = n_slices == 1 ? item : item / n_slices;
-    const int r = rg * rpi + sub;
-    const int m = m0 + r;
-    if (r >= R || m >= p.M) return;
-    if (lig < k) {
-      const int64_t idx = (int64_t)m * k + lig;
-      nloc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n);
-    }
-    if (need_self) sloc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, wshift_s);
-  };
-
-  uint32_t nloc_next, sloc_next;
-  load_locs(warp, nloc_next, sloc_next);
   for (int item = warp; item < n_items; item += kWarps) {
     const int rg = n_slices == 1 ? item : item / n_slices;
     const int sl = n_slices == 1 ? 0 : item - rg * n_slices;
     const int r = rg * rpi + sub;
+    if (r >= R) continue;                                // (only when R is not a multiple of rpi)
     const int m = m0 + r;
-    const bool valid = r < R && m < p.M;
-    const uint32_t nloc0 = nloc_next, sloc = sloc_next;
-    load_locs(item + kWarps, nloc_next, sloc_next);      // prefetch: overlaps this item's row loads
     const int chunk = lig + 32 * sl;                     // this lane's 16-byte chunk of the row
     const int f0 = chunk * VEC;                          // first feature of the chunk
-    const bool lane_nbr = f0 < d_nbr;                    // chunk holds real neighbour features
-    const bool lane_self = need_self && f0 < d_self && sloc != 0xFFFFFFFFu;
-    const char* sptr = lane_self ? loc_ptr(p.tself, sloc, self_row_bytes) + (size_t)chunk * 16 : p.zero_row + lane * 16;
-
-    float acc[VEC];
+    const size_t coff = (size_t)chunk * 16;
+    float acc[VEC], sv[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-    Chunk<DT> sraw;
-    bool self_loaded = false;
-    for (int jb = 0; jb < k; jb += lpr) {
-      const int cnt = min(lpr, k - jb);
-      uint32_t ploc = nloc0;
-      if (jb > 0) {        // k > lanes per row: fetch this pass's locators inline
-        ploc = 0xFFFFFFFFu;
-        if (valid && lig < cnt) {
-          const int64_t idx = (int64_t)m * k + jb + lig;
-          ploc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n);
-        }
-      }
-      for (int j0 = 0; j0 < cnt; j0 += U) {
+    for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
+    // lanes whose chunk lies beyond the real feature width skip the loads altogether (their A
+    // columns are the zero K-padding); the others issue self + U neighbour loads back to back
+    if (f0 < d_nbr) {
+      const char* const* ptrs = sPtrN + (size_t)r * k;
+      Chunk<DT> sraw;
+      const bool self_ld = need_self && f0 < d_self;
+      if (self_ld) sraw.load(sPtrS[r] + coff);
+      for (int j0 = 0; j0 < k; j0 += U) {
         Chunk<DT> raw[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = j0 + u;
-          const uint32_t loc = __shfl_sync(0xffffffffu, ploc, j < cnt ? j : 0, lpr);
-          const bool use = (j < cnt) && (loc != 0xFFFFFFFFu) && lane_nbr;
-          raw[u].load(use ? loc_ptr(p.tnbr, loc, nbr_row_bytes) + (size_t)chunk * 16 : p.zero_row + lane * 16);
+          const int j = j0 + u < k ? j0 + u : k - 1;      // tail slots re-read the last row (masked below)
+          raw[u].load(ptrs[j] + coff);
         }
-        if (!self_loaded) { sraw.load(sptr); self_loaded = true; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) raw[u].add_to(acc);
+        for (int u = 0; u < U; ++u)
+          if (j0 + u < k) raw[u].add_to(acc);
       }
-    }
-    if (!self_loaded) sraw.load(sptr);                   // k == 0
-    float sv[VEC];
+      if (self_ld) sraw.add_to(sv);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sv[i] = 0.f;
-    sraw.add_to(sv);
+      for (int i = 0; i < VEC; ++i) {                    // tail masks (dims that are not multiples of VEC)
+        if (f0 + i >= d_self) sv[i] = 0.f;
+        if (f0 + i >= d_nbr) acc[i] = 0.f;
+      }
+    } else if (need_self && f0 < d_self) {               // self wider than the neighbour half (rare)
+      Chunk<DT> sraw;
+      sraw.load(sPtrS[r] + coff);
+      sraw.add_to(sv);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {                      // tail masks (dims that are not multiples of VEC)
-      if (f0 + i >= d_self) sv[i] = 0.f;
-      if (f0 + i >= d_nbr) acc[i] = 0.f;
+      for (int i = 0; i < VEC; ++i) if (f0 + i >= d_self) sv[i] = 0.f;
     }
-    if (r < R) {                                         // rows beyond R belong to another CTA's tile
-      const size_t a_off = (size_t)m * k_total;
-      __nv_bfloat16* asave = (p.a_save && valid) ? p.a_save : nullptr;
-      if (has_self) put_chunk<VEC>(sA, asave, a_off, r, f0, sv);
+    const size_t a_off = (size_t)m * k_total;
+    __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
+    if (has_self) put_chunk<VEC>(sA, asave, a_off, r, f0, sv);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
-      put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
-    }
+    for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
+    put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
   }
+  GLB_TS(3);
   umma::fence_proxy_async_smem();     // generic-proxy st.shared -> visible to tcgen05 (async proxy)
   __syncthreads();
+  GLB_TS(4);
 
   // --- GEMM: one thread issues all MMAs; accumulator lives in TMEM
   if (tid == 0) {
     umma::mbar_wait(bar_w, 0);
+    GLB_TS(5);
     umma::tc_fence_after();
     const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -316,16 +321,20 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
       }
     }
     umma::mma_commit(bar_mma);
+    GLB_TS(6);
   }
   __syncwarp();
   umma::mbar_wait(bar_mma, 0);
+  GLB_TS(7);
   umma::tc_fence_after();
 
-  // --- epilogue: TMEM -> registers -> bias/ReLU -> global
-  {
+  // --- epilogue: TMEM -> registers -> bias/ReLU -> global.  A warp may only touch TMEM lane quarter
+  //     (warp % 4); the column range is split over 8 warp groups (N >= 128) or 4 (N = 64).
+  const int epi_groups = (p.N % 128 == 0) ? 8 : 4;
+  if (warp < 4 * epi_groups) {
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int g = warp >> 2;             // column group
-    const int cols_per_group = p.N >> 2; // multiple of 16
+    const int cols_per_group = p.N / epi_groups;   // multiple of 16
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = row < R && m < p.M;
@@ -374,8 +383,10 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
       }
     }
   }
+  GLB_TS(8);
   umma::tc_fence_before();
   __syncthreads();
+  GLB_TS(9);
   if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -476,7 +487,8 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
                                            const c10::optional<at::Tensor>& bias, int64_t N,
                                            int64_t n_out, bool relu, bool out_bf16, bool save_a, int64_t rows_per_cta,
                                            const c10::optional<at::Tensor>& out_buf,
-                                           const c10::optional<at::Tensor>& a_buf) {
+                                           const c10::optional<at::Tensor>& a_buf,
+                                           const c10::optional<at::Tensor>& debug_ts) {
   TORCH_CHECK(w_img.is_cuda() && w_img.scalar_type() == at::kBFloat16, "w_img must be CUDA bf16");
   c10::cuda::CUDAGuard guard(w_img.device());
   SageParams p;
@@ -491,7 +503,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   TORCH_CHECK(n_out <= N && n_out >= 1);
   TORCH_CHECK(w_img.numel() == (int64_t)k_total * N, "weight image size mismatch: expected ", k_total * N);
   TORCH_CHECK((reinterpret_cast<uintptr_t>(w_img.data_ptr()) & 15) == 0, "weight image must be 16 B aligned");
-  size_t smem = (size_t)sage_smem_bytes(k_total, N);
+  size_t smem = (size_t)sage_smem_bytes(k_total, N);   // + locator staging, added below
   TORCH_CHECK(smem <= 232448, "tile does not fit in shared memory (", smem, " B); use the unfused path");
   at::Tensor sv, nv, b;
   p.self_vids = nullptr; p.nbr_vids = nullptr; p.bias = nullptr;
@@ -536,11 +548,23 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   int R = kTileM;
   if (rows_per_cta > 0) R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (rows_per_cta + 7) / 8 * 8));
   else {
+    // balance whole waves: w = number of 148-CTA waves needed at <= 128 rows per CTA, then the
+    // smallest R (multiple of 8) that still fits M into w waves
     const int64_t sms = 148;
-    int64_t want = (M + sms - 1) / sms;
+    int64_t waves = (M + sms * kTileM - 1) / (sms * kTileM);
+    int64_t want = (M + sms * waves - 1) / (sms * waves);
     R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (want + 7) / 8 * 8));
   }
+  // shared-memory row-pointer staging: 8 B per (row, neighbour) + 8 B per row; shrink R until it fits
+  while (R > 8 && smem + 32 + (size_t)R * (k + 1) * 8 > 232448) R -= 8;
+  TORCH_CHECK(smem + 32 + (size_t)R * (k + 1) * 8 <= 232448, "fan-out too large for the fused kernel's id staging");
+  smem += 32 + (size_t)R * (k + 1) * 8;
   p.rows_per_cta = R;
+  p.debug_ts = nullptr;
+  if (debug_ts.has_value()) {
+    TORCH_CHECK(debug_ts->scalar_type() == at::kLong && debug_ts->numel() >= (int64_t)((M + R - 1) / R) * 16);
+    p.debug_ts = reinterpret_cast<long long*>(debug_ts->data_ptr<int64_t>());
+  }
   TORCH_CHECK(p.tself.dtype == p.tnbr.dtype, "fused SAGE layer needs self / neighbour tables of the same dtype");
   TORCH_CHECK(p.kp_self == 0 || p.kp_self == p.kp_nbr, "fused SAGE layer needs equally padded self / neighbour dims");
   auto log2_or_neg = [](int w) { int s = 0; while ((1 << s) < w) ++s; return (1 << s) == w ? s : -1; };
@@ -556,7 +580,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   }
   unsigned grid = (unsigned)((M + R - 1) / R);
   auto stream = at::cuda::getCurrentCUDAStream();
-  const int u = k <= 4 ? 4 : k <= 8 ? 8 : 13;
+  const int u = k <= 4 ? 4 : (k % 5 == 0 || k > 12) ? 5 : 6;
   const int dt = p.tnbr.dtype;
 #define LAUNCH(UU, DD)                                                                            \
   do {                                                                                            \
@@ -568,8 +592,8 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
     }                                                                                             \
     sage_fused_fwd_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                           \
   } while (0)
-  if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 8) LAUNCH(8, 0); else LAUNCH(13, 0); }
-  else         { if (u == 4) LAUNCH(4, 1); else if (u == 8) LAUNCH(8, 1); else LAUNCH(13, 1); }
+  if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
+  else         { if (u == 4) LAUNCH(4, 1); else if (u == 5) LAUNCH(5, 1); else LAUNCH(6, 1); }
 #undef LAUNCH
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, save_a ? a_save : at::Tensor()};

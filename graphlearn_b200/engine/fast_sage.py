@@ -135,13 +135,13 @@ class FastSageTrainer:
                 if l == 1:
                     d = self.nodes.feat_desc
                     C.sage_fused_forward(d, hops[i], d, hops[i + 1], self.n[i], k, mode, img, c.bias, N, c.out_dim,
-                                         not last, not last, True, 0, out, a)
+                                         not last, not last, True, 0, out, a, None)
                 else:
                     po = self.seg_off[l - 2]
                     xs = self.H[l - 2][po[i]:po[i + 1]]
                     xn = self.H[l - 2][po[i + 1]:po[i + 2]]
                     C.sage_fused_forward(local_table_desc(xs), None, local_table_desc(xn), None, self.n[i], k, mode,
-                                         img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a)
+                                         img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a, None)
         # ---- loss (seeds are owned locally: labels are a local lookup)
         top = self.convs[L - 1]
         C.softmax_ce(self.H[L - 1], self.nodes.labels.local, self.seeds, self.rt.world, self.loss, self.dZ[L - 1],

@@ -12,7 +12,8 @@ from graphlearn_b200.store.synthetic import make_sharded_graph
 small = os.environ.get("GLB_SMALL", "0") == "1"
 rt = init()
 shape = dict(num_nodes=2_449_029, num_edges=123_718_280) if not small else dict(num_nodes=200_000, num_edges=5_000_000)
-nodes, csr = make_sharded_graph(rt, feat_dim=100, num_classes=47, seed=0, **shape)
+fdt = torch.bfloat16 if os.environ.get('GLB_FDT','fp32')=='bf16' else torch.float32
+nodes, csr = make_sharded_graph(rt, feat_dim=100, num_classes=47, seed=0, feature_dtype=fdt, **shape)
 model = EgoGraphSAGE(100, 256, 47, 2).to(rt.device)
 T = SageTrainer if os.environ.get('GLB_ENGINE','fast')=='autograd' else FastSageTrainer
 tr = T(rt, nodes, csr, model, [25, 10], 1024, use_cuda_graph=False)
