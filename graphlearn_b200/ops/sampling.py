@@ -209,7 +209,11 @@ def sample_full(csr: CsrShard, src_vids: torch.Tensor, cap: int = 0, want_eids: 
     B = int(src.numel())
     offsets = torch.zeros(B + 1, dtype=torch.int64, device=src.device)
     offsets[1:] = torch.cumsum(deg, 0)
-    maxd = int(deg.max().item()) if B > 0 else 0
+    maxd_t = deg.max().reshape(1) if B > 0 else torch.zeros(1, dtype=torch.int64, device=src.device)
+    if W > 1:       # every owner must answer with the same row width
+        import torch.distributed as dist
+        dist.all_reduce(maxd_t, op=dist.ReduceOp.MAX)
+    maxd = int(maxd_t.item())
     if maxd == 0:
         z = torch.zeros(0, dtype=torch.int64, device=src.device)
         return z, (z.clone() if want_eids else None), offsets

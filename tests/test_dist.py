@@ -1,0 +1,41 @@
+"""Multi-rank tests: the same SPMD worker runs on CPU (gloo, world_size 2 - portable
+partition/all-to-all path) and on GPUs (NCCL bootstrap + peer-memory kernels)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(nproc, port, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    env["PYTHONPATH"] = ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0 and "DIST_WORKER_OK" in out, out[-4000:]
+
+
+def test_two_ranks_cpu_gloo():
+    _run(2, 29641, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": ""})
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+def test_two_ranks_gpu_peer():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(2, 29642, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+def test_eight_ranks_gpu_peer():
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    _run(8, 29643, {})
