@@ -19,50 +19,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
 
 
-def _gen_data(root, n_nodes, n_edges, dim, classes, seed=0):
-    """ogbn-products-shaped random graph as the reference's TSV dialect (cached on disk)."""
-    import numpy as np
-    import pyarrow as pa
-    import pyarrow.csv as pacsv
-    os.makedirs(root, exist_ok=True)
-    done = os.path.join(root, "DONE")
-    node_f, edge_f = os.path.join(root, "node.tsv"), os.path.join(root, "edge.tsv")
-    if os.path.exists(done):
-        return node_f, edge_f
-    rs = np.random.RandomState(seed)
-    lut = np.array(["%.2f" % (i / 100.0) for i in range(-400, 401)], dtype=object)
-    with open(node_f, "w") as f:
-        f.write("id:int64\tlabel:int32\tfeature:string\n")
-        step = 100_000
-        for s in range(0, n_nodes, step):
-            e = min(n_nodes, s + step)
-            q = np.clip((rs.randn(e - s, dim) * 100).astype(np.int64), -400, 400) + 400
-            lab = rs.randint(0, classes, e - s)
-            strs = lut[q]
-            f.write("".join("%d\t%d\t%s\n" % (s + i, lab[i], ":".join(strs[i])) for i in range(e - s)))
-    # skewed out-degree like our synthetic generator
-    w = np.exp(rs.randn(n_nodes))
-    deg = np.floor(w / w.sum() * n_edges).astype(np.int64)
-    rem = n_edges - int(deg.sum())
-    deg += np.bincount(rs.randint(0, n_nodes, rem), minlength=n_nodes)
-    src = np.repeat(np.arange(n_nodes, dtype=np.int64), deg)
-    dst = rs.randint(0, n_nodes, n_edges).astype(np.int64)
-    tbl = pa.table({"src_id:int64": src, "dst_id:int64": dst})
-    pacsv.write_csv(tbl, edge_f, write_options=pacsv.WriteOptions(delimiter="\t", quoting_style="none"))
-    open(done, "w").write("ok")
-    return node_f, edge_f
-
-
 def main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    try:
-        sys.path.insert(0, REF)
-        import graphlearn as gl
-    except Exception as e:
+    if not os.path.isdir(os.path.join(REF, "graphlearn")):
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "cannot import baseline/_ref graphlearn: %r" % (e,)}))
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed (see DESIGN.md)"}))
         return
+    import subprocess
+    from multiprocessing import shared_memory
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -81,34 +46,55 @@ def main(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl" if use_cuda else "gloo")
     root = os.environ.get("GLB_REF_DATA", "/tmp/glb_ref_data_%d_%d" % (shape["n_nodes"], shape["n_edges"]))
+    sampler = os.path.join(HERE, "ref_sampler.py")
+    common = [sys.executable, sampler, "--root", root, "--nodes", str(shape["n_nodes"]), "--edges",
+              str(shape["n_edges"]), "--dim", str(dim), "--classes", str(classes), "--batch", str(B)]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
     t0 = time.time()
     if rank == 0:
-        _gen_data(root, dim=dim, classes=classes, **shape)
+        subprocess.run(common + ["--gen-only"], check=True, env=env, stdout=subprocess.DEVNULL)
+    tracker = os.path.join(root, "tracker_%s" % os.environ.get("MASTER_PORT", "0"))
     if world > 1:
-        dist.barrier()
-    node_f, edge_f = os.path.join(root, "node.tsv"), os.path.join(root, "edge.tsv")
-    gen_s = time.time() - t0
-
-    # ---- the reference's own graph engine (local mode for N=1, worker mode with a FS tracker for N>1)
-    t0 = time.time()
-    g = gl.Graph() \
-        .node(node_f, "i", decoder=gl.Decoder(labeled=True, attr_types=["float"] * dim)) \
-        .edge(edge_f, ("i", "i", "e"), decoder=gl.Decoder())
-    if world == 1:
-        g.init()
-    else:
-        tracker = os.path.join(root, "tracker_%s" % os.environ.get("MASTER_PORT", "0"))
         if rank == 0:
             import shutil
             shutil.rmtree(tracker, ignore_errors=True)
             os.makedirs(tracker, exist_ok=True)
         dist.barrier()
-        g.init(task_index=rank, task_count=world, tracker=tracker)
-    load_s = time.time() - t0
-    q = g.V("i").batch(B).shuffle(traverse=True).alias("src") \
-         .outV("e").sample(fanouts[0]).by("random").alias("h1") \
-         .outV("e").sample(fanouts[1]).by("random").alias("h2").values()
-    ds = gl.Dataset(q, window=10)
+    gen_s = time.time() - t0
+    # ---- the reference engine lives in its own interpreter (see ref_sampler.py for why)
+    base_port = int(os.environ.get("MASTER_PORT", "29500")) + 211
+    hosts = ",".join("127.0.0.1:%d" % (base_port + r) for r in range(world)) if world > 1 else ""
+    child = subprocess.Popen(common + ["--rank", str(rank), "--world", str(world), "--tracker", tracker,
+                                       "--hosts", hosts],
+                             stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1, env=env)
+    line = ""
+    while not line.startswith("SHM"):
+        line = child.stdout.readline()
+        if not line:
+            raise RuntimeError("reference sampler process died during graph load")
+    _, shm_name, slot_bytes, load_s = line.split()
+    slot_bytes, load_s = int(slot_bytes), float(load_s)
+    shm = shared_memory.SharedMemory(name=shm_name)
+    n0, n1, n2 = B, B * fanouts[0], B * fanouts[0] * fanouts[1]
+    fbytes = (n0 + n1 + n2) * dim * 4
+
+    def next_batch():
+        while True:
+            l = child.stdout.readline()
+            if not l:
+                raise RuntimeError("reference sampler process died")
+            if l.startswith("READY"):
+                s = int(l.split()[1])
+                break
+        off = s * slot_bytes
+        x = np.ndarray((n0 + n1 + n2, dim), dtype=np.float32, buffer=shm.buf, offset=off)
+        y = np.ndarray((B,), dtype=np.int64, buffer=shm.buf, offset=off + fbytes)
+        return s, x, y
+
+    def free_slot(s):
+        child.stdin.write("FREE %d\n" % s)
+        child.stdin.flush()
 
     class SAGE(nn.Module):
         def __init__(self):
@@ -132,20 +118,14 @@ def main(args):
     h2d = [0]
 
     def step():
-        while True:
-            try:
-                r = ds.next()
-                break
-            except gl.OutOfRangeError:
-                continue
-        xs = [r["src"].float_attrs.reshape(-1, dim), r["h1"].float_attrs.reshape(-1, dim),
-              r["h2"].float_attrs.reshape(-1, dim)]
-        y = r["src"].labels.reshape(-1).astype(np.int64)
-        h2d[0] = sum(x.nbytes for x in xs) + y.nbytes
-        xt = [torch.from_numpy(np.ascontiguousarray(x)).to(dev, non_blocking=True) for x in xs]
-        yt = torch.from_numpy(y).to(dev, non_blocking=True)
+        s, x, y = next_batch()
+        h2d[0] = x.nbytes + y.nbytes
+        xt = torch.from_numpy(x).to(dev, non_blocking=False)
+        yt = torch.from_numpy(y).to(dev, non_blocking=False)
+        free_slot(s)
+        x0, x1, x2 = xt[:n0], xt[n0:n0 + n1], xt[n0 + n1:]
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_cuda):
-            logits = model(*xt)
+            logits = model(x0, x1, x2)
         loss = F.cross_entropy(logits.float(), yt)
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -190,10 +170,12 @@ def main(args):
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": 4},
             "gpu_launches": 0, "final_loss": loss}))
     try:
-        ds.close()
+        child.stdin.write("STOP\n")
+        child.stdin.flush()
+        child.wait(timeout=60)
     except Exception:
-        pass
-    g.close()
+        child.kill()
+    shm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

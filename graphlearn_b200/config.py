@@ -63,6 +63,7 @@ class Config:
     feature_dtype: str = "fp32"          # fp32 | bf16   storage dtype of float attribute tables in HBM
     loader_threads: int = max(1, (os.cpu_count() or 8) // 2)
     use_peer_kernels: bool = True        # False -> torch.distributed (NCCL/gloo) baseline path
+    sage_gather_mode: int = int(os.environ.get("GLB_SAGE_GATHER_MODE", "0"))   # fused SAGE kernel: 0 auto, 1 register loads, 2 TMA ring
     seed: int = 0
     actor_enabled: bool = False
 
@@ -127,6 +128,7 @@ set_feature_dtype = _setter("feature_dtype", str)
 set_loader_threads = _setter("loader_threads", int)
 set_use_peer_kernels = _setter("use_peer_kernels", bool)
 set_seed = _setter("seed", int)
+set_sage_gather_mode = _setter("sage_gather_mode", int)
 
 
 def set_inner_threadnum(n):

@@ -24,7 +24,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor&, const c10::optiona
                                            const c10::optional<at::Tensor>&, int64_t, int64_t, int64_t,
                                            const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t,
                                            bool, bool, bool, int64_t, const c10::optional<at::Tensor>&,
-                                           const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&);
+                                           const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t);
 // train_ops.cu
 void softmax_ce(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, const at::Tensor&,
                 const at::Tensor&, const c10::optional<at::Tensor>&);

@@ -146,6 +146,65 @@ __device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_save, si
   }
 }
 
+// epilogue shared by both kernel variants: TMEM -> registers -> bias/ReLU -> global
+__device__ __forceinline__ void sage_epilogue(const SageParams& p, uint32_t tmem_base, int m0, int R, int warp, int lane) {
+  // --- epilogue: TMEM -> registers -> bias/ReLU -> global.  A warp may only touch TMEM lane quarter
+  //     (warp % 4); the column range is split over 8 warp groups (N >= 128) or 4 (N = 64).
+  const int epi_groups = (p.N % 128 == 0) ? 8 : 4;
+  if (warp < 4 * epi_groups) {
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int g = warp >> 2;             // column group
+    const int cols_per_group = p.N / epi_groups;   // multiple of 16
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = row < R && m < p.M;
+    for (int c0 = 0; c0 < cols_per_group; c0 += 16) {
+      const int n0 = g * cols_per_group + c0;
+      uint32_t v[16];
+      umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
+      umma::tmem_ld_wait();
+      if (row_ok && n0 < p.n_out) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = __uint_as_float(v[i]);
+          if (p.bias && n0 + i < p.n_out) x += __ldg(p.bias + n0 + i);
+          if (p.relu) x = fmaxf(x, 0.f);
+          f[i] = x;
+        }
+        const bool full = (n0 + 16 <= p.n_out);
+        if (p.out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_stride + n0;
+          if (full && (p.out_stride & 7) == 0) {
+            uint4 a, b;
+            a.x = pack_bf16x2(f[0], f[1]); a.y = pack_bf16x2(f[2], f[3]);
+            a.z = pack_bf16x2(f[4], f[5]); a.w = pack_bf16x2(f[6], f[7]);
+            b.x = pack_bf16x2(f[8], f[9]); b.y = pack_bf16x2(f[10], f[11]);
+            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+            reinterpret_cast<uint4*>(o)[0] = a;
+            reinterpret_cast<uint4*>(o)[1] = b;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + i < p.n_out) o[i] = __float2bfloat16(f[i]);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_stride + n0;
+          if (full && (p.out_stride & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + i < p.n_out) o[i] = f[i];
+          }
+        }
+      }
+    }
+  }
+}
+
 // U  = neighbour row loads kept in flight per lane (one batch)
 // DT = storage dtype of the self AND neighbour tables (0 fp32, 1 bf16)
 //
@@ -156,6 +215,8 @@ __device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_save, si
 // lane group (1) already holds the neighbour locators (prefetched during the previous item),
 // (2) issues ALL self + neighbour chunk loads of the batch unconditionally (masked lanes read a
 // zero row), (3) reduces in fp32, (4) writes bf16 into the SW128 A tile.
+constexpr int kMaxSlots = 64;
+
 #define GLB_TS(i) do { if (p.debug_ts && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
 template <int U, int DT>
@@ -209,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   const int R = p.rows_per_cta;
   const int m0 = blockIdx.x * R;
   const int k = p.k;
-  const char** sPtrN = reinterpret_cast<const char**>(bars + 4);       // [R * k]
+  const char** sPtrN = reinterpret_cast<const char**>(bars + 4 + 2 * kMaxSlots);   // [R * k]
   const char** sPtrS = sPtrN + (size_t)R * k;                          // [R]
   const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
   {
@@ -328,61 +389,191 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   GLB_TS(7);
   umma::tc_fence_after();
 
-  // --- epilogue: TMEM -> registers -> bias/ReLU -> global.  A warp may only touch TMEM lane quarter
-  //     (warp % 4); the column range is split over 8 warp groups (N >= 128) or 4 (N = 64).
-  const int epi_groups = (p.N % 128 == 0) ? 8 : 4;
-  if (warp < 4 * epi_groups) {
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int g = warp >> 2;             // column group
-    const int cols_per_group = p.N / epi_groups;   // multiple of 16
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = row < R && m < p.M;
-    for (int c0 = 0; c0 < cols_per_group; c0 += 16) {
-      const int n0 = g * cols_per_group + c0;
-      uint32_t v[16];
-      umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
-      umma::tmem_ld_wait();
-      if (row_ok && n0 < p.n_out) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = __uint_as_float(v[i]);
-          if (p.bias && n0 + i < p.n_out) x += __ldg(p.bias + n0 + i);
-          if (p.relu) x = fmaxf(x, 0.f);
-          f[i] = x;
-        }
-        const bool full = (n0 + 16 <= p.n_out);
-        if (p.out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_stride + n0;
-          if (full && (p.out_stride & 7) == 0) {
-            uint4 a, b;
-            a.x = pack_bf16x2(f[0], f[1]); a.y = pack_bf16x2(f[2], f[3]);
-            a.z = pack_bf16x2(f[4], f[5]); a.w = pack_bf16x2(f[6], f[7]);
-            b.x = pack_bf16x2(f[8], f[9]); b.y = pack_bf16x2(f[10], f[11]);
-            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-            reinterpret_cast<uint4*>(o)[0] = a;
-            reinterpret_cast<uint4*>(o)[1] = b;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (n0 + i < p.n_out) o[i] = __float2bfloat16(f[i]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_stride + n0;
-          if (full && (p.out_stride & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (n0 + i < p.n_out) o[i] = f[i];
-          }
-        }
-      }
+  sage_epilogue(p, tmem_base, m0, R, warp, lane);
+  GLB_TS(8);
+  umma::tc_fence_before();
+  __syncthreads();
+  GLB_TS(9);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-gather variant.  Same math and same tile / MMA / epilogue as above, but the feature rows are
+// pulled by the TMA engine (cp.async.bulk, one bulk copy per row, completion on mbarriers) into a
+// shared-memory ring instead of through registers: ~128 KB of row fetches stay in flight per SM
+// with zero register cost, which is what hides HBM *and* NVLink latency (peer rows cost ~2 us).
+// The ring lives in the weight region: W is only needed after the gather, so it is fetched (one
+// more bulk copy, from L2) once the ring has drained.
+//   warp 0            producer: per destination row issues (1 + k) row copies into the next slot
+//   warps 1..31       consumers: wait for a slot, reduce the k neighbour rows (fp32), write the bf16
+//                     A-tile chunks (+ the row-major copy saved for backward), release the slot
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 1) sage_fused_tma_kernel(const SageParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  GLB_TS(0);
+  const int k_total = p.kp_self + p.kp_nbr;
+  const int nkb = k_total >> 6;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);                     // ring during the gather, W afterwards
+  const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;
+  const uint32_t w_bytes = (uint32_t)nkb * w_kb_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)w_bytes);
+  uint64_t* bar_w = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = bars + 4;                                           // [kMaxSlots]
+  uint64_t* empty = full + kMaxSlots;                                  // [kMaxSlots]
+  const char** sPtrN = reinterpret_cast<const char**>(empty + kMaxSlots);
+  const int R = p.rows_per_cta;
+  const int k = p.k;
+  const char** sPtrS = sPtrN + (size_t)R * k;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  constexpr int VEC = Chunk<DT>::kVec;
+  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
+  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+  // bytes actually copied per row: the real features rounded up to 16 B (never more than the stride)
+  const uint32_t nbr_copy = min(nbr_row_bytes, (uint32_t)((p.tnbr.dim * (DT == 0 ? 4 : 2) + 15) & ~15));
+  const uint32_t self_copy = need_self ? min(self_row_bytes, (uint32_t)((p.tself.dim * (DT == 0 ? 4 : 2) + 15) & ~15)) : 0u;
+  const uint32_t slot_bytes = self_copy + (uint32_t)k * nbr_copy;
+  const int S = min((int)(w_bytes / slot_bytes), kMaxSlots);
+
+  if (tid == 0) {
+    umma::mbar_init(bar_w, 1);
+    umma::mbar_init(bar_mma, 1);
+    for (int s = 0; s < S; ++s) { umma::mbar_init(full + s, 1); umma::mbar_init(empty + s, 1); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    umma::tmem_relinquish();
+  }
+  // resolve ids -> row pointers (coalesced), as in the register variant
+  const int m0 = blockIdx.x * R;
+  {
+    const int64_t base = (int64_t)m0 * k;
+    const int64_t lim = (int64_t)p.M * k;
+    for (int i = tid; i < R * k; i += kThreads) {
+      const int64_t idx = base + i;
+      uint32_t loc = 0xFFFFFFFFu;
+      if (idx < lim) loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr);
+      sPtrN[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) : p.zero_row;
+    }
+    for (int i = tid; i < R; i += kThreads) {
+      const int m = m0 + i;
+      uint32_t loc = 0xFFFFFFFFu;
+      if (need_self && m < p.M) loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self);
+      sPtrS[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) : p.zero_row;
     }
   }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  GLB_TS(2);
+
+  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
+  const bool has_self = p.kp_self > 0;
+  float scale = 1.f;
+  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
+  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
+
+  if (warp == 0) {
+    // ===== producer: one slot per destination row =====
+    for (int i = 0; i < R; ++i) {
+      const int s = i % S, turn = i / S;
+      if (turn > 0) umma::mbar_wait(empty + s, (uint32_t)((turn - 1) & 1));
+      uint8_t* slot = sW + (size_t)s * slot_bytes;
+      if (lane == 0) umma::mbar_arrive_expect_tx(full + s, slot_bytes);
+      __syncwarp();
+      if (need_self && lane == 0) umma::bulk_g2s(slot, sPtrS[i], self_copy, full + s);
+      for (int j = lane; j < k; j += 32)
+        umma::bulk_g2s(slot + self_copy + (size_t)j * nbr_copy, sPtrN[(size_t)i * k + j], nbr_copy, full + s);
+    }
+  } else {
+    // ===== consumers =====
+    // Slot s is always drained by the SAME consumer warp (s % C) in increasing turn order: an
+    // mbarrier only distinguishes the parity of a phase, so two warps waiting for different turns
+    // of one slot would alias.
+    const int nchunks = p.kp_nbr / VEC;                  // 16-byte chunks per K half
+    const int C = kWarps - 1, c = warp - 1;
+    for (int turn = 0; turn * S < R; ++turn)
+    for (int s = c; s < S; s += C) {
+      const int i = turn * S + s;
+      if (i >= R) break;
+      umma::mbar_wait(full + s, (uint32_t)(turn & 1));
+      const uint8_t* slot = sW + (size_t)s * slot_bytes;
+      const int m = m0 + i;
+      const size_t a_off = (size_t)m * k_total;
+      __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
+      for (int chunk = lane; chunk < nchunks; chunk += 32) {
+        const int f0 = chunk * VEC;
+        float acc[VEC], sv[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { acc[q] = 0.f; sv[q] = 0.f; }
+        if (f0 < d_nbr) {
+          const uint8_t* np = slot + self_copy + (size_t)chunk * 16;
+          for (int j = 0; j < k; ++j) {
+            Chunk<DT> c;
+            c.v = *reinterpret_cast<const decltype(c.v)*>(np + (size_t)j * nbr_copy);
+            c.add_to(acc);
+          }
+        }
+        if (need_self && f0 < d_self) {
+          Chunk<DT> c;
+          c.v = *reinterpret_cast<const decltype(c.v)*>(slot + (size_t)chunk * 16);
+          c.add_to(sv);
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          if (f0 + q >= d_self) sv[q] = 0.f;
+          if (f0 + q >= d_nbr) acc[q] = 0.f;
+        }
+        if (has_self) put_chunk<VEC>(sA, asave, a_off, i, f0, sv);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = (acc[q] + (p.mode == kGcnMean ? sv[q] : 0.f)) * scale;
+        put_chunk<VEC>(sA, asave, a_off, i, p.kp_self + f0, acc);
+      }
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(empty + s);
+    }
+  }
+  GLB_TS(3);
+  umma::fence_proxy_async_smem();     // A-tile st.shared visible to tcgen05; ring reads ordered before the W copy
+  __syncthreads();
+  GLB_TS(4);
+
+  // --- weights into the (now idle) ring region, then the MMAs
+  if (tid == 0) {
+    umma::mbar_arrive_expect_tx(bar_w, w_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_img);
+    for (int kb = 0; kb < nkb; ++kb)
+      umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
+    umma::mbar_wait(bar_w, 0);
+    GLB_TS(5);
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
+      const uint32_t b_base = umma::smem_u32(sW + (size_t)kb * w_kb_bytes);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma::mma_bf16_ss(tmem_base, umma::make_desc_sw128(a_base + k4 * 32),
+                          umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
+    }
+    umma::mma_commit(bar_mma);
+    GLB_TS(6);
+  }
+  __syncwarp();
+  umma::mbar_wait(bar_mma, 0);
+  GLB_TS(7);
+  umma::tc_fence_after();
+  sage_epilogue(p, tmem_base, m0, R, warp, lane);
   GLB_TS(8);
   umma::tc_fence_before();
   __syncthreads();
@@ -488,7 +679,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
                                            int64_t n_out, bool relu, bool out_bf16, bool save_a, int64_t rows_per_cta,
                                            const c10::optional<at::Tensor>& out_buf,
                                            const c10::optional<at::Tensor>& a_buf,
-                                           const c10::optional<at::Tensor>& debug_ts) {
+                                           const c10::optional<at::Tensor>& debug_ts, int64_t gather_mode) {
   TORCH_CHECK(w_img.is_cuda() && w_img.scalar_type() == at::kBFloat16, "w_img must be CUDA bf16");
   c10::cuda::CUDAGuard guard(w_img.device());
   SageParams p;
@@ -556,9 +747,10 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
     R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (want + 7) / 8 * 8));
   }
   // shared-memory row-pointer staging: 8 B per (row, neighbour) + 8 B per row; shrink R until it fits
-  while (R > 8 && smem + 32 + (size_t)R * (k + 1) * 8 > 232448) R -= 8;
-  TORCH_CHECK(smem + 32 + (size_t)R * (k + 1) * 8 <= 232448, "fan-out too large for the fused kernel's id staging");
-  smem += 32 + (size_t)R * (k + 1) * 8;
+  const size_t bar_bytes = 32 + 2 * kMaxSlots * 8;          // control words + TMA ring barriers
+  while (R > 8 && smem + bar_bytes + (size_t)R * (k + 1) * 8 > 232448) R -= 8;
+  TORCH_CHECK(smem + bar_bytes + (size_t)R * (k + 1) * 8 <= 232448, "fan-out too large for the fused kernel's id staging");
+  smem += bar_bytes + (size_t)R * (k + 1) * 8;
   p.rows_per_cta = R;
   p.debug_ts = nullptr;
   if (debug_ts.has_value()) {
@@ -582,19 +774,34 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   auto stream = at::cuda::getCurrentCUDAStream();
   const int u = k <= 4 ? 4 : (k % 5 == 0 || k > 12) ? 5 : 6;
   const int dt = p.tnbr.dtype;
-#define LAUNCH(UU, DD)                                                                            \
+  // gather_mode: 1 = register-staged loads, 2 = TMA bulk copies into the shared-memory ring,
+  // 0 = auto = register-staged.  MEASURED (profiles/): per-row cp.async.bulk copies of 400 B cost
+  // ~110 cycles each in the TMA unit (1408 copies -> 153 k cycles per 128-row tile, 0.76 TB/s), 4x
+  // slower than the register path (36 k cycles) - the ring variant is kept for wide rows only.
+  const size_t slot_bytes = (size_t)(k + 1) * (size_t)p.tnbr.stride * (dt == 0 ? 4 : 2);
+  const bool tma_ok = k >= 1 && slot_bytes <= (size_t)k_total / 64 * N * 128;
+  bool use_tma = gather_mode == 2;
+  use_tma = use_tma && tma_ok;
+#define SET_ATTR(KERNEL)                                                                          \
   do {                                                                                            \
     static bool attr_done = false;                                                                \
     if (!attr_done) {                                                                             \
-      C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_fwd_kernel<UU, DD>,                          \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));  \
+      C10_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
       attr_done = true;                                                                           \
     }                                                                                             \
+  } while (0)
+#define LAUNCH(UU, DD)                                                                            \
+  do {                                                                                            \
+    SET_ATTR((sage_fused_fwd_kernel<UU, DD>));                                                    \
     sage_fused_fwd_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                           \
   } while (0)
-  if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
-  else         { if (u == 4) LAUNCH(4, 1); else if (u == 5) LAUNCH(5, 1); else LAUNCH(6, 1); }
+  if (use_tma) {
+    if (dt == 0) { SET_ATTR(sage_fused_tma_kernel<0>); sage_fused_tma_kernel<0><<<grid, kThreads, smem, stream>>>(p); }
+    else         { SET_ATTR(sage_fused_tma_kernel<1>); sage_fused_tma_kernel<1><<<grid, kThreads, smem, stream>>>(p); }
+  } else if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
+  else                { if (u == 4) LAUNCH(4, 1); else if (u == 5) LAUNCH(5, 1); else LAUNCH(6, 1); }
 #undef LAUNCH
+#undef SET_ATTR
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, save_a ? a_save : at::Tensor()};
 }

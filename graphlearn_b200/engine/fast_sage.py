@@ -36,7 +36,8 @@ from ..store.shards import CsrShard, NodeTable
 class FastSageTrainer:
     def __init__(self, rt: Runtime, nodes: NodeTable, csr: CsrShard, model, fanouts: Sequence[int], batch_size: int,
                  lr: float = 3e-3, strategy: str = "random", use_cuda_graph: bool = True, allreduce: str = "peer",
-                 seed: int = 0):
+                 seed: int = 0, gather_mode: int = 0):
+        self.gather_mode = int(gather_mode)
         assert rt.is_cuda, "FastSageTrainer is the CUDA engine; use SageTrainer for the portable path"
         self.rt, self.nodes, self.csr, self.model = rt, nodes, csr, model
         self.fanouts = list(fanouts)
@@ -135,13 +136,13 @@ class FastSageTrainer:
                 if l == 1:
                     d = self.nodes.feat_desc
                     C.sage_fused_forward(d, hops[i], d, hops[i + 1], self.n[i], k, mode, img, c.bias, N, c.out_dim,
-                                         not last, not last, True, 0, out, a, None)
+                                         not last, not last, True, 0, out, a, None, self.gather_mode)
                 else:
                     po = self.seg_off[l - 2]
                     xs = self.H[l - 2][po[i]:po[i + 1]]
                     xn = self.H[l - 2][po[i + 1]:po[i + 2]]
                     C.sage_fused_forward(local_table_desc(xs), None, local_table_desc(xn), None, self.n[i], k, mode,
-                                         img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a, None)
+                                         img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a, None, self.gather_mode)
         # ---- loss (seeds are owned locally: labels are a local lookup)
         top = self.convs[L - 1]
         C.softmax_ce(self.H[L - 1], self.nodes.labels.local, self.seeds, self.rt.world, self.loss, self.dZ[L - 1],

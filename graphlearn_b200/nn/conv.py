@@ -64,3 +64,110 @@ class EgoSAGEConv(nn.Module):
         return sage_ops.sage_layer(self.weight_p, self.bias, k=expand, mode=self.agg_type, relu=relu,
                                    out_bf16=out_bf16, self_table=table, self_vids=self_vids.reshape(-1),
                                    nbr_table=nbr_table or table, nbr_vids=nbr_vids.reshape(-1))
+
+
+class EgoGATConv(nn.Module):
+    """Multi-head attention over a fixed fan-out neighbourhood; heads are AVERAGED like the
+    reference (ego_gat_conv.py:80-117: x'=W_x x, n'=W_n n, score = a.[x'||n'],
+    softmax(leaky_relu) over the k neighbours (self included), weighted sum)."""
+
+    def __init__(self, in_dim, out_dim, num_head=1, bias=True, attn_drop=0.0, negative_slope=0.2):
+        super().__init__()
+        self.in_self = int(in_dim if not isinstance(in_dim, (tuple, list)) else in_dim[0])
+        self.in_nbr = int(in_dim if not isinstance(in_dim, (tuple, list)) else in_dim[1])
+        self.out_dim, self.num_head = int(out_dim), int(num_head)
+        self.lin_self = nn.Linear(self.in_self, out_dim * num_head, bias=False)
+        self.lin_nbr = nn.Linear(self.in_nbr, out_dim * num_head, bias=False)
+        self.att_self = nn.Parameter(torch.empty(num_head, out_dim))
+        self.att_nbr = nn.Parameter(torch.empty(num_head, out_dim))
+        self.bias = nn.Parameter(torch.zeros(out_dim)) if bias else None
+        self.attn_drop, self.slope = attn_drop, negative_slope
+        nn.init.xavier_uniform_(self.att_self)
+        nn.init.xavier_uniform_(self.att_nbr)
+
+    def forward(self, x, neighbor, expand):
+        M, H, D = x.size(0), self.num_head, self.out_dim
+        xs = self.lin_self(x.float()).view(M, 1, H, D)
+        xn = self.lin_nbr(neighbor.float()).view(M, expand, H, D)
+        xn = torch.cat([xs, xn], 1)                                   # self loop joins the softmax
+        score = (xs * self.att_self).sum(-1) + (xn * self.att_nbr).sum(-1)     # [M, 1+k, H]
+        coef = torch.softmax(F.leaky_relu(score, self.slope), dim=1)
+        if self.training and self.attn_drop > 0:
+            coef = F.dropout(coef, self.attn_drop)
+        out = (coef.unsqueeze(-1) * xn).sum(1).mean(1)                # average heads
+        return out + self.bias if self.bias is not None else out
+
+
+class EgoGINConv(nn.Module):
+    """W((1 + eps) x + sum(nbrs))  (ego_gin_conv.py:80-100); separate input projections when the
+    self / neighbour dims differ."""
+
+    def __init__(self, in_dim, out_dim, eps=0.0, train_eps=False, bias=True):
+        super().__init__()
+        self.in_self = int(in_dim if not isinstance(in_dim, (tuple, list)) else in_dim[0])
+        self.in_nbr = int(in_dim if not isinstance(in_dim, (tuple, list)) else in_dim[1])
+        self.eps = nn.Parameter(torch.tensor(float(eps))) if train_eps else float(eps)
+        self.proj_self = self.proj_nbr = None
+        if self.in_self != self.in_nbr:
+            self.proj_self = nn.Linear(self.in_self, out_dim, bias=False)
+            self.proj_nbr = nn.Linear(self.in_nbr, out_dim, bias=False)
+            self.lin = nn.Linear(out_dim, out_dim, bias=bias)
+        else:
+            self.lin = nn.Linear(self.in_self, out_dim, bias=bias)
+
+    def forward(self, x, neighbor, expand):
+        agg = neighbor.float().view(x.size(0), expand, -1).sum(1)
+        xs = x.float()
+        if self.proj_self is not None:
+            xs, agg = self.proj_self(xs), self.proj_nbr(agg)
+        return self.lin((1.0 + self.eps) * xs + agg)
+
+
+class EgoRGCNConv(nn.Module):
+    """Relational GCN on ego graphs: sum_r mean_r(nbrs_r) W_r + x W_0 with basis or block-diagonal
+    weight decomposition (ego_rgcn_conv.py:108-139)."""
+
+    def __init__(self, in_dim, out_dim, num_relations, num_bases=None, num_blocks=None, bias=True):
+        super().__init__()
+        self.in_dim, self.out_dim, self.R = int(in_dim), int(out_dim), int(num_relations)
+        self.num_bases, self.num_blocks = num_bases, num_blocks
+        if num_bases:
+            self.basis = nn.Parameter(torch.empty(num_bases, in_dim, out_dim))
+            self.comp = nn.Parameter(torch.empty(num_relations, num_bases))
+            nn.init.xavier_uniform_(self.basis)
+            nn.init.xavier_uniform_(self.comp)
+        elif num_blocks:
+            assert in_dim % num_blocks == 0 and out_dim % num_blocks == 0
+            self.blocks = nn.Parameter(torch.empty(num_relations, num_blocks, in_dim // num_blocks, out_dim // num_blocks))
+            nn.init.xavier_uniform_(self.blocks)
+        else:
+            self.weight = nn.Parameter(torch.empty(num_relations, in_dim, out_dim))
+            nn.init.xavier_uniform_(self.weight)
+        self.root = nn.Linear(in_dim, out_dim, bias=bias)
+
+    def relation_weights(self):
+        if self.num_bases:
+            return torch.einsum("rb,bio->rio", self.comp, self.basis)
+        if self.num_blocks:
+            return torch.stack([torch.block_diag(*self.blocks[r]) for r in range(self.R)])
+        return self.weight
+
+    def forward(self, x, neighbors, expands):
+        """neighbors: list (one per relation) of [M*k_r, d]; expands: list of k_r."""
+        W = self.relation_weights()
+        out = self.root(x.float())
+        for r, (nb, k) in enumerate(zip(neighbors, expands)):
+            out = out + nb.float().view(x.size(0), k, -1).mean(1) @ W[r]
+        return out
+
+
+class EgoLayer(nn.Module):
+    """Applies one conv to every adjacent hop pair (ego_layer.py:54-91)."""
+
+    def __init__(self, convs):
+        super().__init__()
+        self.convs = nn.ModuleList(convs)
+
+    def forward(self, x_list, expands):
+        assert len(self.convs) == len(x_list) - 1
+        return [self.convs[i](x_list[i], x_list[i + 1], expands[i]) for i in range(len(x_list) - 1)]

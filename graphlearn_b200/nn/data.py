@@ -1,0 +1,145 @@
+"""Model-side data containers (graphlearn/python/nn/data.py, nn/tf/data/{egograph,
+batchgraph,hetero_batchgraph}.py): ``Data`` (one node/edge set), ``EgoGraph`` (dense fixed
+fan-out hops), ``BatchGraph`` / ``HeteroBatchGraph`` (concatenated subgraphs with node offsets).
+Everything holds device tensors."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+
+class Data(object):
+    def __init__(self, ids=None, ints=None, floats=None, strings=None, labels=None, weights=None, **kwargs):
+        self.ids, self.ints, self.floats, self.strings = ids, ints, floats, strings
+        self.labels, self.weights = labels, weights
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @staticmethod
+    def from_values(v, flatten=True) -> "Data":
+        """From a ``Nodes`` / ``Edges`` result object (device tensors, no host copies)."""
+        def t(name):
+            x = v.tensor(name)
+            if x is None or not isinstance(x, torch.Tensor):
+                return x
+            if flatten:
+                return x.reshape(-1, x.shape[-1]) if name.endswith("_attrs") else x.reshape(-1)
+            return x
+        ids = v.tensor("ids") if "ids" in v._t else v.tensor("dst_ids")
+        return Data(ids.reshape(-1) if flatten else ids, t("int_attrs"), t("float_attrs"), v._t.get("string_attrs"),
+                    t("labels"), t("weights"))
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, v.to(device))
+        return self
+
+    def apply(self, func):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, func(v))
+        return self
+
+
+class EgoGraph(object):
+    """src + K hops of fixed fan-out neighbours (egograph.py:41-123)."""
+
+    def __init__(self, src: Data, nbr_nodes: Sequence[Data], node_schema=None, nbr_nums: Sequence[int] = (),
+                 nbr_edges: Optional[Sequence[Data]] = None, edge_schema=None):
+        self._src, self._nbr_nodes, self._nbr_edges = src, list(nbr_nodes), list(nbr_edges or [])
+        self._node_schema, self._edge_schema = node_schema, edge_schema
+        self._nbr_nums = list(nbr_nums)
+
+    src = property(lambda self: self._src)
+    nbr_nodes = property(lambda self: self._nbr_nodes)
+    nbr_edges = property(lambda self: self._nbr_edges)
+    nbr_nums = property(lambda self: self._nbr_nums)
+    node_schema = property(lambda self: self._node_schema)
+    edge_schema = property(lambda self: self._edge_schema)
+
+    def hop_node(self, i) -> Data:
+        return self._nbr_nodes[i]
+
+    def hop_edge(self, i) -> Data:
+        return self._nbr_edges[i]
+
+    def hops(self) -> List[Data]:
+        return [self._src] + self._nbr_nodes
+
+    def transform(self, encoders) -> List[torch.Tensor]:
+        """Encode every hop with its FeatureEncoder (one per hop or one shared) -> dense inputs."""
+        encs = encoders if isinstance(encoders, (list, tuple)) else [encoders] * (len(self._nbr_nodes) + 1)
+        return [e(d.floats, d.ints, d.strings) for e, d in zip(encs, self.hops())]
+
+
+class BatchGraph(object):
+    """Several subgraphs stacked into one big disconnected graph (batchgraph.py): node features
+    concatenated, edge_index shifted by the per-graph node offset."""
+
+    def __init__(self, edge_index, nodes: Data, node_schema=None, graph_node_offsets=None, edges: Optional[Data] = None,
+                 graph_edge_offsets=None, additional_keys=(), **kwargs):
+        self.edge_index, self.nodes, self.edges = edge_index, nodes, edges
+        self.node_schema = node_schema
+        self.graph_node_offsets, self.graph_edge_offsets = graph_node_offsets, graph_edge_offsets
+        self.additional_keys = list(additional_keys)
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self):
+        return int(self.nodes.ids.numel())
+
+    @property
+    def num_edges(self):
+        return int(self.edge_index.size(1))
+
+    @property
+    def num_graphs(self):
+        return int(self.graph_node_offsets.numel()) - 1
+
+    @property
+    def graph_assign(self):
+        n = self.graph_node_offsets[1:] - self.graph_node_offsets[:-1]
+        return torch.repeat_interleave(torch.arange(n.numel(), device=n.device), n)
+
+    @staticmethod
+    def from_graphs(graphs, additional_keys=()) -> "BatchGraph":
+        """graphs: list of ``SubGraph`` results."""
+        dev = graphs[0].edge_index_t.device
+        offs, eis, ids, floats, ints, labels = [0], [], [], [], [], []
+        for g in graphs:
+            n = g.num_nodes
+            eis.append(g.edge_index_t + offs[-1])
+            ids.append(g.nodes.ids_t.reshape(-1))
+            f = g.nodes.tensor("float_attrs")
+            if isinstance(f, torch.Tensor):
+                floats.append(f.reshape(n, -1))
+            i = g.nodes.tensor("int_attrs")
+            if isinstance(i, torch.Tensor):
+                ints.append(i.reshape(n, -1))
+            l = g.nodes.tensor("labels")
+            if isinstance(l, torch.Tensor):
+                labels.append(l.reshape(-1))
+            offs.append(offs[-1] + n)
+        nodes = Data(torch.cat(ids), torch.cat(ints) if ints else None, torch.cat(floats) if floats else None, None,
+                     torch.cat(labels) if labels else None)
+        extra = {}
+        for key in additional_keys:
+            vals = [torch.as_tensor(getattr(g, key)).to(dev) for g in graphs if hasattr(g, key)]
+            if vals:
+                extra[key] = torch.cat(vals)
+        return BatchGraph(torch.cat(eis, 1), nodes, graph_node_offsets=torch.tensor(offs, device=dev),
+                          additional_keys=additional_keys, **extra)
+
+
+class HeteroBatchGraph(object):
+    """dict-of-types variant: edge_index_dict[(src_t, edge_t, dst_t)], nodes_dict[type]."""
+
+    def __init__(self, edge_index_dict: Dict, nodes_dict: Dict[str, Data], graph_node_offsets_dict=None):
+        self.edge_index_dict, self.nodes_dict = edge_index_dict, nodes_dict
+        self.graph_node_offsets_dict = graph_node_offsets_dict or {}
+
+    def num_nodes(self, t):
+        return int(self.nodes_dict[t].ids.numel())

@@ -1,0 +1,77 @@
+"""``nn.Dataset``: turn GSL query results into model inputs (graphlearn/python/nn/dataset.py:82-181,
+nn/pytorch/data/dataset.py:31-98).  ``TorchDataset`` is the ``torch.utils.data.IterableDataset``
+adapter; because batches are born on the GPU there are no DataLoader worker processes (the
+reference turns every worker into a sampling client, pyg_dataloader.py:42-117)."""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from .. import errors
+from ..gsl.dataset import Dataset as _GslDataset
+from .data import BatchGraph, Data, EgoGraph
+
+
+class Dataset(object):
+    def __init__(self, query, window=10, induce_func: Optional[Callable] = None, **kwargs):
+        self._query = query
+        self._ds = _GslDataset(query, window=window, **kwargs)
+        self._induce = induce_func
+
+    @property
+    def raw(self):
+        return self._ds
+
+    def next(self):
+        return self._ds.next()
+
+    def get_data_dict(self) -> dict:
+        """alias -> Data (flattened device tensors) of the next batch."""
+        res = self._ds.next()
+        return {k: Data.from_values(v) for k, v in res.items() if hasattr(v, "_t")}
+
+    def get_egograph(self, source: str, neighbors: Sequence[str], nbr_nums: Optional[Sequence[int]] = None,
+                     res=None) -> EgoGraph:
+        """EgoGraph rooted at alias `source` with hop aliases `neighbors` (in hop order)."""
+        res = res if res is not None else self._ds.next()
+        src = Data.from_values(res[source])
+        hops = [Data.from_values(res[a]) for a in neighbors]
+        if nbr_nums is None:
+            nbr_nums = [int(res[a].shape[-1]) for a in neighbors]
+        return EgoGraph(src, hops, nbr_nums=nbr_nums)
+
+    def get_batchgraph(self, alias: str, additional_keys=()) -> BatchGraph:
+        res = self._ds.next()
+        g = res[alias]
+        graphs = g if isinstance(g, (list, tuple)) else [g]
+        if self._induce is not None:
+            graphs = self._induce(res)
+        return BatchGraph.from_graphs(graphs, additional_keys)
+
+    def state_dict(self):
+        return self._ds.state_dict()
+
+    def load_state_dict(self, sd):
+        self._ds.load_state_dict(sd)
+
+
+class TorchDataset(torch.utils.data.IterableDataset):
+    """Iterate one epoch of a query; every item is a dict alias -> Data (or the output of
+    ``transform``).  Use with ``DataLoader(ds, batch_size=None)`` or iterate directly."""
+
+    def __init__(self, query, window=10, transform: Optional[Callable] = None, length: Optional[int] = None):
+        super().__init__()
+        self._nn = Dataset(query, window=window)
+        self._transform = transform
+        self._length = length
+
+    def __iter__(self):
+        n = 0
+        while self._length is None or n < self._length:
+            try:
+                d = self._nn.get_data_dict()
+            except errors.OutOfRangeError:
+                return
+            n += 1
+            yield self._transform(d) if self._transform else d

@@ -1,0 +1,86 @@
+"""Feature encoding (graphlearn/python/nn/tf/data/feature_column.py:34-299,
+feature_handler.py:77-214): float attributes pass through, int / hashed-string attributes are
+embedded (optionally hashed into buckets), same-dimension embeddings are FUSED into one table,
+multi-value strings become a summed sparse embedding.  Output = concat of all pieces."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from ..data.feature_spec import DenseSpec, FeatureSpec, MultivalSpec, SparseSpec
+
+
+def _hash_bucket(x: torch.Tensor, buckets: int) -> torch.Tensor:
+    """deterministic integer hash -> [0, buckets)."""
+    h = (x.to(torch.int64) * 2654435761) & 0x7FFFFFFFFFFFFFFF
+    h = h ^ (h >> 29)
+    return h % buckets
+
+
+class FeatureEncoder(nn.Module):
+    def __init__(self, spec: FeatureSpec, fuse_embedding: bool = True):
+        super().__init__()
+        self.spec = spec
+        self.int_specs = list(spec.int_specs)
+        self.n_float = spec.num_float
+        self.dense_int = [i for i, s in enumerate(self.int_specs) if isinstance(s, DenseSpec)]
+        self.sparse_int = [i for i, s in enumerate(self.int_specs) if isinstance(s, SparseSpec)]
+        # fused tables: one nn.Embedding per embedding dim, rows = sum of bucket sizes (+ offsets)
+        self.fuse = fuse_embedding
+        self.groups = {}
+        self.tables = nn.ModuleDict()
+        for i in self.sparse_int:
+            s = self.int_specs[i]
+            if not s.bucket_size:
+                raise ValueError("embedding columns need a bucket size (dynamic tables are PAI-TF only)")
+            key = str(s.dimension) if fuse_embedding else "%d_%d" % (s.dimension, i)
+            self.groups.setdefault(key, []).append(i)
+        self.offsets = {}
+        for key, cols in self.groups.items():
+            off, total = [], 0
+            for i in cols:
+                off.append(total)
+                total += int(self.int_specs[i].bucket_size)
+            self.offsets[key] = off
+            self.tables[key] = nn.Embedding(total, int(self.int_specs[cols[0]].dimension))
+        self.multival = nn.ModuleList([nn.EmbeddingBag(int(s.bucket_size), int(s.dimension), mode="sum")
+                                       for s in spec.string_specs if isinstance(s, MultivalSpec)])
+
+    @property
+    def output_dim(self):
+        d = self.n_float + len(self.dense_int)
+        for key, cols in self.groups.items():
+            d += len(cols) * self.tables[key].embedding_dim
+        d += sum(m.embedding_dim for m in self.multival)
+        return d
+
+    def forward(self, float_attrs: Optional[torch.Tensor] = None, int_attrs: Optional[torch.Tensor] = None,
+                string_attrs=None) -> torch.Tensor:
+        parts: List[torch.Tensor] = []
+        if self.n_float and float_attrs is not None:
+            parts.append(float_attrs.float().reshape(-1, self.n_float))
+        if int_attrs is not None and self.int_specs:
+            ia = int_attrs.reshape(-1, len(self.int_specs))
+            if self.dense_int:
+                parts.append(ia[:, self.dense_int].float())
+            for key, cols in self.groups.items():
+                idx = []
+                for c, off in zip(cols, self.offsets[key]):
+                    s = self.int_specs[c]
+                    v = _hash_bucket(ia[:, c], int(s.bucket_size)) if s.need_hash else ia[:, c].clamp(0, int(s.bucket_size) - 1)
+                    idx.append(v + off)
+                emb = self.tables[key](torch.stack(idx, 1))              # [n, cols, dim]  one fused lookup
+                parts.append(emb.reshape(emb.size(0), -1))
+        if self.multival and string_attrs is not None:
+            for j, m in enumerate(self.multival):
+                spec = [s for s in self.spec.string_specs if isinstance(s, MultivalSpec)][j]
+                flat, offs = [], [0]
+                for row in string_attrs[:, j]:
+                    toks = [t for t in str(row).split(spec.delimiter) if t]
+                    flat.extend(hash(t) % int(spec.bucket_size) for t in toks)
+                    offs.append(len(flat))
+                dev = m.weight.device
+                parts.append(m(torch.tensor(flat, dtype=torch.long, device=dev), torch.tensor(offs[:-1], dtype=torch.long, device=dev)))
+        return torch.cat(parts, 1) if parts else torch.zeros(0)

@@ -93,7 +93,7 @@ class _SageFusedFn(torch.autograd.Function):
         img, w16 = C.pack_weight_f32(weight_p.detach().contiguous(), N, bool(need_x))
         out, a_save = C.sage_fused_forward(tself_desc, self_vids, tnbr_desc, nbr_vids, int(M), int(k), MODE[mode], img,
                                            bias, N, n_out, bool(relu), bool(out_bf16), bool(need_w),
-                                           int(rows_per_cta), None, None, None)
+                                           int(rows_per_cta), None, None, None, int(_config.get().sage_gather_mode))
         ctx.save_for_backward(a_save if need_w else None, w16 if need_x else None, out if relu else None)
         ctx.meta = (d_self, d_nbr, kp_self, kp_nbr, int(M), int(k), mode, relu, bias is not None,
                     x_self is not None, x_nbr is not None)

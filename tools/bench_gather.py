@@ -9,6 +9,7 @@ from graphlearn_b200.store.shards import IdMap, NodeTable
 
 rt = init(); C = native(); dev = rt.device
 M, k, d, n_out = 25600, 10, 100, 256
+MODE = int(os.environ.get("GLB_MODE", "0"))
 w = torch.randn(n_out, 256, device=dev) * 0.05
 img, _ = C.pack_weight_f32(w, 256, False)
 bias = torch.zeros(n_out, device=dev)
@@ -21,12 +22,12 @@ def run(n_nodes, dt, R, save_a=True, iters=20):
     sv = [torch.randint(0, n_nodes, (M,), device=dev) for _ in range(iters)]
     nv = [torch.randint(0, n_nodes, (M * k,), device=dev) for _ in range(iters)]
     for i in range(3):
-        C.sage_fused_forward(t.feat_desc, sv[i], t.feat_desc, nv[i], M, k, 0, img, bias, 256, n_out, True, True, save_a, R, out, asave if save_a else None, None)
+        C.sage_fused_forward(t.feat_desc, sv[i], t.feat_desc, nv[i], M, k, 0, img, bias, 256, n_out, True, True, save_a, R, out, asave if save_a else None, None, MODE)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
-        C.sage_fused_forward(t.feat_desc, sv[i], t.feat_desc, nv[i], M, k, 0, img, bias, 256, n_out, True, True, save_a, R, out, asave if save_a else None, None)
+        C.sage_fused_forward(t.feat_desc, sv[i], t.feat_desc, nv[i], M, k, 0, img, bias, 256, n_out, True, True, save_a, R, out, asave if save_a else None, None, MODE)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1000 / iters
     esz = 4 if dt == torch.float32 else 2

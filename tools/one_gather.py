@@ -16,6 +16,6 @@ t = NodeTable(rt, "t", IdMap(rt, torch.arange(n_nodes, device=dev), dense=True))
 t.set_float(torch.randn(n_nodes, d, device=dev), dt)
 for it in range(4):
     sv = torch.randint(0, n_nodes, (M,), device=dev); nv = torch.randint(0, n_nodes, (M * k,), device=dev)
-    C.sage_fused_forward(t.feat_desc, sv, t.feat_desc, nv, M, k, 0, img, bias, 256, n_out, True, True, True, 128, out, asave, None)
+    C.sage_fused_forward(t.feat_desc, sv, t.feat_desc, nv, M, k, 0, img, bias, 256, n_out, True, True, True, 128, out, asave, None, int(os.environ.get('GLB_MODE','0')))
 torch.cuda.synchronize()
 print("ok")

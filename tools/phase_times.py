@@ -6,6 +6,7 @@ from graphlearn_b200.parallel.runtime import init, native
 from graphlearn_b200.store.shards import IdMap, NodeTable
 rt = init(); C = native(); dev = rt.device
 M, k, d, n_out = 25600, 10, 100, 256
+MODE = int(os.environ.get("GLB_MODE", "0"))
 w = torch.randn(n_out, 256, device=dev) * 0.05
 img, _ = C.pack_weight_f32(w, 256, False)
 bias = torch.zeros(n_out, device=dev)
@@ -21,7 +22,7 @@ for dt in (torch.float32, torch.bfloat16):
         ts = torch.zeros(grid * 16, dtype=torch.int64, device=dev)
         for it in range(3):
             sv = torch.randint(0, n_nodes, (M,), device=dev); nv = torch.randint(0, n_nodes, (M * k,), device=dev)
-            C.sage_fused_forward(t.feat_desc, sv, t.feat_desc, nv, M, k, 0, img, bias, 256, n_out, True, True, True, R, out, asave, ts)
+            C.sage_fused_forward(t.feat_desc, sv, t.feat_desc, nv, M, k, 0, img, bias, 256, n_out, True, True, True, R, out, asave, ts, MODE)
         torch.cuda.synchronize()
         T = ts.view(grid, 16).cpu().double()
         d_ = (T[:, 1:10] - T[:, 0:9])
