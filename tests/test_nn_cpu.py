@@ -1,0 +1,188 @@
+"""CPU tests of the model layer, losses, feature encoding, checkpoint/resume and native loader."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import graphlearn_b200 as gl
+from graphlearn_b200 import models
+from graphlearn_b200 import nn as glnn
+from tests import fixtures as fx
+
+
+def test_ego_sage_conv_math():
+    torch.manual_seed(0)
+    for agg in ("mean", "sum", "gcn", "max"):
+        c = glnn.EgoSAGEConv(6, 5, agg)
+        x, nb = torch.randn(4, 6), torch.randn(12, 6)
+        y = c(x, nb, 3)
+        n3 = nb.view(4, 3, 6)
+        if agg == "gcn":
+            a = (x + n3.sum(1)) / 4
+        else:
+            a = torch.cat([x, {"mean": n3.mean(1), "sum": n3.sum(1), "max": n3.max(1).values}[agg]], 1)
+        ref = F.linear(a, c.weight, c.bias)
+        assert torch.allclose(y, ref, atol=1e-5), agg
+
+
+def test_padded_weight_roundtrip():
+    from graphlearn_b200.ops import sage as SG
+    w = torch.randn(7, 100 + 100)
+    wp = SG.pad_weight(w, 100, 100, "mean")
+    assert wp.shape == (7, 256) and torch.equal(SG.logical_weight(wp, 100, 100, "mean"), w)
+    assert float(wp[:, 100:128].abs().sum()) == 0 and float(wp[:, 228:].abs().sum()) == 0
+    assert SG.fused_supported(100, 100, 256, "mean") and not SG.fused_supported(600, 600, 256, "mean")
+
+
+def test_gat_softmax_rows_sum_to_one():
+    s = torch.randn(10, 2)
+    idx = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2, 3])
+    a = glnn.segment_softmax(s, idx, 4)
+    sums = torch.zeros(4, 2).index_add_(0, idx, a)
+    assert torch.allclose(sums, torch.ones(4, 2), atol=1e-6)
+
+
+def test_sparse_convs_vs_dense():
+    torch.manual_seed(1)
+    x = torch.randn(5, 4)
+    ei = torch.tensor([[0, 0, 1, 2, 3, 4], [1, 2, 2, 3, 4, 0]])
+    A = torch.zeros(5, 5)
+    A[ei[0], ei[1]] = 1
+    c = glnn.SAGEConv(4, 3, "mean")
+    ref = c.lin_self(x) + c.lin_nbr((A @ x) / A.sum(1, keepdim=True).clamp(min=1))
+    assert torch.allclose(c(x, ei), ref, atol=1e-5)
+    g = glnn.GCNConv(4, 3)
+    Ah = A + torch.eye(5)
+    d = Ah.sum(1).pow(-0.5)
+    ref = (d[:, None] * Ah * d[None, :]) @ g.lin(x) + g.bias
+    assert torch.allclose(g(x, ei), ref, atol=1e-5)
+
+
+def test_losses():
+    L = glnn.loss
+    pos, neg = torch.tensor([10.0, 10.0]), torch.tensor([-10.0, -10.0, -10.0])
+    assert float(L.sigmoid_cross_entropy_loss(pos, neg)) < 1e-3
+    s = torch.eye(3)
+    l = L.unsupervised_softmax_cross_entropy_loss(s * 10, s * 10, -s.repeat_interleave(2, 0) * 10)
+    assert float(l) < 1e-3
+    z = torch.zeros(2, 3)
+    assert float(L.triplet_margin_loss(z, z, z, z, z, z, margin=1.0)) == pytest.approx(1.0)
+    assert float(L.triplet_softplus_loss(z, z, z, z, z, z)) == pytest.approx(2 * np.log(2), abs=1e-5)
+
+
+def test_feature_encoder_fused_tables():
+    d = gl.Decoder(attr_types=["float", ("int", 10), ("string", 20), ("int", 5), "int", "float"],
+                   attr_dims=[None, 8, 8, 4, None, None])
+    spec = d.feature_spec
+    enc = glnn.FeatureEncoder(spec)
+    assert set(enc.tables.keys()) == {"8", "4"}           # two dim-8 columns fused into one table
+    assert enc.tables["8"].num_embeddings == 30
+    out = enc(torch.randn(6, 2), torch.randint(0, 100, (6, 4)))
+    assert out.shape == (6, enc.output_dim) and enc.output_dim == 2 + 1 + 8 + 8 + 4
+
+
+def test_node2vec_pairs_and_model():
+    path = torch.arange(12).view(2, 6)
+    s, d = models.gen_pair(path, 1, 1)
+    assert s.numel() == 2 * (6 * 2 - 2)
+    m = models.Node2Vec(50, 8, sparse=False)
+    loss = m(torch.tensor([1, 2]), torch.tensor([3, 4]), torch.randint(0, 50, (2, 5)))
+    loss.backward()
+    assert m.src_emb.weight.grad is not None
+
+
+def test_seal_labels_and_model():
+    ds = torch.tensor([0, 1, 1, 2, 2 ** 31 - 1])
+    dd = torch.tensor([1, 0, 1, 1, 2])
+    z = models.drnl_node_labeling(ds, dd)
+    assert z[0] == 1 and z[1] == 1 and z[4] == 0 and z[2] == 2
+    m = models.SEAL(4, 8, num_layers=2)
+    ei = torch.tensor([[0, 1, 2, 3], [2, 2, 3, 0]])
+    out = m(torch.randn(5, 4), ei, z)
+    assert out.shape == ()
+
+
+def test_ego_gnn_variants_and_bipartite():
+    xs = [torch.randn(4, 6), torch.randn(12, 6), torch.randn(24, 6)]
+    for kind in ("sage", "gat", "gin"):
+        m = models.make_ego_gnn(kind, 6, 8, 3, 2)
+        assert m(xs, [3, 2]).shape == (4, 3)
+    b = models.EgoBipartiteSAGE(6, 5, 8, 4, hops=2)
+    u = [torch.randn(4, 6), torch.randn(8, 5), torch.randn(16, 6)]
+    i = [torch.randn(4, 5), torch.randn(8, 6), torch.randn(16, 5)]
+    ue, ie = b(u, i, [2, 2], [2, 2])
+    assert ue.shape == (4, 4) and ie.shape == (4, 4)
+    assert float(b.in_batch_negative_loss(ue, ie)) > 0
+
+
+def test_nn_dataset_egograph(tmp_path):
+    g = fx.build_graph(fx.write_graph(str(tmp_path)))
+    q = g.V("item").batch(5).alias("s").outV("sim").sample(2).by("topk").alias("h1") \
+         .outV("sim").sample(2).by("topk").alias("h2").values()
+    ds = glnn.Dataset(q)
+    ego = ds.get_egograph("s", ["h1", "h2"])
+    assert ego.nbr_nums == [2, 2]
+    assert ego.src.floats.shape == (5, 4) and ego.hop_node(1).floats.shape == (20, 4)
+    m = models.EgoGraphSAGE(4, 8, 3, 2, bf16_activations=False)
+    out = m([h.floats for h in ego.hops()], ego.nbr_nums)
+    assert out.shape == (5, 3)
+
+
+def test_checkpoint_resume_is_deterministic(tmp_path):
+    """model + optimizer + RNG + traversal state round-trip: resumed run == uninterrupted run."""
+    from graphlearn_b200.engine.trainer import SageTrainer
+    from graphlearn_b200.parallel.runtime import init
+    from graphlearn_b200.store.synthetic import make_sharded_graph
+    from graphlearn_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+    rt = init(device="cpu")
+    nodes, csr = make_sharded_graph(rt, 500, 4000, 16, 4, seed=2)
+
+    def mk():
+        torch.manual_seed(0)
+        return SageTrainer(rt, nodes, csr, models.EgoGraphSAGE(16, 8, 4, 2), [3, 2], 32, lr=1e-2, seed=5)
+
+    seeds = [torch.randint(0, 500, (32,), generator=torch.Generator().manual_seed(i)) for i in range(8)]
+    a = mk()
+    la = [float(a.step(s)) for s in seeds]
+    b = mk()
+    for s in seeds[:4]:
+        b.step(s)
+    save_checkpoint(str(tmp_path / "ck"), trainer=b)
+    c = mk()
+    load_checkpoint(str(tmp_path / "ck"), trainer=c)
+    lc = [float(c.step(s)) for s in seeds[4:]]
+    assert np.allclose(lc, la[4:], rtol=1e-5, atol=1e-6), (lc, la[4:])
+
+
+def test_embedding_dump_roundtrip(tmp_path):
+    from graphlearn_b200.utils.checkpoint import embedding_decoder, save_embeddings
+    ids = torch.arange(10) * 3
+    emb = torch.randn(10, 6)
+    p = str(tmp_path / "emb.txt")
+    save_embeddings(p, ids, emb)
+    assert open(p).readline().strip() == "id:int64\temb:string"
+    g = gl.Graph().node(p, "e", decoder=embedding_decoder(6)).init(device="cpu")
+    back = g.lookup_nodes("e", ids.numpy()).float_attrs
+    assert np.allclose(back, emb.numpy(), atol=1e-4)
+
+
+def test_loader_rejects_malformed(tmp_path):
+    p = tmp_path / "bad.tsv"
+    p.write_text("id:int64\tfeature:string\n1\t0.5:xx\n")
+    g = gl.Graph().node(str(p), "n", decoder=gl.Decoder(attr_types=["float", "float"]))
+    with pytest.raises(RuntimeError):
+        g.init(device="cpu")
+
+
+def test_config_setters_and_errors():
+    gl.set_default_neighbor_id(-3)
+    gl.set_padding_mode(gl.REPLICATE)
+    gl.set_inner_threadnum(7)
+    cfg = gl.get_config()
+    assert cfg.default_neighbor_id == -3 and cfg.padding_mode == gl.REPLICATE and cfg.inter_threadnum == 7
+    assert issubclass(gl.OutOfRangeError, gl.errors.GLError) and gl.OutOfRangeError().error_code == 11
+    assert gl.errors.exception_type_from_error_code(5) is gl.errors.NotFoundError
+    assert gl.strategy2op("edge_weight") == "EdgeWeightSampler"
+    assert gl.get_mask_type("i", gl.Mask.TRAIN) == "MASKTRAIN_i"
