@@ -1,0 +1,189 @@
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+
+class SampleStore(object):
+    """Fixed-capacity, timestamp-ordered neighbour samples per source vertex, in device memory."""
+
+    def __init__(self, num_vertices: int, capacity: int, device, feat_dim: int = 0):
+        self.n, self.K = int(num_vertices), int(capacity)
+        self.device = device
+        self.nbr = torch.full((self.n, self.K), -1, dtype=torch.int64, device=device)
+        self.ts = torch.full((self.n, self.K), -(2 ** 62), dtype=torch.int64, device=device)
+        self.w = torch.zeros((self.n, self.K), dtype=torch.float32, device=device)
+        self.count = torch.zeros(self.n, dtype=torch.int64, device=device)
+        self.feat = torch.zeros((self.n, feat_dim), dtype=torch.float32, device=device) if feat_dim else None
+        self.feat_ts = torch.full((self.n,), -(2 ** 62), dtype=torch.int64, device=device) if feat_dim else None
+
+    def apply_edges(self, src: torch.Tensor, dst: torch.Tensor, ts: torch.Tensor, w: Optional[torch.Tensor] = None):
+        """TopK-by-timestamp: an incoming edge replaces the OLDEST kept sample of its source if it is
+        newer.  Processed in timestamp order; duplicates of one source inside a batch are resolved in
+        rounds (each round applies at most one update per source)."""
+        src, dst, ts = src.to(self.device), dst.to(self.device), ts.to(self.device)
+        w = torch.ones_like(ts, dtype=torch.float32) if w is None else w.to(self.device).float()
+        order = torch.argsort(ts, stable=True)
+        src, dst, ts, w = src[order], dst[order], ts[order], w[order]
+        pending = torch.ones_like(src, dtype=torch.bool)
+        while bool(pending.any()):
+            idx = pending.nonzero().flatten()
+            s = src[idx]
+            # first pending occurrence of every source in this round
+            uniq, inv = torch.unique(s, return_inverse=True)
+            first = torch.full((uniq.numel(),), idx.numel(), dtype=torch.int64, device=self.device)
+            first.scatter_reduce_(0, inv, torch.arange(idx.numel(), device=self.device), "amin")
+            sel = idx[first]
+            vs, vd, vt, vw = src[sel], dst[sel], ts[sel], w[sel]
+            slot = torch.argmin(self.ts[vs], dim=1)                    # oldest (or empty) slot
+            newer = vt > self.ts[vs, slot]
+            vs2, sl2 = vs[newer], slot[newer]
+            was_empty = self.nbr[vs2, sl2] < 0
+            self.nbr[vs2, sl2] = vd[newer]
+            self.ts[vs2, sl2] = vt[newer]
+            self.w[vs2, sl2] = vw[newer]
+            self.count[vs2] += was_empty.to(torch.int64)
+            pending[sel] = False
+
+    def apply_vertices(self, vid: torch.Tensor, ts: torch.Tensor, feat: torch.Tensor):
+        """latest-version vertex sampler: keep the feature row with the largest timestamp."""
+        if self.feat is None:
+            return
+        vid, ts, feat = vid.to(self.device), ts.to(self.device), feat.to(self.device).float()
+        order = torch.argsort(ts, stable=True)
+        vid, ts, feat = vid[order], ts[order], feat[order]
+        newer = ts >= self.feat_ts[vid]
+        # later rows of the (sorted) batch win
+        self.feat[vid[newer]] = feat[newer]
+        self.feat_ts.scatter_reduce_(0, vid[newer], ts[newer], "amax")
+
+    def lookup(self, vids: torch.Tensor, k: int):
+        """most recent k samples of each vertex: (nbr [B,k], ts [B,k], w [B,k]); -1 padded."""
+        t, order = torch.sort(self.ts[vids], dim=1, descending=True)
+        order = order[:, :k]
+        return (torch.gather(self.nbr[vids], 1, order), t[:, :k], torch.gather(self.w[vids], 1, order))
+
+    def state_dict(self):
+        return {k: getattr(self, k).clone() for k in ("nbr", "ts", "w", "count") } | \
+               ({"feat": self.feat.clone(), "feat_ts": self.feat_ts.clone()} if self.feat is not None else {})
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            getattr(self, k).copy_(v)
+
+
+class QueryPlan(object):
+    """SOURCE -> sampler hops, e.g. QueryPlan("user").out("click", 10).out("sim", 5)."""
+
+    def __init__(self, source_type: str):
+        self.source_type = source_type
+        self.hops: List[tuple] = []
+
+    def out(self, edge_type: str, k: int, strategy: str = "topk_by_timestamp"):
+        assert strategy == "topk_by_timestamp", "the streaming sampler keeps the k most recent edges"
+        self.hops.append((edge_type, int(k)))
+        return self
+
+
+class AdaptiveRateLimiter(object):
+    """If fewer than 99 % of recent query latencies meet the P99 target, divide the ingest
+    concurrency by 3; after a stable window multiply it by 1.3 (adaptive_rate_limiter.cc:52-87)."""
+
+    def __init__(self, target_ms: float = 20.0, max_concurrency: int = 64, stable_windows: int = 3):
+        self.target_ms, self.max_c = target_ms, max_concurrency
+        self.concurrency = max_concurrency
+        self._lat: List[float] = []
+        self._stable = 0
+        self._need = stable_windows
+
+    def record(self, latency_ms: float):
+        self._lat.append(latency_ms)
+
+    def tick(self) -> int:
+        if self._lat:
+            ok = sum(1 for x in self._lat if x <= self.target_ms) / len(self._lat)
+            if ok < 0.99:
+                self.concurrency = max(1, self.concurrency // 3)
+                self._stable = 0
+            else:
+                self._stable += 1
+                if self._stable >= self._need:
+                    self.concurrency = min(self.max_c, max(self.concurrency + 1, int(self.concurrency * 1.3)))
+                    self._stable = 0
+        self._lat = []
+        return self.concurrency
+
+
+class DynamicGraphService(object):
+    def __init__(self, schema: Dict[str, dict], device=None):
+        """schema: {"vertices": {type: {"count": n, "feat_dim": d}}, "edges": {etype: {"src": t, "dst": t}}}"""
+        self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.schema = schema
+        self.stores: Dict[str, SampleStore] = {}
+        self.vstores: Dict[str, SampleStore] = {}
+        self.queries: Dict[int, QueryPlan] = {}
+        self.limiter = AdaptiveRateLimiter()
+        self.ingested = 0
+        for vt, info in schema["vertices"].items():
+            self.vstores[vt] = SampleStore(info["count"], 1, self.device, feat_dim=info.get("feat_dim", 0))
+
+    def install_query(self, qid: int, plan: QueryPlan):
+        """Allocates sampler state for every (edge type, capacity) the plan needs - like the
+        reference, only what a query subscribes to is kept."""
+        for etype, k in plan.hops:
+            e = self.schema["edges"][etype]
+            n = self.schema["vertices"][e["src"]]["count"]
+            cur = self.stores.get(etype)
+            if cur is None or cur.K < k:
+                st = SampleStore(n, k, self.device)
+                if cur is not None:                       # back-fill existing samples
+                    st.nbr[:, :cur.K], st.ts[:, :cur.K], st.w[:, :cur.K] = cur.nbr, cur.ts, cur.w
+                    st.count.copy_(cur.count)
+                self.stores[etype] = st
+        self.queries[qid] = plan
+
+    def apply_updates(self, batch: dict):
+        """batch: {"edges": {etype: {"src","dst","ts"[,"weight"]}}, "vertices": {vtype: {"id","ts","feat"}}}"""
+        for etype, rec in batch.get("edges", {}).items():
+            if etype in self.stores:
+                self.stores[etype].apply_edges(torch.as_tensor(rec["src"]), torch.as_tensor(rec["dst"]),
+                                               torch.as_tensor(rec["ts"]),
+                                               None if rec.get("weight") is None else torch.as_tensor(rec["weight"]))
+                self.ingested += len(rec["src"])
+        for vt, rec in batch.get("vertices", {}).items():
+            self.vstores[vt].apply_vertices(torch.as_tensor(rec["id"]), torch.as_tensor(rec["ts"]),
+                                            torch.as_tensor(rec["feat"]))
+
+    def run_query(self, qid: int, vids: Sequence[int]) -> dict:
+        """Batched inference-time lookup: hop i returns ids [B*prod(k_<i), k_i] (-1 padded) + timestamps,
+        and the latest features of every returned vertex."""
+        t0 = time.perf_counter()
+        plan = self.queries[qid]
+        cur = torch.as_tensor(list(vids) if not isinstance(vids, torch.Tensor) else vids, dtype=torch.int64).to(self.device)
+        out = {"src": cur, "hops": []}
+        cur_type = plan.source_type
+        for etype, k in plan.hops:
+            st = self.stores[etype]
+            safe = cur.clamp(min=0)
+            nbr, ts, w = st.lookup(safe.reshape(-1), k)
+            nbr = torch.where((cur.reshape(-1) >= 0)[:, None], nbr, torch.full_like(nbr, -1))
+            cur_type = self.schema["edges"][etype]["dst"]
+            vs = self.vstores[cur_type]
+            feat = vs.feat[nbr.clamp(min=0)] if vs.feat is not None else None
+            out["hops"].append({"edge_type": etype, "ids": nbr, "timestamps": ts, "weights": w, "features": feat})
+            cur = nbr.reshape(-1)
+        self.limiter.record((time.perf_counter() - t0) * 1e3)
+        return out
+
+    def checkpoint(self) -> dict:
+        return {"stores": {k: v.state_dict() for k, v in self.stores.items()},
+                "vstores": {k: v.state_dict() for k, v in self.vstores.items()}, "ingested": self.ingested}
+
+    def restore(self, ck: dict):
+        for k, v in ck["stores"].items():
+            self.stores[k].load_state_dict(v)
+        for k, v in ck["vstores"].items():
+            self.vstores[k].load_state_dict(v)
+        self.ingested = ck["ingested"]

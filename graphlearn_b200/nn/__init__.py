@@ -1,7 +1,9 @@
 """PyTorch model layer (``gl.nn``): the math of graphlearn/python/nn/tf/* re-implemented as
 torch Modules, with the GraphSAGE layer on the fused sm_100a kernel."""
 from . import loss  # noqa: F401
-from .conv import EgoGATConv, EgoGINConv, EgoLayer, EgoRGCNConv, EgoSAGEConv  # noqa: F401
+from .conv import (EgoGATConv, EgoGINConv, EgoLayer, EgoRGCNConv, EgoSAGEConv, EgoTGATConv,  # noqa: F401
+                   TimeEncoder)
+from .norm import compute_saint_norm  # noqa: F401
 from .data import BatchGraph, Data, EgoGraph, HeteroBatchGraph  # noqa: F401
 from .dataset import Dataset, TorchDataset  # noqa: F401
 from .feature import FeatureEncoder  # noqa: F401

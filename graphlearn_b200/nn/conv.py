@@ -171,3 +171,35 @@ class EgoLayer(nn.Module):
     def forward(self, x_list, expands):
         assert len(self.convs) == len(x_list) - 1
         return [self.convs[i](x_list[i], x_list[i + 1], expands[i]) for i in range(len(x_list) - 1)]
+
+
+class TimeEncoder(nn.Module):
+    """Functional time encoding cos(t * w + b) used by the temporal models (EgoTGAT / TGN:
+    graphlearn/python/nn/tf/data/temporal_graph.py, examples/tf/ego_tgat)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.lin = nn.Linear(1, dim)
+        with torch.no_grad():
+            self.lin.weight.copy_((1.0 / 10 ** torch.linspace(0, 9, dim)).view(dim, 1))
+            self.lin.bias.zero_()
+
+    def forward(self, t: torch.Tensor) -> torch.Tensor:
+        return torch.cos(self.lin(t.float().unsqueeze(-1)))
+
+
+class EgoTGATConv(nn.Module):
+    """Temporal GAT layer on ego graphs: attention over the k most recent neighbours with
+    [feature || time-encoding(t_self - t_edge)] keys (ego_tgat)."""
+
+    def __init__(self, in_dim: int, out_dim: int, time_dim: int = 16, num_head: int = 2):
+        super().__init__()
+        self.time = TimeEncoder(time_dim)
+        self.att = EgoGATConv((in_dim + time_dim, in_dim + time_dim), out_dim, num_head)
+
+    def forward(self, x, neighbor, expand, t_self, t_edge):
+        """x [M,d], neighbor [M*k,d], t_self [M], t_edge [M*k]."""
+        dt = t_self.repeat_interleave(expand) - t_edge
+        xs = torch.cat([x.float(), self.time(torch.zeros_like(t_self))], 1)
+        xn = torch.cat([neighbor.float(), self.time(dt)], 1)
+        return self.att(xs, xn, expand)

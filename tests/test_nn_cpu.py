@@ -186,3 +186,24 @@ def test_config_setters_and_errors():
     assert gl.errors.exception_type_from_error_code(5) is gl.errors.NotFoundError
     assert gl.strategy2op("edge_weight") == "EdgeWeightSampler"
     assert gl.get_mask_type("i", gl.Mask.TRAIN) == "MASKTRAIN_i"
+
+
+def test_generic_trainer_loop(tmp_path):
+    """engine.loop.Trainer over a GSL dataset: loss decreases, epoch ends on OutOfRange, ckpt written."""
+    from graphlearn_b200.engine.loop import Trainer
+    g = fx.build_graph(fx.write_graph(str(tmp_path / "g")))
+    q = g.V("user").batch(8).shuffle(traverse=True).alias("u").outV("buy").sample(3).by("edge_weight").alias("i").values()
+    ds = gl.Dataset(q)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+
+    def step(m, b):
+        x = b["i"].tensor("float_attrs").mean(1)
+        return F.cross_entropy(m(x), b["u"].tensor("labels"))
+
+    tr = Trainer(g.runtime, model, ds, step, lr=2e-2, ckpt_path=str(tmp_path / "ck"), ckpt_every=5, log_every=1000)
+    first = tr.train_epoch()
+    for _ in range(15):
+        last = tr.train_epoch()
+    assert tr.global_step == 16 * (fx.N_USER // 8) and last < first
+    assert os.path.exists(str(tmp_path / "ck") + ".rank0")
