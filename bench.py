@@ -106,15 +106,21 @@ def count_own_launches(trainer):
             torch.cuda.synchronize()
         own, lib = 0, 0
         names = {}
+        times = {}
         for ev in prof.events():
             if ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.name and \
                     not ev.name.startswith("Memcpy") and not ev.name.startswith("Memset"):
+                key = ev.name.split("(")[0][:60]
+                t = getattr(ev, "device_time", None)
+                if t is None:
+                    t = getattr(ev, "cuda_time", 0.0)
+                times[key] = round(times.get(key, 0.0) + float(t), 1)
                 if "glb::" in ev.name:
                     own += 1
-                    key = ev.name.split("(")[0]
                     names[key] = names.get(key, 0) + 1
                 else:
                     lib += 1
+        trainer._kernel_us = times
         return own, lib, names
     finally:
         trainer.graph = trainer_graph
@@ -145,7 +151,7 @@ def run_ours(args):
     model = EgoGraphSAGE(shape["feat_dim"], HIDDEN, shape["num_classes"], 2).to(rt.device)
     Trainer = SageTrainer if args.engine == "autograd" else FastSageTrainer
     tr = Trainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
-                 use_cuda_graph=not args.no_graph)
+                 use_cuda_graph=not args.no_graph, **({"gather_mode": args.gather_mode} if args.engine == "fast" else {}))
     # host-side seed stream: each rank traverses (shuffled) its own nodes, like the reference's
     # V().batch().shuffle(traverse=True) root which is unsharded (node_getter.cc:64-92)
     gen = torch.Generator().manual_seed(1234 + rt.rank)
@@ -208,12 +214,12 @@ def run_ours(args):
                        "feat_dim": shape["feat_dim"], "feature_storage": args.feature_dtype,
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
                                     % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * (2 if fdt == torch.bfloat16 else 4) / 1e9),
-                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine,
+                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine, "gather_mode": args.gather_mode,
                        "graph_build_s": round(build_s, 2)},
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": args.batch * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": own * args.steps, "own_kernels_per_step": own, "library_kernels_per_step": lib,
-            "own_kernel_names": names, "clocks": clk, "final_loss": final_loss,
+            "own_kernel_names": names, "kernel_us_eager_step": getattr(tr, "_kernel_us", {}), "clocks": clk, "final_loss": final_loss,
         }
         print(json.dumps(out))
     rt.barrier()
@@ -236,9 +242,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--feature-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--feature-dtype", default="bf16", choices=["fp32", "bf16"],
+                    help="HBM storage dtype of the float attribute table (compute is bf16 either way; bf16 halves NVLink bytes)")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gather-mode", type=int, default=0,
+                    help="fused SAGE kernel gather: 0 auto, 1 registers, 2 TMA ring, 3 cp.async ring, 4 split (gather kernel + GEMM)")
     ap.add_argument("--engine", default="fast", choices=["fast", "autograd"],
                     help="fast = hand-scheduled fwd/bwd kernel chain; autograd = torch.autograd over the same kernels")
     ap.add_argument("--small", action="store_true", help="small graph for quick functional runs")

@@ -55,6 +55,7 @@ struct SageParams {
   const char* zero_row;       // >= 2 KB of zeros: target of the loads of masked lanes / missing rows
   int wshift_self, wshift_nbr; // log2(world) of each table when it is a power of two, else -1
   long long* debug_ts;        // optional [grid][16] phase timestamps (clock64) written by thread 0
+  const __nv_bfloat16* a_src; // optional precomputed A [M, K_total] (row-major): skip the gather, just stage it
 };
 
 __device__ __forceinline__ float4 load4_rt(const void* row, int c, int dtype) {
@@ -216,6 +217,7 @@ __device__ __forceinline__ void sage_epilogue(const SageParams& p, uint32_t tmem
 // (2) issues ALL self + neighbour chunk loads of the batch unconditionally (masked lanes read a
 // zero row), (3) reduces in fp32, (4) writes bf16 into the SW128 A tile.
 constexpr int kMaxSlots = 64;
+constexpr int kProducers = 4;
 
 #define GLB_TS(i) do { if (p.debug_ts && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
@@ -263,6 +265,24 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
       umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
   }
 
+  const int R = p.rows_per_cta;
+  const int m0 = blockIdx.x * R;
+  if (p.a_src != nullptr) {
+    // split path (multi-GPU): A was produced by gather_self_mean_kernel; stage the tile with coalesced
+    // 16-byte loads -> swizzled 16-byte shared stores
+    const int R_ = p.rows_per_cta;
+    const int m0_ = blockIdx.x * R_;
+    const int chunks_row = k_total >> 3;                 // 16-byte chunks per A row
+    for (int i = tid; i < R_ * chunks_row; i += kThreads) {
+      const int r = i / chunks_row, c = i - r * chunks_row;
+      const int m = m0_ + r;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (m < p.M) v = ld_nc_u4(reinterpret_cast<const uint4*>(p.a_src + (size_t)m * k_total) + c);
+      const int kcol = c * 8;
+      *reinterpret_cast<uint4*>(sA + (size_t)(kcol >> 6) * (kTileM * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63))) = v;
+    }
+    GLB_TS(2);
+  } else {
   // --- phase 0: resolve the tile's neighbour / self ids into ROW POINTERS staged in shared memory
   //     (coalesced read of nbr_vids[m0*k .. (m0+R)*k); missing rows point at a zero row).  The
   //     hot loop below is then just  LDS.64 + IADD + LDG  per row chunk.
@@ -361,6 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
     for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
     put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
   }
+  }  // gather vs. dense-A
   GLB_TS(3);
   umma::fence_proxy_async_smem();     // generic-proxy st.shared -> visible to tcgen05 (async proxy)
   __syncthreads();
@@ -581,6 +602,285 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_tma_kernel(const SageP
   if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// cp.async-gather variant (the multi-GPU / multi-wave default).  Same ring-in-the-W-region structure
+// as the TMA variant, but the rows are moved by per-lane 16-byte cp.async (LDGSTS): normal LSU issue
+// rate (the TMA unit needs ~110 cycles per small bulk copy), zero registers held while in flight,
+// and the ring keeps ~128 KB of row fetches outstanding per SM - enough to cover NVLink peer
+// latency.  kProducers warps issue copies, the remaining warps reduce + write the A tile.
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 1) sage_fused_async_kernel(const SageParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  GLB_TS(0);
+  const int k_total = p.kp_self + p.kp_nbr;
+  const int nkb = k_total >> 6;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);                     // ring during the gather, W afterwards
+  const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;
+  const uint32_t w_bytes = (uint32_t)nkb * w_kb_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)w_bytes);
+  uint64_t* bar_w = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = bars + 4;                                           // [kMaxSlots]
+  uint64_t* empty = full + kMaxSlots;                                  // [kMaxSlots]
+  const char** sPtrN = reinterpret_cast<const char**>(empty + kMaxSlots);
+  const int R = p.rows_per_cta;
+  const int k = p.k;
+  const char** sPtrS = sPtrN + (size_t)R * k;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  constexpr int VEC = Chunk<DT>::kVec;
+  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
+  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+  // bytes actually copied per row: the real features rounded up to 16 B (never more than the stride)
+  const uint32_t nbr_copy = min(nbr_row_bytes, (uint32_t)((p.tnbr.dim * (DT == 0 ? 4 : 2) + 15) & ~15));
+  const uint32_t self_copy = need_self ? min(self_row_bytes, (uint32_t)((p.tself.dim * (DT == 0 ? 4 : 2) + 15) & ~15)) : 0u;
+  const uint32_t slot_bytes = self_copy + (uint32_t)k * nbr_copy;
+  constexpr int P = kProducers;                                         // producer warps
+  const int S = (min((int)(w_bytes / slot_bytes), kMaxSlots) / P) * P;   // slot s belongs to producer s % P
+
+  if (tid == 0) {
+    umma::mbar_init(bar_w, 1);
+    umma::mbar_init(bar_mma, 1);
+    for (int s = 0; s < S; ++s) { umma::mbar_init(full + s, 32); umma::mbar_init(empty + s, 1); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    umma::tmem_relinquish();
+  }
+  // resolve ids -> row pointers (coalesced), as in the register variant
+  const int m0 = blockIdx.x * R;
+  {
+    const int64_t base = (int64_t)m0 * k;
+    const int64_t lim = (int64_t)p.M * k;
+    for (int i = tid; i < R * k; i += kThreads) {
+      const int64_t idx = base + i;
+      uint32_t loc = 0xFFFFFFFFu;
+      if (idx < lim) loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr);
+      sPtrN[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) : p.zero_row;
+    }
+    for (int i = tid; i < R; i += kThreads) {
+      const int m = m0 + i;
+      uint32_t loc = 0xFFFFFFFFu;
+      if (need_self && m < p.M) loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self);
+      sPtrS[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) : p.zero_row;
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  GLB_TS(2);
+
+  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
+  const bool has_self = p.kp_self > 0;
+  float scale = 1.f;
+  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
+  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
+
+  if (warp < P) {
+    // ===== producers: warp p fills the slots s = p (mod P); every lane moves 16-byte chunks with
+    //       cp.async (LDGSTS) and the slot's mbarrier fires when all 32 lanes' copies have landed =====
+    const uint32_t cps = self_copy >> 4, cpn = nbr_copy >> 4;          // 16-byte chunks per row
+    const uint32_t total = cps + (uint32_t)k * cpn;
+    for (int turn = 0; turn * S < R; ++turn)
+    for (int s = warp; s < S; s += P) {
+      const int i = turn * S + s;
+      if (i >= R) break;
+      if (turn > 0) umma::mbar_wait(empty + s, (uint32_t)((turn - 1) & 1));
+      uint8_t* slot = sW + (size_t)s * slot_bytes;
+      const char* sp = sPtrS[i];
+      const char* const* np = sPtrN + (size_t)i * k;
+      for (uint32_t c = lane; c < total; c += 32) {
+        const char* src;
+        if (c < cps) src = sp + (size_t)c * 16;
+        else { const uint32_t cc = c - cps; const uint32_t j = cc / cpn; src = np[j] + (size_t)(cc - j * cpn) * 16; }
+        umma::cp_async16(slot + (size_t)c * 16, src);
+      }
+      umma::cp_async_mbar_arrive_noinc(full + s);
+    }
+  } else {
+    // ===== consumers =====
+    // Slot s is always drained by the SAME consumer warp (s % C) in increasing turn order: an
+    // mbarrier only distinguishes the parity of a phase, so two warps waiting for different turns
+    // of one slot would alias.
+    const int nchunks = p.kp_nbr / VEC;                  // 16-byte chunks per K half
+    const int C = kWarps - P, c = warp - P;
+    for (int turn = 0; turn * S < R; ++turn)
+    for (int s = c; s < S; s += C) {
+      const int i = turn * S + s;
+      if (i >= R) break;
+      umma::mbar_wait(full + s, (uint32_t)(turn & 1));
+      const uint8_t* slot = sW + (size_t)s * slot_bytes;
+      const int m = m0 + i;
+      const size_t a_off = (size_t)m * k_total;
+      __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
+      for (int chunk = lane; chunk < nchunks; chunk += 32) {
+        const int f0 = chunk * VEC;
+        float acc[VEC], sv[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { acc[q] = 0.f; sv[q] = 0.f; }
+        if (f0 < d_nbr) {
+          const uint8_t* np = slot + self_copy + (size_t)chunk * 16;
+          for (int j = 0; j < k; ++j) {
+            Chunk<DT> c;
+            c.v = *reinterpret_cast<const decltype(c.v)*>(np + (size_t)j * nbr_copy);
+            c.add_to(acc);
+          }
+        }
+        if (need_self && f0 < d_self) {
+          Chunk<DT> c;
+          c.v = *reinterpret_cast<const decltype(c.v)*>(slot + (size_t)chunk * 16);
+          c.add_to(sv);
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          if (f0 + q >= d_self) sv[q] = 0.f;
+          if (f0 + q >= d_nbr) acc[q] = 0.f;
+        }
+        if (has_self) put_chunk<VEC>(sA, asave, a_off, i, f0, sv);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = (acc[q] + (p.mode == kGcnMean ? sv[q] : 0.f)) * scale;
+        put_chunk<VEC>(sA, asave, a_off, i, p.kp_self + f0, acc);
+      }
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(empty + s);
+    }
+  }
+  GLB_TS(3);
+  umma::fence_proxy_async_smem();     // A-tile st.shared visible to tcgen05; ring reads ordered before the W copy
+  __syncthreads();
+  GLB_TS(4);
+
+  // --- weights into the (now idle) ring region, then the MMAs
+  if (tid == 0) {
+    umma::mbar_arrive_expect_tx(bar_w, w_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_img);
+    for (int kb = 0; kb < nkb; ++kb)
+      umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
+    umma::mbar_wait(bar_w, 0);
+    GLB_TS(5);
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
+      const uint32_t b_base = umma::smem_u32(sW + (size_t)kb * w_kb_bytes);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma::mma_bf16_ss(tmem_base, umma::make_desc_sw128(a_base + k4 * 32),
+                          umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
+    }
+    umma::mma_commit(bar_mma);
+    GLB_TS(6);
+  }
+  __syncwarp();
+  umma::mbar_wait(bar_mma, 0);
+  GLB_TS(7);
+  umma::tc_fence_after();
+  sage_epilogue(p, tmem_base, m0, R, warp, lane);
+  GLB_TS(8);
+  umma::tc_fence_before();
+  __syncthreads();
+  GLB_TS(9);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split path, stage 1 (used when rows live on peer GPUs): a small, maximum-occupancy kernel
+// (256 threads, ~40 registers -> 48-64 resident warps per SM) that only gathers + aggregates and
+// writes the bf16 A matrix [M, K_total] = [ self || agg(nbrs) ] (zero K-padding included).  NVLink
+// peer reads need far more requests in flight than the 1-CTA/SM fused kernel can keep up
+// (measured: 580-640 GB/s remote for this shape vs ~170 GB/s inside the fused kernel); stage 2 is
+// the same tcgen05 kernel fed from this (L2-resident) A instead of gathering itself.
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256, 5) gather_self_mean_kernel(const SageParams p) {
+  constexpr int VEC = Chunk<DT>::kVec;
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31;
+  const int k = p.k;
+  const int k_total = p.kp_self + p.kp_nbr;
+  const int lanes_row = p.kp_nbr / VEC;
+  const int lpr = lanes_row < 32 ? lanes_row : 32;
+  const int lshift = 31 - __clz(lpr);
+  const int rpi = 32 >> lshift;
+  const int n_slices = lanes_row > 32 ? lanes_row >> 5 : 1;
+  const int sub = lane >> lshift, lig = lane & (lpr - 1);
+  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
+  const bool has_self = p.kp_self > 0;
+  const bool need_self = has_self || p.mode == kGcnMean;
+  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+  float scale = 1.f;
+  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
+  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
+  const int64_t n_items = ((int64_t)p.M + rpi - 1) / rpi * n_slices;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps) {
+    const int64_t rg = item / n_slices;
+    const int sl = (int)(item - rg * n_slices);
+    const int64_t m = rg * rpi + sub;
+    if (m >= p.M) continue;
+    const int chunk = lig + 32 * sl;
+    const int f0 = chunk * VEC;
+    const size_t coff = (size_t)chunk * 16;
+    float acc[VEC], sv[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
+    if (f0 < d_nbr || (need_self && f0 < d_self)) {
+      Chunk<DT> sraw;
+      const bool self_ld = need_self && f0 < d_self;
+      if (self_ld) {
+        const uint32_t loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : m, p.wshift_self);
+        sraw.load(loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) + coff : p.zero_row + coff);
+      }
+      if (f0 < d_nbr) {
+        const int64_t base = m * k;
+        for (int j0 = 0; j0 < k; j0 += U) {
+          Chunk<DT> raw[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + u < k ? j0 + u : k - 1;
+            const uint32_t loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + base + j) : base + j, p.wshift_nbr);
+            raw[u].load(loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) + coff : p.zero_row + coff);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (j0 + u < k) raw[u].add_to(acc);
+        }
+      }
+      if (self_ld) sraw.add_to(sv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        if (f0 + i >= d_self) sv[i] = 0.f;
+        if (f0 + i >= d_nbr) acc[i] = 0.f;
+      }
+    }
+    __nv_bfloat16* out = p.a_save + (size_t)m * k_total;
+    auto store = [&](int kcol, const float (&v)[VEC]) {
+      if constexpr (VEC == 4) {
+        uint2 u2; u2.x = pack_bf16x2(v[0], v[1]); u2.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(out + kcol) = u2;
+      } else {
+        uint4 u4; u4.x = pack_bf16x2(v[0], v[1]); u4.y = pack_bf16x2(v[2], v[3]);
+        u4.z = pack_bf16x2(v[4], v[5]); u4.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(out + kcol) = u4;
+      }
+    };
+    if (has_self) store(f0, sv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
+    store(p.kp_self + f0, acc);
+  }
+}
+
 // bf16 row-major [n_real, k_total] -> SW128 K-major image with N (>= n_real) rows per k-block
 __global__ void pack_sw128_kernel(const __nv_bfloat16* __restrict__ w, int n_real, int N, int k_total,
                                   uint8_t* __restrict__ img) {
@@ -680,6 +980,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
                                            const c10::optional<at::Tensor>& out_buf,
                                            const c10::optional<at::Tensor>& a_buf,
                                            const c10::optional<at::Tensor>& debug_ts, int64_t gather_mode) {
+  // gather_mode 4 = split path: gather_self_mean_kernel -> A (global) -> tcgen05 kernel staged from A
   TORCH_CHECK(w_img.is_cuda() && w_img.scalar_type() == at::kBFloat16, "w_img must be CUDA bf16");
   c10::cuda::CUDAGuard guard(w_img.device());
   SageParams p;
@@ -728,6 +1029,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
     }
     p.a_save = reinterpret_cast<__nv_bfloat16*>(a_save.data_ptr());
   }
+  p.a_src = nullptr;
   p.w_img = w_img.data_ptr();
   p.out = out.data_ptr();
   p.out_stride = out.stride(0);
@@ -774,13 +1076,37 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   auto stream = at::cuda::getCurrentCUDAStream();
   const int u = k <= 4 ? 4 : (k % 5 == 0 || k > 12) ? 5 : 6;
   const int dt = p.tnbr.dtype;
+  // MEASURED (2 GPUs, fp32 rows): fused register path 7.7k steps/s vs split 6.9k - the remote rows are
+  // NVLink-bandwidth bound either way (394 GB/s achieved vs 580 GB/s best random-row rate), so the
+  // split path stays opt-in.
+  const bool split = gather_mode == 4;
+  if (split) {
+    if (!a_save.defined()) {
+      a_save = at::empty({M, (int64_t)k_total}, opts.dtype(at::kBFloat16));
+      p.a_save = reinterpret_cast<__nv_bfloat16*>(a_save.data_ptr());
+    }
+    const int lanes_row = p.kp_nbr / (dt == 0 ? 4 : 8);
+    const int rpi = lanes_row < 32 ? 32 / lanes_row : 1;
+    const int n_slices = lanes_row > 32 ? lanes_row / 32 : 1;
+    const int64_t items = (M + rpi - 1) / rpi * n_slices;
+    const unsigned gblocks = (unsigned)std::min<int64_t>((items + 7) / 8, 148 * 8);
+    if (dt == 0) gather_self_mean_kernel<0><<<gblocks, 256, 0, stream>>>(p);
+    else         gather_self_mean_kernel<1><<<gblocks, 256, 0, stream>>>(p);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    p.a_src = p.a_save;
+    p.a_save = nullptr;
+  }
   // gather_mode: 1 = register-staged loads, 2 = TMA bulk copies into the shared-memory ring,
-  // 0 = auto = register-staged.  MEASURED (profiles/): per-row cp.async.bulk copies of 400 B cost
+  // 3 = per-lane cp.async into the same ring; 0 = auto = cp.async ring for multi-wave launches and
+  // whenever rows may live on a peer GPU, register-staged otherwise.  MEASURED (profiles/): per-row cp.async.bulk copies of 400 B cost
   // ~110 cycles each in the TMA unit (1408 copies -> 153 k cycles per 128-row tile, 0.76 TB/s), 4x
   // slower than the register path (36 k cycles) - the ring variant is kept for wide rows only.
   const size_t slot_bytes = (size_t)(k + 1) * (size_t)p.tnbr.stride * (dt == 0 ? 4 : 2);
   const bool tma_ok = k >= 1 && slot_bytes <= (size_t)k_total / 64 * N * 128;
   bool use_tma = gather_mode == 2;
+  // cp.async ring (mode 3): needs >= kProducers slots
+  const bool async_ok = k >= 1 && slot_bytes * kProducers <= (size_t)k_total / 64 * N * 128;
+  bool use_async = gather_mode == 3 && async_ok;   // MEASURED slower than the register path (2-GPU: 5.4k vs 7.7k steps/s)
   use_tma = use_tma && tma_ok;
 #define SET_ATTR(KERNEL)                                                                          \
   do {                                                                                            \
@@ -795,7 +1121,10 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
     SET_ATTR((sage_fused_fwd_kernel<UU, DD>));                                                    \
     sage_fused_fwd_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                           \
   } while (0)
-  if (use_tma) {
+  if (use_async) {
+    if (dt == 0) { SET_ATTR(sage_fused_async_kernel<0>); sage_fused_async_kernel<0><<<grid, kThreads, smem, stream>>>(p); }
+    else         { SET_ATTR(sage_fused_async_kernel<1>); sage_fused_async_kernel<1><<<grid, kThreads, smem, stream>>>(p); }
+  } else if (use_tma) {
     if (dt == 0) { SET_ATTR(sage_fused_tma_kernel<0>); sage_fused_tma_kernel<0><<<grid, kThreads, smem, stream>>>(p); }
     else         { SET_ATTR(sage_fused_tma_kernel<1>); sage_fused_tma_kernel<1><<<grid, kThreads, smem, stream>>>(p); }
   } else if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
@@ -803,7 +1132,7 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
 #undef LAUNCH
 #undef SET_ATTR
   C10_CUDA_KERNEL_LAUNCH_CHECK();
-  return {out, save_a ? a_save : at::Tensor()};
+  return {out, (save_a || split) ? a_save : at::Tensor()};
 }
 
 }  // namespace glb

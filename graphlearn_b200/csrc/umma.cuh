@@ -47,6 +47,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS, per-lane 16 B)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival from this thread once all of the thread's prior
+// cp.async copies have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA (bulk, non-tensor)
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier
 // (SASS: UBLKCP).  size must be a multiple of 16, both addresses 16 B aligned.
