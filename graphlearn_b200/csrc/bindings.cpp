@@ -12,6 +12,9 @@ void rng_advance(const at::Tensor&, int64_t);
 // walk.cu
 at::Tensor random_walk(const at::Tensor&, const at::Tensor&, int64_t, double, double, int64_t, int64_t,
                        const at::Tensor&, int64_t);
+// negative.cu
+at::Tensor negative_sample(const at::Tensor&, const at::Tensor&, int64_t, const c10::optional<at::Tensor>&,
+                           const at::Tensor&, int64_t, bool, int64_t, int64_t, const at::Tensor&, int64_t);
 // gather.cu
 at::Tensor gather_rows(const at::Tensor&, const at::Tensor&, bool, double);
 at::Tensor gather_agg(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t);
@@ -55,6 +58,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sample_full", &glb::sample_full);
   m.def("rng_advance", &glb::rng_advance);
   m.def("random_walk", &glb::random_walk);
+  m.def("negative_sample", &glb::negative_sample);
   m.def("gather_rows", &glb::gather_rows);
   m.def("gather_agg", &glb::gather_agg);
   m.def("scatter_add_rows", &glb::scatter_add_rows);

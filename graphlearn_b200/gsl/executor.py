@@ -210,7 +210,8 @@ class QueryExecutor(object):
         else:
             et = p["edge_type"]
             dst_t = self.store.edges[et].dst_type if p.get("direction", "out") == "out" else self.store.edges[et].src_type
-            neg = NEG.edge_negative(self.store, et, src_v, k, strategy, gen, direction=p.get("direction", "out"))
+            neg = NEG.edge_negative(self.store, et, src_v, k, strategy, gen, direction=p.get("direction", "out"),
+                                    rng=self.rng, salt=self._salt)
         ids = self.g.to_ids(dst_t, neg)
         out = _Out(ids=ids, vids=neg, shape=(B, k))
         out.value = V_.Nodes(ids, dst_t, shape=(B, k), graph=self.g, vids=neg)

@@ -98,12 +98,40 @@ def _is_neighbor(csr, src_v: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
     return (keys[pos] == q.reshape(-1)).reshape(B, k)
 
 
-def edge_negative(store, etype: str, src_v: torch.Tensor, k: int, strategy: str, gen, direction: str = "out"):
+def _shard_offsets(tab, device):
+    off = [0]
+    for n in tab.nrows:
+        off.append(off[-1] + int(n))
+    return torch.tensor(off, dtype=torch.int64, device=device), off[-1]
+
+
+def edge_negative(store, etype: str, src_v: torch.Tensor, k: int, strategy: str, gen, direction: str = "out",
+                  rng=None, salt: int = 0):
     cfg = _config.get()
     csr = store.edges[etype] if direction == "out" else store.reverse_csr(etype)
     dst_tab = store.nodes[csr.dst_type]
     B = int(src_v.numel())
     dev = src_v.device
+    if store.rt.is_cuda and cfg.use_peer_kernels and rng is not None and strategy in ("random", "in_degree"):
+        # K2 kernel: candidate draw + neighbour rejection against the (peer-mapped) CSR in one launch
+        from ..parallel.runtime import native
+        cum = None
+        if strategy == "in_degree":
+            key = ("indeg", etype, direction)
+            if key not in _CACHE:
+                if direction == "out":
+                    store.reverse_csr(etype)
+                    wloc = dst_tab.in_degrees[etype].float()
+                else:
+                    wloc = store.nodes[csr.dst_type].out_degrees[etype].float()
+                _CACHE[key] = _WeightedSampler(store.rt, wloc)
+            cum = _CACHE[key].cum
+        off, total = _shard_offsets(dst_tab, dev)
+        if total == 0:
+            return torch.full((B, k), -1, dtype=torch.int64, device=dev)
+        return native().negative_sample(csr.desc, src_v.reshape(-1), int(k), cum, off, int(total),
+                                        strategy == "in_degree", int(cfg.neg_sampling_retry_times), 1024,
+                                        rng.state, int(salt))
     if strategy == "random":
         return _draw_global_uniform(dst_tab, B, k, gen, dev)
     if strategy == "in_degree":

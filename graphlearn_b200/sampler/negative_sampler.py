@@ -30,7 +30,7 @@ class NegativeSampler(object):
         if self._is_edge:
             csr = g.store.edges[self._type]
             src_v = g.to_vids(csr.src_type, ids_t)
-            neg = NEG.edge_negative(g.store, self._type, src_v, self._k, self._strategy, gen)
+            neg = NEG.edge_negative(g.store, self._type, src_v, self._k, self._strategy, gen, rng=self._rng, salt=7)
             dst_t = csr.dst_type
         else:
             src_v = g.to_vids(self._type, ids_t)

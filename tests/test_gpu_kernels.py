@@ -347,3 +347,32 @@ def test_random_walk(rt, graph):
                 else:
                     assert int(w[b, s]) == 0
             cur = w[:, s]
+
+
+def test_negative_sampler_kernel(rt, graph):
+    """K2: in_degree negatives are never true neighbours; the draw follows the in-degree distribution."""
+    from graphlearn_b200.graph import Graph
+    from graphlearn_b200.ops import negative as NEG
+    from graphlearn_b200.ops import rng as R
+    from graphlearn_b200.store.graph_store import GraphStore
+    nodes, csr = graph
+    store = GraphStore(rt)
+    store.nodes["n"], store.edges["e"] = nodes, csr
+    store.topology.add("e", "n", "n")
+    rng = R.DeviceRng(rt, 3)
+    src = torch.randint(0, 5000, (2000,), device=rt.device)
+    ip, idx = _adj(csr)
+    for strat in ("random", "in_degree"):
+        neg = NEG.edge_negative(store, "e", src, 5, strat, None, rng=rng, salt=11)
+        assert neg.shape == (2000, 5) and int(neg.min()) >= 0 and int(neg.max()) < 5000
+        if strat == "in_degree":
+            nc, sc = neg.cpu(), src.cpu()
+            bad = 0
+            for b in range(2000):
+                a = set(idx[int(ip[sc[b]]):int(ip[sc[b] + 1])].tolist())
+                bad += sum(1 for x in nc[b].tolist() if x in a)
+            assert bad == 0, bad
+            indeg = torch.bincount(csr.indices.local, minlength=5000).float().cpu()
+            cnt = torch.bincount(neg.reshape(-1).cpu(), minlength=5000).float()
+            hi = indeg > indeg.median()
+            assert cnt[hi].sum() > 0.6 * cnt.sum()
