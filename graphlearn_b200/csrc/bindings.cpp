@@ -34,6 +34,8 @@ void softmax_ce(const at::Tensor&, const at::Tensor&, const c10::optional<at::Te
 void sage_bwd_input(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t, int64_t, double,
                     const c10::optional<at::Tensor>&, const at::Tensor&, const c10::optional<at::Tensor>&);
 std::vector<at::Tensor> pack_weight_f32(const at::Tensor&, int64_t, bool);
+at::Tensor tc_linear_forward(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t, bool,
+                             bool);
 // comm.cu
 int64_t symm_alloc(int64_t, int64_t);
 void symm_free(int64_t, int64_t);
@@ -67,6 +69,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("pack_weight_sw128", &glb::pack_weight_sw128);
   m.def("sage_fused_forward", &glb::sage_fused_forward);
   m.def("pack_weight_f32", &glb::pack_weight_f32);
+  m.def("tc_linear_forward", &glb::tc_linear_forward);
   m.def("softmax_ce", &glb::softmax_ce);
   m.def("sage_bwd_input", &glb::sage_bwd_input);
   m.def("symm_alloc", &glb::symm_alloc);

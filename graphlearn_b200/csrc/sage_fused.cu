@@ -21,6 +21,7 @@
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <cstring>
 #include "host_utils.h"
 #include "umma.cuh"
 
@@ -1133,6 +1134,51 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
 #undef SET_ATTR
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, (save_a || split) ? a_save : at::Tensor()};
+}
+
+// K7 standalone: out = act(A . W^T + b) for a dense bf16 A [M, K] (K multiple of 64, <= 512; N <= 256)
+// on the same tcgen05 / TMEM tile kernel (A staged from global memory instead of gathered).
+at::Tensor tc_linear_forward(const at::Tensor& a, const at::Tensor& w_img, const c10::optional<at::Tensor>& bias,
+                             int64_t N, int64_t n_out, bool relu, bool out_bf16) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.is_contiguous(),
+              "A must be a contiguous CUDA bf16 [M, K] matrix");
+  const int64_t M = a.size(0), K = a.size(1);
+  TORCH_CHECK(K % 64 == 0 && K >= 64 && K <= 512, "K must be a multiple of 64 in [64, 512]");
+  TORCH_CHECK(N % 64 == 0 && N >= 64 && N <= 256 && n_out <= N && n_out >= 1);
+  TORCH_CHECK(w_img.numel() == K * N && w_img.scalar_type() == at::kBFloat16, "weight image size mismatch");
+  c10::cuda::CUDAGuard guard(a.device());
+  SageParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.tself.world = 1; p.tnbr.world = 1;
+  p.tself.dtype = 1; p.tnbr.dtype = 1;
+  p.M = (int)M; p.k = 0; p.mode = kConcatMean;
+  p.kp_self = 0; p.kp_nbr = (int)K;
+  at::Tensor b;
+  if (bias.has_value()) { b = bias->contiguous();
+    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out); p.bias = b.data_ptr<float>(); }
+  auto out = at::empty({M, n_out}, a.options().dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
+  p.w_img = w_img.data_ptr(); p.out = out.data_ptr(); p.out_stride = n_out;
+  p.N = (int)N; p.n_out = (int)n_out; p.relu = relu ? 1 : 0; p.out_bf16 = out_bf16 ? 1 : 0;
+  p.tmem_cols = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  p.a_src = reinterpret_cast<const __nv_bfloat16*>(a.data_ptr());
+  if (M == 0) return out;
+  size_t smem = (size_t)sage_smem_bytes(K, N);
+  TORCH_CHECK(smem <= 232448, "tile does not fit in shared memory");
+  const int64_t sms = 148;
+  int64_t waves = (M + sms * kTileM - 1) / (sms * kTileM);
+  int64_t want = (M + sms * waves - 1) / (sms * waves);
+  int R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (want + 7) / 8 * 8));
+  p.rows_per_cta = R;
+  smem += 32 + 2 * kMaxSlots * 8 + 64;
+  unsigned grid = (unsigned)((M + R - 1) / R);
+  static bool attr_done = false;
+  if (!attr_done) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_fwd_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+  sage_fused_fwd_kernel<4, 1><<<grid, kThreads, smem, at::cuda::getCurrentCUDAStream()>>>(p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return out;
 }
 
 }  // namespace glb

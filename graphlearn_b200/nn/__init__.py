@@ -6,5 +6,6 @@ from .conv import (EgoGATConv, EgoGINConv, EgoLayer, EgoRGCNConv, EgoSAGEConv, E
 from .norm import compute_saint_norm  # noqa: F401
 from .data import BatchGraph, Data, EgoGraph, HeteroBatchGraph  # noqa: F401
 from .dataset import Dataset, TorchDataset  # noqa: F401
+from .embedding import ShardedEmbedding  # noqa: F401
 from .feature import FeatureEncoder  # noqa: F401
 from .sparse_conv import GATConv, GCNConv, SAGEConv, segment_softmax  # noqa: F401

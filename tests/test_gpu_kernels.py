@@ -376,3 +376,36 @@ def test_negative_sampler_kernel(rt, graph):
             # size-biased draw: E[indeg | sampled] = E[d^2]/E[d] > E[d]
             sampled_mean = indeg[neg.reshape(-1).cpu()].mean()
             assert float(sampled_mean) > float(indeg.mean()) + 0.4, (float(sampled_mean), float(indeg.mean()))
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 100, 47), (4096, 256, 256), (130, 512, 64), (20000, 64, 128)])
+def test_tc_linear(rt, M, K, N):
+    """standalone tcgen05 dense layer (K7) vs fp32 reference, forward and backward."""
+    from graphlearn_b200.ops.linear import tc_linear
+    g = torch.Generator(device=rt.device).manual_seed(M + K)
+    x = torch.randn(M, K, device=rt.device, generator=g).to(torch.bfloat16).requires_grad_()
+    w = (torch.randn(N, K, device=rt.device, generator=g) / math.sqrt(K)).requires_grad_()
+    b = torch.randn(N, device=rt.device, generator=g).requires_grad_()
+    y = tc_linear(x, w, b, relu=True)
+    go = torch.randn(M, N, device=rt.device, generator=g)
+    y.backward(go)
+    x2, w2, b2 = x.detach().float().requires_grad_(), w.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    y2 = torch.relu(torch.nn.functional.linear(x2, w2, b2))
+    y2.backward(go)
+    assert (y - y2).abs().max() < 0.05
+    for a_, r_, name in ((w.grad, w2.grad, "w"), (b.grad, b2.grad, "b"), (x.grad.float(), x2.grad, "x")):
+        rel = (a_ - r_).abs().max() / (r_.abs().max() + 1e-6)
+        assert rel < 0.03, (name, float(rel))
+
+
+def test_sharded_embedding_gpu(rt):
+    from graphlearn_b200 import nn as glnn
+    emb = glnn.ShardedEmbedding(rt, 1000, 32, lr=0.1)
+    w0 = emb.local_weight().clone()
+    ids = torch.tensor([3, 3, 10, 999], device=rt.device)
+    out = emb(ids)
+    assert torch.equal(out[0], w0[3])
+    out.sum().backward()
+    w1 = emb.local_weight()
+    assert torch.allclose(w1[3], w0[3] - 0.2, atol=1e-6) and torch.allclose(w1[10], w0[10] - 0.1, atol=1e-6)
+    assert torch.equal(w1[11], w0[11])

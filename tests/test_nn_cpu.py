@@ -207,3 +207,16 @@ def test_generic_trainer_loop(tmp_path):
         last = tr.train_epoch()
     assert tr.global_step == 16 * (fx.N_USER // 8) and last < first
     assert os.path.exists(str(tmp_path / "ck") + ".rank0")
+
+
+def test_sharded_embedding_sparse_sgd():
+    from graphlearn_b200.parallel.runtime import init
+    rt = init(device="cpu")
+    emb = glnn.ShardedEmbedding(rt, 50, 8, lr=0.5)
+    w0 = emb.local_weight().clone()
+    ids = torch.tensor([[1, 2], [2, 7]])
+    out = emb(ids)
+    assert out.shape == (2, 2, 8) and torch.allclose(out[0, 0], w0[1])
+    out.sum().backward()
+    w1 = emb.local_weight()
+    assert torch.allclose(w1[1], w0[1] - 0.5) and torch.allclose(w1[2], w0[2] - 1.0) and torch.allclose(w1[3], w0[3])
