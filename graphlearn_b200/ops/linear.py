@@ -38,7 +38,9 @@ class _TcLinearFn(torch.autograd.Function):
             g = g * (out > 0).to(g.dtype)
         g16 = g.to(torch.bfloat16)
         dx = (g16 @ w16)[:, :ctx.k_in] if ctx.needs_input_grad[0] else None
-        dw = (g16.t() @ a).float()[:, :ctx.k_in] if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = (torch.mm(g16.t(), a, out_dtype=torch.float32) if sage_ops._HAS_OUT_DTYPE else (g16.t() @ a).float())[:, :ctx.k_in]
         db = g.float().sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db, None, None
 
