@@ -146,8 +146,12 @@ def edge_negative(store, etype: str, src_v: torch.Tensor, k: int, strategy: str,
         ws = _CACHE[key]
         neg = ws.draw((B, k), gen, dev)
         for _ in range(max(1, cfg.neg_sampling_retry_times)):
-            bad = _is_neighbor(csr, src_v, neg)
-            if not bool(bad.any()):
+            bad = _is_neighbor(csr, src_v, neg)             # collective when world > 1
+            any_bad = bad.any().to(torch.int32).reshape(1)
+            if store.rt.world > 1:                          # every rank must run the same number of rounds
+                import torch.distributed as dist
+                dist.all_reduce(any_bad, op=dist.ReduceOp.MAX)
+            if int(any_bad.item()) == 0:
                 break
             redraw = ws.draw((B, k), gen, dev)
             neg = torch.where(bad, redraw, neg)

@@ -1,0 +1,82 @@
+"""SPMD worker: the PUBLIC API (gl.Graph from TSV files, GSL, samplers, lookups) on >= 2 ranks.
+Each rank only stores its hash partition; results must equal the closed-form fixture."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import graphlearn_b200 as gl
+from tests import fixtures as fx
+
+
+def main():
+    d = sys.argv[1]
+    dev = "cpu" if os.environ.get("GLB_TEST_DEVICE", "") == "cpu" else None
+    g = gl.Graph()
+    g.node(os.path.join(d, "user.tsv"), "user",
+           decoder=gl.Decoder(weighted=True, labeled=True, attr_types=["int", "int", ("string", 16), "float"]))
+    g.node(os.path.join(d, "item.tsv"), "item", decoder=gl.Decoder(attr_types=["float"] * 4))
+    g.edge(os.path.join(d, "u2i.tsv"), ("user", "item", "buy"), decoder=gl.Decoder(weighted=True))
+    g.edge(os.path.join(d, "i2i.tsv"), ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
+    g.init(device=dev)
+    rt = g.runtime
+    W, r = rt.world, rt.rank
+    assert W >= 2
+    st = g.get_stats()
+    assert sum(st["user"]) == fx.N_USER and sum(st["item"]) == fx.N_ITEM
+    assert sum(st["buy"]) == sum((u % 5) + 1 for u in range(fx.N_USER))
+    # lookups of ids owned by OTHER ranks
+    ids = np.arange(fx.N_USER)
+    n = g.lookup_nodes("user", ids)
+    assert np.allclose(n.weights, 1.0 + ids) and (n.labels == ids % 3).all()
+    assert np.allclose(n.float_attrs[:, 0], ids / 2.0) and (n.int_attrs[:, 0] == ids).all()
+    it = g.lookup_nodes("item", np.arange(fx.N_ITEM))
+    assert np.allclose(it.float_attrs[:, 1], np.arange(fx.N_ITEM) + 0.25)
+    # neighbour sampling from seeds on any rank
+    adj = fx.u2i_adj()
+    for strategy in ("random", "topk", "edge_weight", "random_without_replacement"):
+        lay = g.neighbor_sampler(["buy", "sim"], [3, 2], strategy=strategy if strategy != "edge_weight" else "random").get(ids)
+        n1 = lay.layer_nodes(1).ids
+        for u in ids:
+            assert set(n1[u].tolist()) <= {x[0] for x in adj[u]}
+        n2 = lay.layer_nodes(2).ids
+        dd = (n2 - n1.reshape(-1)[:, None]) % fx.N_ITEM
+        assert ((dd >= 1) & (dd <= 3)).all()
+    assert g.out_degrees(ids, "buy").tolist() == [len(adj[u]) for u in ids]
+    exp = np.zeros(fx.N_ITEM, int)
+    for u in adj:
+        for i, _ in adj[u]:
+            exp[i] += 1
+    assert g.in_degrees(np.arange(fx.N_ITEM), "buy").tolist() == exp.tolist()
+    # GSL: every rank traverses ITS OWN users; union over ranks = all users, once per epoch
+    q = g.V("user").batch(4).alias("u").outV("buy").sample(2).by("random").alias("i") \
+         .outV("sim").sample(2).by("topk").alias("ii").values()
+    ds = gl.Dataset(q)
+    mine = []
+    try:
+        while True:
+            res = ds.next()
+            mine.extend(res["u"].ids.tolist())
+            assert res["ii"].float_attrs.shape[-1] == 4
+            assert (res["u"].labels == res["u"].ids % 3).all()
+    except gl.OutOfRangeError:
+        pass
+    assert all(u % W == r for u in mine)
+    allu = rt.all_gather_object(mine)
+    assert sorted(sum(allu, [])) == list(range(fx.N_USER))
+    # negative sampling + random walk + aggregation across ranks
+    neg = g.negative_sampler("buy", 4, "in_degree").get(ids)
+    for u, row in zip(ids, neg.ids):
+        assert not (set(row.tolist()) & {x[0] for x in adj[u]})
+    nodes = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
+    assert np.allclose(nodes.embedding_agg("mean"), nodes.float_attrs.mean(1), atol=1e-5)
+    rt.barrier()
+    if r == 0:
+        print("DIST_API_OK world=%d device=%s" % (W, rt.device))
+    rt.shutdown()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,19 +10,35 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, port, env_extra):
+def _run(nproc, port, env_extra, script="dist_worker.py", args=(), token="DIST_WORKER_OK"):
     env = dict(os.environ)
     env.update(env_extra)
     env["PYTHONPATH"] = ROOT
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", script)] + list(args)
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     out = p.stdout + p.stderr
-    assert p.returncode == 0 and "DIST_WORKER_OK" in out, out[-4000:]
+    assert p.returncode == 0 and token in out, out[-4000:]
 
 
 def test_two_ranks_cpu_gloo():
     _run(2, 29641, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": ""})
+
+
+def test_public_api_two_ranks_cpu_gloo(tmp_path):
+    from tests import fixtures as fx
+    d = fx.write_graph(str(tmp_path))
+    _run(2, 29647, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": ""}, "dist_api_worker.py", [d], "DIST_API_OK")
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+def test_public_api_two_ranks_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from tests import fixtures as fx
+    d = fx.write_graph(str(tmp_path))
+    _run(2, 29648, {}, "dist_api_worker.py", [d], "DIST_API_OK")
 
 
 @pytest.mark.gpu
