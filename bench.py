@@ -145,6 +145,20 @@ def run_ours(args):
     fdt = torch.bfloat16 if args.feature_dtype == "bf16" else torch.float32
     t0 = time.time()
     nodes, csr = make_sharded_graph(rt, feature_dtype=fdt, seed=0, **shape)
+    # N17 replica cache of remote feature rows in local HBM (the reference's
+    # set_local_node_cache_capacity): -1 = as many remote rows as fit in 25% of the free HBM
+    cache_rows = 0
+    if W > 1 and args.feature_cache_rows != 0:
+        cap = args.feature_cache_rows
+        if cap < 0:
+            free_b, _ = torch.cuda.mem_get_info()
+            cap = int(0.25 * free_b) // (nodes.feats.local.size(1) * nodes.feats.local.element_size())
+        scores = None
+        if cap < shape["num_nodes"]:
+            max_vid = max(int(n) for n in nodes.nrows) * W
+            scores = torch.bincount(csr.indices.local.clamp(min=0), minlength=max_vid).float()[:max_vid]
+            dist.all_reduce(scores)
+        cache_rows = nodes.build_feature_cache(cap, scores=scores)
     torch.cuda.synchronize()
     build_s = time.time() - t0
     torch.manual_seed(0)
@@ -212,6 +226,7 @@ def run_ours(args):
                        "fanout": FANOUTS, "parallelism": "dp%d+graph-partition%d" % (W, W),
                        "num_nodes": shape["num_nodes"], "num_edges": shape["num_edges"],
                        "feat_dim": shape["feat_dim"], "feature_storage": args.feature_dtype,
+                       "feature_cache_rows_per_gpu": cache_rows,
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
                                     % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * (2 if fdt == torch.bfloat16 else 4) / 1e9),
                        "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine, "gather_mode": args.gather_mode,
@@ -250,6 +265,8 @@ def main():
                     help="fused SAGE kernel gather: 0 auto, 1 registers, 2 TMA ring, 3 cp.async ring, 4 split (gather kernel + GEMM)")
     ap.add_argument("--engine", default="fast", choices=["fast", "autograd"],
                     help="fast = hand-scheduled fwd/bwd kernel chain; autograd = torch.autograd over the same kernels")
+    ap.add_argument("--feature-cache-rows", type=int, default=-1,
+                    help="remote feature rows replicated per GPU (N17 cache): -1 auto (25%% of free HBM), 0 off")
     ap.add_argument("--small", action="store_true", help="small graph for quick functional runs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

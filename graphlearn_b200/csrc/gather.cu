@@ -38,6 +38,10 @@ __device__ __forceinline__ const void* row_ptr(const TableView& t, int64_t vid) 
   int64_t row = vid / t.world;
   if (row >= t.nrows[owner]) return nullptr;
   size_t esz = t.dtype == 0 ? 4 : 2;
+  if (t.cmap != nullptr && owner != t.self) {   // replica cache of remote rows (read paths only)
+    const int s = __ldg(t.cmap + vid);
+    if (s >= 0) return t.cbase + (size_t)s * (size_t)t.stride * esz;
+  }
   return reinterpret_cast<const char*>(t.base.p[owner]) + (size_t)row * (size_t)t.stride * esz;
 }
 
@@ -225,6 +229,7 @@ void scatter_add_rows(const at::Tensor& table_desc, const at::Tensor& vids, cons
   c10::cuda::CUDAGuard guard(vids.device());
   TableView t = table_from_desc(table_desc);
   TORCH_CHECK(t.dtype == 0, "scatter_add_rows needs an fp32 table");
+  t.cmap = nullptr;   // updates always go to the owner, never to a replica
   auto v = vids.contiguous();
   auto g = grad.contiguous();
   TORCH_CHECK(g.is_cuda() && g.scalar_type() == at::kFloat && g.dim() == 2 && g.size(1) == t.dim &&

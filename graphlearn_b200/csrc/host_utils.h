@@ -12,6 +12,8 @@ inline void check_cuda_i64(const at::Tensor& t, const char* name) {
 
 // Sharded dense table descriptor (CPU int64 tensor):
 //   [world, dim, stride_elems, dtype_code(0=f32,1=bf16), nrows[8], ptr[8]]
+// optionally followed by the replica cache of remote rows (N17):
+//   [self_rank, cache_map ptr (int32[max_vid+1]: slot or -1), cache rows ptr (same stride/dtype)]
 struct TableView {
   PeerTable base;
   int64_t nrows[kMaxWorld];
@@ -19,12 +21,15 @@ struct TableView {
   int dim;
   int64_t stride;   // elements
   int dtype;        // 0 = fp32, 1 = bf16
+  int self;               // rank owning the cache (only meaningful when cmap != nullptr)
+  const int32_t* cmap;    // vid -> cache slot, -1 = not cached; nullptr = no cache
+  const char* cbase;      // cache rows
 };
 
 inline TableView table_from_desc(const at::Tensor& desc) {
   TORCH_CHECK(desc.device().is_cpu() && desc.scalar_type() == at::kLong &&
-                  desc.numel() == 4 + 2 * kMaxWorld,
-              "table desc must be a CPU int64 tensor of 20 entries");
+                  (desc.numel() == 4 + 2 * kMaxWorld || desc.numel() == 7 + 2 * kMaxWorld),
+              "table desc must be a CPU int64 tensor of 20 (or 23, with cache) entries");
   const int64_t* d = desc.data_ptr<int64_t>();
   TableView t;
   t.world = (int)d[0];
@@ -35,6 +40,14 @@ inline TableView table_from_desc(const at::Tensor& desc) {
   for (int r = 0; r < kMaxWorld; ++r) {
     t.nrows[r] = d[4 + r];
     t.base.p[r] = reinterpret_cast<const void*>(d[4 + kMaxWorld + r]);
+  }
+  t.self = 0;
+  t.cmap = nullptr;
+  t.cbase = nullptr;
+  if (desc.numel() == 7 + 2 * kMaxWorld && d[5 + 2 * kMaxWorld] != 0) {
+    t.self = (int)d[4 + 2 * kMaxWorld];
+    t.cmap = reinterpret_cast<const int32_t*>(d[5 + 2 * kMaxWorld]);
+    t.cbase = reinterpret_cast<const char*>(d[6 + 2 * kMaxWorld]);
   }
   return t;
 }

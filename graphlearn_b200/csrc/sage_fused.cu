@@ -130,6 +130,19 @@ __device__ __forceinline__ const char* loc_ptr(const TableView& t, uint32_t loc,
   return reinterpret_cast<const char*>(t.base.p[loc & 7u]) + (size_t)(loc >> 3) * row_bytes;
 }
 
+// row address of a vid: the local replica-cache copy when the row is remote and cached (N17),
+// the owner's HBM otherwise; `zero_row` for missing / padded ids
+__device__ __forceinline__ const char* vid_ptr(const TableView& t, int64_t vid, int wshift, uint32_t row_bytes,
+                                               const char* zero_row) {
+  const uint32_t loc = make_loc(t, vid, wshift);
+  if (loc == 0xFFFFFFFFu) return zero_row;
+  if (t.cmap != nullptr && (int)(loc & 7u) != t.self) {
+    const int s = __ldg(t.cmap + vid);
+    if (s >= 0) return t.cbase + (size_t)s * row_bytes;
+  }
+  return loc_ptr(t, loc, row_bytes);
+}
+
 // write VEC consecutive K elements of tile row r starting at K column kcol (multiple of VEC)
 template <int VEC>
 __device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_save, size_t a_off, int r, int kcol,
@@ -302,15 +315,11 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
     const int64_t lim = (int64_t)p.M * k;
     for (int i = tid; i < R * k; i += kThreads) {
       const int64_t idx = base + i;
-      uint32_t loc = 0xFFFFFFFFu;
-      if (idx < lim) loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n);
-      sPtrN[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) : p.zero_row;
+      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n, nbr_row_bytes, p.zero_row) : p.zero_row;
     }
     for (int i = tid; i < R; i += kThreads) {
       const int m = m0 + i;
-      uint32_t loc = 0xFFFFFFFFu;
-      if (need_self && m < p.M) loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, wshift_s);
-      sPtrS[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) : p.zero_row;
+      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, wshift_s, self_row_bytes, p.zero_row) : p.zero_row;
     }
   }
   __syncthreads();
@@ -482,15 +491,11 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_tma_kernel(const SageP
     const int64_t lim = (int64_t)p.M * k;
     for (int i = tid; i < R * k; i += kThreads) {
       const int64_t idx = base + i;
-      uint32_t loc = 0xFFFFFFFFu;
-      if (idx < lim) loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr);
-      sPtrN[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) : p.zero_row;
+      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr, nbr_row_bytes, p.zero_row) : p.zero_row;
     }
     for (int i = tid; i < R; i += kThreads) {
       const int m = m0 + i;
-      uint32_t loc = 0xFFFFFFFFu;
-      if (need_self && m < p.M) loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self);
-      sPtrS[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) : p.zero_row;
+      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self, self_row_bytes, p.zero_row) : p.zero_row;
     }
   }
   umma::tc_fence_before();
@@ -663,15 +668,11 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_async_kernel(const Sag
     const int64_t lim = (int64_t)p.M * k;
     for (int i = tid; i < R * k; i += kThreads) {
       const int64_t idx = base + i;
-      uint32_t loc = 0xFFFFFFFFu;
-      if (idx < lim) loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr);
-      sPtrN[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) : p.zero_row;
+      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr, nbr_row_bytes, p.zero_row) : p.zero_row;
     }
     for (int i = tid; i < R; i += kThreads) {
       const int m = m0 + i;
-      uint32_t loc = 0xFFFFFFFFu;
-      if (need_self && m < p.M) loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self);
-      sPtrS[i] = loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) : p.zero_row;
+      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self, self_row_bytes, p.zero_row) : p.zero_row;
     }
   }
   umma::tc_fence_before();
@@ -839,8 +840,7 @@ __global__ void __launch_bounds__(256, 5) gather_self_mean_kernel(const SagePara
       Chunk<DT> sraw;
       const bool self_ld = need_self && f0 < d_self;
       if (self_ld) {
-        const uint32_t loc = make_loc(p.tself, p.self_vids ? __ldg(p.self_vids + m) : m, p.wshift_self);
-        sraw.load(loc != 0xFFFFFFFFu ? loc_ptr(p.tself, loc, self_row_bytes) + coff : p.zero_row + coff);
+        sraw.load(vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : m, p.wshift_self, self_row_bytes, p.zero_row) + coff);
       }
       if (f0 < d_nbr) {
         const int64_t base = m * k;
@@ -849,8 +849,7 @@ __global__ void __launch_bounds__(256, 5) gather_self_mean_kernel(const SagePara
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int j = j0 + u < k ? j0 + u : k - 1;
-            const uint32_t loc = make_loc(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + base + j) : base + j, p.wshift_nbr);
-            raw[u].load(loc != 0xFFFFFFFFu ? loc_ptr(p.tnbr, loc, nbr_row_bytes) + coff : p.zero_row + coff);
+            raw[u].load(vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + base + j) : base + j, p.wshift_nbr, nbr_row_bytes, p.zero_row) + coff);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u)

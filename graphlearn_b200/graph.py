@@ -127,6 +127,9 @@ class Graph(object):
         self._store.node_decoders = self._node_decoders
         self._store.edge_decoders = self._edge_decoders
         self._store.build(self._node_sources, self._edge_sources)
+        cap = int(_config.get().local_node_cache_capacity)
+        if cap > 0:      # reference: set_local_node_cache_capacity -> LFU cache of remote node attrs
+            self._store.build_feature_caches(cap)
         self._topology = self._store.topology
         self._inited = True
         return self

@@ -42,6 +42,16 @@ def gather_rows(rt: Runtime, st: SymmTensor, desc: Optional[torch.Tensor], vids:
     v = vids.reshape(-1).to(torch.int64)
     if rt.is_cuda and _config.get().use_peer_kernels and desc is not None:
         return native().gather_rows(desc, v, out_dtype == torch.bfloat16, float(fill))
+    cmap = getattr(st, "cache_map", None)
+    if cmap is not None and rt.world > 1:
+        # replica cache (N17): hits are served from local HBM, only misses travel
+        inb = (v >= 0) & (v < cmap.numel())
+        slot = torch.where(inb, cmap[v.clamp(min=0, max=cmap.numel() - 1)].long(), torch.full_like(v, -1))
+        hit = slot >= 0
+        (rows,) = part.remote_apply(torch.where(hit, torch.full_like(v, -1), v),
+                                    lambda x: (_local_rows(st, x, rt.world, fill)[:, :dim],), rt.world)
+        rows = torch.where(hit[:, None], st.cache_rows[slot.clamp(min=0)][:, :dim].to(rows.dtype), rows)
+        return rows.to(out_dtype)
     (rows,) = part.remote_apply(v, lambda x: (_local_rows(st, x, rt.world, fill)[:, :dim],), rt.world)
     return rows.to(out_dtype)
 

@@ -238,6 +238,32 @@ class GraphStore(object):
             self.stats[et] = rt.all_gather_object(csr.n_edges)
         rt.barrier()
 
+    # ------------------------------------------------------------------ N17: hot-feature replica cache
+    def build_feature_caches(self, capacity: int) -> Dict[str, int]:
+        """Cache up to ``capacity`` remote feature rows per node type on every rank, hottest
+        (largest global in-degree over all edge types pointing at the type) first.
+        ``gl.set_local_node_cache_capacity(n)`` before ``g.init()`` calls this.  Collective."""
+        rt = self.rt
+        out: Dict[str, int] = {}
+        if rt.world == 1 or capacity <= 0:
+            return out
+        for t, tab in self.nodes.items():
+            if tab.feats is None:
+                continue
+            max_vid = max(int(n) for n in tab.nrows) * rt.world
+            deg = torch.zeros(max_vid, dtype=torch.float32, device=rt.device)
+            for et, csr in self.edges.items():
+                if csr.dst_type != t or csr.indices is None:
+                    continue
+                idx = csr.indices.local
+                idx = idx[(idx >= 0) & (idx < max_vid)]
+                if idx.numel():
+                    deg += torch.bincount(idx, minlength=max_vid).float()
+            import torch.distributed as dist
+            dist.all_reduce(deg)
+            out[t] = tab.build_feature_cache(capacity, scores=deg)
+        return out
+
     # ------------------------------------------------------------------ in-edges (lazy; collective)
     def reverse_csr(self, etype: str) -> CsrShard:
         """CSR of the in-edges of `etype`, partitioned by DESTINATION owner (for inV / in-degrees)."""

@@ -107,6 +107,14 @@ class IdMap:
         return torch.where(flat >= 0, ids, torch.full_like(ids, -1)).reshape(vids.shape)
 
 
+class _NoCache(object):
+    """view of a SymmTensor that hides its replica cache (used while filling the cache)."""
+
+    def __init__(self, st):
+        self.local, self.nrows, self.ptrs = st.local, st.nrows, st.ptrs
+        self.cache_map = self.cache_rows = None
+
+
 class NodeTable:
     def __init__(self, rt: Runtime, ntype: str, idmap: IdMap):
         self.rt = rt
@@ -142,6 +150,72 @@ class NodeTable:
         self.feats = st
         self.rt.barrier()
         self.feat_desc = make_table_desc(self.rt.world, d, stride, dtype, st.nrows, st.ptrs)
+
+    # ------------------------------------------------------------------ N17: replica cache of remote rows
+    def build_feature_cache(self, capacity: int, scores: Optional[torch.Tensor] = None) -> int:
+        """Replicate up to ``capacity`` REMOTE float-feature rows into this rank's HBM.
+
+        Reference: the optional LFU cache of remote node attributes
+        (graphlearn/src/core/graph/storage/remote_node_storage.cc:55-82, cache_policy.h:37-78,
+        enabled by ``set_local_node_cache_capacity``).  B200 design: a STATIC, score-ordered
+        replica (highest global in-degree first, PaGraph style) because a device kernel cannot
+        maintain LFU state cheaply and 180 GB of HBM usually holds the whole table; the kernels
+        resolve ``vid -> cache slot`` through one int32 map (csrc/host_utils.h TableView).
+        ``scores``: float/int tensor indexed by vid (higher = hotter), identical on every rank;
+        None = cache in vid order.  Collective.  Returns the number of cached rows."""
+        rt, W = self.rt, self.rt.world
+        if W == 1 or self.feats is None or capacity <= 0:
+            return 0
+        dev = rt.device
+        max_vid = max(int(n) for n in self.nrows) * W
+        vid = torch.arange(max_vid, device=dev, dtype=torch.int64)
+        nrows = torch.tensor([int(n) for n in self.nrows], device=dev, dtype=torch.int64)
+        exists = torch.div(vid, W, rounding_mode="floor") < nrows[vid % W]
+        remote = exists & ((vid % W) != rt.rank)
+        n_remote = int(remote.sum().item())
+        C = min(int(capacity), n_remote)
+        if C <= 0:
+            return 0
+        if C == n_remote:
+            sel = vid[remote]
+        else:
+            sc = torch.zeros(max_vid, device=dev, dtype=torch.float32) if scores is None else \
+                scores.to(dev).float()[:max_vid].clone()
+            if scores is None:
+                sc = -vid.float()
+            sc[~remote] = float("-inf")
+            sel = torch.topk(sc, C).indices.sort().values
+        st = self.feats
+        stride = int(st.local.size(1))
+        rows = torch.zeros(C, stride, dtype=st.local.dtype, device=dev)
+        from ..ops import gather as G
+        base_desc = make_table_desc(W, self.float_dim, stride, st.local.dtype, st.nrows, st.ptrs) \
+            if rt.is_cuda else None
+        step = 1 << 20
+        # every rank must run the same number of (collective on the portable path) rounds
+        n_rounds = (max(rt.all_gather_object(C)) + step - 1) // step
+        for i in range(n_rounds):
+            chunk = sel[i * step:(i + 1) * step]
+            got = G.gather_rows(rt, _NoCache(st), base_desc, chunk, self.float_dim, out_dtype=st.local.dtype)
+            if chunk.numel():
+                rows[i * step:i * step + chunk.numel(), :self.float_dim] = got
+        cmap = torch.full((max_vid,), -1, dtype=torch.int32, device=dev)
+        cmap[sel] = torch.arange(C, device=dev, dtype=torch.int32)
+        st.cache_map, st.cache_rows = cmap, rows
+        rt.barrier()
+        if rt.is_cuda:
+            self.feat_desc = make_table_desc(W, self.float_dim, stride, st.local.dtype, st.nrows, st.ptrs,
+                                             cache=(rt.rank, cmap.data_ptr(), rows.data_ptr()))
+        return C
+
+    def drop_feature_cache(self):
+        st = self.feats
+        if st is None or getattr(st, "cache_map", None) is None:
+            return
+        st.cache_map = st.cache_rows = None
+        if self.rt.is_cuda:
+            self.feat_desc = make_table_desc(self.rt.world, self.float_dim, int(st.local.size(1)), st.local.dtype,
+                                             st.nrows, st.ptrs)
 
     def _set_symm(self, name, x: torch.Tensor):
         st = self.rt.symm_empty(tuple(x.shape), x.dtype)

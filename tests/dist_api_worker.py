@@ -72,6 +72,17 @@ def main():
         assert not (set(row.tolist()) & {x[0] for x in adj[u]})
     nodes = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
     assert np.allclose(nodes.embedding_agg("mean"), nodes.float_attrs.mean(1), atol=1e-5)
+    # N17: replica cache of remote feature rows (partial, then full); results must not change
+    for cap in (5, 10 ** 6):
+        got = g._store.build_feature_caches(cap)
+        n_remote_items = fx.N_ITEM - len([i for i in range(fx.N_ITEM) if i % W == r])
+        assert got["item"] == min(cap, n_remote_items), got
+        it2 = g.lookup_nodes("item", np.arange(fx.N_ITEM))
+        assert np.allclose(it2.float_attrs, it.float_attrs)
+        nodes2 = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
+        assert np.allclose(nodes2.embedding_agg("mean"), nodes.float_attrs.mean(1), atol=1e-5)
+        cm = g._store.nodes["item"].feats.cache_map
+        assert int((cm >= 0).sum()) == got["item"] and all(int(v) % W != r for v in torch.nonzero(cm >= 0).flatten())
     rt.barrier()
     if r == 0:
         print("DIST_API_OK world=%d device=%s" % (W, rt.device))

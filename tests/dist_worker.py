@@ -39,6 +39,12 @@ def main():
     ips = gather_all(csr.indptr.local)
     idxs = gather_all(csr.indices.local)
     feats = gather_all(nodes.feats.local[:, :D].float())
+    cache_cap = int(os.environ.get("GLB_TEST_CACHE", "0"))
+    if cache_cap:      # N17 replica cache: every check below must give identical results through it
+        sc = torch.bincount(csr.indices.local.clamp(min=0), minlength=max(nodes.nrows) * W).float()
+        dist.all_reduce(sc)
+        got = nodes.build_feature_cache(cache_cap, scores=sc)
+        assert got == min(cache_cap, N - nodes.n_local), got
 
     def adj(v):
         o, row = v % W, v // W

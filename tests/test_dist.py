@@ -25,6 +25,10 @@ def test_two_ranks_cpu_gloo():
     _run(2, 29641, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": ""})
 
 
+def test_two_ranks_cpu_gloo_feature_cache():
+    _run(2, 29644, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": "", "GLB_TEST_CACHE": "1000"})
+
+
 def test_public_api_two_ranks_cpu_gloo(tmp_path):
     from tests import fixtures as fx
     d = fx.write_graph(str(tmp_path))
@@ -47,6 +51,14 @@ def test_two_ranks_gpu_peer():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(2, 29642, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+def test_two_ranks_gpu_peer_feature_cache():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(2, 29645, {"GLB_TEST_CACHE": "1000"})
 
 
 @pytest.mark.gpu
