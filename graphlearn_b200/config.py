@@ -40,6 +40,7 @@ class Config:
     tape_capacity: int = 10
     storage_mode: int = 2
     local_node_cache_capacity: int = 0
+    sliced_load: bool = True          # each rank parses 1/world of a file, rows are shuffled to owners
     knn_metric: int = 0          # 0 = L2, 1 = inner product
     field_delimiter: str = "\t"
     vineyard_graph_id: int = 0

@@ -49,7 +49,8 @@ void adam_flat(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at
                double, double, double, double, double);
 // host_loader.cpp
 std::vector<at::Tensor> load_table(const std::string&, bool, bool, bool, bool, std::vector<int64_t>,
-                                   std::vector<int64_t>, const std::string&, const std::string&, int64_t);
+                                   std::vector<int64_t>, const std::string&, const std::string&, int64_t,
+                                   int64_t, int64_t);
 void save_embeddings(const std::string&, const at::Tensor&, const at::Tensor&, bool);
 }  // namespace glb
 

@@ -175,7 +175,8 @@ at::Tensor concat(const std::vector<Columns>& cols, std::vector<T> Columns::*fie
 std::vector<at::Tensor> load_table(const std::string& path, bool is_edge, bool weighted, bool labeled,
                                    bool timestamped, std::vector<int64_t> attr_types,
                                    std::vector<int64_t> buckets, const std::string& attr_delim,
-                                   const std::string& field_delim, int64_t threads) {
+                                   const std::string& field_delim, int64_t threads, int64_t part_index,
+                                   int64_t part_count) {
   Schema sc;
   sc.is_edge = is_edge; sc.weighted = weighted; sc.labeled = labeled; sc.timestamped = timestamped;
   for (auto t : attr_types) sc.attr_types.push_back((int)t);
@@ -191,30 +192,62 @@ std::vector<at::Tensor> load_table(const std::string& path, bool is_edge, bool w
     else sc.n_str++;
   }
 
-  // slurp
+  // Read only this part's byte range of the file (SliceReader semantics,
+  // graphlearn/src/core/io/slice_reader.h:60-86: `part_count` contiguous record ranges).  A record
+  // belongs to the part whose raw byte range contains its first byte.
   FILE* fp = std::fopen(path.c_str(), "rb");
   TORCH_CHECK(fp != nullptr, "cannot open data source: ", path);
   std::fseek(fp, 0, SEEK_END);
-  long sz = std::ftell(fp);
-  std::fseek(fp, 0, SEEK_SET);
-  std::vector<char> buf((size_t)sz);
-  size_t rd = sz > 0 ? std::fread(buf.data(), 1, (size_t)sz, fp) : 0;
-  std::fclose(fp);
-  TORCH_CHECK((long)rd == sz, "short read on ", path);
-  const char* begin = buf.data();
-  const char* end = begin + sz;
-
+  const long sz = std::ftell(fp);
+  TORCH_CHECK(part_count >= 1 && part_index >= 0 && part_index < part_count, "bad part index/count");
   // header detection: "name:type<TAB>name:type..." (first field not numeric)
-  if (begin < end) {
-    const char* eol = (const char*)memchr(begin, '\n', (size_t)(end - begin));
-    if (!eol) eol = end;
-    const char* t = (const char*)memchr(begin, sc.field_delim, (size_t)(eol - begin));
-    if (!t) t = eol;
-    int64_t dummy;
-    const char* fe = t;
-    if (fe > begin && fe[-1] == '\r') --fe;
-    if (!parse_i64(begin, fe, &dummy)) begin = (eol < end) ? eol + 1 : end;
+  long data_begin = 0;
+  {
+    std::vector<char> head((size_t)std::min<long>(sz, 1 << 16));
+    std::fseek(fp, 0, SEEK_SET);
+    size_t hn = head.empty() ? 0 : std::fread(head.data(), 1, head.size(), fp);
+    const char* hb = head.data();
+    const char* he = hb + hn;
+    if (hb < he) {
+      const char* eol = (const char*)memchr(hb, '\n', (size_t)(he - hb));
+      if (!eol) eol = he;
+      const char* t = (const char*)memchr(hb, sc.field_delim, (size_t)(eol - hb));
+      if (!t) t = eol;
+      int64_t dummy;
+      const char* fe = t;
+      if (fe > hb && fe[-1] == '\r') --fe;
+      if (!parse_i64(hb, fe, &dummy)) data_begin = (eol < he) ? (long)(eol - hb) + 1 : (long)hn;
+    }
   }
+  auto line_start_at_or_after = [&](long c) -> long {   // c > data_begin
+    long pos = c - 1;
+    char tmp[1 << 14];
+    std::fseek(fp, pos, SEEK_SET);
+    while (pos < sz) {
+      size_t n = std::fread(tmp, 1, (size_t)std::min<long>((long)sizeof(tmp), sz - pos), fp);
+      if (n == 0) break;
+      const char* nl = (const char*)memchr(tmp, '\n', n);
+      if (nl) return pos + (long)(nl - tmp) + 1;
+      pos += (long)n;
+    }
+    return sz;
+  };
+  const long span = sz - data_begin;
+  long lo = data_begin, hi = sz;
+  if (part_count > 1) {
+    const long c0 = data_begin + (long)((__int128)span * part_index / part_count);
+    const long c1 = data_begin + (long)((__int128)span * (part_index + 1) / part_count);
+    lo = (part_index == 0 || c0 <= data_begin) ? data_begin : line_start_at_or_after(c0);
+    hi = (part_index == part_count - 1) ? sz : (c1 <= data_begin ? data_begin : line_start_at_or_after(c1));
+    if (hi < lo) hi = lo;
+  }
+  std::vector<char> buf((size_t)(hi - lo));
+  std::fseek(fp, lo, SEEK_SET);
+  size_t rd = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), fp);
+  std::fclose(fp);
+  TORCH_CHECK(rd == buf.size(), "short read on ", path);
+  const char* begin = buf.data();
+  const char* end = begin + buf.size();
 
   int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads, 64));
   if ((end - begin) < (1 << 16)) nt = 1;

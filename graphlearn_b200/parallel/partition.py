@@ -69,3 +69,34 @@ def remote_apply(ids: torch.Tensor, fn: Callable[[torch.Tensor], Sequence[torch.
         back = _all_to_all_v(o, recv_counts, send_counts)
         results.append(back[inv])
     return results
+
+
+def shuffle_rows(cols: dict, owner: torch.Tensor, world: int, device) -> dict:
+    """Load-time shuffle (C4 / K11): row i of every column goes to rank ``owner[i]``.
+
+    Reference: loader threads batch parsed rows into UpdateNodes/UpdateEdges requests that the
+    distributed op runner routes to the owning server (graphlearn/src/core/graph/graph_store.cc:
+    60-165,210-250; shard keys graph_update_request.cc:151-156,234-237).  Here: one all-to-all-v
+    per column over NCCL/gloo; object (string) columns travel pickled."""
+    if world == 1:
+        return dict(cols)
+    import numpy as np
+    owner = owner.to(device)
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world)
+    send_counts = [int(x) for x in counts.tolist()]
+    recv_counts = exchange_counts(counts)
+    out = {}
+    for k, v in cols.items():
+        if v is None:
+            out[k] = None
+        elif isinstance(v, torch.Tensor):
+            out[k] = _all_to_all_v(v.to(device)[order], send_counts, recv_counts)
+        else:
+            vs = np.asarray(v, dtype=object)[order.cpu().numpy()]
+            pieces = np.split(vs, np.cumsum(send_counts)[:-1])
+            gathered = [None] * world
+            dist.all_gather_object(gathered, pieces)
+            me = dist.get_rank()
+            out[k] = np.concatenate([g[me] for g in gathered]) if gathered else vs[:0]
+    return out

@@ -8,8 +8,9 @@ sequence (graphlearn/src/service/server_impl.cc:163-195):
            arrays -> columnar tensors
   shuffle  rows are assigned to owner = |id| % world (edges by SRC id, nodes by
            node id - graph_update_request.cc:151-156,234-237).  Every rank
-           parses the source and keeps what it owns (no RPC shuffle needed on a
-           single box where all ranks see the same files).
+           parses 1/world of each file (byte-range slices, or whole files of a
+           directory dealt round-robin) and one all-to-all-v per column moves
+           the rows to their owners (parallel/partition.py shuffle_rows).
   build    id maps (id <-> virtual id), node tables and CSR shards in HBM, peer
            pointer tables exchanged through CUDA IPC.
 """
@@ -23,6 +24,7 @@ import torch
 
 from .. import config as _config
 from ..data.decoder import Decoder
+from ..parallel import partition as part
 from ..parallel.runtime import Runtime, native
 from .shards import CsrShard, IdMap, NodeTable
 
@@ -77,8 +79,12 @@ def _expand_paths(path: str) -> List[str]:
     return out
 
 
-def _load_source(src: Source) -> Dict[str, object]:
-    """-> dict(a, b, w, label, ts, ia, fa, strs) of CPU tensors."""
+def _load_source(src: Source, part_index: int = 0, part_count: int = 1) -> Dict[str, object]:
+    """-> dict(a, b, w, label, ts, ia, fa, strs) of CPU tensors.
+
+    ``part_count > 1`` reads only this rank's share (SliceReader, graphlearn/src/core/io/
+    slice_reader.h:60-86,137-157): a single file is cut into ``part_count`` contiguous record
+    ranges; the files of a directory are dealt round-robin, whole, to the parts."""
     dec: Decoder = src.decoder
     if src.data is not None:
         d = src.data
@@ -92,11 +98,24 @@ def _load_source(src: Source) -> Dict[str, object]:
     cfg = _config.get()
     codes, buckets = dec.loader_schema()
     parts = []
-    for p in _expand_paths(src.path):
-        parts.append(C.load_table(p, src.kind == "edge", dec.weighted, dec.labeled, dec.timestamped, codes, buckets,
-                                  dec.attr_delimiter, cfg.field_delimiter, int(cfg.loader_threads)))
-    if not parts:
+    paths = _expand_paths(src.path)
+    if not paths:
         raise FileNotFoundError("no data files for source %r" % (src.path,))
+    for j, p in enumerate(paths):
+        if len(paths) > 1 and part_count > 1:
+            if j % part_count != part_index:
+                continue
+            pi, pc = 0, 1
+        else:
+            pi, pc = part_index, part_count
+        parts.append(C.load_table(p, src.kind == "edge", dec.weighted, dec.labeled, dec.timestamped, codes, buckets,
+                                  dec.attr_delimiter, cfg.field_delimiter, int(cfg.loader_threads), pi, pc))
+    if not parts:       # more ranks than files: this rank contributes an empty slice
+        parts.append(C.load_table(paths[0], src.kind == "edge", dec.weighted, dec.labeled, dec.timestamped, codes,
+                                  buckets, dec.attr_delimiter, cfg.field_delimiter, 1, 0, 1))
+        parts[0] = [t[:0] if i < 7 else t for i, t in enumerate(parts[0])]
+        parts[0][7] = parts[0][7][:0]
+        parts[0][8] = parts[0][8][:1]
     cat = [torch.cat([p[i] for p in parts]) if i < 7 else None for i in range(7)]
     strs = None
     if dec.string_attr_num > 0:
@@ -146,22 +165,35 @@ class GraphStore(object):
         cfg = _config.get()
         fdt = torch.bfloat16 if cfg.feature_dtype == "bf16" else torch.float32
         # ---- load + keep what this rank owns
+        # File sources: every rank parses 1/W of the bytes and one all-to-all-v per column moves the
+        # rows to their owners (N10 + C4).  In-memory sources are identical on every rank -> filter.
+        def load_owned(s, key):
+            if s.data is None and W > 1 and cfg.sliced_load:
+                d = _load_source(s, r, W)
+                if s.kind == "edge" and s.direction == REVERSED:
+                    d["a"], d["b"] = d["b"], d["a"]
+                dst_own = None
+                if s.kind == "edge":
+                    ub = torch.unique(d["b"])
+                    dst_own = part.shuffle_rows({"a": ub}, ub.abs() % W, W, dev)["a"]
+                return part.shuffle_rows(d, d[key].abs() % W, W, dev), dst_own
+            d = _load_source(s)
+            if s.kind == "edge" and s.direction == REVERSED:
+                d["a"], d["b"] = d["b"], d["a"]
+            dst_own = d["b"][d["b"].abs() % W == r] if s.kind == "edge" else None
+            keep = (d[key].abs() % W == r).nonzero().flatten()
+            return _take(d, keep), dst_own
+
         nd: Dict[str, List[Dict]] = {}
         for s in node_sources:
-            d = _load_source(s)
-            keep = (d["a"].abs() % W == r).nonzero().flatten()
-            nd.setdefault(s.types, []).append(_take(d, keep))
+            d, _ = load_owned(s, "a")
+            nd.setdefault(s.types, []).append(d)
         ed: Dict[str, List[Dict]] = {}
         ends: Dict[str, List[torch.Tensor]] = {}   # node type -> owned endpoint ids seen in edges
         for s in edge_sources:
-            d = _load_source(s)
             st, dt, et = s.types
-            if s.direction == REVERSED:
-                d["a"], d["b"] = d["b"], d["a"]
-            own_dst = d["b"][d["b"].abs() % W == r]
+            dk, own_dst = load_owned(s, "a")
             ends.setdefault(dt, []).append(own_dst)
-            keep = (d["a"].abs() % W == r).nonzero().flatten()
-            dk = _take(d, keep)
             ends.setdefault(st, []).append(dk["a"])
             ed.setdefault(et, []).append(dk)
             self.topology.add(et, st, dt)
@@ -170,9 +202,10 @@ class GraphStore(object):
         types = rt.all_gather_object(types)[0] if W > 1 else types
         for t in types:
             parts = nd.get(t, [])
-            ids_src = torch.cat([p["a"] for p in parts]) if parts else torch.zeros(0, dtype=torch.int64)
-            ids_all = torch.cat([ids_src] + ends.get(t, [])) if (parts or t in ends) else ids_src
-            idmap = IdMap.build(rt, ids_all.to(dev))
+            ids_src = torch.cat([p["a"].to(dev) for p in parts]) if parts else \
+                torch.zeros(0, dtype=torch.int64, device=dev)
+            ids_all = torch.cat([ids_src] + [e.to(dev) for e in ends.get(t, [])]) if (parts or t in ends) else ids_src
+            idmap = IdMap.build(rt, ids_all)
             tab = NodeTable(rt, t, idmap)
             n = idmap.n_local
             dec = self.node_decoders.get(t, Decoder())
@@ -180,7 +213,7 @@ class GraphStore(object):
             present = torch.zeros(n, dtype=torch.bool, device=dev)
             present[rows] = True
             tab.present = present
-            merged = {k: (torch.cat([p[k] for p in parts]) if parts and parts[0][k] is not None and k != "strs" else None)
+            merged = {k: (torch.cat([p[k].to(dev) for p in parts]) if parts and parts[0][k] is not None and k != "strs" else None)
                       for k in ("w", "label", "ts", "ia", "fa")}
             if dec.float_attr_num > 0:
                 x = torch.full((n, dec.float_attr_num), float(cfg.default_float_attribute), device=dev)
@@ -218,7 +251,7 @@ class GraphStore(object):
         for et in self.topology.edge_types():
             st, dt = self.topology.get_src_type(et), self.topology.get_dst_type(et)
             parts = ed.get(et, [])
-            cat = lambda k: (torch.cat([p[k] for p in parts]).to(dev) if parts and parts[0][k] is not None else None)  # noqa: E731
+            cat = lambda k: (torch.cat([p[k].to(dev) for p in parts]) if parts and parts[0][k] is not None else None)  # noqa: E731
             src = cat("a") if parts else torch.zeros(0, dtype=torch.int64, device=dev)
             dst = cat("b") if parts else torch.zeros(0, dtype=torch.int64, device=dev)
             src_tab, dst_tab = self.nodes[st], self.nodes[dt]

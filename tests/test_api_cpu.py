@@ -255,3 +255,24 @@ def test_non_dense_ids(tmp_path):
     lay = g4.neighbor_sampler("e", 2).get(ids)
     assert (lay.layer_nodes(1).ids[:, 0] == np.roll(ids, 1)).all()
     assert (g4.lookup_nodes("n", ids).labels == np.arange(5)).all()
+
+
+def test_native_loader_byte_range_slices(tmp_path):
+    """N10: the union of the `part_count` record ranges of a file is the file, in order, for any
+    part count (with / without header, tiny and multi-threaded sizes)."""
+    import torch
+    from graphlearn_b200.parallel.runtime import native
+    C = native()
+    for header, n in ((True, 7), (False, 5000), (True, 40000)):
+        p = str(tmp_path / ("e_%d_%d.tsv" % (header, n)))
+        with open(p, "w") as f:
+            if header:
+                f.write("src_id:int64\tdst_id:int64\tweight:float\n")
+            for i in range(n):
+                f.write("%d\t%d\t%.3f\n" % (i * 7, (i * 13) % 1000, 0.5 + (i % 9)))
+        full = C.load_table(p, True, True, False, False, [], [], ":", "\t", 4, 0, 1)
+        assert full[0].numel() == n
+        for parts in (2, 3, 8, 11):
+            got = [C.load_table(p, True, True, False, False, [], [], ":", "\t", 4, i, parts) for i in range(parts)]
+            for col in range(3):
+                assert torch.equal(torch.cat([g[col] for g in got]), full[col]), (header, n, parts, col)
