@@ -11,13 +11,13 @@ import graphlearn_b200 as gl
 from graphlearn_b200 import models
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--p", type=float, default=1.0)
     ap.add_argument("--q", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--device", default=None)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     node_f, edge_f, dim, _ = write_citation_like(tempfile.mkdtemp(), n=1000)
     g = gl.Graph().node(node_f, "i", decoder=gl.Decoder(labeled=True, attr_types=["float"] * dim)) \
         .edge(edge_f, ("i", "i", "e"), decoder=gl.Decoder(weighted=True), directed=False).init(device=a.device)

@@ -14,12 +14,12 @@ from graphlearn_b200 import models
 from graphlearn_b200 import nn as glnn
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--device", default=None)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     d = tempfile.mkdtemp()
     node_f, edge_f, dim, classes = write_citation_like(d)
     g = gl.Graph() \

@@ -15,13 +15,13 @@ from graphlearn_b200.utils.checkpoint import save_checkpoint
 from graphlearn_b200.utils.trace import ProgressLogger
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--nodes", type=int, default=2_449_029)
     ap.add_argument("--edges", type=int, default=123_718_280)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--ckpt", default="")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     rt = init()
     nodes, csr = make_sharded_graph(rt, a.nodes, a.edges, 100, 47)
     model = EgoGraphSAGE(100, 256, 47, 2).to(rt.device)

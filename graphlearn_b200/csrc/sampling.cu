@@ -32,7 +32,7 @@ enum Strategy : int {
 enum FilterMode : int {
   kNoFilter = 0,
   kFilterIdEqual = 1,        // drop neighbours whose id == filter[b]
-  kFilterTsLargerThan = 2,   // drop edges whose timestamp > filter[b] (rows sorted by ts asc)
+  kFilterTsLargerThan = 2,   // keep edges whose timestamp < filter[b] (rows sorted by ts asc)
 };
 
 struct SampleParams {
@@ -51,12 +51,14 @@ struct SampleParams {
   uint32_t salt;
 };
 
-// number of leading edges of the (ts-ascending) row with ts <= bound
+// number of leading edges of the (ts-ascending) row with ts < bound: the reference's accelerated
+// timestamp filter keeps exactly the edges BEFORE the bound (filter.cc:68-82,193-228), so an event
+// never sees itself or a simultaneous edge
 __device__ __forceinline__ int64_t ts_prefix(const RowRef& r, int64_t bound) {
   int64_t lo = 0, hi = r.deg;
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
-    if (__ldg(r.ts + r.beg + mid) <= bound) lo = mid + 1; else hi = mid;
+    if (__ldg(r.ts + r.beg + mid) < bound) lo = mid + 1; else hi = mid;
   }
   return lo;
 }

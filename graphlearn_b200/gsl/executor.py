@@ -85,19 +85,26 @@ class QueryExecutor(object):
             ids = tab.idmap.to_id(vids) if not tab.idmap.dense else vids
             # vids must live in the BASE table (edges index the unmasked node type)
             base = node._base_type
+            vtype = node.type
             if base != node.type and base in self.store.nodes:
+                # masked roots (V(t, mask=...)) only choose WHICH ids are traversed; labels and
+                # attributes are looked up in the base table (graph.py:582-588: set_path(t, ...))
                 bvids = self.store.nodes[base].idmap.to_vid(ids)
+                vtype, vids = base, bvids
             else:
                 bvids = vids
             out = _Out(ids=ids, vids=bvids, shape=(int(ids.numel()),))
-            out.value = V_.Nodes(ids, node.type, shape=out.shape, graph=self.g, vids=vids)
+            out.value = V_.Nodes(ids, vtype, shape=out.shape, graph=self.g, vids=vids)
             return out
         # nodes from edge end points
         csr = self.store.edges[p["edge_type"]]
         if self._iter is None:
             self._iter = SeedIterator(csr.n_edges, bs, strategy, self.rt.device, seed=_config.get().seed + 17 * r,
                                       drop_last=self.drop_last)
-        idx = self._iter.next_index()
+            # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
+        # index, memory_edge_storage.cc; GetEdges by_order walks edge ids) - chronological event
+        # files therefore yield chronological batches although the CSR is row-major
+        idx = csr.insertion_pos()[self._iter.next_index()]
         if p["node_from"] == EDGE_SRC:
             vids = csr._row_of_edge[idx] * W + r
             t = csr.src_type
@@ -117,7 +124,10 @@ class QueryExecutor(object):
         if self._iter is None:
             self._iter = SeedIterator(csr.n_edges, bs, p.get("strategy", "by_order"), self.rt.device,
                                       seed=_config.get().seed + 17 * r, drop_last=self.drop_last)
-        idx = self._iter.next_index()
+            # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
+        # index, memory_edge_storage.cc; GetEdges by_order walks edge ids) - chronological event
+        # files therefore yield chronological batches although the CSR is row-major
+        idx = csr.insertion_pos()[self._iter.next_index()]
         src_v = csr._row_of_edge[idx] * W + r
         dst_v = csr.indices.local[idx]
         src_ids = self.g.to_ids(csr.src_type, src_v)
@@ -171,10 +181,13 @@ class QueryExecutor(object):
             if fv.numel() != src_v.numel():
                 fv = fv.reshape(-1, 1).expand(-1, src_v.numel() // max(fv.numel(), 1)).reshape(-1)
             fmode, fvals = S.FILTER_ID, fv
-        elif csr.timestamped and getattr(up.value, "_t", {}).get("timestamps") is not None and p.get("temporal", True):
-            ts = up.value.tensor("timestamps")
-            if ts is not None and ts.numel() == src_v.numel():
-                fmode, fvals = S.FILTER_TS, ts.reshape(-1).to(torch.int64)
+        elif csr.timestamped and self._root_ts is not None and p.get("temporal", True):
+            # temporal roots constrain EVERY downstream traversal to edges before the root element's
+            # timestamp (dag_node.py:357-364,387-392); values are expanded by fan-out to align with src ids
+            ts = self._root_ts.reshape(-1).to(torch.int64)
+            n = int(src_v.numel())
+            if ts.numel() > 0 and n % ts.numel() == 0:
+                fmode, fvals = S.FILTER_TS, ts.reshape(-1, 1).expand(-1, n // ts.numel()).reshape(-1)
         nbr, eid = S.sample_neighbors(csr, src_v, k, strategy, fmode, fvals, want_eids=True, rng=self.rng,
                                       salt=self._salt)
         B = int(src_v.numel())
@@ -185,8 +198,10 @@ class QueryExecutor(object):
             out.src_ids, out.src_vids, out.eids = src_ids, src_v, eid
             topo = self.g.get_topology()
             st = topo.get_src_type(et) if direction == "out" else topo.get_dst_type(et)
-            out.value = V_.Edges(src_ids, st, ids, dst_t, et, eid, shape=(B, k), graph=self.g,
-                                 src_vids=src_v.reshape(-1, 1).expand(B, k))
+            # attribute rows live on the owner of the edge's ORIGINAL source: for in-edges that is the
+            # sampled neighbour (eid = position in the forward CSR there)
+            owner_v = nbr if direction == "in" else src_v.reshape(-1, 1).expand(B, k)
+            out.value = V_.Edges(src_ids, st, ids, dst_t, et, eid, shape=(B, k), graph=self.g, src_vids=owner_v)
         else:
             out.value = V_.Nodes(ids, dst_t, shape=(B, k), graph=self.g, vids=nbr)
         return out
@@ -263,6 +278,8 @@ class QueryExecutor(object):
         return out
 
     # ------------------------------------------------------------------ run one batch
+    _root_ts = None
+
     def run(self) -> Dict[str, object]:
         results: Dict[int, _Out] = {}
         for node in self._order:
@@ -294,6 +311,17 @@ class QueryExecutor(object):
             else:
                 raise errors.UnimplementedError("unknown GSL node %r" % (node.op_name,))
             results[id(node)] = res
+            if node is self.dag.root:
+                self._root_ts = None
+                if isinstance(node, TraverseSourceEdgeDagNode):
+                    timed = self.store.edges[node.params["edge_type"]].timestamped
+                elif isinstance(node, SubGraphDagNode):
+                    timed = False
+                else:
+                    tab = self.store.nodes.get(node.type)
+                    timed = tab is not None and tab.timestamps is not None and node.params.get("node_from", NODE) == NODE
+                if timed and hasattr(res.value, "tensor"):
+                    self._root_ts = res.value.tensor("timestamps")
         self.rng.advance(1)
         out = {}
         for alias in self.dag.list_alias():

@@ -4,3 +4,5 @@ from .ego_gnn import EgoGNN, make_ego_gnn  # noqa: F401
 from .graphsage import EgoGraphSAGE  # noqa: F401
 from .node2vec import Node2Vec, gen_pair  # noqa: F401
 from .sparse_gnn import SEAL, SparseGNN, drnl_node_labeling  # noqa: F401
+from .tgn import TGN, TGNMemory, TemporalAttention, TemporalBatch, TemporalBatchLoader  # noqa: F401
+from .ultra_gcn import UltraGCN  # noqa: F401

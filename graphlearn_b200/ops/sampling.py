@@ -34,6 +34,14 @@ STRATEGY = {
 FILTER_NONE, FILTER_ID, FILTER_TS = 0, 1, 2
 
 
+def _eid_of(csr: CsrShard, pos: torch.Tensor) -> torch.Tensor:
+    """edge id of a CSR position: the position itself, or the explicit id column of in-edge CSRs."""
+    e = getattr(csr, "eids", None)
+    if e is None or e.local.numel() == 0:
+        return pos
+    return e.local[pos.clamp(max=e.local.numel() - 1)]
+
+
 def _local_sample(csr: CsrShard, vids: torch.Tensor, k: int, strategy: str, filter_mode: int,
                   fvals: Optional[torch.Tensor], circular: bool, default_id: int,
                   gen: Optional[torch.Generator]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -58,12 +66,13 @@ def _local_sample(csr: CsrShard, vids: torch.Tensor, k: int, strategy: str, filt
     reversed_ = False
     if filter_mode == FILTER_TS and csr.ts is not None:
         ts = csr.ts.local
-        # per-row count of edges with ts <= bound (rows are ts-ascending)
+        # per-row count of edges with ts < bound (rows are ts-ascending; strict like the reference's
+        # accelerated path, filter.cc:68-82,193-228)
         maxd = int(deg.max().item()) if B > 0 else 0
         ar = torch.arange(max(maxd, 1), device=dev)
         pos = (beg[:, None] + ar[None, :]).clamp_(max=max(ts.numel() - 1, 0))
         inrow = ar[None, :] < deg[:, None]
-        m = ((ts[pos] <= fvals[:, None]) & inrow).sum(1) if ts.numel() > 0 else torch.zeros_like(deg)
+        m = ((ts[pos] < fvals[:, None]) & inrow).sum(1) if ts.numel() > 0 else torch.zeros_like(deg)
         reversed_ = True
     rnd = lambda *shape: torch.rand(*shape, device=dev, generator=gen)  # noqa: E731
     j = torch.arange(k, device=dev)[None, :].expand(B, k)
@@ -104,7 +113,7 @@ def _local_sample(csr: CsrShard, vids: torch.Tensor, k: int, strategy: str, filt
     pos = (beg[:, None] + pick).clamp_(min=0, max=max(indices.numel() - 1, 0))
     if indices.numel() > 0:
         nbr = torch.where(valid, indices[pos], nbr)
-        eid = torch.where(valid, pos, eid)
+        eid = torch.where(valid, _eid_of(csr, pos), eid)
     return nbr, eid
 
 
@@ -143,7 +152,9 @@ def _local_sample_idfilter(csr, vids, k, strategy, fvals, circular, default_id, 
             if i >= 0:
                 nbr[b, jx] = indices[i]
                 eid[b, jx] = i
-    return nbr.to(vids.device), eid.to(vids.device)
+    eid = eid.to(vids.device)
+    eid = torch.where(eid >= 0, _eid_of(csr, eid.clamp(min=0)), eid)
+    return nbr.to(vids.device), eid
 
 
 def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: str = "random",
@@ -226,7 +237,8 @@ def sample_full(csr: CsrShard, src_vids: torch.Tensor, cap: int = 0, want_eids: 
         beg = ip[rc]
         ar = torch.arange(maxd, device=v.device)
         pos = (beg[:, None] + ar[None, :]).clamp_(max=max(idx.numel() - 1, 0))
-        return (idx[pos] if idx.numel() > 0 else torch.zeros(v.numel(), maxd, dtype=torch.int64, device=v.device), pos)
+        return (idx[pos] if idx.numel() > 0 else torch.zeros(v.numel(), maxd, dtype=torch.int64, device=v.device),
+                _eid_of(csr, pos))
 
     dense_n, dense_e = part.remote_apply(src, fn, W)
     mask = torch.arange(maxd, device=src.device)[None, :] < deg[:, None]

@@ -32,6 +32,8 @@ class NodeSampler(object):
 
     def get(self):
         idx = self._it.next_index()
+        if self._from != NODE:
+            idx = self._csr.insertion_pos()[idx]     # edge traversal follows insertion (edge id) order
         W, r = self._rt.world, self._rt.rank
         if self._from == NODE:
             vids = self._rows[idx] * W + r
@@ -63,9 +65,9 @@ class EdgeSampler(object):
                                 seed=_config.get().seed + 37 * self._rt.rank)
 
     def get(self):
-        idx = self._it.next_index()
-        W, r = self._rt.world, self._rt.rank
         csr = self._csr
+        idx = csr.insertion_pos()[self._it.next_index()]     # insertion (edge id) order, like the reference
+        W, r = self._rt.world, self._rt.rank
         src_v = csr._row_of_edge[idx] * W + r
         dst_v = csr.indices.local[idx]
         src = self._g.to_ids(csr.src_type, src_v)

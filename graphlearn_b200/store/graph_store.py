@@ -309,6 +309,8 @@ class GraphStore(object):
         src_vids = csr._row_of_edge * W + rt.rank
         dst_vids = csr.indices.local
         w = csr.weights.local if csr.weights is not None else None
+        ts = csr.ts.local if csr.ts is not None else None
+        fwd = torch.arange(csr.n_edges, device=dst_vids.device)     # edge id = position in the forward CSR
         if W > 1:
             ok = dst_vids >= 0
             sorted_dst, order, counts = part.partition_by_owner(dst_vids[ok], W)
@@ -316,14 +318,21 @@ class GraphStore(object):
             rc = part.exchange_counts(counts)
             dst_vids = part._all_to_all_v(sorted_dst, sc, rc)
             src_vids = part._all_to_all_v(src_vids[ok][order], sc, rc)
+            fwd = part._all_to_all_v(fwd[ok][order], sc, rc)
             if w is not None:
                 w = part._all_to_all_v(w[ok][order], sc, rc)
+            if ts is not None:
+                ts = part._all_to_all_v(ts[ok][order], sc, rc)
         else:
             ok = dst_vids >= 0
-            dst_vids, src_vids = dst_vids[ok], src_vids[ok]
+            dst_vids, src_vids, fwd = dst_vids[ok], src_vids[ok], fwd[ok]
             w = w[ok] if w is not None else None
+            ts = ts[ok] if ts is not None else None
         rows = torch.div(dst_vids, W, rounding_mode="floor")
-        rev = CsrShard.from_coo(rt, etype + "#in", dt, st, rows, src_vids, self.nodes[dt].n_local, weights=w)
+        # in-edge rows keep the forward edge's id, weight and timestamp: inE()/inV() then honour
+        # topk / temporal filters and edge-attribute lookups address the ORIGINAL edge
+        rev = CsrShard.from_coo(rt, etype + "#in", dt, st, rows, src_vids, self.nodes[dt].n_local, weights=w, ts=ts,
+                                eids=fwd)
         self.reverse[etype] = rev
         ip = rev.indptr.local
         self.nodes[dt].in_degrees[etype] = ip[1:] - ip[:-1]

@@ -264,11 +264,19 @@ class CsrShard:
         self.timestamped = False
         self.dst_ids_unique: Optional[torch.Tensor] = None   # distinct dst vids on this shard (neg sampling)
 
+    def insertion_pos(self) -> torch.Tensor:
+        """CSR position of the i-th INSERTED edge of this shard (inverse of ``_order``)."""
+        if getattr(self, "_ins_pos", None) is None:
+            inv = torch.empty_like(self._order)
+            inv[self._order] = torch.arange(self._order.numel(), device=self._order.device)
+            self._ins_pos = inv
+        return self._ins_pos
+
     @staticmethod
     def from_coo(rt: Runtime, etype, src_type, dst_type, src_rows: torch.Tensor, dst_vids: torch.Tensor,
                  n_src_rows: int, weights: Optional[torch.Tensor] = None, ts: Optional[torch.Tensor] = None,
                  labels: Optional[torch.Tensor] = None, float_attrs: Optional[torch.Tensor] = None,
-                 int_attrs: Optional[torch.Tensor] = None) -> "CsrShard":
+                 int_attrs: Optional[torch.Tensor] = None, eids: Optional[torch.Tensor] = None) -> "CsrShard":
         """K11: build the CSR on the device.  Rows are ordered by timestamp
         ascending when `ts` is given, else by weight descending (top-k prefix)."""
         self = CsrShard(rt, etype, src_type, dst_type)
@@ -298,6 +306,8 @@ class CsrShard:
         if ts is not None:
             self.ts = rt.symm_from(ts[order].to(torch.int64))
             self.timestamped = True
+        if eids is not None:       # explicit edge ids (in-edge CSR: position of the edge in the forward CSR)
+            self.eids = rt.symm_from(eids[order].to(torch.int64))
         if labels is not None:
             self.labels = rt.symm_from(labels[order].to(torch.int64))
         if float_attrs is not None and float_attrs.numel() > 0:
@@ -331,7 +341,8 @@ class CsrShard:
         W = self.rt.world
         self.desc = make_csr_desc(
             W, self.indptr.nrows and [n - 1 for n in self.indptr.nrows], self.indptr.ptrs, self.indices.ptrs,
-            None, self.cumw.ptrs if self.cumw is not None else None,
+            self.eids.ptrs if getattr(self, "eids", None) is not None else None,
+            self.cumw.ptrs if self.cumw is not None else None,
             self.ts.ptrs if self.ts is not None else None)
         if self.cumw_indeg is not None:
             self.desc_indeg = make_csr_desc(
