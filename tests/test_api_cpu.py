@@ -229,7 +229,7 @@ def test_undirected_and_masks(tmp_path):
     assert g2.out_degrees(np.array([5]), "sim").tolist() == [6]
     q = g2.V("item", mask=gl.Mask.TRAIN).batch(4).alias("s").outV("sim").sample(3).by("random").alias("n").values()
     res = gl.Dataset(q).next()
-    assert res["s"].type == "MASKTRAIN_item" and res["n"].ids.shape == (4, 3)
+    assert res["s"].type == "item" and res["n"].ids.shape == (4, 3)
     d1 = (res["n"].ids - res["s"].ids[:, None]) % fx.N_ITEM
     assert (np.isin(d1, [1, 2, 3, fx.N_ITEM - 1, fx.N_ITEM - 2, fx.N_ITEM - 3])).all()
 
