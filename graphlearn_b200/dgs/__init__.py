@@ -14,7 +14,18 @@ state in HBM tables:
 * ``DynamicGraphService``  install_query / apply_updates / run_query (batched) / checkpoint / restore,
                       plus the adaptive ingest rate limiter (adaptive_rate_limiter.cc:52-87)
 
-Kafka, RocksDB, the HTTP front end, the Java client and the Helm chart are deployment glue around
-this core and are out of scope; ``apply_updates`` takes record batches (dict of arrays) directly.
+* ``Schema`` / ``Options``  the reference's JSON schema and YAML option files (schema.py)
+* ``QueryPlan.from_json``   the install-query JSON produced by the Java GSL client (plan.py)
+* ``FileLoader``            pattern-file driven record ingestion (file_loader.py; dataloader SDK)
+* ``HttpFrontEnd``          ``/infer?qid&vid`` + admin API (install query, checkpoint, barrier, stats)
+* ``CheckpointManager`` / ``BarrierMonitor``   coordinator duties (coordinator.py)
+
+Kafka, RocksDB, the Java client and the Helm chart are deployment glue around this core and are out
+of scope; ``apply_updates`` takes record batches (dict of arrays) directly.
 """
-from .service import AdaptiveRateLimiter, DynamicGraphService, QueryPlan, SampleStore  # noqa: F401
+from .coordinator import BarrierMonitor, CheckpointManager  # noqa: F401
+from .file_loader import FileLoader, RecordBatchBuilder  # noqa: F401
+from .http_server import HttpFrontEnd  # noqa: F401
+from .plan import PlanNode, QueryPlan  # noqa: F401
+from .schema import Options, Schema  # noqa: F401
+from .service import AdaptiveRateLimiter, DynamicGraphService, SampleStore  # noqa: F401

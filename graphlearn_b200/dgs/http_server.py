@@ -1,0 +1,117 @@
+"""HTTP front end (D11 + the admin surface of D12): the reference serves ``/infer?qid=&vid=`` from a
+seastar httpd on every serving worker (dynamic_graph_service/src/service/service.cc, docs/en/dgs) and
+installs queries / triggers checkpoints / sets barriers through the coordinator's admin HTTP API.
+Here one ``ThreadingHTTPServer`` fronts a ``DynamicGraphService``; query work is serialised on the
+device stream by a lock.
+
+  GET  /infer?qid=0&vid=12[,13,...]   -> {"src": [...], "nodes": {plan_node_id: {...}}}
+  POST /admin/init                     body = install-query JSON (reference format)   -> {"query_id": n}
+  POST /admin/ingest                   body = {"edges": {...}, "vertices": {...}}     (testing / small feeds)
+  POST /admin/checkpoint               -> {"checkpoint_id": n}
+  POST /admin/barrier/set?name=x[&produced=n]     GET /admin/barrier/status?name=x
+  GET  /admin/stats                    liveness + counters (k8s probes)
+"""
+from __future__ import annotations
+
+import json
+import threading
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from urllib.parse import parse_qs, urlparse
+
+import torch
+
+from .coordinator import BarrierMonitor, CheckpointManager
+from .plan import QueryPlan
+
+
+def _jsonable(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().tolist()
+    if isinstance(x, dict):
+        return {str(k): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    return x
+
+
+class HttpFrontEnd(object):
+    def __init__(self, service, schema=None, checkpoint_dir: str = "", host: str = "127.0.0.1", port: int = 0):
+        self.service, self.schema = service, schema
+        self.ckpt = CheckpointManager(service, checkpoint_dir) if checkpoint_dir else None
+        self.barriers = BarrierMonitor(service)
+        self._lock = threading.Lock()
+        front = self
+
+        class Handler(BaseHTTPRequestHandler):
+            def log_message(self, *a):      # quiet
+                pass
+
+            def _send(self, code, obj):
+                body = json.dumps(obj).encode()
+                self.send_response(code)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Length", str(len(body)))
+                self.end_headers()
+                self.wfile.write(body)
+
+            def _body(self):
+                n = int(self.headers.get("Content-Length", 0) or 0)
+                return json.loads(self.rfile.read(n) or b"{}") if n else {}
+
+            def do_GET(self):
+                u = urlparse(self.path)
+                q = parse_qs(u.query)
+                try:
+                    if u.path == "/infer":
+                        vids = [int(v) for v in q["vid"][0].split(",")]
+                        with front._lock:
+                            res = front.service.run_query(int(q["qid"][0]), vids)
+                        self._send(200, {"src": _jsonable(res["src"]), "nodes": _jsonable(res["nodes"])})
+                    elif u.path == "/admin/stats":
+                        self._send(200, front.service.stats())
+                    elif u.path == "/admin/barrier/status":
+                        self._send(200, {"status": front.barriers.status(q["name"][0])})
+                    else:
+                        self._send(404, {"error": "unknown path"})
+                except Exception as e:  # noqa: BLE001
+                    self._send(400, {"error": repr(e)})
+
+            def do_POST(self):
+                u = urlparse(self.path)
+                q = parse_qs(u.query)
+                try:
+                    if u.path == "/admin/init":
+                        d = self._body()
+                        plan = QueryPlan.from_json(d, front.schema)
+                        qid = int(d.get("query_id", len(front.service.queries)))
+                        with front._lock:
+                            front.service.install_query(qid, plan)
+                        self._send(200, {"query_id": qid})
+                    elif u.path == "/admin/ingest":
+                        with front._lock:
+                            front.service.apply_updates(self._body())
+                        self._send(200, {"ingested": front.service.ingested})
+                    elif u.path == "/admin/checkpoint":
+                        with front._lock:
+                            cid = front.ckpt.save()
+                        self._send(200, {"checkpoint_id": cid})
+                    elif u.path == "/admin/barrier/set":
+                        front.barriers.set(q["name"][0], int(q["produced"][0]) if "produced" in q else None)
+                        self._send(200, {"ok": True})
+                    else:
+                        self._send(404, {"error": "unknown path"})
+                except Exception as e:  # noqa: BLE001
+                    self._send(400, {"error": repr(e)})
+
+        self.httpd = ThreadingHTTPServer((host, port), Handler)
+        self.port = self.httpd.server_address[1]
+        self._thread = None
+
+    def start(self):
+        self._thread = threading.Thread(target=self.httpd.serve_forever, daemon=True)
+        self._thread.start()
+        return self
+
+    def stop(self):
+        self.httpd.shutdown()
+        self.httpd.server_close()

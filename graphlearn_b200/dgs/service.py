@@ -19,11 +19,30 @@ class SampleStore(object):
         self.feat = torch.zeros((self.n, feat_dim), dtype=torch.float32, device=device) if feat_dim else None
         self.feat_ts = torch.full((self.n,), -(2 ** 62), dtype=torch.int64, device=device) if feat_dim else None
 
+    def ensure(self, n: int):
+        """grow the tables (doubling) so that vertex ids < n are addressable - the reference's KV store
+        has no fixed vertex universe, the HBM tables emulate that by amortised growth"""
+        if n <= self.n:
+            return
+        new_n = max(n, 2 * self.n)
+        grow = new_n - self.n
+
+        def ext(t, fill):
+            pad = torch.full((grow,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+            return torch.cat([t, pad])
+        self.nbr, self.ts, self.w = ext(self.nbr, -1), ext(self.ts, -(2 ** 62)), ext(self.w, 0)
+        self.count = ext(self.count, 0)
+        if self.feat is not None:
+            self.feat, self.feat_ts = ext(self.feat, 0), ext(self.feat_ts, -(2 ** 62))
+        self.n = new_n
+
     def apply_edges(self, src: torch.Tensor, dst: torch.Tensor, ts: torch.Tensor, w: Optional[torch.Tensor] = None):
         """TopK-by-timestamp: an incoming edge replaces the OLDEST kept sample of its source if it is
         newer.  Processed in timestamp order; duplicates of one source inside a batch are resolved in
         rounds (each round applies at most one update per source)."""
         src, dst, ts = src.to(self.device), dst.to(self.device), ts.to(self.device)
+        if src.numel():
+            self.ensure(int(src.max().item()) + 1)
         w = torch.ones_like(ts, dtype=torch.float32) if w is None else w.to(self.device).float()
         order = torch.argsort(ts, stable=True)
         src, dst, ts, w = src[order], dst[order], ts[order], w[order]
@@ -52,6 +71,8 @@ class SampleStore(object):
         if self.feat is None:
             return
         vid, ts, feat = vid.to(self.device), ts.to(self.device), feat.to(self.device).float()
+        if vid.numel():
+            self.ensure(int(vid.max().item()) + 1)
         order = torch.argsort(ts, stable=True)
         vid, ts, feat = vid[order], ts[order], feat[order]
         newer = ts >= self.feat_ts[vid]
@@ -61,6 +82,7 @@ class SampleStore(object):
 
     def lookup(self, vids: torch.Tensor, k: int):
         """most recent k samples of each vertex: (nbr [B,k], ts [B,k], w [B,k]); -1 padded."""
+        vids = torch.where(vids < self.n, vids, torch.zeros_like(vids)) if vids.numel() else vids
         t, order = torch.sort(self.ts[vids], dim=1, descending=True)
         order = order[:, :k]
         return (torch.gather(self.nbr[vids], 1, order), t[:, :k], torch.gather(self.w[vids], 1, order))
@@ -70,21 +92,12 @@ class SampleStore(object):
                ({"feat": self.feat.clone(), "feat_ts": self.feat_ts.clone()} if self.feat is not None else {})
 
     def load_state_dict(self, sd):
+        self.ensure(int(sd["nbr"].size(0)))
         for k, v in sd.items():
-            getattr(self, k).copy_(v)
+            getattr(self, k)[:v.size(0)].copy_(v)
 
 
-class QueryPlan(object):
-    """SOURCE -> sampler hops, e.g. QueryPlan("user").out("click", 10).out("sim", 5)."""
-
-    def __init__(self, source_type: str):
-        self.source_type = source_type
-        self.hops: List[tuple] = []
-
-    def out(self, edge_type: str, k: int, strategy: str = "topk_by_timestamp"):
-        assert strategy == "topk_by_timestamp", "the streaming sampler keeps the k most recent edges"
-        self.hops.append((edge_type, int(k)))
-        return self
+from .plan import PlanNode, QueryPlan  # noqa: E402,F401
 
 
 class AdaptiveRateLimiter(object):
@@ -126,6 +139,7 @@ class DynamicGraphService(object):
         self.queries: Dict[int, QueryPlan] = {}
         self.limiter = AdaptiveRateLimiter()
         self.ingested = 0
+        self.served = 0
         for vt, info in schema["vertices"].items():
             self.vstores[vt] = SampleStore(info["count"], 1, self.device, feat_dim=info.get("feat_dim", 0))
 
@@ -157,25 +171,52 @@ class DynamicGraphService(object):
                                             torch.as_tensor(rec["feat"]))
 
     def run_query(self, qid: int, vids: Sequence[int]) -> dict:
-        """Batched inference-time lookup: hop i returns ids [B*prod(k_<i), k_i] (-1 padded) + timestamps,
-        and the latest features of every returned vertex."""
+        """Batched inference-time lookup.  Walks the plan tree (QueryExecutor, query_executor.cc:42-125):
+        every EDGE_SAMPLER node returns ids [B*prod(k of its ancestors), k] (-1 padded) + timestamps +
+        weights and the latest features of the returned vertices; VERTEX_SAMPLER nodes return the
+        latest feature rows of their input vertices.  ``out["hops"]`` lists the edge nodes in plan
+        order (chain plans: hop i), ``out["nodes"][plan_node_id]`` has every node."""
         t0 = time.perf_counter()
         plan = self.queries[qid]
-        cur = torch.as_tensor(list(vids) if not isinstance(vids, torch.Tensor) else vids, dtype=torch.int64).to(self.device)
-        out = {"src": cur, "hops": []}
-        cur_type = plan.source_type
-        for etype, k in plan.hops:
-            st = self.stores[etype]
-            safe = cur.clamp(min=0)
-            nbr, ts, w = st.lookup(safe.reshape(-1), k)
-            nbr = torch.where((cur.reshape(-1) >= 0)[:, None], nbr, torch.full_like(nbr, -1))
-            cur_type = self.schema["edges"][etype]["dst"]
-            vs = self.vstores[cur_type]
-            feat = vs.feat[nbr.clamp(min=0)] if vs.feat is not None else None
-            out["hops"].append({"edge_type": etype, "ids": nbr, "timestamps": ts, "weights": w, "features": feat})
-            cur = nbr.reshape(-1)
+        src = torch.as_tensor(list(vids) if not isinstance(vids, torch.Tensor) else vids, dtype=torch.int64).to(self.device)
+        out = {"src": src, "hops": [], "nodes": {}}
+        cur_ids = {0: (src, plan.source_type)}
+        for nid in plan.topo_order():
+            node = plan.nodes[nid]
+            if node.kind == "SOURCE":
+                continue
+            cur, cur_type = cur_ids[node.parent]
+            flat = cur.reshape(-1)
+            if node.kind == "VERTEX_SAMPLER":
+                vs = self.vstores[node.vtype or cur_type]
+                ok = (flat >= 0) & (flat < vs.n)
+                feat = vs.feat[torch.where(ok, flat, torch.zeros_like(flat))] if vs.feat is not None else None
+                if feat is not None:
+                    feat = torch.where(ok[:, None], feat, torch.zeros_like(feat))
+                out["nodes"][nid] = {"kind": node.kind, "ids": flat, "features": feat}
+                continue
+            st = self.stores[node.etype]
+            nbr, ts, w = st.lookup(flat.clamp(min=0), node.fanout)
+            ok = ((flat >= 0) & (flat < st.n))[:, None]
+            nbr = torch.where(ok, nbr, torch.full_like(nbr, -1))
+            dst_type = self.schema["edges"][node.etype]["dst"]
+            vs = self.vstores[dst_type]
+            feat = None
+            if vs.feat is not None:
+                okv = (nbr >= 0) & (nbr < vs.n)
+                feat = vs.feat[torch.where(okv, nbr, torch.zeros_like(nbr))] * okv.unsqueeze(-1)
+            rec = {"kind": node.kind, "edge_type": node.etype, "ids": nbr, "timestamps": ts, "weights": w, "features": feat}
+            out["nodes"][nid] = rec
+            out["hops"].append(rec)
+            cur_ids[nid] = (nbr, dst_type)
         self.limiter.record((time.perf_counter() - t0) * 1e3)
+        self.served += int(src.numel())
         return out
+
+    def stats(self) -> dict:
+        return {"ingested": self.ingested, "served": self.served, "queries": sorted(self.queries),
+                "concurrency": self.limiter.concurrency,
+                "stores": {k: {"vertices": v.n, "capacity": v.K, "filled": int((v.count > 0).sum())} for k, v in self.stores.items()}}
 
     def checkpoint(self) -> dict:
         return {"stores": {k: v.state_dict() for k, v in self.stores.items()},

@@ -49,3 +49,79 @@ def test_rate_limiter():
             rl.record(1.0)
         c = rl.tick()
     assert c == 11
+
+
+def test_reference_config_formats_file_loader_http_and_checkpoints(tmp_path):
+    """The reference's own schema / install-query JSON drive the service; records come from a pattern
+    file; inference goes through the HTTP front end; a checkpoint restores into a fresh service."""
+    import json
+    import urllib.request
+    from graphlearn_b200.dgs import (CheckpointManager, FileLoader, HttpFrontEnd, Options, QueryPlan, Schema)
+    schema_json = {
+        "attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}, {"type": 1, "name": "weight", "value_type": "FLOAT32"},
+                      {"type": 2, "name": "feature", "value_type": "FLOAT32_LIST"}],
+        "vertex_defs": [{"vtype": 0, "name": "user", "attr_types": [0, 2]}, {"vtype": 1, "name": "item", "attr_types": [0, 2]}],
+        "edge_defs": [{"etype": 2, "name": "u2i", "attr_types": [0, 1]}, {"etype": 3, "name": "i2i", "attr_types": [0, 1]}],
+        "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}, {"etype": 3, "src_vtype": 1, "dst_vtype": 1}]}
+    sp = tmp_path / "schema.json"
+    sp.write_text(json.dumps(schema_json))
+    schema = Schema.from_json(str(sp))
+    assert schema.relations == {"u2i": ("user", "item"), "i2i": ("item", "item")}
+    (tmp_path / "opt.yml").write_text("worker-type: Serving\nrecord-polling:\n  process-concurrency: 4\n")
+    opt = Options.from_yaml(str(tmp_path / "opt.yml"))
+    assert opt.get("record-polling.process-concurrency") == 4 and opt.get("record-polling.retry-interval-ms") == 1000
+
+    def node(i, kind, links, **params):
+        return {"id": i, "kind": kind, "type": "EDGE" if kind == "EDGE_SAMPLER" else "VERTEX",
+                "links": [{"node": l, "src_output": 0, "dst_input": 0} for l in links],
+                "params": [{"key": k, "value": v} for k, v in params.items()]}
+    install = {"query_id": 7, "query_plan": {"plan_nodes": [
+        node(0, "SOURCE", [1, 2], vtype=0, versions=1), node(1, "VERTEX_SAMPLER", [], vtype=0, versions=1),
+        node(2, "EDGE_SAMPLER", [3, 4], vtype=0, etype=2, fanout=3, strategy=0),
+        node(3, "VERTEX_SAMPLER", [], vtype=1, versions=1), node(4, "EDGE_SAMPLER", [], vtype=1, etype=3, fanout=2, strategy=0)]}}
+    plan = QueryPlan.from_json(install, schema)
+    assert plan.hops == [("u2i", 3), ("i2i", 2)]
+    svc = DynamicGraphService(schema.to_service_schema(capacity=4, feat_dims={"user": 2, "item": 2}), device="cpu")
+    front = HttpFrontEnd(svc, schema, checkpoint_dir=str(tmp_path / "ck")).start()
+    base = "http://127.0.0.1:%d" % front.port
+
+    def call(path, body=None):
+        req = urllib.request.Request(base + path, data=None if body is None else json.dumps(body).encode(),
+                                     method="GET" if body is None else "POST")
+        with urllib.request.urlopen(req, timeout=10) as r:
+            return json.loads(r.read())
+    try:
+        assert call("/admin/init", install)["query_id"] == 7
+        (tmp_path / "pattern").write_text("#VERTEX:user,vid,timestamp,feature\n#VERTEX:item,vid,timestamp,feature\n"
+                                          "#EDGE:u2i,src,dst,timestamp,weight\n#EDGE:i2i,src,dst,timestamp,weight\n")
+        lines = ["user,%d,1,0.5:%d" % (u, u) for u in range(10)] + ["item,%d,1,%d:0.25" % (i, i) for i in range(40)]
+        want = {}
+        for t in range(200):
+            u, i = t % 10, (t * 7) % 40
+            lines.append("u2i,%d,%d,%d,1.5" % (u, i, 100 + t))
+            want.setdefault(u, []).append((100 + t, i))
+            lines.append("i2i,%d,%d,%d,0.5" % (i, (i + 1) % 40, 100 + t))
+        (tmp_path / "data").write_text("\n".join(lines) + "\n")
+        n = FileLoader(str(tmp_path / "pattern"), schema, batch_size=64).load(str(tmp_path / "data"), svc)
+        assert n == len(lines) and svc.stores["u2i"].n >= 10          # tables grew past the initial capacity 4
+        res = call("/infer?qid=7&vid=3,4")
+        nodes = res["nodes"]
+        e = [v for v in nodes.values() if v.get("edge_type") == "u2i"][0]
+        for row, u in zip(e["ids"], (3, 4)):
+            assert row == [i for _, i in sorted(want[u], reverse=True)[:3]]
+        e2 = [v for v in nodes.values() if v.get("edge_type") == "i2i"][0]
+        assert e2["ids"][0][0] == (e["ids"][0][0] + 1) % 40
+        vs = [v for v in nodes.values() if v["kind"] == "VERTEX_SAMPLER" and len(v["ids"]) == 2][0]
+        assert vs["features"][0] == [0.5, 3.0]
+        call("/admin/barrier/set?name=b1&produced=%d" % (svc.ingested + 5), {})
+        assert call("/admin/barrier/status?name=b1")["status"] == "PRODUCED"
+        call("/admin/ingest", {"edges": {"u2i": {"src": [1] * 5, "dst": [2] * 5, "ts": list(range(900, 905))}}})
+        assert call("/admin/barrier/status?name=b1")["status"] == "READY"
+        assert call("/admin/checkpoint", {})["checkpoint_id"] == 1
+        assert call("/admin/stats")["served"] == 2
+    finally:
+        front.stop()
+    svc2 = DynamicGraphService(schema.to_service_schema(capacity=4, feat_dims={"user": 2, "item": 2}), device="cpu")
+    assert CheckpointManager(svc2, str(tmp_path / "ck")).restore_latest() == 1
+    a, b = svc.run_query(7, [1, 3]), svc2.run_query(7, [1, 3])
+    assert torch.equal(a["hops"][0]["ids"], b["hops"][0]["ids"]) and torch.equal(a["hops"][1]["ids"], b["hops"][1]["ids"])
