@@ -194,7 +194,10 @@ def run_ours(args):
     torch.cuda.synchronize(); rt.barrier()
     ms_dev = ev0.elapsed_time(ev1)
 
-    # ---- end-to-end region: pinned-host seeds -> device each step, loss -> host each step
+    # ---- end-to-end region through the public step(): every call copies that call's seed batch from pinned
+    # host memory to the device and one loss back to pinned host memory.  Both copies are nodes of the step's
+    # CUDA graph on side branches (the batch staged by call t is trained by call t+1: input prefetch), so the
+    # PCIe round trips overlap the compute instead of serialising with it.
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rt.barrier(); torch.cuda.synchronize()
     ev2.record()

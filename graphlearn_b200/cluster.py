@@ -23,3 +23,19 @@ def get_cluster(cluster_spec=None, job_name=None, task_index=None):
     rank = int(os.environ.get("RANK", "0"))
     spec = cluster_spec or {"server_count": world, "client_count": world}
     return spec, job_name or "worker", rank if task_index is None else task_index
+
+
+def get_cluster_spec(port=None, addr=None, gl_rank=None, world_size=None):
+    """PyTorch-side helper of the reference (nn/pytorch/data/utils.py:64-110): every DDP rank
+    all-reduces its sampler server's ip:port to build the cluster spec.  There are no sampler
+    servers here - sampling is a device kernel inside each rank - so the spec only names the ranks."""
+    world = int(world_size if world_size is not None else os.environ.get("WORLD_SIZE", "1"))
+    host = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+    return {"server": ",".join("%s:%d" % (host, 0) for _ in range(world)), "client_count": world}
+
+
+def launch_server(graph, cluster=None, task_index=0):
+    """Reference: starts a GL server in a daemon process next to each trainer
+    (nn/pytorch/data/utils.py:112-138).  Here "serving" the graph means having built this rank's
+    shard in HBM, so the call just initialises the graph (idempotent) and returns it."""
+    return graph.init(task_index=task_index, cluster=cluster or "", job_name="server")

@@ -84,6 +84,7 @@ class FastSageTrainer:
             self.dZ.append(torch.zeros(rows, c.out_dim, dtype=torch.bfloat16, device=dev))
             self.dA.append(torch.zeros(rows, kt, dtype=torch.bfloat16, device=dev) if l > 1 else None)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._post_loss_hook = None
         self.use_graph = bool(use_cuda_graph)
         self._steps = 0
         self.h_seeds = torch.zeros(self.B, dtype=torch.int64).pin_memory()
@@ -155,6 +156,8 @@ class FastSageTrainer:
         top = self.convs[L - 1]
         C.softmax_ce(self.H[L - 1], self.nodes.labels.local, self.seeds, self.rt.world, self.loss, self.dZ[L - 1],
                      top.bias.grad if top.bias is not None else None)
+        if self._post_loss_hook is not None:
+            self._post_loss_hook()          # e2e graph capture: fork the loss D2H here, parallel to the backward
         # ---- backward
         for l in range(L, 0, -1):
             c = self.convs[l - 1]
@@ -199,16 +202,36 @@ class FastSageTrainer:
         with torch.cuda.graph(g):
             self._step_body()
         self.graph = g
+        # (b) two end-to-end graphs, software pipelined so that no PCIe round trip sits on the critical
+        # path (tools/diag_e2e.py: the two host-memory accesses cost 18 us when serialised with the step):
+        #   branch 1  the training step on the seed batch already resident in seeds buffer i
+        #   branch 2  prefetch of the NEXT step's seeds, pinned host staging slot i^1 -> seeds buffer i^1
+        #   branch 3  (forked right after the loss kernel) loss -> pinned host slot i, overlapping the backward
+        self._seeds_bufs = [self.seeds, torch.zeros_like(self.seeds)]
         self._e2e_graphs = []
+        side_in, side_out = torch.cuda.Stream(), torch.cuda.Stream()
         for i in range(2):
             gi = torch.cuda.CUDAGraph()
+            self.seeds = self._seeds_bufs[i]
             with torch.cuda.graph(gi, pool=g.pool()):
-                # zero-copy staging: the pinned host buffers are read / written by tiny copy KERNELS over
-                # PCIe (UVA-mapped), which is ~3x cheaper than DMA memcpy nodes for 8 KB / 4 B payloads
-                self.seeds.copy_(self._h_seeds_dev[i])
+                main = torch.cuda.current_stream()
+                side_in.wait_stream(main)
+                with torch.cuda.stream(side_in):
+                    # zero-copy staging: a tiny copy KERNEL reads the UVA-mapped pinned buffer over PCIe
+                    self._seeds_bufs[i ^ 1].copy_(self._h_seeds_dev[i ^ 1])
+
+                def hook(i=i):
+                    side_out.wait_stream(main)
+                    with torch.cuda.stream(side_out):
+                        self._h_loss_dev[i].copy_(self.loss)
+                self._post_loss_hook = hook
                 self._step_body()
-                self._h_loss_dev[i].copy_(self.loss)
+                self._post_loss_hook = None
+                main.wait_stream(side_in)
+                main.wait_stream(side_out)
             self._e2e_graphs.append(gi)
+        self.seeds = self._seeds_bufs[0]
+        self._primed = False
         torch.cuda.synchronize()
         self.rt.barrier()
 
@@ -224,9 +247,15 @@ class FastSageTrainer:
         train, loss -> pinned host.  Asynchronous: synchronise before reading the returned tensor.
         With CUDA graphs the copies are nodes of the step graph (double-buffered staging)."""
         if self.graph is not None and getattr(self, "_e2e_graphs", None):
+            # Pipelined: this call stages `seed_ids_host` (H2D happens inside the graph, in parallel with the
+            # training step) and trains on the batch staged by the PREVIOUS call; the returned pinned tensor
+            # receives that step's loss.  The very first call also places its batch on the device directly.
             i = self._steps & 1
-            self._e2e_done[i].synchronize()                 # step t-2 no longer reads staging slot i
-            self._h_seeds2[i].copy_(seed_ids_host)
+            if not self._primed:
+                self._seeds_bufs[i].copy_(seed_ids_host)
+                self._primed = True
+            self._e2e_done[i].synchronize()    # step t-2 (same graph) was the last reader of staging slot i^1
+            self._h_seeds2[i ^ 1].copy_(seed_ids_host)
             self._e2e_graphs[i].replay()
             self._e2e_done[i].record()
             self._steps += 1

@@ -5,7 +5,7 @@ from .conv import (EgoGATConv, EgoGINConv, EgoLayer, EgoRGCNConv, EgoSAGEConv, E
                    TimeEncoder)
 from .norm import compute_saint_norm  # noqa: F401
 from .data import BatchGraph, Data, EgoGraph, HeteroBatchGraph  # noqa: F401
-from .dataset import Dataset, TorchDataset  # noqa: F401
+from .dataset import Batch, Dataset, PyGDataLoader, SubGraphData, TorchDataset  # noqa: F401
 from .embedding import ShardedEmbedding  # noqa: F401
 from .feature import FeatureEncoder  # noqa: F401
 from .sparse_conv import GATConv, GCNConv, SAGEConv, segment_softmax  # noqa: F401

@@ -75,3 +75,62 @@ class TorchDataset(torch.utils.data.IterableDataset):
                 return
             n += 1
             yield self._transform(d) if self._transform else d
+
+
+class SubGraphData(object):
+    """Minimal stand-in for a PyG ``Data`` (x, edge_index, y [, extra]) - PyG is not part of this
+    image; models in ``graphlearn_b200.models`` consume (x, edge_index) directly."""
+
+    def __init__(self, x, edge_index, y=None, **kw):
+        self.x, self.edge_index, self.y = x, edge_index, y
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self):
+        return int(self.x.size(0))
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, v.to(device))
+        return self
+
+
+class Batch(SubGraphData):
+    """Concatenation of SubGraphData items with node offsets (``Batch.from_data_list``)."""
+
+    @staticmethod
+    def from_data_list(items: Sequence[SubGraphData]) -> "Batch":
+        off, xs, eis, ys, batch = 0, [], [], [], []
+        for i, d in enumerate(items):
+            xs.append(d.x); eis.append(d.edge_index + off)
+            if d.y is not None:
+                ys.append(d.y.reshape(-1))
+            batch.append(torch.full((d.num_nodes,), i, dtype=torch.long, device=d.x.device))
+            off += d.num_nodes
+        return Batch(torch.cat(xs), torch.cat(eis, 1), torch.cat(ys) if ys else None, batch=torch.cat(batch),
+                     num_graphs=len(items))
+
+
+class PyGDataLoader(object):
+    """Loader over a ``TorchDataset`` whose ``transform`` (the reference's ``induce_func``) returns a
+    list of subgraphs per GSL batch; yields one collated ``Batch`` per GSL batch
+    (graphlearn/python/nn/pytorch/data/pyg_dataloader.py:42-117: batch_size is forced to 1 there because
+    the GSL query already batches; ``length`` fixes the number of iterations per epoch so that all
+    DDP ranks take the same number of steps).  No worker processes: batches are born on the GPU."""
+
+    def __init__(self, dataset: TorchDataset, length: Optional[int] = None, collate_fn: Optional[Callable] = None, **_ignored):
+        self.dataset, self.length = dataset, length
+        self.collate_fn = collate_fn or Batch.from_data_list
+
+    def __iter__(self):
+        n = 0
+        for item in self.dataset:
+            if self.length is not None and n >= self.length:
+                return
+            n += 1
+            yield self.collate_fn(item) if isinstance(item, (list, tuple)) else item
+
+    def __len__(self):
+        return self.length if self.length is not None else 0

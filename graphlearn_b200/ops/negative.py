@@ -195,7 +195,21 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
     base_strategy = strategy if strategy in ("random", "in_degree") else "random"
     out = edge_negative(store, etype, src_v, k, base_strategy, gen)
     cols = [("int", c, p) for c, p in zip(cond.get("int_cols", []), cond.get("int_props", []))] + \
-           [("float", c, p) for c, p in zip(cond.get("float_cols", []), cond.get("float_props", []))]
+           [("float", c, p) for c, p in zip(cond.get("float_cols", []), cond.get("float_props", []))] + \
+           [("str", c, p) for c, p in zip(cond.get("str_cols", []), cond.get("str_props", []))]
+    batch_share = bool(cond.get("batch_share"))
+    if batch_share:
+        # the exclusion set is the batch's positive dst ids, shared by every row, instead of each
+        # row's own neighbourhood (conditional_negative_sampler.cc:113-126)
+        pos_sorted = torch.sort(torch.unique(dst_v))[0]
+
+        def _excluded(cand):
+            pos = torch.searchsorted(pos_sorted, cand.reshape(-1)).clamp_(max=max(pos_sorted.numel() - 1, 0))
+            return (pos_sorted[pos] == cand.reshape(-1)).reshape(cand.shape)
+        out = torch.where(_excluded(out), edge_negative(store, etype, src_v, k, base_strategy, gen), out)
+    else:
+        def _excluded(cand):
+            return _is_neighbor(csr, src_v, cand) | (cand == dst_v[:, None])
     if not cols:
         return out
     slot = 0
@@ -204,7 +218,18 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
         if n_slots <= 0 or slot >= k:
             continue
         n_slots = min(n_slots, k - slot)
-        if kind == "int":
+        if kind == "str":
+            # string attributes live on the host of the owning rank: factorise the local column and the
+            # positives' values into integer codes, then reuse the sorted-run index below
+            import numpy as np
+            if tab.strings is None or rt.world > 1:
+                slot += n_slots        # remote string lookups are not routed: slots keep base-strategy draws
+                continue
+            col = np.asarray(tab.strings[:, c], dtype=object)
+            uniq, codes = np.unique(col.astype(str), return_inverse=True)
+            local_vals = torch.as_tensor(codes, device=dev).long()
+            dstv = local_vals[torch.div(dst_v, rt.world, rounding_mode="floor").clamp(min=0, max=max(local_vals.numel() - 1, 0))]
+        elif kind == "int":
             attr_all = tab.ints
             dstv = G.gather_any(rt, attr_all, dst_v, fill=0)[:, c]
             local_vals = attr_all.local[:, c]
@@ -223,8 +248,7 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
         pick = torch.minimum(pick, (hi - 1).clamp(min=0)[:, None]).clamp_(min=0, max=max(order.numel() - 1, 0))
         cand = order[pick] * rt.world + rt.rank if order.numel() else torch.full((B, n_slots), -1, device=dev)
         ok = (span > 0)[:, None].expand(B, n_slots)
-        bad_nbr = _is_neighbor(csr, src_v, cand) | (cand == dst_v[:, None])
-        use = ok & ~bad_nbr
+        use = ok & ~_excluded(cand)
         out[:, slot:slot + n_slots] = torch.where(use, cand, out[:, slot:slot + n_slots])
         slot += n_slots
     if cond.get("unique"):

@@ -330,6 +330,31 @@ def test_fast_engine_learns_3layer(rt):
     assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
 
 
+def test_fast_engine_e2e_pipeline_staging(rt):
+    """public step(): seeds travel pinned host -> device inside the step graph one call ahead of the
+    step that trains on them, the loss comes back through the pinned slot of the same call."""
+    from graphlearn_b200.engine.fast_sage import FastSageTrainer
+    from graphlearn_b200.models.graphsage import EgoGraphSAGE
+    from graphlearn_b200.store.synthetic import make_sharded_graph
+    nodes, csr = make_sharded_graph(rt, 20000, 400000, 64, 8, seed=11)
+    model = EgoGraphSAGE(64, 128, 8, 2).to(rt.device)
+    tr = FastSageTrainer(rt, nodes, csr, model, [5, 4], 256, lr=5e-3)
+    tr.seeds.copy_(torch.randint(0, 20000, (256,), device=rt.device))
+    tr.capture()
+    s = [torch.randint(0, 20000, (256,)) for _ in range(4)]
+    l0 = tr.step(s[0]); torch.cuda.synchronize()
+    assert torch.equal(tr._seeds_bufs[0].cpu(), s[0]) and torch.equal(tr._seeds_bufs[1].cpu(), s[0])
+    l1 = tr.step(s[1]); torch.cuda.synchronize()
+    assert torch.equal(tr._seeds_bufs[0].cpu(), s[1])          # prefetched for the next call
+    assert float(l0) > 0 and float(l1) > 0 and l0.is_pinned() and l0.data_ptr() != l1.data_ptr()
+    l2 = tr.step(s[2]); torch.cuda.synchronize()
+    assert torch.equal(tr._seeds_bufs[1].cpu(), s[2]) and float(l2) > 0
+    # the eager (non-graph) trainer trains on the batch of the SAME call
+    tr2 = FastSageTrainer(rt, nodes, csr, EgoGraphSAGE(64, 128, 8, 2).to(rt.device), [5, 4], 256, use_cuda_graph=False)
+    l = tr2.step(s[3]); torch.cuda.synchronize()
+    assert torch.equal(tr2.seeds.cpu(), s[3]) and float(l) > 0
+
+
 def test_random_walk(rt, graph):
     from graphlearn_b200.ops import walk as WK
     nodes, csr = graph

@@ -220,3 +220,32 @@ def test_sharded_embedding_sparse_sgd():
     out.sum().backward()
     w1 = emb.local_weight()
     assert torch.allclose(w1[1], w0[1] - 0.5) and torch.allclose(w1[2], w0[2] - 1.0) and torch.allclose(w1[3], w0[3])
+
+
+def test_pyg_style_loader_and_cluster_helpers(tmp_path):
+    """P8: TorchDataset + induce_func -> list of subgraphs -> PyGDataLoader -> collated Batch."""
+    import graphlearn_b200 as gl
+    from graphlearn_b200 import nn as glnn
+    from graphlearn_b200.cluster import get_cluster_spec, launch_server
+    from tests import fixtures as fx
+    d = fx.write_graph(str(tmp_path))
+    g = gl.Graph().node(d + "/item.tsv", "item", decoder=gl.Decoder(attr_types=["float"] * 4)) \
+        .edge(d + "/i2i.tsv", ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
+    launch_server(g)                                   # == init()
+    assert get_cluster_spec(world_size=2)["client_count"] == 2
+    q = g.V("item").batch(5).alias("src").outV("sim").sample(3).by("random").alias("n1").values()
+
+    def induce(data):
+        src, n1 = data["src"], data["n1"]
+        out = []
+        for i in range(src.ids.numel()):
+            x = torch.cat([src.floats[i:i + 1], n1.floats[3 * i:3 * i + 3]])
+            ei = torch.tensor([[0, 0, 0], [1, 2, 3]], device=x.device)
+            out.append(glnn.SubGraphData(x, ei, y=src.ids[i:i + 1]))
+        return out
+    loader = glnn.PyGDataLoader(glnn.TorchDataset(q, transform=induce), length=3)
+    batches = list(loader)
+    assert len(batches) == 3
+    b = batches[0]
+    assert b.num_graphs == 5 and b.x.shape == (20, 4) and b.edge_index.shape == (2, 15)
+    assert b.edge_index[:, 3:6].tolist() == [[4, 4, 4], [5, 6, 7]] and b.batch.tolist() == sum([[i] * 4 for i in range(5)], [])
