@@ -85,6 +85,8 @@ class FastSageTrainer:
             self.dA.append(torch.zeros(rows, kt, dtype=torch.bfloat16, device=dev) if l > 1 else None)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._post_loss_hook = None
+        self._sides = (torch.cuda.Stream(), torch.cuda.Stream())
+        self._ev_pack = torch.cuda.Event()
         self.use_graph = bool(use_cuda_graph)
         self._steps = 0
         self.h_seeds = torch.zeros(self.B, dtype=torch.int64).pin_memory()
@@ -125,33 +127,61 @@ class FastSageTrainer:
 
     # ------------------------------------------------------------------ the step
     def _step_body(self):
+        """One training step as a small DAG of launches.  Independent work runs on forked streams (graph
+        branches under capture) so that kernel-boundary latencies overlap instead of adding up:
+            side B : zero grads, pack W_1..W_L (bf16 SW128 images)      || sampling (main)
+            side B : rng / optimiser step counters (after sampling)     || forward
+            side A : layer-l segment 0                                  || segments >= 1 (main)
+            side A : dW_l GEMM                                          || dA_l GEMM + input-gradient kernels (main)
+        everything joins before the gradient all-reduce + Adam."""
         C, L = self.C, self.L
-        self.g_store.zero_()
+        main = torch.cuda.current_stream()
+        sA, sB = self._sides
+        # ---- fork B: gradient zeroing + weight packing do not depend on the sampled batch
+        sB.wait_stream(main)
+        packs = []
+        with torch.cuda.stream(sB):
+            self.g_store.zero_()
+            for l in range(1, L + 1):
+                c = self.convs[l - 1]
+                packs.append(C.pack_weight_f32(c.weight_p.detach(), sage_ops.pad_n(c.out_dim), l > 1))
+            self._ev_pack.record(sB)
         hops = self.sample(self.seeds)
+        # counters advance once the sampling kernels have consumed the RNG offset; needed again only by Adam
+        sB.wait_stream(main)
+        with torch.cuda.stream(sB):
+            self.opt.advance(self.rng.state)
+        main.wait_event(self._ev_pack)
         # ---- forward
-        w16 = []
+        w16 = [p[1] for p in packs]
         for l in range(1, L + 1):
             c = self.convs[l - 1]
             last = l == L
             N = sage_ops.pad_n(c.out_dim)
-            img, wrow = C.pack_weight_f32(c.weight_p.detach(), N, l > 1)
-            w16.append(wrow)
+            img = packs[l - 1][0]
             offs = self.seg_off[l - 1]
             mode = sage_ops.MODE[c.agg_type]
-            for i in range(L - l + 1):
+            nseg = L - l + 1
+            if nseg > 1:
+                sA.wait_stream(main)
+            for i in range(nseg):
                 out = self.H[l - 1][offs[i]:offs[i + 1]]
                 a = self.A[l - 1][offs[i]:offs[i + 1]]
                 k = self.fanouts[i]
-                if l == 1:
-                    d = self.nodes.feat_desc
-                    C.sage_fused_forward(d, hops[i], d, hops[i + 1], self.n[i], k, mode, img, c.bias, N, c.out_dim,
-                                         not last, not last, True, 0, out, a, None, self.gather_mode)
-                else:
-                    po = self.seg_off[l - 2]
-                    xs = self.H[l - 2][po[i]:po[i + 1]]
-                    xn = self.H[l - 2][po[i + 1]:po[i + 2]]
-                    C.sage_fused_forward(local_table_desc(xs), None, local_table_desc(xn), None, self.n[i], k, mode,
-                                         img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a, None, self.gather_mode)
+                with torch.cuda.stream(sA if (i == 0 and nseg > 1) else main):
+                    if l == 1:
+                        d = self.nodes.feat_desc
+                        C.sage_fused_forward(d, hops[i], d, hops[i + 1], self.n[i], k, mode, img, c.bias, N, c.out_dim,
+                                             not last, not last, True, 0, out, a, None, self.gather_mode)
+                    else:
+                        po = self.seg_off[l - 2]
+                        xs = self.H[l - 2][po[i]:po[i + 1]]
+                        xn = self.H[l - 2][po[i + 1]:po[i + 2]]
+                        C.sage_fused_forward(local_table_desc(xs), None, local_table_desc(xn), None, self.n[i], k, mode,
+                                             img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a, None,
+                                             self.gather_mode)
+            if nseg > 1:
+                main.wait_stream(sA)
         # ---- loss (seeds are owned locally: labels are a local lookup)
         top = self.convs[L - 1]
         C.softmax_ce(self.H[L - 1], self.nodes.labels.local, self.seeds, self.rt.world, self.loss, self.dZ[L - 1],
@@ -162,9 +192,12 @@ class FastSageTrainer:
         for l in range(L, 0, -1):
             c = self.convs[l - 1]
             dz, a = self.dZ[l - 1], self.A[l - 1]
-            self._mm_into(c.weight_p.grad, dz.t(), a)                    # dW_l = dZ^T A
             if l == 1:
+                self._mm_into(c.weight_p.grad, dz.t(), a)                # dW_1 = dZ^T A (last launch of the backward)
                 break
+            sA.wait_stream(main)
+            with torch.cuda.stream(sA):
+                self._mm_into(c.weight_p.grad, dz.t(), a)                # dW_l = dZ^T A
             da = self.dA[l - 1]
             torch.mm(dz, w16[l - 1], out=da)                             # dA_l = dZ W_l
             prev = self.convs[l - 2]
@@ -179,9 +212,11 @@ class FastSageTrainer:
                 scale = (1.0 / k) if c.agg_type == "mean" else 1.0
                 C.sage_bwd_input(da_self, da_nbr, kp_self, k, scale, self.H[l - 2][rows], self.dZ[l - 2][rows],
                                  prev.bias.grad if prev.bias is not None else None)
-        # ---- gradient all-reduce + optimiser
+        # ---- join, gradient all-reduce + optimiser
+        main.wait_stream(sA)
+        main.wait_stream(sB)
         self.ar(self.flat_g, average=True)
-        self.opt.step(self.rng.state)
+        self.opt.apply()
 
     # ------------------------------------------------------------------ graph / public step (same API as SageTrainer)
     def capture(self, warmup: int = 3):

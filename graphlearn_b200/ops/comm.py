@@ -65,12 +65,20 @@ class FlatAdam:
         self.step_t = torch.zeros(1, dtype=torch.int64, device=flat_param.device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
 
+    def advance(self, rng_state=None):
+        """CUDA only: bump the device-resident optimiser step (and RNG offset) - split from ``apply`` so an
+        engine can run it on a side stream as soon as its sampling kernels have launched."""
+        native().step_advance(rng_state, self.step_t, 1)
+
+    def apply(self):
+        """CUDA only: fused Adam over the flat buffers using the already advanced step counter."""
+        native().adam_flat(self.p, self.g, self.m, self.v, self.step_t, self.lr, self.betas[0], self.betas[1], self.eps,
+                           self.wd)
+
     def step(self, rng_state=None):
         if self.p.is_cuda:
-            C = native()
-            C.step_advance(rng_state, self.step_t, 1)
-            C.adam_flat(self.p, self.g, self.m, self.v, self.step_t, self.lr, self.betas[0], self.betas[1], self.eps,
-                        self.wd)
+            self.advance(rng_state)
+            self.apply()
             return
         self.step_t += 1
         if rng_state is not None:
