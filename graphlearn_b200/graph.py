@@ -55,6 +55,7 @@ class Graph(object):
         self._datasets = []
         self._inited = False
         self._with_vineyard = False
+        self._node_views: List[tuple] = []
 
     # ------------------------------------------------------------------ description
     def node(self, source, node_type, decoder=None, option=None, mask=Mask.NONE):
@@ -73,6 +74,20 @@ class Graph(object):
             self._node_sources.append(Source("node", None, t, decoder, option=option, data=source))
         else:
             self._node_sources.append(Source("node", source, t, decoder, option=option))
+        return self
+
+    def node_view(self, node_type, mask=Mask.NONE, seed=0, nsplit=1, split_range=(0, 1)):
+        """Virtual masked view of an existing node type: the nodes whose ``hash(id, seed) % nsplit`` falls in
+        ``[split_range[0], split_range[1])`` become ``V(node_type, mask=mask)`` - train / val / test splits
+        without extra id files and without loading anything twice (graphlearn/python/graph.py:243-262; the
+        reference offers this for its Vineyard backend only, here it works for every source)."""
+        if not any(s.types == node_type for s in self._node_sources):
+            raise ValueError('Node type "%s" doesn\'t exist.' % (node_type,))
+        if mask == Mask.NONE:
+            raise ValueError("node_view() needs a TRAIN / VAL / TEST mask")
+        mt = get_mask_type(node_type, mask)
+        self._node_decoders[mt] = self._node_decoders[node_type]
+        self._node_views.append((node_type, mt, int(seed), int(nsplit), (int(split_range[0]), int(split_range[1]))))
         return self
 
     def edge(self, source, edge_type, decoder=None, directed=True, option=None, mask=Mask.NONE):
@@ -127,6 +142,8 @@ class Graph(object):
         self._store.node_decoders = self._node_decoders
         self._store.edge_decoders = self._edge_decoders
         self._store.build(self._node_sources, self._edge_sources)
+        for base, mt, seed, nsplit, rng in self._node_views:
+            self._store.add_node_view(base, mt, seed, nsplit, rng)
         cap = int(_config.get().local_node_cache_capacity)
         if cap > 0:      # reference: set_local_node_cache_capacity -> LFU cache of remote node attrs
             self._store.build_feature_caches(cap)

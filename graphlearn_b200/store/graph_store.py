@@ -271,6 +271,27 @@ class GraphStore(object):
             self.stats[et] = rt.all_gather_object(csr.n_edges)
         rt.barrier()
 
+    # ------------------------------------------------------------------ masked views (Graph.node_view)
+    def add_node_view(self, base_type: str, masked_type: str, seed: int, nsplit: int, split_range):
+        """Masked node table holding the ids of ``base_type`` with hash(id, seed) % nsplit in split_range.
+        Every rank filters the ids it owns, so the view is partitioned like its base.  Collective."""
+        base = self.nodes[base_type]
+        rows = base.present.nonzero().flatten() if base.present is not None else \
+            torch.arange(base.n_local, device=self.rt.device)
+        vids = rows * self.rt.world + self.rt.rank
+        ids = base.idmap.to_id(vids) if not base.idmap.dense else vids
+        h = (ids ^ (int(seed) * 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)) & 0x7FFFFFFFFFFFFFFF
+        h = ((h ^ (h >> 30)) * 0x5851F42D4C957F2D) & 0x7FFFFFFFFFFFFFFF      # splitmix-style mixing
+        h = ((h ^ (h >> 27)) * 0x14057B7EF767814F) & 0x7FFFFFFFFFFFFFFF
+        bucket = (h ^ (h >> 31)) % max(int(nsplit), 1)
+        keep = ids[(bucket >= split_range[0]) & (bucket < split_range[1])]
+        idmap = IdMap.build(self.rt, keep)
+        tab = NodeTable(self.rt, masked_type, idmap)
+        tab.present = torch.ones(idmap.n_local, dtype=torch.bool, device=self.rt.device)
+        self.nodes[masked_type] = tab
+        self.stats[masked_type] = self.rt.all_gather_object(idmap.n_local)
+        return tab
+
     # ------------------------------------------------------------------ N17: hot-feature replica cache
     def build_feature_caches(self, capacity: int) -> Dict[str, int]:
         """Cache up to ``capacity`` remote feature rows per node type on every rank, hottest

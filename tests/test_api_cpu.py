@@ -276,3 +276,31 @@ def test_native_loader_byte_range_slices(tmp_path):
             got = [C.load_table(p, True, True, False, False, [], [], ":", "\t", 4, i, parts) for i in range(parts)]
             for col in range(3):
                 assert torch.equal(torch.cat([g[col] for g in got]), full[col]), (header, n, parts, col)
+
+
+def test_node_view_splits(tmp_path):
+    """node_view(): hash splits of one node type act as TRAIN / VAL / TEST masks (disjoint, complete,
+    attributes come from the base table)."""
+    d = fx.write_graph(str(tmp_path))
+    g = gl.Graph()
+    g.node(d + "/item.tsv", "item", decoder=gl.Decoder(attr_types=["float"] * 4))
+    g.edge(d + "/i2i.tsv", ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
+    g.node_view("item", gl.Mask.TRAIN, seed=3, nsplit=10, split_range=(0, 7))
+    g.node_view("item", gl.Mask.VAL, seed=3, nsplit=10, split_range=(7, 8))
+    g.node_view("item", gl.Mask.TEST, seed=3, nsplit=10, split_range=(8, 10))
+    g.init(device="cpu")
+    got = {}
+    for m in (gl.Mask.TRAIN, gl.Mask.VAL, gl.Mask.TEST):
+        ds = gl.Dataset(g.V("item", mask=m).batch(16).alias("s").outV("sim").sample(2).by("random").alias("n").values())
+        ids = []
+        try:
+            while True:
+                r = ds.next()
+                ids.extend(r["s"].ids.tolist())
+                assert np.allclose(r["s"].float_attrs[:, 1], np.asarray(r["s"].ids) + 0.25)
+        except gl.OutOfRangeError:
+            pass
+        got[m] = ids
+    all_ids = sum(got.values(), [])
+    assert sorted(all_ids) == list(range(fx.N_ITEM))
+    assert len(got[gl.Mask.TRAIN]) > len(got[gl.Mask.TEST]) > 0
