@@ -47,6 +47,12 @@ void allreduce_oneshot(const at::Tensor&, const at::Tensor&, const at::Tensor&, 
 void step_advance(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t);
 void adam_flat(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
                double, double, double, double, double);
+// graph_ops.cu
+std::vector<at::Tensor> relabel(const at::Tensor&);
+at::Tensor relabel_lookup(const at::Tensor&, const at::Tensor&, const at::Tensor&);
+at::Tensor edge_scatter(const at::Tensor&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&,
+                        int64_t, int64_t);
+at::Tensor edge_dot(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, int64_t);
 // host_loader.cpp
 std::vector<at::Tensor> load_table(const std::string&, bool, bool, bool, bool, std::vector<int64_t>,
                                    std::vector<int64_t>, const std::string&, const std::string&, int64_t,
@@ -82,6 +88,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_oneshot", &glb::allreduce_oneshot);
   m.def("step_advance", &glb::step_advance);
   m.def("adam_flat", &glb::adam_flat);
+  m.def("relabel", &glb::relabel);
+  m.def("relabel_lookup", &glb::relabel_lookup);
+  m.def("edge_scatter", &glb::edge_scatter);
+  m.def("edge_dot", &glb::edge_dot);
   m.def("load_table", &glb::load_table);
   m.def("save_embeddings", &glb::save_embeddings);
 }

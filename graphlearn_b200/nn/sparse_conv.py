@@ -6,6 +6,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.sparse import spmm
+
 
 def segment_softmax(score: torch.Tensor, index: torch.Tensor, num_segments: int) -> torch.Tensor:
     """softmax of `score` [E, ...] within groups given by `index` [E] (utils/softmax.py:24-50)."""
@@ -38,7 +40,7 @@ class GCNConv(nn.Module):
             deg = torch.zeros(n, device=x.device).scatter_add(0, row, w)
             dinv = deg.clamp(min=1).pow(-0.5)
             w = dinv[row] * dinv[col]
-        out = torch.zeros(n, h.size(1), device=x.device).index_add_(0, row, h[col] * w[:, None])
+        out = spmm(h, row, col, w, n)                  # fused gather x norm -> scatter-add (K6)
         return out + self.bias if self.bias is not None else out
 
 
@@ -55,7 +57,7 @@ class SAGEConv(nn.Module):
         n = x.size(0) if num_nodes is None else num_nodes
         row, col = edge_index[0], edge_index[1]
         xf = x.float()
-        agg = torch.zeros(n, xf.size(1), device=x.device).index_add_(0, row, xf[col])
+        agg = spmm(xf, row, col, None, n)
         if self.agg_type == "mean":
             deg = torch.zeros(n, device=x.device).scatter_add(0, row, torch.ones(row.numel(), device=x.device))
             agg = agg / deg.clamp(min=1)[:, None]
@@ -88,6 +90,6 @@ class GATConv(nn.Module):
         a = segment_softmax(e, row, n)
         if self.training and self.attn_drop > 0:
             a = F.dropout(a, self.attn_drop)
-        out = torch.zeros(n, self.H, self.D, device=x.device).index_add_(0, row, h[col] * a.unsqueeze(-1))
+        out = spmm(h.reshape(-1, self.H * self.D), row, col, a, n, heads=self.H).view(n, self.H, self.D)
         out = out.reshape(n, self.H * self.D) if self.concat else out.mean(1)
         return out + self.bias if self.bias is not None else out

@@ -22,9 +22,11 @@ from . import sampling as S
 
 
 def unique_relabel(ids: torch.Tensor):
-    """sorted unique ids + position of every input id (the K4 dedup/relabel primitive)."""
-    uniq, inv = torch.unique(ids.reshape(-1), return_inverse=True)
-    return uniq, inv.reshape(ids.shape)
+    """unique ids in first-occurrence order + compact index of every input id (K4 dedup/relabel; device hash
+    table on CUDA, ops/sparse.py:Relabel)."""
+    from .sparse import Relabel
+    r = Relabel(ids)
+    return r.uniq, r.inverse
 
 
 def _bfs(n: int, row: torch.Tensor, col: torch.Tensor, start: int, removed: int, max_iters: int = 64):
@@ -62,22 +64,19 @@ def induce_subgraph(store, etype: str, seeds: torch.Tensor, num_nbrs: List[int],
         all_nodes.append(frontier)
     cat = torch.cat(all_nodes)
     cat = cat[cat >= 0]
+    from .sparse import Relabel
     if need_dist and src is not None and dst is not None and src.numel() == 1:
-        # SEAL: src is node 0, dst is node 1, the rest sorted
-        s0, d0 = src.reshape(-1)[:1], dst.reshape(-1)[:1]
-        rest = torch.unique(cat)
-        rest = rest[(rest != s0) & (rest != d0)]
-        nodes = torch.cat([s0, d0, rest])
-    else:
-        nodes = torch.unique(cat)
+        # SEAL: src is node 0, dst is node 1 (first-occurrence order puts them first)
+        cat = torch.cat([src.reshape(-1)[:1], dst.reshape(-1)[:1], cat])
+    rl = Relabel(cat)          # K4: device hash table, unique ids in first-occurrence order (seeds first)
+    nodes = rl.uniq
     n = int(nodes.numel())
     vals, eids, offs = S.sample_full(csr, nodes, cap=cfg.default_full_nbr_num, want_eids=True)
     counts = offs[1:] - offs[:-1]
     rows = torch.repeat_interleave(torch.arange(n, device=dev), counts)
-    snodes, sperm = torch.sort(nodes)
-    pos = torch.searchsorted(snodes, vals).clamp_(max=max(n - 1, 0))
-    hit = (snodes[pos] == vals) if n > 0 else torch.zeros(0, dtype=torch.bool, device=dev)
-    r, c, e = rows[hit], sperm[pos[hit]], eids[hit]
+    cidx = rl.lookup(vals)     # membership test + local index in one table probe
+    hit = cidx >= 0
+    r, c, e = rows[hit], cidx[hit], eids[hit]
     row = torch.cat([r, c])
     col = torch.cat([c, r])
     eid = torch.cat([e, e])

@@ -249,3 +249,17 @@ def test_pyg_style_loader_and_cluster_helpers(tmp_path):
     b = batches[0]
     assert b.num_graphs == 5 and b.x.shape == (20, 4) and b.edge_index.shape == (2, 15)
     assert b.edge_index[:, 3:6].tolist() == [[4, 4, 4], [5, 6, 7]] and b.batch.tolist() == sum([[i] * 4 for i in range(5)], [])
+
+
+def test_relabel_and_spmm_portable():
+    from graphlearn_b200.ops.sparse import Relabel, spmm
+    ids = torch.tensor([[7, 3, 7], [-1, 9, 3]])
+    r = Relabel(ids)
+    assert r.uniq.tolist() == [7, 3, 9] and r.inverse.tolist() == [[0, 1, 0], [-1, 2, 1]]
+    assert r.lookup(torch.tensor([9, 4, 7, -1])).tolist() == [2, -1, 0, -1]
+    x = torch.randn(5, 6, requires_grad=True)
+    row, col = torch.tensor([0, 0, 2, 4]), torch.tensor([1, 3, 3, 0])
+    w = torch.rand(4, 2, requires_grad=True)
+    out = spmm(x, row, col, w, 5, heads=2)
+    ref = torch.zeros(5, 2, 3).index_add_(0, row, x[col].view(-1, 2, 3) * w[:, :, None]).reshape(5, 6)
+    assert torch.allclose(out, ref)
