@@ -86,7 +86,9 @@ class FastSageTrainer:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._post_loss_hook = None
         self._sides = (torch.cuda.Stream(), torch.cuda.Stream())
+        self._side_c = torch.cuda.Stream()
         self._ev_pack = torch.cuda.Event()
+        self._ev_zero = torch.cuda.Event()
         self.use_graph = bool(use_cuda_graph)
         self._steps = 0
         self.h_seeds = torch.zeros(self.B, dtype=torch.int64).pin_memory()
@@ -126,35 +128,64 @@ class FastSageTrainer:
         return hops
 
     # ------------------------------------------------------------------ the step
-    def _step_body(self):
+    def _step_body(self, pipe=None):
         """One training step as a small DAG of launches.  Independent work runs on forked streams (graph
         branches under capture) so that kernel-boundary latencies overlap instead of adding up:
-            side B : zero grads, pack W_1..W_L (bf16 SW128 images)      || sampling (main)
-            side B : rng / optimiser step counters (after sampling)     || forward
+            side B : zero grads || side C : pack W_2..W_L || main : pack W_1 (bf16 SW128 images)
+            sampling: on main (plain schedule) or, under graph capture, the NEXT batch on its own branch
+            side B / sampling branch : rng + optimiser step counters (after the sampling kernels)
             side A : layer-l segment 0                                  || segments >= 1 (main)
             side A : dW_l GEMM                                          || dA_l GEMM + input-gradient kernels (main)
         everything joins before the gradient all-reduce + Adam."""
         C, L = self.C, self.L
         main = torch.cuda.current_stream()
         sA, sB = self._sides
-        # ---- fork B: gradient zeroing + weight packing do not depend on the sampled batch
+        # ---- head: gradient zeroing (side B) || pack W_1 (main) || pack W_2.. (side C); layer 1 only waits
+        # for its own weight image
+        sC = self._side_c
         sB.wait_stream(main)
-        packs = []
+        sC.wait_stream(main)
         with torch.cuda.stream(sB):
             self.g_store.zero_()
-            for l in range(1, L + 1):
+            self._ev_zero.record(sB)
+        packs = [None] * L
+        with torch.cuda.stream(sC):
+            for l in range(2, L + 1):
                 c = self.convs[l - 1]
-                packs.append(C.pack_weight_f32(c.weight_p.detach(), sage_ops.pad_n(c.out_dim), l > 1))
-            self._ev_pack.record(sB)
-        hops = self.sample(self.seeds)
-        # counters advance once the sampling kernels have consumed the RNG offset; needed again only by Adam
-        sB.wait_stream(main)
-        with torch.cuda.stream(sB):
-            self.opt.advance(self.rng.state)
-        main.wait_event(self._ev_pack)
+                packs[l - 1] = C.pack_weight_f32(c.weight_p.detach(), sage_ops.pad_n(c.out_dim), True)
+            self._ev_pack.record(sC)
+        packs[0] = C.pack_weight_f32(self.convs[0].weight_p.detach(), sage_ops.pad_n(self.convs[0].out_dim), False)
+        if pipe is None:
+            # plain schedule: sample this step's batch, then train on it
+            seeds = self.seeds
+            hops = self.sample(seeds)
+            # counters advance once the sampling kernels have consumed the RNG offset; needed again only by Adam
+            sB.wait_stream(main)
+            with torch.cuda.stream(sB):
+                self.opt.advance(self.rng.state)
+        else:
+            # pipelined schedule (graph capture): train on the batch sampled by the PREVIOUS replay while a
+            # forked branch stages + samples the NEXT batch (the reference's sampling || training pipeline:
+            # dag_scheduler.cc:51-62 / dag_dataset.cc:38-43, here inside one CUDA graph)
+            cur, nxt, host_slot = pipe
+            hops = self._hops[cur]
+            seeds = hops[0]
+            sS = self._sample_stream
+            sS.wait_stream(main)
+            with torch.cuda.stream(sS):
+                if host_slot is not None:
+                    # zero-copy staging: a tiny copy KERNEL reads the UVA-mapped pinned buffer over PCIe
+                    self._hops[nxt][0].copy_(self._h_seeds_dev[host_slot])
+                nb = self._hops[nxt][0]
+                for i, k in enumerate(self.fanouts):
+                    out, _ = S.sample_neighbors(self.csr, nb, k, self.strategy, want_eids=False, rng=self.rng, salt=i + 1)
+                    self._hops[nxt][i + 1].copy_(out.reshape(-1))
+                    nb = self._hops[nxt][i + 1]
+                self.opt.advance(self.rng.state)
         # ---- forward
-        w16 = [p[1] for p in packs]
         for l in range(1, L + 1):
+            if l == 2:
+                main.wait_event(self._ev_pack)
             c = self.convs[l - 1]
             last = l == L
             N = sage_ops.pad_n(c.out_dim)
@@ -182,9 +213,10 @@ class FastSageTrainer:
                                              self.gather_mode)
             if nseg > 1:
                 main.wait_stream(sA)
-        # ---- loss (seeds are owned locally: labels are a local lookup)
+        # ---- loss (seeds are owned locally: labels are a local lookup); first writer of the gradient storage
+        main.wait_event(self._ev_zero)
         top = self.convs[L - 1]
-        C.softmax_ce(self.H[L - 1], self.nodes.labels.local, self.seeds, self.rt.world, self.loss, self.dZ[L - 1],
+        C.softmax_ce(self.H[L - 1], self.nodes.labels.local, seeds, self.rt.world, self.loss, self.dZ[L - 1],
                      top.bias.grad if top.bias is not None else None)
         if self._post_loss_hook is not None:
             self._post_loss_hook()          # e2e graph capture: fork the loss D2H here, parallel to the backward
@@ -199,22 +231,29 @@ class FastSageTrainer:
             with torch.cuda.stream(sA):
                 self._mm_into(c.weight_p.grad, dz.t(), a)                # dW_l = dZ^T A
             da = self.dA[l - 1]
-            torch.mm(dz, w16[l - 1], out=da)                             # dA_l = dZ W_l
+            torch.mm(dz, packs[l - 1][1], out=da)                        # dA_l = dZ W_l
             prev = self.convs[l - 2]
             kp_self, _ = sage_ops.padded_dims(c.in_self, c.in_nbr, c.agg_type)
             offs, po = self.seg_off[l - 1], self.seg_off[l - 2]
             nseg_prev = L - l + 2
+            sC = self._side_c
+            sC.wait_stream(main)               # the (small) seed segment runs beside the big ones
             for s in range(nseg_prev):
                 rows = slice(po[s], po[s + 1])
                 da_self = da[offs[s]:offs[s + 1]] if s <= L - l else None
                 da_nbr = da[offs[s - 1]:offs[s]] if s >= 1 else None
                 k = self.fanouts[s - 1] if s >= 1 else 1
                 scale = (1.0 / k) if c.agg_type == "mean" else 1.0
-                C.sage_bwd_input(da_self, da_nbr, kp_self, k, scale, self.H[l - 2][rows], self.dZ[l - 2][rows],
-                                 prev.bias.grad if prev.bias is not None else None)
+                with torch.cuda.stream(sC if s == 0 else main):
+                    C.sage_bwd_input(da_self, da_nbr, kp_self, k, scale, self.H[l - 2][rows], self.dZ[l - 2][rows],
+                                     prev.bias.grad if prev.bias is not None else None)
+            main.wait_stream(sC)
         # ---- join, gradient all-reduce + optimiser
         main.wait_stream(sA)
         main.wait_stream(sB)
+        main.wait_stream(sC)
+        if pipe is not None:
+            main.wait_stream(self._sample_stream)
         self.ar(self.flat_g, average=True)
         self.opt.apply()
 
@@ -233,46 +272,57 @@ class FastSageTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.rt.barrier()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._step_body()
-        self.graph = g
-        # (b) two end-to-end graphs, software pipelined so that no PCIe round trip sits on the critical
-        # path (tools/diag_e2e.py: the two host-memory accesses cost 18 us when serialised with the step):
-        #   branch 1  the training step on the seed batch already resident in seeds buffer i
-        #   branch 2  prefetch of the NEXT step's seeds, pinned host staging slot i^1 -> seeds buffer i^1
-        #   branch 3  (forked right after the loss kernel) loss -> pinned host slot i, overlapping the backward
-        self._seeds_bufs = [self.seeds, torch.zeros_like(self.seeds)]
-        self._e2e_graphs = []
-        side_in, side_out = torch.cuda.Stream(), torch.cuda.Stream()
-        for i in range(2):
-            gi = torch.cuda.CUDAGraph()
-            self.seeds = self._seeds_bufs[i]
-            with torch.cuda.graph(gi, pool=g.pool()):
-                main = torch.cuda.current_stream()
-                side_in.wait_stream(main)
-                with torch.cuda.stream(side_in):
-                    # zero-copy staging: a tiny copy KERNEL reads the UVA-mapped pinned buffer over PCIe
-                    self._seeds_bufs[i ^ 1].copy_(self._h_seeds_dev[i ^ 1])
-
-                def hook(i=i):
-                    side_out.wait_stream(main)
-                    with torch.cuda.stream(side_out):
-                        self._h_loss_dev[i].copy_(self.loss)
-                self._post_loss_hook = hook
-                self._step_body()
-                self._post_loss_hook = None
-                main.wait_stream(side_in)
-                main.wait_stream(side_out)
-            self._e2e_graphs.append(gi)
-        self.seeds = self._seeds_bufs[0]
+        # Four graphs over one memory pool, all software pipelined: graph i trains on hop buffers i and
+        # samples the next batch into hop buffers i^1 on a forked branch.
+        #   device-only pair : next seeds = whatever hop buffer i^1 holds (re-sampled with a fresh RNG offset)
+        #   end-to-end pair  : + next seeds copied from pinned host slot i^1 at the head of the sampling branch
+        #                      + loss -> pinned host slot i forked right after the loss kernel
+        # No PCIe round trip and no sampling kernel sits on the critical path (tools/diag_e2e.py).
+        self._sample_stream = torch.cuda.Stream()
+        self._hops = [[torch.zeros(n, dtype=torch.int64, device=self.rt.device) for n in self.n] for _ in range(2)]
+        self._hops[0][0] = self.seeds                      # `tr.seeds` stays the handle of buffer 0
+        self._seeds_bufs = [self._hops[0][0], self._hops[1][0]]
+        self._prime_hops(self.seeds)
+        self._dev_graphs, self._e2e_graphs = [], []
+        side_out = torch.cuda.Stream()
+        pool = None
+        for e2e in (False, True):
+            for i in range(2):
+                gi = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gi, pool=pool):
+                    main = torch.cuda.current_stream()
+                    if e2e:
+                        def hook(i=i, main=main):
+                            side_out.wait_stream(main)
+                            with torch.cuda.stream(side_out):
+                                self._h_loss_dev[i].copy_(self.loss)
+                        self._post_loss_hook = hook
+                    self._step_body(pipe=(i, i ^ 1, (i ^ 1) if e2e else None))
+                    self._post_loss_hook = None
+                    if e2e:
+                        main.wait_stream(side_out)
+                pool = gi.pool() if pool is None else pool
+                (self._e2e_graphs if e2e else self._dev_graphs).append(gi)
+        self.graph = self._dev_graphs[0]
         self._primed = False
         torch.cuda.synchronize()
         self.rt.barrier()
 
+    def _prime_hops(self, seeds: torch.Tensor):
+        """Fill BOTH hop buffers with a sample of `seeds` so that whichever graph replays first finds a batch."""
+        hops = self.sample(seeds)
+        for j in range(2):
+            for dst, src in zip(self._hops[j], hops):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
+
     def step_device(self):
+        """Device-only step (no host traffic): graph replay on the resident seed buffers."""
         if self.graph is not None:
-            self.graph.replay()
+            if not self._primed:
+                self._prime_hops(self._hops[self._steps & 1][0])
+                self._primed = True
+            self._dev_graphs[self._steps & 1].replay()
         else:
             self._step_body()
         self._steps += 1
@@ -287,7 +337,7 @@ class FastSageTrainer:
             # receives that step's loss.  The very first call also places its batch on the device directly.
             i = self._steps & 1
             if not self._primed:
-                self._seeds_bufs[i].copy_(seed_ids_host)
+                self._prime_hops(seed_ids_host.to(self.rt.device))
                 self._primed = True
             self._e2e_done[i].synchronize()    # step t-2 (same graph) was the last reader of staging slot i^1
             self._h_seeds2[i ^ 1].copy_(seed_ids_host)
