@@ -204,15 +204,33 @@ class NodeTable:
         st.cache_map, st.cache_rows = cmap, rows
         rt.barrier()
         if rt.is_cuda:
-            self.feat_desc = make_table_desc(W, self.float_dim, stride, st.local.dtype, st.nrows, st.ptrs,
-                                             cache=(rt.rank, cmap.data_ptr(), rows.data_ptr()))
+            if C == n_remote:
+                # FULL replica: `sel` is sorted by vid, so the rows of owner r form the strided subsequence
+                # vid % W == r in row order.  Regroup them per owner and point the descriptor's peer slot r
+                # at the local copy: kernels then run the plain local path (no map lookup at all).
+                owner = sel % W
+                ptrs, keep = list(st.ptrs), []
+                for r in range(W):
+                    if r == rt.rank:
+                        continue
+                    rep = rows[owner == r].contiguous()          # [nrows[r], stride], row order == owner's
+                    assert rep.size(0) == int(self.nrows[r])
+                    keep.append(rep)
+                    ptrs[r] = rep.data_ptr()
+                st.replicas = keep
+                st.cache_map = st.cache_rows = None       # the regrouped copies replace the slot table
+                self.feat_desc = make_table_desc(W, self.float_dim, stride, st.local.dtype, st.nrows, ptrs)
+            else:
+                self.feat_desc = make_table_desc(W, self.float_dim, stride, st.local.dtype, st.nrows, st.ptrs,
+                                                 cache=(rt.rank, cmap.data_ptr(), rows.data_ptr()))
         return C
 
     def drop_feature_cache(self):
         st = self.feats
-        if st is None or getattr(st, "cache_map", None) is None:
+        if st is None or (getattr(st, "cache_map", None) is None and getattr(st, "replicas", None) is None):
             return
         st.cache_map = st.cache_rows = None
+        st.replicas = None
         if self.rt.is_cuda:
             self.feat_desc = make_table_desc(self.rt.world, self.float_dim, int(st.local.size(1)), st.local.dtype,
                                              st.nrows, st.ptrs)

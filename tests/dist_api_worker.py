@@ -81,8 +81,12 @@ def main():
         assert np.allclose(it2.float_attrs, it.float_attrs)
         nodes2 = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
         assert np.allclose(nodes2.embedding_agg("mean"), nodes.float_attrs.mean(1), atol=1e-5)
-        cm = g._store.nodes["item"].feats.cache_map
-        assert int((cm >= 0).sum()) == got["item"] and all(int(v) % W != r for v in torch.nonzero(cm >= 0).flatten())
+        feats = g._store.nodes["item"].feats
+        cm = feats.cache_map
+        if cm is None:      # CUDA full replica: per-owner local copies instead of a slot table
+            assert sum(t.size(0) for t in feats.replicas) == got["item"]
+        else:
+            assert int((cm >= 0).sum()) == got["item"] and all(int(v) % W != r for v in torch.nonzero(cm >= 0).flatten())
     rt.barrier()
     if r == 0:
         print("DIST_API_OK world=%d device=%s" % (W, rt.device))

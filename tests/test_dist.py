@@ -58,7 +58,8 @@ def test_two_ranks_gpu_peer():
 def test_two_ranks_gpu_peer_feature_cache():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    _run(2, 29645, {"GLB_TEST_CACHE": "1000"})
+    _run(2, 29645, {"GLB_TEST_CACHE": "1000"})           # partial cache: vid -> slot map inside the kernels
+    _run(2, 29646, {"GLB_TEST_CACHE": "100000"})         # full replica: peer slots point at local copies
 
 
 @pytest.mark.gpu
