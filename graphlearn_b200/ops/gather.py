@@ -66,19 +66,18 @@ def gather_any(rt: Runtime, st: SymmTensor, vids: torch.Tensor, fill) -> torch.T
         width = 1 if loc.dim() == 1 else int(loc.size(1))
         f32_per = 2 if loc.dtype == torch.int64 else 1
         dimf = width * f32_per
-        if dimf % 4 == 0 or True:
-            # stride (in fp32 elements) must keep rows 16-byte aligned for the vector path
-            if (dimf % 4) == 0:
-                desc = make_table_desc(rt.world, dimf, dimf, torch.float32, st.nrows, st.ptrs)
-                out = native().gather_rows(desc, v, False, 0.0)
-                res = out.view(loc.dtype).reshape((v.numel(),) + tuple(loc.shape[1:]))
-                if fill != 0:
-                    W = rt.world
-                    nrows = torch.tensor(st.nrows, device=v.device)
-                    ok = (v >= 0) & (torch.div(v, W, rounding_mode="floor") < nrows[v.clamp(min=0) % W])
-                    okb = ok.view(-1, *([1] * (res.dim() - 1)))
-                    res = torch.where(okb, res, torch.full_like(res, fill))
-                return res
+        # stride (in fp32 elements) must keep rows 16-byte aligned for the vector path
+        if (dimf % 4) == 0:
+            desc = make_table_desc(rt.world, dimf, dimf, torch.float32, st.nrows, st.ptrs)
+            out = native().gather_rows(desc, v, False, 0.0)
+            res = out.view(loc.dtype).reshape((v.numel(),) + tuple(loc.shape[1:]))
+            if fill != 0:
+                W = rt.world
+                nrows = torch.tensor(st.nrows, device=v.device)
+                ok = (v >= 0) & (torch.div(v, W, rounding_mode="floor") < nrows[v.clamp(min=0) % W])
+                okb = ok.view(-1, *([1] * (res.dim() - 1)))
+                res = torch.where(okb, res, torch.full_like(res, fill))
+            return res
     (rows,) = part.remote_apply(v, lambda x: (_local_rows(st, x, rt.world, fill),), rt.world)
     return rows
 

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Race / memory checking of the hand-written kernels (the reference has no sanitizer jobs at all).
+# Run on a GPU box:   gpurun --timeout 1500 -- 'bash tools/sanitize.sh memcheck'   (or racecheck / synccheck / initcheck)
+# The kernel tests are small enough for compute-sanitizer's ~50x slowdown; the CUDA-graph engine tests are
+# excluded (graph capture is not supported under the sanitizer) - their kernels are covered eagerly by
+# test_fast_engine_matches_autograd.
+tool=${1:-memcheck}
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 1400 compute-sanitizer --tool "$tool" --error-exitcode 3 --log-file gpurun_out/sanitizer_$tool.log \
+  python -m pytest tests/test_gpu_kernels.py -m gpu -x -q \
+  -k "not cuda_graph and not learns and not pipeline" > gpurun_out/sanitizer_$tool.pytest.log 2>&1
+echo "exit $?"
+tail -5 gpurun_out/sanitizer_$tool.log
+tail -3 gpurun_out/sanitizer_$tool.pytest.log
