@@ -40,6 +40,7 @@ class Config:
     tape_capacity: int = 10
     storage_mode: int = 2
     local_node_cache_capacity: int = 0
+    actor_local_shard_count: int = 1
     sliced_load: bool = True          # each rank parses 1/world of a file, rows are shuffled to owners
     knn_metric: int = 0          # 0 = L2, 1 = inner product
     field_delimiter: str = "\t"
@@ -130,6 +131,18 @@ set_loader_threads = _setter("loader_threads", int)
 set_use_peer_kernels = _setter("use_peer_kernels", bool)
 set_seed = _setter("seed", int)
 set_sage_gather_mode = _setter("sage_gather_mode", int)
+
+
+# exact reference spellings (graphlearn/python/config.py:77,114,118)
+set_datainit_batchsize = set_data_init_batch_size
+set_sampler_retry_times = set_sampling_retry_times
+
+
+def set_actor_local_shard_count(count):
+    """Actor engine knob (per-core shards of the hiactor runtime); accepted for script parity - the SM grid is
+    the sharded executor here, there is nothing to size."""
+    assert isinstance(count, int) and count > 0
+    _CFG.actor_local_shard_count = int(count)
 
 
 def set_inner_threadnum(n):

@@ -23,6 +23,23 @@ class MultivalSpec(object):
         self.delimiter = delimiter
 
 
+class DynamicSparseSpec(object):
+    """Embedding column without a fixed bucket count (PAI-TF dynamic embedding in the reference,
+    feature_spec.py); accepted for script parity, ``nn.FeatureEncoder`` needs a bucket size."""
+
+    def __init__(self, dimension, need_hash=True):
+        self.bucket_size = None
+        self.dimension = dimension
+        self.need_hash = need_hash
+
+
+class DynamicMultivalSpec(object):
+    def __init__(self, dimension, delimiter=","):
+        self.bucket_size = None
+        self.dimension = dimension
+        self.delimiter = delimiter
+
+
 class FeatureSpec(object):
     def __init__(self, size, weighted=False, labeled=False, timestamped=False):
         self.size = size

@@ -1,2 +1,2 @@
 """Edge traversal sampler (graphlearn/python/sampler/edge_sampler.py)."""
-from .node_sampler import EdgeSampler  # noqa: F401
+from .node_sampler import ByOrderEdgeSampler, EdgeSampler, RandomEdgeSampler, ShuffleEdgeSampler  # noqa: F401

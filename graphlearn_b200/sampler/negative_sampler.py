@@ -59,3 +59,10 @@ class ConditionalNegativeSampler(object):
                                        self._rng.torch_generator(2))
         self._rng.advance(1)
         return V_.Nodes(g.to_ids(csr.dst_type, neg), csr.dst_type, shape=(int(s.numel()), self._k), graph=g, vids=neg)
+
+
+from .neighbor_sampler import _fixed_strategy  # noqa: E402
+
+RandomNegativeSampler = _fixed_strategy(NegativeSampler, "random", "RandomNegativeSampler")
+InDegreeNegativeSampler = _fixed_strategy(NegativeSampler, "in_degree", "InDegreeNegativeSampler")
+NodeWeightNegativeSampler = _fixed_strategy(NegativeSampler, "node_weight", "NodeWeightNegativeSampler")

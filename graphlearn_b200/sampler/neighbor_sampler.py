@@ -83,3 +83,20 @@ class FullNeighborSampler(NeighborSampler):
             layers.append_layer(V_.Layer(nodes, edges, shape=(B, maxd)))
             cur_ids, cur_v = nbr_ids, vals
         return layers
+
+
+def _fixed_strategy(base, strategy, doc):
+    """Named strategy subclasses of the reference (neighbor_sampler.py:143-163 etc.): same constructor minus
+    the ``strategy`` argument."""
+    def __init__(self, graph, *args, **kwargs):
+        kwargs.pop("strategy", None)
+        base.__init__(self, graph, *args, strategy=strategy, **kwargs)
+    return type(doc, (base,), {"__init__": __init__, "__doc__": "%s fixed to strategy %r." % (base.__name__, strategy)})
+
+
+RandomNeighborSampler = _fixed_strategy(NeighborSampler, "random", "RandomNeighborSampler")
+RandomWithoutReplacementNeighborSampler = _fixed_strategy(NeighborSampler, "random_without_replacement",
+                                                          "RandomWithoutReplacementNeighborSampler")
+EdgeWeightNeighborSampler = _fixed_strategy(NeighborSampler, "edge_weight", "EdgeWeightNeighborSampler")
+TopkNeighborSampler = _fixed_strategy(NeighborSampler, "topk", "TopkNeighborSampler")
+InDegreeNeighborSampler = _fixed_strategy(NeighborSampler, "in_degree", "InDegreeNeighborSampler")

@@ -77,3 +77,13 @@ class EdgeSampler(object):
     @property
     def epoch(self):
         return self._it.epoch
+
+
+from .neighbor_sampler import _fixed_strategy  # noqa: E402
+
+RandomNodeSampler = _fixed_strategy(NodeSampler, "random", "RandomNodeSampler")
+ByOrderNodeSampler = _fixed_strategy(NodeSampler, "by_order", "ByOrderNodeSampler")
+ShuffleNodeSampler = _fixed_strategy(NodeSampler, "shuffle", "ShuffleNodeSampler")
+RandomEdgeSampler = _fixed_strategy(EdgeSampler, "random", "RandomEdgeSampler")
+ByOrderEdgeSampler = _fixed_strategy(EdgeSampler, "by_order", "ByOrderEdgeSampler")
+ShuffleEdgeSampler = _fixed_strategy(EdgeSampler, "shuffle", "ShuffleEdgeSampler")

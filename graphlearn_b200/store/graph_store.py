@@ -31,8 +31,26 @@ from .shards import CsrShard, IdMap, NodeTable
 ORIGIN, REVERSED = 0, 1
 
 
+class EdgeInfo(object):
+    def __init__(self, src_type, dst_type):
+        self.src_type, self.dst_type = src_type, dst_type
+
+
 class Topology(object):
     """edge type -> (src type, dst type)  (graphlearn/python/data/topology.py)."""
+
+    def get_edge_info(self, edge_type):
+        if edge_type not in self._edges:
+            raise ValueError("edge_type {} not exists in the graph.".format(edge_type))
+        return EdgeInfo(*self._edges[edge_type])
+
+    def print_all(self):
+        for k, (s, d) in self._edges.items():
+            print("edge_type:{}, src_type:{}, dst_type:{}\n".format(k, s, d))
+
+    def print_one(self, edge_type):
+        e = self.get_edge_info(edge_type)
+        print("edge_type:{}, src_type:{}, dst_type:{}\n".format(edge_type, e.src_type, e.dst_type))
 
     def __init__(self):
         self._edges: Dict[str, Tuple[str, str]] = {}
