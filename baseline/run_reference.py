@@ -19,6 +19,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
 
 
+def _scratch_cwd():
+    d = os.path.join(os.environ.get("TMPDIR", "/tmp"), "glb_ref_logs")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
 def main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -67,7 +73,8 @@ def main(args):
     hosts = ",".join("127.0.0.1:%d" % (base_port + r) for r in range(world)) if world > 1 else ""
     child = subprocess.Popen(common + ["--rank", str(rank), "--world", str(world), "--tracker", tracker,
                                        "--hosts", hosts],
-                             stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1, env=env)
+                             stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1, env=env,
+                             cwd=_scratch_cwd())       # the reference writes its glog files into the cwd
     line = ""
     while not line.startswith("SHM"):
         line = child.stdout.readline()

@@ -63,7 +63,7 @@ class Config:
     server_hosts: str = ""
     # --- B200 engine specific
     feature_dtype: str = "fp32"          # fp32 | bf16   storage dtype of float attribute tables in HBM
-    loader_threads: int = max(1, (os.cpu_count() or 8) // 2)
+    loader_threads: int = 0           # 0 = auto: all cores divided by the number of ranks on the box
     use_peer_kernels: bool = True        # False -> torch.distributed (NCCL/gloo) baseline path
     sage_gather_mode: int = int(os.environ.get("GLB_SAGE_GATHER_MODE", "0"))   # fused SAGE kernel: 0 auto, 1 register loads, 2 TMA ring
     seed: int = 0

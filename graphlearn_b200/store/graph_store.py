@@ -97,6 +97,11 @@ def _expand_paths(path: str) -> List[str]:
     return out
 
 
+def _loader_threads(ranks_on_box: int) -> int:
+    n = int(_config.get().loader_threads)
+    return n if n > 0 else max(1, (os.cpu_count() or 8) // max(int(ranks_on_box), 1))
+
+
 def _load_source(src: Source, part_index: int = 0, part_count: int = 1) -> Dict[str, object]:
     """-> dict(a, b, w, label, ts, ia, fa, strs) of CPU tensors.
 
@@ -127,7 +132,7 @@ def _load_source(src: Source, part_index: int = 0, part_count: int = 1) -> Dict[
         else:
             pi, pc = part_index, part_count
         parts.append(C.load_table(p, src.kind == "edge", dec.weighted, dec.labeled, dec.timestamped, codes, buckets,
-                                  dec.attr_delimiter, cfg.field_delimiter, int(cfg.loader_threads), pi, pc))
+                                  dec.attr_delimiter, cfg.field_delimiter, _loader_threads(part_count), pi, pc))
     if not parts:       # more ranks than files: this rank contributes an empty slice
         parts.append(C.load_table(paths[0], src.kind == "edge", dec.weighted, dec.labeled, dec.timestamped, codes,
                                   buckets, dec.attr_delimiter, cfg.field_delimiter, 1, 0, 1))
@@ -211,8 +216,9 @@ class GraphStore(object):
         for s in edge_sources:
             st, dt, et = s.types
             dk, own_dst = load_owned(s, "a")
-            ends.setdefault(dt, []).append(own_dst)
-            ends.setdefault(st, []).append(dk["a"])
+            # endpoint id sets: edge files are usually grouped by src, so collapse runs before the real unique
+            ends.setdefault(dt, []).append(torch.unique_consecutive(own_dst))
+            ends.setdefault(st, []).append(torch.unique_consecutive(dk["a"]))
             ed.setdefault(et, []).append(dk)
             self.topology.add(et, st, dt)
         # ---- node tables

@@ -306,7 +306,12 @@ class CsrShard:
                 order = torch.argsort(ts, stable=True)
             elif weights is not None:
                 order = torch.argsort(weights, descending=True, stable=True)
-            order = order[torch.argsort(src_rows[order], stable=True)]
+            elif bool((src_rows[1:] >= src_rows[:-1]).all()):
+                order = None                      # already grouped by source row (the common file layout)
+            if order is None:
+                order = torch.arange(E, device=dev)
+            else:
+                order = order[torch.argsort(src_rows[order], stable=True)]
         srt = src_rows[order]
         counts = torch.bincount(srt, minlength=n_src_rows) if E > 0 else torch.zeros(n_src_rows, dtype=torch.int64, device=dev)
         indptr = torch.zeros(n_src_rows + 1, dtype=torch.int64, device=dev)
