@@ -17,7 +17,7 @@ def main():
     g = gl.Graph()
     g.node(os.path.join(d, "user.tsv"), "user",
            decoder=gl.Decoder(weighted=True, labeled=True, attr_types=["int", "int", ("string", 16), "float"]))
-    g.node(os.path.join(d, "item.tsv"), "item", decoder=gl.Decoder(attr_types=["float"] * 4))
+    g.node(os.path.join(d, "item_parts"), "item", decoder=gl.Decoder(attr_types=["float"] * 4))   # directory source
     g.edge(os.path.join(d, "u2i.tsv"), ("user", "item", "buy"), decoder=gl.Decoder(weighted=True))
     g.edge(os.path.join(d, "i2i.tsv"), ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
     g.init(device=dev)

@@ -29,6 +29,13 @@ def write_graph(d):
         f.write("id:int64\tfeature:string\n")
         for i in range(N_ITEM):
             f.write("%d\t%s\n" % (i, ":".join("%f" % item_float(i, j) for j in range(4))))
+    # the same item table again as a DIRECTORY of 3 part files (dealt round-robin to the ranks, N10)
+    os.makedirs(os.path.join(d, "item_parts"), exist_ok=True)
+    for p in range(3):
+        with open(os.path.join(d, "item_parts", "part-%d" % p), "w") as f:
+            f.write("id:int64\tfeature:string\n")
+            for i in range(p, N_ITEM, 3):
+                f.write("%d\t%s\n" % (i, ":".join("%f" % item_float(i, j) for j in range(4))))
     with open(os.path.join(d, "u2i.tsv"), "w") as f:
         f.write("src_id:int64\tdst_id:int64\tweight:float\n")
         for u in range(N_USER):

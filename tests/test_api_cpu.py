@@ -304,3 +304,13 @@ def test_node_view_splits(tmp_path):
     all_ids = sum(got.values(), [])
     assert sorted(all_ids) == list(range(fx.N_ITEM))
     assert len(got[gl.Mask.TRAIN]) > len(got[gl.Mask.TEST]) > 0
+
+
+def test_directory_and_comma_list_sources(tmp_path):
+    """A node source may be a directory of part files or a comma separated list (slice_reader.h:137-157)."""
+    d = fx.write_graph(str(tmp_path))
+    for src in (d + "/item_parts", ",".join(d + "/item_parts/part-%d" % p for p in range(3)), "file://" + d + "/item_parts"):
+        g = gl.Graph().node(src, "item", decoder=gl.Decoder(attr_types=["float"] * 4)).init(device="cpu")
+        n = g.lookup_nodes("item", np.arange(fx.N_ITEM))
+        assert np.allclose(n.float_attrs[:, 1], np.arange(fx.N_ITEM) + 0.25) and g.get_stats()["item"] == [fx.N_ITEM]
+        g.close()
