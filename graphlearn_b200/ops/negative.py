@@ -187,6 +187,7 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
     selected column gets ``prop`` of the k slots, the remainder is filled by the base strategy
     (conditional_negative_sampler.cc:37-156).  True neighbours of src and (unique=True)
     duplicates are avoided on a best-effort basis like the reference."""
+    cfg = _config.get()
     csr = store.edges[etype]
     tab = store.nodes[csr.dst_type]
     rt = store.rt
@@ -206,7 +207,8 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
         def _excluded(cand):
             pos = torch.searchsorted(pos_sorted, cand.reshape(-1)).clamp_(max=max(pos_sorted.numel() - 1, 0))
             return (pos_sorted[pos] == cand.reshape(-1)).reshape(cand.shape)
-        out = torch.where(_excluded(out), edge_negative(store, etype, src_v, k, base_strategy, gen), out)
+        for _ in range(max(1, int(cfg.neg_sampling_retry_times))):       # strictness is dropped after the retries
+            out = torch.where(_excluded(out), edge_negative(store, etype, src_v, k, base_strategy, gen), out)
     else:
         def _excluded(cand):
             return _is_neighbor(csr, src_v, cand) | (cand == dst_v[:, None])
@@ -240,16 +242,33 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
         # the run of equal values (the reference's AttributeNodesMap)
         order = torch.argsort(local_vals, stable=True)
         sv = local_vals[order]
-        lo = torch.searchsorted(sv, dstv.to(sv.dtype), right=False)
-        hi = torch.searchsorted(sv, dstv.to(sv.dtype), right=True)
+        key = dstv.to(sv.dtype).contiguous()
+        lo = torch.searchsorted(sv, key, right=False)
+        hi = torch.searchsorted(sv, key, right=True)
         span = (hi - lo)
-        u = torch.rand(B, n_slots, device=dev, generator=gen)
-        pick = lo[:, None] + (u * span[:, None].clamp(min=1).float()).long().clamp_(max=None)
-        pick = torch.minimum(pick, (hi - 1).clamp(min=0)[:, None]).clamp_(min=0, max=max(order.numel() - 1, 0))
-        cand = order[pick] * rt.world + rt.rank if order.numel() else torch.full((B, n_slots), -1, device=dev)
         ok = (span > 0)[:, None].expand(B, n_slots)
-        use = ok & ~_excluded(cand)
-        out[:, slot:slot + n_slots] = torch.where(use, cand, out[:, slot:slot + n_slots])
+        chosen = out[:, slot:slot + n_slots].clone()
+        todo = ok.clone()
+        # redraw excluded candidates for a few rounds before leaving a slot to the base strategy
+        # (the reference's ConditionTable::Sample skips ids of the exclusion set while filling the quota)
+        for _ in range(max(1, int(cfg.neg_sampling_retry_times)) + 1):
+            u = torch.rand(B, n_slots, device=dev, generator=gen)
+            pick = lo[:, None] + (u * span[:, None].clamp(min=1).float()).long()
+            pick = torch.minimum(pick, (hi - 1).clamp(min=0)[:, None]).clamp_(min=0, max=max(order.numel() - 1, 0))
+            cand = order[pick] * rt.world + rt.rank if order.numel() else torch.full((B, n_slots), -1, device=dev)
+            good = todo & ~_excluded(cand)       # `_excluded` is collective on > 1 rank: fixed round count
+            if cond.get("unique"):
+                # a candidate already chosen in another slot of the row is not "good" either
+                dupe = (cand.unsqueeze(2) == chosen.unsqueeze(1)).any(2)
+                good &= ~dupe
+                # and keep only the first of equal candidates inside this round
+                srt, idx = torch.sort(torch.where(good, cand, torch.full_like(cand, -1)), dim=1, stable=True)
+                rep = torch.zeros_like(good)
+                rep[:, 1:] = (srt[:, 1:] == srt[:, :-1]) & (srt[:, 1:] >= 0)
+                good &= ~torch.zeros_like(good).scatter(1, idx, rep)
+            chosen = torch.where(good, cand, chosen)
+            todo &= ~good
+        out[:, slot:slot + n_slots] = chosen
         slot += n_slots
     if cond.get("unique"):
         # replace in-row duplicates by fresh base draws (best effort, one round)

@@ -314,3 +314,89 @@ def test_directory_and_comma_list_sources(tmp_path):
         n = g.lookup_nodes("item", np.arange(fx.N_ITEM))
         assert np.allclose(n.float_attrs[:, 1], np.arange(fx.N_ITEM) + 0.25) and g.get_stats()["item"] == [fx.N_ITEM]
         g.close()
+
+
+def _cat_graph(tmp_path, n_user=30, n_item=60):
+    """users buy items; every item has an int category (i % 4), a float price band and a string brand."""
+    d = str(tmp_path)
+    with open(d + "/u.tsv", "w") as f:
+        f.write("id:int64\n" + "".join("%d\n" % u for u in range(n_user)))
+    with open(d + "/i.tsv", "w") as f:
+        f.write("id:int64\tfeature:string\n")
+        for i in range(n_item):
+            f.write("%d\t%d:%.1f:b%d\n" % (i, i % 4, float(i % 3), i % 5))
+    with open(d + "/b.tsv", "w") as f:
+        f.write("src_id:int64\tdst_id:int64\n")
+        for u in range(n_user):
+            for k in range(3):
+                f.write("%d\t%d\n" % (u, (u * 2 + k * 7) % n_item))
+    g = gl.Graph().node(d + "/u.tsv", "u", decoder=gl.Decoder()) \
+        .node(d + "/i.tsv", "i", decoder=gl.Decoder(attr_types=["int", "float", "string"])) \
+        .edge(d + "/b.tsv", ("u", "i", "buy"), decoder=gl.Decoder()).init(device="cpu")
+    return g
+
+
+def test_conditional_negative_sampler(tmp_path):
+    """O12: negatives share the selected attribute values of the positive dst; true neighbours and the
+    positive itself are excluded; batch_share excludes every positive of the batch; unique de-duplicates."""
+    g = _cat_graph(tmp_path)
+    src = np.arange(30)
+    dst = (src * 2) % 60
+    nbrs = {u: {(u * 2 + k * 7) % 60 for k in range(3)} for u in src}
+    s = g.negative_sampler("buy", 8, "random", conditional=True, int_cols=[0], int_props=[1.0])
+    neg = s.get(src, dst).ids
+    assert neg.shape == (30, 8)
+    assert (neg % 4 == (dst % 4)[:, None]).all()                       # same int category as the positive
+    assert all(not (set(neg[b].tolist()) & nbrs[b]) for b in range(30))
+    s2 = g.negative_sampler("buy", 6, "random", conditional=True, float_cols=[0], float_props=[0.5],
+                            str_cols=[0], str_props=[0.5], unique=True)
+    neg2 = s2.get(src, dst).ids
+    assert (neg2[:, :3] % 3 == (dst % 3)[:, None]).all()               # float column slots
+    assert (neg2[:, 3:] % 5 == (dst % 5)[:, None]).all()               # string column slots
+    s3 = g.negative_sampler("buy", 8, "random", conditional=True, int_cols=[0], int_props=[0.5], batch_share=True)
+    gl.set_neg_sampling_retry_times(8)
+    neg3 = s3.get(src[:6], dst[:6]).ids
+    assert not (set(neg3.reshape(-1).tolist()) & set(dst[:6].tolist()))   # no positive of the whole batch
+
+
+def test_temporal_root_constrains_all_hops_and_in_edges(tmp_path):
+    """Temporal roots: every traversal only sees edges strictly before the root element's timestamp, most recent
+    first (dag_node.py:357-392, filter.cc:68-82); in-edge samples carry the ORIGINAL edge's id / timestamp / attrs."""
+    d = str(tmp_path)
+    n_src, n_dst, T = 6, 5, 60
+    ev = [(t % n_src, 100 + (t * 3) % n_dst, t + 1, float(t)) for t in range(T)]
+    with open(d + "/s.tsv", "w") as f:
+        f.write("id:int64\n" + "".join("%d\n" % i for i in range(n_src)))
+    with open(d + "/d.tsv", "w") as f:
+        f.write("id:int64\n" + "".join("%d\n" % (100 + i) for i in range(n_dst)))
+    with open(d + "/e.tsv", "w") as f:
+        f.write("src_id:int64\tdst_id:int64\ttimestamp:int64\tfeature:string\n")
+        f.write("".join("%d\t%d\t%d\t%.1f\n" % e for e in ev))
+    gl.set_default_neighbor_id(-1)
+    gl.set_padding_mode(gl.REPLICATE)
+    dec = gl.Decoder(timestamped=True, attr_types=["float"])
+    g = gl.Graph().node(d + "/s.tsv", "s", decoder=gl.Decoder()).node(d + "/d.tsv", "d", decoder=gl.Decoder()) \
+        .edge(d + "/e.tsv", ("s", "d", "ev"), decoder=dec, directed=False).init(device="cpu")
+    root = g.E("ev").batch(7).alias("e")
+    root.outV().alias("src").outE("ev").sample(3).by("topk").alias("src_hist")
+    root.inV().alias("dst").inE("ev").sample(3).by("topk").alias("dst_hist")
+    ds = gl.Dataset(root.values())
+    seen = []
+    try:
+        while True:
+            r = ds.next()
+            e, sh, dh = r["e"], r["src_hist"], r["dst_hist"]
+            seen.extend(e.timestamps.tolist())
+            for b in range(len(e.src_ids)):
+                u, v, t = int(e.src_ids[b]), int(e.dst_ids[b]), int(e.timestamps[b])
+                want = [x for x in reversed(ev) if x[0] == u and x[2] < t][:3]
+                got = [(int(sh.dst_ids[b, j]), int(sh.timestamps[b, j]), float(sh.float_attrs[b, j, 0]))
+                       for j in range(3) if sh.dst_ids[b, j] >= 0]
+                assert got == [(x[1], x[2], x[3]) for x in want], (u, t, got, want)
+                wantd = [x for x in reversed(ev) if x[1] == v and x[2] < t][:3]
+                gotd = [(int(dh.dst_ids[b, j]), int(dh.timestamps[b, j]), float(dh.float_attrs[b, j, 0]))
+                        for j in range(3) if dh.dst_ids[b, j] >= 0]
+                assert gotd == [(x[0], x[2], x[3]) for x in wantd], (v, t, gotd, wantd)
+    except gl.OutOfRangeError:
+        pass
+    assert seen == sorted(seen) and len(seen) == T          # edges traversed in insertion (= time) order, once
