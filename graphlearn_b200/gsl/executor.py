@@ -53,17 +53,43 @@ class QueryExecutor(object):
 
     # ------------------------------------------------------------------ plan
     def _toposort(self):
-        order, seen = [], set()
+        """Topological order of the DAG.  Besides its upstream a node may depend on a SIBLING branch:
+        ``filter(alias)`` and ``where(alias, condition)`` read another node's output (the reference wires these
+        as extra DagEdges, dag_node.py:236-304), so edges = upstream + filter target + condition target."""
+        nodes, seen = [], set()
 
-        def visit(n: DagNode):
+        def collect(n: DagNode):
             if id(n) in seen:
                 return
             seen.add(id(n))
-            order.append(n)
+            nodes.append(n)
             for d in n.downstreams:
-                visit(d)
+                collect(d)
 
-        visit(self.dag.root)
+        collect(self.dag.root)
+
+        def deps(n: DagNode):
+            out = [n.upstream] if n.upstream is not None else []
+            if n._filter is not None:
+                out.append(n._filter)
+            if isinstance(n.params.get("dst_node"), DagNode):
+                out.append(n.params["dst_node"])
+            return [d for d in out if id(d) in seen]
+
+        order, done = [], set()
+
+        def visit(n: DagNode, stack=()):
+            if id(n) in done:
+                return
+            if id(n) in stack:
+                raise errors.InvalidArgumentError("cyclic filter / where dependency in the GSL query")
+            for d in deps(n):
+                visit(d, stack + (id(n),))
+            done.add(id(n))
+            order.append(n)
+
+        for n in nodes:
+            visit(n)
         return order
 
     # ------------------------------------------------------------------ roots

@@ -232,10 +232,14 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
             local_vals = torch.as_tensor(codes, device=dev).long()
             dstv = local_vals[torch.div(dst_v, rt.world, rounding_mode="floor").clamp(min=0, max=max(local_vals.numel() - 1, 0))]
         elif kind == "int":
+            if tab.ints is None:
+                raise ValueError("conditional negative sampling: node type %r has no int attributes" % (csr.dst_type,))
             attr_all = tab.ints
             dstv = G.gather_any(rt, attr_all, dst_v, fill=0)[:, c]
             local_vals = attr_all.local[:, c]
         else:
+            if tab.feats is None:
+                raise ValueError("conditional negative sampling: node type %r has no float attributes" % (csr.dst_type,))
             dstv = G.gather_rows(rt, tab.feats, tab.feat_desc, dst_v, tab.float_dim)[:, c]
             local_vals = tab.feats.local[:, c].float()
         # inverted index over the LOCAL shard: sort rows by attribute value, pick uniformly inside

@@ -400,3 +400,17 @@ def test_temporal_root_constrains_all_hops_and_in_edges(tmp_path):
     except gl.OutOfRangeError:
         pass
     assert seen == sorted(seen) and len(seen) == T          # edges traversed in insertion (= time) order, once
+
+
+def test_gsl_where_depends_on_sibling_branch(tmp_path):
+    """`outNeg(...).where(dst_alias, condition)` reads the output of a SIBLING branch: the executor must
+    schedule that branch first (extra DAG edge in the reference, dag_node.py:236-304)."""
+    g = _cat_graph(tmp_path)
+    e = g.E("buy").batch(10).alias("e")
+    s = e.outV().alias("src")                # `src` (and its children) come before `dst` in declaration order
+    e.inV().alias("dst")
+    s.outNeg("buy").sample(5).by("random").where("dst", condition={"int_cols": [0], "int_props": [1.0]}).alias("neg")
+    r = gl.Dataset(e.values()).next()
+    neg, dst = r["neg"].ids, r["dst"].ids
+    assert neg.shape == (10, 5) and (neg % 4 == (dst % 4)[:, None]).all()
+    assert not (neg == dst[:, None]).any()
