@@ -68,6 +68,11 @@ def _node2vec_step(csr, cur, prev, p, q, rng, salt, gen, cfg):
         take = pending & accept
         result = torch.where(take | (pending & (t == 63)), cand, result)
         pending = pending & ~accept
-        if not bool(pending.any()):
+        # every rank must run the same number of (collective) proposal rounds
+        more = pending.any().to(torch.int32).reshape(1)
+        if csr.rt.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if int(more.item()) == 0:
             break
     return result

@@ -72,6 +72,25 @@ def main():
         assert not (set(row.tolist()) & {x[0] for x in adj[u]})
     nodes = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
     assert np.allclose(nodes.embedding_agg("mean"), nodes.float_attrs.mean(1), atol=1e-5)
+    # ---- ops whose portable path loops a data-dependent number of collective rounds (lock-step across ranks)
+    w = gl.Dataset(g.V("item").batch(5).alias("s").random_walk("sim", 4, p=0.5, q=2.0).alias("w").values()).next()
+    steps = np.concatenate([w["s"].ids[:, None], w["w"].ids], 1)
+    dd = (steps[:, 1:] - steps[:, :-1]) % fx.N_ITEM
+    assert ((dd >= 1) & (dd <= 3)).all()                       # every hop follows a real i -> i+k edge
+    sg = gl.Dataset(g.SubGraph("item", "sim", batch_size=6).alias("sg").values()).next()["sg"]
+    ei, nid = sg.edge_index, sg.nodes.ids
+    assert ei.shape[0] == 2 and all(((nid[c] - nid[r_]) % fx.N_ITEM in (1, 2, 3)) or ((nid[r_] - nid[c]) % fx.N_ITEM in (1, 2, 3))
+                                    for r_, c in zip(ei[0], ei[1]))
+    e = g.E("buy").batch(6).alias("e")
+    s_ = e.outV().alias("src")
+    e.inV().alias("dst")
+    s_.outNeg("buy").sample(4).by("in_degree").where("dst", condition={"float_cols": [0], "float_props": [0.5], "unique": True}).alias("neg")
+    res = gl.Dataset(e.values()).next()
+    for u, row in zip(res["src"].ids, res["neg"].ids):
+        assert not (set(row.tolist()) & {x[0] for x in adj[int(u)]})
+    qv = np.stack([np.arange(4, dtype=np.float32) * 0.25 + i for i in (3.0, 17.0)])     # == item 3 / item 17 features
+    knn_ids, _ = g.search("item", qv, gl.KnnOption(k=2))
+    assert knn_ids[:, 0].tolist() == [3, 17]
     # N17: replica cache of remote feature rows (partial, then full); results must not change
     for cap in (5, 10 ** 6):
         got = g._store.build_feature_caches(cap)
