@@ -216,6 +216,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     own, lib, names = count_own_launches(tr)
+    # remote feature traffic of the fused gather (hot path b/c): rows read per step and rank = self rows of both
+    # layer-1 segments + their neighbour rows; a row owned by another rank and not replicated locally crosses NVLink
+    row_bytes = int(nodes.feats.local.size(1)) * nodes.feats.local.element_size()
+    rows_per_step = args.batch * (1 + FANOUTS[0]) + args.batch * FANOUTS[0] * (1 + FANOUTS[1])
+    n_total = sum(int(x) for x in nodes.nrows)
+    remote_frac = 0.0 if W == 1 else (W - 1) / W * max(0.0, 1.0 - cache_rows / max(n_total - nodes.n_local, 1))
+    remote_bytes = rows_per_step * row_bytes * remote_frac
     if rt.rank == 0:
         steps_per_s = W * args.steps / (ms_dev / 1e3)
         e2e_steps_per_s = W * args.steps / (ms_e2e / 1e3)
@@ -230,6 +237,14 @@ def run_ours(args):
                        "num_nodes": shape["num_nodes"], "num_edges": shape["num_edges"],
                        "feat_dim": shape["feat_dim"], "feature_storage": args.feature_dtype,
                        "feature_cache_rows_per_gpu": cache_rows,
+                       "feature_cache": ("n/a (single GPU)" if W == 1 else
+                                         "none (every remote row is read from its owner's HBM over NVLink inside the fused kernel)"
+                                         if cache_rows == 0 else
+                                         "replica cache of remote feature rows in local HBM (reference: set_local_node_cache_capacity); "
+                                         "topology stays partitioned; --feature-cache-rows 0 disables it"),
+                       "remote_feature_bytes_per_step_per_gpu": int(remote_bytes),
+                       "remote_feature_GBps_per_gpu": round(remote_bytes / (ms_dev / args.steps * 1e-3) / 1e9, 1),
+                       "nvlink_random_row_ceiling_GBps": 477 if row_bytes <= 256 else 580,
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
                                     % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * (2 if fdt == torch.bfloat16 else 4) / 1e9),
                        "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine, "gather_mode": args.gather_mode,
