@@ -15,9 +15,15 @@ pre-allocated buffers (static shapes -> CUDA graph friendly):
   K8  peer-memory all-reduce of the flat gradient (world > 1)
       RNG/step advance + fused Adam                       (2 launches)
 
-~16 launches for the 2-layer flagship instead of ~60 on the autograd path.
+18 launches for the 2-layer flagship instead of ~60 on the autograd path.
 Layer l consumes hop pairs (i, i+1) for i in 0..L-l, exactly the EgoGNN
 recursion of graphlearn/python/nn/tf/model/ego_gnn.py:58-110.
+
+Scheduling (see ``_step_body`` / ``capture``): the launches above form a DAG, not a chain - independent ones
+run on forked streams, which become parallel branches of the captured CUDA graph; under capture the step is
+additionally software pipelined: graph replay t trains on the batch that replay t-1 staged (pinned host ->
+device) and sampled on a side branch, and the loss leaves through another branch.  Public API: ``capture()``,
+``step(seed_ids_host)`` (end to end), ``step_device()`` (no host traffic), ``predict``, ``state_dict``.
 """
 from __future__ import annotations
 
@@ -259,9 +265,9 @@ class FastSageTrainer:
 
     # ------------------------------------------------------------------ graph / public step (same API as SageTrainer)
     def capture(self, warmup: int = 3):
-        """Warm up eagerly, then capture (a) the device-only step and (b) two end-to-end step graphs
-        that also contain the H2D copy of the seed batch (from a pinned staging buffer) and the D2H
-        copy of the loss: the whole public `step()` is then ONE graph launch."""
+        """Warm up eagerly, then capture four graphs (device-only pair + end-to-end pair, one per hop-buffer
+        parity); the whole public ``step()`` - H2D of the seeds, sampling, training, D2H of the loss - is then
+        ONE graph launch."""
         if not self.use_graph or self.graph is not None:
             return
         s = torch.cuda.Stream()
