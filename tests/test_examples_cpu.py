@@ -69,3 +69,11 @@ def test_ultra_gcn():
 def test_tgn_temporal_link_prediction():
     first, last, val_auc = _run("tgn", ["--device", "cpu", "--epochs", "3"])
     assert last < first and val_auc > 0.6
+
+
+def test_export_serving_model_and_online_inference(tmp_path):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        acc, same, out = _run("export_serving_model", ["--epochs", "2", "--nodes", "600", "--out", str(tmp_path / "m.pt")])
+    assert same and acc > 0.8 and os.path.getsize(out) > 0
