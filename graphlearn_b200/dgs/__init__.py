@@ -19,6 +19,7 @@ state in HBM tables:
 * ``FileLoader``            pattern-file driven record ingestion (file_loader.py; dataloader SDK)
 * ``HttpFrontEnd``          ``/infer?qid&vid`` + admin API (install query, checkpoint, barrier, stats)
 * ``CheckpointManager`` / ``BarrierMonitor``   coordinator duties (coordinator.py)
+* ``PartitionedGraphService``  vid-hash partitioned stores (one per GPU) with per-hop routing (partitioned.py)
 
 Kafka, RocksDB, the Java client and the Helm chart are deployment glue around this core and are out
 of scope; ``apply_updates`` takes record batches (dict of arrays) directly.
@@ -26,6 +27,7 @@ of scope; ``apply_updates`` takes record batches (dict of arrays) directly.
 from .coordinator import BarrierMonitor, CheckpointManager  # noqa: F401
 from .file_loader import FileLoader, RecordBatchBuilder  # noqa: F401
 from .http_server import HttpFrontEnd  # noqa: F401
+from .partitioned import PartitionedGraphService, Partitioner  # noqa: F401
 from .plan import PlanNode, QueryPlan  # noqa: F401
 from .schema import Options, Schema  # noqa: F401
 from .service import AdaptiveRateLimiter, DynamicGraphService, SampleStore  # noqa: F401

@@ -199,6 +199,8 @@ class DynamicGraphService(object):
             nbr, ts, w = st.lookup(flat.clamp(min=0), node.fanout)
             ok = ((flat >= 0) & (flat < st.n))[:, None]
             nbr = torch.where(ok, nbr, torch.full_like(nbr, -1))
+            ts = torch.where(ok, ts, torch.full_like(ts, -(2 ** 62)))      # unknown vertices answer like empty ones
+            w = torch.where(ok, w, torch.zeros_like(w))
             dst_type = self.schema["edges"][node.etype]["dst"]
             vs = self.vstores[dst_type]
             feat = None

@@ -125,3 +125,33 @@ def test_reference_config_formats_file_loader_http_and_checkpoints(tmp_path):
     assert CheckpointManager(svc2, str(tmp_path / "ck")).restore_latest() == 1
     a, b = svc.run_query(7, [1, 3]), svc2.run_query(7, [1, 3])
     assert torch.equal(a["hops"][0]["ids"], b["hops"][0]["ids"]) and torch.equal(a["hops"][1]["ids"], b["hops"][1]["ids"])
+
+
+def test_partitioned_service_matches_single_store():
+    """D1 partitioner / router: P vid-hash partitions answer exactly like one store."""
+    from graphlearn_b200.dgs import PartitionedGraphService
+    schema = {"vertices": {"u": {"count": 16, "feat_dim": 2}, "i": {"count": 16, "feat_dim": 3}},
+              "edges": {"click": {"src": "u", "dst": "i"}, "sim": {"src": "i", "dst": "i"}}}
+    one = DynamicGraphService(schema, device="cpu")
+    many = PartitionedGraphService(schema, num_partitions=3, devices=["cpu"] * 3)
+    plan = QueryPlan("u").out("click", 3).out("sim", 2)
+    one.install_query(0, plan); many.install_query(0, plan)
+    rs = np.random.RandomState(1)
+    t = 0
+    for _ in range(5):
+        n = 150
+        b = {"edges": {"click": {"src": rs.randint(0, 40, n), "dst": rs.randint(0, 50, n), "ts": np.arange(t, t + n)},
+                       "sim": {"src": rs.randint(0, 50, n), "dst": rs.randint(0, 50, n), "ts": np.arange(t, t + n),
+                               "weight": rs.rand(n).astype(np.float32)}},
+             "vertices": {"i": {"id": rs.randint(0, 50, 20), "ts": np.arange(t, t + 20), "feat": rs.randn(20, 3).astype(np.float32)}}}
+        t += n
+        one.apply_updates(b); many.apply_updates(b)
+    q = list(range(40)) + [45]           # 45: beyond every stored vertex
+    a, c = one.run_query(0, q), many.run_query(0, q)
+    for h in range(2):
+        for key in ("ids", "timestamps", "weights", "features"):
+            assert torch.allclose(a["hops"][h][key].float(), c["hops"][h][key].float()), (h, key)
+    ck = many.checkpoint()
+    again = PartitionedGraphService(schema, num_partitions=3, devices=["cpu"] * 3)
+    again.install_query(0, plan); again.restore(ck)
+    assert torch.equal(again.run_query(0, q)["hops"][1]["ids"], c["hops"][1]["ids"]) and many.stats()["ingested"] == one.ingested
