@@ -8,4 +8,6 @@ from .data import BatchGraph, Data, EgoGraph, HeteroBatchGraph  # noqa: F401
 from .dataset import Batch, Dataset, PyGDataLoader, SubGraphData, TorchDataset  # noqa: F401
 from .embedding import ShardedEmbedding  # noqa: F401
 from .feature import FeatureEncoder  # noqa: F401
+from .hetero import (BipartiteSAGEConv, HeteroConv, HeteroSubGraph, LinkPredictor, SubGraphInducer,  # noqa: F401
+                     SubGraphProcessor)
 from .sparse_conv import GATConv, GCNConv, SAGEConv, segment_softmax  # noqa: F401

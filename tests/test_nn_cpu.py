@@ -263,3 +263,28 @@ def test_relabel_and_spmm_portable():
     out = spmm(x, row, col, w, 5, heads=2)
     ref = torch.zeros(5, 2, 3).index_add_(0, row, x[col].view(-1, 2, 3) * w[:, :, None]).reshape(5, 6)
     assert torch.allclose(out, ref)
+
+
+def test_hetero_conv_and_link_predictor():
+    """HeteroConv: per-edge-type convs, results for the same destination type are aggregated; bipartite convs get
+    [x_src, x_dst]; LinkPredictor returns one logit per pair."""
+    from graphlearn_b200 import nn as glnn
+    torch.manual_seed(0)
+    xu, xi = torch.randn(5, 6), torch.randn(7, 4)
+    ei_ui = torch.tensor([[0, 1, 1, 6], [0, 0, 4, 2]])          # rows: items, cols: users
+    ei_ii = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 0]])
+    conv = glnn.HeteroConv({("u", "buy", "i"): glnn.BipartiteSAGEConv(6, 4, 8),
+                            ("i", "sim", "i"): glnn.SAGEConv(4, 8)}, agg_type="sum")
+    out = conv({("u", "buy", "i"): ei_ui, ("i", "sim", "i"): ei_ii}, {"u": xu, "i": xi})
+    assert set(out) == {"i"} and out["i"].shape == (7, 8)
+    a = conv.convs[0](ei_ui, [xu, xi])
+    b = conv.convs[1](ei_ii, xi)
+    assert torch.allclose(out["i"], a + b, atol=1e-6)
+    # closed form of the bipartite conv for item 1: mean of users 0 and 4
+    c0 = conv.convs[0]
+    want = c0.lin_self(xi[1]) + c0.lin_nbr((xu[0] + xu[4]) / 2)
+    assert torch.allclose(a[1], want, atol=1e-5)
+    lp = glnn.LinkPredictor(8, num_layers=2)
+    assert lp(torch.randn(9, 8)).shape == (9,)
+    sg = glnn.HeteroSubGraph({("u", "buy", "i"): ei_ui}, {"u": glnn.Data(ids=torch.arange(5)), "i": glnn.Data(ids=torch.arange(7))})
+    assert sg.num_nodes("i") == 7 and sg.num_edges(("u", "buy", "i")) == 4 and sg.edge_types == [("u", "buy", "i")]
