@@ -74,6 +74,34 @@ class EgoGraph(object):
         return [e(d.floats, d.ints, d.strings) for e, d in zip(encs, self.hops())]
 
 
+class TemporalGraph(object):
+    """EgoGraph with time: centre nodes + their timestamps, and per hop the neighbour nodes, the timestamps of the
+    connecting edges and (optionally) the edge features (graphlearn/python/nn/tf/data/temporalgraph.py:29-140).
+    ``transform(time_encoder)`` replaces raw times by encoded time SPANS (centre time - edge time), the input the
+    temporal layers (``nn.EgoTGATConv``, ``models.TGN``) consume."""
+
+    def __init__(self, src: Data, src_t: torch.Tensor, nbr_nodes: Sequence[Data], nbr_t: Sequence[torch.Tensor],
+                 nbr_edges: Optional[Sequence[Data]] = None, nbr_nums: Sequence[int] = (), node_schema=None,
+                 edge_schema=None, time_dim: int = 16):
+        self.src, self.src_t = src, src_t
+        self.nbr_nodes, self.nbr_t, self.nbr_edges = list(nbr_nodes), list(nbr_t), list(nbr_edges or [])
+        self.nbr_nums, self.node_schema, self.edge_schema, self.time_dim = list(nbr_nums), node_schema, edge_schema, time_dim
+
+    def time_spans(self):
+        """per hop: (time of the hop's parent element) - (edge time), flattened like the hop."""
+        spans, parent_t = [], self.src_t.reshape(-1)
+        for t, k in zip(self.nbr_t, self.nbr_nums):
+            tt = t.reshape(-1)
+            spans.append(parent_t.repeat_interleave(k) - tt)
+            parent_t = tt
+        return spans
+
+    def transform(self, time_encoder):
+        enc = [time_encoder(s.clamp(min=0)) for s in self.time_spans()]
+        return TemporalGraph(self.src, time_encoder(torch.zeros_like(self.src_t.reshape(-1))), self.nbr_nodes, enc,
+                             self.nbr_edges, self.nbr_nums, None, None, self.time_dim)
+
+
 class BatchGraph(object):
     """Several subgraphs stacked into one big disconnected graph (batchgraph.py): node features
     concatenated, edge_index shifted by the per-graph node offset."""

@@ -10,7 +10,7 @@ import torch
 
 from .. import errors
 from ..gsl.dataset import Dataset as _GslDataset
-from .data import BatchGraph, Data, EgoGraph
+from .data import BatchGraph, Data, EgoGraph, TemporalGraph
 
 
 class Dataset(object):
@@ -40,6 +40,19 @@ class Dataset(object):
         if nbr_nums is None:
             nbr_nums = [int(res[a].shape[-1]) for a in neighbors]
         return EgoGraph(src, hops, nbr_nums=nbr_nums)
+
+    def get_temporalgraph(self, source: str, nbr_edges: Sequence[str], nbr_nodes: Sequence[str], res=None,
+                          time_dim: int = 16) -> TemporalGraph:
+        """TemporalGraph rooted at alias `source` (a timestamped node or edge root); hop i is described by the edge
+        alias ``nbr_edges[i]`` (timestamps / edge features) and the node alias ``nbr_nodes[i]``."""
+        res = res if res is not None else self._ds.next()
+        src = Data.from_values(res[source])
+        src_t = res[source].tensor("timestamps").reshape(-1)
+        nodes = [Data.from_values(res[a]) for a in nbr_nodes]
+        edges = [Data.from_values(res[a]) for a in nbr_edges]
+        nbr_t = [res[a].tensor("timestamps").reshape(-1) for a in nbr_edges]
+        nums = [int(res[a].shape[-1]) for a in nbr_edges]
+        return TemporalGraph(src, src_t, nodes, nbr_t, edges, nums, time_dim=time_dim)
 
     def get_batchgraph(self, alias: str, additional_keys=()) -> BatchGraph:
         res = self._ds.next()

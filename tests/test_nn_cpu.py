@@ -288,3 +288,31 @@ def test_hetero_conv_and_link_predictor():
     assert lp(torch.randn(9, 8)).shape == (9,)
     sg = glnn.HeteroSubGraph({("u", "buy", "i"): ei_ui}, {"u": glnn.Data(ids=torch.arange(5)), "i": glnn.Data(ids=torch.arange(7))})
     assert sg.num_nodes("i") == 7 and sg.num_edges(("u", "buy", "i")) == 4 and sg.edge_types == [("u", "buy", "i")]
+
+
+def test_temporal_graph_container(tmp_path):
+    """nn.Dataset.get_temporalgraph: centre times, per-hop edge times, time spans >= 0 under the temporal filter."""
+    import os
+    import graphlearn_b200 as gl
+    from graphlearn_b200 import nn as glnn
+    d = str(tmp_path)
+    with open(d + "/n.tsv", "w") as f:
+        f.write("id:int64\ttimestamp:int64\tfeature:string\n" + "".join("%d\t%d\t%d:%d\n" % (i, 100 + 10 * i, i, i) for i in range(20)))
+    with open(d + "/e.tsv", "w") as f:
+        f.write("src_id:int64\tdst_id:int64\ttimestamp:int64\n")
+        for i in range(20):
+            for k in range(1, 4):
+                f.write("%d\t%d\t%d\n" % (i, (i + k) % 20, 95 + 10 * i - k))
+    gl.set_default_neighbor_id(-1)
+    gl.set_padding_mode(gl.REPLICATE)
+    g = gl.Graph().node(d + "/n.tsv", "n", decoder=gl.Decoder(timestamped=True, attr_types=["float", "float"])) \
+        .edge(d + "/e.tsv", ("n", "n", "e"), decoder=gl.Decoder(timestamped=True)).init(device="cpu")
+    src = g.V("n").batch(5).alias("s")
+    src.outE("e").sample(2).by("topk").alias("e1").inV().alias("h1")
+    ds = glnn.Dataset(src.values())
+    tg = ds.get_temporalgraph("s", ["e1"], ["h1"])
+    assert tg.nbr_nums == [2] and tg.src_t.tolist() == [100, 110, 120, 130, 140]
+    spans = tg.time_spans()[0].reshape(5, 2)
+    assert (spans == torch.tensor([[6, 7]] * 5)).all()          # edge times 95+10i-k, most recent first: k = 1, 2
+    enc = tg.transform(glnn.TimeEncoder(8))
+    assert enc.nbr_t[0].shape == (10, 8) and enc.src_t.shape == (5, 8)
