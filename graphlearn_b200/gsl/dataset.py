@@ -26,10 +26,12 @@ class DagValues(dict):
 
 
 class Dataset(object):
-    def __init__(self, dag, window=10, keep_alive_rounds=1, drop_last=False, prefetch=True):
+    def __init__(self, dag, window=10, keep_alive_rounds=1, drop_last=False, prefetch=True, sync_epoch=None):
+        """``sync_epoch``: end the epoch on every rank as soon as one rank runs out of seeds (None = automatic: on
+        for multi-rank runs whose sampling ops are collectives, i.e. the portable path)."""
         self._dag = dag
         self._graph = dag.graph
-        self._exec = QueryExecutor(dag, drop_last=drop_last)
+        self._exec = QueryExecutor(dag, drop_last=drop_last, sync_epoch=sync_epoch)
         self._window = max(1, int(window))
         self._ring = collections.deque()
         self._pending_eoe = False

@@ -38,7 +38,7 @@ class _Out(object):
 
 
 class QueryExecutor(object):
-    def __init__(self, dag, drop_last: bool = False, seed: Optional[int] = None):
+    def __init__(self, dag, drop_last: bool = False, seed: Optional[int] = None, sync_epoch: Optional[bool] = None):
         if not dag.is_ready():
             raise ValueError("query is not ready: end it with .values()")
         self.dag = dag
@@ -50,6 +50,9 @@ class QueryExecutor(object):
         self._iter: Optional[SeedIterator] = None
         self._order = self._toposort()
         self._salt = 0
+        if sync_epoch is None:      # auto: on whenever the sampling ops of this run are collectives
+            sync_epoch = self.rt.world > 1 and not (self.rt.is_cuda and _config.get().use_peer_kernels)
+        self.sync_epoch = bool(sync_epoch) and self.rt.world > 1
 
     # ------------------------------------------------------------------ plan
     def _toposort(self):
@@ -93,6 +96,41 @@ class QueryExecutor(object):
         return order
 
     # ------------------------------------------------------------------ roots
+    def _ensure_root_iter(self):
+        """Create the seed iterator of the root (this rank's nodes / edges of the root type) on first use."""
+        if self._iter is not None:
+            return
+        node, r, dev = self.dag.root, self.rt.rank, self.rt.device
+        p = node.params
+        seed = _config.get().seed + 17 * r
+        if isinstance(node, SubGraphDagNode):
+            tab = self.store.nodes[p["seed_type"]]
+            self._iter = SeedIterator(tab.n_local, int(p["batch_size"]), "shuffle" if "random" in p["strategy"] else "by_order",
+                                      dev, seed=seed)
+        elif isinstance(node, TraverseSourceEdgeDagNode) or p.get("node_from", NODE) != NODE:
+            csr = self.store.edges[p["edge_type"]]
+            self._iter = SeedIterator(csr.n_edges, int(p.get("batch_size", 64)), p.get("strategy", "by_order"), dev,
+                                      seed=seed, drop_last=self.drop_last)
+        else:
+            tab = self.store.nodes[node.type]
+            rows = tab.present.nonzero().flatten() if tab.present is not None else torch.arange(tab.n_local, device=dev)
+            self._rows = rows
+            self._iter = SeedIterator(int(rows.numel()), int(p.get("batch_size", 64)), p.get("strategy", "by_order"), dev,
+                                      seed=seed, drop_last=self.drop_last)
+
+    def _sync_epoch_end(self):
+        """Multi-rank lock step: when ANY rank has exhausted its shard, every rank ends the epoch now (ranks that
+        still had batches drop them, like ``DistributedSampler(drop_last=True)``).  Needed whenever the query's
+        ops are collectives (portable path; non-dense id maps / string lookups also on GPUs): a rank that stopped
+        iterating would leave the others blocked inside an all-to-all."""
+        import torch.distributed as dist
+        self._ensure_root_iter()
+        flag = torch.tensor([1 if self._iter.has_next() else 0], dtype=torch.int32, device=self.rt.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self._iter.end_epoch()
+            raise errors.OutOfRangeError("end of epoch (synchronised across ranks)")
+
     def _root_nodes(self, node: DagNode) -> _Out:
         p = node.params
         bs = int(p.get("batch_size", 64))
@@ -100,11 +138,7 @@ class QueryExecutor(object):
         W, r = self.rt.world, self.rt.rank
         if p.get("node_from", NODE) == NODE:
             tab = self.store.nodes[node.type]
-            if self._iter is None:
-                rows = tab.present.nonzero().flatten() if tab.present is not None else torch.arange(tab.n_local, device=self.rt.device)
-                self._rows = rows
-                self._iter = SeedIterator(int(rows.numel()), bs, strategy, self.rt.device, seed=_config.get().seed + 17 * r,
-                                          drop_last=self.drop_last)
+            self._ensure_root_iter()
             idx = self._iter.next_index()
             rows = self._rows[idx]
             vids = rows * W + r
@@ -124,10 +158,8 @@ class QueryExecutor(object):
             return out
         # nodes from edge end points
         csr = self.store.edges[p["edge_type"]]
-        if self._iter is None:
-            self._iter = SeedIterator(csr.n_edges, bs, strategy, self.rt.device, seed=_config.get().seed + 17 * r,
-                                      drop_last=self.drop_last)
-            # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
+        self._ensure_root_iter()
+        # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
         # index, memory_edge_storage.cc; GetEdges by_order walks edge ids) - chronological event
         # files therefore yield chronological batches although the CSR is row-major
         idx = csr.insertion_pos()[self._iter.next_index()]
@@ -147,10 +179,8 @@ class QueryExecutor(object):
         csr = self.store.edges[p["edge_type"]]
         W, r = self.rt.world, self.rt.rank
         bs = int(p.get("batch_size", 64))
-        if self._iter is None:
-            self._iter = SeedIterator(csr.n_edges, bs, p.get("strategy", "by_order"), self.rt.device,
-                                      seed=_config.get().seed + 17 * r, drop_last=self.drop_last)
-            # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
+        self._ensure_root_iter()
+        # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
         # index, memory_edge_storage.cc; GetEdges by_order walks edge ids) - chronological event
         # files therefore yield chronological batches although the CSR is row-major
         idx = csr.insertion_pos()[self._iter.next_index()]
@@ -275,10 +305,7 @@ class QueryExecutor(object):
         csr = self.store.edges[et]
         if up is None:
             # root SubGraph: seeds from a node iterator over the seed type
-            if self._iter is None:
-                tab = self.store.nodes[p["seed_type"]]
-                self._iter = SeedIterator(tab.n_local, int(p["batch_size"]), "shuffle" if "random" in p["strategy"] else "by_order",
-                                          self.rt.device, seed=_config.get().seed + 17 * self.rt.rank)
+            self._ensure_root_iter()
             idx = self._iter.next_index()
             seeds = idx * self.rt.world + self.rt.rank
             src = dst = None
@@ -307,6 +334,8 @@ class QueryExecutor(object):
     _root_ts = None
 
     def run(self) -> Dict[str, object]:
+        if self.sync_epoch:
+            self._sync_epoch_end()
         results: Dict[int, _Out] = {}
         for node in self._order:
             up = results.get(id(node.upstream)) if node.upstream is not None else None
@@ -364,10 +393,6 @@ class QueryExecutor(object):
 
     def load_state_dict(self, sd):
         if sd.get("iter") is not None:
-            if self._iter is None:
-                try:
-                    self.run()
-                except errors.OutOfRangeError:
-                    pass
+            self._ensure_root_iter()
             self._iter.load_state_dict(sd["iter"])
         self.rng.load_state_dict(sd["rng"])

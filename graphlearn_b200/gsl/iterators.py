@@ -56,6 +56,21 @@ class SeedIterator(object):
         self.cursor = end
         return idx
 
+    def has_next(self) -> bool:
+        """would ``next_index()`` return a batch (True) or raise OutOfRangeError (False)?"""
+        if self.n == 0:
+            return False
+        if self.strategy == "random":
+            return True
+        return not (self.cursor >= self.n or (self.drop_last and self.cursor + self.bs > self.n))
+
+    def end_epoch(self):
+        """close the current pass early (remaining indices are dropped) - used for multi-rank lock step"""
+        if self.strategy != "random":
+            self.cursor = 0
+            self._perm = None
+        self.epoch += 1
+
     def state_dict(self):
         return {"epoch": self.epoch, "cursor": self.cursor, "seed": self.seed, "strategy": self.strategy}
 

@@ -20,6 +20,7 @@ def main():
     g.node(os.path.join(d, "item_parts"), "item", decoder=gl.Decoder(attr_types=["float"] * 4))   # directory source
     g.edge(os.path.join(d, "u2i.tsv"), ("user", "item", "buy"), decoder=gl.Decoder(weighted=True))
     g.edge(os.path.join(d, "i2i.tsv"), ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
+    g.node_view("item", gl.Mask.TRAIN, seed=5, nsplit=3, split_range=(0, 2))
     g.init(device=dev)
     rt = g.runtime
     W, r = rt.world, rt.rank
@@ -72,6 +73,23 @@ def main():
         assert not (set(row.tolist()) & {x[0] for x in adj[u]})
     nodes = g.get_nodes("item", np.array([[1, 2, 3], [10, 20, 30]]))
     assert np.allclose(nodes.embedding_agg("mean"), nodes.float_attrs.mean(1), atol=1e-5)
+    # ---- unequal shards: hash views give the ranks different numbers of seeds; with collective sampling ops the
+    # epoch must end on every rank together (Dataset sync_epoch auto-on for the portable path)
+    if not rt.is_cuda:
+        dsv = gl.Dataset(g.V("item", mask=gl.Mask.TRAIN).batch(3).alias("s").outV("sim").sample(2).by("random").alias("n").values())
+        counts = []
+        for _ in range(2):
+            nb = 0
+            try:
+                while True:
+                    dsv.next(); nb += 1
+            except gl.OutOfRangeError:
+                pass
+            counts.append(nb)
+        sizes = rt.all_gather_object(int(g._store.nodes[gl.get_mask_type("item", gl.Mask.TRAIN)].n_local))
+        allc = rt.all_gather_object(counts)
+        assert sizes[0] != sizes[1], sizes                       # the shards really are unequal ...
+        assert all(c == allc[0] for c in allc) and allc[0][0] == -(-min(sizes) // 3), (sizes, allc)   # ... the epochs equal
     # ---- ops whose portable path loops a data-dependent number of collective rounds (lock-step across ranks)
     w = gl.Dataset(g.V("item").batch(5).alias("s").random_walk("sim", 4, p=0.5, q=2.0).alias("w").values()).next()
     steps = np.concatenate([w["s"].ids[:, None], w["w"].ids], 1)
