@@ -87,6 +87,10 @@ def main(argv=None):
         loss = tr.train_epoch()
         test_acc = tr.evaluate(test_ds, acc)
         print("epoch %d loss %.4f test acc %.3f" % (ep, loss, test_acc))
+    if g.runtime.world > 1:         # data-parallel replicas must hold identical parameters
+        ps = g.runtime.all_gather_object(tr.flat_p.detach().cpu())
+        assert all(torch.allclose(p, ps[0], atol=1e-6) for p in ps), "replicas diverged"
+        print("replicas in sync on %d ranks" % g.runtime.world)
     return test_acc
 
 

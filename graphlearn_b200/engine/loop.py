@@ -24,6 +24,9 @@ class Trainer(object):
         """step_fn(model, batch) -> loss tensor.  `dataset.next()` yields batches (gl.Dataset / nn.Dataset)."""
         self.rt, self.model, self.dataset, self.step_fn = rt, model, dataset, step_fn
         self.flat_p, self.flat_g = comm_ops.flatten_module(model)
+        if rt.world > 1:            # replicas start from rank 0's initialisation (what DDP does at construction)
+            import torch.distributed as dist
+            dist.broadcast(self.flat_p, src=0)
         self.opt = optimizer or comm_ops.FlatAdam(self.flat_p, self.flat_g, lr=lr)
         self._flat_opt = optimizer is None
         self.ar = comm_ops.PeerAllReduce(rt, self.flat_g.numel(), backend=allreduce)

@@ -35,6 +35,17 @@ def test_public_api_two_ranks_cpu_gloo(tmp_path):
     _run(2, 29647, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": ""}, "dist_api_worker.py", [d], "DIST_API_OK")
 
 
+def test_data_parallel_example_two_ranks_cpu_gloo():
+    """examples/train_gcn_sparse.py under torchrun: masks + full neighbourhoods + generic Trainer (flat gradients,
+    all-reduce, lock-step epochs) - replicas must end with identical parameters."""
+    env = dict(os.environ, GLB_TEST_DEVICE="cpu", CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29649", os.path.join(ROOT, "examples", "train_gcn_sparse.py"), "--device", "cpu",
+           "--epochs", "2", "--nodes", "500"]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=os.path.join(ROOT, "examples"))
+    assert p.returncode == 0 and "replicas in sync on 2 ranks" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.multigpu
 def test_public_api_two_ranks_gpu(tmp_path):
