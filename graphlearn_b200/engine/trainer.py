@@ -37,6 +37,10 @@ class SageTrainer:
         self.strategy = strategy
         self.rng = rng_ops.DeviceRng(rt, seed)
         self.flat_p, self.flat_g = comm_ops.flatten_module(model)
+        if rt.world > 1:            # replicas start from rank 0's initialisation (what DDP does at construction)
+            import torch.distributed as dist
+            with torch.no_grad():
+                dist.broadcast(self.flat_p, src=0)
         self.opt = comm_ops.FlatAdam(self.flat_p, self.flat_g, lr=lr)
         self.ar = comm_ops.PeerAllReduce(rt, self.flat_g.numel(), backend=allreduce)
         self.seeds = torch.zeros(self.B, dtype=torch.int64, device=rt.device)     # static input buffer
