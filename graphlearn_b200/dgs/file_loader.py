@@ -65,9 +65,12 @@ class FileLoader(object):
             out.extend(float(x) for x in (v.split(self.ldelim) if a.is_list else [v]) if x != "")
         return out
 
-    def load(self, path: str, service) -> int:
-        """Stream one file into the service; returns the number of records applied."""
+    def load(self, path: str, service, adaptive: bool = False) -> int:
+        """Stream one file into the service; returns the number of records applied.  ``adaptive=True`` scales the
+        ingest batch size with the service's ``AdaptiveRateLimiter`` (record-polling concurrency in the reference:
+        the limiter shrinks ingest when query latencies miss their P99 target and restores it when stable)."""
         b, n = RecordBatchBuilder(), 0
+        base_bs = self.batch_size
         with open(path) as f:
             for line in f:
                 parts = line.rstrip("\n").split(self.delim)
@@ -88,6 +91,10 @@ class FileLoader(object):
                 n += 1
                 if b.size >= self.batch_size:
                     service.apply_updates(b.finish())
+                    if adaptive and hasattr(service, "limiter"):
+                        c = service.limiter.tick()
+                        self.batch_size = max(1, base_bs * c // max(service.limiter.max_c, 1))
         if b.size:
             service.apply_updates(b.finish())
+        self.batch_size = base_bs
         return n

@@ -80,6 +80,18 @@ class SampleStore(object):
         self.feat[vid[newer]] = feat[newer]
         self.feat_ts.scatter_reduce_(0, vid[newer], ts[newer], "amax")
 
+    def expire(self, before_ts: int) -> int:
+        """TTL: drop every kept sample older than ``before_ts`` (the reference stores edge samples in a RocksDB
+        ``DBWithTTL``, sample_store.h:71-170, option ``sample-store.ttl-hours``).  Returns the number dropped."""
+        old = (self.ts < int(before_ts)) & (self.nbr >= 0)
+        n = int(old.sum().item())
+        if n:
+            self.nbr[old] = -1
+            self.ts[old] = -(2 ** 62)
+            self.w[old] = 0
+            self.count -= old.sum(1)
+        return n
+
     def lookup(self, vids: torch.Tensor, k: int):
         """most recent k samples of each vertex: (nbr [B,k], ts [B,k], w [B,k]); -1 padded."""
         vids = torch.where(vids < self.n, vids, torch.zeros_like(vids)) if vids.numel() else vids
@@ -214,6 +226,10 @@ class DynamicGraphService(object):
         self.limiter.record((time.perf_counter() - t0) * 1e3)
         self.served += int(src.numel())
         return out
+
+    def expire(self, before_ts: int) -> int:
+        """apply the sample TTL to every edge store (timestamps are whatever unit the records use)"""
+        return sum(st.expire(before_ts) for st in self.stores.values())
 
     def stats(self) -> dict:
         return {"ingested": self.ingested, "served": self.served, "queries": sorted(self.queries),

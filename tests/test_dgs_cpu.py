@@ -155,3 +155,29 @@ def test_partitioned_service_matches_single_store():
     again = PartitionedGraphService(schema, num_partitions=3, devices=["cpu"] * 3)
     again.install_query(0, plan); again.restore(ck)
     assert torch.equal(again.run_query(0, q)["hops"][1]["ids"], c["hops"][1]["ids"]) and many.stats()["ingested"] == one.ingested
+
+
+def test_sample_ttl_and_adaptive_ingest(tmp_path):
+    from graphlearn_b200.dgs import FileLoader, Schema
+    schema = {"vertices": {"u": {"count": 8, "feat_dim": 0}, "i": {"count": 8, "feat_dim": 0}},
+              "edges": {"click": {"src": "u", "dst": "i"}}}
+    svc = DynamicGraphService(schema, device="cpu")
+    svc.install_query(0, QueryPlan("u").out("click", 4))
+    svc.apply_updates({"edges": {"click": {"src": [1, 1, 1, 2], "dst": [3, 4, 5, 6], "ts": [10, 20, 30, 40]}}})
+    assert svc.expire(25) == 2
+    r = svc.run_query(0, [1, 2])["hops"][0]
+    assert r["ids"][0].tolist() == [5, -1, -1, -1] and r["ids"][1].tolist() == [6, -1, -1, -1]
+    assert svc.stores["click"].count[1].item() == 1
+    # adaptive ingest: slow queries shrink the ingest batch, the loader restores its nominal size afterwards
+    sj = {"attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}],
+          "vertex_defs": [{"vtype": 0, "name": "u", "attr_types": [0]}, {"vtype": 1, "name": "i", "attr_types": [0]}],
+          "edge_defs": [{"etype": 2, "name": "click", "attr_types": [0]}],
+          "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}]}
+    (tmp_path / "pat").write_text("#EDGE:click,src,dst,timestamp\n")
+    (tmp_path / "data").write_text("".join("click,%d,%d,%d\n" % (i % 8, (i * 3) % 8, 100 + i) for i in range(500)))
+    for _ in range(50):
+        svc.limiter.record(1000.0)                      # pretend the serving latency target is being missed
+    fl = FileLoader(str(tmp_path / "pat"), Schema(sj), batch_size=64)
+    assert fl.load(str(tmp_path / "data"), svc, adaptive=True) == 500
+    assert svc.limiter.concurrency < svc.limiter.max_c and fl.batch_size == 64
+    assert svc.run_query(0, [3])["hops"][0]["timestamps"][0, 0].item() == 100 + 499 - (499 - 3) % 8
