@@ -82,3 +82,41 @@ class ProgressLogger(object):
             self._t0, self._step0 = time.perf_counter(), self.step
             return rate
         return None
+
+
+class StepProfiler(object):
+    """Chrome-trace dumps of selected training steps - the reference's ``profiling=True`` option writes
+    ``timeline_<step>.json`` for steps 500-1000 every 100 (examples/tf/trainer.py:309-322,387-402).
+
+        prof = StepProfiler("traces", start=500, stop=1000, every=100)
+        for step in range(n):
+            with prof.step(step):
+                trainer.step(...)
+
+    Selected steps run under ``torch.profiler`` (CPU + CUDA activities when a GPU is present) and are exported
+    to ``<dir>/timeline_<step>.json`` (open in chrome://tracing or Perfetto); all other steps cost nothing."""
+
+    def __init__(self, out_dir: str, start: int = 0, stop: int = 1 << 62, every: int = 1):
+        import os
+        self.out_dir, self.start, self.stop, self.every = out_dir, int(start), int(stop), max(1, int(every))
+        os.makedirs(out_dir, exist_ok=True)
+        self.written = []
+
+    def selected(self, step: int) -> bool:
+        return self.start <= step < self.stop and (step - self.start) % self.every == 0
+
+    @contextlib.contextmanager
+    def step(self, step: int):
+        if not self.selected(step):
+            yield
+            return
+        import os
+        from torch.profiler import ProfilerActivity, profile
+        acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if torch.cuda.is_available() else [])
+        with profile(activities=acts) as prof:
+            yield
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+        path = os.path.join(self.out_dir, "timeline_%d.json" % step)
+        prof.export_chrome_trace(path)
+        self.written.append(path)

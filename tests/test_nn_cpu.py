@@ -316,3 +316,17 @@ def test_temporal_graph_container(tmp_path):
     assert (spans == torch.tensor([[6, 7]] * 5)).all()          # edge times 95+10i-k, most recent first: k = 1, 2
     enc = tg.transform(glnn.TimeEncoder(8))
     assert enc.nbr_t[0].shape == (10, 8) and enc.src_t.shape == (5, 8)
+
+
+def test_step_profiler_writes_chrome_traces(tmp_path):
+    import json
+    from graphlearn_b200.utils.trace import DeviceTimer, StepProfiler
+    prof = StepProfiler(str(tmp_path), start=2, stop=7, every=2)
+    x = torch.randn(64, 64)
+    timer = DeviceTimer()
+    for step in range(8):
+        with prof.step(step), timer.section("mm"):
+            (x @ x).sum().item()
+    assert [os.path.basename(p) for p in prof.written] == ["timeline_2.json", "timeline_4.json", "timeline_6.json"]
+    assert "traceEvents" in json.load(open(prof.written[0]))
+    assert timer.summary()["mm"]["calls"] == 8
