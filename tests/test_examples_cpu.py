@@ -77,3 +77,8 @@ def test_export_serving_model_and_online_inference(tmp_path):
         warnings.simplefilter("ignore")
         acc, same, out = _run("export_serving_model", ["--epochs", "2", "--nodes", "600", "--out", str(tmp_path / "m.pt")])
     assert same and acc > 0.8 and os.path.getsize(out) > 0
+
+
+def test_subgraph_sage_edge_inducer():
+    first, last = _run("train_subgraph_sage", ["--device", "cpu", "--epochs", "2", "--nodes", "500"])
+    assert last < first
