@@ -18,7 +18,19 @@ from .errors import *  # noqa: F401,F403
 from .errors import OutOfRangeError  # noqa: F401
 from .graph import EDGE_DST, EDGE_SRC, NODE, Graph  # noqa: F401
 from .gsl.dataset import Dataset  # noqa: F401
-from .ops.knn import KnnOption  # noqa: F401
+from .data.feature_spec import (DenseSpec, DynamicMultivalSpec, DynamicSparseSpec, MultivalSpec,  # noqa: F401
+                                SparseSpec)
+from .errors import BaseError  # noqa: F401
+from .ops.knn import KnnOperator, KnnOption  # noqa: F401
+from .sampler.negative_sampler import (ConditionalNegativeSampler, InDegreeNegativeSampler,  # noqa: F401
+                                       NegativeSampler, NodeWeightNegativeSampler, RandomNegativeSampler)
+from .sampler.neighbor_sampler import (EdgeWeightNeighborSampler, FullNeighborSampler,  # noqa: F401
+                                       InDegreeNeighborSampler, NeighborSampler, RandomNeighborSampler,
+                                       RandomWithoutReplacementNeighborSampler, TopkNeighborSampler)
+from .sampler.node_sampler import (ByOrderEdgeSampler, ByOrderNodeSampler, EdgeSampler, NodeSampler,  # noqa: F401
+                                   RandomEdgeSampler, RandomNodeSampler, ShuffleEdgeSampler, ShuffleNodeSampler)
+from .sampler.subgraph_sampler import SubGraphSampler  # noqa: F401
+from .utils import deprecated  # noqa: F401
 from .store.graph_store import Topology  # noqa: F401
 from .utils import Mask, get_mask_type, strategy2op  # noqa: F401
 

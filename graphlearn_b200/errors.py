@@ -36,6 +36,7 @@ class GLError(Exception):
 
 
 OpError = GLError
+BaseError = GLError          # the reference's name for the base class (python/errors.py:22)
 
 
 def _mk(name, code, doc):

@@ -55,3 +55,14 @@ def search(rt, table, queries: torch.Tensor, k: int, metric: int = 0):
     ids = table.idmap.to_id(vids)
     d = s if metric == 1 else -s
     return ids, d
+
+
+class KnnOperator(object):
+    """Imperative form of ``Graph.search`` (graphlearn/python/operator/knn_operator.py): bound to a node type,
+    ``search(inputs, k)`` returns (ids [B, k], distances [B, k]) as numpy arrays."""
+
+    def __init__(self, graph, node_type):
+        self._g, self._type = graph, node_type
+
+    def search(self, inputs, k=1):
+        return self._g.search(self._type, inputs, KnnOption(k))

@@ -42,3 +42,16 @@ def ensure_list(x):
     if isinstance(x, (list, tuple)):
         return list(x)
     return [x]
+
+
+def deprecated(date, old, instead):
+    """Decorator that prints an API-change notice on every call (graphlearn/python/utils.py:22-32)."""
+    import functools
+
+    def log_decorator(func):
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            print("[WARNING] %s will not be supported after %s, please use %s instead." % (old, date, instead))
+            return func(*args, **kwargs)
+        return wrapper
+    return log_decorator
