@@ -36,6 +36,8 @@ from .utils import Mask, get_mask_type, strategy2op  # noqa: F401
 
 __version__ = "0.1.0"
 
+from . import nn  # noqa: E402,F401  (gl.nn, like the reference's `import graphlearn.python.nn as nn`)
+
 
 class IndexOption(object):
     """KNN index options of the reference (graphlearn/python/c/py_export.cc); only the flat
