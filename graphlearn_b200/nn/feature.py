@@ -12,6 +12,15 @@ import torch.nn as nn
 from ..data.feature_spec import DenseSpec, FeatureSpec, MultivalSpec, SparseSpec
 
 
+def _hash_token(tok: str) -> int:
+    """Process-independent string hash (FNV-1a 64): Python's ``hash()`` is salted per process, which would map the
+    same token to different buckets on different ranks and between training and serving."""
+    h = 0xcbf29ce484222325
+    for b in tok.encode("utf-8"):
+        h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
 def _hash_bucket(x: torch.Tensor, buckets: int) -> torch.Tensor:
     """deterministic integer hash -> [0, buckets)."""
     h = (x.to(torch.int64) * 2654435761) & 0x7FFFFFFFFFFFFFFF
@@ -79,7 +88,7 @@ class FeatureEncoder(nn.Module):
                 flat, offs = [], [0]
                 for row in string_attrs[:, j]:
                     toks = [t for t in str(row).split(spec.delimiter) if t]
-                    flat.extend(hash(t) % int(spec.bucket_size) for t in toks)
+                    flat.extend(_hash_token(t) % int(spec.bucket_size) for t in toks)
                     offs.append(len(flat))
                 dev = m.weight.device
                 parts.append(m(torch.tensor(flat, dtype=torch.long, device=dev), torch.tensor(offs[:-1], dtype=torch.long, device=dev)))

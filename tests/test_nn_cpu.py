@@ -330,3 +330,15 @@ def test_step_profiler_writes_chrome_traces(tmp_path):
     assert [os.path.basename(p) for p in prof.written] == ["timeline_2.json", "timeline_4.json", "timeline_6.json"]
     assert "traceEvents" in json.load(open(prof.written[0]))
     assert timer.summary()["mm"]["calls"] == 8
+
+
+def test_multival_token_hash_is_process_independent():
+    """string tokens must land in the same embedding bucket in every process (ranks, train vs serve)."""
+    import subprocess
+    import sys
+    from graphlearn_b200.nn.feature import _hash_token
+    code = "import sys; sys.path.insert(0, %r); from graphlearn_b200.nn.feature import _hash_token; print(_hash_token('brand_42'), _hash_token(''))" % \
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONHASHSEED=str(s))).stdout.strip()
+            for s in (1, 2)}
+    assert outs == {"%d %d" % (_hash_token("brand_42"), _hash_token(""))}
