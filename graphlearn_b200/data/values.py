@@ -332,6 +332,10 @@ class Edges(Values):
         return self._graph.get_edge_decoder(self._edge_type)
 
     def _lookup(self):
+        if self._t.get("edge_ids") is None and self._t.get("dst_ids") is not None:
+            # edges given by their end points only (g.get_edges(etype, src, dst)): resolve the ids first
+            e = self._graph.find_edge_ids(self._edge_type, self._t["src_ids"], self._t["dst_ids"])
+            self._t["edge_ids"] = e.reshape(self._shape)
         return self._graph.lookup_edges(self._edge_type, self._t["src_ids"], self._t["edge_ids"],
                                         src_vids=self._t.get("src_vids"))
 

@@ -314,6 +314,25 @@ class Graph(object):
             return V_.Nodes(ids, node_type, shape=shape, graph=self)
         return V_.SparseNodes(ids, offsets, shape, node_type, graph=self)
 
+    def find_edge_ids(self, edge_type, src_ids, dst_ids):
+        """edge id of every (src, dst) pair (first match in the source's adjacency row, -1 when the edge does not
+        exist).  The reference cannot look up attributes of edges given only by their end points; this resolves
+        them with one full-row fetch + match (collective on the portable multi-rank path)."""
+        csr = self._csr(edge_type)
+        s = _as_tensor(src_ids, self.device).reshape(-1)
+        d = _as_tensor(dst_ids, self.device).reshape(-1)
+        sv = self._table(csr.src_type).idmap.to_vid(s)
+        dv = self._table(csr.dst_type).idmap.to_vid(d)
+        vals, eids, offs = S.sample_full(csr, sv, cap=0, want_eids=True)
+        counts = offs[1:] - offs[:-1]
+        seg = torch.repeat_interleave(torch.arange(s.numel(), device=self.device), counts)
+        hit = vals == dv[seg]
+        out = torch.full((s.numel(),), -1, dtype=torch.int64, device=self.device)
+        # first match wins: scatter in reverse order so that earlier positions overwrite later ones
+        idx = torch.nonzero(hit).flatten().flip(0)
+        out[seg[idx]] = eids[idx]
+        return out
+
     def get_edges(self, edge_type, src_ids, dst_ids, edge_ids=None, offsets=None, shape=None):
         st, dt = self._topology.get_src_type(edge_type), self._topology.get_dst_type(edge_type)
         if offsets is None:

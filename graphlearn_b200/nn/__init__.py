@@ -3,7 +3,7 @@ torch Modules, with the GraphSAGE layer on the fused sm_100a kernel."""
 from . import loss  # noqa: F401
 from .conv import (EgoGATConv, EgoGINConv, EgoLayer, EgoRGCNConv, EgoSAGEConv, EgoTGATConv,  # noqa: F401
                    TimeEncoder)
-from .norm import compute_saint_norm  # noqa: F401
+from .norm import compute_norm, compute_saint_norm  # noqa: F401
 from .data import BatchGraph, Data, EgoGraph, HeteroBatchGraph, TemporalGraph  # noqa: F401
 from .dataset import Batch, Dataset, PyGDataLoader, SubGraphData, TorchDataset  # noqa: F401
 from .embedding import ShardedEmbedding  # noqa: F401

@@ -414,3 +414,19 @@ def test_gsl_where_depends_on_sibling_branch(tmp_path):
     neg, dst = r["neg"].ids, r["dst"].ids
     assert neg.shape == (10, 5) and (neg % 4 == (dst % 4)[:, None]).all()
     assert not (neg == dst[:, None]).any()
+
+
+def test_get_edges_by_endpoints_and_saint_norm(g):
+    """`g.get_edges(etype, src, dst)` without edge ids resolves them from the adjacency rows (missing edge -> defaults);
+    `nn.compute_norm` consumes a subgraph sampler like the reference's compute_norm."""
+    adj = fx.u2i_adj()
+    src = np.array([3, 3, 7, 9])
+    dst = np.array([adj[3][0][0], adj[3][1][0], adj[7][0][0], 59 if 59 not in [x[0] for x in adj[9]] else 58])
+    e = g.get_edges("buy", src, dst)
+    assert np.allclose(e.weights[:3], [adj[3][0][1], adj[3][1][1], adj[7][0][1]])
+    assert e.edge_ids[3] == -1 and e.weights[3] == gl.get_config().default_weight
+    from graphlearn_b200 import nn as glnn
+    node_norm, edge_norm = glnn.compute_norm(fx.N_ITEM, sum(g.get_stats()["sim"]), g.subgraph_sampler("item", "sim", batch_size=12),
+                                             sample_coverage=3)
+    assert node_norm.shape == (fx.N_ITEM,) and edge_norm.shape == (sum(g.get_stats()["sim"]),)
+    assert float(node_norm.min()) > 0 and float(edge_norm.max()) <= 1e4
