@@ -342,3 +342,18 @@ def test_multival_token_hash_is_process_independent():
     outs = {subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONHASHSEED=str(s))).stdout.strip()
             for s in (1, 2)}
     assert outs == {"%d %d" % (_hash_token("brand_42"), _hash_token(""))}
+
+
+def test_stall_detector_fires_once_and_rearms():
+    import time
+    from graphlearn_b200.utils.watchdog import StallDetector
+    hits = []
+    sd = StallDetector(timeout_s=0.15, on_stall=lambda idle: hits.append(idle), poll_s=0.02).start()
+    for _ in range(5):                       # a healthy loop never trips it
+        time.sleep(0.05); sd.tick()
+    assert hits == []
+    time.sleep(0.4)                          # a hang does, exactly once
+    assert len(hits) == 1 and hits[0] > 0.15
+    sd.tick(); time.sleep(0.4)               # re-armed by the next step
+    assert len(hits) == 2
+    sd.stop()
