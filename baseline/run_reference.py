@@ -69,7 +69,9 @@ def main(args):
         dist.barrier()
     gen_s = time.time() - t0
     # ---- the reference engine lives in its own interpreter (see ref_sampler.py for why)
-    base_port = int(os.environ.get("MASTER_PORT", "29500")) + 211
+    # ports of the reference servers: derived from MASTER_PORT (unique per job), kept inside 30000-50007 whatever
+    # the launcher chose, and never equal to MASTER_PORT itself
+    base_port = 30000 + (int(os.environ.get("MASTER_PORT", "29500")) + 211) % 20000
     hosts = ",".join("127.0.0.1:%d" % (base_port + r) for r in range(world)) if world > 1 else ""
     child = subprocess.Popen(common + ["--rank", str(rank), "--world", str(world), "--tracker", tracker,
                                        "--hosts", hosts],
