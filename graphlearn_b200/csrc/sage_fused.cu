@@ -795,6 +795,219 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_async_kernel(const Sag
 }
 
 // ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL (gather_mode = 5, not measured in round 1 - see DESIGN.md "Round-2 plan"): the same tile with
+// TWO resident CTAs per SM.  ncu shows the default kernel at 23 % of the copy roofline with 40 % long-scoreboard
+// and 25 % barrier stalls: one 1024-thread CTA per SM serialises id staging -> gather -> MMA -> epilogue, and
+// while it is outside the gather no loads are in flight on that SM.  Here the CTA has 512 threads and keeps only
+// the A tile (nkb x 16 KB) plus a 2-deep ring of W slices of kNS = 32 output columns (nkb x 4 KB each) in
+// shared memory (<= ~110 KB for K = 256), so two CTAs fit and their phases interleave.  Thread 0 streams the W
+// slices with bulk copies and issues M128 x N32 x K16 MMAs slice by slice into disjoint TMEM column ranges
+// (2 x 256 columns for the two CTAs = the whole TMEM).  Every mbarrier has exactly one waiter (thread 0).
+// ---------------------------------------------------------------------------------------------
+constexpr int kOccThreads = 512;
+constexpr int kOccWarps = kOccThreads / 32;
+constexpr int kNS = 32;                 // output columns per W slice
+
+template <int U, int DT>
+__global__ void __launch_bounds__(kOccThreads, 2) sage_fused_occ2_kernel(const SageParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int k_total = p.kp_self + p.kp_nbr;
+  const int nkb = k_total >> 6;
+  const int n_slices_w = p.N / kNS;
+  uint8_t* sA = smem;
+  const uint32_t slice_kb_bytes = (uint32_t)kNS * 128u;                 // one k-block of one slice: 4 KB
+  const uint32_t slice_bytes = (uint32_t)nkb * slice_kb_bytes;
+  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);                      // ring: 2 slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 2 * (size_t)slice_bytes);
+  uint64_t* full = bars;                 // [2]
+  uint64_t* empty = bars + 2;            // [2]
+  uint64_t* bar_mma = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const char** sPtrN = reinterpret_cast<const char**>(bars + 8);        // [R * k]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    umma::mbar_init(full + 0, 1); umma::mbar_init(full + 1, 1);
+    umma::mbar_init(empty + 0, 1); umma::mbar_init(empty + 1, 1);
+    umma::mbar_init(bar_mma, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    umma::tmem_relinquish();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w_img);
+  const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;                     // one k-block of the FULL image
+  auto load_slice = [&](int s, int b) {                                 // thread 0 only
+    umma::mbar_arrive_expect_tx(full + b, slice_bytes);
+    for (int kb = 0; kb < nkb; ++kb)
+      umma::bulk_g2s(sW + (size_t)b * slice_bytes + (size_t)kb * slice_kb_bytes,
+                     wsrc + (size_t)kb * w_kb_bytes + (size_t)s * slice_kb_bytes, slice_kb_bytes, full + b);
+  };
+  if (tid == 0) {                        // the first two slices stream in behind the gather
+    load_slice(0, 0);
+    if (n_slices_w > 1) load_slice(1, 1);
+  }
+
+  // --- phase 0: ids -> row pointers (same as the default kernel)
+  constexpr int VEC = Chunk<DT>::kVec;
+  const int R = p.rows_per_cta;
+  const int m0 = blockIdx.x * R;
+  const int k = p.k;
+  const char** sPtrS = sPtrN + (size_t)R * k;
+  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
+  {
+    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+    const int64_t base = (int64_t)m0 * k;
+    const int64_t lim = (int64_t)p.M * k;
+    for (int i = tid; i < R * k; i += kOccThreads) {
+      const int64_t idx = base + i;
+      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr, nbr_row_bytes, p.zero_row) : p.zero_row;
+    }
+    for (int i = tid; i < R; i += kOccThreads) {
+      const int m = m0 + i;
+      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self, self_row_bytes, p.zero_row) : p.zero_row;
+    }
+  }
+  __syncthreads();
+
+  // --- phase 1: gather + aggregate -> A tile (identical math / layout to the default kernel)
+  {
+    const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
+    const int lanes_row = p.kp_nbr / VEC;
+    const int lpr = lanes_row < 32 ? lanes_row : 32;
+    const int lshift = 31 - __clz(lpr);
+    const int rpi = 32 >> lshift;
+    const int n_sl = lanes_row > 32 ? lanes_row >> 5 : 1;
+    const int row_groups = (R + rpi - 1) / rpi;
+    const int n_items = row_groups * n_sl;
+    const int sub = lane >> lshift;
+    const int lig = lane & (lpr - 1);
+    const bool has_self = p.kp_self > 0;
+    float scale = 1.f;
+    if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
+    else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
+    for (int item = warp; item < n_items; item += kOccWarps) {
+      const int rg = n_sl == 1 ? item : item / n_sl;
+      const int sl = n_sl == 1 ? 0 : item - rg * n_sl;
+      const int r = rg * rpi + sub;
+      if (r >= R) continue;
+      const int m = m0 + r;
+      const int chunk = lig + 32 * sl;
+      const int f0 = chunk * VEC;
+      const size_t coff = (size_t)chunk * 16;
+      float acc[VEC], sv[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
+      if (f0 < d_nbr) {
+        const char* const* ptrs = sPtrN + (size_t)r * k;
+        Chunk<DT> sraw;
+        const bool self_ld = need_self && f0 < d_self;
+        if (self_ld) sraw.load(sPtrS[r] + coff);
+        for (int j0 = 0; j0 < k; j0 += U) {
+          Chunk<DT> raw[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + u < k ? j0 + u : k - 1;
+            raw[u].load(ptrs[j] + coff);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (j0 + u < k) raw[u].add_to(acc);
+        }
+        if (self_ld) sraw.add_to(sv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          if (f0 + i >= d_self) sv[i] = 0.f;
+          if (f0 + i >= d_nbr) acc[i] = 0.f;
+        }
+      } else if (need_self && f0 < d_self) {
+        Chunk<DT> sraw;
+        sraw.load(sPtrS[r] + coff);
+        sraw.add_to(sv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) if (f0 + i >= d_self) sv[i] = 0.f;
+      }
+      const size_t a_off = (size_t)m * k_total;
+      __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
+      if (has_self) put_chunk<VEC>(sA, asave, a_off, r, f0, sv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
+      put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
+    }
+  }
+  umma::fence_proxy_async_smem();
+  __syncthreads();
+
+  // --- GEMM: slice s of W (kNS output columns) x the whole A tile -> TMEM columns [s*kNS, (s+1)*kNS)
+  if (tid == 0) {
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::make_idesc_bf16(kTileM, kNS);
+    for (int s = 0; s < n_slices_w; ++s) {
+      const int b = s & 1;
+      umma::mbar_wait(full + b, (uint32_t)((s >> 1) & 1));
+      umma::tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
+        const uint32_t b_base = umma::smem_u32(sW + (size_t)b * slice_bytes + (size_t)kb * slice_kb_bytes);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma::mma_bf16_ss(tmem_base + (uint32_t)(s * kNS), umma::make_desc_sw128(a_base + k4 * 32),
+                            umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
+      }
+      umma::mma_commit(empty + b);                       // buffer b is free once these MMAs have read it
+      if (s >= 1 && s + 1 < n_slices_w) {                 // refill the buffer slice s-1 used with slice s+1
+        const int pb = (s - 1) & 1;
+        umma::mbar_wait(empty + pb, (uint32_t)(((s - 1) >> 1) & 1));
+        load_slice(s + 1, pb);
+      }
+    }
+    umma::mma_commit(bar_mma);
+  }
+  __syncwarp();
+  umma::mbar_wait(bar_mma, 0);
+  umma::tc_fence_after();
+
+  // --- epilogue: 16 warps = 4 TMEM lane quarters x 4 column groups
+  {
+    const int q = warp & 3, g = warp >> 2;
+    const int cols_per_group = p.N / 4;                   // multiple of 16 (N is a multiple of 64)
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = row < R && m < p.M;
+    for (int c0 = 0; c0 < cols_per_group; c0 += 16) {
+      const int n0 = g * cols_per_group + c0;
+      uint32_t v[16];
+      umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
+      umma::tmem_ld_wait();
+      if (row_ok && n0 < p.n_out) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (n0 + i >= p.n_out) continue;
+          float x = __uint_as_float(v[i]);
+          if (p.bias) x += __ldg(p.bias + n0 + i);
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)m * p.out_stride + n0 + i] = __float2bfloat16(x);
+          else reinterpret_cast<float*>(p.out)[(size_t)m * p.out_stride + n0 + i] = x;
+        }
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Split path, stage 1 (used when rows live on peer GPUs): a small, maximum-occupancy kernel
 // (256 threads, ~40 registers -> 48-64 resident warps per SM) that only gathers + aggregates and
 // writes the bf16 A matrix [M, K_total] = [ self || agg(nbrs) ] (zero K-padding included).  NVLink
@@ -1076,6 +1289,34 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
   auto stream = at::cuda::getCurrentCUDAStream();
   const int u = k <= 4 ? 4 : (k % 5 == 0 || k > 12) ? 5 : 6;
   const int dt = p.tnbr.dtype;
+  if (gather_mode == 5) {
+    // EXPERIMENTAL two-CTA-per-SM variant (see sage_fused_occ2_kernel): falls through to the default kernel when
+    // the tile does not fit twice into an SM.
+    const size_t nkb5 = (size_t)k_total / 64;
+    const size_t base5 = nkb5 * (kTileM * 128) + 2 * nkb5 * (kNS * 128) + 64 + 1024;     // A + W ring + barriers + alignment
+    const int64_t per_wave = 148 * 2;
+    const int64_t waves5 = (M + per_wave * kTileM - 1) / (per_wave * kTileM);
+    int R5 = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, ((M + per_wave * waves5 - 1) / (per_wave * waves5) + 7) / 8 * 8));
+    if (rows_per_cta > 0) R5 = R;
+    const size_t limit5 = 112 * 1024;      // 2 x (dynamic + 1 KB static + 1 KB reserved) <= 228 KB per SM
+    while (R5 > 8 && base5 + (size_t)R5 * (k + 1) * 8 > limit5) R5 -= 8;
+    if (base5 + (size_t)R5 * (k + 1) * 8 <= limit5 && !p.debug_ts) {
+      const size_t smem5 = base5 + (size_t)R5 * (k + 1) * 8;
+      p.rows_per_cta = R5;
+      const unsigned grid5 = (unsigned)((M + R5 - 1) / R5);
+#define LAUNCH5(UU, DD)                                                                           \
+  do {                                                                                            \
+    C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_occ2_kernel<UU, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit5)); \
+    sage_fused_occ2_kernel<UU, DD><<<grid5, kOccThreads, smem5, stream>>>(p);                     \
+  } while (0)
+      if (dt == 0) { if (u == 4) LAUNCH5(4, 0); else if (u == 5) LAUNCH5(5, 0); else LAUNCH5(6, 0); }
+      else         { if (u == 4) LAUNCH5(4, 1); else if (u == 5) LAUNCH5(5, 1); else LAUNCH5(6, 1); }
+#undef LAUNCH5
+      C10_CUDA_KERNEL_LAUNCH_CHECK();
+      return {out, save_a ? a_save : at::Tensor()};
+    }
+    p.rows_per_cta = R;
+  }
   // MEASURED (2 GPUs, fp32 rows): fused register path 7.7k steps/s vs split 6.9k - the remote rows are
   // NVLink-bandwidth bound either way (394 GB/s achieved vs 580 GB/s best random-row rate), so the
   // split path stays opt-in.

@@ -1,6 +1,7 @@
 """GPU numerics / semantics tests: every sm_100a kernel against a plain PyTorch
 fp32 reference of the same op (run with ``pytest -m gpu`` on a B200)."""
 import math
+import os
 
 import pytest
 import torch
@@ -218,6 +219,32 @@ def test_sage_fused_store_numerics(rt, cfg):
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err < 0.03 * max(scale, 1.0), (err, scale)
+
+
+@pytest.mark.skipif(os.environ.get("GLB_EXPERIMENTAL", "0") != "1",
+                    reason="round-2 candidate kernel (two CTAs per SM); enable with GLB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("M,k,d,n_out", [(300, 10, 100, 256), (25600, 10, 100, 256), (1000, 25, 64, 128)])
+def test_sage_fused_occ2_matches_default(rt, M, k, d, n_out):
+    """EXPERIMENTAL gather_mode=5 (sage_fused_occ2_kernel) must reproduce the default kernel bit for bit
+    (same gather order, same MMA K order; only the N-slicing of W differs)."""
+    import graphlearn_b200 as gl
+    from graphlearn_b200.ops import sage as SG
+    from graphlearn_b200.store.shards import IdMap, NodeTable
+    n = 50000
+    g = torch.Generator(device=rt.device).manual_seed(1)
+    t = NodeTable(rt, "t", IdMap(rt, torch.arange(n, device=rt.device), dense=True))
+    t.set_float(torch.randn(n, d, device=rt.device, generator=g), torch.bfloat16)
+    sv = torch.randint(0, n, (M,), device=rt.device, generator=g)
+    nv = torch.randint(0, n, (M * k,), device=rt.device, generator=g)
+    w = torch.randn(n_out, 2 * d, device=rt.device, generator=g) / math.sqrt(2 * d)
+    b = torch.randn(n_out, device=rt.device, generator=g)
+    outs = []
+    for mode in (1, 5):
+        gl.set_sage_gather_mode(mode)
+        outs.append(SG.sage_layer(SG.pad_weight(w, d, d, "mean"), b, k=k, mode="mean", relu=True, out_bf16=True, self_table=t,
+                                  self_vids=sv, nbr_table=t, nbr_vids=nv).float())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())
 
 
 def test_sage_fused_dense_backward(rt):
