@@ -35,6 +35,10 @@ def test_public_api_two_ranks_cpu_gloo(tmp_path):
     _run(2, 29647, {"GLB_TEST_DEVICE": "cpu", "CUDA_VISIBLE_DEVICES": ""}, "dist_api_worker.py", [d], "DIST_API_OK")
 
 
+def test_sharded_embedding_two_ranks_cpu_gloo():
+    _run(2, 29650, {"CUDA_VISIBLE_DEVICES": ""}, "dist_embedding_worker.py", [], "EMB_OK 1")
+
+
 def test_data_parallel_example_two_ranks_cpu_gloo():
     """examples/train_gcn_sparse.py under torchrun: masks + full neighbourhoods + generic Trainer (flat gradients,
     all-reduce, lock-step epochs) - replicas must end with identical parameters."""
