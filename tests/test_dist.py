@@ -36,7 +36,7 @@ def test_public_api_two_ranks_cpu_gloo(tmp_path):
 
 
 def test_sharded_embedding_two_ranks_cpu_gloo():
-    _run(2, 29650, {"CUDA_VISIBLE_DEVICES": ""}, "dist_embedding_worker.py", [], "EMB_OK 1")
+    _run(2, 29650, {"CUDA_VISIBLE_DEVICES": ""}, "dist_embedding_worker.py", [], "EMB_ALL_OK")
 
 
 def test_data_parallel_example_two_ranks_cpu_gloo():
