@@ -26,7 +26,7 @@ from .. import config as _config
 from ..data.decoder import Decoder
 from ..parallel import partition as part
 from ..parallel.runtime import Runtime, native
-from .shards import CsrShard, IdMap, NodeTable
+from .shards import CsrShard, IdMap, NodeTable, sorted_unique
 
 ORIGIN, REVERSED = 0, 1
 
@@ -197,7 +197,7 @@ class GraphStore(object):
                     d["a"], d["b"] = d["b"], d["a"]
                 dst_own = None
                 if s.kind == "edge":
-                    ub = torch.unique(d["b"])
+                    ub = sorted_unique(d["b"])
                     dst_own = part.shuffle_rows({"a": ub}, ub.abs() % W, W, dev)["a"]
                 return part.shuffle_rows(d, d[key].abs() % W, W, dev), dst_own
             d = _load_source(s)

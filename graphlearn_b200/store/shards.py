@@ -33,6 +33,20 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def sorted_unique(ids: torch.Tensor) -> torch.Tensor:
+    """``torch.unique(ids)`` (sorted) without the sort when the id space is reasonably dense: a presence bitmap
+    + ``nonzero`` is O(n) and ~5x faster on 10^8 edge end points (the sort-based unique dominated the CPU build)."""
+    n = int(ids.numel())
+    if n < (1 << 20):
+        return torch.unique(ids)
+    lo, hi = int(ids.min().item()), int(ids.max().item())
+    if lo < 0 or hi >= 8 * n:
+        return torch.unique(ids)
+    present = torch.zeros(hi + 1, dtype=torch.bool, device=ids.device)
+    present[ids] = True
+    return present.nonzero().flatten()
+
+
 class IdMap:
     """global id <-> vid for one node type."""
 
@@ -46,7 +60,7 @@ class IdMap:
     @staticmethod
     def build(rt: Runtime, local_ids: torch.Tensor) -> "IdMap":
         """`local_ids`: unique ids owned by this rank (any order)."""
-        local_ids = torch.unique(local_ids)     # sorted
+        local_ids = sorted_unique(local_ids)
         n = int(local_ids.numel())
         W = rt.world
         # dense iff the owned ids are exactly {rank, rank+W, rank+2W, ...}
@@ -339,7 +353,7 @@ class CsrShard:
         if int_attrs is not None and int_attrs.numel() > 0:
             self.int_dim = int(int_attrs.size(1))
             self.int_attrs = rt.symm_from(int_attrs[order].to(torch.int64))
-        self.dst_ids_unique = torch.unique(self.indices.local) if E > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
+        self.dst_ids_unique = sorted_unique(self.indices.local) if E > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
         self._make_desc()
         return self
 
