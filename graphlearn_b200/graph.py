@@ -264,13 +264,33 @@ class Graph(object):
         return out
 
     def _lookup_strings(self, tab, vids):
-        W = self._rt.world
-        if W > 1:
-            raise errors.UnimplementedError("string attributes are host side and only served by the owning rank")
-        rows = torch.div(vids, W, rounding_mode="floor").cpu().numpy()
-        ok = (vids >= 0).cpu().numpy() & (rows < tab.n_local)
-        arr = np.full((len(rows), tab.str_dim), _config.get().default_string_attribute, dtype=object)
-        arr[ok] = tab.strings[rows[ok]]
+        """String attributes live on the HOST of the owning rank.  One rank: direct indexing.  Several ranks: a
+        request / response exchange of pickled lists (two ``all_gather_object`` rounds - the reference ships strings
+        inside its LookupNodes protobuf responses); collective, every rank must call it."""
+        W, r = self._rt.world, self._rt.rank
+        default = _config.get().default_string_attribute
+        v = vids.reshape(-1).cpu().numpy()
+        arr = np.full((len(v), tab.str_dim), default, dtype=object)
+
+        def local_rows(req):
+            rows = req // W
+            ok = (req >= 0) & (rows < tab.n_local)
+            out = np.full((len(req), tab.str_dim), default, dtype=object)
+            if ok.any():
+                out[ok] = tab.strings[rows[ok]]
+            return out
+
+        if W == 1:
+            return local_rows(v)
+        owner = np.where(v >= 0, v % W, -1)
+        want = [v[owner == o] for o in range(W)]                      # ids I need from rank o
+        asked = self._rt.all_gather_object(want)                      # asked[q][o]: what rank q wants from rank o
+        answers = [local_rows(np.asarray(asked[q][r], dtype=np.int64)) for q in range(W)]
+        got = self._rt.all_gather_object(answers)                     # got[o][q]: rank o's answer to rank q
+        for o in range(W):
+            m = owner == o
+            if m.any():
+                arr[m] = got[o][r]
         return arr
 
     def lookup_edges(self, edge_type, src_ids, edge_ids, src_vids=None) -> V_.Edges:
@@ -300,11 +320,32 @@ class Graph(object):
             out._t["float_attrs"] = G.gather_any(rt, csr.float_attrs, key, fill=cfg.default_float_attribute)
         if dec.int_attr_num > 0 and csr.int_attrs is not None:
             out._t["int_attrs"] = G.gather_any(rt, csr.int_attrs, key, fill=cfg.default_int_attribute)
-        if dec.string_attr_num > 0 and getattr(csr, "strings", None) is not None and W == 1:
-            e = eid_t.reshape(-1).cpu().numpy()
-            arr = np.full((len(e), dec.string_attr_num), cfg.default_string_attribute, dtype=object)
-            ok = (e >= 0) & (e < len(csr.strings))
-            arr[ok] = csr.strings[e[ok]]
+        if dec.string_attr_num > 0 and (W > 1 or getattr(csr, "strings", None) is not None):
+            # edge strings sit on the host of the SOURCE's owner at position edge_id: key = eid * W + owner
+            kk = key.cpu().numpy()
+            n_str = dec.string_attr_num
+            strings = getattr(csr, "strings", None)
+
+            def local_rows(req):
+                e = req // W
+                out_ = np.full((len(req), n_str), cfg.default_string_attribute, dtype=object)
+                if strings is not None:
+                    ok = (req >= 0) & (e < len(strings))
+                    if ok.any():
+                        out_[ok] = np.asarray(strings, dtype=object).reshape(len(strings), -1)[e[ok]]
+                return out_
+
+            if W == 1:
+                arr = local_rows(kk)
+            else:
+                arr = np.full((len(kk), n_str), cfg.default_string_attribute, dtype=object)
+                owner = np.where(kk >= 0, kk % W, -1)
+                asked = rt.all_gather_object([kk[owner == o] for o in range(W)])
+                got = rt.all_gather_object([local_rows(np.asarray(asked[q][rt.rank], dtype=np.int64)) for q in range(W)])
+                for o in range(W):
+                    m = owner == o
+                    if m.any():
+                        arr[m] = got[o][rt.rank]
             out._t["string_attrs"] = arr
         return out
 

@@ -50,8 +50,15 @@ class QueryExecutor(object):
         self._iter: Optional[SeedIterator] = None
         self._order = self._toposort()
         self._salt = 0
-        if sync_epoch is None:      # auto: on whenever the sampling ops of this run are collectives
-            sync_epoch = self.rt.world > 1 and not (self.rt.is_cuda and _config.get().use_peer_kernels)
+        if sync_epoch is None:
+            # auto: on whenever the ops of this query are collectives - always on the portable path; on the peer
+            # kernel path only id translation of non-dense id spaces and host-side string attributes are
+            collective = not (self.rt.is_cuda and _config.get().use_peer_kernels)
+            for tab in self.store.nodes.values():
+                collective = collective or tab.strings is not None or not tab.idmap.dense
+            for csr in self.store.edges.values():
+                collective = collective or getattr(csr, "strings", None) is not None
+            sync_epoch = self.rt.world > 1 and collective
         self.sync_epoch = bool(sync_epoch) and self.rt.world > 1
 
     # ------------------------------------------------------------------ plan

@@ -16,7 +16,7 @@ def main():
     dev = "cpu" if os.environ.get("GLB_TEST_DEVICE", "") == "cpu" else None
     g = gl.Graph()
     g.node(os.path.join(d, "user.tsv"), "user",
-           decoder=gl.Decoder(weighted=True, labeled=True, attr_types=["int", "int", ("string", 16), "float"]))
+           decoder=gl.Decoder(weighted=True, labeled=True, attr_types=["int", "int", "string", "float"]))
     g.node(os.path.join(d, "item_parts"), "item", decoder=gl.Decoder(attr_types=["float"] * 4))   # directory source
     g.edge(os.path.join(d, "u2i.tsv"), ("user", "item", "buy"), decoder=gl.Decoder(weighted=True))
     g.edge(os.path.join(d, "i2i.tsv"), ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
@@ -33,6 +33,7 @@ def main():
     n = g.lookup_nodes("user", ids)
     assert np.allclose(n.weights, 1.0 + ids) and (n.labels == ids % 3).all()
     assert np.allclose(n.float_attrs[:, 0], ids / 2.0) and (n.int_attrs[:, 0] == ids).all()
+    assert list(n.string_attrs[:, 0]) == ["u%d" % i for i in ids]          # host-side strings of REMOTE owners too
     it = g.lookup_nodes("item", np.arange(fx.N_ITEM))
     assert np.allclose(it.float_attrs[:, 1], np.arange(fx.N_ITEM) + 0.25)
     # neighbour sampling from seeds on any rank
