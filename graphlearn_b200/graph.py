@@ -264,34 +264,7 @@ class Graph(object):
         return out
 
     def _lookup_strings(self, tab, vids):
-        """String attributes live on the HOST of the owning rank.  One rank: direct indexing.  Several ranks: a
-        request / response exchange of pickled lists (two ``all_gather_object`` rounds - the reference ships strings
-        inside its LookupNodes protobuf responses); collective, every rank must call it."""
-        W, r = self._rt.world, self._rt.rank
-        default = _config.get().default_string_attribute
-        v = vids.reshape(-1).cpu().numpy()
-        arr = np.full((len(v), tab.str_dim), default, dtype=object)
-
-        def local_rows(req):
-            rows = req // W
-            ok = (req >= 0) & (rows < tab.n_local)
-            out = np.full((len(req), tab.str_dim), default, dtype=object)
-            if ok.any():
-                out[ok] = tab.strings[rows[ok]]
-            return out
-
-        if W == 1:
-            return local_rows(v)
-        owner = np.where(v >= 0, v % W, -1)
-        want = [v[owner == o] for o in range(W)]                      # ids I need from rank o
-        asked = self._rt.all_gather_object(want)                      # asked[q][o]: what rank q wants from rank o
-        answers = [local_rows(np.asarray(asked[q][r], dtype=np.int64)) for q in range(W)]
-        got = self._rt.all_gather_object(answers)                     # got[o][q]: rank o's answer to rank q
-        for o in range(W):
-            m = owner == o
-            if m.any():
-                arr[m] = got[o][r]
-        return arr
+        return tab.lookup_strings(vids, _config.get().default_string_attribute)
 
     def lookup_edges(self, edge_type, src_ids, edge_ids, src_vids=None) -> V_.Edges:
         csr = self._csr(edge_type)

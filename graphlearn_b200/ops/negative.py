@@ -224,13 +224,16 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
             # string attributes live on the host of the owning rank: factorise the local column and the
             # positives' values into integer codes, then reuse the sorted-run index below
             import numpy as np
-            if tab.strings is None or rt.world > 1:
-                slot += n_slots        # remote string lookups are not routed: slots keep base-strategy draws
-                continue
-            col = np.asarray(tab.strings[:, c], dtype=object)
-            uniq, codes = np.unique(col.astype(str), return_inverse=True)
-            local_vals = torch.as_tensor(codes, device=dev).long()
-            dstv = local_vals[torch.div(dst_v, rt.world, rounding_mode="floor").clamp(min=0, max=max(local_vals.numel() - 1, 0))]
+            if tab.str_dim == 0:
+                raise ValueError("conditional negative sampling: node type %r has no string attributes" % (csr.dst_type,))
+            # factorise the LOCAL column and the positives' values (fetched from their owners) with one shared
+            # vocabulary, then reuse the sorted-run index below
+            col = np.asarray(tab.strings[:, c], dtype=object).astype(str) if tab.strings is not None and tab.n_local else \
+                np.zeros(0, dtype=str)
+            want = tab.lookup_strings(dst_v, cfg.default_string_attribute)[:, c].astype(str)
+            vocab, codes = np.unique(np.concatenate([col, want]), return_inverse=True)
+            local_vals = torch.as_tensor(codes[:len(col)], device=dev).long()
+            dstv = torch.as_tensor(codes[len(col):], device=dev).long()
         elif kind == "int":
             if tab.ints is None:
                 raise ValueError("conditional negative sampling: node type %r has no int attributes" % (csr.dst_type,))

@@ -249,6 +249,36 @@ class NodeTable:
             self.feat_desc = make_table_desc(self.rt.world, self.float_dim, int(st.local.size(1)), st.local.dtype,
                                              st.nrows, st.ptrs)
 
+    def lookup_strings(self, vids: torch.Tensor, default: str = ""):
+        """[n, str_dim] object array of the string attributes of `vids`.  Strings live on the HOST of the owning
+        rank: one rank = direct indexing; several ranks = request / response exchange of pickled lists (two
+        ``all_gather_object`` rounds - the reference ships strings inside its LookupNodes protobuf responses).
+        Collective when world > 1."""
+        import numpy as np
+        W, r = self.rt.world, self.rt.rank
+        v = vids.reshape(-1).cpu().numpy()
+
+        def local_rows(req):
+            rows = req // W
+            out = np.full((len(req), self.str_dim), default, dtype=object)
+            if self.strings is not None:
+                ok = (req >= 0) & (rows < self.n_local)
+                if ok.any():
+                    out[ok] = self.strings[rows[ok]]
+            return out
+
+        if W == 1:
+            return local_rows(v)
+        arr = np.full((len(v), self.str_dim), default, dtype=object)
+        owner = np.where(v >= 0, v % W, -1)
+        asked = self.rt.all_gather_object([v[owner == o] for o in range(W)])   # asked[q][o]: rank q wants from rank o
+        got = self.rt.all_gather_object([local_rows(np.asarray(asked[q][r], dtype=np.int64)) for q in range(W)])
+        for o in range(W):
+            m = owner == o
+            if m.any():
+                arr[m] = got[o][r]
+        return arr
+
     def _set_symm(self, name, x: torch.Tensor):
         st = self.rt.symm_empty(tuple(x.shape), x.dtype)
         st.local.copy_(x)
