@@ -1,5 +1,5 @@
 """Coordinator duties that survive without Kafka / k8s (D12): periodic + on-demand checkpoints with
-retention (``SubServiceCheckpointManager``, python/coordinator/checkpoint.py:135-241) and global
+retention (``SubServiceCheckpointManager``, dynamic_graph_service/python/coordinator/checkpoint.py:135-241) and global
 barriers over the ingest stream (``GlobalBarrierMonitor``, barrier.py:85-168: a barrier is released
 once every record produced BEFORE it has been applied - here: once the ingested-record counter
 reaches the value captured when the barrier was set)."""

@@ -1,7 +1,8 @@
 """K7: dense ``act(x W^T + b)`` on the tcgen05 / TMEM tile kernel (``csrc/sage_fused.cu``,
 A staged from global memory).  Used by the non-SAGE layers (GAT / GIN / RGCN projections) when
 the shapes fit one tile (K <= 512, out <= 256); otherwise - and on CPU - it is ``F.linear``.
-Backward = two plain library GEMMs."""
+Backward = two plain library GEMMs.
+Reference counterpart: the dense layers of graphlearn/python/nn/tf/layers/linear_layer.py used by every conv."""
 from __future__ import annotations
 
 from typing import Optional

@@ -5,7 +5,9 @@ relabel primitive (K4).
 GCNConv (w = D^-1/2 A D^-1/2 entries), SAGEConv (w = None) and GATConv (w = attention) in ONE kernel
 (csrc/graph_ops.cu edge_scatter_kernel: gather x weight -> float4 ``red.global.add`` atomics) instead of
 gather -> multiply -> index_add.  Differentiable: d/dx is the same kernel with row/col swapped, d/dw is
-the per-edge dot product kernel.  CPU tensors use the equivalent torch ops (oracle for the tests)."""
+the per-edge dot product kernel.  CPU tensors use the equivalent torch ops (oracle for the tests).
+Reference ops replaced: graphlearn/python/nn/tf/layers/{gcn,sage,gat}_conv.py (gather + segment_sum / softmax) and
+the host-side id->index maps of nn/pytorch/data/pyg_dataloader.py:56-64."""
 from __future__ import annotations
 
 from typing import Optional
