@@ -348,12 +348,12 @@ def test_stall_detector_fires_once_and_rearms():
     import time
     from graphlearn_b200.utils.watchdog import StallDetector
     hits = []
-    sd = StallDetector(timeout_s=0.15, on_stall=lambda idle: hits.append(idle), poll_s=0.02).start()
+    sd = StallDetector(timeout_s=0.6, on_stall=lambda idle: hits.append(idle), poll_s=0.05).start()
     for _ in range(5):                       # a healthy loop never trips it
         time.sleep(0.05); sd.tick()
     assert hits == []
-    time.sleep(0.4)                          # a hang does, exactly once
-    assert len(hits) == 1 and hits[0] > 0.15
-    sd.tick(); time.sleep(0.4)               # re-armed by the next step
+    time.sleep(1.5)                          # a hang does, exactly once
+    assert len(hits) == 1 and hits[0] > 0.6
+    sd.tick(); time.sleep(1.5)               # re-armed by the next step
     assert len(hits) == 2
     sd.stop()
