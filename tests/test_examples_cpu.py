@@ -14,6 +14,10 @@ def _run(name, *args, **kw):
     if EX not in sys.path:
         sys.path.insert(0, EX)
     mod = importlib.import_module(name)
+    import numpy as np
+    import torch
+    torch.manual_seed(0)                  # model initialisation: deterministic thresholds below
+    np.random.seed(0)
     return mod.main(*args, **kw)
 
 
