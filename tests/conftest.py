@@ -13,7 +13,9 @@ def pytest_configure(config):
 
 @pytest.fixture(autouse=True)
 def _fresh_config():
+    import torch
     from graphlearn_b200 import config
     config.reset()
+    torch.manual_seed(0)            # model initialisations inside tests are reproducible (learning thresholds)
     yield
     config.reset()
