@@ -11,7 +11,8 @@ from graphlearn_b200 import models
 from graphlearn_b200.nn.data import Data
 
 
-def main(steps=40, device=None):
+def main(steps=40, device=None, conv="sage"):
+    """conv="gat": the Taobao-shaped config (2-layer, 4-head bipartite GAT, weighted sampling, in-batch negatives)."""
     d = write_bipartite(tempfile.mkdtemp())
     g = gl.Graph() \
         .node(d + "/user.tsv", "u", decoder=gl.Decoder(attr_types=["float"] * 8)) \
@@ -25,7 +26,7 @@ def main(steps=40, device=None):
         e.inV().alias("i").outV("u2i_reverse").sample(4).by("random").alias("i1")
          .outV("u2i").sample(3).by("edge_weight").alias("i2"))).values()
     ds = gl.Dataset(q)
-    model = models.EgoBipartiteSAGE(8, 8, 32, 16, hops=2).to(g.device)
+    model = models.EgoBipartiteSAGE(8, 8, 32, 16, hops=2, conv=conv, num_head=4).to(g.device)
     opt = torch.optim.Adam(model.parameters(), lr=5e-3)
     f = lambda v: Data.from_values(v).floats  # noqa: E731
     first = last = None
@@ -45,4 +46,5 @@ def main(steps=40, device=None):
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(conv="gat" if "--gat" in sys.argv else "sage")

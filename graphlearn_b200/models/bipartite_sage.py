@@ -10,13 +10,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..nn.conv import EgoSAGEConv
+from ..nn.conv import EgoGATConv, EgoSAGEConv
 from ..nn.loss import sigmoid_cross_entropy_loss, unsupervised_softmax_cross_entropy_loss
 
 
 class _Tower(nn.Module):
-    def __init__(self, dims_by_hop: Sequence[int], hidden: int, out: int, agg="mean"):
+    def __init__(self, dims_by_hop: Sequence[int], hidden: int, out: int, agg="mean", conv="sage", num_head=4):
         super().__init__()
+        self.conv_kind = conv
         L = len(dims_by_hop) - 1
         self.L = L
         convs = []
@@ -25,7 +26,9 @@ class _Tower(nn.Module):
             for i in range(L - l):
                 d_self = dims_by_hop[i] if l == 0 else hidden
                 d_nbr = dims_by_hop[i + 1] if l == 0 else hidden
-                row.append(EgoSAGEConv((d_self, d_nbr), out if l == L - 1 else hidden, agg))
+                o = out if l == L - 1 else hidden
+                row.append(EgoSAGEConv((d_self, d_nbr), o, agg) if conv == "sage" else
+                           EgoGATConv((d_self, d_nbr), o, num_head))
             convs.append(row)
         self.convs = nn.ModuleList(convs)
 
@@ -33,17 +36,25 @@ class _Tower(nn.Module):
         h = list(xs)
         for l in range(self.L):
             last = l == self.L - 1
-            h = [self.convs[l][i](h[i], h[i + 1], expands[i], relu=not last) for i in range(self.L - l)]
+            if self.conv_kind == "sage":
+                h = [self.convs[l][i](h[i], h[i + 1], expands[i], relu=not last) for i in range(self.L - l)]
+            else:
+                h = [self.convs[l][i](h[i], h[i + 1], expands[i]) for i in range(self.L - l)]
+                if not last:
+                    h = [F.elu(t) for t in h]
         return h[0].float()
 
 
 class EgoBipartiteSAGE(nn.Module):
-    def __init__(self, user_dim: int, item_dim: int, hidden: int, out: int, hops: int = 2, agg="mean"):
+    def __init__(self, user_dim: int, item_dim: int, hidden: int, out: int, hops: int = 2, agg="mean", conv="sage",
+                 num_head=4):
+        """conv = "sage" (EgoSAGEConv) or "gat" (EgoGATConv with `num_head` averaged heads - the 2-layer 4-head
+        bipartite GAT of the Taobao-shaped benchmark config)."""
         super().__init__()
         u_dims = [user_dim if i % 2 == 0 else item_dim for i in range(hops + 1)]
         i_dims = [item_dim if i % 2 == 0 else user_dim for i in range(hops + 1)]
-        self.user_tower = _Tower(u_dims, hidden, out, agg)
-        self.item_tower = _Tower(i_dims, hidden, out, agg)
+        self.user_tower = _Tower(u_dims, hidden, out, agg, conv, num_head)
+        self.item_tower = _Tower(i_dims, hidden, out, agg, conv, num_head)
 
     def forward(self, user_ego, item_ego, expands_u, expands_i):
         return self.user_tower(user_ego, expands_u), self.item_tower(item_ego, expands_i)

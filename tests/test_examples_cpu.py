@@ -60,6 +60,11 @@ def test_bipartite_sage():
     assert last < first
 
 
+def test_bipartite_gat_4head():
+    first, last = _run("bipartite_sage", steps=25, device="cpu", conv="gat")
+    assert last < first
+
+
 def test_seal():
     out = _run("seal_link_prediction", steps=15, device="cpu")
     assert out is None or out[1] <= out[0] * 1.05
