@@ -165,7 +165,7 @@ def run_ours(args):
     model = EgoGraphSAGE(shape["feat_dim"], HIDDEN, shape["num_classes"], 2).to(rt.device)
     Trainer = SageTrainer if args.engine == "autograd" else FastSageTrainer
     tr = Trainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
-                 use_cuda_graph=not args.no_graph, **({"gather_mode": args.gather_mode} if args.engine == "fast" else {}))
+                 use_cuda_graph=not args.no_graph)
     # host-side seed stream: each rank traverses (shuffled) its own nodes, like the reference's
     # V().batch().shuffle(traverse=True) root which is unsharded (node_getter.cc:64-92)
     gen = torch.Generator().manual_seed(1234 + rt.rank)
@@ -247,7 +247,7 @@ def run_ours(args):
                        "nvlink_random_row_ceiling_GBps": 477 if row_bytes <= 256 else 580,
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
                                     % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * (2 if fdt == torch.bfloat16 else 4) / 1e9),
-                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine, "gather_mode": args.gather_mode,
+                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine,
                        "graph_build_s": round(build_s, 2)},
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": args.batch * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -279,8 +279,6 @@ def main():
                     help="HBM storage dtype of the float attribute table (compute is bf16 either way; bf16 halves NVLink bytes)")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--gather-mode", type=int, default=0,
-                    help="fused SAGE kernel gather: 0 auto, 1 registers, 2 TMA ring, 3 cp.async ring, 4 split (gather kernel + GEMM)")
     ap.add_argument("--engine", default="fast", choices=["fast", "autograd"],
                     help="fast = hand-scheduled fwd/bwd kernel chain; autograd = torch.autograd over the same kernels")
     ap.add_argument("--feature-cache-rows", type=int, default=-1,

@@ -65,7 +65,6 @@ class Config:
     feature_dtype: str = "fp32"          # fp32 | bf16   storage dtype of float attribute tables in HBM
     loader_threads: int = 0           # 0 = auto: all cores divided by the number of ranks on the box
     use_peer_kernels: bool = True        # False -> torch.distributed (NCCL/gloo) baseline path
-    sage_gather_mode: int = int(os.environ.get("GLB_SAGE_GATHER_MODE", "0"))   # fused SAGE kernel: 0 auto, 1 register loads, 2 TMA ring
     seed: int = 0
     actor_enabled: bool = False
 
@@ -130,7 +129,6 @@ set_feature_dtype = _setter("feature_dtype", str)
 set_loader_threads = _setter("loader_threads", int)
 set_use_peer_kernels = _setter("use_peer_kernels", bool)
 set_seed = _setter("seed", int)
-set_sage_gather_mode = _setter("sage_gather_mode", int)
 
 
 # exact reference spellings (graphlearn/python/config.py:77,114,118)

@@ -5,7 +5,7 @@ namespace glb {
 // sampling.cu
 std::vector<at::Tensor> sample_neighbors(const at::Tensor&, const at::Tensor&, int64_t, int64_t, int64_t,
                                          const c10::optional<at::Tensor>&, bool, int64_t, int64_t,
-                                         const at::Tensor&, int64_t, bool);
+                                         const at::Tensor&, int64_t, bool, const c10::optional<at::Tensor>&);
 at::Tensor get_degrees(const at::Tensor&, const at::Tensor&, int64_t);
 std::vector<at::Tensor> sample_full(const at::Tensor&, const at::Tensor&, int64_t, bool);
 void rng_advance(const at::Tensor&, int64_t);
@@ -27,7 +27,23 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor&, const c10::optiona
                                            const c10::optional<at::Tensor>&, int64_t, int64_t, int64_t,
                                            const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t,
                                            bool, bool, bool, int64_t, const c10::optional<at::Tensor>&,
-                                           const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t);
+                                           const c10::optional<at::Tensor>&);
+void sage_fused_multi(const at::Tensor&, const at::Tensor&, const std::vector<c10::optional<at::Tensor>>&,
+                      const std::vector<c10::optional<at::Tensor>>&, const std::vector<int64_t>&, const std::vector<int64_t>&,
+                      const std::vector<int64_t>&, const std::vector<int64_t>&, const std::vector<at::Tensor>&,
+                      const std::vector<c10::optional<at::Tensor>>&, int64_t, const at::Tensor&,
+                      const c10::optional<at::Tensor>&, int64_t, int64_t, bool, bool, int64_t,
+                      const std::vector<c10::optional<at::Tensor>>&, int64_t, int64_t);
+int sm_count();
+void sage_set_debug_trace(const c10::optional<at::Tensor>&);
+void sage_set_max_ctas(int64_t);
+// sage_bwd.cu
+at::Tensor pack_weight_t(const at::Tensor&, int64_t, int64_t);
+void sage_bwd_dw(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, const std::vector<int64_t>&,
+                 const std::vector<int64_t>&, const std::vector<c10::optional<at::Tensor>>&,
+                 const std::vector<c10::optional<at::Tensor>>&, const std::vector<int64_t>&, const std::vector<double>&, int64_t,
+                 const c10::optional<at::Tensor>&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t,
+                 const std::vector<int64_t>&);
 // train_ops.cu
 void softmax_ce(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, const at::Tensor&,
                 const at::Tensor&, const c10::optional<at::Tensor>&);
@@ -44,9 +60,12 @@ int64_t ipc_open_handle(const std::string&, int64_t);
 void ipc_close_handle(int64_t, int64_t);
 at::Tensor tensor_from_ptr(int64_t, std::vector<int64_t>, int64_t, int64_t);
 void allreduce_oneshot(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, double);
+void copy_i64(const at::Tensor&, const at::Tensor&);
 void step_advance(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, int64_t);
 void adam_flat(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
                double, double, double, double, double);
+void adam_pack(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, double, double, double,
+               double, double, const c10::optional<at::Tensor>&, const at::Tensor&);
 // graph_ops.cu
 std::vector<at::Tensor> relabel(const at::Tensor&);
 at::Tensor relabel_lookup(const at::Tensor&, const at::Tensor&, const at::Tensor&);
@@ -75,6 +94,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sage_smem_bytes", &glb::sage_smem_bytes);
   m.def("pack_weight_sw128", &glb::pack_weight_sw128);
   m.def("sage_fused_forward", &glb::sage_fused_forward);
+  m.def("sage_fused_multi", &glb::sage_fused_multi);
+  m.def("sm_count", &glb::sm_count);
+  m.def("sage_set_debug_trace", &glb::sage_set_debug_trace);
+  m.def("sage_set_max_ctas", &glb::sage_set_max_ctas);
+  m.def("pack_weight_t", &glb::pack_weight_t);
+  m.def("sage_bwd_dw", &glb::sage_bwd_dw);
   m.def("pack_weight_f32", &glb::pack_weight_f32);
   m.def("tc_linear_forward", &glb::tc_linear_forward);
   m.def("softmax_ce", &glb::softmax_ce);
@@ -87,7 +112,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("tensor_from_ptr", &glb::tensor_from_ptr);
   m.def("allreduce_oneshot", &glb::allreduce_oneshot);
   m.def("step_advance", &glb::step_advance);
+  m.def("copy_i64", &glb::copy_i64);
   m.def("adam_flat", &glb::adam_flat);
+  m.def("adam_pack", &glb::adam_pack);
   m.def("relabel", &glb::relabel);
   m.def("relabel_lookup", &glb::relabel_lookup);
   m.def("edge_scatter", &glb::edge_scatter);

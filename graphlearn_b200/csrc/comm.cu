@@ -195,6 +195,152 @@ adam_flat_kernel(float* __restrict__ w, const float* __restrict__ g, float* __re
   }
 }
 
+// ---------------------------------------------------------------------------
+// Adam fused with everything the next step needs from the parameters (engine/fast_sage.py):
+//   * the gradient (and the scratch accumulators behind it) is zeroed in the same pass - no memset per step
+//   * every weight matrix is re-emitted as the bf16 SWIZZLE_128B K-major image the fused forward kernel feeds
+//     to tcgen05.mma (and, for layers >= 2, the image of W^T used by dA = dZ . W) - no pack kernels per step
+//   * the loss accumulated by the fused CE epilogue is moved to `loss_out` before it is cleared
+// One thread owns 8 consecutive parameters (parameter starts are 8-aligned in the flat buffer).
+// ---------------------------------------------------------------------------
+constexpr int kMaxPackMats = 8;
+struct PackMat {
+  long long off;          // first element in the flat buffer
+  int n_out, k_total;     // fp32 master [n_out, k_total]
+  int N;                  // rows of the forward image per k-block (padded n_out)
+  uint8_t* img;           // forward image: (k_total/64) k-blocks of [N x 64] bf16, SW128
+  uint8_t* img_t;         // W^T images (or null): [n_imgs][kpad_t/64 k-blocks][nrows_t x 64]
+  int kpad_t, nrows_t;
+};
+struct AdamPackParams {
+  float* w; float* g; float* m; float* v;
+  long long n;                       // parameters (multiple of 8)
+  const long long* step_ptr;
+  float lr, beta1, beta2, eps, weight_decay;
+  float* scratch; int n_scratch;     // accumulators behind the gradients (zeroed); scratch[0] = loss
+  float* loss_out;
+  PackMat mats[kMaxPackMats];
+  int n_mats;
+};
+
+__global__ void __launch_bounds__(64) adam_pack_kernel(const __grid_constant__ AdamPackParams p) {
+  const float step = (float)p.step_ptr[0];
+  const float bc1 = 1.f - powf(p.beta1, step);
+  const float bc2 = 1.f - powf(p.beta2, step);
+  const float step_size = p.lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (p.loss_out) p.loss_out[0] = p.scratch[0];
+    for (int i = 0; i < p.n_scratch; ++i) p.scratch[i] = 0.f;
+  }
+  const long long chunks = p.n >> 3;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (long long)gridDim.x * blockDim.x) {
+    const long long i0 = c << 3;
+    float w[8], g[8], m[8], v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 a = *reinterpret_cast<const float4*>(p.w + i0 + 4 * h), b = *reinterpret_cast<const float4*>(p.g + i0 + 4 * h);
+      const float4 cm = *reinterpret_cast<const float4*>(p.m + i0 + 4 * h), cv = *reinterpret_cast<const float4*>(p.v + i0 + 4 * h);
+      w[4 * h] = a.x; w[4 * h + 1] = a.y; w[4 * h + 2] = a.z; w[4 * h + 3] = a.w;
+      g[4 * h] = b.x; g[4 * h + 1] = b.y; g[4 * h + 2] = b.z; g[4 * h + 3] = b.w;
+      m[4 * h] = cm.x; m[4 * h + 1] = cm.y; m[4 * h + 2] = cm.z; m[4 * h + 3] = cm.w;
+      v[4 * h] = cv.x; v[4 * h + 1] = cv.y; v[4 * h + 2] = cv.z; v[4 * h + 3] = cv.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float gi = g[i];
+      if (p.weight_decay != 0.f) gi += p.weight_decay * w[i];
+      m[i] = p.beta1 * m[i] + (1.f - p.beta1) * gi;
+      v[i] = p.beta2 * v[i] + (1.f - p.beta2) * gi * gi;
+      w[i] -= step_size * m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + p.eps);
+    }
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(p.w + i0 + 4 * h) = make_float4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
+      *reinterpret_cast<float4*>(p.m + i0 + 4 * h) = make_float4(m[4 * h], m[4 * h + 1], m[4 * h + 2], m[4 * h + 3]);
+      *reinterpret_cast<float4*>(p.v + i0 + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+      *reinterpret_cast<float4*>(p.g + i0 + 4 * h) = z;
+    }
+    // ---- weight images
+    int mi = -1;
+#pragma unroll
+    for (int j = 0; j < kMaxPackMats; ++j)
+      if (j < p.n_mats && i0 >= p.mats[j].off && i0 < p.mats[j].off + (long long)p.mats[j].n_out * p.mats[j].k_total) mi = j;
+    if (mi >= 0) {
+      const PackMat& pm = p.mats[mi];
+      const int rel = (int)(i0 - pm.off);
+      const int n = rel / pm.k_total, kcol = rel - n * pm.k_total;      // kcol is a multiple of 8: one 16-byte chunk
+      uint4 val;
+      val.x = pack_bf16x2(w[0], w[1]); val.y = pack_bf16x2(w[2], w[3]); val.z = pack_bf16x2(w[4], w[5]); val.w = pack_bf16x2(w[6], w[7]);
+      const int kb = kcol >> 6, ch = (kcol & 63) >> 3;
+      const size_t off = (size_t)kb * pm.N * 128 + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)((ch ^ (n & 7)) * 16);
+      *reinterpret_cast<uint4*>(pm.img + off) = val;
+      if (pm.img_t) {
+        // W^T image: row = column of W (kcol + i), k index = n
+        const int nkb_t = pm.kpad_t >> 6;
+        const int kbt = n >> 6, cht = (n & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = kcol + i;
+          const int h = col / pm.nrows_t, r = col - h * pm.nrows_t;
+          const size_t o = ((size_t)h * nkb_t + kbt) * pm.nrows_t * 128 + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 +
+                           (size_t)((cht ^ (r & 7)) * 16) + (size_t)(n & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(pm.img_t + o) = __float2bfloat16(w[i]);
+        }
+      }
+    }
+  }
+}
+
+// mats: CPU int64 [n_mats, 8] = (off, n_out, k_total, N, img_ptr, img_t_ptr, kpad_t, nrows_t)
+void adam_pack(const at::Tensor& w, const at::Tensor& g_store, const at::Tensor& m, const at::Tensor& v, const at::Tensor& step,
+               double lr, double beta1, double beta2, double eps, double weight_decay, const c10::optional<at::Tensor>& loss_out,
+               const at::Tensor& mats) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.is_contiguous() && w.numel() % 8 == 0, "flat params must be padded to 8");
+  TORCH_CHECK(g_store.is_cuda() && g_store.scalar_type() == at::kFloat && g_store.numel() >= w.numel() && m.numel() == w.numel() && v.numel() == w.numel());
+  TORCH_CHECK(mats.device().is_cpu() && mats.scalar_type() == at::kLong && mats.dim() == 2 && mats.size(1) == 8 && mats.size(0) <= kMaxPackMats);
+  c10::cuda::CUDAGuard guard(w.device());
+  AdamPackParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.w = w.data_ptr<float>(); p.g = g_store.data_ptr<float>(); p.m = m.data_ptr<float>(); p.v = v.data_ptr<float>();
+  p.n = w.numel();
+  p.step_ptr = reinterpret_cast<const long long*>(step.data_ptr<int64_t>());
+  p.lr = (float)lr; p.beta1 = (float)beta1; p.beta2 = (float)beta2; p.eps = (float)eps; p.weight_decay = (float)weight_decay;
+  p.scratch = p.g + p.n; p.n_scratch = (int)(g_store.numel() - w.numel());
+  if (loss_out.has_value() && loss_out->defined()) { TORCH_CHECK(loss_out->is_cuda() && loss_out->scalar_type() == at::kFloat); p.loss_out = loss_out->data_ptr<float>(); }
+  p.n_mats = (int)mats.size(0);
+  const int64_t* d = mats.data_ptr<int64_t>();
+  for (int i = 0; i < p.n_mats; ++i) {
+    PackMat& pm = p.mats[i];
+    pm.off = d[8 * i]; pm.n_out = (int)d[8 * i + 1]; pm.k_total = (int)d[8 * i + 2]; pm.N = (int)d[8 * i + 3];
+    pm.img = reinterpret_cast<uint8_t*>(d[8 * i + 4]); pm.img_t = reinterpret_cast<uint8_t*>(d[8 * i + 5]);
+    pm.kpad_t = (int)d[8 * i + 6]; pm.nrows_t = (int)d[8 * i + 7];
+    TORCH_CHECK(pm.off % 8 == 0 && pm.k_total % 64 == 0, "weight matrices must start 8-aligned with K padded to 64");
+  }
+  if (p.n == 0) return;
+  // small blocks: the work is one 8-element chunk per thread, spread it over every SM
+  const int blocks = (int)std::min<int64_t>((int64_t)sm_count() * 16, ((p.n >> 3) + 63) / 64);
+  adam_pack_kernel<<<std::max(blocks, 1), 64, 0, at::cuda::getCurrentCUDAStream()>>>(p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// dst[i] = src[i] (int64); src may alias pinned host memory (UVA): the engine's seed staging copy
+__global__ void copy_i64_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+void copy_i64(const at::Tensor& dst, const at::Tensor& src) {
+  TORCH_CHECK(dst.is_cuda() && dst.scalar_type() == at::kLong && src.scalar_type() == at::kLong && dst.numel() == src.numel() &&
+              dst.is_contiguous() && src.is_contiguous());
+  c10::cuda::CUDAGuard guard(dst.device());
+  const int64_t n = dst.numel();
+  if (n == 0) return;
+  copy_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(dst.data_ptr<int64_t>(), src.data_ptr<int64_t>(), n);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
 void step_advance(const c10::optional<at::Tensor>& rng_state, const c10::optional<at::Tensor>& opt_step,
                   int64_t rng_inc) {
   uint64_t* rp = nullptr; long long* sp = nullptr;
@@ -215,7 +361,7 @@ void adam_flat(const at::Tensor& w, const at::Tensor& g, const at::Tensor& m, co
   c10::cuda::CUDAGuard guard(w.device());
   int64_t n = w.numel();
   if (n == 0) return;
-  int blocks = (int)std::min<int64_t>(148 * 4, (n + 255) / 256);
+  int blocks = (int)std::min<int64_t>((int64_t)sm_count() * 4, (n + 255) / 256);
   adam_flat_kernel<<<blocks, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
       w.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), n,
       reinterpret_cast<const long long*>(step.data_ptr<int64_t>()), (float)lr, (float)beta1, (float)beta2,

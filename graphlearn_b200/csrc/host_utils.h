@@ -5,6 +5,8 @@
 
 namespace glb {
 
+int sm_count();   // SMs of the current device (sage_fused.cu)
+
 inline void check_cuda_i64(const at::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
   TORCH_CHECK(t.scalar_type() == at::kLong, name, " must be int64");

@@ -1,99 +1,100 @@
-// K6+K7 fused: GraphSAGE / EgoSAGE layer forward in ONE kernel
+// K6+K7 fused: GraphSAGE / EgoSAGE layer forward as ONE persistent, warp-specialised kernel
 //
 //     out[m, :] = act( [ x_self[m] || agg_j x_nbr[m, j] ] . W^T + b )
 //
-// * gather + aggregate: 16 warps pull the self row and the k neighbour rows of
-//   128 destination nodes straight from the (peer-mapped) feature shards -
-//   local HBM or a remote GPU over NVLink, picked per row by vid % world -
-//   reduce them in fp32 registers and write the bf16 A tile into shared
-//   memory in the UMMA K-major SWIZZLE_128B canonical layout.  The rows never
-//   round-trip through HBM ("agg(X).W" instead of materialising [B*k, D]).
-// * weights: the pre-swizzled bf16 image of W is fetched by the TMA engine
-//   (cp.async.bulk -> UBLKCP) while the gather is in flight.
-// * GEMM: one elected thread issues tcgen05.mma (M=128, N<=256, K=16) with
-//   the fp32 accumulator in TMEM; completion is tracked with an mbarrier via
-//   tcgen05.commit.
-// * epilogue: tcgen05.ld -> bias -> ReLU -> bf16/fp32 store.
+// One CTA per SM stays resident and walks a static list of row tiles (<= 128 destination rows each)
+// that may span SEVERAL segments of the ego graph (e.g. seeds<-hop1 with k=25 and hop1<-hop2 with
+// k=10 of a 2-layer GraphSAGE): the tile height of every segment is chosen on the host so that all
+// tiles cost about the same number of row fetches and the tile count is a multiple of the SM count.
+// Inside the CTA the phases of a tile overlap instead of running back to back:
+//
+//   warps 9-31  gather        each warp owns work items (1-4 destination rows x one 512-byte slice): it
+//                             translates the item's ids into row pointers (local HBM, a peer GPU's HBM over
+//                             NVLink, or the local replica cache) in a private SMEM scratch - the ids of the
+//                             NEXT item are prefetched while the current rows are in flight -, pulls the self
+//                             row and the k neighbour rows with batches of 16-byte loads, reduces in fp32
+//                             registers and writes the bf16 A tile in the UMMA K-major SWIZZLE_128B layout
+//                             (and row-major to global for the backward pass); items are dealt round-robin
+//                             ACROSS tile boundaries so no warp idles
+//   warp 8      MMA           W image fetched ONCE per CTA by the TMA engine (cp.async.bulk); one
+//                             elected thread issues tcgen05.mma (M=128, N<=256, K=16) into one of two
+//                             TMEM accumulators; tcgen05.commit frees the A tile and publishes the
+//                             accumulator through mbarriers
+//   warps 0-7   epilogue      tcgen05.ld -> bias -> ReLU -> bf16/fp32 store of tile t while the gather
+//                             warps are already loading tile t+1; for the top layer a second, coalesced
+//                             phase (one warp per row, one lane per class) computes the softmax
+//                             cross-entropy loss, dlogits and the bias gradient (fused CE)
+//
+// The rows never round-trip through HBM ("agg(X).W" instead of materialising [B*k, D]).
 //
 // Math parity: EgoSAGEConv (graphlearn/python/nn/tf/layers/ego_sage_conv.py:71-106):
-// agg in {mean,sum} over neighbor.reshape(-1,k,d), out = W.[x || agg]; 'gcn'
-// = mean over {x} U nbrs then W.
+// agg in {mean,sum} over neighbor.reshape(-1,k,d), out = W.[x || agg]; 'gcn' = mean over {x} U nbrs
+// then W.  Loss parity: graphlearn/python/nn/tf/loss.py (softmax cross entropy).
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <cfloat>
 #include <cstring>
 #include "host_utils.h"
 #include "umma.cuh"
 
 namespace glb {
 
-constexpr int kTileM = 128;
-constexpr int kThreads = 1024;         // 32 warps: the gather needs warps in flight, not registers
-constexpr int kEpiWarps = 16;          // warps that drain TMEM in the epilogue
-constexpr int kWarps = kThreads / 32;
+constexpr int kTileM = 64;                         // destination rows per tile = UMMA M (two A tiles fit next to the W image)
+constexpr int kABufs = 2;
+constexpr int kThreads = 1024;
+constexpr int kEpiWarps = 8;                       // warps 0..7 (TMEM lane quarter = warp & 3, 32-column chunks interleaved by warp >> 2)
+constexpr int kMmaWarp = 8;
+constexpr int kGatherWarp0 = 9;
+constexpr int kGatherWarps = kThreads / 32 - kGatherWarp0;   // 23
+constexpr int kMaxSegs = 4;
+constexpr int kScrCap = 64;                        // row pointers per gather warp (private scratch): rows_per_item * (k + 1) <= 64
+constexpr size_t kSmemLimit = 232448;
 
 enum SageMode : int { kConcatMean = 0, kConcatSum = 1, kGcnMean = 2 };
+
+struct SageSeg {
+  const int64_t* self_vids;   // [M] or null (identity: self_base + m)
+  const int64_t* nbr_vids;    // [M, k] or null (identity: nbr_base + m*k + j)
+  int64_t self_base, nbr_base;
+  char* out;                  // [M, n_out] rows of this segment
+  __nv_bfloat16* a_save;      // [M, K_total] or null
+  int M, k;
+  int R;                      // destination rows per tile (<= 64, multiple of 8)
+  int tile0;                  // index of the segment's first tile
+};
 
 struct SageParams {
   TableView tself;
   TableView tnbr;
-  const int64_t* self_vids;   // [M] or null (identity)
-  const int64_t* nbr_vids;    // [M, k] or null (identity m*k+j)
+  SageSeg seg[kMaxSegs];
+  int nseg, total_tiles;
   const void* w_img;          // bf16 image, (K_total/64) blocks of [N x 64] SW128
-  const float* bias;          // [N] (padded) or null
-  void* out;                  // [M, n_out]
-  __nv_bfloat16* a_save;      // [M, K_total] or null
-  int64_t out_stride;
-  int M, k;
+  const float* bias;          // [n_out] or null
+  int64_t out_stride;         // elements
   int kp_self, kp_nbr;        // padded K of each half, in {0,64,128,256,512}
   int mode;
-  int N;                      // padded output width: multiple of 64, <= 256
+  int N;                      // padded output width: multiple of 16, <= 256
   int n_out;                  // real output width
   int relu;
   int out_bf16;
   int tmem_cols;
-  int rows_per_cta;           // destination rows gathered by one CTA (<= 128)
   const char* zero_row;       // >= 2 KB of zeros: target of the loads of masked lanes / missing rows
   int wshift_self, wshift_nbr; // log2(world) of each table when it is a power of two, else -1
-  long long* debug_ts;        // optional [grid][16] phase timestamps (clock64) written by thread 0
-  const __nv_bfloat16* a_src; // optional precomputed A [M, K_total] (row-major): skip the gather, just stage it
+  // fused softmax cross-entropy (top layer): active when ce_labels != nullptr
+  const int64_t* ce_labels;   // label table
+  const int64_t* ce_seeds;    // [M] vids (label = ce_labels[seed / ce_world]) or null (label = ce_labels[m])
+  int ce_world;
+  float* ce_loss;             // accumulated mean loss
+  __nv_bfloat16* ce_dlogits;  // [M, ce_dl_stride], columns >= n_out are written as zero
+  int ce_dl_stride;
+  float* ce_dbias;            // [n_out] accumulated, or null
+  float ce_inv_b;
+  // several weight images in one launch (dA = dZ . W with K_total > 256): CTA b uses image b % n_imgs, walks the tiles
+  // b / n_imgs + j * (gridDim.x / n_imgs) and writes output columns [img * N, img * N + n_out)
+  int n_imgs;
+  long long* dbg;             // optional [grid][64] clock64 trace (tools/persist_timeline.py), lane 0 of one warp per role
 };
-
-__device__ __forceinline__ float4 load4_rt(const void* row, int c, int dtype) {
-  if (dtype == 0) return ld_nc_f4(reinterpret_cast<const float4*>(row) + c);
-  uint2 u = ld_nc_u2(reinterpret_cast<const uint2*>(row) + c);
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
-__device__ __forceinline__ const char* table_row(const TableView& t, int64_t vid) {
-  if (vid < 0) return nullptr;
-  int owner = (int)(vid % t.world);
-  int64_t row = vid / t.world;
-  if (row >= t.nrows[owner]) return nullptr;
-  size_t esz = t.dtype == 0 ? 4 : 2;
-  return reinterpret_cast<const char*>(t.base.p[owner]) + (size_t)row * (size_t)t.stride * esz;
-}
-
-__device__ __forceinline__ float4 mask_tail(float4 v, int f, int dim) {
-  if (f + 3 >= dim) {
-    if (f >= dim) v.x = 0.f;
-    if (f + 1 >= dim) v.y = 0.f;
-    if (f + 2 >= dim) v.z = 0.f;
-    if (f + 3 >= dim) v.w = 0.f;
-  }
-  return v;
-}
-
-// store 4 consecutive K elements (kcol multiple of 4) of tile row r
-__device__ __forceinline__ void put_a(uint8_t* sA, int r, int kcol, float4 v) {
-  int kb = kcol >> 6;
-  uint32_t off = (uint32_t)kb * (kTileM * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63));
-  uint2 u;
-  u.x = pack_bf16x2(v.x, v.y);
-  u.y = pack_bf16x2(v.z, v.w);
-  *reinterpret_cast<uint2*>(sA + off) = u;
-}
 
 // One 16-byte storage chunk of a feature row: 4 fp32 or 8 bf16 features.  Kept RAW
 // (unconverted) so that a whole batch of row loads is issued back to back before the first use.
@@ -145,77 +146,203 @@ __device__ __forceinline__ const char* vid_ptr(const TableView& t, int64_t vid, 
 
 // write VEC consecutive K elements of tile row r starting at K column kcol (multiple of VEC)
 template <int VEC>
-__device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_save, size_t a_off, int r, int kcol,
-                                          const float (&v)[VEC]) {
+__device__ __forceinline__ void put_chunk(uint8_t* sA, __nv_bfloat16* a_row, int r, int kcol, const float (&v)[VEC]) {
   const int kb = kcol >> 6;
   const uint32_t off = (uint32_t)kb * (kTileM * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63));
   if constexpr (VEC == 4) {
     uint2 u; u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
     *reinterpret_cast<uint2*>(sA + off) = u;
-    if (a_save) *reinterpret_cast<uint2*>(a_save + a_off + kcol) = u;
+    if (a_row) *reinterpret_cast<uint2*>(a_row + kcol) = u;
   } else {
     uint4 u; u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
     u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(sA + off) = u;
-    if (a_save) *reinterpret_cast<uint4*>(a_save + a_off + kcol) = u;
+    if (a_row) *reinterpret_cast<uint4*>(a_row + kcol) = u;
   }
 }
 
-// epilogue shared by both kernel variants: TMEM -> registers -> bias/ReLU -> global
-__device__ __forceinline__ void sage_epilogue(const SageParams& p, uint32_t tmem_base, int m0, int R, int warp, int lane) {
-  // --- epilogue: TMEM -> registers -> bias/ReLU -> global.  A warp may only touch TMEM lane quarter
-  //     (warp % 4); the column range is split over 8 warp groups (N >= 128) or 4 (N = 64).
-  const int epi_groups = (p.N % 128 == 0) ? 8 : 4;
-  if (warp < 4 * epi_groups) {
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int g = warp >> 2;             // column group
-    const int cols_per_group = p.N / epi_groups;   // multiple of 16
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = row < R && m < p.M;
-    for (int c0 = 0; c0 < cols_per_group; c0 += 16) {
-      const int n0 = g * cols_per_group + c0;
-      uint32_t v[16];
-      umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
-      umma::tmem_ld_wait();
-      if (row_ok && n0 < p.n_out) {
-        float f[16];
+__device__ __forceinline__ int find_seg(const SageParams& p, int t) {
+  int s = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = __uint_as_float(v[i]);
-          if (p.bias && n0 + i < p.n_out) x += __ldg(p.bias + n0 + i);
-          if (p.relu) x = fmaxf(x, 0.f);
-          f[i] = x;
-        }
-        const bool full = (n0 + 16 <= p.n_out);
-        if (p.out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_stride + n0;
-          if (full && (p.out_stride & 7) == 0) {
-            uint4 a, b;
-            a.x = pack_bf16x2(f[0], f[1]); a.y = pack_bf16x2(f[2], f[3]);
-            a.z = pack_bf16x2(f[4], f[5]); a.w = pack_bf16x2(f[6], f[7]);
-            b.x = pack_bf16x2(f[8], f[9]); b.y = pack_bf16x2(f[10], f[11]);
-            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-            reinterpret_cast<uint4*>(o)[0] = a;
-            reinterpret_cast<uint4*>(o)[1] = b;
-          } else {
+  for (int i = 1; i < kMaxSegs; ++i)
+    if (i < p.nseg && t >= p.seg[i].tile0) s = i;
+  return s;
+}
+
+#define GLB_DBG(slot) do { if (p.dbg && lane == 0) p.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+
+// shared-memory control block (after the pointer buffers)
+enum : int { kBarW = 0, kBarAFull = 1, kBarAFree = 3, kBarTFull = 5, kBarTFree = 7, kNumBars = 9 };
+
+// ------------------------------------------------------------------------------------------------
+// epilogue of one tile: TMEM -> registers -> bias/ReLU -> global (warps 0..3, one row per thread)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_cols32(const SageParams& p, const SageSeg& sg, int m, int n0, const float (&f)[32]) {
+  if (n0 >= p.n_out) return;
+  const bool full = (n0 + 32 <= p.n_out);
+  if (p.out_bf16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(sg.out) + (size_t)m * p.out_stride + n0;
+    if (full && (p.out_stride & 7) == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (n0 + i < p.n_out) o[i] = __float2bfloat16(f[i]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_stride + n0;
-          if (full && (p.out_stride & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (n0 + i < p.n_out) o[i] = f[i];
-          }
-        }
+      for (int i = 0; i < 4; ++i) {
+        uint4 a;
+        a.x = pack_bf16x2(f[8 * i], f[8 * i + 1]); a.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+        a.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]); a.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+        reinterpret_cast<uint4*>(o)[i] = a;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.n_out) o[i] = __float2bfloat16(f[i]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(sg.out) + (size_t)m * p.out_stride + n0;
+    if (full && (p.out_stride & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.n_out) o[i] = f[i];
+    }
+  }
+}
+
+// bias vector staged once per CTA in shared memory (fp32 [N], zero beyond n_out)
+__device__ __forceinline__ void load_cols32(const SageParams& p, const float* sBias, uint32_t taddr, int n0, float (&f)[32]) {
+  uint32_t v[32];
+  umma::tmem_ld32(taddr + (uint32_t)n0, v);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = *reinterpret_cast<const float4*>(sBias + n0 + 4 * i);     // same address for all lanes: broadcast
+    float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+    float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+    f[4 * i] = x0; f[4 * i + 1] = x1; f[4 * i + 2] = x2; f[4 * i + 3] = x3;
+  }
+}
+
+// phase A of the epilogue: TMEM -> registers -> bias/ReLU -> global.  Eight warps: lane quarter q = warp & 3,
+// 32-column chunks interleaved between the two warps (warp >> 2) that share a quarter.
+__device__ __forceinline__ void sage_epilogue_tile(const SageParams& p, const SageSeg& sg, const float* sBias, uint32_t tmem_acc,
+                                                   int m0, int rows, int warp, int lane) {
+  // UMMA M = 64: accumulator row r lives in TMEM lane (r / 16) * 32 + (r % 16), i.e. lanes 0..15 of every quarter
+  const int q = warp & 3, half = warp >> 2;
+  if (q * 16 >= rows) return;                          // warp-uniform: this lane quarter holds no valid row
+  const int row = q * 16 + lane;
+  const int m = m0 + row;
+  const bool row_ok = lane < 16 && row < rows;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+  for (int n0 = half * 32; n0 < p.N; n0 += 64) {
+    if (n0 >= p.n_out) break;                          // padded output columns are never read back
+    float f[32];
+    load_cols32(p, sBias, taddr, n0, f);
+    if (row_ok && sg.out) store_cols32(p, sg, m, n0, f);
+  }
+}
+
+// phase B (top layer only): softmax cross-entropy of the tile's rows, one warp per row, lanes = classes
+// (n_out <= 64: columns lane and lane + 32), reading the logits phase A has just written (L2).
+__device__ __forceinline__ void sage_ce_tile(const SageParams& p, const SageSeg& sg, int m0, int rows, int warp, int lane) {
+  const float* logits = reinterpret_cast<const float*>(sg.out);
+  const int c0 = lane, c1 = lane + 32;
+  float db0 = 0.f, db1 = 0.f, lsum = 0.f;
+  for (int r = warp; r < rows; r += kEpiWarps) {
+    const int m = m0 + r;
+    const float* lrow = logits + (size_t)m * p.out_stride;
+    const float x0 = c0 < p.n_out ? __ldcg(lrow + c0) : -FLT_MAX;
+    const float x1 = c1 < p.n_out ? __ldcg(lrow + c1) : -FLT_MAX;
+    long long y = -1;
+    if (lane == 0) y = p.ce_seeds ? __ldg(p.ce_labels + __ldg(p.ce_seeds + m) / p.ce_world) : __ldg(p.ce_labels + m);
+    y = __shfl_sync(0xffffffffu, y, 0);
+    const bool valid = y >= 0 && y < p.n_out;
+    float mx = fmaxf(x0, x1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e0 = c0 < p.n_out ? __expf(x0 - mx) : 0.f, e1 = c1 < p.n_out ? __expf(x1 - mx) : 0.f;
+    float se = e0 + e1;
+    float xy = (c0 == (int)y ? x0 : 0.f) + (c1 == (int)y ? x1 : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); xy += __shfl_xor_sync(0xffffffffu, xy, o); }
+    const float inv = 1.f / se;
+    const float g0 = (valid && c0 < p.n_out) ? (e0 * inv - (c0 == (int)y ? 1.f : 0.f)) * p.ce_inv_b : 0.f;
+    const float g1 = (valid && c1 < p.n_out) ? (e1 * inv - (c1 == (int)y ? 1.f : 0.f)) * p.ce_inv_b : 0.f;
+    __nv_bfloat16* drow = p.ce_dlogits + (size_t)m * p.ce_dl_stride;
+    if (c0 < p.ce_dl_stride) drow[c0] = __float2bfloat16(g0);
+    if (c1 < p.ce_dl_stride) drow[c1] = __float2bfloat16(g1);
+    db0 += g0; db1 += g1;
+    if (valid) lsum += (mx + __logf(se) - xy) * p.ce_inv_b;
+  }
+  if (p.ce_dbias) {
+    if (c0 < p.n_out && db0 != 0.f) atomicAdd(p.ce_dbias + c0, db0);
+    if (c1 < p.n_out && db1 != 0.f) atomicAdd(p.ce_dbias + c1, db1);
+  }
+  if (lane == 0 && lsum != 0.f) atomicAdd(p.ce_loss, lsum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather-warp helpers
+// ------------------------------------------------------------------------------------------------
+struct TileCtx {       // kept small on purpose: the gather loop holds two of these next to its row loads
+  int s;               // segment index
+  int m0, rows;
+};
+
+struct GatherGeom {
+  int rpi, n_slices, lshift, sub, lig;
+};
+
+// position (it, item) -> first tile at or after `it` in which this warp still has an item; false past the last tile
+__device__ __forceinline__ bool seek_item(const SageParams& p, const GatherGeom& gg, int& it, int& item, TileCtx& c) {
+  for (;;) {
+    const int t = (int)blockIdx.x / p.n_imgs + it * ((int)gridDim.x / p.n_imgs);
+    if (t >= p.total_tiles) return false;
+    const int s = find_seg(p, t);
+    const int m0 = (t - p.seg[s].tile0) * p.seg[s].R;
+    const int rows = min(p.seg[s].R, p.seg[s].M - m0);
+    const int n_items = ((rows + gg.rpi - 1) / gg.rpi) * gg.n_slices;
+    if (item < n_items) { c.s = s; c.m0 = m0; c.rows = rows; return true; }
+    item -= n_items;
+    ++it;
+  }
+}
+
+// ids of one item, flat index f = sub_row * (k + 1) + j (j == k: the self id); lane holds f = lane and lane + 32
+__device__ __forceinline__ void load_item_ids(const SageParams& p, const GatherGeom& gg, const TileCtx& c, int item, bool need_self,
+                                              int lane, int64_t (&ids)[2]) {
+  const SageSeg& sg = p.seg[c.s];
+  const int rg = gg.n_slices == 1 ? item : item / gg.n_slices;
+  const int k1 = sg.k + 1;
+  const int n_ids = gg.rpi * k1;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int f = lane + 32 * u;
+    ids[u] = -1;
+    if (f < n_ids) {
+      const int sr = f / k1, j = f - sr * k1;
+      const int r = rg * gg.rpi + sr;
+      if (r < c.rows) {
+        const int64_t m = c.m0 + r;
+        if (j < sg.k) ids[u] = sg.nbr_vids ? __ldg(sg.nbr_vids + m * sg.k + j) : sg.nbr_base + m * sg.k + j;
+        else if (need_self) ids[u] = sg.self_vids ? __ldg(sg.self_vids + m) : sg.self_base + m;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void write_item_ptrs(const SageParams& p, const GatherGeom& gg, const TileCtx& c, const int64_t (&ids)[2],
+                                                int lane, const char** scr, uint32_t self_row_bytes, uint32_t nbr_row_bytes) {
+  const int k = p.seg[c.s].k;
+  const int n_ids = gg.rpi * (k + 1);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int f = lane + 32 * u;
+    if (f < n_ids) {
+      const int j = f % (k + 1);
+      scr[f] = j < k ? vid_ptr(p.tnbr, ids[u], p.wshift_nbr, nbr_row_bytes, p.zero_row)
+                     : vid_ptr(p.tself, ids[u], p.wshift_self, self_row_bytes, p.zero_row);
     }
   }
 }
@@ -223,21 +350,18 @@ __device__ __forceinline__ void sage_epilogue(const SageParams& p, uint32_t tmem
 // U  = neighbour row loads kept in flight per lane (one batch)
 // DT = storage dtype of the self AND neighbour tables (0 fp32, 1 bf16)
 //
-// Work decomposition: the CTA owns `rows_per_cta` consecutive destination rows (<= 128; a small M
-// is spread over many CTAs - the unused rows of the 128-row MMA tile are never stored).  A row
-// needs LPR = kp / VEC lanes (16-byte chunk per lane); when LPR < 32 a warp processes 32/LPR rows
-// side by side (sub-warp groups), when LPR > 32 the row is cut into 32-lane slices.  Per item a
-// lane group (1) already holds the neighbour locators (prefetched during the previous item),
-// (2) issues ALL self + neighbour chunk loads of the batch unconditionally (masked lanes read a
-// zero row), (3) reduces in fp32, (4) writes bf16 into the SW128 A tile.
-constexpr int kMaxSlots = 64;
-constexpr int kProducers = 4;
-
-#define GLB_TS(i) do { if (p.debug_ts && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
-
+// Gather decomposition: a row needs LPR = kp / VEC lanes (16-byte chunk per lane); when LPR < 32 a
+// warp processes 32/LPR rows side by side (sub-warp groups), when LPR > 32 the row is cut into
+// 32-lane slices.  Per item a lane group issues ALL self + neighbour chunk loads of a batch
+// unconditionally (masked lanes read a zero row), reduces in fp32 and writes bf16 into the SW128
+// A tile.
 template <int U, int DT>
-__global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageParams p) {
-  GLB_TS(0);
+__global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_constant__ SageParams p) {
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[(size_t)blockIdx.x * 64 + 60] = (long long)gt;
+    p.dbg[(size_t)blockIdx.x * 64 + 61] = clock64();
+  }
   // keep every pointer derived from the __shared__ symbol by plain integer offsets so that the
   // compiler emits LDS/STS (a uintptr_t round trip would demote them to generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -245,23 +369,30 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   const int k_total = p.kp_self + p.kp_nbr;
   const int nkb = k_total >> 6;
   uint8_t* sA = smem;
-  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);
+  const uint32_t a_buf_bytes = (uint32_t)nkb * (kTileM * 128);
+  uint8_t* sW = sA + (size_t)kABufs * a_buf_bytes;
   const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)nkb * w_kb_bytes);
-  uint64_t* bar_w = bars;
-  uint64_t* bar_mma = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const char** sScr = reinterpret_cast<const char**>(sW + (size_t)nkb * w_kb_bytes);   // [kGatherWarps][kScrCap]
+  float* sBias = reinterpret_cast<float*>(sScr + kGatherWarps * kScrCap);              // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
   if (tid == 0) {
-    umma::mbar_init(bar_w, 1);
-    umma::mbar_init(bar_mma, 1);
+    umma::mbar_init(bars + kBarW, 1);
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(bars + kBarAFull + i, kGatherWarps);
+      umma::mbar_init(bars + kBarAFree + i, 1);
+      umma::mbar_init(bars + kBarTFull + i, 1);
+      umma::mbar_init(bars + kBarTFree + i, kEpiWarps);
+    }
     umma::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (tid < 256) sBias[tid] = (p.bias && tid < p.n_out) ? __ldg(p.bias + tid) : 0.f;
+  if (warp == kMmaWarp) {
     umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     umma::tmem_relinquish();
   }
@@ -269,828 +400,200 @@ __global__ void __launch_bounds__(kThreads, 1) sage_fused_fwd_kernel(const SageP
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  GLB_TS(1);
+  const int img = (int)blockIdx.x % p.n_imgs;
+  const int tile_first = (int)blockIdx.x / p.n_imgs, tile_stride = (int)gridDim.x / p.n_imgs;
+  if (warp == 0) GLB_DBG(0);
 
-  // --- weights: TMA bulk copies of the pre-swizzled image, overlapped with the gather
-  if (tid == 0) {
-    umma::mbar_arrive_expect_tx(bar_w, (uint32_t)nkb * w_kb_bytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_img);
-    for (int kb = 0; kb < nkb; ++kb)
-      umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
-  }
-
-  const int R = p.rows_per_cta;
-  const int m0 = blockIdx.x * R;
-  if (p.a_src != nullptr) {
-    // split path (multi-GPU): A was produced by gather_self_mean_kernel; stage the tile with coalesced
-    // 16-byte loads -> swizzled 16-byte shared stores
-    const int R_ = p.rows_per_cta;
-    const int m0_ = blockIdx.x * R_;
-    const int chunks_row = k_total >> 3;                 // 16-byte chunks per A row
-    for (int i = tid; i < R_ * chunks_row; i += kThreads) {
-      const int r = i / chunks_row, c = i - r * chunks_row;
-      const int m = m0_ + r;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (m < p.M) v = ld_nc_u4(reinterpret_cast<const uint4*>(p.a_src + (size_t)m * k_total) + c);
-      const int kcol = c * 8;
-      *reinterpret_cast<uint4*>(sA + (size_t)(kcol >> 6) * (kTileM * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63))) = v;
-    }
-    GLB_TS(2);
-  } else {
-  // --- phase 0: resolve the tile's neighbour / self ids into ROW POINTERS staged in shared memory
-  //     (coalesced read of nbr_vids[m0*k .. (m0+R)*k); missing rows point at a zero row).  The
-  //     hot loop below is then just  LDS.64 + IADD + LDG  per row chunk.
-  constexpr int VEC = Chunk<DT>::kVec;
-  const int R = p.rows_per_cta;
-  const int m0 = blockIdx.x * R;
-  const int k = p.k;
-  const char** sPtrN = reinterpret_cast<const char**>(bars + 4 + 2 * kMaxSlots);   // [R * k]
-  const char** sPtrS = sPtrN + (size_t)R * k;                          // [R]
-  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
-  {
-    const int wshift_n = p.wshift_nbr, wshift_s = p.wshift_self;
-    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
-    const int64_t base = (int64_t)m0 * k;
-    const int64_t lim = (int64_t)p.M * k;
-    for (int i = tid; i < R * k; i += kThreads) {
-      const int64_t idx = base + i;
-      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, wshift_n, nbr_row_bytes, p.zero_row) : p.zero_row;
-    }
-    for (int i = tid; i < R; i += kThreads) {
-      const int m = m0 + i;
-      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, wshift_s, self_row_bytes, p.zero_row) : p.zero_row;
-    }
-  }
-  __syncthreads();
-  GLB_TS(2);
-
-  // --- phase 1: gather + aggregate -> A tile (bf16, SW128 K-major)
-  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
-  const int lanes_row = p.kp_nbr / VEC;                 // 16-byte chunks per (half) row: 8..128
-  const int lpr = lanes_row < 32 ? lanes_row : 32;      // lanes per row inside a warp
-  const int lshift = 31 - __clz(lpr);                   // log2(lpr)
-  const int rpi = 32 >> lshift;                         // rows per item
-  const int n_slices = lanes_row > 32 ? lanes_row >> 5 : 1;
-  const int row_groups = (R + rpi - 1) / rpi;
-  const int n_items = row_groups * n_slices;
-  const int sub = lane >> lshift;                       // which row of the item this lane works on
-  const int lig = lane & (lpr - 1);                     // lane index inside its row group
-  const bool has_self = p.kp_self > 0;
-  float scale = 1.f;
-  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
-  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
-
-  for (int item = warp; item < n_items; item += kWarps) {
-    const int rg = n_slices == 1 ? item : item / n_slices;
-    const int sl = n_slices == 1 ? 0 : item - rg * n_slices;
-    const int r = rg * rpi + sub;
-    if (r >= R) continue;                                // (only when R is not a multiple of rpi)
-    const int m = m0 + r;
-    const int chunk = lig + 32 * sl;                     // this lane's 16-byte chunk of the row
-    const int f0 = chunk * VEC;                          // first feature of the chunk
-    const size_t coff = (size_t)chunk * 16;
-    float acc[VEC], sv[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
-    // lanes whose chunk lies beyond the real feature width skip the loads altogether (their A
-    // columns are the zero K-padding); the others issue self + U neighbour loads back to back
-    if (f0 < d_nbr) {
-      const char* const* ptrs = sPtrN + (size_t)r * k;
-      Chunk<DT> sraw;
-      const bool self_ld = need_self && f0 < d_self;
-      if (self_ld) sraw.load(sPtrS[r] + coff);
-      for (int j0 = 0; j0 < k; j0 += U) {
-        Chunk<DT> raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = j0 + u < k ? j0 + u : k - 1;      // tail slots re-read the last row (masked below)
-          raw[u].load(ptrs[j] + coff);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (j0 + u < k) raw[u].add_to(acc);
-      }
-      if (self_ld) sraw.add_to(sv);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {                    // tail masks (dims that are not multiples of VEC)
-        if (f0 + i >= d_self) sv[i] = 0.f;
-        if (f0 + i >= d_nbr) acc[i] = 0.f;
-      }
-    } else if (need_self && f0 < d_self) {               // self wider than the neighbour half (rare)
-      Chunk<DT> sraw;
-      sraw.load(sPtrS[r] + coff);
-      sraw.add_to(sv);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) if (f0 + i >= d_self) sv[i] = 0.f;
-    }
-    const size_t a_off = (size_t)m * k_total;
-    __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
-    if (has_self) put_chunk<VEC>(sA, asave, a_off, r, f0, sv);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
-    put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
-  }
-  }  // gather vs. dense-A
-  GLB_TS(3);
-  umma::fence_proxy_async_smem();     // generic-proxy st.shared -> visible to tcgen05 (async proxy)
-  __syncthreads();
-  GLB_TS(4);
-
-  // --- GEMM: one thread issues all MMAs; accumulator lives in TMEM
-  if (tid == 0) {
-    umma::mbar_wait(bar_w, 0);
-    GLB_TS(5);
-    umma::tc_fence_after();
-    const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
-      const uint32_t b_base = umma::smem_u32(sW + (size_t)kb * w_kb_bytes);
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        umma::mma_bf16_ss(tmem_base, umma::make_desc_sw128(a_base + k4 * 32),
-                          umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
-      }
-    }
-    umma::mma_commit(bar_mma);
-    GLB_TS(6);
-  }
-  __syncwarp();
-  umma::mbar_wait(bar_mma, 0);
-  GLB_TS(7);
-  umma::tc_fence_after();
-
-  sage_epilogue(p, tmem_base, m0, R, warp, lane);
-  GLB_TS(8);
-  umma::tc_fence_before();
-  __syncthreads();
-  GLB_TS(9);
-  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// TMA-gather variant.  Same math and same tile / MMA / epilogue as above, but the feature rows are
-// pulled by the TMA engine (cp.async.bulk, one bulk copy per row, completion on mbarriers) into a
-// shared-memory ring instead of through registers: ~128 KB of row fetches stay in flight per SM
-// with zero register cost, which is what hides HBM *and* NVLink latency (peer rows cost ~2 us).
-// The ring lives in the weight region: W is only needed after the gather, so it is fetched (one
-// more bulk copy, from L2) once the ring has drained.
-//   warp 0            producer: per destination row issues (1 + k) row copies into the next slot
-//   warps 1..31       consumers: wait for a slot, reduce the k neighbour rows (fp32), write the bf16
-//                     A-tile chunks (+ the row-major copy saved for backward), release the slot
-// ---------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(kThreads, 1) sage_fused_tma_kernel(const SageParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  GLB_TS(0);
-  const int k_total = p.kp_self + p.kp_nbr;
-  const int nkb = k_total >> 6;
-  uint8_t* sA = smem;
-  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);                     // ring during the gather, W afterwards
-  const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;
-  const uint32_t w_bytes = (uint32_t)nkb * w_kb_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)w_bytes);
-  uint64_t* bar_w = bars;
-  uint64_t* bar_mma = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  uint64_t* full = bars + 4;                                           // [kMaxSlots]
-  uint64_t* empty = full + kMaxSlots;                                  // [kMaxSlots]
-  const char** sPtrN = reinterpret_cast<const char**>(empty + kMaxSlots);
-  const int R = p.rows_per_cta;
-  const int k = p.k;
-  const char** sPtrS = sPtrN + (size_t)R * k;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  constexpr int VEC = Chunk<DT>::kVec;
-  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
-  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
-  // bytes actually copied per row: the real features rounded up to 16 B (never more than the stride)
-  const uint32_t nbr_copy = min(nbr_row_bytes, (uint32_t)((p.tnbr.dim * (DT == 0 ? 4 : 2) + 15) & ~15));
-  const uint32_t self_copy = need_self ? min(self_row_bytes, (uint32_t)((p.tself.dim * (DT == 0 ? 4 : 2) + 15) & ~15)) : 0u;
-  const uint32_t slot_bytes = self_copy + (uint32_t)k * nbr_copy;
-  const int S = min((int)(w_bytes / slot_bytes), kMaxSlots);
-
-  if (tid == 0) {
-    umma::mbar_init(bar_w, 1);
-    umma::mbar_init(bar_mma, 1);
-    for (int s = 0; s < S; ++s) { umma::mbar_init(full + s, 1); umma::mbar_init(empty + s, 1); }
-    umma::fence_barrier_init();
-  }
-  if (warp == 1) {
-    umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    umma::tmem_relinquish();
-  }
-  // resolve ids -> row pointers (coalesced), as in the register variant
-  const int m0 = blockIdx.x * R;
-  {
-    const int64_t base = (int64_t)m0 * k;
-    const int64_t lim = (int64_t)p.M * k;
-    for (int i = tid; i < R * k; i += kThreads) {
-      const int64_t idx = base + i;
-      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr, nbr_row_bytes, p.zero_row) : p.zero_row;
-    }
-    for (int i = tid; i < R; i += kThreads) {
-      const int m = m0 + i;
-      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self, self_row_bytes, p.zero_row) : p.zero_row;
-    }
-  }
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  GLB_TS(2);
-
-  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
-  const bool has_self = p.kp_self > 0;
-  float scale = 1.f;
-  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
-  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
-
-  if (warp == 0) {
-    // ===== producer: one slot per destination row =====
-    for (int i = 0; i < R; ++i) {
-      const int s = i % S, turn = i / S;
-      if (turn > 0) umma::mbar_wait(empty + s, (uint32_t)((turn - 1) & 1));
-      uint8_t* slot = sW + (size_t)s * slot_bytes;
-      if (lane == 0) umma::mbar_arrive_expect_tx(full + s, slot_bytes);
+  if (warp < kEpiWarps) {
+    // =================================================================== epilogue warps
+    int it = 0;
+    for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++it) {
+      const int acc = it & 1;
+      umma::mbar_wait(bars + kBarTFull + acc, (uint32_t)((it >> 1) & 1));
+      umma::tc_fence_after();
+      if (warp == 0 && it < 4) GLB_DBG(4 + it * 2);
+      const int s = find_seg(p, t);
+      SageSeg sg = p.seg[s];
+      if (sg.out) sg.out += (size_t)img * p.N * (p.out_bf16 ? 2 : 4);
+      const int m0 = (t - sg.tile0) * sg.R;
+      const int rows = min(sg.R, sg.M - m0);
+      sage_epilogue_tile(p, sg, sBias, tmem_base + (uint32_t)(acc * p.N), m0, rows, warp, lane);
+      umma::tc_fence_before();
       __syncwarp();
-      if (need_self && lane == 0) umma::bulk_g2s(slot, sPtrS[i], self_copy, full + s);
-      for (int j = lane; j < k; j += 32)
-        umma::bulk_g2s(slot + self_copy + (size_t)j * nbr_copy, sPtrN[(size_t)i * k + j], nbr_copy, full + s);
+      if (lane == 0) umma::mbar_arrive(bars + kBarTFree + acc);
+      if (p.ce_labels != nullptr) {
+        __threadfence_block();
+        asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");     // logits of the tile are written
+        sage_ce_tile(p, sg, m0, rows, warp, lane);
+      }
+      if (warp == 0 && it < 4) GLB_DBG(5 + it * 2);
     }
-  } else {
-    // ===== consumers =====
-    // Slot s is always drained by the SAME consumer warp (s % C) in increasing turn order: an
-    // mbarrier only distinguishes the parity of a phase, so two warps waiting for different turns
-    // of one slot would alias.
-    const int nchunks = p.kp_nbr / VEC;                  // 16-byte chunks per K half
-    const int C = kWarps - 1, c = warp - 1;
-    for (int turn = 0; turn * S < R; ++turn)
-    for (int s = c; s < S; s += C) {
-      const int i = turn * S + s;
-      if (i >= R) break;
-      umma::mbar_wait(full + s, (uint32_t)(turn & 1));
-      const uint8_t* slot = sW + (size_t)s * slot_bytes;
-      const int m = m0 + i;
-      const size_t a_off = (size_t)m * k_total;
-      __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
-      for (int chunk = lane; chunk < nchunks; chunk += 32) {
-        const int f0 = chunk * VEC;
-        float acc[VEC], sv[VEC];
+  } else if (warp == kMmaWarp) {
+    // =================================================================== MMA issuer (+ W image via TMA)
+    if (lane == 0) {
+      umma::mbar_arrive_expect_tx(bars + kBarW, (uint32_t)nkb * w_kb_bytes);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)img * nkb * w_kb_bytes;
+      for (int kb = 0; kb < nkb; ++kb)
+        umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bars + kBarW);
+    }
+    __syncwarp();
+    umma::mbar_wait(bars + kBarW, 0);
+    GLB_DBG(1);
+    const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
+    int it = 0;
+    for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++it) {
+      const int acc = it & 1;
+      umma::mbar_wait(bars + kBarAFull + acc, (uint32_t)((it >> 1) & 1));
+      umma::mbar_wait(bars + kBarTFree + acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+      umma::tc_fence_after();
+      if (it < 4) GLB_DBG(12 + it * 2);
+      if (lane == 0) {
+        const uint32_t d = tmem_base + (uint32_t)(acc * p.N);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t a_base = umma::smem_u32(sA + (size_t)acc * a_buf_bytes + (size_t)kb * (kTileM * 128));
+          const uint32_t b_base = umma::smem_u32(sW + (size_t)kb * w_kb_bytes);
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { acc[q] = 0.f; sv[q] = 0.f; }
-        if (f0 < d_nbr) {
-          const uint8_t* np = slot + self_copy + (size_t)chunk * 16;
-          for (int j = 0; j < k; ++j) {
-            Chunk<DT> c;
-            c.v = *reinterpret_cast<const decltype(c.v)*>(np + (size_t)j * nbr_copy);
-            c.add_to(acc);
-          }
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma::mma_bf16_ss(d, umma::make_desc_sw128(a_base + k4 * 32), umma::make_desc_sw128(b_base + k4 * 32), idesc,
+                              (kb | k4) ? 1u : 0u);
         }
-        if (need_self && f0 < d_self) {
-          Chunk<DT> c;
-          c.v = *reinterpret_cast<const decltype(c.v)*>(slot + (size_t)chunk * 16);
-          c.add_to(sv);
-        }
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          if (f0 + q >= d_self) sv[q] = 0.f;
-          if (f0 + q >= d_nbr) acc[q] = 0.f;
-        }
-        if (has_self) put_chunk<VEC>(sA, asave, a_off, i, f0, sv);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[q] = (acc[q] + (p.mode == kGcnMean ? sv[q] : 0.f)) * scale;
-        put_chunk<VEC>(sA, asave, a_off, i, p.kp_self + f0, acc);
+        umma::mma_commit(bars + kBarAFree + acc);     // this A buffer may be overwritten
+        umma::mma_commit(bars + kBarTFull + acc);     // the accumulator may be drained
       }
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(empty + s);
-    }
-  }
-  GLB_TS(3);
-  umma::fence_proxy_async_smem();     // A-tile st.shared visible to tcgen05; ring reads ordered before the W copy
-  __syncthreads();
-  GLB_TS(4);
-
-  // --- weights into the (now idle) ring region, then the MMAs
-  if (tid == 0) {
-    umma::mbar_arrive_expect_tx(bar_w, w_bytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_img);
-    for (int kb = 0; kb < nkb; ++kb)
-      umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
-    umma::mbar_wait(bar_w, 0);
-    GLB_TS(5);
-    umma::tc_fence_after();
-    const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
-      const uint32_t b_base = umma::smem_u32(sW + (size_t)kb * w_kb_bytes);
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma::mma_bf16_ss(tmem_base, umma::make_desc_sw128(a_base + k4 * 32),
-                          umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
-    }
-    umma::mma_commit(bar_mma);
-    GLB_TS(6);
-  }
-  __syncwarp();
-  umma::mbar_wait(bar_mma, 0);
-  GLB_TS(7);
-  umma::tc_fence_after();
-  sage_epilogue(p, tmem_base, m0, R, warp, lane);
-  GLB_TS(8);
-  umma::tc_fence_before();
-  __syncthreads();
-  GLB_TS(9);
-  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// cp.async-gather variant (the multi-GPU / multi-wave default).  Same ring-in-the-W-region structure
-// as the TMA variant, but the rows are moved by per-lane 16-byte cp.async (LDGSTS): normal LSU issue
-// rate (the TMA unit needs ~110 cycles per small bulk copy), zero registers held while in flight,
-// and the ring keeps ~128 KB of row fetches outstanding per SM - enough to cover NVLink peer
-// latency.  kProducers warps issue copies, the remaining warps reduce + write the A tile.
-// ---------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(kThreads, 1) sage_fused_async_kernel(const SageParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  GLB_TS(0);
-  const int k_total = p.kp_self + p.kp_nbr;
-  const int nkb = k_total >> 6;
-  uint8_t* sA = smem;
-  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);                     // ring during the gather, W afterwards
-  const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;
-  const uint32_t w_bytes = (uint32_t)nkb * w_kb_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)w_bytes);
-  uint64_t* bar_w = bars;
-  uint64_t* bar_mma = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  uint64_t* full = bars + 4;                                           // [kMaxSlots]
-  uint64_t* empty = full + kMaxSlots;                                  // [kMaxSlots]
-  const char** sPtrN = reinterpret_cast<const char**>(empty + kMaxSlots);
-  const int R = p.rows_per_cta;
-  const int k = p.k;
-  const char** sPtrS = sPtrN + (size_t)R * k;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  constexpr int VEC = Chunk<DT>::kVec;
-  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
-  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
-  // bytes actually copied per row: the real features rounded up to 16 B (never more than the stride)
-  const uint32_t nbr_copy = min(nbr_row_bytes, (uint32_t)((p.tnbr.dim * (DT == 0 ? 4 : 2) + 15) & ~15));
-  const uint32_t self_copy = need_self ? min(self_row_bytes, (uint32_t)((p.tself.dim * (DT == 0 ? 4 : 2) + 15) & ~15)) : 0u;
-  const uint32_t slot_bytes = self_copy + (uint32_t)k * nbr_copy;
-  constexpr int P = kProducers;                                         // producer warps
-  const int S = (min((int)(w_bytes / slot_bytes), kMaxSlots) / P) * P;   // slot s belongs to producer s % P
-
-  if (tid == 0) {
-    umma::mbar_init(bar_w, 1);
-    umma::mbar_init(bar_mma, 1);
-    for (int s = 0; s < S; ++s) { umma::mbar_init(full + s, 32); umma::mbar_init(empty + s, 1); }
-    umma::fence_barrier_init();
-  }
-  if (warp == 1) {
-    umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    umma::tmem_relinquish();
-  }
-  // resolve ids -> row pointers (coalesced), as in the register variant
-  const int m0 = blockIdx.x * R;
-  {
-    const int64_t base = (int64_t)m0 * k;
-    const int64_t lim = (int64_t)p.M * k;
-    for (int i = tid; i < R * k; i += kThreads) {
-      const int64_t idx = base + i;
-      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr, nbr_row_bytes, p.zero_row) : p.zero_row;
-    }
-    for (int i = tid; i < R; i += kThreads) {
-      const int m = m0 + i;
-      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self, self_row_bytes, p.zero_row) : p.zero_row;
-    }
-  }
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  GLB_TS(2);
-
-  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
-  const bool has_self = p.kp_self > 0;
-  float scale = 1.f;
-  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
-  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
-
-  if (warp < P) {
-    // ===== producers: warp p fills the slots s = p (mod P); every lane moves 16-byte chunks with
-    //       cp.async (LDGSTS) and the slot's mbarrier fires when all 32 lanes' copies have landed =====
-    const uint32_t cps = self_copy >> 4, cpn = nbr_copy >> 4;          // 16-byte chunks per row
-    const uint32_t total = cps + (uint32_t)k * cpn;
-    for (int turn = 0; turn * S < R; ++turn)
-    for (int s = warp; s < S; s += P) {
-      const int i = turn * S + s;
-      if (i >= R) break;
-      if (turn > 0) umma::mbar_wait(empty + s, (uint32_t)((turn - 1) & 1));
-      uint8_t* slot = sW + (size_t)s * slot_bytes;
-      const char* sp = sPtrS[i];
-      const char* const* np = sPtrN + (size_t)i * k;
-      for (uint32_t c = lane; c < total; c += 32) {
-        const char* src;
-        if (c < cps) src = sp + (size_t)c * 16;
-        else { const uint32_t cc = c - cps; const uint32_t j = cc / cpn; src = np[j] + (size_t)(cc - j * cpn) * 16; }
-        umma::cp_async16(slot + (size_t)c * 16, src);
-      }
-      umma::cp_async_mbar_arrive_noinc(full + s);
+      if (it < 4) GLB_DBG(13 + it * 2);
     }
   } else {
-    // ===== consumers =====
-    // Slot s is always drained by the SAME consumer warp (s % C) in increasing turn order: an
-    // mbarrier only distinguishes the parity of a phase, so two warps waiting for different turns
-    // of one slot would alias.
-    const int nchunks = p.kp_nbr / VEC;                  // 16-byte chunks per K half
-    const int C = kWarps - P, c = warp - P;
-    for (int turn = 0; turn * S < R; ++turn)
-    for (int s = c; s < S; s += C) {
-      const int i = turn * S + s;
-      if (i >= R) break;
-      umma::mbar_wait(full + s, (uint32_t)(turn & 1));
-      const uint8_t* slot = sW + (size_t)s * slot_bytes;
-      const int m = m0 + i;
-      const size_t a_off = (size_t)m * k_total;
-      __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
-      for (int chunk = lane; chunk < nchunks; chunk += 32) {
-        const int f0 = chunk * VEC;
-        float acc[VEC], sv[VEC];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) { acc[q] = 0.f; sv[q] = 0.f; }
-        if (f0 < d_nbr) {
-          const uint8_t* np = slot + self_copy + (size_t)chunk * 16;
-          for (int j = 0; j < k; ++j) {
-            Chunk<DT> c;
-            c.v = *reinterpret_cast<const decltype(c.v)*>(np + (size_t)j * nbr_copy);
-            c.add_to(acc);
-          }
-        }
-        if (need_self && f0 < d_self) {
-          Chunk<DT> c;
-          c.v = *reinterpret_cast<const decltype(c.v)*>(slot + (size_t)chunk * 16);
-          c.add_to(sv);
-        }
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          if (f0 + q >= d_self) sv[q] = 0.f;
-          if (f0 + q >= d_nbr) acc[q] = 0.f;
-        }
-        if (has_self) put_chunk<VEC>(sA, asave, a_off, i, f0, sv);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[q] = (acc[q] + (p.mode == kGcnMean ? sv[q] : 0.f)) * scale;
-        put_chunk<VEC>(sA, asave, a_off, i, p.kp_self + f0, acc);
-      }
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(empty + s);
-    }
-  }
-  GLB_TS(3);
-  umma::fence_proxy_async_smem();     // A-tile st.shared visible to tcgen05; ring reads ordered before the W copy
-  __syncthreads();
-  GLB_TS(4);
-
-  // --- weights into the (now idle) ring region, then the MMAs
-  if (tid == 0) {
-    umma::mbar_arrive_expect_tx(bar_w, w_bytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_img);
-    for (int kb = 0; kb < nkb; ++kb)
-      umma::bulk_g2s(sW + (size_t)kb * w_kb_bytes, src + (size_t)kb * w_kb_bytes, w_kb_bytes, bar_w);
-    umma::mbar_wait(bar_w, 0);
-    GLB_TS(5);
-    umma::tc_fence_after();
-    const uint32_t idesc = umma::make_idesc_bf16(kTileM, p.N);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
-      const uint32_t b_base = umma::smem_u32(sW + (size_t)kb * w_kb_bytes);
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma::mma_bf16_ss(tmem_base, umma::make_desc_sw128(a_base + k4 * 32),
-                          umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
-    }
-    umma::mma_commit(bar_mma);
-    GLB_TS(6);
-  }
-  __syncwarp();
-  umma::mbar_wait(bar_mma, 0);
-  GLB_TS(7);
-  umma::tc_fence_after();
-  sage_epilogue(p, tmem_base, m0, R, warp, lane);
-  GLB_TS(8);
-  umma::tc_fence_before();
-  __syncthreads();
-  GLB_TS(9);
-  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (gather_mode = 5, not measured in round 1 - see DESIGN.md "Round-2 plan"): the same tile with
-// TWO resident CTAs per SM.  ncu shows the default kernel at 23 % of the copy roofline with 40 % long-scoreboard
-// and 25 % barrier stalls: one 1024-thread CTA per SM serialises id staging -> gather -> MMA -> epilogue, and
-// while it is outside the gather no loads are in flight on that SM.  Here the CTA has 512 threads and keeps only
-// the A tile (nkb x 16 KB) plus a 2-deep ring of W slices of kNS = 32 output columns (nkb x 4 KB each) in
-// shared memory (<= ~110 KB for K = 256), so two CTAs fit and their phases interleave.  Thread 0 streams the W
-// slices with bulk copies and issues M128 x N32 x K16 MMAs slice by slice into disjoint TMEM column ranges
-// (2 x 256 columns for the two CTAs = the whole TMEM).  Every mbarrier has exactly one waiter (thread 0).
-// ---------------------------------------------------------------------------------------------
-constexpr int kOccThreads = 512;
-constexpr int kOccWarps = kOccThreads / 32;
-constexpr int kNS = 32;                 // output columns per W slice
-
-template <int U, int DT>
-__global__ void __launch_bounds__(kOccThreads, 2) sage_fused_occ2_kernel(const SageParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int k_total = p.kp_self + p.kp_nbr;
-  const int nkb = k_total >> 6;
-  const int n_slices_w = p.N / kNS;
-  uint8_t* sA = smem;
-  const uint32_t slice_kb_bytes = (uint32_t)kNS * 128u;                 // one k-block of one slice: 4 KB
-  const uint32_t slice_bytes = (uint32_t)nkb * slice_kb_bytes;
-  uint8_t* sW = sA + (size_t)nkb * (kTileM * 128);                      // ring: 2 slices
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 2 * (size_t)slice_bytes);
-  uint64_t* full = bars;                 // [2]
-  uint64_t* empty = bars + 2;            // [2]
-  uint64_t* bar_mma = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  const char** sPtrN = reinterpret_cast<const char**>(bars + 8);        // [R * k]
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  if (tid == 0) {
-    umma::mbar_init(full + 0, 1); umma::mbar_init(full + 1, 1);
-    umma::mbar_init(empty + 0, 1); umma::mbar_init(empty + 1, 1);
-    umma::mbar_init(bar_mma, 1);
-    umma::fence_barrier_init();
-  }
-  if (warp == 1) {
-    umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    umma::tmem_relinquish();
-  }
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w_img);
-  const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;                     // one k-block of the FULL image
-  auto load_slice = [&](int s, int b) {                                 // thread 0 only
-    umma::mbar_arrive_expect_tx(full + b, slice_bytes);
-    for (int kb = 0; kb < nkb; ++kb)
-      umma::bulk_g2s(sW + (size_t)b * slice_bytes + (size_t)kb * slice_kb_bytes,
-                     wsrc + (size_t)kb * w_kb_bytes + (size_t)s * slice_kb_bytes, slice_kb_bytes, full + b);
-  };
-  if (tid == 0) {                        // the first two slices stream in behind the gather
-    load_slice(0, 0);
-    if (n_slices_w > 1) load_slice(1, 1);
-  }
-
-  // --- phase 0: ids -> row pointers (same as the default kernel)
-  constexpr int VEC = Chunk<DT>::kVec;
-  const int R = p.rows_per_cta;
-  const int m0 = blockIdx.x * R;
-  const int k = p.k;
-  const char** sPtrS = sPtrN + (size_t)R * k;
-  const bool need_self = p.kp_self > 0 || p.mode == kGcnMean;
-  {
-    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
-    const int64_t base = (int64_t)m0 * k;
-    const int64_t lim = (int64_t)p.M * k;
-    for (int i = tid; i < R * k; i += kOccThreads) {
-      const int64_t idx = base + i;
-      sPtrN[i] = idx < lim ? vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + idx) : idx, p.wshift_nbr, nbr_row_bytes, p.zero_row) : p.zero_row;
-    }
-    for (int i = tid; i < R; i += kOccThreads) {
-      const int m = m0 + i;
-      sPtrS[i] = (need_self && m < p.M) ? vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : (int64_t)m, p.wshift_self, self_row_bytes, p.zero_row) : p.zero_row;
-    }
-  }
-  __syncthreads();
-
-  // --- phase 1: gather + aggregate -> A tile (identical math / layout to the default kernel)
-  {
+    // =================================================================== gather warps
+    constexpr int VEC = Chunk<DT>::kVec;
+    const int gw = warp - kGatherWarp0;
+    const int kp = p.kp_nbr > 0 ? p.kp_nbr : p.kp_self;
     const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
-    const int lanes_row = p.kp_nbr / VEC;
-    const int lpr = lanes_row < 32 ? lanes_row : 32;
-    const int lshift = 31 - __clz(lpr);
-    const int rpi = 32 >> lshift;
-    const int n_sl = lanes_row > 32 ? lanes_row >> 5 : 1;
-    const int row_groups = (R + rpi - 1) / rpi;
-    const int n_items = row_groups * n_sl;
-    const int sub = lane >> lshift;
-    const int lig = lane & (lpr - 1);
+    const int lanes_row = kp / VEC;                       // 16-byte chunks per (half) row: 8..128
+    const int lpr = lanes_row < 32 ? lanes_row : 32;      // lanes per row inside a warp
+    GatherGeom gg;
+    gg.lshift = 31 - __clz(lpr);                          // log2(lpr)
+    gg.rpi = 32 >> gg.lshift;                             // rows per item
+    gg.n_slices = lanes_row > 32 ? lanes_row >> 5 : 1;
+    gg.sub = lane >> gg.lshift;                           // which row of the item this lane works on
+    gg.lig = lane & (lpr - 1);                            // lane index inside its row group
     const bool has_self = p.kp_self > 0;
-    float scale = 1.f;
-    if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
-    else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
-    for (int item = warp; item < n_items; item += kOccWarps) {
-      const int rg = n_sl == 1 ? item : item / n_sl;
-      const int sl = n_sl == 1 ? 0 : item - rg * n_sl;
-      const int r = rg * rpi + sub;
-      if (r >= R) continue;
-      const int m = m0 + r;
-      const int chunk = lig + 32 * sl;
-      const int f0 = chunk * VEC;
+    const bool has_nbr = p.kp_nbr > 0;
+    const bool need_self = has_self || p.mode == kGcnMean;
+    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
+    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+    const char** scr = sScr + gw * kScrCap;
+    const int n_tiles_cta = (p.total_tiles - tile_first + tile_stride - 1) / tile_stride;
+
+    int arrived = 0;                                      // tiles this warp has already arrived for on a_full
+    // arrive for every tile < upto (tiles in which this warp has no item left); an arrival for tile j (A buffer
+    // j & 1) is only legal once the MMA of tile j-2 has been committed, otherwise it would be counted in that
+    // tile's phase (a fresh barrier passes the parity-1 wait, so tiles 0 and 1 need no special case)
+    auto arrive_upto = [&](int upto) {
+      while (arrived < upto) {
+        umma::mbar_wait(bars + kBarAFree + (arrived & 1), (uint32_t)(((arrived >> 1) & 1) ^ 1));
+        if (lane == 0) umma::mbar_arrive(bars + kBarAFull + (arrived & 1));
+        ++arrived;
+      }
+    };
+
+    int it = 0, item = gw;
+    TileCtx cur;
+    bool valid = seek_item(p, gg, it, item, cur);
+    if (valid) {
+      int64_t ids[2];
+      load_item_ids(p, gg, cur, item, need_self, lane, ids);
+      write_item_ptrs(p, gg, cur, ids, lane, scr, self_row_bytes, nbr_row_bytes);
+      __syncwarp();
+    }
+    if (gw == 0) GLB_DBG(28);
+    while (valid) {
+      // ---- prefetch the ids of this warp's NEXT item (their latency hides behind the row loads below)
+      int nit = it, nitem = item + kGatherWarps;
+      TileCtx nxt;
+      const bool nvalid = seek_item(p, gg, nit, nitem, nxt);
+      int64_t nids[2];
+      if (nvalid) load_item_ids(p, gg, nxt, nitem, need_self, lane, nids);
+      // ---- current item
+      const SageSeg& sg = p.seg[cur.s];
+      const int k = sg.k;
+      const int rg = gg.n_slices == 1 ? item : item / gg.n_slices;
+      const int sl = gg.n_slices == 1 ? 0 : item - rg * gg.n_slices;
+      const int r = rg * gg.rpi + gg.sub;
+      const bool row_ok = r < cur.rows;
+      const int chunk = gg.lig + 32 * sl;                 // this lane's 16-byte chunk of the row
+      const int f0 = chunk * VEC;                         // first feature of the chunk
       const size_t coff = (size_t)chunk * 16;
       float acc[VEC], sv[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
-      if (f0 < d_nbr) {
-        const char* const* ptrs = sPtrN + (size_t)r * k;
-        Chunk<DT> sraw;
+      if (row_ok) {
+        // lanes whose chunk lies beyond the real feature width skip the loads altogether (their A
+        // columns are the zero K-padding); the others issue self + U neighbour loads back to back
+        const char* const* ptrs = scr + gg.sub * (k + 1);
         const bool self_ld = need_self && f0 < d_self;
-        if (self_ld) sraw.load(sPtrS[r] + coff);
-        for (int j0 = 0; j0 < k; j0 += U) {
-          Chunk<DT> raw[U];
+        Chunk<DT> sraw;
+        if (self_ld) sraw.load(ptrs[k] + coff);
+        if (has_nbr && f0 < d_nbr) {
+          for (int j0 = 0; j0 < k; j0 += U) {
+            Chunk<DT> raw[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + u < k ? j0 + u : k - 1;
-            raw[u].load(ptrs[j] + coff);
+            for (int u = 0; u < U; ++u) {
+              const int j = j0 + u < k ? j0 + u : k - 1;  // tail slots re-read the last row (masked below)
+              raw[u].load(ptrs[j] + coff);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (j0 + u < k) raw[u].add_to(acc);
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (j0 + u < k) raw[u].add_to(acc);
         }
         if (self_ld) sraw.add_to(sv);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
+        for (int i = 0; i < VEC; ++i) {                    // tail masks (dims that are not multiples of VEC)
           if (f0 + i >= d_self) sv[i] = 0.f;
           if (f0 + i >= d_nbr) acc[i] = 0.f;
         }
-      } else if (need_self && f0 < d_self) {
-        Chunk<DT> sraw;
-        sraw.load(sPtrS[r] + coff);
-        sraw.add_to(sv);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) if (f0 + i >= d_self) sv[i] = 0.f;
       }
-      const size_t a_off = (size_t)m * k_total;
-      __nv_bfloat16* asave = (p.a_save && m < p.M) ? p.a_save : nullptr;
-      if (has_self) put_chunk<VEC>(sA, asave, a_off, r, f0, sv);
+      // ---- A buffer it & 1 may only be written once the MMA of tile it-2 has consumed it
+      arrive_upto(it);
+      umma::mbar_wait(bars + kBarAFree + (it & 1), (uint32_t)(((it >> 1) & 1) ^ 1));
+      uint8_t* sAt = sA + (size_t)(it & 1) * a_buf_bytes;
+      if (row_ok) {
+        const int m = cur.m0 + r;
+        __nv_bfloat16* a_row = (sg.a_save && img == 0) ? sg.a_save + (size_t)m * k_total : nullptr;
+        if (has_self) put_chunk<VEC>(sAt, a_row, r, f0, sv);
+        if (has_nbr) {
+          float scale = 1.f;
+          if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
+          else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
-      put_chunk<VEC>(sA, asave, a_off, r, p.kp_self + f0, acc);
-    }
-  }
-  umma::fence_proxy_async_smem();
-  __syncthreads();
-
-  // --- GEMM: slice s of W (kNS output columns) x the whole A tile -> TMEM columns [s*kNS, (s+1)*kNS)
-  if (tid == 0) {
-    umma::tc_fence_after();
-    const uint32_t idesc = umma::make_idesc_bf16(kTileM, kNS);
-    for (int s = 0; s < n_slices_w; ++s) {
-      const int b = s & 1;
-      umma::mbar_wait(full + b, (uint32_t)((s >> 1) & 1));
-      umma::tc_fence_after();
-      for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t a_base = umma::smem_u32(sA + (size_t)kb * (kTileM * 128));
-        const uint32_t b_base = umma::smem_u32(sW + (size_t)b * slice_bytes + (size_t)kb * slice_kb_bytes);
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          umma::mma_bf16_ss(tmem_base + (uint32_t)(s * kNS), umma::make_desc_sw128(a_base + k4 * 32),
-                            umma::make_desc_sw128(b_base + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
-      }
-      umma::mma_commit(empty + b);                       // buffer b is free once these MMAs have read it
-      if (s >= 1 && s + 1 < n_slices_w) {                 // refill the buffer slice s-1 used with slice s+1
-        const int pb = (s - 1) & 1;
-        umma::mbar_wait(empty + pb, (uint32_t)(((s - 1) >> 1) & 1));
-        load_slice(s + 1, pb);
-      }
-    }
-    umma::mma_commit(bar_mma);
-  }
-  __syncwarp();
-  umma::mbar_wait(bar_mma, 0);
-  umma::tc_fence_after();
-
-  // --- epilogue: 16 warps = 4 TMEM lane quarters x 4 column groups
-  {
-    const int q = warp & 3, g = warp >> 2;
-    const int cols_per_group = p.N / 4;                   // multiple of 16 (N is a multiple of 64)
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = row < R && m < p.M;
-    for (int c0 = 0; c0 < cols_per_group; c0 += 16) {
-      const int n0 = g * cols_per_group + c0;
-      uint32_t v[16];
-      umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
-      umma::tmem_ld_wait();
-      if (row_ok && n0 < p.n_out) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (n0 + i >= p.n_out) continue;
-          float x = __uint_as_float(v[i]);
-          if (p.bias) x += __ldg(p.bias + n0 + i);
-          if (p.relu) x = fmaxf(x, 0.f);
-          if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)m * p.out_stride + n0 + i] = __float2bfloat16(x);
-          else reinterpret_cast<float*>(p.out)[(size_t)m * p.out_stride + n0 + i] = x;
+          for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
+          put_chunk<VEC>(sAt, a_row, r, p.kp_self + f0, acc);
         }
       }
+      if (!nvalid || nit != it) {                         // last item of this warp in tile `it`
+        umma::fence_proxy_async_smem();                   // generic-proxy st.shared -> visible to tcgen05 (async proxy)
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bars + kBarAFull + (it & 1));
+        arrived = it + 1;
+        if (gw == 0 && it < 4) GLB_DBG(30 + it * 3);
+      }
+      __syncwarp();                                       // every lane is done reading the scratch pointers
+      if (nvalid) {
+        write_item_ptrs(p, gg, nxt, nids, lane, scr, self_row_bytes, nbr_row_bytes);
+        __syncwarp();
+      }
+      it = nit; item = nitem; cur = nxt; valid = nvalid;
     }
+    arrive_upto(n_tiles_cta);
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Split path, stage 1 (used when rows live on peer GPUs): a small, maximum-occupancy kernel
-// (256 threads, ~40 registers -> 48-64 resident warps per SM) that only gathers + aggregates and
-// writes the bf16 A matrix [M, K_total] = [ self || agg(nbrs) ] (zero K-padding included).  NVLink
-// peer reads need far more requests in flight than the 1-CTA/SM fused kernel can keep up
-// (measured: 580-640 GB/s remote for this shape vs ~170 GB/s inside the fused kernel); stage 2 is
-// the same tcgen05 kernel fed from this (L2-resident) A instead of gathering itself.
-// ---------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(256, 5) gather_self_mean_kernel(const SageParams p) {
-  constexpr int VEC = Chunk<DT>::kVec;
-  constexpr int U = 4;
-  const int lane = threadIdx.x & 31;
-  const int k = p.k;
-  const int k_total = p.kp_self + p.kp_nbr;
-  const int lanes_row = p.kp_nbr / VEC;
-  const int lpr = lanes_row < 32 ? lanes_row : 32;
-  const int lshift = 31 - __clz(lpr);
-  const int rpi = 32 >> lshift;
-  const int n_slices = lanes_row > 32 ? lanes_row >> 5 : 1;
-  const int sub = lane >> lshift, lig = lane & (lpr - 1);
-  const int d_self = p.tself.dim, d_nbr = p.tnbr.dim;
-  const bool has_self = p.kp_self > 0;
-  const bool need_self = has_self || p.mode == kGcnMean;
-  const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-  const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
-  float scale = 1.f;
-  if (p.mode == kConcatMean) scale = k > 0 ? 1.f / (float)k : 0.f;
-  else if (p.mode == kGcnMean) scale = 1.f / (float)(k + 1);
-  const int64_t n_items = ((int64_t)p.M + rpi - 1) / rpi * n_slices;
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps) {
-    const int64_t rg = item / n_slices;
-    const int sl = (int)(item - rg * n_slices);
-    const int64_t m = rg * rpi + sub;
-    if (m >= p.M) continue;
-    const int chunk = lig + 32 * sl;
-    const int f0 = chunk * VEC;
-    const size_t coff = (size_t)chunk * 16;
-    float acc[VEC], sv[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
-    if (f0 < d_nbr || (need_self && f0 < d_self)) {
-      Chunk<DT> sraw;
-      const bool self_ld = need_self && f0 < d_self;
-      if (self_ld) {
-        sraw.load(vid_ptr(p.tself, p.self_vids ? __ldg(p.self_vids + m) : m, p.wshift_self, self_row_bytes, p.zero_row) + coff);
-      }
-      if (f0 < d_nbr) {
-        const int64_t base = m * k;
-        for (int j0 = 0; j0 < k; j0 += U) {
-          Chunk<DT> raw[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + u < k ? j0 + u : k - 1;
-            raw[u].load(vid_ptr(p.tnbr, p.nbr_vids ? __ldg(p.nbr_vids + base + j) : base + j, p.wshift_nbr, nbr_row_bytes, p.zero_row) + coff);
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (j0 + u < k) raw[u].add_to(acc);
-        }
-      }
-      if (self_ld) sraw.add_to(sv);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        if (f0 + i >= d_self) sv[i] = 0.f;
-        if (f0 + i >= d_nbr) acc[i] = 0.f;
-      }
-    }
-    __nv_bfloat16* out = p.a_save + (size_t)m * k_total;
-    auto store = [&](int kcol, const float (&v)[VEC]) {
-      if constexpr (VEC == 4) {
-        uint2 u2; u2.x = pack_bf16x2(v[0], v[1]); u2.y = pack_bf16x2(v[2], v[3]);
-        *reinterpret_cast<uint2*>(out + kcol) = u2;
-      } else {
-        uint4 u4; u4.x = pack_bf16x2(v[0], v[1]); u4.y = pack_bf16x2(v[2], v[3]);
-        u4.z = pack_bf16x2(v[4], v[5]); u4.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(out + kcol) = u4;
-      }
-    };
-    if (has_self) store(f0, sv);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] + (p.mode == kGcnMean ? sv[i] : 0.f)) * scale;
-    store(p.kp_self + f0, acc);
+  if (warp == 0) GLB_DBG(2);
+  if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[(size_t)blockIdx.x * 64 + 62] = (long long)gt;
   }
 }
 
@@ -1144,8 +647,15 @@ static int pad_k(int d) {
 
 int64_t sage_pad_k(int64_t d) { return pad_k((int)d); }
 
+// dynamic shared memory of the persistent kernel: A tile + W image + per-warp pointer scratch + bias + control + alignment slack
 int64_t sage_smem_bytes(int64_t k_total, int64_t N) {
-  return 1024 + (k_total / 64) * (kTileM * 128) + (k_total / 64) * N * 128 + 64;
+  return 1024 + kABufs * (k_total / 64) * (kTileM * 128) + (k_total / 64) * N * 128 + kGatherWarps * kScrCap * 8 + 256 * 4 + (kNumBars + 2) * 8;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
 }
 
 at::Tensor pack_weight_sw128(const at::Tensor& w_padded, int64_t N) {
@@ -1183,6 +693,202 @@ std::vector<at::Tensor> pack_weight_f32(const at::Tensor& w_padded, int64_t N, b
   return {img, want_rowmajor ? w16 : at::Tensor()};
 }
 
+static long long* g_dbg_ptr = nullptr;
+static int g_max_ctas = 0;     // 0 = all SMs; engines cap a launch that should co-run with another whole-SM kernel
+void sage_set_max_ctas(int64_t n) { g_max_ctas = (int)n; }
+static int usable_sms() { const int s = sm_count(); return g_max_ctas > 0 ? std::min(s, g_max_ctas) : s; }
+void sage_set_debug_trace(const c10::optional<at::Tensor>& t) {
+  g_dbg_ptr = (t.has_value() && t->defined()) ? reinterpret_cast<long long*>(t->data_ptr<int64_t>()) : nullptr;
+}
+
+static int log2_or_neg(int w) { int s = 0; while ((1 << s) < w) ++s; return (1 << s) == w ? s : -1; }
+
+static const char* zero_row_for(const at::TensorOptions& opts, int dev) {
+  static std::vector<at::Tensor> zero_rows(64);
+  if (!zero_rows[dev].defined()) zero_rows[dev] = at::zeros({1024}, opts.dtype(at::kFloat));
+  return reinterpret_cast<const char*>(zero_rows[dev].data_ptr());
+}
+
+// Balanced tiling: every tile should cost about the same number of row fetches ((k + 1) per destination
+// row, + 2 for the epilogue / A stores) and the tile count should just fill `waves` tiles per SM.
+static void plan_tiles(SageParams& p, int64_t rows_forced) {
+  const int sms = std::max(1, usable_sms() / p.n_imgs);
+  int64_t n128 = 0;
+  double total_cost = 0.0;
+  for (int s = 0; s < p.nseg; ++s) {
+    n128 += (p.seg[s].M + kTileM - 1) / kTileM;
+    total_cost += (double)p.seg[s].M * (p.seg[s].k + 3);
+  }
+  const int64_t waves = std::max<int64_t>(1, (n128 + sms - 1) / sms);
+  const double target = total_cost / (double)(sms * waves);
+  int tiles = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    SageSeg& sg = p.seg[s];
+    int64_t R = (int64_t)std::ceil(target / (double)(sg.k + 3));
+    R = (R + 7) / 8 * 8;
+    if (rows_forced > 0) R = (rows_forced + 7) / 8 * 8;
+    R = std::min<int64_t>(kTileM, std::max<int64_t>(8, R));
+    sg.R = (int)R;
+    sg.tile0 = tiles;
+    tiles += sg.M > 0 ? (int)((sg.M + R - 1) / R) : 0;
+  }
+  p.total_tiles = tiles;
+}
+
+static void launch_persist(SageParams& p, size_t smem, cudaStream_t stream) {
+  if (p.total_tiles == 0) return;
+  const unsigned grid = (unsigned)(p.n_imgs * std::min<int>(std::max(1, usable_sms() / p.n_imgs), p.total_tiles));
+  int kmax = 1;
+  for (int s = 0; s < p.nseg; ++s) kmax = std::max(kmax, p.seg[s].k);
+  const int u = kmax <= 4 ? 4 : (kmax % 5 == 0 || kmax > 12) ? 5 : 6;
+  const int dt = p.tnbr.dtype;
+#define LAUNCH(UU, DD)                                                                                     \
+  do {                                                                                                     \
+    static bool attr_done = false;                                                                         \
+    if (!attr_done) {                                                                                      \
+      C10_CUDA_CHECK(cudaFuncSetAttribute(sage_persist_kernel<UU, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit)); \
+      attr_done = true;                                                                                    \
+    }                                                                                                      \
+    sage_persist_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                                      \
+  } while (0)
+  if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
+  else         { if (u == 4) LAUNCH(4, 1); else if (u == 5) LAUNCH(5, 1); else LAUNCH(6, 1); }
+#undef LAUNCH
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// Multi-segment entry point.  All segments share the tables, the weight image, the bias and the output
+// layout; segment i reads ids (self_vids[i], nbr_vids[i]) - or identity ids self_base[i] + m /
+// nbr_base[i] + m*k + j when the tensors are None - and writes outs[i] ([M_i, n_out]) and optionally
+// a_saves[i] ([M_i, K_total] bf16, the [self || agg] rows for the backward pass).
+// ce = optional fused softmax cross-entropy on the output rows of segment 0:
+//   [labels_table(int64), seeds(int64)|undefined, loss(fp32 >=1), dlogits(bf16 [M, stride]), dbias(fp32)|undefined]
+void sage_fused_multi(const at::Tensor& tself_desc, const at::Tensor& tnbr_desc,
+                      const std::vector<c10::optional<at::Tensor>>& self_vids,
+                      const std::vector<c10::optional<at::Tensor>>& nbr_vids,
+                      const std::vector<int64_t>& self_base, const std::vector<int64_t>& nbr_base,
+                      const std::vector<int64_t>& Ms, const std::vector<int64_t>& ks,
+                      const std::vector<at::Tensor>& outs, const std::vector<c10::optional<at::Tensor>>& a_saves,
+                      int64_t mode, const at::Tensor& w_img, const c10::optional<at::Tensor>& bias, int64_t N,
+                      int64_t n_out, bool relu, bool out_bf16, int64_t rows_forced,
+                      const std::vector<c10::optional<at::Tensor>>& ce, int64_t ce_world, int64_t n_imgs) {
+  TORCH_CHECK(w_img.is_cuda() && w_img.scalar_type() == at::kBFloat16, "w_img must be CUDA bf16");
+  c10::cuda::CUDAGuard guard(w_img.device());
+  const int nseg = (int)Ms.size();
+  TORCH_CHECK(nseg >= 1 && nseg <= kMaxSegs, "1..", kMaxSegs, " segments per launch");
+  TORCH_CHECK((int)ks.size() == nseg && (int)outs.size() == nseg && (int)a_saves.size() == nseg &&
+              (int)self_vids.size() == nseg && (int)nbr_vids.size() == nseg && (int)self_base.size() == nseg &&
+              (int)nbr_base.size() == nseg, "per-segment argument lists must have equal lengths");
+  SageParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.tself = table_from_desc(tself_desc);
+  p.tnbr = table_from_desc(tnbr_desc);
+  p.nseg = nseg;
+  p.mode = (int)mode;
+  bool any_nbr = false;
+  for (int s = 0; s < nseg; ++s) any_nbr = any_nbr || ks[s] > 0;
+  p.kp_self = (mode == kGcnMean) ? 0 : pad_k(p.tself.dim);
+  p.kp_nbr = any_nbr ? pad_k(p.tnbr.dim) : 0;
+  if (mode == kGcnMean) TORCH_CHECK(p.tself.dim == p.tnbr.dim, "gcn mode needs equal dims");
+  const int k_total = p.kp_self + p.kp_nbr;
+  TORCH_CHECK(k_total >= 64, "empty layer");
+  TORCH_CHECK(N % 32 == 0 && N >= 32 && N <= 256, "padded N must be a multiple of 32 in [32, 256]");
+  TORCH_CHECK(n_out <= N && n_out >= 1);
+  TORCH_CHECK(n_imgs >= 1 && n_imgs <= 8 && (n_imgs == 1 || n_out == N), "bad image count");
+  p.n_imgs = (int)n_imgs;
+  TORCH_CHECK(w_img.numel() == n_imgs * (int64_t)k_total * N, "weight image size mismatch: expected ", n_imgs * k_total * N, " got ", w_img.numel());
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(w_img.data_ptr()) & 15) == 0, "weight image must be 16 B aligned");
+  const size_t smem = (size_t)sage_smem_bytes(k_total, N);
+  TORCH_CHECK(smem <= kSmemLimit, "tile does not fit in shared memory (", smem, " B); use the unfused path");
+  TORCH_CHECK(p.tself.dtype == p.tnbr.dtype && (p.tself.dtype == 0 || p.tself.dtype == 1),
+              "fused SAGE layer needs fp32 or bf16 self / neighbour tables of the same dtype");
+  TORCH_CHECK(p.kp_self == 0 || p.kp_nbr == 0 || p.kp_self == p.kp_nbr, "fused SAGE layer needs equally padded self / neighbour dims");
+  TORCH_CHECK((p.tself.stride * (p.tself.dtype == 0 ? 4 : 2)) % 16 == 0 && (p.tnbr.stride * (p.tnbr.dtype == 0 ? 4 : 2)) % 16 == 0,
+              "table rows must be 16-byte aligned (stride multiple of 4 fp32 / 8 bf16 elements)");
+  {
+    const int vec = p.tnbr.dtype == 0 ? 4 : 8;
+    const int lanes_row = (p.kp_nbr > 0 ? p.kp_nbr : p.kp_self) / vec;
+    const int rpi = lanes_row < 32 ? 32 / lanes_row : 1;
+    for (int s = 0; s < nseg; ++s)
+      TORCH_CHECK(rpi * (ks[s] + 1) <= kScrCap, "fan-out too large for the fused kernel's pointer scratch: k <= ", kScrCap / rpi - 1);
+  }
+  std::vector<at::Tensor> keep;
+  at::Tensor b;
+  if (bias.has_value() && bias->defined()) {
+    b = bias->contiguous();
+    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out, "bias must be fp32 [>= n_out]");
+    p.bias = b.data_ptr<float>();
+  }
+  p.out_stride = -1;
+  for (int s = 0; s < nseg; ++s) {
+    SageSeg& sg = p.seg[s];
+    sg.M = (int)Ms[s]; sg.k = (int)ks[s];
+    sg.self_base = self_base[s]; sg.nbr_base = nbr_base[s];
+    if (self_vids[s].has_value() && self_vids[s]->defined()) {
+      at::Tensor t = self_vids[s]->contiguous(); check_cuda_i64(t, "self_vids");
+      TORCH_CHECK(t.numel() == Ms[s]); keep.push_back(t); sg.self_vids = t.data_ptr<int64_t>();
+    }
+    if (nbr_vids[s].has_value() && nbr_vids[s]->defined()) {
+      at::Tensor t = nbr_vids[s]->contiguous(); check_cuda_i64(t, "nbr_vids");
+      TORCH_CHECK(t.numel() == Ms[s] * ks[s]); keep.push_back(t); sg.nbr_vids = t.data_ptr<int64_t>();
+    }
+    const at::Tensor& out = outs[s];
+    if (out.defined()) {
+      TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.size(0) == Ms[s] && out.size(1) == n_out && out.stride(1) == 1,
+                  "outs[i] must be [M_i, n_out] with unit inner stride");
+      TORCH_CHECK(out.scalar_type() == (out_bf16 ? at::kBFloat16 : at::kFloat), "out dtype mismatch");
+      TORCH_CHECK(p.out_stride < 0 || p.out_stride == out.stride(0), "all outputs must share the row stride");
+      p.out_stride = out.stride(0);
+      sg.out = reinterpret_cast<char*>(out.data_ptr());
+    }
+    if (a_saves[s].has_value() && a_saves[s]->defined()) {
+      const at::Tensor& a = *a_saves[s];
+      TORCH_CHECK(a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.size(0) == Ms[s] && a.size(1) == k_total &&
+                  a.stride(1) == 1 && a.stride(0) == k_total, "a_saves[i] must be a row-contiguous bf16 [M_i, K_total] view");
+      sg.a_save = reinterpret_cast<__nv_bfloat16*>(a.data_ptr());
+    }
+  }
+  if (p.out_stride < 0) p.out_stride = n_out;
+  p.w_img = w_img.data_ptr();
+  p.N = (int)N; p.n_out = (int)n_out; p.relu = relu ? 1 : 0; p.out_bf16 = out_bf16 ? 1 : 0;
+  const int need_cols = 2 * (int)N;
+  p.tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
+  p.wshift_self = log2_or_neg(p.tself.world);
+  p.wshift_nbr = log2_or_neg(p.tnbr.world);
+  p.zero_row = zero_row_for(w_img.options(), w_img.get_device());
+  if (!ce.empty()) {
+    TORCH_CHECK(ce.size() == 5 && nseg == 1 && N <= 64, "fused CE needs one segment and n_out <= 64");
+    TORCH_CHECK(p.seg[0].out != nullptr && !out_bf16, "fused CE needs the fp32 logits output (its second phase re-reads it)");
+    const at::Tensor& labels = *ce[0];
+    TORCH_CHECK(labels.is_cuda() && labels.scalar_type() == at::kLong);
+    p.ce_labels = labels.data_ptr<int64_t>();
+    if (ce[1].has_value() && ce[1]->defined()) {
+      TORCH_CHECK(ce[1]->scalar_type() == at::kLong && ce[1]->numel() == Ms[0] && ce[1]->is_contiguous());
+      p.ce_seeds = ce[1]->data_ptr<int64_t>();
+    } else {
+      TORCH_CHECK(labels.numel() >= Ms[0]);
+    }
+    p.ce_world = (int)std::max<int64_t>(ce_world, 1);
+    const at::Tensor& loss = *ce[2];
+    TORCH_CHECK(loss.is_cuda() && loss.scalar_type() == at::kFloat && loss.numel() >= 1);
+    p.ce_loss = loss.data_ptr<float>();
+    const at::Tensor& dl = *ce[3];
+    TORCH_CHECK(dl.is_cuda() && dl.scalar_type() == at::kBFloat16 && dl.dim() == 2 && dl.size(0) == Ms[0] && dl.stride(1) == 1 &&
+                dl.stride(0) >= n_out, "dlogits must be bf16 [M, >= n_out]");
+    p.ce_dlogits = reinterpret_cast<__nv_bfloat16*>(dl.data_ptr());
+    p.ce_dl_stride = (int)dl.stride(0);
+    if (ce[4].has_value() && ce[4]->defined()) {
+      TORCH_CHECK(ce[4]->scalar_type() == at::kFloat && ce[4]->numel() >= n_out);
+      p.ce_dbias = ce[4]->data_ptr<float>();
+    }
+    p.ce_inv_b = 1.f / (float)Ms[0];
+  }
+  p.dbg = g_dbg_ptr;
+  plan_tiles(p, rows_forced);
+  launch_persist(p, smem, at::cuda::getCurrentCUDAStream());
+}
+
+// single-segment convenience wrapper (autograd op in ops/sage.py)
 std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
                                            const c10::optional<at::Tensor>& self_vids,
                                            const at::Tensor& tnbr_desc,
@@ -1191,233 +897,40 @@ std::vector<at::Tensor> sage_fused_forward(const at::Tensor& tself_desc,
                                            const c10::optional<at::Tensor>& bias, int64_t N,
                                            int64_t n_out, bool relu, bool out_bf16, bool save_a, int64_t rows_per_cta,
                                            const c10::optional<at::Tensor>& out_buf,
-                                           const c10::optional<at::Tensor>& a_buf,
-                                           const c10::optional<at::Tensor>& debug_ts, int64_t gather_mode) {
-  // gather_mode 4 = split path: gather_self_mean_kernel -> A (global) -> tcgen05 kernel staged from A
-  TORCH_CHECK(w_img.is_cuda() && w_img.scalar_type() == at::kBFloat16, "w_img must be CUDA bf16");
+                                           const c10::optional<at::Tensor>& a_buf) {
   c10::cuda::CUDAGuard guard(w_img.device());
-  SageParams p;
-  p.tself = table_from_desc(tself_desc);
-  p.tnbr = table_from_desc(tnbr_desc);
-  p.M = (int)M; p.k = (int)k; p.mode = (int)mode;
-  p.kp_self = (mode == kGcnMean) ? 0 : pad_k(p.tself.dim);
-  p.kp_nbr = pad_k(p.tnbr.dim);
-  if (mode == kGcnMean) TORCH_CHECK(p.tself.dim == p.tnbr.dim, "gcn mode needs equal dims");
-  const int k_total = p.kp_self + p.kp_nbr;
-  TORCH_CHECK(N % 64 == 0 && N >= 64 && N <= 256, "padded N must be a multiple of 64 in [64, 256]");
-  TORCH_CHECK(n_out <= N && n_out >= 1);
-  TORCH_CHECK(w_img.numel() == (int64_t)k_total * N, "weight image size mismatch: expected ", k_total * N);
-  TORCH_CHECK((reinterpret_cast<uintptr_t>(w_img.data_ptr()) & 15) == 0, "weight image must be 16 B aligned");
-  size_t smem = (size_t)sage_smem_bytes(k_total, N);   // + locator staging, added below
-  TORCH_CHECK(smem <= 232448, "tile does not fit in shared memory (", smem, " B); use the unfused path");
-  at::Tensor sv, nv, b;
-  p.self_vids = nullptr; p.nbr_vids = nullptr; p.bias = nullptr;
-  if (self_vids.has_value()) { sv = self_vids->contiguous(); check_cuda_i64(sv, "self_vids");
-    TORCH_CHECK(sv.numel() == M); p.self_vids = sv.data_ptr<int64_t>(); }
-  if (nbr_vids.has_value()) { nv = nbr_vids->contiguous(); check_cuda_i64(nv, "nbr_vids");
-    TORCH_CHECK(nv.numel() == M * k); p.nbr_vids = nv.data_ptr<int64_t>(); }
-  if (bias.has_value()) { b = bias->contiguous();
-    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out, "bias must be fp32 [>= n_out]");
-    p.bias = b.data_ptr<float>(); }
   auto opts = w_img.options();
-  at::Tensor out;
-  if (out_buf.has_value()) {
-    out = *out_buf;
-    TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.size(0) == M && out.size(1) == n_out && out.stride(1) == 1,
-                "out_buf must be [M, n_out] with unit inner stride");
-    TORCH_CHECK(out.scalar_type() == (out_bf16 ? at::kBFloat16 : at::kFloat), "out_buf dtype mismatch");
-  } else {
-    out = at::empty({M, n_out}, opts.dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
-  }
+  at::Tensor out = out_buf.has_value() && out_buf->defined() ? *out_buf
+                                                             : at::empty({M, n_out}, opts.dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
   at::Tensor a_save;
-  p.a_save = nullptr;
   if (save_a) {
-    if (a_buf.has_value()) {
-      a_save = *a_buf;
-      TORCH_CHECK(a_save.scalar_type() == at::kBFloat16 && a_save.dim() == 2 && a_save.size(0) == M &&
-                  a_save.size(1) == k_total && a_save.stride(1) == 1 && a_save.stride(0) == k_total,
-                  "a_buf must be a row-contiguous bf16 [M, K_total] view");
-    } else {
-      a_save = at::empty({M, (int64_t)k_total}, opts.dtype(at::kBFloat16));
-    }
-    p.a_save = reinterpret_cast<__nv_bfloat16*>(a_save.data_ptr());
+    const TableView ts = table_from_desc(tself_desc), tn = table_from_desc(tnbr_desc);
+    const int64_t k_total = ((mode == kGcnMean) ? 0 : pad_k(ts.dim)) + (k > 0 ? pad_k(tn.dim) : 0);
+    a_save = a_buf.has_value() && a_buf->defined() ? *a_buf : at::empty({M, k_total}, opts.dtype(at::kBFloat16));
   }
-  p.a_src = nullptr;
-  p.w_img = w_img.data_ptr();
-  p.out = out.data_ptr();
-  p.out_stride = out.stride(0);
-  p.N = (int)N; p.n_out = (int)n_out; p.relu = relu ? 1 : 0; p.out_bf16 = out_bf16 ? 1 : 0;
-  p.tmem_cols = N <= 64 ? 64 : N <= 128 ? 128 : 256;
-  if (M == 0) return {out, save_a ? a_save : at::Tensor()};
-  // spread small M over the whole chip: aim for >= 2 CTAs' worth of work per SM-wave but never
-  // more than 128 rows per CTA; keep R a multiple of 8 (one 1024-byte swizzle atom)
-  int R = kTileM;
-  if (rows_per_cta > 0) R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (rows_per_cta + 7) / 8 * 8));
-  else {
-    // balance whole waves: w = number of 148-CTA waves needed at <= 128 rows per CTA, then the
-    // smallest R (multiple of 8) that still fits M into w waves
-    const int64_t sms = 148;
-    int64_t waves = (M + sms * kTileM - 1) / (sms * kTileM);
-    int64_t want = (M + sms * waves - 1) / (sms * waves);
-    R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (want + 7) / 8 * 8));
-  }
-  // shared-memory row-pointer staging: 8 B per (row, neighbour) + 8 B per row; shrink R until it fits
-  const size_t bar_bytes = 32 + 2 * kMaxSlots * 8;          // control words + TMA ring barriers
-  while (R > 8 && smem + bar_bytes + (size_t)R * (k + 1) * 8 > 232448) R -= 8;
-  TORCH_CHECK(smem + bar_bytes + (size_t)R * (k + 1) * 8 <= 232448, "fan-out too large for the fused kernel's id staging");
-  smem += bar_bytes + (size_t)R * (k + 1) * 8;
-  p.rows_per_cta = R;
-  p.debug_ts = nullptr;
-  if (debug_ts.has_value()) {
-    TORCH_CHECK(debug_ts->scalar_type() == at::kLong && debug_ts->numel() >= (int64_t)((M + R - 1) / R) * 16);
-    p.debug_ts = reinterpret_cast<long long*>(debug_ts->data_ptr<int64_t>());
-  }
-  TORCH_CHECK(p.tself.dtype == p.tnbr.dtype, "fused SAGE layer needs self / neighbour tables of the same dtype");
-  TORCH_CHECK(p.kp_self == 0 || p.kp_self == p.kp_nbr, "fused SAGE layer needs equally padded self / neighbour dims");
-  auto log2_or_neg = [](int w) { int s = 0; while ((1 << s) < w) ++s; return (1 << s) == w ? s : -1; };
-  p.wshift_self = log2_or_neg(p.tself.world);
-  p.wshift_nbr = log2_or_neg(p.tnbr.world);
-  TORCH_CHECK((p.tself.stride * (p.tself.dtype == 0 ? 4 : 2)) % 16 == 0 && (p.tnbr.stride * (p.tnbr.dtype == 0 ? 4 : 2)) % 16 == 0,
-              "table rows must be 16-byte aligned (stride multiple of 4 fp32 / 8 bf16 elements)");
-  {
-    static std::vector<at::Tensor> zero_rows(64);
-    int dev = w_img.get_device();
-    if (!zero_rows[dev].defined()) zero_rows[dev] = at::zeros({1024}, opts.dtype(at::kFloat));
-    p.zero_row = reinterpret_cast<const char*>(zero_rows[dev].data_ptr());
-  }
-  unsigned grid = (unsigned)((M + R - 1) / R);
-  auto stream = at::cuda::getCurrentCUDAStream();
-  const int u = k <= 4 ? 4 : (k % 5 == 0 || k > 12) ? 5 : 6;
-  const int dt = p.tnbr.dtype;
-  if (gather_mode == 5) {
-    // EXPERIMENTAL two-CTA-per-SM variant (see sage_fused_occ2_kernel): falls through to the default kernel when
-    // the tile does not fit twice into an SM.
-    const size_t nkb5 = (size_t)k_total / 64;
-    const size_t base5 = nkb5 * (kTileM * 128) + 2 * nkb5 * (kNS * 128) + 64 + 1024;     // A + W ring + barriers + alignment
-    const int64_t per_wave = 148 * 2;
-    const int64_t waves5 = (M + per_wave * kTileM - 1) / (per_wave * kTileM);
-    int R5 = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, ((M + per_wave * waves5 - 1) / (per_wave * waves5) + 7) / 8 * 8));
-    if (rows_per_cta > 0) R5 = R;
-    const size_t limit5 = 112 * 1024;      // 2 x (dynamic + 1 KB static + 1 KB reserved) <= 228 KB per SM
-    while (R5 > 8 && base5 + (size_t)R5 * (k + 1) * 8 > limit5) R5 -= 8;
-    if (base5 + (size_t)R5 * (k + 1) * 8 <= limit5 && !p.debug_ts) {
-      const size_t smem5 = base5 + (size_t)R5 * (k + 1) * 8;
-      p.rows_per_cta = R5;
-      const unsigned grid5 = (unsigned)((M + R5 - 1) / R5);
-#define LAUNCH5(UU, DD)                                                                           \
-  do {                                                                                            \
-    C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_occ2_kernel<UU, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit5)); \
-    sage_fused_occ2_kernel<UU, DD><<<grid5, kOccThreads, smem5, stream>>>(p);                     \
-  } while (0)
-      if (dt == 0) { if (u == 4) LAUNCH5(4, 0); else if (u == 5) LAUNCH5(5, 0); else LAUNCH5(6, 0); }
-      else         { if (u == 4) LAUNCH5(4, 1); else if (u == 5) LAUNCH5(5, 1); else LAUNCH5(6, 1); }
-#undef LAUNCH5
-      C10_CUDA_KERNEL_LAUNCH_CHECK();
-      return {out, save_a ? a_save : at::Tensor()};
-    }
-    p.rows_per_cta = R;
-  }
-  // MEASURED (2 GPUs, fp32 rows): fused register path 7.7k steps/s vs split 6.9k - the remote rows are
-  // NVLink-bandwidth bound either way (394 GB/s achieved vs 580 GB/s best random-row rate), so the
-  // split path stays opt-in.
-  const bool split = gather_mode == 4;
-  if (split) {
-    if (!a_save.defined()) {
-      a_save = at::empty({M, (int64_t)k_total}, opts.dtype(at::kBFloat16));
-      p.a_save = reinterpret_cast<__nv_bfloat16*>(a_save.data_ptr());
-    }
-    const int lanes_row = p.kp_nbr / (dt == 0 ? 4 : 8);
-    const int rpi = lanes_row < 32 ? 32 / lanes_row : 1;
-    const int n_slices = lanes_row > 32 ? lanes_row / 32 : 1;
-    const int64_t items = (M + rpi - 1) / rpi * n_slices;
-    const unsigned gblocks = (unsigned)std::min<int64_t>((items + 7) / 8, 148 * 8);
-    if (dt == 0) gather_self_mean_kernel<0><<<gblocks, 256, 0, stream>>>(p);
-    else         gather_self_mean_kernel<1><<<gblocks, 256, 0, stream>>>(p);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    p.a_src = p.a_save;
-    p.a_save = nullptr;
-  }
-  // gather_mode: 1 = register-staged loads, 2 = TMA bulk copies into the shared-memory ring,
-  // 3 = per-lane cp.async into the same ring; 0 = auto = cp.async ring for multi-wave launches and
-  // whenever rows may live on a peer GPU, register-staged otherwise.  MEASURED (profiles/): per-row cp.async.bulk copies of 400 B cost
-  // ~110 cycles each in the TMA unit (1408 copies -> 153 k cycles per 128-row tile, 0.76 TB/s), 4x
-  // slower than the register path (36 k cycles) - the ring variant is kept for wide rows only.
-  const size_t slot_bytes = (size_t)(k + 1) * (size_t)p.tnbr.stride * (dt == 0 ? 4 : 2);
-  const bool tma_ok = k >= 1 && slot_bytes <= (size_t)k_total / 64 * N * 128;
-  bool use_tma = gather_mode == 2;
-  // cp.async ring (mode 3): needs >= kProducers slots
-  const bool async_ok = k >= 1 && slot_bytes * kProducers <= (size_t)k_total / 64 * N * 128;
-  bool use_async = gather_mode == 3 && async_ok;   // MEASURED slower than the register path (2-GPU: 5.4k vs 7.7k steps/s)
-  use_tma = use_tma && tma_ok;
-#define SET_ATTR(KERNEL)                                                                          \
-  do {                                                                                            \
-    static bool attr_done = false;                                                                \
-    if (!attr_done) {                                                                             \
-      C10_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
-      attr_done = true;                                                                           \
-    }                                                                                             \
-  } while (0)
-#define LAUNCH(UU, DD)                                                                            \
-  do {                                                                                            \
-    SET_ATTR((sage_fused_fwd_kernel<UU, DD>));                                                    \
-    sage_fused_fwd_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                           \
-  } while (0)
-  if (use_async) {
-    if (dt == 0) { SET_ATTR(sage_fused_async_kernel<0>); sage_fused_async_kernel<0><<<grid, kThreads, smem, stream>>>(p); }
-    else         { SET_ATTR(sage_fused_async_kernel<1>); sage_fused_async_kernel<1><<<grid, kThreads, smem, stream>>>(p); }
-  } else if (use_tma) {
-    if (dt == 0) { SET_ATTR(sage_fused_tma_kernel<0>); sage_fused_tma_kernel<0><<<grid, kThreads, smem, stream>>>(p); }
-    else         { SET_ATTR(sage_fused_tma_kernel<1>); sage_fused_tma_kernel<1><<<grid, kThreads, smem, stream>>>(p); }
-  } else if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
-  else                { if (u == 4) LAUNCH(4, 1); else if (u == 5) LAUNCH(5, 1); else LAUNCH(6, 1); }
-#undef LAUNCH
-#undef SET_ATTR
-  C10_CUDA_KERNEL_LAUNCH_CHECK();
-  return {out, (save_a || split) ? a_save : at::Tensor()};
+  if (M == 0) return {out, a_save};
+  sage_fused_multi(tself_desc, tnbr_desc, {self_vids}, {nbr_vids}, {0}, {0}, {M}, {k}, {out},
+                   {save_a ? c10::optional<at::Tensor>(a_save) : c10::nullopt}, mode, w_img, bias, N, n_out, relu, out_bf16,
+                   rows_per_cta, {}, 1, 1);
+  return {out, a_save};
 }
 
 // K7 standalone: out = act(A . W^T + b) for a dense bf16 A [M, K] (K multiple of 64, <= 512; N <= 256)
-// on the same tcgen05 / TMEM tile kernel (A staged from global memory instead of gathered).
+// on the same persistent tcgen05 / TMEM kernel (the "gather" degenerates to staging A's rows).
 at::Tensor tc_linear_forward(const at::Tensor& a, const at::Tensor& w_img, const c10::optional<at::Tensor>& bias,
                              int64_t N, int64_t n_out, bool relu, bool out_bf16) {
-  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.is_contiguous(),
-              "A must be a contiguous CUDA bf16 [M, K] matrix");
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.stride(1) == 1,
+              "A must be a CUDA bf16 [M, K] matrix with unit inner stride");
   const int64_t M = a.size(0), K = a.size(1);
-  TORCH_CHECK(K % 64 == 0 && K >= 64 && K <= 512, "K must be a multiple of 64 in [64, 512]");
-  TORCH_CHECK(N % 64 == 0 && N >= 64 && N <= 256 && n_out <= N && n_out >= 1);
-  TORCH_CHECK(w_img.numel() == K * N && w_img.scalar_type() == at::kBFloat16, "weight image size mismatch");
+  TORCH_CHECK(K % 8 == 0 && K >= 8 && K <= 512 && a.stride(0) % 8 == 0, "K must be a multiple of 8 in [8, 512]");
   c10::cuda::CUDAGuard guard(a.device());
-  SageParams p;
-  std::memset(&p, 0, sizeof(p));
-  p.tself.world = 1; p.tnbr.world = 1;
-  p.tself.dtype = 1; p.tnbr.dtype = 1;
-  p.M = (int)M; p.k = 0; p.mode = kConcatMean;
-  p.kp_self = 0; p.kp_nbr = (int)K;
-  at::Tensor b;
-  if (bias.has_value()) { b = bias->contiguous();
-    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out); p.bias = b.data_ptr<float>(); }
   auto out = at::empty({M, n_out}, a.options().dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
-  p.w_img = w_img.data_ptr(); p.out = out.data_ptr(); p.out_stride = n_out;
-  p.N = (int)N; p.n_out = (int)n_out; p.relu = relu ? 1 : 0; p.out_bf16 = out_bf16 ? 1 : 0;
-  p.tmem_cols = N <= 64 ? 64 : N <= 128 ? 128 : 256;
-  p.a_src = reinterpret_cast<const __nv_bfloat16*>(a.data_ptr());
   if (M == 0) return out;
-  size_t smem = (size_t)sage_smem_bytes(K, N);
-  TORCH_CHECK(smem <= 232448, "tile does not fit in shared memory");
-  const int64_t sms = 148;
-  int64_t waves = (M + sms * kTileM - 1) / (sms * kTileM);
-  int64_t want = (M + sms * waves - 1) / (sms * waves);
-  int R = (int)std::min<int64_t>(kTileM, std::max<int64_t>(8, (want + 7) / 8 * 8));
-  p.rows_per_cta = R;
-  smem += 32 + 2 * kMaxSlots * 8 + 64;
-  unsigned grid = (unsigned)((M + R - 1) / R);
-  static bool attr_done = false;
-  if (!attr_done) {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(sage_fused_fwd_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
-  }
-  sage_fused_fwd_kernel<4, 1><<<grid, kThreads, smem, at::cuda::getCurrentCUDAStream()>>>(p);
-  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  std::vector<int64_t> d(4 + 2 * kMaxWorld, 0);
+  d[0] = 1; d[1] = K; d[2] = a.stride(0); d[3] = 1; d[4] = M; d[4 + kMaxWorld] = reinterpret_cast<int64_t>(a.data_ptr());
+  at::Tensor desc = at::from_blob(d.data(), {(int64_t)d.size()}, at::kLong).clone();
+  sage_fused_multi(desc, desc, {c10::nullopt}, {c10::nullopt}, {0}, {0}, {M}, {0}, {out}, {c10::nullopt}, kConcatMean, w_img, bias,
+                   N, n_out, relu, out_bf16, 0, {}, 1, 1);
   return out;
 }
 

@@ -231,14 +231,22 @@ std::vector<at::Tensor> sample_neighbors(const at::Tensor& csr_desc, const at::T
                                          int64_t k, int64_t strategy, int64_t filter_mode,
                                          const c10::optional<at::Tensor>& filter,
                                          bool padding_circular, int64_t retry, int64_t default_id,
-                                         const at::Tensor& rng_state, int64_t salt, bool want_eids) {
+                                         const at::Tensor& rng_state, int64_t salt, bool want_eids,
+                                         const c10::optional<at::Tensor>& out_buf) {
   check_cuda_i64(src, "src");
   TORCH_CHECK(rng_state.is_cuda() && rng_state.scalar_type() == at::kLong && rng_state.numel() >= 2,
               "rng_state must be a CUDA int64[2] tensor");
   c10::cuda::CUDAGuard guard(src.device());
   CsrView g = csr_from_desc(csr_desc);
   int64_t B = src.numel();
-  auto nbr = at::empty({B, k}, src.options());
+  at::Tensor nbr;
+  if (out_buf.has_value() && out_buf->defined()) {
+    check_cuda_i64(*out_buf, "out");
+    TORCH_CHECK(out_buf->is_contiguous() && out_buf->numel() == B * k, "out must be a contiguous int64 buffer of B*k elements");
+    nbr = out_buf->view({B, k});
+  } else {
+    nbr = at::empty({B, k}, src.options());
+  }
   at::Tensor eid;
   if (want_eids) eid = at::empty({B, k}, src.options());
   if (B * k == 0) return {nbr, want_eids ? eid : at::Tensor()};

@@ -16,7 +16,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cfloat>
-#include "common.cuh"
+#include "host_utils.h"
 
 namespace glb {
 
@@ -231,14 +231,14 @@ void sage_bwd_input(const c10::optional<at::Tensor>& dA_self, const c10::optiona
   if (v8) {
     constexpr int U = 2;
     TORCH_CHECK(n < (int64_t)1 << 31, "too many rows");
-    int blocks8 = (int)std::min<int64_t>(148 * 4, ((n + U - 1) / U * 32 + 255) / 256);
+    int blocks8 = (int)std::min<int64_t>((int64_t)sm_count() * 4, ((n + U - 1) / U * 32 + 255) / 256);
     sage_bwd_input_v8_kernel<U><<<blocks8, 256, (size_t)d * sizeof(float), at::cuda::getCurrentCUDAStream()>>>(
         ps, pn, ld_da, (int)kp_self, (int)std::max<int64_t>(k, 1), (float)scale, ph, ld_h,
         reinterpret_cast<__nv_bfloat16*>(out.data_ptr()), out.stride(0), n, d, db);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return;
   }
-  int blocks = (int)std::min<int64_t>(148 * 4, (n * 32 + 255) / 256);
+  int blocks = (int)std::min<int64_t>((int64_t)sm_count() * 4, (n * 32 + 255) / 256);
   sage_bwd_input_kernel<<<blocks, 256, (size_t)d * sizeof(float), at::cuda::getCurrentCUDAStream()>>>(
       ps, pn, ld_da, (int)kp_self, (int)std::max<int64_t>(k, 1), (float)scale, ph, ld_h,
       reinterpret_cast<__nv_bfloat16*>(out.data_ptr()), out.stride(0), n, d, db);

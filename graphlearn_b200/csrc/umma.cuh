@@ -68,17 +68,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
-// 2-D tiled TMA load (SASS: UTMALDG) through a CUtensorMap in param/const/global space
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0,
-                                            int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
-}
 
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -107,6 +96,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
         "=r"(v[15])
+      : "r"(taddr));
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() {
@@ -151,6 +152,32 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
   d |= 1u << 4;                        // c_format  = F32
   d |= 1u << 7;                        // a_format  = BF16
   d |= 1u << 10;                       // b_format  = BF16
+  d |= (uint32_t)(N >> 3) << 17;       // n_dim
+  d |= (uint32_t)(M >> 4) << 24;       // m_dim
+  return d;
+}
+
+// MN-major, 128-byte-swizzled operand tile (cute make_umma_desc<Major::MN>, SWIZZLE_128B, in uint128 units
+// ((8,n),(8,k)):((1,LBO),(8,SBO))): rows of 64 MN-elements (128 B) indexed by K, 8-row groups of 1024 B
+// (SBO = stride between 8-row K groups), 64-element MN groups `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor with selectable operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16_major(int M, int N, int a_mn, int b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format  = F32
+  d |= 1u << 7;                        // a_format  = BF16
+  d |= 1u << 10;                       // b_format  = BF16
+  d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn ? 1 : 0) << 16;
   d |= (uint32_t)(N >> 3) << 17;       // n_dim
   d |= (uint32_t)(M >> 4) << 24;       // m_dim
   return d;

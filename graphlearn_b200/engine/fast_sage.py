@@ -42,8 +42,7 @@ from ..store.shards import CsrShard, NodeTable
 class FastSageTrainer:
     def __init__(self, rt: Runtime, nodes: NodeTable, csr: CsrShard, model, fanouts: Sequence[int], batch_size: int,
                  lr: float = 3e-3, strategy: str = "random", use_cuda_graph: bool = True, allreduce: str = "peer",
-                 seed: int = 0, gather_mode: int = 0):
-        self.gather_mode = int(gather_mode)
+                 seed: int = 0):
         assert rt.is_cuda, "FastSageTrainer is the CUDA engine; use SageTrainer for the portable path"
         self.rt, self.nodes, self.csr, self.model = rt, nodes, csr, model
         self.fanouts = list(fanouts)
@@ -72,12 +71,13 @@ class FastSageTrainer:
         self.convs = convs
         for c in convs:
             assert c.agg_type in ("mean", "sum"), "fast engine supports mean / sum aggregation"
-            assert sage_ops.fused_supported(c.in_self, c.in_nbr, c.out_dim, c.agg_type)
+            assert sage_ops.fused_supported(c.in_self, c.in_nbr, c.out_dim, c.agg_type, max(self.fanouts))
         # per layer l (1-based): segments i = 0..L-l, rows concatenated
         self.seg_off: List[List[int]] = []
         self.H: List[Optional[torch.Tensor]] = []      # layer outputs (bf16; last layer fp32 logits)
         self.A: List[torch.Tensor] = []                # saved [self || agg] tiles (bf16)
         self.dZ: List[torch.Tensor] = []
+        self.dZp: List[torch.Tensor] = []              # dZ with the row padded to the K padding of the dA GEMM
         self.dA: List[Optional[torch.Tensor]] = []
         for l in range(1, self.L + 1):
             c = convs[l - 1]
@@ -89,21 +89,42 @@ class FastSageTrainer:
             self.seg_off.append(offs)
             last = l == self.L
             kt = c.weight_p.size(1)
-            self.H.append(torch.zeros(rows, c.out_dim, dtype=torch.float32 if last else torch.bfloat16, device=dev))
+            hw = sage_ops.pad_n(c.out_dim) if last else c.out_dim      # padded logits rows: vectorised epilogue stores
+            self.H.append(torch.zeros(rows, hw, dtype=torch.float32 if last else torch.bfloat16, device=dev)[:, :c.out_dim])
             self.A.append(torch.zeros(rows, kt, dtype=torch.bfloat16, device=dev))
-            self.dZ.append(torch.zeros(rows, c.out_dim, dtype=torch.bfloat16, device=dev))
+            self.dZp.append(torch.zeros(rows, sage_ops.pad_k(c.out_dim), dtype=torch.bfloat16, device=dev))
+            self.dZ.append(self.dZp[-1][:, :c.out_dim])
             self.dA.append(torch.zeros(rows, kt, dtype=torch.bfloat16, device=dev) if l > 1 else None)
+        # persistent bf16 weight images (written by the fused Adam kernel at the end of every step)
+        self.img: List[torch.Tensor] = []
+        self.img_t: List[Optional[torch.Tensor]] = []
+        mats = []
+        for l in range(1, self.L + 1):
+            c = convs[l - 1]
+            n_out, kt = c.weight_p.shape
+            N = sage_ops.pad_n(n_out)
+            self.img.append(torch.zeros(kt * N, dtype=torch.bfloat16, device=dev))
+            kpad = self.dZp[l - 1].size(1)
+            self.img_t.append(torch.zeros((kt + 255) // 256, kpad * 256, dtype=torch.bfloat16, device=dev) if l > 1 else None)
+            mats.append([model._glb_param_offsets[id(c.weight_p)], n_out, kt, N, self.img[-1].data_ptr(),
+                         self.img_t[-1].data_ptr() if l > 1 else 0, kpad, 256])
+        self._mats = torch.tensor(mats, dtype=torch.int64)
+        self.loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.repack()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._post_loss_hook = None
-        self._sides = (torch.cuda.Stream(), torch.cuda.Stream())
-        self._side_c = torch.cuda.Stream()
+        self._pre_opt_join = None
+        self._skip_opt = False          # tests: stop before the optimiser to inspect the gradients
+        # training branches run at high priority: pending CTAs of the whole-SM persistent kernels must win SM slots
+        # against the (low-priority) next-batch sampling branch
+        self._sides = (torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=-1))
+        self._side_c = torch.cuda.Stream(priority=-1)
         self._ev_pack = torch.cuda.Event()
         self._ev_zero = torch.cuda.Event()
         self.use_graph = bool(use_cuda_graph)
         self._steps = 0
         self.h_seeds = torch.zeros(self.B, dtype=torch.int64).pin_memory()
         self.h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
-        self._mm_out_ok = None
         self._h_seeds2 = [torch.zeros(self.B, dtype=torch.int64).pin_memory() for _ in range(2)]
         self._h_loss2 = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
         # device-side aliases of the pinned host buffers (cudaHostAlloc memory is UVA-mapped)
@@ -114,20 +135,6 @@ class FastSageTrainer:
             e.record()
 
     # ------------------------------------------------------------------ helpers
-    def _mm_into(self, out_f32: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
-        """out (fp32, may be a view of the flat grad buffer) = a @ b for bf16 a, b."""
-        if self._mm_out_ok is None:
-            try:
-                torch.mm(a, b, out_dtype=torch.float32, out=out_f32)
-                self._mm_out_ok = True
-                return
-            except Exception:
-                self._mm_out_ok = False
-        if self._mm_out_ok:
-            torch.mm(a, b, out_dtype=torch.float32, out=out_f32)
-        else:
-            out_f32.copy_(torch.mm(a, b, out_dtype=torch.float32))
-
     def sample(self, seeds: torch.Tensor):
         hops = [seeds]
         cur = seeds
@@ -150,29 +157,15 @@ class FastSageTrainer:
         C, L = self.C, self.L
         main = torch.cuda.current_stream()
         sA, sB = self._sides
-        # ---- head: gradient zeroing (side B) || pack W_1 (main) || pack W_2.. (side C); layer 1 only waits
-        # for its own weight image
         sC = self._side_c
-        sB.wait_stream(main)
-        sC.wait_stream(main)
-        with torch.cuda.stream(sB):
-            self.g_store.zero_()
-            self._ev_zero.record(sB)
-        packs = [None] * L
-        with torch.cuda.stream(sC):
-            for l in range(2, L + 1):
-                c = self.convs[l - 1]
-                packs[l - 1] = C.pack_weight_f32(c.weight_p.detach(), sage_ops.pad_n(c.out_dim), True)
-            self._ev_pack.record(sC)
-        packs[0] = C.pack_weight_f32(self.convs[0].weight_p.detach(), sage_ops.pad_n(self.convs[0].out_dim), False)
+        # no head work: the gradients were zeroed and the bf16 weight images refreshed by the fused Adam kernel of
+        # the previous step (``repack()`` covers the very first step and externally modified weights)
         if pipe is None:
             # plain schedule: sample this step's batch, then train on it
             seeds = self.seeds
             hops = self.sample(seeds)
             # counters advance once the sampling kernels have consumed the RNG offset; needed again only by Adam
-            sB.wait_stream(main)
-            with torch.cuda.stream(sB):
-                self.opt.advance(self.rng.state)
+            self.opt.advance(self.rng.state)
         else:
             # pipelined schedule (graph capture): train on the batch sampled by the PREVIOUS replay while a
             # forked branch stages + samples the NEXT batch (the reference's sampling || training pipeline:
@@ -185,87 +178,111 @@ class FastSageTrainer:
             with torch.cuda.stream(sS):
                 if host_slot is not None:
                     # zero-copy staging: a tiny copy KERNEL reads the UVA-mapped pinned buffer over PCIe
-                    self._hops[nxt][0].copy_(self._h_seeds_dev[host_slot])
+                    C.copy_i64(self._hops[nxt][0], self._h_seeds_dev[host_slot])
                 nb = self._hops[nxt][0]
                 for i, k in enumerate(self.fanouts):
-                    out, _ = S.sample_neighbors(self.csr, nb, k, self.strategy, want_eids=False, rng=self.rng, salt=i + 1)
-                    self._hops[nxt][i + 1].copy_(out.reshape(-1))
+                    S.sample_neighbors(self.csr, nb, k, self.strategy, want_eids=False, rng=self.rng, salt=i + 1,
+                                       out=self._hops[nxt][i + 1])
                     nb = self._hops[nxt][i + 1]
                 self.opt.advance(self.rng.state)
-        # ---- forward
+        # ---- forward: ONE persistent launch per layer covering all of its hop-pair segments; the top layer's
+        # launch also computes the loss, dlogits and the bias gradient in its epilogue (fused CE)
+        top = self.convs[L - 1]
         for l in range(1, L + 1):
-            if l == 2:
-                main.wait_event(self._ev_pack)
             c = self.convs[l - 1]
             last = l == L
             N = sage_ops.pad_n(c.out_dim)
-            img = packs[l - 1][0]
+            img = self.img[l - 1]
             offs = self.seg_off[l - 1]
             mode = sage_ops.MODE[c.agg_type]
             nseg = L - l + 1
-            if nseg > 1:
-                sA.wait_stream(main)
-            for i in range(nseg):
-                out = self.H[l - 1][offs[i]:offs[i + 1]]
-                a = self.A[l - 1][offs[i]:offs[i + 1]]
-                k = self.fanouts[i]
-                with torch.cuda.stream(sA if (i == 0 and nseg > 1) else main):
-                    if l == 1:
-                        d = self.nodes.feat_desc
-                        C.sage_fused_forward(d, hops[i], d, hops[i + 1], self.n[i], k, mode, img, c.bias, N, c.out_dim,
-                                             not last, not last, True, 0, out, a, None, self.gather_mode)
-                    else:
-                        po = self.seg_off[l - 2]
-                        xs = self.H[l - 2][po[i]:po[i + 1]]
-                        xn = self.H[l - 2][po[i + 1]:po[i + 2]]
-                        C.sage_fused_forward(local_table_desc(xs), None, local_table_desc(xn), None, self.n[i], k, mode,
-                                             img, c.bias, N, c.out_dim, not last, not last, True, 0, out, a, None,
-                                             self.gather_mode)
-            if nseg > 1:
-                main.wait_stream(sA)
-        # ---- loss (seeds are owned locally: labels are a local lookup); first writer of the gradient storage
-        main.wait_event(self._ev_zero)
-        top = self.convs[L - 1]
-        C.softmax_ce(self.H[L - 1], self.nodes.labels.local, seeds, self.rt.world, self.loss, self.dZ[L - 1],
-                     top.bias.grad if top.bias is not None else None)
+            outs = [self.H[l - 1][offs[i]:offs[i + 1]] for i in range(nseg)]
+            asv = [self.A[l - 1][offs[i]:offs[i + 1]] for i in range(nseg)]
+            Ms, ks = [self.n[i] for i in range(nseg)], [self.fanouts[i] for i in range(nseg)]
+            ce = []
+            if last:
+                ce = [self.nodes.labels.local, seeds, self.loss, self.dZ[L - 1],
+                      top.bias.grad if top.bias is not None else None]
+            if l == 1:
+                d = self.nodes.feat_desc
+                C.sage_fused_multi(d, d, [hops[i] for i in range(nseg)], [hops[i + 1] for i in range(nseg)],
+                                   [0] * nseg, [0] * nseg, Ms, ks, outs, asv, mode, img, c.bias, N, c.out_dim,
+                                   not last, not last, 0, ce, self.rt.world, 1)
+            else:
+                po = self.seg_off[l - 2]
+                d = local_table_desc(self.H[l - 2])
+                C.sage_fused_multi(d, d, [None] * nseg, [None] * nseg, [po[i] for i in range(nseg)],
+                                   [po[i + 1] for i in range(nseg)], Ms, ks, outs, asv, mode, img, c.bias, N,
+                                   c.out_dim, not last, not last, 0, ce, self.rt.world, 1)
         if self._post_loss_hook is not None:
             self._post_loss_hook()          # e2e graph capture: fork the loss D2H here, parallel to the backward
-        # ---- backward
+        # ---- backward: all GEMMs on tcgen05 (csrc/sage_bwd.cu), no library kernels
+        #   top layer   : dW_L = dZ_L^T A_L with the dense dZ_L written by the fused loss epilogue
+        #   layer l < L : dW_l = dZ_l^T A_l where dZ_l = relu'(H_l) * (self + 1/k neighbour rows of dA_{l+1}) is
+        #                 computed inside the GEMM's producer warps (never stored for l = 1); bias grads fall out
+        #   dA_l = dZ_l . W_l  (l >= 2) on the persistent forward kernel with a K-major image of W_l^T
         for l in range(L, 0, -1):
             c = self.convs[l - 1]
-            dz, a = self.dZ[l - 1], self.A[l - 1]
-            if l == 1:
-                self._mm_into(c.weight_p.grad, dz.t(), a)                # dW_1 = dZ^T A (last launch of the backward)
-                break
-            sA.wait_stream(main)
-            with torch.cuda.stream(sA):
-                self._mm_into(c.weight_p.grad, dz.t(), a)                # dW_l = dZ^T A
-            da = self.dA[l - 1]
-            torch.mm(dz, packs[l - 1][1], out=da)                        # dA_l = dZ W_l
-            prev = self.convs[l - 2]
-            kp_self, _ = sage_ops.padded_dims(c.in_self, c.in_nbr, c.agg_type)
-            offs, po = self.seg_off[l - 1], self.seg_off[l - 2]
-            nseg_prev = L - l + 2
-            sC = self._side_c
-            sC.wait_stream(main)               # the (small) seed segment runs beside the big ones
-            for s in range(nseg_prev):
-                rows = slice(po[s], po[s + 1])
-                da_self = da[offs[s]:offs[s + 1]] if s <= L - l else None
-                da_nbr = da[offs[s - 1]:offs[s]] if s >= 1 else None
-                k = self.fanouts[s - 1] if s >= 1 else 1
-                scale = (1.0 / k) if c.agg_type == "mean" else 1.0
-                with torch.cuda.stream(sC if s == 0 else main):
-                    C.sage_bwd_input(da_self, da_nbr, kp_self, k, scale, self.H[l - 2][rows], self.dZ[l - 2][rows],
-                                     prev.bias.grad if prev.bias is not None else None)
-            main.wait_stream(sC)
-        # ---- join, gradient all-reduce + optimiser
+            a = self.A[l - 1]
+            if l == L:
+                sA.wait_stream(main)
+                with torch.cuda.stream(sA):            # dW_L runs beside dA_L
+                    C.sage_bwd_dw(self.dZ[l - 1], None, [], [], [], [], [], [], 0, None, a, c.weight_p.grad, None,
+                                  c.out_dim, [])
+            else:
+                nxt = self.convs[l]
+                da = self.dA[l]
+                offs, po = self.seg_off[l], self.seg_off[l - 1]
+                nseg = L - l + 1
+                kp_self_n, _ = sage_ops.padded_dims(nxt.in_self, nxt.in_nbr, nxt.agg_type)
+                r0 = [po[s] for s in range(nseg)]
+                r1 = [po[s + 1] for s in range(nseg)]
+                selfs = [da[offs[s]:offs[s + 1]] if s <= L - l - 1 else None for s in range(nseg)]
+                nbrs = [da[offs[s - 1]:offs[s]] if s >= 1 else None for s in range(nseg)]
+                ks = [self.fanouts[s - 1] if s >= 1 else 1 for s in range(nseg)]
+                scales = [((1.0 / self.fanouts[s - 1]) if nxt.agg_type == "mean" else 1.0) if s >= 1 else 1.0
+                          for s in range(nseg)]
+                C.sage_bwd_dw(None, self.H[l - 1], r0, r1, selfs, nbrs, ks, scales, kp_self_n,
+                              self.dZ[l - 1] if l >= 2 else None, a, c.weight_p.grad,
+                              c.bias.grad if c.bias is not None else None, c.out_dim, [])
+            if l >= 2:
+                # dA_l [rows, K_total] = dZ_l [rows, n_out] . W_l, one launch per 256-column block
+                dzp = self.dZp[l - 1]
+                d = local_table_desc(dzp)
+                wt = self.img_t[l - 1]
+                da = self.dA[l - 1]
+                rows = da.size(0)
+                # one launch: CTA b multiplies by image b % n_imgs and writes the columns [256 img, 256 img + 256)
+                n_imgs = wt.size(0)
+                cols = min(256, da.size(1))
+                if l == L:
+                    # dW_L (<= 32 whole-SM CTAs for a 1024-row top layer) runs beside this launch: leave it its SMs
+                    C.sage_set_max_ctas(max(C.sm_count() - 32, C.sm_count() // 2))
+                C.sage_fused_multi(d, d, [None], [None], [0], [0], [rows], [0], [da[:, :cols]], [None], 0, wt, None, 256, cols,
+                                   False, True, 0, [], 1, n_imgs)
+                C.sage_set_max_ctas(0)
+        # ---- join, gradient all-reduce + fused optimiser (Adam + zero grads + next step's weight images)
         main.wait_stream(sA)
-        main.wait_stream(sB)
-        main.wait_stream(sC)
         if pipe is not None:
             main.wait_stream(self._sample_stream)
+        if self._pre_opt_join is not None:
+            main.wait_stream(self._pre_opt_join)       # the loss must have left before the optimiser clears it
         self.ar(self.flat_g, average=True)
-        self.opt.apply()
+        if self._skip_opt:
+            return
+        o = self.opt
+        C.adam_pack(self.flat_p, self.g_store, o.m, o.v, o.step_t, o.lr, o.betas[0], o.betas[1], o.eps, o.wd, self.loss_out,
+                    self._mats)
+
+    def repack(self):
+        """Rebuild the bf16 weight images from the fp32 master weights (after init / load_state_dict / any
+        external modification of the parameters)."""
+        for l in range(1, self.L + 1):
+            c = self.convs[l - 1]
+            N = sage_ops.pad_n(c.out_dim)
+            self.img[l - 1].copy_(self.C.pack_weight_f32(c.weight_p.detach().contiguous(), N, False)[0])
+            if l > 1:
+                self.img_t[l - 1].copy_(self.C.pack_weight_t(c.weight_p.detach().contiguous(), self.dZp[l - 1].size(1), 256))
 
     # ------------------------------------------------------------------ graph / public step (same API as SageTrainer)
     def capture(self, warmup: int = 3):
@@ -288,7 +305,8 @@ class FastSageTrainer:
         #   end-to-end pair  : + next seeds copied from pinned host slot i^1 at the head of the sampling branch
         #                      + loss -> pinned host slot i forked right after the loss kernel
         # No PCIe round trip and no sampling kernel sits on the critical path (tools/diag_e2e.py).
-        self._sample_stream = torch.cuda.Stream()
+        self._sample_stream = torch.cuda.Stream(priority=0)
+        cap_stream = torch.cuda.Stream(priority=-1)
         self._hops = [[torch.zeros(n, dtype=torch.int64, device=self.rt.device) for n in self.n] for _ in range(2)]
         self._hops[0][0] = self.seeds                      # `tr.seeds` stays the handle of buffer 0
         self._seeds_bufs = [self._hops[0][0], self._hops[1][0]]
@@ -299,7 +317,7 @@ class FastSageTrainer:
         for e2e in (False, True):
             for i in range(2):
                 gi = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gi, pool=pool):
+                with torch.cuda.graph(gi, pool=pool, stream=cap_stream):
                     main = torch.cuda.current_stream()
                     if e2e:
                         def hook(i=i, main=main):
@@ -307,8 +325,10 @@ class FastSageTrainer:
                             with torch.cuda.stream(side_out):
                                 self._h_loss_dev[i].copy_(self.loss)
                         self._post_loss_hook = hook
+                        self._pre_opt_join = side_out
                     self._step_body(pipe=(i, i ^ 1, (i ^ 1) if e2e else None))
                     self._post_loss_hook = None
+                    self._pre_opt_join = None
                     if e2e:
                         main.wait_stream(side_out)
                 pool = gi.pool() if pool is None else pool
@@ -359,7 +379,7 @@ class FastSageTrainer:
         self.h_seeds.copy_(seed_ids_host)
         self.seeds.copy_(self.h_seeds, non_blocking=True)
         self.step_device()
-        self.h_loss.copy_(self.loss, non_blocking=True)
+        self.h_loss.copy_(self.loss_out, non_blocking=True)
         return self.h_loss
 
     def synchronize(self):
@@ -379,6 +399,7 @@ class FastSageTrainer:
 
     def load_state_dict(self, sd):
         self.flat_p.copy_(sd["model"])
+        self.repack()
         self.opt.load_state_dict(sd["opt"])
         self.rng.load_state_dict(sd["rng"])
         self._steps = int(sd["steps"])

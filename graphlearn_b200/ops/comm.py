@@ -103,10 +103,15 @@ class FlatAdam:
 
 def flatten_module(module: torch.nn.Module):
     """Re-home all parameters (and their .grad) into two flat fp32 buffers
-    (padded to a multiple of 4 elements).  Returns (flat_param, flat_grad)."""
+    (every parameter 8-element aligned).  Returns (flat_param, flat_grad)."""
     params = [p for p in module.parameters() if p.requires_grad]
-    total = sum(p.numel() for p in params)
-    n = (total + 3) // 4 * 4
+    # every parameter starts on an 8-element (32-byte) boundary: the fused Adam kernel owns 8 consecutive
+    # elements per thread and emits one 16-byte chunk of the bf16 weight images from them
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + 7) // 8 * 8
+    n = total
     dev = params[0].device
     flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
     # 4 spare floats behind the gradients: scratch accumulators (e.g. the loss) that must be zeroed
@@ -114,12 +119,11 @@ def flatten_module(module: torch.nn.Module):
     g_store = torch.zeros(n + 4, dtype=torch.float32, device=dev)
     flat_g = g_store[:n]
     module._glb_grad_storage = g_store
-    off = 0
     with torch.no_grad():
-        for p in params:
+        for p, off in zip(params, offs):
             k = p.numel()
             flat_p[off:off + k].copy_(p.reshape(-1))
             p.data = flat_p[off:off + k].view_as(p)
             p.grad = flat_g[off:off + k].view_as(p)
-            off += k
+    module._glb_param_offsets = {id(p): off for p, off in zip(params, offs)}
     return flat_p, flat_g

@@ -20,7 +20,7 @@ class _TcLinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, relu, out_bf16):
         C = native()
         n_out, k_in = weight.shape
-        kp = (k_in + 63) // 64 * 64
+        kp = sage_ops.pad_k(k_in)
         N = sage_ops.pad_n(n_out)
         a = torch.zeros(x.size(0), kp, dtype=torch.bfloat16, device=x.device)
         a[:, :k_in] = x
@@ -49,8 +49,7 @@ class _TcLinearFn(torch.autograd.Function):
 def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
               out_bf16: bool = False) -> torch.Tensor:
     k_in, n_out = weight.size(1), weight.size(0)
-    kp = (k_in + 63) // 64 * 64
-    fits = kp <= 512 and n_out <= 256 and 1024 + (kp // 64) * (128 * 128 + sage_ops.pad_n(n_out) * 128) + 1200 <= 232448
+    fits = k_in <= 512 and n_out <= 256 and sage_ops.smem_fits(sage_ops.pad_k(k_in), sage_ops.pad_n(n_out))
     if x.is_cuda and x.dim() == 2 and fits and _config.get().use_peer_kernels:
         return _TcLinearFn.apply(x, weight, bias, relu, out_bf16)
     y = F.linear(x.float(), weight.float(), None if bias is None else bias.float())

@@ -43,12 +43,21 @@ def padded_dims(d_self: int, d_nbr: int, mode: str):
     return kp_self, pad_k(d_nbr)
 
 
-def fused_supported(d_self: int, d_nbr: int, n_out: int, mode: str) -> bool:
+def fused_supported(d_self: int, d_nbr: int, n_out: int, mode: str, k: int = 0, dtype=torch.bfloat16) -> bool:
     if max(d_self, d_nbr) > 512 or n_out > 256:
         return False
     kp_self, kp_nbr = padded_dims(d_self, d_nbr, mode)
-    kt = kp_self + kp_nbr
-    return 1024 + (kt // 64) * (128 * 128 + pad_n(n_out) * 128) + 64 <= _SMEM_LIMIT
+    # a gather warp keeps the row pointers of one work item (1-4 destination rows) in a 64-entry scratch
+    lanes_row = max(kp_self, kp_nbr) // (4 if dtype == torch.float32 else 8)
+    rows_per_item = 32 // lanes_row if lanes_row < 32 else 1
+    if rows_per_item * (k + 1) > 64:
+        return False
+    return smem_fits(kp_self + kp_nbr, pad_n(n_out))
+
+
+def smem_fits(k_total: int, n_pad: int) -> bool:
+    """A tile + W image + pointer staging of the persistent kernel (csrc/sage_fused.cu sage_smem_bytes)."""
+    return 1024 + (k_total // 64) * (128 * 128 + n_pad * 128) + 23 * 64 * 8 + 1024 + 72 <= _SMEM_LIMIT
 
 
 def logical_weight(weight_p: torch.Tensor, d_self: int, d_nbr: int, mode: str) -> torch.Tensor:
@@ -93,7 +102,7 @@ class _SageFusedFn(torch.autograd.Function):
         img, w16 = C.pack_weight_f32(weight_p.detach().contiguous(), N, bool(need_x))
         out, a_save = C.sage_fused_forward(tself_desc, self_vids, tnbr_desc, nbr_vids, int(M), int(k), MODE[mode], img,
                                            bias, N, n_out, bool(relu), bool(out_bf16), bool(need_w),
-                                           int(rows_per_cta), None, None, None, int(_config.get().sage_gather_mode))
+                                           int(rows_per_cta), None, None)
         ctx.save_for_backward(a_save if need_w else None, w16 if need_x else None, out if relu else None)
         ctx.meta = (d_self, d_nbr, kp_self, kp_nbr, int(M), int(k), mode, relu, bias is not None,
                     x_self is not None, x_nbr is not None)
@@ -179,7 +188,7 @@ def sage_layer(weight_p: torch.Tensor, bias: Optional[torch.Tensor], *, k: int, 
     dt_nbr = x_nbr.dtype if x_nbr is not None else nbr_table.feats.local.dtype
     kp_s, kp_n = padded_dims(d_self, d_nbr, mode)
     compatible = dt_self == dt_nbr and dt_self in (torch.float32, torch.bfloat16) and (kp_s == 0 or kp_s == kp_n)
-    if use_cuda and compatible and fused_supported(d_self, d_nbr, weight_p.size(0), mode):
+    if use_cuda and compatible and fused_supported(d_self, d_nbr, weight_p.size(0), mode, k, dt_self):
         return _SageFusedFn.apply(weight_p, bias, x_self, x_nbr,
                                   None if self_table is None else self_table.feat_desc, self_vids,
                                   None if nbr_table is None else nbr_table.feat_desc, nbr_vids,

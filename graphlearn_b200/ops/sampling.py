@@ -160,8 +160,10 @@ def _local_sample_idfilter(csr, vids, k, strategy, fvals, circular, default_id, 
 def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: str = "random",
                      filter_mode: int = FILTER_NONE, filter_values: Optional[torch.Tensor] = None,
                      want_eids: bool = True, rng: Optional["_rng.DeviceRng"] = None, salt: int = 0,
-                     padding_circular: Optional[bool] = None):
-    """src_vids: int64 [B] -> (nbr_vids [B, k], edge_ids [B, k] | None)."""
+                     padding_circular: Optional[bool] = None, out: Optional[torch.Tensor] = None):
+    """src_vids: int64 [B] -> (nbr_vids [B, k], edge_ids [B, k] | None).  ``out`` (CUDA kernel path): a
+    pre-allocated contiguous int64 buffer of B*k elements the neighbour ids are written into (static-shape
+    engines sample straight into their hop buffers - no copy kernel)."""
     cfg = _config.get()
     circular = (cfg.padding_mode == _config.PADDING_CIRCULAR) if padding_circular is None else padding_circular
     if strategy == "full":
@@ -176,7 +178,7 @@ def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: st
             raise ValueError("in_degree sampling needs in-degree weights (CsrShard.set_indegree_weights)")
         nbr, eid = native().sample_neighbors(desc, src, int(k), STRATEGY[strategy], int(filter_mode), filter_values,
                                              bool(circular), int(cfg.sampling_retry_times),
-                                             int(cfg.default_neighbor_id), rng.state, int(salt), bool(want_eids))
+                                             int(cfg.default_neighbor_id), rng.state, int(salt), bool(want_eids), out)
         return nbr, (eid if want_eids else None)
     gen = rng.torch_generator(salt)
     extra = (filter_values.reshape(-1),) if filter_mode != FILTER_NONE else ()
@@ -186,6 +188,8 @@ def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: st
                              cfg.default_neighbor_id, gen)
 
     nbr, eid = part.remote_apply(src, fn, csr.rt.world, extra)
+    if out is not None:
+        out.view(-1).copy_(nbr.reshape(-1))
     return nbr, (eid if want_eids else None)
 
 

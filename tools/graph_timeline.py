@@ -26,7 +26,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
 # split into replays by the Adam kernel
-ends = [i for i, e in enumerate(evs) if "adam_flat" in e.name]
+ends = [i for i, e in enumerate(evs) if "adam_pack" in e.name]
 lo, hi = ends[2] + 1, ends[3] + 1
 t0 = evs[lo].time_range.start
 print("timeline of replay 4 (%s), %d kernels, span %.1f us" % ("e2e" if e2e else "device", hi - lo,
