@@ -104,6 +104,8 @@ def count_own_launches(trainer):
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             trainer._step_body()
             torch.cuda.synchronize()
+            if trainer.rt.world > 1:
+                trainer.rt.barrier()
         own, lib = 0, 0
         names = {}
         times = {}
@@ -126,30 +128,42 @@ def count_own_launches(trainer):
         trainer.graph = trainer_graph
 
 
-def run_ours(args):
+def build_trainer(args, rt, shape, feature_dtype, cache_rows_arg):
+    """Public-API path: in-memory sources -> gl.Graph -> GSL query -> compiled plan -> fused engine.
+    (--api raw keeps the round-1 path that hands raw shards to the trainer, for A/B.)"""
     import torch
     import torch.distributed as dist
 
+    import graphlearn_b200 as gl
     from graphlearn_b200.engine.fast_sage import FastSageTrainer
     from graphlearn_b200.engine.trainer import SageTrainer
     from graphlearn_b200.models.graphsage import EgoGraphSAGE
-    from graphlearn_b200.parallel.runtime import init
-    from graphlearn_b200.store.synthetic import make_sharded_graph
+    from graphlearn_b200.store.synthetic import make_partitioned_sources, make_sharded_graph
 
-    rt = init()
-    assert rt.is_cuda, "bench.py needs a CUDA device"
     W = rt.world
-    shape = dict(PRODUCTS)
-    if args.small:
-        shape = dict(num_nodes=200_000, num_edges=5_000_000, feat_dim=100, num_classes=47)
-    fdt = torch.bfloat16 if args.feature_dtype == "bf16" else torch.float32
     t0 = time.time()
-    nodes, csr = make_sharded_graph(rt, feature_dtype=fdt, seed=0, **shape)
-    # N17 replica cache of remote feature rows in local HBM (the reference's
-    # set_local_node_cache_capacity): -1 = as many remote rows as fit in 25% of the free HBM
+    gl.set_feature_dtype(feature_dtype)
+    g = q = None
+    if args.api == "gsl":
+        node_src, edge_src = make_partitioned_sources(rt, seed=0, **shape)
+        g = gl.Graph()
+        g.node(node_src, "n", decoder=gl.Decoder(labeled=True, attr_types=["float"] * shape["feat_dim"]))
+        g.edge(edge_src, ("n", "n", "e"), decoder=gl.Decoder())
+        g.init()
+        del node_src, edge_src
+        nodes, csr = g.store.nodes["n"], g.store.edges["e"]
+        q = g.V("n").batch(args.batch).shuffle(traverse=True).alias("src")
+        for i, k in enumerate(FANOUTS):
+            q = q.outV("e").sample(k).by("random").alias("h%d" % (i + 1))
+        q = q.values()
+    else:
+        fdt = torch.bfloat16 if feature_dtype == "bf16" else torch.float32
+        nodes, csr = make_sharded_graph(rt, feature_dtype=fdt, seed=0, **shape)
+    # N17 replica cache of remote feature rows in local HBM (the reference's set_local_node_cache_capacity, default 0 =
+    # off there and here): -1 = as many remote rows as fit in 25% of the free HBM
     cache_rows = 0
-    if W > 1 and args.feature_cache_rows != 0:
-        cap = args.feature_cache_rows
+    if W > 1 and cache_rows_arg != 0:
+        cap = cache_rows_arg
         if cap < 0:
             free_b, _ = torch.cuda.mem_get_info()
             cap = int(0.25 * free_b) // (nodes.feats.local.size(1) * nodes.feats.local.element_size())
@@ -162,70 +176,129 @@ def run_ours(args):
     torch.cuda.synchronize()
     build_s = time.time() - t0
     torch.manual_seed(0)
-    model = EgoGraphSAGE(shape["feat_dim"], HIDDEN, shape["num_classes"], 2).to(rt.device)
-    Trainer = SageTrainer if args.engine == "autograd" else FastSageTrainer
-    tr = Trainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
-                 use_cuda_graph=not args.no_graph)
-    # host-side seed stream: each rank traverses (shuffled) its own nodes, like the reference's
-    # V().batch().shuffle(traverse=True) root which is unsharded (node_getter.cc:64-92)
+    model = EgoGraphSAGE(shape["feat_dim"], HIDDEN, shape["num_classes"], len(FANOUTS)).to(rt.device)
+    if args.engine == "autograd":
+        tr = SageTrainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
+                         use_cuda_graph=not args.no_graph)
+    elif q is not None:
+        tr = FastSageTrainer.from_query(g, q, model, lr=3e-3, allreduce=args.allreduce, use_cuda_graph=not args.no_graph)
+    else:
+        tr = FastSageTrainer(rt, nodes, csr, model, FANOUTS, args.batch, lr=3e-3, allreduce=args.allreduce,
+                             use_cuda_graph=not args.no_graph)
+    return tr, nodes, csr, cache_rows, build_s, g
+
+
+def time_trainer(args, rt, tr, nodes, steps, clocks=None):
+    """(device-timed ms, e2e ms, last loss).  Device region: K graph replays, every one samples a FRESH seed batch
+    (already resident on the device).  End-to-end region: the public step - host seeds (GSL traversal when built
+    from a query) -> pinned staging -> H2D inside the step graph, loss -> pinned host every step."""
+    import torch
+    import torch.distributed as dist
+    W = rt.world
     gen = torch.Generator().manual_seed(1234 + rt.rank)
     n_local = nodes.n_local
-    total = args.warmup + 2 * args.steps + 8
-    seed_rows = torch.randint(0, n_local, (total, args.batch), generator=gen)
-    seed_ids = (seed_rows * W + rt.rank).pin_memory()
+    warm = max(args.warmup, 3)
+    total = warm + 2 * steps + 8
+    seed_ids = (torch.randint(0, n_local, (total, args.batch), generator=gen) * W + rt.rank)
+    dev_seeds = seed_ids.to(rt.device)
+    seed_ids = seed_ids.pin_memory()
+    use_query = hasattr(tr, "step_query")
     tr.seeds.copy_(seed_ids[0])
     tr.capture()
     it = 0
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         tr.step(seed_ids[it]); it += 1
+    for _ in range(2):
+        tr.step_device(dev_seeds[it]); it += 1
     torch.cuda.synchronize()
     rt.barrier()
-
-    # ---- device-timed region (kernel path): seeds already resident, K graph replays
-    clocks = ClockSampler(rt.local_rank) if rt.rank == 0 else None
     if clocks:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rt.barrier(); torch.cuda.synchronize()
     ev0.record()
-    for _ in range(args.steps):
-        tr.step_device()
+    for _ in range(steps):
+        tr.step_device(dev_seeds[it]); it += 1
     ev1.record()
     torch.cuda.synchronize(); rt.barrier()
     ms_dev = ev0.elapsed_time(ev1)
-
-    # ---- end-to-end region through the public step(): every call copies that call's seed batch from pinned
-    # host memory to the device and one loss back to pinned host memory.  Both copies are nodes of the step's
-    # CUDA graph on side branches (the batch staged by call t is trained by call t+1: input prefetch), so the
-    # PCIe round trips overlap the compute instead of serialising with it.
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import graphlearn_b200 as gl
     rt.barrier(); torch.cuda.synchronize()
     ev2.record()
     last = None
-    for _ in range(args.steps):
-        last = tr.step(seed_ids[it]); it += 1
+    done = 0
+    while done < steps:
+        if use_query:
+            try:
+                last = tr.step_query()
+            except gl.OutOfRangeError:      # epoch boundary of the GSL traversal: the next call starts a new pass
+                continue
+        else:
+            last = tr.step(seed_ids[it]); it += 1
+        done += 1
     ev3.record()
     torch.cuda.synchronize(); rt.barrier()
     ms_e2e = ev2.elapsed_time(ev3)
-    clk = clocks.stop() if clocks else None
     final_loss = float(last)
-    tr.ar.check()
-
+    if hasattr(tr, "ar"):
+        tr.ar.check()
     t = torch.tensor([ms_dev, ms_e2e], device=rt.device, dtype=torch.float64)
     if W > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    return float(t[0]), float(t[1]), final_loss
+
+
+def run_ours(args):
+    import torch
+
+    from graphlearn_b200.parallel.runtime import init
+
+    rt = init()
+    assert rt.is_cuda, "bench.py needs a CUDA device"
+    W = rt.world
+    shape = dict(PRODUCTS)
+    if args.small:
+        shape = dict(num_nodes=200_000, num_edges=5_000_000, feat_dim=100, num_classes=47)
+    # ---- headline: hash-partitioned graph, NO replica cache: every remote row crosses NVLink inside the fused kernel
+    tr, nodes, csr, cache_rows, build_s, g = build_trainer(args, rt, shape, args.feature_dtype, args.feature_cache_rows)
+    clocks = ClockSampler(rt.local_rank) if rt.rank == 0 else None
+    ms_dev, ms_e2e, final_loss = time_trainer(args, rt, tr, nodes, args.steps, clocks)
+    clk = clocks.stop() if clocks else None
     own, lib, names = count_own_launches(tr)
-    # remote feature traffic of the fused gather (hot path b/c): rows read per step and rank = self rows of both
-    # layer-1 segments + their neighbour rows; a row owned by another rank and not replicated locally crosses NVLink
     row_bytes = int(nodes.feats.local.size(1)) * nodes.feats.local.element_size()
     rows_per_step = args.batch * (1 + FANOUTS[0]) + args.batch * FANOUTS[0] * (1 + FANOUTS[1])
     n_total = sum(int(x) for x in nodes.nrows)
     remote_frac = 0.0 if W == 1 else (W - 1) / W * max(0.0, 1.0 - cache_rows / max(n_total - nodes.n_local, 1))
     remote_bytes = rows_per_step * row_bytes * remote_frac
+    kernel_us = getattr(tr, "_kernel_us", {})
+    extra = {}
+    # ---- secondary measurements (clearly labelled; never the headline)
+    sec_steps = min(args.steps, 300)
+    if W > 1 and args.feature_cache_rows == 0 and not args.no_secondary:
+        del tr
+        torch.cuda.empty_cache()
+        tr2, nodes2, _, cr2, _, _ = build_trainer(args, rt, shape, args.feature_dtype, -1)
+        d2, e2, _ = time_trainer(args, rt, tr2, nodes2, sec_steps)
+        extra["replica_cache_run"] = {"what": "same job with the N17 replica cache of remote feature rows filled (reference: "
+                                      "set_local_node_cache_capacity); remote feature traffic = 0", "feature_cache_rows_per_gpu": cr2,
+                                      "value": W * sec_steps / (d2 / 1e3), "e2e_value": W * sec_steps / (e2 / 1e3), "unit": "steps/s",
+                                      "steps": sec_steps}
+        del tr2, nodes2
+    elif W == 1 and not args.no_secondary:
+        other = "fp32" if args.feature_dtype == "bf16" else "bf16"
+        del tr
+        torch.cuda.empty_cache()
+        tr2, nodes2, _, _, _, _ = build_trainer(args, rt, shape, other, 0)
+        d2, e2, _ = time_trainer(args, rt, tr2, nodes2, sec_steps)
+        extra["%s_feature_rows_run" % other] = {"what": "same job with %s feature rows in HBM (compute stays bf16)" % other,
+                                                "value": sec_steps / (d2 / 1e3), "e2e_value": sec_steps / (e2 / 1e3),
+                                                "unit": "steps/s", "steps": sec_steps}
+        del tr2, nodes2
     if rt.rank == 0:
         steps_per_s = W * args.steps / (ms_dev / 1e3)
         e2e_steps_per_s = W * args.steps / (ms_e2e / 1e3)
+        fbytes = 2 if args.feature_dtype == "bf16" else 4
         out = {
             "metric": "sampled-subgraph train steps/sec (2-layer GraphSAGE fanout 25,10, ogbn-products-shaped synthetic)",
             "value": steps_per_s, "unit": "steps/s", "n_gpus": W, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -234,29 +307,37 @@ def run_ours(args):
             "impl": "graphlearn_b200",
             "config": {"model": "GraphSAGE-2layer-mean hidden256", "global_batch": args.batch * W, "seq_len": None,
                        "fanout": FANOUTS, "parallelism": "dp%d+graph-partition%d" % (W, W),
+                       "api": "gsl (in-memory sources -> gl.Graph -> GSL query -> compiled plan -> fused engine)" if args.api == "gsl"
+                              else "raw shards",
                        "num_nodes": shape["num_nodes"], "num_edges": shape["num_edges"],
                        "feat_dim": shape["feat_dim"], "feature_storage": args.feature_dtype,
                        "feature_cache_rows_per_gpu": cache_rows,
                        "feature_cache": ("n/a (single GPU)" if W == 1 else
-                                         "none (every remote row is read from its owner's HBM over NVLink inside the fused kernel)"
-                                         if cache_rows == 0 else
-                                         "replica cache of remote feature rows in local HBM (reference: set_local_node_cache_capacity); "
-                                         "topology stays partitioned; --feature-cache-rows 0 disables it"),
+                                         "none: the graph is hash-partitioned, every remote row is read from its owner's HBM over NVLink "
+                                         "inside the fused kernel" if cache_rows == 0 else
+                                         "replica cache of remote feature rows in local HBM (reference: set_local_node_cache_capacity)"),
                        "remote_feature_bytes_per_step_per_gpu": int(remote_bytes),
                        "remote_feature_GBps_per_gpu": round(remote_bytes / (ms_dev / args.steps * 1e-3) / 1e9, 1),
-                       "nvlink_random_row_ceiling_GBps": 477 if row_bytes <= 256 else 580,
+                       "nvlink_peer_copy_GBps_measured": 770,
+                       "seeds": "fresh seed batch every step in both timed regions (device region: resident on the device; "
+                                "e2e region: GSL shuffle(traverse=True) epochs on the host)",
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
-                                    % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * (2 if fdt == torch.bfloat16 else 4) / 1e9),
-                       "allreduce": tr.ar.backend if W > 1 else "none", "cuda_graph": tr.graph is not None, "engine": args.engine,
+                                    % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * fbytes / 1e9),
+                       "allreduce": tr_backend(W, args), "cuda_graph": not args.no_graph, "engine": args.engine,
                        "graph_build_s": round(build_s, 2)},
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": args.batch * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": own * args.steps, "own_kernels_per_step": own, "library_kernels_per_step": lib,
-            "own_kernel_names": names, "kernel_us_eager_step": getattr(tr, "_kernel_us", {}), "clocks": clk, "final_loss": final_loss,
+            "own_kernel_names": names, "kernel_us_eager_step": kernel_us, "clocks": clk, "final_loss": final_loss,
         }
+        out.update(extra)
         print(json.dumps(out))
     rt.barrier()
     rt.shutdown()
+
+
+def tr_backend(W, args):
+    return "none" if W == 1 else ("peer" if args.allreduce == "peer" else "nccl")
 
 
 def run_reference(args):
@@ -281,8 +362,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--engine", default="fast", choices=["fast", "autograd"],
                     help="fast = hand-scheduled fwd/bwd kernel chain; autograd = torch.autograd over the same kernels")
-    ap.add_argument("--feature-cache-rows", type=int, default=-1,
-                    help="remote feature rows replicated per GPU (N17 cache): -1 auto (25%% of free HBM), 0 off")
+    ap.add_argument("--feature-cache-rows", type=int, default=0,
+                    help="remote feature rows replicated per GPU (N17 cache): 0 off (default, = the reference's default), "
+                         "-1 auto (25%% of free HBM)")
+    ap.add_argument("--api", default="gsl", choices=["gsl", "raw"],
+                    help="gsl = in-memory sources -> gl.Graph -> GSL query -> compiled plan -> engine; raw = shards handed to the trainer")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the labelled secondary run (replica cache / other row dtype)")
     ap.add_argument("--small", action="store_true", help="small graph for quick functional runs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -218,14 +218,30 @@ __global__ void __launch_bounds__(kDwThreads, 1) sage_bwd_dw_kernel(const __grid
         process(st + 1, rb);
       }
     }
-    // bias gradient = column sums of the computed dZ (only the n-block-0 CTAs of an m-block contribute)
-    if (p.dbias && !p.dz && nb == 0 && zcol_ok) {
+    // bias gradient = column sums of the computed dZ (only the n-block-0 CTAs of an m-block contribute): the two
+    // rows of a warp are folded with a shuffle, every warp parks its 128 sums in the (now idle) stage memory and
+    // 128 threads add the 16 rows up - no shared-memory atomics (they were 32-way same-address conflicts)
+    const bool do_bias = p.dbias && !p.dz && nb == 0 && n_steps > 0;
+    if (do_bias) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&colsum[zc * 8 + i], cs[i]);
+      for (int i = 0; i < 8; ++i) cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+      // all MMAs have been issued and committed by the time the last stage was filled; wait for them before the
+      // stage memory is reused
+      umma::mbar_wait(bar_done, 0);
+      float* wsum = reinterpret_cast<float*>(stages) + warp * 128;
+      if (lane < 16) {
+        *reinterpret_cast<float4*>(wsum + zc * 8) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+        *reinterpret_cast<float4*>(wsum + zc * 8 + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+      }
     }
   }
   __syncthreads();
-  if (p.dbias && !p.dz && nb == 0 && tid < 128 && mb * 128 + tid < p.n_out && n_steps > 0) atomicAdd(p.dbias + mb * 128 + tid, colsum[tid]);
+  if (p.dbias && !p.dz && nb == 0 && tid < 128 && mb * 128 + tid < p.n_out && n_steps > 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDwProdWarps; ++w) v += reinterpret_cast<const float*>(stages)[w * 128 + tid];
+    atomicAdd(p.dbias + mb * 128 + tid, v);
+  }
   // ------------------------------------------------------------------ epilogue: TMEM -> red.global.add into dW
   if (n_steps > 0) {
     umma::mbar_wait(bar_done, 0);

@@ -42,7 +42,7 @@ class CheckpointManager(object):
         ids = self._list()
         if not ids:
             return None
-        ck = torch.load(os.path.join(self.path, "ckpt.%d.pt" % ids[-1]), weights_only=False)
+        ck = torch.load(os.path.join(self.path, "ckpt.%d.pt" % ids[-1]), weights_only=True)
         from .plan import PlanNode, QueryPlan
         for q, d in ck["queries"].items():
             plan = QueryPlan(d["source"])

@@ -36,11 +36,24 @@ class SampleStore(object):
             self.feat, self.feat_ts = ext(self.feat, 0), ext(self.feat_ts, -(2 ** 62))
         self.n = new_n
 
+    MAX_VERTEX_ID = 1 << 31        # growth cap of the HBM tables: ids come from the network (HTTP ingest)
+
+    def _valid_rows(self, key, *cols):
+        """drop records whose key id is negative (would wrap to another vertex's row) or absurdly large (would make
+        ``ensure`` allocate without bound)"""
+        if key.numel() == 0:
+            return (key,) + cols
+        ok = (key >= 0) & (key < self.MAX_VERTEX_ID)
+        if bool(ok.all()):
+            return (key,) + cols
+        return (key[ok],) + tuple(None if c is None else c.to(key.device)[ok] for c in cols)
+
     def apply_edges(self, src: torch.Tensor, dst: torch.Tensor, ts: torch.Tensor, w: Optional[torch.Tensor] = None):
         """TopK-by-timestamp: an incoming edge replaces the OLDEST kept sample of its source if it is
         newer.  Processed in timestamp order; duplicates of one source inside a batch are resolved in
         rounds (each round applies at most one update per source)."""
         src, dst, ts = src.to(self.device), dst.to(self.device), ts.to(self.device)
+        src, dst, ts, w = self._valid_rows(src, dst, ts, w)
         if src.numel():
             self.ensure(int(src.max().item()) + 1)
         w = torch.ones_like(ts, dtype=torch.float32) if w is None else w.to(self.device).float()
@@ -71,6 +84,7 @@ class SampleStore(object):
         if self.feat is None:
             return
         vid, ts, feat = vid.to(self.device), ts.to(self.device), feat.to(self.device).float()
+        vid, ts, feat = self._valid_rows(vid, ts, feat)
         if vid.numel():
             self.ensure(int(vid.max().item()) + 1)
         order = torch.argsort(ts, stable=True)
@@ -163,10 +177,12 @@ class DynamicGraphService(object):
             n = self.schema["vertices"][e["src"]]["count"]
             cur = self.stores.get(etype)
             if cur is None or cur.K < k:
-                st = SampleStore(n, k, self.device)
+                # the existing store may have grown past the schema's vertex count (ensure()): size the wider one to
+                # whatever is larger and back-fill only the rows / slots that exist
+                st = SampleStore(max(n, cur.n) if cur is not None else n, k, self.device)
                 if cur is not None:                       # back-fill existing samples
-                    st.nbr[:, :cur.K], st.ts[:, :cur.K], st.w[:, :cur.K] = cur.nbr, cur.ts, cur.w
-                    st.count.copy_(cur.count)
+                    st.nbr[:cur.n, :cur.K], st.ts[:cur.n, :cur.K], st.w[:cur.n, :cur.K] = cur.nbr, cur.ts, cur.w
+                    st.count[:cur.n].copy_(cur.count)
                 self.stores[etype] = st
         self.queries[qid] = plan
 

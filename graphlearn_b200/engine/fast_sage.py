@@ -134,6 +134,84 @@ class FastSageTrainer:
         for e in self._e2e_done:
             e.record()
 
+    # ------------------------------------------------------------------ GSL front end
+    @classmethod
+    def from_query(cls, graph, query, model, lr: float = 3e-3, **kw) -> "FastSageTrainer":
+        """Train from a ``gl.Graph`` + GSL query (the API the reference trains through,
+        graphlearn/python/gsl/dag_node.py:164-305, gsl/dag_dataset.py:29-97):
+
+            q = g.V("i").batch(1024).shuffle(traverse=True).alias("src") \
+                 .outV("e").sample(25).by("random").alias("h1").outV("e").sample(10).by("random").alias("h2").values()
+            tr = FastSageTrainer.from_query(g, q, model); tr.capture()
+            while True:
+                try: loss = tr.step_query()
+                except gl.OutOfRangeError: break        # end of epoch
+
+        The query is compiled to a static sampling plan (gsl/compile.py); its hop chain becomes the sampling branch of
+        the captured training-step graph, its root traversal (batch / shuffle / epochs) drives ``step_query``."""
+        from ..gsl.compile import compilable, compile_query
+        from ..gsl.iterators import SeedIterator
+        plan = compile_query(query)
+        if plan is None or not compilable(graph, plan):
+            raise ValueError("query cannot be lowered to a static sampling plan (need V().batch()[.shuffle()] followed by "
+                             "outV/inV(...).sample(k).by(strategy) hops over dense-id node types on CUDA)")
+        ets = {(h.edge_type, h.direction, h.strategy) for h in plan.hops}
+        if len(ets) != 1:
+            raise ValueError("the fused engine trains homogeneous chains: every hop must use the same edge type and strategy")
+        et, direction, strategy = next(iter(ets))
+        store = graph.store
+        csr = store.reverse_csr(et) if direction == "in" else store.edges[et]
+        if strategy == "in_degree" and direction == "out":
+            store.ensure_indegree_weights(et)
+        nodes = store.nodes[plan.base_type]
+        if any(h.dst_type != plan.base_type for h in plan.hops):
+            raise ValueError("the fused engine needs src and dst of the sampled edge type to be the root's node type")
+        tr = cls(graph.runtime, nodes, csr, model, plan.fanouts, plan.batch_size, lr=lr, strategy=strategy, **kw)
+        tr.plan, tr.graph_api = plan, graph
+        rt = graph.runtime
+        tab = store.nodes[plan.root_type]
+        rows = tab.present.nonzero().flatten() if tab.present is not None else torch.arange(tab.n_local, device=rt.device)
+        vids = rows * rt.world + rt.rank
+        if plan.base_type != plan.root_type:
+            vids = nodes.idmap.to_vid(tab.idmap.to_id(vids))
+        tr._q_vids = vids.cpu()
+        # full batches only: the step graph has static shapes and the loss is normalised by B (the reference's PyTorch
+        # loader also truncates every rank to min(count) // batch_size batches, examples/pytorch/gcn/train.py:174)
+        from .. import config as _config
+        tr._q_iter = SeedIterator(int(vids.numel()), plan.batch_size, plan.traverse, "cpu",
+                                  seed=_config.get().seed + 17 * rt.rank, drop_last=True)
+        tr._q_epoch, tr._q_order = -1, None
+        tr._q_refresh()
+        return tr
+
+    def _q_refresh(self):
+        """Per-epoch seed order: the root traversal's permutation applied to this rank's vids once per epoch, so that a
+        step only slices it (host work per step stays at a few microseconds)."""
+        it = self._q_iter
+        if it.strategy == "shuffle":
+            self._q_order = self._q_vids[it.prime()]
+        elif it.strategy == "by_order":
+            self._q_order = self._q_vids
+        else:
+            self._q_order = None
+        self._q_epoch = it.epoch
+
+    def step_query(self) -> torch.Tensor:
+        """One training step on the next seed batch of the compiled GSL query (host traversal -> pinned staging ->
+        the step graph).  Raises ``OutOfRangeError`` at the end of an epoch, exactly like ``Dataset.next()``."""
+        it = self._q_iter
+        if self._q_epoch != it.epoch:
+            self._q_refresh()
+        if self._q_order is None:                       # 'random' traversal: draws with replacement
+            return self.step(self._q_vids[it.next_index()])
+        lo = it.cursor
+        it.next_index()                                  # advances the cursor / raises OutOfRangeError at the epoch end
+        return self.step(self._q_order[lo:lo + self.B])
+
+    @property
+    def epoch(self) -> int:
+        return self._q_iter.epoch
+
     # ------------------------------------------------------------------ helpers
     def sample(self, seeds: torch.Tensor):
         hops = [seeds]
@@ -346,14 +424,21 @@ class FastSageTrainer:
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src)
 
-    def step_device(self):
-        """Device-only step (no host traffic): graph replay on the resident seed buffers."""
+    def step_device(self, next_seeds: Optional[torch.Tensor] = None):
+        """Device-only step (no host traffic): graph replay on the resident seed buffers.  ``next_seeds`` (device
+        int64 [B]) are the seeds of the batch the replay samples for the FOLLOWING step (software pipeline); without
+        them the resident seeds are re-sampled with a fresh RNG offset."""
         if self.graph is not None:
+            i = self._steps & 1
             if not self._primed:
-                self._prime_hops(self._hops[self._steps & 1][0])
+                self._prime_hops(self._hops[i][0] if next_seeds is None else next_seeds)
                 self._primed = True
-            self._dev_graphs[self._steps & 1].replay()
+            if next_seeds is not None:
+                self.C.copy_i64(self._hops[i ^ 1][0], next_seeds)
+            self._dev_graphs[i].replay()
         else:
+            if next_seeds is not None:
+                self.seeds.copy_(next_seeds)
             self._step_body()
         self._steps += 1
 

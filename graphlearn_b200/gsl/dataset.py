@@ -15,6 +15,7 @@ import collections
 import torch
 
 from .. import errors
+from .compile import CompiledQuery, compilable, compile_query
 from .executor import QueryExecutor
 
 
@@ -31,8 +32,14 @@ class Dataset(object):
         for multi-rank runs whose sampling ops are collectives, i.e. the portable path)."""
         self._dag = dag
         self._graph = dag.graph
-        self._exec = QueryExecutor(dag, drop_last=drop_last, sync_epoch=sync_epoch)
         self._window = max(1, int(window))
+        # static multi-hop chains run as a captured CUDA graph over a ring of `window` pre-allocated batches
+        # (gsl/compile.py); everything else is interpreted node by node (gsl/executor.py)
+        self.plan = compile_query(dag)
+        self._compiled = None
+        if prefetch and compilable(self._graph, self.plan):
+            self._compiled = CompiledQuery(self._graph, self.plan, depth=min(max(self._window, 2), 8), drop_last=drop_last)
+        self._exec = None if self._compiled is not None else QueryExecutor(dag, drop_last=drop_last, sync_epoch=sync_epoch)
         self._ring = collections.deque()
         self._pending_eoe = False
         self._prefetch = bool(prefetch) and self._graph.runtime.is_cuda
@@ -44,6 +51,14 @@ class Dataset(object):
         """Produce one batch (on the sampling stream) and push (values, event) to the ring."""
         if self._pending_eoe:
             return False
+        if self._compiled is not None:
+            try:
+                slot, m = self._compiled.launch()
+            except errors.OutOfRangeError:
+                self._pending_eoe = True
+                return False
+            self._ring.append(((slot, m), None))
+            return True
         try:
             if self._stream is not None:
                 self._stream.wait_stream(torch.cuda.current_stream())
@@ -70,10 +85,13 @@ class Dataset(object):
         vals, ev = self._ring.popleft()
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
-        # keep the pipeline `window` deep (sampling of later batches overlaps the consumer's compute)
-        ahead = min(self._window - 1, 2)
+        # keep the pipeline `window` deep (sampling of later batches overlaps the consumer's compute); the compiled
+        # ring re-uses slot buffers, so one slot stays reserved for the batch the consumer is holding
+        ahead = (self._compiled.depth - 2) if self._compiled is not None else (self._window - 1)
         while len(self._ring) < ahead and self._produce_one():
             pass
+        if self._compiled is not None:
+            vals = self._compiled.values(*vals)
         res = DagValues(vals)
         f = self._dag.value_func
         return f(res) if f is not None else res
@@ -84,16 +102,21 @@ class Dataset(object):
         return self
 
     @property
+    def compiled(self) -> bool:
+        """True when the query runs as a captured CUDA graph (static sampling plan)."""
+        return self._compiled is not None
+
+    @property
     def epoch(self):
-        return self._exec.epoch
+        return (self._compiled or self._exec).epoch
 
     def state_dict(self):
-        return self._exec.state_dict()
+        return (self._compiled or self._exec).state_dict()
 
     def load_state_dict(self, sd):
         self._ring.clear()
         self._pending_eoe = False
-        self._exec.load_state_dict(sd)
+        (self._compiled or self._exec).load_state_dict(sd)
 
     def close(self):
         self._closed = True

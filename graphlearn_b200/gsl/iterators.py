@@ -56,6 +56,13 @@ class SeedIterator(object):
         self.cursor = end
         return idx
 
+    def prime(self):
+        """Build the current epoch's permutation now (``randperm`` of millions of rows costs tens of ms - callers
+        that time their first batch, or pre-gather per-epoch values, do it up front)."""
+        if self.strategy == "shuffle" and self._perm is None and self.n > 0:
+            self._perm = torch.randperm(self.n, generator=self._gen()).to(self.device)
+        return self._perm
+
     def has_next(self) -> bool:
         """would ``next_index()`` return a batch (True) or raise OutOfRangeError (False)?"""
         if self.n == 0:

@@ -79,7 +79,15 @@ class _WeightedSampler(object):
         return row * self.W + owner
 
 
-_CACHE: Dict[tuple, _WeightedSampler] = {}
+def _cache_of(store) -> Dict[tuple, "_WeightedSampler"]:
+    """Weighted-sampler cache of ONE graph store (reference: AliasMethodFactory caches per edge type inside a server
+    process, in_degree_negative_sampler.cc:61-98).  It lives on the store object so that a second Graph with the same
+    type names - or a rebuilt one - can never see a stale distribution."""
+    c = getattr(store, "_neg_cache", None)
+    if c is None:
+        c = {}
+        store._neg_cache = c
+    return c
 
 
 def _is_neighbor(csr, src_v: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
@@ -118,14 +126,14 @@ def edge_negative(store, etype: str, src_v: torch.Tensor, k: int, strategy: str,
         cum = None
         if strategy == "in_degree":
             key = ("indeg", etype, direction)
-            if key not in _CACHE:
+            if key not in _cache_of(store):
                 if direction == "out":
                     store.reverse_csr(etype)
                     wloc = dst_tab.in_degrees[etype].float()
                 else:
                     wloc = store.nodes[csr.dst_type].out_degrees[etype].float()
-                _CACHE[key] = _WeightedSampler(store.rt, wloc)
-            cum = _CACHE[key].cum
+                _cache_of(store)[key] = _WeightedSampler(store.rt, wloc)
+            cum = _cache_of(store)[key].cum
         off, total = _shard_offsets(dst_tab, dev)
         if total == 0:
             return torch.full((B, k), -1, dtype=torch.int64, device=dev)
@@ -136,14 +144,14 @@ def edge_negative(store, etype: str, src_v: torch.Tensor, k: int, strategy: str,
         return _draw_global_uniform(dst_tab, B, k, gen, dev)
     if strategy == "in_degree":
         key = ("indeg", etype, direction)
-        if key not in _CACHE:
+        if key not in _cache_of(store):
             if direction == "out":
                 store.reverse_csr(etype)
                 wloc = dst_tab.in_degrees[etype].float()
             else:
                 wloc = store.nodes[csr.dst_type].out_degrees[etype].float()
-            _CACHE[key] = _WeightedSampler(store.rt, wloc)
-        ws = _CACHE[key]
+            _cache_of(store)[key] = _WeightedSampler(store.rt, wloc)
+        ws = _cache_of(store)[key]
         neg = ws.draw((B, k), gen, dev)
         for _ in range(max(1, cfg.neg_sampling_retry_times)):
             bad = _is_neighbor(csr, src_v, neg)             # collective when world > 1
@@ -167,9 +175,9 @@ def node_weight_negative(store, ntype: str, src_v: torch.Tensor, k: int, gen):
     if tab.weights is None:
         return _draw_global_uniform(tab, B, k, gen, dev)
     key = ("nw", ntype)
-    if key not in _CACHE:
-        _CACHE[key] = _WeightedSampler(store.rt, tab.weights.local)
-    ws = _CACHE[key]
+    if key not in _cache_of(store):
+        _cache_of(store)[key] = _WeightedSampler(store.rt, tab.weights.local)
+    ws = _cache_of(store)[key]
     neg = ws.draw((B, k), gen, dev)
     batch = torch.sort(torch.unique(src_v))[0]
     for _ in range(max(1, cfg.neg_sampling_retry_times)):

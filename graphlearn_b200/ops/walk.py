@@ -57,9 +57,12 @@ def _node2vec_step(csr, cur, prev, p, q, rng, salt, gen, cfg):
         cand = cand.reshape(-1)
         is_prev = cand == prev
         if keys.numel():
-            qk = torch.arange(B, device=dev) * base + (cand.clamp(max=base - 2) + 1)
+            # a candidate larger than every parent neighbour cannot be a member: mark it instead of clamping it onto
+            # the largest neighbour id (which would hand it weight 1 instead of 1/q when that id is in the row)
+            in_range = (cand >= 0) & (cand <= base - 2)
+            qk = torch.arange(B, device=dev) * base + (cand.clamp(min=0, max=base - 2) + 1)
             pos = torch.searchsorted(keys, qk).clamp_(max=keys.numel() - 1)
-            nb = keys[pos] == qk
+            nb = (keys[pos] == qk) & in_range
         else:
             nb = torch.zeros(B, dtype=torch.bool, device=dev)
         w = torch.where(is_prev, torch.full((B,), 1.0 / p, device=dev),

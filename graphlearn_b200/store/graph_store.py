@@ -191,6 +191,14 @@ class GraphStore(object):
         # File sources: every rank parses 1/W of the bytes and one all-to-all-v per column moves the
         # rows to their owners (N10 + C4).  In-memory sources are identical on every rank -> filter.
         def load_owned(s, key):
+            if s.data is not None and s.data.get("partitioned"):
+                # in-memory source that already holds exactly this rank's rows (ids with |id| % world == rank, edges by
+                # their source id) - e.g. generated or pre-sharded on the device: nothing to filter or move
+                d = _load_source(s)
+                if s.kind == "edge" and s.direction == REVERSED:
+                    raise ValueError("partitioned in-memory edge sources must be directed (rows are owned by their source)")
+                dst_own = d["b"][d["b"].abs() % W == r] if s.kind == "edge" else None
+                return d, dst_own
             if s.data is None and W > 1 and cfg.sliced_load:
                 d = _load_source(s, r, W)
                 if s.kind == "edge" and s.direction == REVERSED:

@@ -35,7 +35,9 @@ def save_checkpoint(path: str, trainer=None, model: Optional[torch.nn.Module] = 
 
 def load_checkpoint(path: str, trainer=None, model: Optional[torch.nn.Module] = None, datasets: Optional[Dict] = None,
                     rank: int = 0, map_location=None) -> dict:
-    state = torch.load("%s.rank%d" % (path, rank), map_location=map_location, weights_only=False)
+    # payloads are plain dicts / lists / tensors / numbers: refuse to unpickle anything else (a tampered checkpoint
+    # must not be able to execute code)
+    state = torch.load("%s.rank%d" % (path, rank), map_location=map_location, weights_only=True)
     if trainer is not None and "trainer" in state:
         trainer.load_state_dict(state["trainer"])
     if model is not None and "model" in state:

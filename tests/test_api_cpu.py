@@ -430,3 +430,43 @@ def test_get_edges_by_endpoints_and_saint_norm(g):
                                              sample_coverage=3)
     assert node_norm.shape == (fx.N_ITEM,) and edge_norm.shape == (sum(g.get_stats()["sim"]),)
     assert float(node_norm.min()) > 0 and float(edge_norm.max()) <= 1e4
+
+
+def test_negative_sampler_cache_is_per_graph(tmp_path):
+    """Two graphs with the same edge type name in one process: the in-degree negative sampler of the second must not
+    see the first one's distribution (the cache used to be a module global keyed by type name only)."""
+    import numpy as np
+    import graphlearn_b200 as gl
+
+    def build(n_items, hot):
+        src = np.arange(200) % 10
+        dst = np.full(200, hot)
+        g = gl.Graph()
+        g.node({"ids": np.arange(10)}, "u", decoder=gl.Decoder())
+        g.node({"ids": np.arange(n_items)}, "i", decoder=gl.Decoder())
+        g.edge({"src_ids": src, "dst_ids": dst}, ("u", "i", "buy"), decoder=gl.Decoder())
+        g.init(device="cpu")
+        return g
+
+    ga = build(100, 99)
+    na = ga.negative_sampler("buy", expand_factor=4, strategy="in_degree").get(np.array([0, 1, 2]))
+    ga.close()
+    gb = build(20, 3)
+    nb = gb.negative_sampler("buy", expand_factor=4, strategy="in_degree").get(np.array([0, 1, 2]))
+    ids = np.asarray(nb.ids).reshape(-1)
+    assert ids.max() < 20, ids            # id 99 only exists in graph A
+
+
+def test_dgs_install_wider_query_after_growth():
+    from graphlearn_b200.dgs import DynamicGraphService, QueryPlan
+    import torch
+    schema = {"vertices": {"u": {"count": 4}, "i": {"count": 4}}, "edges": {"buy": {"src": "u", "dst": "i"}}}
+    svc = DynamicGraphService(schema, device="cpu")
+    svc.install_query(1, QueryPlan("u").out("buy", 2))
+    svc.apply_updates({"edges": {"buy": {"src": [10, 1], "dst": [2, 3], "ts": [5, 6]}}})
+    svc.install_query(2, QueryPlan("u").out("buy", 4))          # used to raise a shape mismatch
+    res = svc.run_query(2, [10])
+    assert 2 in res["hops"][0]["ids"].reshape(-1).tolist()
+    # hostile ids are dropped instead of wrapping / exploding the tables
+    svc.apply_updates({"edges": {"buy": {"src": [-1, 1 << 40], "dst": [0, 0], "ts": [7, 8]}}})
+    assert svc.stores["buy"].n < (1 << 20)
