@@ -35,12 +35,15 @@ def gen_data(root, n_nodes, n_edges, dim, classes, seed=0):
     rs = np.random.RandomState(seed)
     lut = np.array(["%.2f" % (i / 100.0) for i in range(-400, 401)], dtype=object)
     with open(node_f, "w") as f:
-        f.write("id:int64\tlabel:int32\tfeature:string\n")
+        f.write("id:int64\tlabel:int32\tfeature:string\n" if dim > 0 else "id:int64\tlabel:int32\n")
         step = 100_000
         for s in range(0, n_nodes, step):
             e = min(n_nodes, s + step)
-            q = np.clip((rs.randn(e - s, dim) * 100).astype(np.int64), -400, 400) + 400
             lab = rs.randint(0, classes, e - s)
+            if dim == 0:
+                f.write("".join("%d\t%d\n" % (s + i, lab[i]) for i in range(e - s)))
+                continue
+            q = np.clip((rs.randn(e - s, dim) * 100).astype(np.int64), -400, 400) + 400
             strs = lut[q]
             f.write("".join("%d\t%d\t%s\n" % (s + i, lab[i], ":".join(strs[i])) for i in range(e - s)))
     w = np.exp(rs.randn(n_nodes))
@@ -73,6 +76,10 @@ def main():
     ap.add_argument("--hosts", default="")
     ap.add_argument("--gen-only", action="store_true")
     ap.add_argument("--slots", type=int, default=2)
+    ap.add_argument("--walk-len", type=int, default=0, help="> 0: DeepWalk mode (random_walk + negatives), timed in this process")
+    ap.add_argument("--neg", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     if a.gen_only:
         t0 = time.time()
@@ -83,11 +90,11 @@ def main():
     import graphlearn as gl            # must be the FIRST native import (it crashes when NumPy is loaded before it)
     import numpy as np
     from multiprocessing import shared_memory
-    f1, f2 = [int(x) for x in a.fanouts.split(",")]
+    fans = [int(x) for x in a.fanouts.split(",")]
     node_f, edge_f = os.path.join(a.root, "node.tsv"), os.path.join(a.root, "edge.tsv")
     t0 = time.time()
     g = gl.Graph() \
-        .node(node_f, "i", decoder=gl.Decoder(labeled=True, attr_types=["float"] * a.dim)) \
+        .node(node_f, "i", decoder=gl.Decoder(labeled=True, attr_types=["float"] * a.dim) if a.dim > 0 else gl.Decoder(labeled=True)) \
         .edge(edge_f, ("i", "i", "e"), decoder=gl.Decoder())
     if a.world > 1 and a.hosts:
         # RPC tracker with an explicit host list: the FS tracker publishes gethostbyname(hostname), which is
@@ -98,13 +105,40 @@ def main():
     else:
         g.init(task_index=a.rank, task_count=a.world, tracker=a.tracker, hosts=a.hosts or None)
     load_s = time.time() - t0
-    q = g.V("i").batch(a.batch).shuffle(traverse=True).alias("src") \
-         .outV("e").sample(f1).by("random").alias("h1") \
-         .outV("e").sample(f2).by("random").alias("h2").values()
+    if a.walk_len > 0:
+        # BASELINE config 5: the reference's own walk path (one sharded request per step, random_walk.cc:55-135)
+        q = g.V("i").batch(a.batch).shuffle(traverse=True).alias("src").random_walk("e", a.walk_len).alias("walk") \
+             .outNeg("e").sample(a.neg).by("random").alias("neg").values()
+        ds = gl.Dataset(q, window=10)
+
+        def one():
+            while True:
+                try:
+                    r = ds.next()
+                    break
+                except gl.OutOfRangeError:
+                    continue
+            return r["walk"].ids.shape[0] + 0 * r["neg"].ids.shape[0]
+        for _ in range(a.warmup):
+            one()
+        t1 = time.time()
+        for _ in range(a.steps):
+            one()
+        dt = time.time() - t1
+        print("WALK %.6f %.1f" % (dt, load_s), flush=True)
+        g.close()
+        return
+    q = g.V("i").batch(a.batch).shuffle(traverse=True).alias("src")
+    for i, f in enumerate(fans):
+        q = q.outV("e").sample(f).by("random").alias("h%d" % (i + 1))
+    q = q.values()
     ds = gl.Dataset(q, window=10)
     B = a.batch
-    n0, n1, n2 = B, B * f1, B * f1 * f2
-    fbytes = (n0 + n1 + n2) * a.dim * 4
+    ns = [B]
+    for f in fans:
+        ns.append(ns[-1] * f)
+    n_rows = sum(ns)
+    fbytes = n_rows * a.dim * 4
     slot_bytes = fbytes + B * 8
     shm = shared_memory.SharedMemory(create=True, size=slot_bytes * a.slots)
     print("SHM %s %d %.1f" % (shm.name, slot_bytes, load_s), flush=True)
@@ -125,16 +159,16 @@ def main():
                 except gl.OutOfRangeError:
                     continue
             off = s * slot_bytes
-            buf = np.ndarray((n0 + n1 + n2, a.dim), dtype=np.float32, buffer=shm.buf, offset=off)
+            buf = np.ndarray((n_rows, a.dim), dtype=np.float32, buffer=shm.buf, offset=off)
             x0 = r["src"].float_attrs.reshape(-1, a.dim)
-            x1 = r["h1"].float_attrs.reshape(-1, a.dim)
-            x2 = r["h2"].float_attrs.reshape(-1, a.dim)
-            if x0.shape[0] != n0:          # short last batch of an epoch: skip
+            if x0.shape[0] != ns[0]:       # short last batch of an epoch: skip
                 free.insert(0, s)
                 continue
-            buf[:n0] = x0
-            buf[n0:n0 + n1] = x1
-            buf[n0 + n1:] = x2
+            buf[:ns[0]] = x0
+            o = ns[0]
+            for i in range(len(fans)):
+                buf[o:o + ns[i + 1]] = r["h%d" % (i + 1)].float_attrs.reshape(-1, a.dim)
+                o += ns[i + 1]
             y = np.ndarray((B,), dtype=np.int64, buffer=shm.buf, offset=off + fbytes)
             y[:] = r["src"].labels.reshape(-1)
             print("READY %d" % s, flush=True)

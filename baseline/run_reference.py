@@ -41,8 +41,16 @@ def main(args):
     import torch.nn.functional as F
 
     small = getattr(args, "small", False)
-    shape = dict(n_nodes=200_000, n_edges=5_000_000) if small else dict(n_nodes=2_449_029, n_edges=123_718_280)
-    dim, classes, hidden, fanouts, B = 100, 47, 256, [25, 10], args.batch
+    cfg = getattr(args, "cfg", None) or {"shape": dict(num_nodes=2_449_029, num_edges=123_718_280, feat_dim=100, num_classes=47),
+                                         "fanouts": [25, 10], "hidden": 256,
+                                         "metric": "sampled-subgraph train steps/sec (2-layer GraphSAGE fanout 25,10, ogbn-products-shaped synthetic)",
+                                         "model": "GraphSAGE-2layer-mean hidden256"}
+    shape = dict(n_nodes=cfg["shape"]["num_nodes"], n_edges=cfg["shape"]["num_edges"])
+    if small:
+        shape = dict(n_nodes=200_000, n_edges=5_000_000)
+    walk_len = int(cfg.get("walk_len", 0))
+    dim, classes, B = cfg["shape"]["feat_dim"], cfg["shape"]["num_classes"], args.batch
+    hidden, fanouts = cfg.get("hidden", 256), cfg.get("fanouts", [1])
     use_cuda = torch.cuda.is_available()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
@@ -53,8 +61,10 @@ def main(args):
         dist.init_process_group("nccl" if use_cuda else "gloo")
     root = os.environ.get("GLB_REF_DATA", "/tmp/glb_ref_data_%d_%d" % (shape["n_nodes"], shape["n_edges"]))
     sampler = os.path.join(HERE, "ref_sampler.py")
+    root += "_%d" % dim
     common = [sys.executable, sampler, "--root", root, "--nodes", str(shape["n_nodes"]), "--edges",
-              str(shape["n_edges"]), "--dim", str(dim), "--classes", str(classes), "--batch", str(B)]
+              str(shape["n_edges"]), "--dim", str(dim), "--classes", str(classes), "--batch", str(B),
+              "--fanouts", ",".join(str(f) for f in fanouts)]
     env = dict(os.environ)
     env.pop("PYTHONPATH", None)
     t0 = time.time()
@@ -73,6 +83,34 @@ def main(args):
     # the launcher chose, and never equal to MASTER_PORT itself
     base_port = 30000 + (int(os.environ.get("MASTER_PORT", "29500")) + 211) % 20000
     hosts = ",".join("127.0.0.1:%d" % (base_port + r) for r in range(world)) if world > 1 else ""
+    if walk_len > 0:
+        # DeepWalk config: sampling only, timed inside the reference's own process (no tensors to hand over)
+        out = subprocess.run(common + ["--rank", str(rank), "--world", str(world), "--tracker", tracker, "--hosts", hosts,
+                                       "--walk-len", str(walk_len), "--neg", str(cfg.get("neg", 5)), "--steps", str(args.steps),
+                                       "--warmup", str(max(args.warmup, 3))], env=env, cwd=_scratch_cwd(), capture_output=True, text=True)
+        line = [l for l in out.stdout.splitlines() if l.startswith("WALK")]
+        if not line:
+            raise RuntimeError("reference walk run failed: " + out.stderr[-500:])
+        dt, load_s = float(line[0].split()[1]), float(line[0].split()[2])
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        if rank == 0:
+            v = world * B * args.steps / dt
+            print(json.dumps({"impl": "reference", "metric": cfg["metric"], "value": v, "unit": "walks/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3 / args.steps,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 ids",
+                              "data": "synthetic TSV of the same shape",
+                              "config": {"model": "reference RandomWalk op + RandomNegativeSampler via GSL (CPU)", "global_batch": B * world,
+                                         "walk_len": walk_len, "num_nodes": shape["n_nodes"], "num_edges": shape["n_edges"],
+                                         "data_gen_s": round(gen_s, 1), "graph_load_s": round(load_s, 1)},
+                              "e2e": {"value": v, "unit": "walks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     child = subprocess.Popen(common + ["--rank", str(rank), "--world", str(world), "--tracker", tracker,
                                        "--hosts", hosts],
                              stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1, env=env,
@@ -85,8 +123,12 @@ def main(args):
     _, shm_name, slot_bytes, load_s = line.split()
     slot_bytes, load_s = int(slot_bytes), float(load_s)
     shm = shared_memory.SharedMemory(name=shm_name)
-    n0, n1, n2 = B, B * fanouts[0], B * fanouts[0] * fanouts[1]
-    fbytes = (n0 + n1 + n2) * dim * 4
+    ns = [B]
+    for f in fanouts:
+        ns.append(ns[-1] * f)
+    n_rows = sum(ns)
+    fbytes = n_rows * dim * 4
+    L = len(fanouts)
 
     def next_batch():
         while True:
@@ -97,7 +139,7 @@ def main(args):
                 s = int(l.split()[1])
                 break
         off = s * slot_bytes
-        x = np.ndarray((n0 + n1 + n2, dim), dtype=np.float32, buffer=shm.buf, offset=off)
+        x = np.ndarray((n_rows, dim), dtype=np.float32, buffer=shm.buf, offset=off)
         y = np.ndarray((B,), dtype=np.int64, buffer=shm.buf, offset=off + fbytes)
         return s, x, y
 
@@ -106,18 +148,24 @@ def main(args):
         child.stdin.flush()
 
     class SAGE(nn.Module):
+        """EgoGraphSAGE of depth L: layer l is applied to every adjacent hop pair (ego_gnn.py:58-110)."""
+
         def __init__(self):
             super().__init__()
-            self.l1 = nn.Linear(2 * dim, hidden)
-            self.l2 = nn.Linear(2 * hidden, classes)
+            dims = [dim] + [hidden] * (L - 1) + [classes]
+            self.lins = nn.ModuleList([nn.Linear(2 * dims[i], dims[i + 1]) for i in range(L)])
 
         def conv(self, lin, x, nb, k):
             return lin(torch.cat([x, nb.view(x.size(0), k, -1).mean(1)], 1))
 
-        def forward(self, x0, x1, x2):
-            h0 = F.relu(self.conv(self.l1, x0, x1, fanouts[0]))
-            h1 = F.relu(self.conv(self.l1, x1, x2, fanouts[1]))
-            return self.conv(self.l2, h0, h1, fanouts[0])
+        def forward(self, *xs):
+            h = list(xs)
+            for l in range(L):
+                last = l == L - 1
+                h = [self.conv(self.lins[l], h[i], h[i + 1], fanouts[i]) for i in range(L - l)]
+                if not last:
+                    h = [F.relu(t) for t in h]
+            return h[0]
 
     torch.manual_seed(0)
     model = SAGE().to(dev)
@@ -132,9 +180,11 @@ def main(args):
         xt = torch.from_numpy(x).to(dev, non_blocking=False)
         yt = torch.from_numpy(y).to(dev, non_blocking=False)
         free_slot(s)
-        x0, x1, x2 = xt[:n0], xt[n0:n0 + n1], xt[n0 + n1:]
+        xs, o = [], 0
+        for n_ in ns:
+            xs.append(xt[o:o + n_]); o += n_
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_cuda):
-            logits = model(x0, x1, x2)
+            logits = model(*xs)
         loss = F.cross_entropy(logits.float(), yt)
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -167,11 +217,11 @@ def main(args):
         v = world * args.steps / (ms / 1e3)
         print(json.dumps({
             "impl": "reference",
-            "metric": "sampled-subgraph train steps/sec (2-layer GraphSAGE fanout 25,10, ogbn-products-shaped synthetic)",
+            "metric": cfg["metric"],
             "value": v, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random graph of ogbn-products shape as TSV, random-init weights)",
-            "config": {"model": "GraphSAGE-2layer-mean hidden256 (plain PyTorch; PyG unavailable offline)",
+            "config": {"model": cfg["model"] + " (plain PyTorch; PyG unavailable offline)",
                        "global_batch": B * world, "fanout": fanouts, "num_nodes": shape["n_nodes"],
                        "num_edges": shape["n_edges"], "feat_dim": dim,
                        "parallelism": "reference %s mode x%d + DDP" % ("local" if world == 1 else "worker", world),

@@ -26,6 +26,24 @@ PRODUCTS = dict(num_nodes=2_449_029, num_edges=123_718_280, feat_dim=100, num_cl
 FANOUTS = [25, 10]
 HIDDEN = 256
 BATCH = 1024
+# BASELINE.json configs.  `products_sage2` is the headline the driver runs; the others are selected with --config.
+CONFIGS = {
+    "products_sage2": dict(shape=PRODUCTS, fanouts=[25, 10], hidden=256,
+                           metric="sampled-subgraph train steps/sec (2-layer GraphSAGE fanout 25,10, ogbn-products-shaped synthetic)",
+                           model="GraphSAGE-2layer-mean hidden256",
+                           data="synthetic (random graph of ogbn-products shape, random-init weights)"),
+    # ogbn-papers100M is 111M nodes / 1.6B edges / 128-d / 172 classes; the reference arm has to write and parse the
+    # graph as TSV text, so both arms use the same 1/32-scale graph of that shape (same degree, dims, fan-outs)
+    "sage3": dict(shape=dict(num_nodes=3_468_000, num_edges=50_500_000, feat_dim=128, num_classes=172), fanouts=[15, 10, 5],
+                  hidden=256,
+                  metric="sampled-subgraph train steps/sec (3-layer GraphSAGE fanout 15,10,5, ogbn-papers100M-shaped synthetic at 1/32 scale)",
+                  model="GraphSAGE-3layer-mean hidden256",
+                  data="synthetic (random graph of ogbn-papers100M shape at 1/32 scale: 3.47M nodes / 50.5M edges / 128-d, random-init weights)"),
+    "deepwalk": dict(shape=dict(num_nodes=3_468_000, num_edges=50_500_000, feat_dim=0, num_classes=2), walk_len=40, neg=5,
+                     metric="DeepWalk random walks/sec (random_walk length 40 + 5 random negatives per walk, ogbn-papers100M-shaped synthetic at 1/32 scale)",
+                     model="DeepWalk walk engine (sampling only)",
+                     data="synthetic (random graph of ogbn-papers100M shape at 1/32 scale: 3.47M nodes / 50.5M edges)"),
+}
 
 
 class ClockSampler:
@@ -129,6 +147,7 @@ def count_own_launches(trainer):
 
 
 def build_trainer(args, rt, shape, feature_dtype, cache_rows_arg):
+    FANOUTS, HIDDEN = args.cfg["fanouts"], args.cfg["hidden"]
     """Public-API path: in-memory sources -> gl.Graph -> GSL query -> compiled plan -> fused engine.
     (--api raw keeps the round-1 path that hands raw shards to the trainer, for A/B.)"""
     import torch
@@ -257,7 +276,10 @@ def run_ours(args):
     rt = init()
     assert rt.is_cuda, "bench.py needs a CUDA device"
     W = rt.world
-    shape = dict(PRODUCTS)
+    if "walk_len" in args.cfg:
+        return run_walks(args, rt)
+    FANOUTS = args.cfg["fanouts"]
+    shape = dict(args.cfg["shape"])
     if args.small:
         shape = dict(num_nodes=200_000, num_edges=5_000_000, feat_dim=100, num_classes=47)
     # ---- headline: hash-partitioned graph, NO replica cache: every remote row crosses NVLink inside the fused kernel
@@ -267,7 +289,10 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
     own, lib, names = count_own_launches(tr)
     row_bytes = int(nodes.feats.local.size(1)) * nodes.feats.local.element_size()
-    rows_per_step = args.batch * (1 + FANOUTS[0]) + args.batch * FANOUTS[0] * (1 + FANOUTS[1])
+    rows_per_step, m_ = 0, args.batch
+    for k_ in FANOUTS:                      # layer 1 gathers (1 + k_i) rows per destination of every hop pair
+        rows_per_step += m_ * (1 + k_)
+        m_ *= k_
     n_total = sum(int(x) for x in nodes.nrows)
     remote_frac = 0.0 if W == 1 else (W - 1) / W * max(0.0, 1.0 - cache_rows / max(n_total - nodes.n_local, 1))
     remote_bytes = rows_per_step * row_bytes * remote_frac
@@ -300,12 +325,12 @@ def run_ours(args):
         e2e_steps_per_s = W * args.steps / (ms_e2e / 1e3)
         fbytes = 2 if args.feature_dtype == "bf16" else 4
         out = {
-            "metric": "sampled-subgraph train steps/sec (2-layer GraphSAGE fanout 25,10, ogbn-products-shaped synthetic)",
+            "metric": args.cfg["metric"],
             "value": steps_per_s, "unit": "steps/s", "n_gpus": W, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic (random graph of ogbn-products shape, random-init weights)",
+            "dtype": "bf16", "data": args.cfg["data"],
             "impl": "graphlearn_b200",
-            "config": {"model": "GraphSAGE-2layer-mean hidden256", "global_batch": args.batch * W, "seq_len": None,
+            "config": {"name": args.config, "model": args.cfg["model"], "global_batch": args.batch * W, "seq_len": None,
                        "fanout": FANOUTS, "parallelism": "dp%d+graph-partition%d" % (W, W),
                        "api": "gsl (in-memory sources -> gl.Graph -> GSL query -> compiled plan -> fused engine)" if args.api == "gsl"
                               else "raw shards",
@@ -322,7 +347,7 @@ def run_ours(args):
                        "seeds": "fresh seed batch every step in both timed regions (device region: resident on the device; "
                                 "e2e region: GSL shuffle(traverse=True) epochs on the host)",
                        "l2_policy": "inputs larger than L2: every step gathers ~%d random feature rows from a %.1f GB table"
-                                    % (args.batch * (1 + 25 + 250), shape["num_nodes"] * shape["feat_dim"] * fbytes / 1e9),
+                                    % (rows_per_step, shape["num_nodes"] * shape["feat_dim"] * fbytes / 1e9),
                        "allreduce": tr_backend(W, args), "cuda_graph": not args.no_graph, "engine": args.engine,
                        "graph_build_s": round(build_s, 2)},
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": args.batch * 8,
@@ -332,6 +357,106 @@ def run_ours(args):
         }
         out.update(extra)
         print(json.dumps(out))
+    rt.barrier()
+    rt.shutdown()
+
+
+def run_walks(args, rt):
+    """BASELINE config 5: DeepWalk random_walk(length 40) + random negatives.  Device region: the resident-walker kernel
+    (K3) + the negative sampler kernel (K2) per step on fresh seeds; e2e region: the same through gl.Graph + GSL +
+    gl.Dataset (``V().batch().shuffle().random_walk().outNeg()``) including the D2H read of the walks."""
+    import torch
+    import torch.distributed as dist
+
+    import graphlearn_b200 as gl
+    from graphlearn_b200.ops import negative as NEG
+    from graphlearn_b200.ops import rng as rng_ops
+    from graphlearn_b200.ops import walk as WALK
+    from graphlearn_b200.store.synthetic import make_partitioned_sources
+    W, cfg = rt.world, args.cfg
+    shape = dict(cfg["shape"])
+    if args.small:
+        shape.update(num_nodes=200_000, num_edges=5_000_000)
+    L, NEGS, B = cfg["walk_len"], cfg["neg"], args.batch
+    t0 = time.time()
+    node_src, edge_src = make_partitioned_sources(rt, seed=0, feat_dim=1, num_classes=2,
+                                                  num_nodes=shape["num_nodes"], num_edges=shape["num_edges"])
+    node_src.pop("float_attrs"); node_src.pop("labels")
+    g = gl.Graph()
+    g.node(node_src, "n", decoder=gl.Decoder())
+    g.edge(edge_src, ("n", "n", "e"), decoder=gl.Decoder())
+    g.init()
+    del node_src, edge_src
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    store = g.store
+    csr, nodes = store.edges["e"], store.nodes["n"]
+    rng = rng_ops.DeviceRng(rt, 0)
+    gen = torch.Generator().manual_seed(99 + rt.rank)
+    warm = max(args.warmup, 3)
+    seeds = (torch.randint(0, nodes.n_local, (warm + args.steps + 4, B), generator=gen) * W + rt.rank).to(rt.device)
+
+    def one(i):
+        walks = WALK.random_walk(csr, seeds[i], L, 1.0, 1.0, rng=rng, salt=i)
+        neg = NEG.edge_negative(store, "e", walks.reshape(-1), NEGS, "random", None, rng=rng, salt=1000 + i)
+        rng.advance()
+        return walks, neg
+    for i in range(warm):
+        one(i)
+    torch.cuda.synchronize(); rt.barrier()
+    clocks = ClockSampler(rt.local_rank) if rt.rank == 0 else None
+    if clocks:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        one(warm + i)
+    ev1.record()
+    torch.cuda.synchronize(); rt.barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    # e2e through the public API
+    q = g.V("n").batch(B).shuffle(traverse=True).alias("src").random_walk("e", L).alias("walk") \
+         .outNeg("e").sample(NEGS).by("random").alias("neg").values()
+    ds = gl.Dataset(q, window=4)
+    for _ in range(warm):
+        ds.next()["walk"].ids
+    torch.cuda.synchronize(); rt.barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    done, d2h = 0, 0
+    while done < args.steps:
+        try:
+            v = ds.next()
+        except gl.OutOfRangeError:
+            continue
+        w_ids, n_ids = v["walk"].ids, v["neg"].ids          # numpy: device -> host read of the step's result
+        d2h = w_ids.nbytes + n_ids.nbytes
+        done += 1
+    ev3.record()
+    torch.cuda.synchronize(); rt.barrier()
+    ms_e2e = ev2.elapsed_time(ev3)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms_dev, ms_e2e], device=rt.device, dtype=torch.float64)
+    if W > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rt.rank == 0:
+        walks_s = W * B * args.steps / (ms_dev / 1e3)
+        hops_s = walks_s * L
+        print(json.dumps({
+            "metric": cfg["metric"], "value": walks_s, "unit": "walks/s", "n_gpus": W, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 ids",
+            "data": cfg["data"], "impl": "graphlearn_b200",
+            "config": {"name": args.config, "model": cfg["model"], "global_batch": B * W, "walk_len": L, "negatives_per_position": NEGS,
+                       "num_nodes": shape["num_nodes"], "num_edges": shape["num_edges"], "parallelism": "graph-partition%d" % W,
+                       "walk_hops_per_s": hops_s,
+                       "remote_adjacency_reads_per_s_per_gpu": round(hops_s / W * (W - 1) / W * 3) if W > 1 else 0,
+                       "l2_policy": "inputs larger than L2: random rows of a %.1f GB CSR" % (shape["num_edges"] * 8 / 1e9),
+                       "graph_build_s": round(build_s, 2)},
+            "e2e": {"value": W * B * args.steps / (ms_e2e / 1e3), "unit": "walks/s", "h2d_bytes_per_step": B * 8,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": 3 * args.steps, "own_kernel_names": {"glb::random_walk_kernel": 1, "glb::negative_sample_kernel": 1,
+                                                                 "glb::step_advance_kernel": 1}, "clocks": clk}))
     rt.barrier()
     rt.shutdown()
 
@@ -355,6 +480,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="products_sage2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: products_sage2 (headline, default) | sage3 | deepwalk")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--feature-dtype", default="bf16", choices=["fp32", "bf16"],
                     help="HBM storage dtype of the float attribute table (compute is bf16 either way; bf16 halves NVLink bytes)")
@@ -370,6 +497,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the labelled secondary run (replica cache / other row dtype)")
     ap.add_argument("--small", action="store_true", help="small graph for quick functional runs")
     args = ap.parse_args()
+    args.cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun

@@ -40,8 +40,9 @@ from . import nn  # noqa: E402,F401  (gl.nn, like the reference's `import graphl
 
 
 class IndexOption(object):
-    """KNN index options of the reference (graphlearn/python/c/py_export.cc); only the flat
-    (brute-force tensor-core) index exists here, the fields are kept for script parity."""
+    """KNN index options of the reference (graphlearn/python/c/py_export.cc): ``index_type`` in
+    flat | ivfflat | ivfpq (+ the ``gpu_`` variants); flat = fused tcgen05 scan, ivfflat = k-means lists probed
+    with the same kernel, ivfpq falls back to ivfflat (ops/knn.py)."""
 
     def __init__(self):
         self.name = "knn"

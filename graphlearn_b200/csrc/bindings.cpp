@@ -7,7 +7,7 @@ std::vector<at::Tensor> sample_neighbors(const at::Tensor&, const at::Tensor&, i
                                          const c10::optional<at::Tensor>&, bool, int64_t, int64_t,
                                          const at::Tensor&, int64_t, bool, const c10::optional<at::Tensor>&);
 at::Tensor get_degrees(const at::Tensor&, const at::Tensor&, int64_t);
-std::vector<at::Tensor> sample_full(const at::Tensor&, const at::Tensor&, int64_t, bool);
+std::vector<at::Tensor> sample_full(const at::Tensor&, const at::Tensor&, int64_t, bool, int64_t);
 void rng_advance(const at::Tensor&, int64_t);
 // walk.cu
 at::Tensor random_walk(const at::Tensor&, const at::Tensor&, int64_t, double, double, int64_t, int64_t,
@@ -65,13 +65,24 @@ void step_advance(const c10::optional<at::Tensor>&, const c10::optional<at::Tens
 void adam_flat(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
                double, double, double, double, double);
 void adam_pack(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, double, double, double,
-               double, double, const c10::optional<at::Tensor>&, const at::Tensor&);
+               double, double, const c10::optional<at::Tensor>&, const at::Tensor&, const c10::optional<at::Tensor>&,
+               const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, double, bool);
 // graph_ops.cu
-std::vector<at::Tensor> relabel(const at::Tensor&);
+std::vector<at::Tensor> relabel(const at::Tensor&, bool);
 at::Tensor relabel_lookup(const at::Tensor&, const at::Tensor&, const at::Tensor&);
 at::Tensor edge_scatter(const at::Tensor&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&,
                         int64_t, int64_t);
 at::Tensor edge_dot(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, int64_t);
+// idmap.cu
+at::Tensor idmap_translate(const at::Tensor&, const at::Tensor&, bool);
+// knn.cu
+std::vector<at::Tensor> knn_flat_topk(const at::Tensor&, int64_t, const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&,
+                                      const at::Tensor&, int64_t, int64_t);
+std::vector<at::Tensor> knn_merge_peers(const at::Tensor&, int64_t, int64_t, int64_t, const at::Tensor&);
+// dgs.cu
+void dgs_apply_edges(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
+                     const at::Tensor&, const c10::optional<at::Tensor>&);
+std::vector<at::Tensor> dgs_lookup(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, int64_t);
 // host_loader.cpp
 std::vector<at::Tensor> load_table(const std::string&, bool, bool, bool, bool, std::vector<int64_t>,
                                    std::vector<int64_t>, const std::string&, const std::string&, int64_t,
@@ -119,6 +130,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("relabel_lookup", &glb::relabel_lookup);
   m.def("edge_scatter", &glb::edge_scatter);
   m.def("edge_dot", &glb::edge_dot);
+  m.def("idmap_translate", &glb::idmap_translate);
+  m.def("knn_flat_topk", &glb::knn_flat_topk);
+  m.def("knn_merge_peers", &glb::knn_merge_peers);
+  m.def("dgs_apply_edges", &glb::dgs_apply_edges);
+  m.def("dgs_lookup", &glb::dgs_lookup);
   m.def("load_table", &glb::load_table);
   m.def("save_embeddings", &glb::save_embeddings);
 }

@@ -67,7 +67,7 @@ at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, int64_t dtyp
 // ---------------------------------------------------------------------------
 // K8: one-shot all-reduce over peer memory
 // ---------------------------------------------------------------------------
-constexpr int kArMaxBlocks = 64;
+constexpr int kArMaxBlocks = 256;
 
 struct AllReduceParams {
   PeerTableMut stage;        // per rank: float [2][n_pad]   (double buffered staging, symmetric)
@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const AllReduceP
   __syncthreads();
 
   // phase 1: block-level cross-GPU barrier (block b of every rank)
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
   if (threadIdx.x < p.world) {
     const int r = threadIdx.x;
     unsigned int* remote = reinterpret_cast<unsigned int*>(p.flags.p[r]) + b * kMaxWorld + p.rank;
@@ -116,10 +119,16 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const AllReduceP
     const unsigned int* mine = reinterpret_cast<const unsigned int*>(p.flags.p[p.rank]) + b * kMaxWorld + r;
     long long t0 = clock64();
     while ((int)(ld_acquire_sys(mine) - (unsigned int)e) < 0) {
-      if (clock64() - t0 > 20000000000LL) { *p.error_flag = 1; break; }   // ~10 s watchdog
+      if (clock64() - t0 > 20000000000LL) { *p.error_flag = 1; timed_out = 1; break; }   // ~10 s watchdog
     }
   }
   __syncthreads();
+  if (timed_out) {
+    // a peer died or diverged: ABORT - the local gradient stays untouched (never reduce half-written staging
+    // buffers); the sticky error flag makes the fused optimiser skip its update and PeerAllReduce.check() raise
+    if (threadIdx.x == 0) p.epochs[b] = e;
+    return;
+  }
 
   // phase 2: pull + reduce every rank's slice straight from peer HBM
   for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi; i += 4 * (int64_t)blockDim.x) {
@@ -207,7 +216,8 @@ constexpr int kMaxPackMats = 8;
 struct PackMat {
   long long off;          // first element in the flat buffer
   int n_out, k_total;     // fp32 master [n_out, k_total]
-  int N;                  // rows of the forward image per k-block (padded n_out)
+  int N;                  // rows of ONE forward image per k-block (padded n_out, or n_out / n_imgs for N-split layers);
+                          // image i holds the weight rows [i * N, i * N + N)
   uint8_t* img;           // forward image: (k_total/64) k-blocks of [N x 64] bf16, SW128
   uint8_t* img_t;         // W^T images (or null): [n_imgs][kpad_t/64 k-blocks][nrows_t x 64]
   int kpad_t, nrows_t;
@@ -221,30 +231,115 @@ struct AdamPackParams {
   float* loss_out;
   PackMat mats[kMaxPackMats];
   int n_mats;
+  // fused one-shot peer all-reduce of the gradient (world > 1): stage -> cross-GPU flag barrier -> every rank pulls
+  // all peers' slices, reduces in registers and applies Adam right away (the reduced gradient is never written back)
+  PeerTableMut stage;                // per rank: [2][n_pad] fp32 (or bf16 in the same bytes), double buffered
+  PeerTableMut flags;                // per rank: uint32 [kArMaxBlocks][kMaxWorld]
+  unsigned long long* epochs;        // local [kArMaxBlocks]
+  int* error_flag;                   // sticky: a barrier timed out -> skip every later update
+  long long n_pad;
+  float ar_scale;
+  int rank, world, stage_bf16;
 };
 
-__global__ void __launch_bounds__(64) adam_pack_kernel(const __grid_constant__ AdamPackParams p) {
+__global__ void __launch_bounds__(128) adam_pack_kernel(const __grid_constant__ AdamPackParams p) {
   const float step = (float)p.step_ptr[0];
   const float bc1 = 1.f - powf(p.beta1, step);
   const float bc2 = 1.f - powf(p.beta2, step);
   const float step_size = p.lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
+  if (p.error_flag != nullptr && *p.error_flag != 0) return;          // a previous collective failed: freeze the model
+  // contiguous slice of 8-element chunks per block (identical on every rank: slices are matched by block index)
+  const long long chunks = p.n >> 3;
+  const long long per_block = (chunks + gridDim.x - 1) / gridDim.x;
+  const long long c_lo = (long long)blockIdx.x * per_block, c_hi = min(chunks, c_lo + per_block);
+  unsigned long long e = 0;
+  int parity = 0;
+  if (p.world > 1) {
+    const int b = blockIdx.x;
+    e = p.epochs[b] + 1;
+    parity = (int)(e & 1);
+    // phase 0: publish my (scaled) slice
+    if (p.stage_bf16) {
+      uint4* st = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.stage.p[p.rank]) + (size_t)parity * p.n_pad);
+      for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+        const float4 a = *reinterpret_cast<const float4*>(p.g + (c << 3)), b4 = *reinterpret_cast<const float4*>(p.g + (c << 3) + 4);
+        uint4 o;
+        o.x = pack_bf16x2(a.x * p.ar_scale, a.y * p.ar_scale); o.y = pack_bf16x2(a.z * p.ar_scale, a.w * p.ar_scale);
+        o.z = pack_bf16x2(b4.x * p.ar_scale, b4.y * p.ar_scale); o.w = pack_bf16x2(b4.z * p.ar_scale, b4.w * p.ar_scale);
+        st[c] = o;
+      }
+    } else {
+      float4* st = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.stage.p[p.rank]) + (size_t)parity * p.n_pad);
+      for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 a = *reinterpret_cast<const float4*>(p.g + (c << 3) + 4 * h);
+          a.x *= p.ar_scale; a.y *= p.ar_scale; a.z *= p.ar_scale; a.w *= p.ar_scale;
+          st[2 * c + h] = a;
+        }
+      }
+    }
+    __threadfence_system();
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    // phase 1: cross-GPU barrier of block b
+    if (threadIdx.x < p.world) {
+      const int r = threadIdx.x;
+      st_release_sys(reinterpret_cast<unsigned int*>(p.flags.p[r]) + b * kMaxWorld + p.rank, (unsigned int)e);
+      const unsigned int* mine = reinterpret_cast<const unsigned int*>(p.flags.p[p.rank]) + b * kMaxWorld + r;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(mine) - (unsigned int)e) < 0) {
+        if (clock64() - t0 > 20000000000LL) { *p.error_flag = 1; timed_out = 1; break; }   // ~10 s watchdog
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.epochs[b] = e;
+    if (timed_out) return;                                             // abort: parameters stay untouched
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (p.loss_out) p.loss_out[0] = p.scratch[0];
     for (int i = 0; i < p.n_scratch; ++i) p.scratch[i] = 0.f;
   }
-  const long long chunks = p.n >> 3;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (long long)gridDim.x * blockDim.x) {
+  for (long long c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
     const long long i0 = c << 3;
     float w[8], g[8], m[8], v[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float4 a = *reinterpret_cast<const float4*>(p.w + i0 + 4 * h), b = *reinterpret_cast<const float4*>(p.g + i0 + 4 * h);
+      const float4 a = *reinterpret_cast<const float4*>(p.w + i0 + 4 * h);
       const float4 cm = *reinterpret_cast<const float4*>(p.m + i0 + 4 * h), cv = *reinterpret_cast<const float4*>(p.v + i0 + 4 * h);
       w[4 * h] = a.x; w[4 * h + 1] = a.y; w[4 * h + 2] = a.z; w[4 * h + 3] = a.w;
-      g[4 * h] = b.x; g[4 * h + 1] = b.y; g[4 * h + 2] = b.z; g[4 * h + 3] = b.w;
       m[4 * h] = cm.x; m[4 * h + 1] = cm.y; m[4 * h + 2] = cm.z; m[4 * h + 3] = cm.w;
       v[4 * h] = cv.x; v[4 * h + 1] = cv.y; v[4 * h + 2] = cv.z; v[4 * h + 3] = cv.w;
+    }
+    if (p.world > 1) {
+      // phase 2: pull + reduce this chunk straight from every peer's staging buffer
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < p.world) {
+          if (p.stage_bf16) {
+            const uint4 u = __ldcv(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.stage.p[r]) + (size_t)parity * p.n_pad) + c);
+            float2 x;
+            x = unpack_bf16x2(u.x); g[0] += x.x; g[1] += x.y;
+            x = unpack_bf16x2(u.y); g[2] += x.x; g[3] += x.y;
+            x = unpack_bf16x2(u.z); g[4] += x.x; g[5] += x.y;
+            x = unpack_bf16x2(u.w); g[6] += x.x; g[7] += x.y;
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.stage.p[r]) + (size_t)parity * p.n_pad) + 2 * c;
+            const float4 a = __ldcv(src), b4 = __ldcv(src + 1);
+            g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w; g[4] += b4.x; g[5] += b4.y; g[6] += b4.z; g[7] += b4.w;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 b4 = *reinterpret_cast<const float4*>(p.g + i0 + 4 * h);
+        g[4 * h] = b4.x; g[4 * h + 1] = b4.y; g[4 * h + 2] = b4.z; g[4 * h + 3] = b4.w;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -274,7 +369,9 @@ __global__ void __launch_bounds__(64) adam_pack_kernel(const __grid_constant__ A
       uint4 val;
       val.x = pack_bf16x2(w[0], w[1]); val.y = pack_bf16x2(w[2], w[3]); val.z = pack_bf16x2(w[4], w[5]); val.w = pack_bf16x2(w[6], w[7]);
       const int kb = kcol >> 6, ch = (kcol & 63) >> 3;
-      const size_t off = (size_t)kb * pm.N * 128 + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)((ch ^ (n & 7)) * 16);
+      const int fi = n / pm.N, nl = n - fi * pm.N;                       // forward image index, row inside it
+      const size_t off = ((size_t)fi * (pm.k_total >> 6) + kb) * pm.N * 128 + (size_t)(nl >> 3) * 1024 + (size_t)(nl & 7) * 128 +
+                         (size_t)((ch ^ (nl & 7)) * 16);
       *reinterpret_cast<uint4*>(pm.img + off) = val;
       if (pm.img_t) {
         // W^T image: row = column of W (kcol + i), k index = n
@@ -296,7 +393,8 @@ __global__ void __launch_bounds__(64) adam_pack_kernel(const __grid_constant__ A
 // mats: CPU int64 [n_mats, 8] = (off, n_out, k_total, N, img_ptr, img_t_ptr, kpad_t, nrows_t)
 void adam_pack(const at::Tensor& w, const at::Tensor& g_store, const at::Tensor& m, const at::Tensor& v, const at::Tensor& step,
                double lr, double beta1, double beta2, double eps, double weight_decay, const c10::optional<at::Tensor>& loss_out,
-               const at::Tensor& mats) {
+               const at::Tensor& mats, const c10::optional<at::Tensor>& ar_desc, const c10::optional<at::Tensor>& ar_epochs,
+               const c10::optional<at::Tensor>& ar_error, double ar_scale, bool stage_bf16) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.is_contiguous() && w.numel() % 8 == 0, "flat params must be padded to 8");
   TORCH_CHECK(g_store.is_cuda() && g_store.scalar_type() == at::kFloat && g_store.numel() >= w.numel() && m.numel() == w.numel() && v.numel() == w.numel());
   TORCH_CHECK(mats.device().is_cpu() && mats.scalar_type() == at::kLong && mats.dim() == 2 && mats.size(1) == 8 && mats.size(0) <= kMaxPackMats);
@@ -318,10 +416,27 @@ void adam_pack(const at::Tensor& w, const at::Tensor& g_store, const at::Tensor&
     pm.kpad_t = (int)d[8 * i + 6]; pm.nrows_t = (int)d[8 * i + 7];
     TORCH_CHECK(pm.off % 8 == 0 && pm.k_total % 64 == 0, "weight matrices must start 8-aligned with K padded to 64");
   }
+  p.world = 1;
+  if (ar_desc.has_value() && ar_desc->defined()) {
+    // desc (CPU int64): [rank, world, n_pad, stage_ptr[8], flags_ptr[8]]  (PeerAllReduce.desc)
+    TORCH_CHECK(ar_desc->device().is_cpu() && ar_desc->scalar_type() == at::kLong && ar_desc->numel() == 3 + 2 * kMaxWorld);
+    const int64_t* a = ar_desc->data_ptr<int64_t>();
+    p.rank = (int)a[0]; p.world = (int)a[1]; p.n_pad = a[2];
+    for (int r = 0; r < kMaxWorld; ++r) {
+      p.stage.p[r] = reinterpret_cast<void*>(a[3 + r]);
+      p.flags.p[r] = reinterpret_cast<void*>(a[3 + kMaxWorld + r]);
+    }
+    TORCH_CHECK(p.n <= p.n_pad && ar_epochs.has_value() && ar_epochs->numel() >= kArMaxBlocks && ar_error.has_value());
+    p.epochs = reinterpret_cast<unsigned long long*>(ar_epochs->data_ptr<int64_t>());
+    p.error_flag = ar_error->data_ptr<int>();
+    p.ar_scale = (float)ar_scale;
+    p.stage_bf16 = stage_bf16 ? 1 : 0;
+  }
   if (p.n == 0) return;
-  // small blocks: the work is one 8-element chunk per thread, spread it over every SM
-  const int blocks = (int)std::min<int64_t>((int64_t)sm_count() * 16, ((p.n >> 3) + 63) / 64);
-  adam_pack_kernel<<<std::max(blocks, 1), 64, 0, at::cuda::getCurrentCUDAStream()>>>(p);
+  // small blocks: one 8-element chunk per thread per pass, spread over every SM; the grid depends only on n, so it
+  // is identical on every rank (the fused all-reduce matches slices by block index)
+  const int blocks = (int)std::min<int64_t>(kArMaxBlocks, ((p.n >> 3) + 127) / 128);
+  adam_pack_kernel<<<std::max(blocks, 1), 128, 0, at::cuda::getCurrentCUDAStream()>>>(p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

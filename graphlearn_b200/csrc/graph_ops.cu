@@ -144,7 +144,9 @@ inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + pe
 }  // namespace
 
 // returns (uniq [U] in first-occurrence order, inverse [n] (-1 for negative ids), table_keys, table_rank)
-std::vector<at::Tensor> relabel(const at::Tensor& ids_in) {
+// sync_free: `uniq` is allocated with the upper bound n (entries past the real count are -1) and the count comes back as
+// a device tensor - no value is read on the host, so the op can sit inside a captured graph.
+std::vector<at::Tensor> relabel(const at::Tensor& ids_in, bool sync_free) {
   check_cuda_i64(ids_in, "ids");
   c10::cuda::CUDAGuard guard(ids_in.device());
   auto ids = ids_in.contiguous().view({-1});
@@ -156,7 +158,7 @@ std::vector<at::Tensor> relabel(const at::Tensor& ids_in) {
   auto first = at::full({cap}, std::numeric_limits<int64_t>::max(), opts);
   auto slot_rank = at::full({cap}, (int64_t)-1, opts);
   auto inverse = at::empty({n}, opts);
-  if (n == 0) return {at::empty({0}, opts), inverse, keys, slot_rank};
+  if (n == 0) return {at::empty({0}, opts), inverse, keys, slot_rank, at::zeros({1}, opts)};
   auto slot_of = at::empty({n}, opts);
   auto flag = at::empty({n}, opts);
   auto stream = at::cuda::getCurrentCUDAStream();
@@ -167,13 +169,13 @@ std::vector<at::Tensor> relabel(const at::Tensor& ids_in) {
   relabel_flag_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ids.data_ptr<int64_t>(), n, kp, fp, mask,
                                                               slot_of.data_ptr<int64_t>(), flag.data_ptr<int64_t>());
   auto rank = at::cumsum(flag, 0);
-  const int64_t U = rank[n - 1].item<int64_t>();        // host sync: the output size is data dependent
-  auto uniq = at::empty({U}, opts);
+  const int64_t U = sync_free ? n : rank[n - 1].item<int64_t>();    // eager API: exact, data dependent size
+  auto uniq = sync_free ? at::full({U}, (int64_t)-1, opts) : at::empty({U}, opts);
   relabel_finish_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(
       ids.data_ptr<int64_t>(), n, slot_of.data_ptr<int64_t>(), fp, rank.data_ptr<int64_t>(),
       uniq.data_ptr<int64_t>(), inverse.data_ptr<int64_t>(), slot_rank.data_ptr<int64_t>());
   C10_CUDA_KERNEL_LAUNCH_CHECK();
-  return {uniq, inverse, keys, slot_rank};
+  return {uniq, inverse, keys, slot_rank, rank.slice(0, n - 1, n)};
 }
 
 // compact index of every query id in a table built by relabel(); -1 when absent

@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
     }
     umma::fence_barrier_init();
   }
-  if (tid < 256) sBias[tid] = (p.bias && tid < p.n_out) ? __ldg(p.bias + tid) : 0.f;
+  const int img = (int)blockIdx.x % p.n_imgs;
+  // (multi-image launches: image `img` owns the output columns [img * N, img * N + N) and the matching bias slice)
+  if (tid < 256) sBias[tid] = (p.bias && tid < p.n_out) ? __ldg(p.bias + img * p.N + tid) : 0.f;
   if (warp == kMmaWarp) {
     umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     umma::tmem_relinquish();
@@ -400,7 +402,6 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int img = (int)blockIdx.x % p.n_imgs;
   const int tile_first = (int)blockIdx.x / p.n_imgs, tile_stride = (int)gridDim.x / p.n_imgs;
   if (warp == 0) GLB_DBG(0);
 
@@ -816,7 +817,7 @@ void sage_fused_multi(const at::Tensor& tself_desc, const at::Tensor& tnbr_desc,
   at::Tensor b;
   if (bias.has_value() && bias->defined()) {
     b = bias->contiguous();
-    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out, "bias must be fp32 [>= n_out]");
+    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out * std::max<int64_t>(n_imgs, 1), "bias must be fp32 [>= n_out]");
     p.bias = b.data_ptr<float>();
   }
   p.out_stride = -1;

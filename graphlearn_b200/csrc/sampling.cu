@@ -195,6 +195,8 @@ full_scatter_kernel(const CsrView g, const int64_t* __restrict__ src, int64_t B,
   int64_t d = r.deg;
   if (cap > 0 && d > cap) d = cap;
   int64_t o = __ldg(offsets + w);
+  const int64_t room = __ldg(offsets + w + 1) - o;        // sync-free mode clamps the offsets to the output capacity
+  if (d > room) d = room;
   for (int64_t i = lane; i < d; i += 32) {
     out_nbr[o + i] = __ldg(r.indices + r.beg + i);
     if (out_eid) out_eid[o + i] = r.eids ? __ldg(r.eids + r.beg + i) : (r.beg + i);
@@ -293,8 +295,11 @@ at::Tensor get_degrees(const at::Tensor& csr_desc, const at::Tensor& src, int64_
 }
 
 // returns (values, eids, offsets[B+1]); sparse output like FullSampler.
+// `max_total` > 0: sync-free mode for static-shape / graph-captured callers - the outputs are allocated with that
+// capacity (rows are truncated when the data needs more; offsets[B] tells how much was really produced) and no
+// device value is read back.  `max_total` <= 0: the exact size is read from the device (one host sync).
 std::vector<at::Tensor> sample_full(const at::Tensor& csr_desc, const at::Tensor& src, int64_t cap,
-                                    bool want_eids) {
+                                    bool want_eids, int64_t max_total) {
   check_cuda_i64(src, "src");
   c10::cuda::CUDAGuard guard(src.device());
   CsrView g = csr_from_desc(csr_desc);
@@ -303,8 +308,14 @@ std::vector<at::Tensor> sample_full(const at::Tensor& csr_desc, const at::Tensor
   auto deg = get_degrees(csr_desc, srcc, cap);
   auto offsets = at::zeros({B + 1}, src.options());
   if (B > 0) offsets.slice(0, 1).copy_(at::cumsum(deg, 0));
-  int64_t total = B > 0 ? offsets[B].item<int64_t>() : 0;   // host sync: output size is data dependent
-  auto vals = at::empty({total}, src.options());
+  int64_t total;
+  if (max_total > 0) {
+    total = max_total;                                        // capacity given by the caller: no host sync
+    offsets.clamp_max_(max_total);                            // rows past the capacity become empty / truncated
+  } else {
+    total = B > 0 ? offsets[B].item<int64_t>() : 0;           // eager API: the exact size is data dependent
+  }
+  auto vals = max_total > 0 ? at::full({total}, (int64_t)-1, src.options()) : at::empty({total}, src.options());
   at::Tensor eids;
   if (want_eids) eids = at::empty({total}, src.options());
   if (total > 0) {

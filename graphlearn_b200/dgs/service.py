@@ -11,7 +11,8 @@ class SampleStore(object):
 
     def __init__(self, num_vertices: int, capacity: int, device, feat_dim: int = 0):
         self.n, self.K = int(num_vertices), int(capacity)
-        self.device = device
+        self.device = torch.device(device)
+        device = self.device
         self.nbr = torch.full((self.n, self.K), -1, dtype=torch.int64, device=device)
         self.ts = torch.full((self.n, self.K), -(2 ** 62), dtype=torch.int64, device=device)
         self.w = torch.zeros((self.n, self.K), dtype=torch.float32, device=device)
@@ -59,6 +60,14 @@ class SampleStore(object):
         w = torch.ones_like(ts, dtype=torch.float32) if w is None else w.to(self.device).float()
         order = torch.argsort(ts, stable=True)
         src, dst, ts, w = src[order], dst[order], ts[order], w[order]
+        if self.device.type == "cuda" and self.K <= 64:
+            # one launch per record batch (csrc/dgs.cu): sort by (src, ts), the thread on the last record of every
+            # source folds that source's <= K newest records into its row
+            from ..parallel.runtime import native
+            o2 = torch.argsort(src, stable=True)
+            native().dgs_apply_edges(self.nbr, self.ts, self.w, self.count, src[o2].contiguous(), dst[o2].contiguous(),
+                                     ts[o2].contiguous(), w[o2].contiguous())
+            return
         pending = torch.ones_like(src, dtype=torch.bool)
         while bool(pending.any()):
             idx = pending.nonzero().flatten()
@@ -108,6 +117,10 @@ class SampleStore(object):
 
     def lookup(self, vids: torch.Tensor, k: int):
         """most recent k samples of each vertex: (nbr [B,k], ts [B,k], w [B,k]); -1 padded."""
+        if self.device.type == "cuda" and self.K <= 64:
+            from ..parallel.runtime import native
+            n_, t_, w_ = native().dgs_lookup(self.nbr, self.ts, self.w, vids.to(self.device).to(torch.int64), int(k))
+            return n_, t_, w_
         vids = torch.where(vids < self.n, vids, torch.zeros_like(vids)) if vids.numel() else vids
         t, order = torch.sort(self.ts[vids], dim=1, descending=True)
         order = order[:, :k]

@@ -42,7 +42,8 @@ from ..store.shards import CsrShard, NodeTable
 class FastSageTrainer:
     def __init__(self, rt: Runtime, nodes: NodeTable, csr: CsrShard, model, fanouts: Sequence[int], batch_size: int,
                  lr: float = 3e-3, strategy: str = "random", use_cuda_graph: bool = True, allreduce: str = "peer",
-                 seed: int = 0):
+                 seed: int = 0, allreduce_dtype: str = "fp32"):
+        self.ar_bf16 = allreduce_dtype == "bf16"      # stage the gradient exchange in bf16 (halves the NVLink bytes)
         assert rt.is_cuda, "FastSageTrainer is the CUDA engine; use SageTrainer for the portable path"
         self.rt, self.nodes, self.csr, self.model = rt, nodes, csr, model
         self.fanouts = list(fanouts)
@@ -69,9 +70,16 @@ class FastSageTrainer:
             self.n.append(self.n[-1] * k)
         convs = list(model.convs)
         self.convs = convs
+        self.n_split: List[int] = []           # forward images per layer (N-split when W does not fit next to the A tiles)
         for c in convs:
             assert c.agg_type in ("mean", "sum"), "fast engine supports mean / sum aggregation"
-            assert sage_ops.fused_supported(c.in_self, c.in_nbr, c.out_dim, c.agg_type, max(self.fanouts))
+            kt, N = c.weight_p.size(1), sage_ops.pad_n(c.out_dim)
+            ns = 1
+            while not sage_ops.smem_fits(kt, N // ns) and (N // ns) % 64 == 0 and ns < 8:
+                ns *= 2
+            assert sage_ops.smem_fits(kt, N // ns) and (ns == 1 or N == c.out_dim), "layer does not fit the fused kernel"
+            assert sage_ops.fused_supported(c.in_self, c.in_nbr, min(c.out_dim, N // ns), c.agg_type, max(self.fanouts))
+            self.n_split.append(ns)
         # per layer l (1-based): segments i = 0..L-l, rows concatenated
         self.seg_off: List[List[int]] = []
         self.H: List[Optional[torch.Tensor]] = []      # layer outputs (bf16; last layer fp32 logits)
@@ -106,7 +114,7 @@ class FastSageTrainer:
             self.img.append(torch.zeros(kt * N, dtype=torch.bfloat16, device=dev))
             kpad = self.dZp[l - 1].size(1)
             self.img_t.append(torch.zeros((kt + 255) // 256, kpad * 256, dtype=torch.bfloat16, device=dev) if l > 1 else None)
-            mats.append([model._glb_param_offsets[id(c.weight_p)], n_out, kt, N, self.img[-1].data_ptr(),
+            mats.append([model._glb_param_offsets[id(c.weight_p)], n_out, kt, N // self.n_split[l - 1], self.img[-1].data_ptr(),
                          self.img_t[-1].data_ptr() if l > 1 else 0, kpad, 256])
         self._mats = torch.tensor(mats, dtype=torch.int64)
         self.loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -269,12 +277,14 @@ class FastSageTrainer:
         for l in range(1, L + 1):
             c = self.convs[l - 1]
             last = l == L
-            N = sage_ops.pad_n(c.out_dim)
+            ns = self.n_split[l - 1]
+            N = sage_ops.pad_n(c.out_dim) // ns
+            n_out = c.out_dim if ns == 1 else N
             img = self.img[l - 1]
             offs = self.seg_off[l - 1]
             mode = sage_ops.MODE[c.agg_type]
             nseg = L - l + 1
-            outs = [self.H[l - 1][offs[i]:offs[i + 1]] for i in range(nseg)]
+            outs = [self.H[l - 1][offs[i]:offs[i + 1], :n_out] for i in range(nseg)]
             asv = [self.A[l - 1][offs[i]:offs[i + 1]] for i in range(nseg)]
             Ms, ks = [self.n[i] for i in range(nseg)], [self.fanouts[i] for i in range(nseg)]
             ce = []
@@ -284,14 +294,14 @@ class FastSageTrainer:
             if l == 1:
                 d = self.nodes.feat_desc
                 C.sage_fused_multi(d, d, [hops[i] for i in range(nseg)], [hops[i + 1] for i in range(nseg)],
-                                   [0] * nseg, [0] * nseg, Ms, ks, outs, asv, mode, img, c.bias, N, c.out_dim,
-                                   not last, not last, 0, ce, self.rt.world, 1)
+                                   [0] * nseg, [0] * nseg, Ms, ks, outs, asv, mode, img, c.bias, N, n_out,
+                                   not last, not last, 0, ce, self.rt.world, ns)
             else:
                 po = self.seg_off[l - 2]
                 d = local_table_desc(self.H[l - 2])
                 C.sage_fused_multi(d, d, [None] * nseg, [None] * nseg, [po[i] for i in range(nseg)],
                                    [po[i + 1] for i in range(nseg)], Ms, ks, outs, asv, mode, img, c.bias, N,
-                                   c.out_dim, not last, not last, 0, ce, self.rt.world, 1)
+                                   n_out, not last, not last, 0, ce, self.rt.world, ns)
         if self._post_loss_hook is not None:
             self._post_loss_hook()          # e2e graph capture: fork the loss D2H here, parallel to the backward
         # ---- backward: all GEMMs on tcgen05 (csrc/sage_bwd.cu), no library kernels
@@ -345,20 +355,30 @@ class FastSageTrainer:
             main.wait_stream(self._sample_stream)
         if self._pre_opt_join is not None:
             main.wait_stream(self._pre_opt_join)       # the loss must have left before the optimiser clears it
-        self.ar(self.flat_g, average=True)
+        o, ar = self.opt, self.ar
         if self._skip_opt:
+            ar(self.flat_g, average=True)
             return
-        o = self.opt
-        C.adam_pack(self.flat_p, self.g_store, o.m, o.v, o.step_t, o.lr, o.betas[0], o.betas[1], o.eps, o.wd, self.loss_out,
-                    self._mats)
+        if ar.backend == "peer":
+            # ONE kernel: stage grads (scaled, optionally bf16) -> cross-GPU flag barrier -> pull + reduce every peer's
+            # slice in registers -> Adam -> zero grads -> next step's weight images (K8 fused with cast/scale + optimiser)
+            C.adam_pack(self.flat_p, self.g_store, o.m, o.v, o.step_t, o.lr, o.betas[0], o.betas[1], o.eps, o.wd,
+                        self.loss_out, self._mats, ar.desc, ar.epochs, ar.error, 1.0 / self.rt.world, self.ar_bf16)
+        else:
+            ar(self.flat_g, average=True)
+            C.adam_pack(self.flat_p, self.g_store, o.m, o.v, o.step_t, o.lr, o.betas[0], o.betas[1], o.eps, o.wd,
+                        self.loss_out, self._mats, None, None, None, 1.0, False)
 
     def repack(self):
         """Rebuild the bf16 weight images from the fp32 master weights (after init / load_state_dict / any
         external modification of the parameters)."""
         for l in range(1, self.L + 1):
             c = self.convs[l - 1]
-            N = sage_ops.pad_n(c.out_dim)
-            self.img[l - 1].copy_(self.C.pack_weight_f32(c.weight_p.detach().contiguous(), N, False)[0])
+            ns = self.n_split[l - 1]
+            N = sage_ops.pad_n(c.out_dim) // ns
+            w = c.weight_p.detach().contiguous()
+            self.img[l - 1].copy_(torch.cat([self.C.pack_weight_f32(w[i * N:(i + 1) * N].contiguous(), N, False)[0]
+                                             for i in range(ns)]) if ns > 1 else self.C.pack_weight_f32(w, N, False)[0])
             if l > 1:
                 self.img_t[l - 1].copy_(self.C.pack_weight_t(c.weight_p.detach().contiguous(), self.dZp[l - 1].size(1), 256))
 

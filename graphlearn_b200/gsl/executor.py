@@ -55,7 +55,7 @@ class QueryExecutor(object):
             # kernel path only id translation of non-dense id spaces and host-side string attributes are
             collective = not (self.rt.is_cuda and _config.get().use_peer_kernels)
             for tab in self.store.nodes.values():
-                collective = collective or tab.strings is not None or not tab.idmap.dense
+                collective = collective or tab.strings is not None or tab.idmap.collective
             for csr in self.store.edges.values():
                 collective = collective or getattr(csr, "strings", None) is not None
             sync_epoch = self.rt.world > 1 and collective

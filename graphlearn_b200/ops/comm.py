@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 from ..parallel.runtime import MAX_WORLD, Runtime, native
 
-_AR_BLOCKS = 64
+_AR_BLOCKS = 256
 
 
 class PeerAllReduce:

@@ -212,12 +212,14 @@ def get_degrees(csr: CsrShard, src_vids: torch.Tensor, cap: int = 0) -> torch.Te
     return part.remote_apply(src, fn, W)[0]
 
 
-def sample_full(csr: CsrShard, src_vids: torch.Tensor, cap: int = 0, want_eids: bool = True):
+def sample_full(csr: CsrShard, src_vids: torch.Tensor, cap: int = 0, want_eids: bool = True, max_total: int = 0):
     """FullSampler: sparse output (values, eids, offsets[B+1])
-    (graphlearn/src/core/operator/sampler/full_sampler.cc:43-88)."""
+    (graphlearn/src/core/operator/sampler/full_sampler.cc:43-88).  ``max_total`` > 0 (CUDA): sync-free mode - outputs
+    have that fixed capacity (-1 padded, rows truncated when the data needs more), nothing is read back on the host,
+    so the op is CUDA-graph capturable; ``offsets[B]`` holds the produced count on the device."""
     src = src_vids.reshape(-1).to(torch.int64)
     if csr.rt.is_cuda and _config.get().use_peer_kernels:
-        vals, eids, offsets = native().sample_full(csr.desc, src, int(cap), bool(want_eids))
+        vals, eids, offsets = native().sample_full(csr.desc, src, int(cap), bool(want_eids), int(max_total))
         return vals, (eids if want_eids else None), offsets
     W = csr.rt.world
     deg = get_degrees(csr, src, cap)

@@ -70,12 +70,14 @@ class Relabel(object):
     compact index of arbitrary ids (-1 when absent) - the sorted-set intersection of the subgraph sampler
     without sorting."""
 
-    def __init__(self, ids: torch.Tensor):
+    def __init__(self, ids: torch.Tensor, sync_free: bool = False):
+        """``sync_free`` (CUDA): ``uniq`` keeps the upper-bound length n (-1 padded) and ``n_unique`` stays on the device - no
+        host sync, CUDA-graph capturable."""
         flat = ids.reshape(-1).to(torch.int64)
         self._shape = tuple(ids.shape)
         C = _native_for(flat)
         if C is not None:
-            self.uniq, inv, self._keys, self._rank = C.relabel(flat)
+            self.uniq, inv, self._keys, self._rank, self.n_unique = C.relabel(flat, bool(sync_free))
             self._C = C
         else:
             self._C = None

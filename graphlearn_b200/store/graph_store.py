@@ -279,6 +279,10 @@ class GraphStore(object):
                     arr[rows.cpu().numpy()] = np.concatenate([p["strs"] for p in parts])
                 tab.strings = arr
             self.nodes[t] = tab
+            for src_ in node_sources:          # g.node(..., option=gl.IndexOption()) -> KNN index on this table
+                if src_.types == t and getattr(src_.option, "name", None) == "knn":
+                    from ..ops import knn as _knn
+                    _knn.build_index(tab, src_.option)
         # ---- edge shards
         for et in self.topology.edge_types():
             st, dt = self.topology.get_src_type(et), self.topology.get_dst_type(et)

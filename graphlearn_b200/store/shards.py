@@ -56,6 +56,22 @@ class IdMap:
         self.local_ids = local_ids              # sorted ascending (general) / implicit (dense)
         self.n_local = int(local_ids.numel())
         self.nrows = rt.all_gather_object(self.n_local)
+        # non-dense id spaces on CUDA: the sorted ids live in a symmetric buffer so that ANY rank translates
+        # id <-> vid with a peer-memory binary search (csrc/idmap.cu) - no collective, no lock-step epochs
+        self.peer_desc = None
+        if not dense and rt.is_cuda:
+            st = rt.symm_empty((max(self.n_local, 1),), torch.int64)
+            if self.n_local:
+                st.local[:self.n_local].copy_(local_ids)
+            self._symm_ids = st
+            pad = lambda xs: list(xs) + [0] * (8 - len(xs))  # noqa: E731
+            self.peer_desc = torch.tensor([rt.world] + pad(self.nrows) + pad(st.ptrs), dtype=torch.int64)
+            rt.barrier()
+
+    @property
+    def collective(self) -> bool:
+        """True when to_vid / to_id are collectives (every rank must call them together)."""
+        return (not self.dense) and self.rt.world > 1 and self.peer_desc is None
 
     @staticmethod
     def build(rt: Runtime, local_ids: torch.Tensor) -> "IdMap":
@@ -93,6 +109,9 @@ class IdMap:
             return torch.where(ok, ids, torch.full_like(ids, -1))
         if W == 1:
             return self._local_rows(ids)        # vid == row
+        if self.peer_desc is not None and ids.is_cuda:
+            from ..parallel.runtime import native
+            return native().idmap_translate(self.peer_desc, ids.reshape(-1), True).reshape(ids.shape)
         flat = ids.reshape(-1)
         (rows,) = part.remote_apply(flat, lambda x: (self._local_rows(x),), W)
         vid = torch.where(rows >= 0, rows * W + part.owner_of(flat, W), torch.full_like(rows, -1))
@@ -116,6 +135,9 @@ class IdMap:
 
         if W == 1:
             return look(flat)[0].reshape(vids.shape)
+        if self.peer_desc is not None and vids.is_cuda:
+            from ..parallel.runtime import native
+            return native().idmap_translate(self.peer_desc, flat, False).reshape(vids.shape)
         # route by owner = vid % W (vids are non-negative when valid)
         (ids,) = part.remote_apply(flat.clamp(min=0), look, W)
         return torch.where(flat >= 0, ids, torch.full_like(ids, -1)).reshape(vids.shape)

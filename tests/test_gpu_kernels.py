@@ -416,7 +416,8 @@ def test_trainer_cuda_graph_learns(rt):
     assert int(tr.rng.state[1].item()) >= 60
 
 
-def test_fast_engine_matches_autograd(rt):
+@pytest.mark.parametrize("L,hidden,fan,B", [(2, 256, [25, 10], 512), (3, 256, [5, 4, 3], 128)])
+def test_fast_engine_matches_autograd(rt, L, hidden, fan, B):
     """Hand-scheduled fwd/bwd (engine/fast_sage.py) vs the autograd path on identical samples."""
     import copy
     import torch.nn.functional as F
@@ -425,10 +426,10 @@ def test_fast_engine_matches_autograd(rt):
     from graphlearn_b200.store.synthetic import make_sharded_graph
     nodes, csr = make_sharded_graph(rt, 30000, 600000, 100, 47, seed=7)
     torch.manual_seed(0)
-    m1 = EgoGraphSAGE(100, 256, 47, 2).to(rt.device)
+    m1 = EgoGraphSAGE(100, hidden, 47, L).to(rt.device)
     m2 = copy.deepcopy(m1)
-    tr = FastSageTrainer(rt, nodes, csr, m1, [25, 10], 512, use_cuda_graph=False)
-    seeds = torch.randint(0, 30000, (512,), device=rt.device)
+    tr = FastSageTrainer(rt, nodes, csr, m1, fan, B, use_cuda_graph=False)
+    seeds = torch.randint(0, 30000, (B,), device=rt.device)
     tr.seeds.copy_(seeds)
     hops = tr.sample(seeds)
     tr.sample = lambda s: hops
@@ -438,7 +439,7 @@ def test_fast_engine_matches_autograd(rt):
     torch.cuda.synchronize()
     g_fast = torch.cat([p.grad.reshape(-1) for p in m1.parameters()])
     loss_fast = float(tr.loss)
-    logits = m2.forward_store(nodes, hops, [25, 10])
+    logits = m2.forward_store(nodes, hops, fan)
     labels = nodes.labels.local[seeds]
     loss = F.cross_entropy(logits, labels)
     loss.backward()

@@ -119,3 +119,69 @@ def test_from_query_matches_raw_trainer_bit_for_bit(tsv_graph):
     assert l1 == l2, (l1[:4], l2[:4])
     assert torch.equal(tr1.flat_p, tr2.flat_p)
     assert l1[-1] < l1[1]        # (pipelined step(): entry 0 reports the priming batch) - it learns
+
+
+def test_dgs_kernels_match_cpu_service():
+    """csrc/dgs.cu (one launch per record batch / per query hop) vs the portable torch implementation."""
+    import numpy as np
+    from graphlearn_b200.dgs import DynamicGraphService, QueryPlan
+    schema = {"vertices": {"u": {"count": 500, "feat_dim": 4}, "i": {"count": 800, "feat_dim": 4}},
+              "edges": {"click": {"src": "u", "dst": "i"}, "sim": {"src": "i", "dst": "i"}}}
+    plan = lambda: QueryPlan("u").out("click", 6).out("sim", 3)   # noqa: E731
+    a, b = DynamicGraphService(schema, device="cuda"), DynamicGraphService(schema, device="cpu")
+    a.install_query(1, plan()); b.install_query(1, plan())
+    rs = np.random.RandomState(1)
+    t = 0
+    for it in range(5):
+        for et, ns in (("click", 500), ("sim", 800)):
+            n = 4000
+            src = (rs.zipf(1.4, n) % ns).astype(np.int64)            # hot sources: many records per vertex per batch
+            dst = rs.randint(0, 800, n).astype(np.int64)
+            ts = np.arange(t, t + n); t += n
+            upd = {"edges": {et: {"src": src, "dst": dst, "ts": ts, "weight": rs.rand(n).astype(np.float32)}}}
+            a.apply_updates(upd); b.apply_updates(upd)
+    feat = rs.rand(800, 4).astype(np.float32)
+    for s in (a, b):
+        s.apply_updates({"vertices": {"i": {"id": np.arange(800), "ts": np.zeros(800, dtype=np.int64), "feat": feat}}})
+    q = list(range(0, 500, 3)) + [499, 700000, -5]
+    ra, rb = a.run_query(1, q), b.run_query(1, q)
+    for h in range(2):
+        assert torch.equal(ra["hops"][h]["timestamps"].cpu(), rb["hops"][h]["timestamps"])
+        assert torch.equal(ra["hops"][h]["ids"].cpu(), rb["hops"][h]["ids"])
+        assert torch.allclose(ra["hops"][h]["weights"].cpu(), rb["hops"][h]["weights"])
+    assert torch.equal(a.stores["click"].count.cpu(), b.stores["click"].count)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_knn_fused_kernel_flat_and_ivf(dtype):
+    """csrc/knn.cu: tcgen05 score GEMM + fused running top-k + merge; recall@k = 1.0 vs an fp32 brute force."""
+    import graphlearn_b200 as gl
+    from graphlearn_b200.ops import knn
+    from graphlearn_b200.parallel.runtime import init
+    from graphlearn_b200.store.shards import IdMap, NodeTable
+    rt = init()
+    g = torch.Generator(device=rt.device).manual_seed(5)
+    n, d, B, k = 70001, 100, 300, 10
+    x = torch.randn(n, d, device=rt.device, generator=g)
+    t = NodeTable(rt, "t", IdMap(rt, torch.arange(n, device=rt.device), dense=True))
+    t.set_float(x, dtype)
+    xs = t.feats.local[:, :d].float()
+    q = torch.randn(B, d, device=rt.device, generator=g)
+    for metric in (0, 1):
+        ids, dist = knn.search(rt, t, q, k, metric)
+        sc = q @ xs.t() if metric == 1 else -torch.cdist(q, xs) ** 2
+        ref_s, ref_i = torch.topk(sc, k, dim=1)
+        assert torch.equal(torch.sort(ids, 1).values, torch.sort(ref_i, 1).values), metric       # recall 1.0
+        want = ref_s if metric == 1 else -ref_s
+        assert torch.allclose(dist, want, rtol=1e-3, atol=1e-2)
+    # IVF-flat: probing every list is exact, probing a quarter keeps most of the neighbours
+    opt = gl.IndexOption(); opt.index_type = "ivfflat"; opt.nlist = 64; opt.nprobe = 64
+    knn.build_index(t, opt)
+    ids, _ = knn.search(rt, t, q, k, 0)
+    ref_i = torch.topk(-torch.cdist(q, xs) ** 2, k, dim=1).indices
+    assert torch.equal(torch.sort(ids, 1).values, torch.sort(ref_i, 1).values)
+    opt.nprobe = 16
+    knn.build_index(t, opt)
+    ids, _ = knn.search(rt, t, q[:64], k, 0)
+    hit = (ids[:, :, None] == ref_i[:64, None, :]).any(2).float().mean()
+    assert hit > 0.5, float(hit)
