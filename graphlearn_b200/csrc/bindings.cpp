@@ -73,6 +73,13 @@ at::Tensor relabel_lookup(const at::Tensor&, const at::Tensor&, const at::Tensor
 at::Tensor edge_scatter(const at::Tensor&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&,
                         int64_t, int64_t);
 at::Tensor edge_dot(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, int64_t);
+// gat.cu
+std::vector<at::Tensor> gat_agg_forward(const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, const at::Tensor&,
+                                        const c10::optional<at::Tensor>&, int64_t, int64_t, int64_t, const at::Tensor&, const at::Tensor&,
+                                        const at::Tensor&, double);
+std::vector<at::Tensor> gat_agg_backward(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t, int64_t,
+                                         const at::Tensor&, const at::Tensor&, const at::Tensor&, double, const at::Tensor&, const at::Tensor&,
+                                         const at::Tensor&, bool);
 // idmap.cu
 at::Tensor idmap_translate(const at::Tensor&, const at::Tensor&, bool);
 // knn.cu
@@ -130,6 +137,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("relabel_lookup", &glb::relabel_lookup);
   m.def("edge_scatter", &glb::edge_scatter);
   m.def("edge_dot", &glb::edge_dot);
+  m.def("gat_agg_forward", &glb::gat_agg_forward);
+  m.def("gat_agg_backward", &glb::gat_agg_backward);
   m.def("idmap_translate", &glb::idmap_translate);
   m.def("knn_flat_topk", &glb::knn_flat_topk);
   m.def("knn_merge_peers", &glb::knn_merge_peers);

@@ -44,6 +44,29 @@ class _Tower(nn.Module):
                     h = [F.elu(t) for t in h]
         return h[0].float()
 
+    def forward_store(self, tables, vids, expands):
+        """Same recursion, but layer 0 reads the raw rows of hop i / i+1 from ``tables[i]`` / ``tables[i + 1]`` by vid
+        INSIDE the fused kernels (``vids[i]``: device int64 ids of hop i) - no [M * k, d] feature tensors."""
+        L = self.L
+        last = L == 1
+        if self.conv_kind == "sage":
+            h = [self.convs[0][i].forward_store(tables[i], vids[i].reshape(-1), vids[i + 1].reshape(-1), expands[i], relu=not last,
+                                                nbr_table=tables[i + 1]) for i in range(L)]
+        else:
+            h = [self.convs[0][i].forward_store(tables[i], vids[i].reshape(-1), vids[i + 1].reshape(-1), expands[i],
+                                                nbr_table=tables[i + 1]) for i in range(L)]
+            if not last:
+                h = [F.elu(t) for t in h]
+        for l in range(1, L):
+            last = l == L - 1
+            if self.conv_kind == "sage":
+                h = [self.convs[l][i](h[i], h[i + 1], expands[i], relu=not last) for i in range(L - l)]
+            else:
+                h = [self.convs[l][i](h[i], h[i + 1], expands[i]) for i in range(L - l)]
+                if not last:
+                    h = [F.elu(t) for t in h]
+        return h[0].float()
+
 
 class EgoBipartiteSAGE(nn.Module):
     def __init__(self, user_dim: int, item_dim: int, hidden: int, out: int, hops: int = 2, agg="mean", conv="sage",
@@ -58,6 +81,11 @@ class EgoBipartiteSAGE(nn.Module):
 
     def forward(self, user_ego, item_ego, expands_u, expands_i):
         return self.user_tower(user_ego, expands_u), self.item_tower(item_ego, expands_i)
+
+    def forward_store(self, user_tables, user_vids, item_tables, item_vids, expands_u, expands_i):
+        """Towers fed by (table, vid) pairs: the first layer gathers inside the fused kernels."""
+        return (self.user_tower.forward_store(user_tables, user_vids, expands_u),
+                self.item_tower.forward_store(item_tables, item_vids, expands_i))
 
     @staticmethod
     def loss(u_emb, pos_emb, neg_emb, kind="softmax", temperature=1.0):

@@ -67,35 +67,88 @@ class EgoSAGEConv(nn.Module):
 
 
 class EgoGATConv(nn.Module):
-    """Multi-head attention over a fixed fan-out neighbourhood; heads are AVERAGED like the
-    reference (ego_gat_conv.py:80-117: x'=W_x x, n'=W_n n, score = a.[x'||n'],
-    softmax(leaky_relu) over the k neighbours (self included), weighted sum)."""
+    """Multi-head attention over a fixed fan-out neighbourhood - math and parameters of the reference
+    (ego_gat_conv.py:50-117): per head  x' = W_x x (+b),  n' = W_n n (+b),  e = LeakyReLU(att . [x' || n'] (+b)),
+    coef = softmax over the k NEIGHBOURS, ret = sum_j coef_j n'_j; heads are AVERAGED.  ``W_n`` is ``W_x`` when
+    both sides have the same input dimension (``in_dim`` an int), like the reference; ``use_bias`` (default False,
+    like the reference) adds biases to all three linear maps.
 
-    def __init__(self, in_dim, out_dim, num_head=1, bias=True, attn_drop=0.0, negative_slope=0.2):
+    Execution: the attention logit is linear in the raw rows, so the layer runs as ONE gather + online-softmax
+    kernel that aggregates RAW rows per head (``ops.gat``) followed by ONE tensor-core GEMM with the concatenated
+    ``W_n`` - no [M*k, H*D] projected neighbour tensor."""
+
+    def __init__(self, in_dim, out_dim, num_head=1, use_bias=False, attn_drop=0.0, negative_slope=0.2, bias=None):
         super().__init__()
-        self.in_self = int(in_dim if not isinstance(in_dim, (tuple, list)) else in_dim[0])
-        self.in_nbr = int(in_dim if not isinstance(in_dim, (tuple, list)) else in_dim[1])
+        homo = not isinstance(in_dim, (tuple, list))
+        self.in_self = int(in_dim if homo else in_dim[0])
+        self.in_nbr = int(in_dim if homo else in_dim[1])
         self.out_dim, self.num_head = int(out_dim), int(num_head)
-        self.lin_self = nn.Linear(self.in_self, out_dim * num_head, bias=False)
-        self.lin_nbr = nn.Linear(self.in_nbr, out_dim * num_head, bias=False)
-        self.att_self = nn.Parameter(torch.empty(num_head, out_dim))
-        self.att_nbr = nn.Parameter(torch.empty(num_head, out_dim))
-        self.bias = nn.Parameter(torch.zeros(out_dim)) if bias else None
+        use_bias = bool(use_bias if bias is None else bias)          # `bias=` kept as an alias of use_bias
+        H, D = self.num_head, self.out_dim
+        self.lin_self = nn.Linear(self.in_self, D * H, bias=use_bias)
+        self.lin_nbr = self.lin_self if homo else nn.Linear(self.in_nbr, D * H, bias=use_bias)
+        self.att = nn.Parameter(torch.empty(H, 2 * D))                # [a_x || a_n] per head
+        self.att_bias = nn.Parameter(torch.zeros(H)) if use_bias else None
         self.attn_drop, self.slope = attn_drop, negative_slope
-        nn.init.xavier_uniform_(self.att_self)
-        nn.init.xavier_uniform_(self.att_nbr)
+        nn.init.xavier_uniform_(self.att)
 
-    def forward(self, x, neighbor, expand):
+    # ---- the two equivalent evaluations
+    def _logit_vectors(self):
+        """u_x [H, d_self], u_n [H, d_nbr], c [H] with e = LeakyReLU(u_x . x + u_n . n + c)."""
+        H, D = self.num_head, self.out_dim
+        a_x, a_n = self.att[:, :D], self.att[:, D:]
+        wx = self.lin_self.weight.view(H, D, self.in_self)
+        wn = self.lin_nbr.weight.view(H, D, self.in_nbr)
+        u_x = torch.einsum("hd,hdi->hi", a_x, wx)
+        u_n = torch.einsum("hd,hdi->hi", a_n, wn)
+        c = torch.zeros(H, device=self.att.device)
+        if self.lin_self.bias is not None:
+            c = c + (a_x * self.lin_self.bias.view(H, D)).sum(1)
+        if self.lin_nbr.bias is not None:
+            c = c + (a_n * self.lin_nbr.bias.view(H, D)).sum(1)
+        if self.att_bias is not None:
+            c = c + self.att_bias
+        return u_x, u_n, c
+
+    def forward_reference(self, x, neighbor, expand):
+        """Literal transcription of the reference layer (projects every neighbour row first) - the parity oracle."""
         M, H, D = x.size(0), self.num_head, self.out_dim
         xs = self.lin_self(x.float()).view(M, 1, H, D)
         xn = self.lin_nbr(neighbor.float()).view(M, expand, H, D)
-        xn = torch.cat([xs, xn], 1)                                   # self loop joins the softmax
-        score = (xs * self.att_self).sum(-1) + (xn * self.att_nbr).sum(-1)     # [M, 1+k, H]
-        coef = torch.softmax(F.leaky_relu(score, self.slope), dim=1)
+        a_x, a_n = self.att[:, :D], self.att[:, D:]
+        score = (xs * a_x).sum(-1) + (xn * a_n).sum(-1)                       # [M, k, H]
+        if self.att_bias is not None:
+            score = score + self.att_bias
+        coef = torch.softmax(F.leaky_relu(score, self.slope), dim=1)          # over the k neighbours only
         if self.training and self.attn_drop > 0:
             coef = F.dropout(coef, self.attn_drop)
-        out = (coef.unsqueeze(-1) * xn).sum(1).mean(1)                # average heads
-        return out + self.bias if self.bias is not None else out
+        return (coef.unsqueeze(-1) * xn).sum(1).mean(1)                       # average heads
+
+    def _project(self, agg):
+        """out = mean_h ( W_n,h agg_h + b_n,h ) as one GEMM over the concatenated, kp-padded per-head blocks."""
+        from ..ops.linear import tc_linear
+        H, D = self.num_head, self.out_dim
+        kp = agg.size(1) // H
+        wn = self.lin_nbr.weight.view(H, D, self.in_nbr)
+        wcat = torch.cat([F.pad(wn[h], (0, kp - self.in_nbr)) for h in range(H)], 1) / H          # [D, H * kp]
+        b = self.lin_nbr.bias.view(H, D).mean(0) if self.lin_nbr.bias is not None else None
+        return tc_linear(agg, wcat, b)
+
+    def forward(self, x, neighbor, expand):
+        if self.training and self.attn_drop > 0:
+            return self.forward_reference(x, neighbor, expand)               # dropout on the coefficients: literal path
+        from ..ops import gat as gat_ops
+        u_x, u_n, c = self._logit_vectors()
+        agg = gat_ops.gat_aggregate(u_x, u_n, c, k=expand, slope=self.slope, x_self=x, x_nbr=neighbor)
+        return self._project(agg).float()
+
+    def forward_store(self, table, self_vids, nbr_vids, expand, nbr_table=None):
+        """First layer: rows are pulled from the sharded feature store inside the attention kernel."""
+        from ..ops import gat as gat_ops
+        u_x, u_n, c = self._logit_vectors()
+        agg = gat_ops.gat_aggregate(u_x, u_n, c, k=expand, slope=self.slope, self_table=table, self_vids=self_vids,
+                                    nbr_table=nbr_table or table, nbr_vids=nbr_vids)
+        return self._project(agg).float()
 
 
 class EgoGINConv(nn.Module):

