@@ -35,7 +35,8 @@ def get_cluster_spec(port=None, addr=None, gl_rank=None, world_size=None):
 
 
 def launch_server(graph, cluster=None, task_index=0):
-    """Reference: starts a GL server in a daemon process next to each trainer
-    (nn/pytorch/data/utils.py:112-138).  Here "serving" the graph means having built this rank's
-    shard in HBM, so the call just initialises the graph (idempotent) and returns it."""
-    return graph.init(task_index=task_index, cluster=cluster or "", job_name="server")
+    """Reference: starts a GL server next to each trainer (nn/pytorch/data/utils.py:112-138).  Builds this rank's shard
+    and - when ``cluster`` names server addresses ({"server": "host:port,...", "client_count": C}) - starts a
+    ``service.GraphServer`` on this task's address (daemon threads; ``graph.wait_for_close()`` blocks until every client
+    has stopped).  Without a cluster spec the call only initialises the graph (worker mode)."""
+    return graph.init(task_index=task_index, cluster=cluster or "", job_name="server" if cluster else "")

@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_flat_kernel(const __grid_c
     const int per_slab = kKnnSlab * chunks_row;
     for (int s = 0; s < n_slabs; ++s) {
       const int b = s & 1;
-      umma::mbar_wait(x_free + b, (uint32_t)(((s >> 1) & 1) ^ 1));
+      umma::mbar_wait(x_free + b, (uint32_t)(((s >> 1) & 1) ^ 1));     // the MMA has consumed the operand tile
+      umma::mbar_wait(t_free + b, (uint32_t)(((s >> 1) & 1) ^ 1));     // the top-k warps have consumed the norm slice
       const int64_t base = r_begin + (int64_t)s * kKnnSlab;
       uint8_t* dst = sX + (size_t)b * tile_bytes;
       for (int i = pt; i < per_slab; i += kKnnProdWarps * 32) {

@@ -71,7 +71,8 @@ struct SageParams {
   SageSeg seg[kMaxSegs];
   int nseg, total_tiles;
   const void* w_img;          // bf16 image, (K_total/64) blocks of [N x 64] SW128
-  const float* bias;          // [n_out] or null
+  const float* bias;          // [bias_len] or null
+  int bias_len;
   int64_t out_stride;         // elements
   int kp_self, kp_nbr;        // padded K of each half, in {0,64,128,256,512}
   int mode;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
   }
   const int img = (int)blockIdx.x % p.n_imgs;
   // (multi-image launches: image `img` owns the output columns [img * N, img * N + N) and the matching bias slice)
-  if (tid < 256) sBias[tid] = (p.bias && tid < p.n_out) ? __ldg(p.bias + img * p.N + tid) : 0.f;
+  if (tid < 256) sBias[tid] = (p.bias && tid < p.n_out && img * p.N + tid < p.bias_len) ? __ldg(p.bias + img * p.N + tid) : 0.f;
   if (warp == kMmaWarp) {
     umma::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     umma::tmem_relinquish();
@@ -770,8 +771,9 @@ void sage_fused_multi(const at::Tensor& tself_desc, const at::Tensor& tnbr_desc,
   at::Tensor b;
   if (bias.has_value() && bias->defined()) {
     b = bias->contiguous();
-    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.numel() >= n_out * std::max<int64_t>(n_imgs, 1), "bias must be fp32 [>= n_out]");
+    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && (n_imgs > 1 || b.numel() >= n_out), "bias must be fp32 [>= n_out]");
     p.bias = b.data_ptr<float>();
+    p.bias_len = (int)b.numel();
   }
   p.out_stride = -1;
   for (int s = 0; s < nseg; ++s) {

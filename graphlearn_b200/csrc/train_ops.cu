@@ -24,9 +24,9 @@ namespace glb {
 // (seed nodes are owned by this rank), else labels_table[r].  loss_accum / dbias must be zeroed by
 // the caller (they live in the flat gradient storage that is memset once per step).
 __global__ void __launch_bounds__(256)
-softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels_table,
+softmax_ce_kernel(const float* __restrict__ logits, int ld_logits, const int64_t* __restrict__ labels_table,
                   const int64_t* __restrict__ seeds, int world, int B, int C, float* __restrict__ loss_accum,
-                  __nv_bfloat16* __restrict__ dlogits, float* __restrict__ dbias /* [C], accumulated */) {
+                  __nv_bfloat16* __restrict__ dlogits, int ld_dl, float* __restrict__ dbias /* [C], accumulated */) {
   extern __shared__ float colsum[];      // [C]
   for (int c = threadIdx.x; c < C; c += blockDim.x) colsum[c] = 0.f;
   __syncthreads();
@@ -34,7 +34,7 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const float invB = 1.f / (float)B;
   if (r < B) {
-    const float* row = logits + (size_t)r * C;
+    const float* row = logits + (size_t)r * ld_logits;
     float mx = -FLT_MAX;
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -46,7 +46,7 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
     const float inv = 1.f / se;
     for (int c = lane; c < C; c += 32) {
       float g = valid ? (__expf(row[c] - mx) * inv - (c == y ? 1.f : 0.f)) * invB : 0.f;
-      dlogits[(size_t)r * C + c] = __float2bfloat16(g);
+      dlogits[(size_t)r * ld_dl + c] = __float2bfloat16(g);
       if (dbias) atomicAdd(&colsum[c], g);
     }
     if (lane == 0 && valid) atomicAdd(loss_accum, (mx + __logf(se) - row[y]) * invB);
@@ -179,9 +179,10 @@ sage_bwd_input_v8_kernel(const __nv_bfloat16* __restrict__ dA_self, const __nv_b
 void softmax_ce(const at::Tensor& logits, const at::Tensor& labels_table, const c10::optional<at::Tensor>& seeds,
                 int64_t world, const at::Tensor& loss_accum, const at::Tensor& dlogits,
                 const c10::optional<at::Tensor>& dbias) {
-  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.is_contiguous());
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.stride(1) == 1);
   TORCH_CHECK(labels_table.is_cuda() && labels_table.scalar_type() == at::kLong);
-  TORCH_CHECK(dlogits.scalar_type() == at::kBFloat16 && dlogits.is_contiguous() && dlogits.numel() == logits.numel());
+  TORCH_CHECK(dlogits.scalar_type() == at::kBFloat16 && dlogits.dim() == 2 && dlogits.stride(1) == 1 && dlogits.size(0) == logits.size(0) &&
+              dlogits.size(1) == logits.size(1), "dlogits must be bf16 [B, C] (rows may be padded)");
   TORCH_CHECK(loss_accum.scalar_type() == at::kFloat && loss_accum.numel() >= 1);
   c10::cuda::CUDAGuard guard(logits.device());
   int B = (int)logits.size(0), C = (int)logits.size(1);
@@ -192,8 +193,8 @@ void softmax_ce(const at::Tensor& logits, const at::Tensor& labels_table, const 
   if (dbias.has_value()) { TORCH_CHECK(dbias->scalar_type() == at::kFloat && dbias->numel() >= C); db = dbias->data_ptr<float>(); }
   int blocks = (B * 32 + 255) / 256;
   softmax_ce_kernel<<<blocks, 256, (size_t)C * sizeof(float), at::cuda::getCurrentCUDAStream()>>>(
-      logits.data_ptr<float>(), labels_table.data_ptr<int64_t>(), sp, (int)world, B, C, loss_accum.data_ptr<float>(),
-      reinterpret_cast<__nv_bfloat16*>(dlogits.data_ptr()), db);
+      logits.data_ptr<float>(), (int)logits.stride(0), labels_table.data_ptr<int64_t>(), sp, (int)world, B, C, loss_accum.data_ptr<float>(),
+      reinterpret_cast<__nv_bfloat16*>(dlogits.data_ptr()), (int)dlogits.stride(0), db);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

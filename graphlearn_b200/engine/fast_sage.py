@@ -71,18 +71,23 @@ class FastSageTrainer:
         convs = list(model.convs)
         self.convs = convs
         self.n_split: List[int] = []           # forward images per layer (N-split when W does not fit next to the A tiles)
+        self.n_img: List[int] = []             # padded output columns per image
         for c in convs:
             assert c.agg_type in ("mean", "sum"), "fast engine supports mean / sum aggregation"
-            kt, N = c.weight_p.size(1), sage_ops.pad_n(c.out_dim)
-            ns = 1
-            while not sage_ops.smem_fits(kt, N // ns) and (N // ns) % 64 == 0 and ns < 8:
-                ns *= 2
-            assert sage_ops.smem_fits(kt, N // ns) and (ns == 1 or N == c.out_dim), "layer does not fit the fused kernel"
-            assert sage_ops.fused_supported(c.in_self, c.in_nbr, min(c.out_dim, N // ns), c.agg_type, max(self.fanouts))
+            kt = c.weight_p.size(1)
+            ns, n_img = 1, sage_ops.pad_n(c.out_dim)
+            while not sage_ops.smem_fits(kt, n_img) and ns < 8:          # fewest images whose W slice fits next to the A tiles
+                ns += 1
+                n_img = (-(-c.out_dim // ns) + 31) // 32 * 32
+            is_top = c is convs[-1]
+            assert sage_ops.smem_fits(kt, n_img) and (ns == 1 or is_top or ns * n_img == c.out_dim), "layer does not fit the fused kernel"
+            assert sage_ops.fused_supported(c.in_self, c.in_nbr, min(c.out_dim, n_img), c.agg_type, max(self.fanouts))
             self.n_split.append(ns)
+            self.n_img.append(n_img)
         # per layer l (1-based): segments i = 0..L-l, rows concatenated
         self.seg_off: List[List[int]] = []
         self.H: List[Optional[torch.Tensor]] = []      # layer outputs (bf16; last layer fp32 logits)
+        self.Hp: List[torch.Tensor] = []               # ... with the rows padded to the image columns
         self.A: List[torch.Tensor] = []                # saved [self || agg] tiles (bf16)
         self.dZ: List[torch.Tensor] = []
         self.dZp: List[torch.Tensor] = []              # dZ with the row padded to the K padding of the dA GEMM
@@ -97,8 +102,9 @@ class FastSageTrainer:
             self.seg_off.append(offs)
             last = l == self.L
             kt = c.weight_p.size(1)
-            hw = sage_ops.pad_n(c.out_dim) if last else c.out_dim      # padded logits rows: vectorised epilogue stores
-            self.H.append(torch.zeros(rows, hw, dtype=torch.float32 if last else torch.bfloat16, device=dev)[:, :c.out_dim])
+            hw = self.n_split[l - 1] * self.n_img[l - 1] if last else c.out_dim      # padded logits rows (all images)
+            self.Hp.append(torch.zeros(rows, hw, dtype=torch.float32 if last else torch.bfloat16, device=dev))
+            self.H.append(self.Hp[-1][:, :c.out_dim])
             self.A.append(torch.zeros(rows, kt, dtype=torch.bfloat16, device=dev))
             self.dZp.append(torch.zeros(rows, sage_ops.pad_k(c.out_dim), dtype=torch.bfloat16, device=dev))
             self.dZ.append(self.dZp[-1][:, :c.out_dim])
@@ -110,11 +116,11 @@ class FastSageTrainer:
         for l in range(1, self.L + 1):
             c = convs[l - 1]
             n_out, kt = c.weight_p.shape
-            N = sage_ops.pad_n(n_out)
+            N = self.n_split[l - 1] * self.n_img[l - 1]
             self.img.append(torch.zeros(kt * N, dtype=torch.bfloat16, device=dev))
             kpad = self.dZp[l - 1].size(1)
             self.img_t.append(torch.zeros((kt + 255) // 256, kpad * 256, dtype=torch.bfloat16, device=dev) if l > 1 else None)
-            mats.append([model._glb_param_offsets[id(c.weight_p)], n_out, kt, N // self.n_split[l - 1], self.img[-1].data_ptr(),
+            mats.append([model._glb_param_offsets[id(c.weight_p)], n_out, kt, self.n_img[l - 1], self.img[-1].data_ptr(),
                          self.img_t[-1].data_ptr() if l > 1 else 0, kpad, 256])
         self._mats = torch.tensor(mats, dtype=torch.int64)
         self.loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -278,17 +284,19 @@ class FastSageTrainer:
             c = self.convs[l - 1]
             last = l == L
             ns = self.n_split[l - 1]
-            N = sage_ops.pad_n(c.out_dim) // ns
+            N = self.n_img[l - 1]
             n_out = c.out_dim if ns == 1 else N
             img = self.img[l - 1]
+            fuse_ce = last and ns == 1 and N <= 64
             offs = self.seg_off[l - 1]
             mode = sage_ops.MODE[c.agg_type]
             nseg = L - l + 1
-            outs = [self.H[l - 1][offs[i]:offs[i + 1], :n_out] for i in range(nseg)]
+            hb = self.H[l - 1] if ns == 1 else self.Hp[l - 1]
+            outs = [hb[offs[i]:offs[i + 1], :n_out] for i in range(nseg)]
             asv = [self.A[l - 1][offs[i]:offs[i + 1]] for i in range(nseg)]
             Ms, ks = [self.n[i] for i in range(nseg)], [self.fanouts[i] for i in range(nseg)]
             ce = []
-            if last:
+            if fuse_ce:
                 ce = [self.nodes.labels.local, seeds, self.loss, self.dZ[L - 1],
                       top.bias.grad if top.bias is not None else None]
             if l == 1:
@@ -302,6 +310,10 @@ class FastSageTrainer:
                 C.sage_fused_multi(d, d, [None] * nseg, [None] * nseg, [po[i] for i in range(nseg)],
                                    [po[i + 1] for i in range(nseg)], Ms, ks, outs, asv, mode, img, c.bias, N,
                                    n_out, not last, not last, 0, ce, self.rt.world, ns)
+            if last and not fuse_ce:
+                # wide / split top layer: the loss runs as its own kernel on the (padded) logits
+                C.softmax_ce(self.H[L - 1], self.nodes.labels.local, seeds, self.rt.world, self.loss, self.dZ[L - 1],
+                             top.bias.grad if top.bias is not None else None)
         if self._post_loss_hook is not None:
             self._post_loss_hook()          # e2e graph capture: fork the loss D2H here, parallel to the backward
         # ---- backward: all GEMMs on tcgen05 (csrc/sage_bwd.cu), no library kernels
@@ -374,11 +386,14 @@ class FastSageTrainer:
         external modification of the parameters)."""
         for l in range(1, self.L + 1):
             c = self.convs[l - 1]
-            ns = self.n_split[l - 1]
-            N = sage_ops.pad_n(c.out_dim) // ns
+            ns, N = self.n_split[l - 1], self.n_img[l - 1]
             w = c.weight_p.detach().contiguous()
-            self.img[l - 1].copy_(torch.cat([self.C.pack_weight_f32(w[i * N:(i + 1) * N].contiguous(), N, False)[0]
-                                             for i in range(ns)]) if ns > 1 else self.C.pack_weight_f32(w, N, False)[0])
+            if ns > 1:
+                wpad = torch.zeros(ns * N, w.size(1), device=w.device)
+                wpad[:w.size(0)] = w
+                self.img[l - 1].copy_(torch.cat([self.C.pack_weight_f32(wpad[i * N:(i + 1) * N].contiguous(), N, False)[0] for i in range(ns)]))
+            else:
+                self.img[l - 1].copy_(self.C.pack_weight_f32(w, N, False)[0])
             if l > 1:
                 self.img_t[l - 1].copy_(self.C.pack_weight_t(c.weight_p.detach().contiguous(), self.dZp[l - 1].size(1), 256))
 

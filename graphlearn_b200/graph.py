@@ -137,6 +137,25 @@ class Graph(object):
         are accepted for script compatibility; the rank/world come from torchrun env vars."""
         if self._inited:
             return self
+        # ---- server mode (graph.py:452-494 of the reference): cluster = {"server": "h:p,h:p", "client_count": C}
+        spec = None
+        if cluster:
+            import json as _json
+            spec = _json.loads(cluster) if isinstance(cluster, str) else dict(cluster)
+        self._remote = None
+        self._server = None
+        if spec and job_name == "client":
+            from .service import RemoteGraphClient
+            self._remote = RemoteGraphClient(spec["server"], client_id=int(task_index), client_count=int(spec.get("client_count", 1)))
+            meta = self._remote.meta
+            self._node_decoders, self._edge_decoders = dict(meta["node_decoders"]), dict(meta["edge_decoders"])
+            self._topology = Topology()
+            for et, (st, dt) in meta["edges"].items():
+                self._topology.add(et, st, dt)
+            self._undirected_edges = list(meta["undirected"])
+            self._remote_node_types = set(meta["node_types"])
+            self._inited = True
+            return self
         self._rt = _rt.init(device=device)
         self._store = GraphStore(self._rt)
         self._store.node_decoders = self._node_decoders
@@ -149,9 +168,25 @@ class Graph(object):
             self._store.build_feature_caches(cap)
         self._topology = self._store.topology
         self._inited = True
+        if spec and job_name == "server":
+            from .service import GraphServer
+            from .service.client import _parse
+            addrs = [a for a in str(spec["server"]).split(",") if a]
+            self._server = GraphServer(self, address=_parse(addrs[int(task_index) % len(addrs)]),
+                                       client_count=int(spec.get("client_count", 1))).start()
         return self
 
+    @property
+    def remote(self) -> bool:
+        """True for a server-mode CLIENT handle (no local graph; queries run on the servers)."""
+        return getattr(self, "_remote", None) is not None
+
     def close(self):
+        if self.remote:
+            self._remote.stop()
+            self._remote = None
+            self._inited = False
+            return
         for ds in self._datasets:
             try:
                 ds.close()
@@ -160,7 +195,11 @@ class Graph(object):
         self._inited = False
 
     def wait_for_close(self):
-        """Server-mode blocking call of the reference; SPMD ranks simply synchronise."""
+        """Server role: serve until every client has stopped (server_impl / fs_coordinator stop protocol); SPMD worker
+        ranks simply synchronise."""
+        if getattr(self, "_server", None) is not None:
+            self._server.wait_for_close()
+            self._server = None
         if self._rt is not None:
             self._rt.barrier()
 
@@ -385,7 +424,7 @@ class Graph(object):
         dag = Dag(self)
         if node_from == NODE:
             node_type = get_mask_type(t, mask)
-            if node_type not in self._store.nodes:
+            if node_type not in (self._remote_node_types if self.remote else self._store.nodes):
                 raise ValueError("node type %r not in graph" % (node_type,))
             params = {"node_from": NODE, "node_type": node_type}
             out_type = node_type

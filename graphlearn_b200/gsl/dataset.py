@@ -27,6 +27,12 @@ class DagValues(dict):
 
 
 class Dataset(object):
+    def __new__(cls, dag, *args, **kwargs):
+        if getattr(dag.graph, "remote", False):             # server-mode client: the query runs on the graph servers
+            from ..service import RemoteDataset
+            return RemoteDataset(dag.graph, dag, kwargs.get("window", args[0] if args else 10))
+        return super().__new__(cls)
+
     def __init__(self, dag, window=10, keep_alive_rounds=1, drop_last=False, prefetch=True, sync_epoch=None):
         """``sync_epoch``: end the epoch on every rank as soon as one rank runs out of seeds (None = automatic: on
         for multi-rank runs whose sampling ops are collectives, i.e. the portable path)."""

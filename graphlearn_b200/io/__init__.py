@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from ..store.graph_store import Source, _expand_paths as expand_paths, _load_source
 from ..utils.checkpoint import save_embeddings  # noqa: F401
+from .filesystem import FileSystem, get_file_system, register_file_system  # noqa: F401
 
 
 def read_table(path: str, decoder, kind: str = "node", part_index: int = 0, part_count: int = 1) -> dict:
@@ -19,4 +20,4 @@ def read_table(path: str, decoder, kind: str = "node", part_index: int = 0, part
     return _load_source(Source(kind, path, types, decoder), part_index, part_count)
 
 
-__all__ = ["read_table", "expand_paths", "save_embeddings"]
+__all__ = ["read_table", "expand_paths", "save_embeddings", "FileSystem", "get_file_system", "register_file_system"]

@@ -86,15 +86,9 @@ class Source(object):
 
 
 def _expand_paths(path: str) -> List[str]:
-    out = []
-    for p in [x.strip() for x in path.split(",") if x.strip()]:
-        if p.startswith("file://"):
-            p = p[len("file://"):]
-        if os.path.isdir(p):
-            out.extend(sorted(os.path.join(p, f) for f in os.listdir(p) if not f.startswith(".")))
-        else:
-            out.append(p)
-    return out
+    """comma list / directory / URL -> LOCAL file paths (remote objects are spooled, io/filesystem.py)"""
+    from ..io import filesystem as _fs
+    return [_fs.localize(p) for p in _fs.expand(path)]
 
 
 def _loader_threads(ranks_on_box: int) -> int:

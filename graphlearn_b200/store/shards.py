@@ -261,6 +261,31 @@ class NodeTable:
                                                  cache=(rt.rank, cmap.data_ptr(), rows.data_ptr()))
         return C
 
+    # ---- LFU policy (reference: cache_policy.h:37-78 LFU over node ids, remote_node_storage.cc:55-82)
+    # A device kernel cannot keep per-access LFU lists, but the engine knows every row it is about to read: the sampled
+    # hop ids.  ``observe_access`` adds them to a per-vid frequency table (one histogram kernel over ids that are already
+    # on the device), ``refresh_feature_cache_lfu`` re-selects the ``capacity`` most frequently read REMOTE rows and
+    # rebuilds the replica - i.e. LFU with batched (epoch / every-N-steps) eviction instead of per-access eviction.
+    def observe_access(self, vids: torch.Tensor):
+        W = self.rt.world
+        max_vid = max(int(n) for n in self.nrows) * W
+        if getattr(self, "_lfu_freq", None) is None or self._lfu_freq.numel() != max_vid:
+            self._lfu_freq = torch.zeros(max_vid, dtype=torch.float32, device=self.rt.device)
+        v = vids.reshape(-1)
+        v = v[(v >= 0) & (v < max_vid)]
+        if v.numel():
+            self._lfu_freq.index_add_(0, v, torch.ones(v.numel(), dtype=torch.float32, device=v.device))
+
+    def refresh_feature_cache_lfu(self, capacity: int, decay: float = 0.5) -> int:
+        """Rebuild the replica cache from the access frequencies seen so far (collective); old counts decay so the
+        policy follows a drifting workload."""
+        freq = getattr(self, "_lfu_freq", None)
+        self.drop_feature_cache()
+        n = self.build_feature_cache(capacity, scores=freq)
+        if freq is not None:
+            freq.mul_(decay)
+        return n
+
     def drop_feature_cache(self):
         st = self.feats
         if st is None or (getattr(st, "cache_map", None) is None and getattr(st, "replicas", None) is None):

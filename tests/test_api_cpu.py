@@ -470,3 +470,90 @@ def test_dgs_install_wider_query_after_growth():
     # hostile ids are dropped instead of wrapping / exploding the tables
     svc.apply_updates({"edges": {"buy": {"src": [-1, 1 << 40], "dst": [0, 0], "ts": [7, 8]}}})
     assert svc.stores["buy"].n < (1 << 20)
+
+
+def test_registered_file_system_sources(tmp_path):
+    """N9: a custom scheme (here an in-memory 'odps://'-like store) loads through the same Graph API."""
+    import io as _io
+    import numpy as np
+    import graphlearn_b200 as gl
+    from graphlearn_b200.io import FileSystem, register_file_system
+
+    blobs = {"/t/node.tsv": b"id:int64\tfeature:string\n" + b"".join(b"%d\t%d.5:1.0\n" % (i, i) for i in range(10)),
+             "/t/edges/part-0": b"src_id:int64\tdst_id:int64\n" + b"".join(b"%d\t%d\n" % (i, (i + 1) % 10) for i in range(0, 10, 2)),
+             "/t/edges/part-1": b"src_id:int64\tdst_id:int64\n" + b"".join(b"%d\t%d\n" % (i, (i + 1) % 10) for i in range(1, 10, 2))}
+
+    class MemFs(FileSystem):
+        def _p(self, path):
+            return path.split("://", 1)[1][len("bucket"):]
+
+        def isdir(self, path):
+            return self._p(path).rstrip("/") == "/t/edges"
+
+        def listdir(self, path):
+            return sorted("mem://bucket" + k for k in blobs if k.startswith("/t/edges/"))
+
+        def open(self, path):
+            return _io.BytesIO(blobs[self._p(path)])
+
+    register_file_system("mem", MemFs())
+    import os
+    os.environ["GLB_SPOOL_DIR"] = str(tmp_path)
+    g = gl.Graph().node("mem://bucket/t/node.tsv", "n", decoder=gl.Decoder(attr_types=["float", "float"])) \
+        .edge("mem://bucket/t/edges", ("n", "n", "e"), decoder=gl.Decoder()).init(device="cpu")
+    assert g.get_stats()["n"] == [10] and g.get_stats()["e"] == [10]
+    nb = g.neighbor_sampler("e", expand_factor=1, strategy="random").get(np.arange(10)).layer_nodes(1).ids.reshape(-1)
+    assert (nb == (np.arange(10) + 1) % 10).all()
+    import pytest
+    with pytest.raises(gl.UnimplementedError):
+        gl.Graph().node("odps://project/table", "n", decoder=gl.Decoder()).init(device="cpu")
+
+
+def test_server_mode_clients_drive_queries_on_a_server(tmp_path):
+    """Client <-> server decoupling: the server process holds the graph, two clients (no graph, no store) ship GSL
+    queries as DagDefs and pull whole batches with attributes; epochs end with OutOfRangeError; stop protocol."""
+    import socket
+    import threading
+    import numpy as np
+    fixtures = fx
+    import graphlearn_b200 as gl
+    d = fixtures.write_graph(str(tmp_path))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cluster = {"server": "127.0.0.1:%d" % port, "client_count": 2}
+    gs = gl.Graph()
+    gs.node(d + "/user.tsv", "user", decoder=gl.Decoder(weighted=True, labeled=True, attr_types=["int", "int", "string", "float"]))
+    gs.node(d + "/item.tsv", "item", decoder=gl.Decoder(attr_types=["float"] * 4))
+    gs.edge(d + "/u2i.tsv", ("user", "item", "buy"), decoder=gl.Decoder(weighted=True))
+    gs.init(cluster=cluster, job_name="server", task_index=0, device="cpu")
+    served = threading.Thread(target=gs.wait_for_close, daemon=True)
+    served.start()
+    results = {}
+
+    def client(cid):
+        g = gl.Graph().init(cluster=cluster, job_name="client", task_index=cid)
+        assert g.remote
+        q = g.V("user").batch(16).alias("u").outV("buy").sample(3).by("topk").alias("i").values()
+        ds = gl.Dataset(q, window=2)
+        seen, feats = [], None
+        while True:
+            try:
+                v = ds.next()
+            except gl.OutOfRangeError:
+                break
+            seen.append(v["u"].ids)
+            assert v["i"].ids.shape == (len(v["u"].ids), 3) and v["i"].float_attrs.shape == (len(v["u"].ids), 3, 4)
+            assert v["u"].labels.shape == v["u"].ids.shape
+            feats = (v["i"].ids, v["i"].float_attrs)
+        results[cid] = (np.concatenate(seen), feats)
+        g.close()
+
+    ts = [threading.Thread(target=client, args=(c,)) for c in range(2)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    served.join(30)
+    assert not served.is_alive(), "server did not shut down after both clients stopped"
+    for cid in range(2):
+        ids, (iid, fa) = results[cid]
+        assert sorted(ids.tolist()) == list(range(fixtures.N_USER))           # every client traverses the server's users once
+        ok = iid >= 0
+        assert np.allclose(fa[..., 1][ok], iid[ok] + 0.25)                      # item_float(i, 1) = i + 0.25
