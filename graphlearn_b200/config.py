@@ -164,6 +164,8 @@ def set_default_attribute(int_value=None, float_value=None, string_value=None):
 
 
 def enable_actor():
-    """The reference switches to its hiactor runtime (graphlearn/src/service/server.cc:52-60).
-    On B200 the SM grid is the sharded executor; the flag is recorded only."""
+    """The reference switches to its hiactor runtime (graphlearn/src/service/server.cc:52-60): per-core sharded stores
+    + (data-size aware) tape dispatch.  On B200 the SM grid is the sharded executor; what the flag turns on is the
+    balanced batch dispatch of engine/dispatch.py: multi-rank GSL root traversals pool their seed batches every epoch
+    and hand every rank the same number of batches with balanced first-hop work."""
     _CFG.actor_enabled = True

@@ -146,9 +146,12 @@ class QueryExecutor(object):
         if p.get("node_from", NODE) == NODE:
             tab = self.store.nodes[node.type]
             self._ensure_root_iter()
-            idx = self._iter.next_index()
-            rows = self._rows[idx]
-            vids = rows * W + r
+            if _config.get().actor_enabled and W > 1 and strategy in ("shuffle", "by_order"):
+                vids = self._next_dispatched(node, bs, strategy)       # gl.enable_actor(): balanced batch dispatch
+            else:
+                idx = self._iter.next_index()
+                rows = self._rows[idx]
+                vids = rows * W + r
             ids = tab.idmap.to_id(vids) if not tab.idmap.dense else vids
             # vids must live in the BASE table (edges index the unmasked node type)
             base = node._base_type
@@ -180,6 +183,35 @@ class QueryExecutor(object):
         out = _Out(ids=ids, vids=vids, shape=(int(ids.numel()),))
         out.value = V_.Nodes(ids, t, shape=out.shape, graph=self.g, vids=vids)
         return out
+
+    def _next_dispatched(self, node: DagNode, bs: int, strategy: str) -> torch.Tensor:
+        """Root batches under ``gl.enable_actor()``: every epoch the ranks pool their seed batches and a data-size
+        aware plan (engine/dispatch.py; reference: actor/runner/tape_dispatcher.cc:61-175) hands every rank the same
+        number of batches with balanced first-hop work.  Collective at epoch boundaries only."""
+        from ..engine.dispatch import BalancedSeedDispatcher
+        W, r, dev = self.rt.world, self.rt.rank, self.rt.device
+        if getattr(self, "_planned", None) is None:
+            rows = self._rows
+            if strategy == "shuffle":
+                g = torch.Generator(device="cpu").manual_seed(_config.get().seed * 7919 + 31 * r + self._iter.epoch)
+                rows = rows[torch.randperm(int(rows.numel()), generator=g).to(dev)]
+            vids = rows * W + r
+            weights = None
+            for d in node.downstreams:                     # work estimate: out-degree along the first sampled edge type
+                et = d.params.get("edge_type")
+                tab = self.store.nodes[node.type]
+                if et in tab.out_degrees:
+                    weights = tab.out_degrees[et][rows].float() + 1.0
+                    break
+            self._planned = BalancedSeedDispatcher(self.rt, bs).plan(vids, weights)
+            self._plan_iter = SeedIterator(int(self._planned.numel()), bs, "by_order", dev)
+        try:
+            idx = self._plan_iter.next_index()
+        except errors.OutOfRangeError:
+            self._planned = None
+            self._iter.epoch += 1
+            raise
+        return self._planned[idx]
 
     def _root_edges(self, node: DagNode) -> _Out:
         p = node.params

@@ -125,6 +125,25 @@ def main():
             assert sum(t.size(0) for t in feats.replicas) == got["item"]
         else:
             assert int((cm >= 0).sum()) == got["item"] and all(int(v) % W != r for v in torch.nonzero(cm >= 0).flatten())
+    # actor-engine capability: balanced batch dispatch (gl.enable_actor) - every rank gets the same number of batches,
+    # together they cover whole global rounds of the pooled seed batches, labels / attributes still resolve (remote rows)
+    gl.enable_actor()
+    dsb = gl.Dataset(g.V("item").batch(4).shuffle(traverse=True).alias("s").outV("sim").sample(2).by("random").alias("n").values())
+    mine_b = []
+    while True:
+        try:
+            v = dsb.next()
+        except gl.OutOfRangeError:
+            break
+        assert v["n"].ids.shape == (4, 2) and v["s"].float_attrs.shape == (4, 4)
+        assert np.allclose(v["s"].float_attrs[:, 0], v["s"].ids.astype(np.float32))          # item_float(i, 0) == i
+        mine_b.append(v["s"].ids.copy())
+    counts_b = rt.all_gather_object(len(mine_b))
+    allb = np.concatenate([np.concatenate(x) if x else np.zeros(0, np.int64) for x in rt.all_gather_object(mine_b)])
+    assert len(set(counts_b)) == 1 and counts_b[0] >= 1, counts_b
+    assert len(set(allb.tolist())) == len(allb) and set(allb.tolist()) <= set(range(fx.N_ITEM))
+    per_rank = [len([i for i in range(fx.N_ITEM) if i % W == q]) // 4 for q in range(W)]
+    assert len(allb) == (sum(per_rank) // W) * W * 4, (len(allb), per_rank)
     rt.barrier()
     if r == 0:
         print("DIST_API_OK world=%d device=%s" % (W, rt.device))
