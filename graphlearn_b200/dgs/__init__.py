@@ -21,13 +21,19 @@ state in HBM tables:
 * ``CheckpointManager`` / ``BarrierMonitor``   coordinator duties (coordinator.py)
 * ``PartitionedGraphService``  vid-hash partitioned stores (one per GPU) with per-hop routing (partitioned.py)
 
-Kafka, RocksDB, the Java client and the Helm chart are deployment glue around this core and are out
-of scope; ``apply_updates`` takes record batches (dict of arrays) directly.
+* ``StreamingCluster``  the reference's decoupled deployment: P sampling workers (ingest partitions, sample stores,
+                      subscription tables) x S serving workers (k-hop row caches fed by published samples) over
+                      ``LogChannel`` topics (workers.py), driven by ``Coordinator`` (worker registry, barriers,
+                      consistent cluster checkpoints)
+
+The Java client and the Helm chart are deployment glue around this core and are out of scope; record batches are
+dicts of arrays (``LogChannel`` persists them as torch segments instead of Kafka/FlatBuffers).
 """
-from .coordinator import BarrierMonitor, CheckpointManager  # noqa: F401
+from .coordinator import BarrierMonitor, CheckpointManager, Coordinator, WorkerRegistry  # noqa: F401
 from .file_loader import FileLoader, RecordBatchBuilder  # noqa: F401
 from .http_server import HttpFrontEnd  # noqa: F401
 from .partitioned import PartitionedGraphService, Partitioner  # noqa: F401
 from .plan import PlanNode, QueryPlan  # noqa: F401
 from .schema import Options, Schema  # noqa: F401
+from .workers import LogChannel, SamplingWorker, ServingWorker, StreamingCluster, SubscriptionTable  # noqa: F401
 from .service import AdaptiveRateLimiter, DynamicGraphService, SampleStore  # noqa: F401

@@ -181,3 +181,83 @@ def test_sample_ttl_and_adaptive_ingest(tmp_path):
     assert fl.load(str(tmp_path / "data"), svc, adaptive=True) == 500
     assert svc.limiter.concurrency < svc.limiter.max_c and fl.batch_size == 64
     assert svc.run_query(0, [3])["hops"][0]["timestamps"][0, 0].item() == 100 + 499 - (499 - 3) % 8
+
+
+def test_streaming_cluster_subscriptions_match_single_store(tmp_path):
+    """D5/D7/D8/D9/D12: sampling workers publish only subscribed rows, serving workers answer from local caches exactly
+    like the monolithic store - also for vertices that become reachable late (rule back-fill) - and a coordinator
+    checkpoint + channel replay restores the whole pipeline."""
+    from graphlearn_b200.dgs import Coordinator, PlanNode, StreamingCluster
+    schema = {"vertices": {"u": {"count": 16, "feat_dim": 0}, "i": {"count": 16, "feat_dim": 3}},
+              "edges": {"click": {"src": "u", "dst": "i"}, "sim": {"src": "i", "dst": "i"}}}
+    plan = QueryPlan("u").out("click", 3).out("sim", 2)
+    plan.add(PlanNode(3, "VERTEX_SAMPLER", vtype="i", parent=1))          # features of the 1-hop items
+    one = DynamicGraphService(schema, device="cpu")
+    one.install_query(0, plan)
+    cl = StreamingCluster(schema, num_sampling=3, num_serving=2, sampling_devices=["cpu"] * 3, serving_devices=["cpu"] * 2,
+                          log_dir=str(tmp_path / "logs"))
+    cl.install_query(plan)
+    co = Coordinator(cl, meta_dir=str(tmp_path / "meta"))
+    info = co.register_worker("sampling", 0, "127.0.0.1:1")
+    assert info["num_serving"] == 2 and info["query_plan"]["source"] == "u" and not co.ready()
+    for k, n in (("sampling", 3), ("serving", 2)):
+        for w in range(n):
+            co.register_worker(k, w); co.report_started(k, w)
+    assert co.ready() and co.sampling.all_registered()
+    co.register_worker("sampling", 1)                                     # a restart resets the dependent group
+    assert not co.sampling.all_registered() and co.serving.all_started()
+
+    rs = np.random.RandomState(3)
+    t = 0
+
+    def batch(n=120):
+        nonlocal t
+        b = {"edges": {"sim": {"src": rs.randint(0, 50, n), "dst": rs.randint(0, 50, n), "ts": np.arange(t, t + n),
+                               "weight": rs.rand(n).astype(np.float32)},
+                       "click": {"src": rs.randint(0, 40, n), "dst": rs.randint(0, 50, n), "ts": np.arange(t, t + n)}},
+             "vertices": {"i": {"id": rs.randint(0, 50, 20), "ts": np.arange(t, t + 20), "feat": rs.randn(20, 3).astype(np.float32)}}}
+        t += n
+        return b
+
+    def same(q):
+        a, c = one.run_query(0, q), cl.run_query(q)
+        for h in range(2):
+            for key in ("ids", "timestamps", "weights"):
+                assert torch.allclose(a["hops"][h][key].float(), c["hops"][h][key].float()), (h, key)
+        assert torch.allclose(a["nodes"][3]["features"], c["nodes"][3]["features"])
+
+    q = list(range(40)) + [45]
+    for r in range(4):
+        b = batch()
+        one.apply_updates(b)
+        assert cl.produce(b) == 260
+        if r == 1:
+            co.set_barrier("b")
+            assert co.barrier_status("b") == "PRODUCED"
+        cl.pump()
+        if r == 1:
+            assert co.barrier_status("b") == "READY" and cl.barrier_ready()
+        same(q)
+    st = cl.stats()
+    total_rows = sum(s["published_rows"] for s in st["sampling"])
+    assert st["produced"] == 4 * 260 and sum(s["applied"] for s in st["sampling"]) == 4 * 260 and total_rows > 0
+    # a serving worker only ever receives the "sim" rows of items it subscribed to (reachable from one of ITS users)
+    for w in cl.serving:
+        have = set((w.rows[2]["nbr"][:, 0] >= 0).nonzero().flatten().tolist())
+        subscribed = set()
+        for sw in cl.sampling:
+            m = sw.subs.mask[2]
+            subscribed |= set((((m >> w.wid) & 1) == 1).nonzero().flatten().tolist())
+        assert have <= subscribed and len(subscribed) > 0
+
+    cid = co.checkpoint()
+    assert cid == 1 and co.latest_checkpoint() == 1
+    more = batch()
+    one.apply_updates(more); cl.produce(more)                              # produced AFTER the checkpoint, not yet consumed
+    cl2 = StreamingCluster(schema, num_sampling=3, num_serving=2, sampling_devices=["cpu"] * 3, serving_devices=["cpu"] * 2,
+                           log_dir=str(tmp_path / "logs"))                 # recovers the channel segments from disk
+    co2 = Coordinator(cl2, meta_dir=str(tmp_path / "meta"))
+    assert co2.restore_latest() == 1
+    cl2.pump()                                                             # replays the batch from the checkpointed offsets
+    a, c = one.run_query(0, q), cl2.run_query(q)
+    assert torch.equal(a["hops"][1]["ids"], c["hops"][1]["ids"]) and torch.equal(a["hops"][0]["ids"], c["hops"][0]["ids"])
