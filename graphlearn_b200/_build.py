@@ -18,6 +18,7 @@ import sys
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
+_INCLUDE = os.path.join(_PKG_DIR, "include")      # public C++ headers (include/glb/api.h)
 _BUILD_DIR = os.path.join(_PKG_DIR, "build")
 _SO_PATH = os.path.join(_PKG_DIR, "_C.so")
 _STAMP = os.path.join(_PKG_DIR, "_C.stamp")
@@ -41,7 +42,7 @@ def sources():
 
 def _digest():
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(_CSRC, "*"))):
+    for f in sorted(glob.glob(os.path.join(_CSRC, "*")) + glob.glob(os.path.join(_INCLUDE, "glb", "*"))):
         if os.path.isfile(f):
             h.update(f.encode())
             with open(f, "rb") as fh:
@@ -72,7 +73,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         sources=sources(),
         extra_cflags=CXX_FLAGS,
         extra_cuda_cflags=CUDA_FLAGS,
-        extra_include_paths=[_CSRC],
+        extra_include_paths=[_CSRC, _INCLUDE],
         build_directory=_BUILD_DIR,
         with_cuda=True,
         is_python_module=False,   # just build; we import from the in-tree copy below

@@ -1,6 +1,8 @@
 // pybind11 surface of the native extension `graphlearn_b200._C`.
 #include <torch/extension.h>
 
+#include "glb/api.h"
+
 namespace glb {
 // sampling.cu
 std::vector<at::Tensor> sample_neighbors(const at::Tensor&, const at::Tensor&, int64_t, int64_t, int64_t,
@@ -37,6 +39,7 @@ void sage_fused_multi(const at::Tensor&, const at::Tensor&, const std::vector<c1
 int sm_count();
 void sage_set_debug_trace(const c10::optional<at::Tensor>&);
 void sage_set_max_ctas(int64_t);
+void sage_set_variant(int64_t);
 // sage_bwd.cu
 at::Tensor pack_weight_t(const at::Tensor&, int64_t, int64_t);
 void sage_bwd_dw(const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&, const std::vector<int64_t>&,
@@ -99,6 +102,55 @@ void save_embeddings(const std::string&, const at::Tensor&, const at::Tensor&, b
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "graphlearn_b200 native runtime: sm_100a kernels + host loader";
+  // ---- public C++ API (include/glb/api.h), exported 1:1 so the test-suite can hold it against the Python path
+  {
+    namespace A = glb::api;
+    py::class_<A::Graph, std::shared_ptr<A::Graph>>(m, "CppGraph")
+        .def(py::init<int, int64_t>(), py::arg("device_index") = 0, py::arg("seed") = 0)
+        .def("add_nodes", [](A::Graph& g, const std::string& t, int64_t n, const c10::optional<at::Tensor>& f,
+                             const c10::optional<at::Tensor>& l, const c10::optional<at::Tensor>& w, bool bf16) { g.AddNodes(t, n, f, l, w, bf16); },
+             py::arg("type"), py::arg("num_nodes"), py::arg("features") = py::none(), py::arg("labels") = py::none(),
+             py::arg("weights") = py::none(), py::arg("store_bf16") = false)
+        .def("add_edges", [](A::Graph& g, const std::string& t, const std::string& s, const std::string& d, const at::Tensor& src,
+                             const at::Tensor& dst, const c10::optional<at::Tensor>& w) { g.AddEdges(t, s, d, src, dst, w); },
+             py::arg("type"), py::arg("src_type"), py::arg("dst_type"), py::arg("src"), py::arg("dst"), py::arg("weights") = py::none())
+        .def("add_node_file", [](A::Graph& g, const std::string& t, const std::string& p, int64_t fd, bool w, bool l, bool bf16) {
+          g.AddNodeFile(t, p, fd, w, l, bf16); }, py::arg("type"), py::arg("path"), py::arg("float_dim"), py::arg("weighted") = false,
+             py::arg("labeled") = false, py::arg("store_bf16") = false)
+        .def("add_edge_file", [](A::Graph& g, const std::string& t, const std::string& s, const std::string& d, const std::string& p, bool w) {
+          g.AddEdgeFile(t, s, d, p, w); }, py::arg("type"), py::arg("src_type"), py::arg("dst_type"), py::arg("path"), py::arg("weighted") = false)
+        .def("init", &A::Graph::Init)
+        .def("sample_neighbors", [](A::Graph& g, const std::string& e, const at::Tensor& ids, int64_t k, const std::string& s) {
+          return g.SampleNeighbors(e, ids, k, A::strategy_from_name(s)); }, py::arg("edge_type"), py::arg("ids"), py::arg("k"),
+             py::arg("strategy") = "random")
+        .def("full_neighbors", &A::Graph::FullNeighbors)
+        .def("get_degree", &A::Graph::GetDegree)
+        .def("lookup_nodes", &A::Graph::LookupNodes, py::arg("node_type"), py::arg("ids"), py::arg("out_bf16") = false)
+        .def("lookup_labels", &A::Graph::LookupLabels)
+        .def("random_walk", &A::Graph::RandomWalk, py::arg("edge_type"), py::arg("ids"), py::arg("walk_len"), py::arg("p") = 1.0,
+             py::arg("q") = 1.0)
+        .def("negative_sample", &A::Graph::NegativeSample, py::arg("edge_type"), py::arg("ids"), py::arg("k"), py::arg("strict") = true,
+             py::arg("by_in_degree") = false)
+        .def("get_stats", [](const A::Graph& g) { auto s = g.GetStats(); return py::make_tuple(s.node_count, s.edge_count); });
+    py::class_<A::Query>(m, "CppQuery")
+        .def_static("V", &A::Query::V, py::arg("node_type"), py::arg("alias") = "src")
+        .def("batch", [](A::Query& q, int64_t b) { return q.Batch(b); })
+        .def("shuffle", [](A::Query& q, bool t) { return q.Shuffle(t); }, py::arg("traverse") = true)
+        .def("outV", [](A::Query& q, const std::string& e, int64_t k, const std::string& s, const std::string& a) {
+          return q.OutV(e, k, A::strategy_from_name(s), a); }, py::arg("edge_type"), py::arg("k"), py::arg("strategy") = "random",
+             py::arg("alias") = "")
+        .def("with_features", [](A::Query& q, bool on) { return q.WithFeatures(on); }, py::arg("on") = true);
+    py::class_<A::Dataset>(m, "CppDataset")
+        .def(py::init<std::shared_ptr<A::Graph>, const A::Query&, int64_t, bool>(), py::arg("graph"), py::arg("query"),
+             py::arg("prefetch") = 2, py::arg("drop_last") = false)
+        .def("next", [](A::Dataset& d) -> py::object {
+          A::Batch b;
+          if (!d.Next(&b)) return py::none();
+          return py::make_tuple(b.size, b.ids, b.features, b.labels.defined() ? py::cast(b.labels) : py::none());
+        })
+        .def_property_readonly("epoch", &A::Dataset::epoch)
+        .def_property_readonly("batches_per_epoch", &A::Dataset::batches_per_epoch);
+  }
   m.def("sample_neighbors", &glb::sample_neighbors);
   m.def("get_degrees", &glb::get_degrees);
   m.def("sample_full", &glb::sample_full);
@@ -116,6 +168,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sm_count", &glb::sm_count);
   m.def("sage_set_debug_trace", &glb::sage_set_debug_trace);
   m.def("sage_set_max_ctas", &glb::sage_set_max_ctas);
+  m.def("sage_set_variant", &glb::sage_set_variant);
   m.def("pack_weight_t", &glb::pack_weight_t);
   m.def("sage_bwd_dw", &glb::sage_bwd_dw);
   m.def("pack_weight_f32", &glb::pack_weight_f32);

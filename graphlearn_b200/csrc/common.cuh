@@ -187,8 +187,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  // bf16 -> fp32 is a 16-bit shift: one SHL for the low element, one LOP for the high one (the library's
+  // __bfloat1622float2 spends PRMT + shift on the high half)
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 }  // namespace glb

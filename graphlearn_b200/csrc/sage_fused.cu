@@ -43,11 +43,11 @@ namespace glb {
 
 constexpr int kTileM = 64;                         // destination rows per tile = UMMA M (two A tiles fit next to the W image)
 constexpr int kABufs = 2;
-constexpr int kThreads = 1024;
-constexpr int kEpiWarps = 8;                       // warps 0..7 (TMEM lane quarter = warp & 3, 32-column chunks interleaved by warp >> 2)
-constexpr int kMmaWarp = 8;
-constexpr int kGatherWarp0 = 9;
-constexpr int kGatherWarps = kThreads / 32 - kGatherWarp0;   // 23
+// Role layout (template parameters EW / GW of the kernel): warps [0, EW) epilogue (TMEM lane quarter = warp & 3, 32-column
+// chunks interleaved by warp >> 2), warp EW = MMA issuer, warps [EW + 1, EW + 1 + GW) gather.  The register file is
+// split evenly over the CTA's threads, so the shape trades gather warps against row loads in flight per lane:
+//   (8, 23) 1024 threads x 64 regs     (4, 19) 768 threads x 80 regs     (4, 11) 512 threads x 128 regs
+constexpr int kMaxGatherWarps = 23;                 // sizes the pointer scratch
 constexpr int kMaxSegs = 4;
 constexpr int kScrCap = 64;                        // row pointers per gather warp (private scratch): rows_per_item * (k + 1) <= 64
 constexpr size_t kSmemLimit = 232448;
@@ -181,7 +181,7 @@ __device__ __forceinline__ void load_cols32(const SageParams& p, const float* sB
 // phase A of the epilogue: TMEM -> registers -> bias/ReLU -> global.  Eight warps: lane quarter q = warp & 3,
 // 32-column chunks interleaved between the two warps (warp >> 2) that share a quarter.
 __device__ __forceinline__ void sage_epilogue_tile(const SageParams& p, const SageSeg& sg, const float* sBias, uint32_t tmem_acc,
-                                                   int m0, int rows, int warp, int lane) {
+                                                   int m0, int rows, int warp, int lane, int epi_warps) {
   // UMMA M = 64: accumulator row r lives in TMEM lane (r / 16) * 32 + (r % 16), i.e. lanes 0..15 of every quarter
   const int q = warp & 3, half = warp >> 2;
   if (q * 16 >= rows) return;                          // warp-uniform: this lane quarter holds no valid row
@@ -189,7 +189,7 @@ __device__ __forceinline__ void sage_epilogue_tile(const SageParams& p, const Sa
   const int m = m0 + row;
   const bool row_ok = lane < 16 && row < rows;
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-  for (int n0 = half * 32; n0 < p.N; n0 += 64) {
+  for (int n0 = half * 32; n0 < p.N; n0 += 8 * epi_warps) {
     if (n0 >= p.n_out) break;                          // padded output columns are never read back
     float f[32];
     load_cols32(p, sBias, taddr, n0, f);
@@ -199,11 +199,11 @@ __device__ __forceinline__ void sage_epilogue_tile(const SageParams& p, const Sa
 
 // phase B (top layer only): softmax cross-entropy of the tile's rows, one warp per row, lanes = classes
 // (n_out <= 64: columns lane and lane + 32), reading the logits phase A has just written (L2).
-__device__ __forceinline__ void sage_ce_tile(const SageParams& p, const SageSeg& sg, int m0, int rows, int warp, int lane) {
+__device__ __forceinline__ void sage_ce_tile(const SageParams& p, const SageSeg& sg, int m0, int rows, int warp, int lane, int epi_warps) {
   const float* logits = reinterpret_cast<const float*>(sg.out);
   const int c0 = lane, c1 = lane + 32;
   float db0 = 0.f, db1 = 0.f, lsum = 0.f;
-  for (int r = warp; r < rows; r += kEpiWarps) {
+  for (int r = warp; r < rows; r += epi_warps) {
     const int m = m0 + r;
     const float* lrow = logits + (size_t)m * p.out_stride;
     const float x0 = c0 < p.n_out ? __ldcg(lrow + c0) : -FLT_MAX;
@@ -246,37 +246,52 @@ struct TileCtx {       // kept small on purpose: the gather loop holds two of th
 
 struct GatherGeom {
   int rpi, n_slices, lshift, sub, lig;
+  int tile_first, tile_stride;     // this CTA's tiles: tile_first + it * tile_stride
 };
 
 // position (it, item) -> first tile at or after `it` in which this warp still has an item; false past the last tile
 __device__ __forceinline__ bool seek_item(const SageParams& p, const GatherGeom& gg, int& it, int& item, TileCtx& c) {
   for (;;) {
-    const int t = (int)blockIdx.x / p.n_imgs + it * ((int)gridDim.x / p.n_imgs);
+    const int t = gg.tile_first + it * gg.tile_stride;
     if (t >= p.total_tiles) return false;
     const int s = find_seg(p, t);
     const int m0 = (t - p.seg[s].tile0) * p.seg[s].R;
     const int rows = min(p.seg[s].R, p.seg[s].M - m0);
-    const int n_items = ((rows + gg.rpi - 1) / gg.rpi) * gg.n_slices;
+    const int n_items = ((rows + gg.rpi - 1) >> (5 - gg.lshift)) * gg.n_slices;     // rpi == 32 >> lshift
     if (item < n_items) { c.s = s; c.m0 = m0; c.rows = rows; return true; }
     item -= n_items;
     ++it;
   }
 }
 
-// ids of one item, flat index f = sub_row * (k + 1) + j (j == k: the self id); lane holds f = lane and lane + 32
-__device__ __forceinline__ void load_item_ids(const SageParams& p, const GatherGeom& gg, const TileCtx& c, int item, bool need_self,
-                                              int lane, int64_t (&ids)[2]) {
-  const SageSeg& sg = p.seg[c.s];
-  const int rg = gg.n_slices == 1 ? item : item / gg.n_slices;
-  const int k1 = sg.k + 1;
+// An item holds rpi * (k + 1) ids, flat index f = sub_row * (k + 1) + j (j == k: the self id); a lane owns f = lane and
+// f = lane + 32.  The (sub_row, j) split of those two slots only depends on the segment's k: it is cached in
+// one byte per slot, (sub_row << 6) | j (0xFF: slot unused; rpi <= 4 and k < 64), both slots packed into one register
+// and recomputed when the warp crosses into another segment, so the steady-state loop has no integer division.
+__device__ __forceinline__ uint32_t decompose_slots(const GatherGeom& gg, int k, int lane) {
+  const int k1 = k + 1;
   const int n_ids = gg.rpi * k1;
+  uint32_t dec = 0;
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int f = lane + 32 * u;
+    const int sr = f / k1;
+    dec |= (f < n_ids ? (uint32_t)((sr << 6) | (f - sr * k1)) : 0xFFu) << (8 * u);
+  }
+  return dec;
+}
+
+__device__ __forceinline__ void load_item_ids(const SageParams& p, const GatherGeom& gg, const TileCtx& c, int item, bool need_self,
+                                              uint32_t dec, int64_t (&ids)[2]) {
+  const SageSeg& sg = p.seg[c.s];
+  const int rg = gg.n_slices == 1 ? item : item / gg.n_slices;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
     ids[u] = -1;
-    if (f < n_ids) {
-      const int sr = f / k1, j = f - sr * k1;
-      const int r = rg * gg.rpi + sr;
+    const int d = (int)((dec >> (8 * u)) & 0xFFu);
+    if (d != 0xFF) {
+      const int j = d & 63;
+      const int r = rg * gg.rpi + (d >> 6);
       if (r < c.rows) {
         const int64_t m = c.m0 + r;
         if (j < sg.k) ids[u] = sg.nbr_vids ? __ldg(sg.nbr_vids + m * sg.k + j) : sg.nbr_base + m * sg.k + j;
@@ -286,17 +301,15 @@ __device__ __forceinline__ void load_item_ids(const SageParams& p, const GatherG
   }
 }
 
-__device__ __forceinline__ void write_item_ptrs(const SageParams& p, const GatherGeom& gg, const TileCtx& c, const int64_t (&ids)[2],
+__device__ __forceinline__ void write_item_ptrs(const SageParams& p, const TileCtx& c, const int64_t (&ids)[2], uint32_t dec,
                                                 int lane, const char** scr, uint32_t self_row_bytes, uint32_t nbr_row_bytes) {
   const int k = p.seg[c.s].k;
-  const int n_ids = gg.rpi * (k + 1);
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    const int f = lane + 32 * u;
-    if (f < n_ids) {
-      const int j = f % (k + 1);
-      scr[f] = j < k ? vid_ptr(p.tnbr, ids[u], p.wshift_nbr, nbr_row_bytes, p.zero_row)
-                     : vid_ptr(p.tself, ids[u], p.wshift_self, self_row_bytes, p.zero_row);
+    const int d = (int)((dec >> (8 * u)) & 0xFFu);
+    if (d != 0xFF) {
+      scr[lane + 32 * u] = (d & 63) < k ? vid_ptr(p.tnbr, ids[u], p.wshift_nbr, nbr_row_bytes, p.zero_row)
+                                             : vid_ptr(p.tself, ids[u], p.wshift_self, self_row_bytes, p.zero_row);
     }
   }
 }
@@ -309,8 +322,9 @@ __device__ __forceinline__ void write_item_ptrs(const SageParams& p, const Gathe
 // 32-lane slices.  Per item a lane group issues ALL self + neighbour chunk loads of a batch
 // unconditionally (masked lanes read a zero row), reduces in fp32 and writes bf16 into the SW128
 // A tile.
-template <int U, int DT>
-__global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_constant__ SageParams p) {
+template <int U, int DT, int EW, int GW>
+__global__ void __launch_bounds__((EW + 1 + GW) * 32, 1) sage_persist_kernel(const __grid_constant__ SageParams p) {
+  constexpr int kEpiWarps = EW, kMmaWarp = EW, kGatherWarp0 = EW + 1, kGatherWarps = GW;
   if (p.dbg && threadIdx.x == 0) {
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.dbg[(size_t)blockIdx.x * 64 + 60] = (long long)gt;
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
   uint8_t* sW = sA + (size_t)kABufs * a_buf_bytes;
   const uint32_t w_kb_bytes = (uint32_t)p.N * 128u;
   const char** sScr = reinterpret_cast<const char**>(sW + (size_t)nkb * w_kb_bytes);   // [kGatherWarps][kScrCap]
-  float* sBias = reinterpret_cast<float*>(sScr + kGatherWarps * kScrCap);              // [256]
+  float* sBias = reinterpret_cast<float*>(sScr + kMaxGatherWarps * kScrCap);           // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
@@ -372,14 +386,14 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
       if (sg.out) sg.out += (size_t)img * p.N * (p.out_bf16 ? 2 : 4);
       const int m0 = (t - sg.tile0) * sg.R;
       const int rows = min(sg.R, sg.M - m0);
-      sage_epilogue_tile(p, sg, sBias, tmem_base + (uint32_t)(acc * p.N), m0, rows, warp, lane);
+      sage_epilogue_tile(p, sg, sBias, tmem_base + (uint32_t)(acc * p.N), m0, rows, warp, lane, kEpiWarps);
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(bars + kBarTFree + acc);
       if (p.ce_labels != nullptr) {
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");     // logits of the tile are written
-        sage_ce_tile(p, sg, m0, rows, warp, lane);
+        sage_ce_tile(p, sg, m0, rows, warp, lane, kEpiWarps);
       }
       if (warp == 0 && it < 4) GLB_DBG(5 + it * 2);
     }
@@ -432,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
     gg.n_slices = lanes_row > 32 ? lanes_row >> 5 : 1;
     gg.sub = lane >> gg.lshift;                           // which row of the item this lane works on
     gg.lig = lane & (lpr - 1);                            // lane index inside its row group
+    gg.tile_first = tile_first; gg.tile_stride = tile_stride;
     const bool has_self = p.kp_self > 0;
     const bool has_nbr = p.kp_nbr > 0;
     const bool need_self = has_self || p.mode == kGcnMean;
@@ -455,10 +470,14 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
     int it = 0, item = gw;
     TileCtx cur;
     bool valid = seek_item(p, gg, it, item, cur);
+    uint32_t dec = 0xFFFFu;                               // id-slot split of the segment `dec_seg`
+    int dec_seg = -1;
     if (valid) {
       int64_t ids[2];
-      load_item_ids(p, gg, cur, item, need_self, lane, ids);
-      write_item_ptrs(p, gg, cur, ids, lane, scr, self_row_bytes, nbr_row_bytes);
+      dec_seg = cur.s;
+      dec = decompose_slots(gg, p.seg[cur.s].k, lane);
+      load_item_ids(p, gg, cur, item, need_self, dec, ids);
+      write_item_ptrs(p, cur, ids, dec, lane, scr, self_row_bytes, nbr_row_bytes);
       __syncwarp();
     }
     if (gw == 0) GLB_DBG(28);
@@ -468,7 +487,11 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
       TileCtx nxt;
       const bool nvalid = seek_item(p, gg, nit, nitem, nxt);
       int64_t nids[2];
-      if (nvalid) load_item_ids(p, gg, nxt, nitem, need_self, lane, nids);
+      if (nvalid) {
+        // (the current item's pointers are already staged: `dec` only serves the NEXT item from here on)
+        if (nxt.s != dec_seg) { dec = decompose_slots(gg, p.seg[nxt.s].k, lane); dec_seg = nxt.s; }   // rare
+        load_item_ids(p, gg, nxt, nitem, need_self, dec, nids);
+      }
       // ---- current item
       const SageSeg& sg = p.seg[cur.s];
       const int k = sg.k;
@@ -490,23 +513,30 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
         Chunk<DT> sraw;
         if (self_ld) sraw.load(ptrs[k] + coff);
         if (has_nbr && f0 < d_nbr) {
-          for (int j0 = 0; j0 < k; j0 += U) {
+          int j0 = 0;
+          for (; j0 + U <= k; j0 += U) {                  // full batches: U unconditional loads, then U adds
             Chunk<DT> raw[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int j = j0 + u < k ? j0 + u : k - 1;  // tail slots re-read the last row (masked below)
-              raw[u].load(ptrs[j] + coff);
-            }
+            for (int u = 0; u < U; ++u) raw[u].load(ptrs[j0 + u] + coff);
+#pragma unroll
+            for (int u = 0; u < U; ++u) raw[u].add_to(acc);
+          }
+          if (j0 < k) {                                   // remainder batch (k % U rows)
+            Chunk<DT> raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) raw[u].load(ptrs[j0 + u < k ? j0 + u : k - 1] + coff);
 #pragma unroll
             for (int u = 0; u < U; ++u)
               if (j0 + u < k) raw[u].add_to(acc);
           }
         }
         if (self_ld) sraw.add_to(sv);
+        if (f0 + VEC > d_self || f0 + VEC > d_nbr) {       // only the chunk that straddles the real width needs masking
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {                    // tail masks (dims that are not multiples of VEC)
-          if (f0 + i >= d_self) sv[i] = 0.f;
-          if (f0 + i >= d_nbr) acc[i] = 0.f;
+          for (int i = 0; i < VEC; ++i) {
+            if (f0 + i >= d_self) sv[i] = 0.f;
+            if (f0 + i >= d_nbr) acc[i] = 0.f;
+          }
         }
       }
       // ---- A buffer it & 1 may only be written once the MMA of tile it-2 has consumed it
@@ -535,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) sage_persist_kernel(const __grid_
       }
       __syncwarp();                                       // every lane is done reading the scratch pointers
       if (nvalid) {
-        write_item_ptrs(p, gg, nxt, nids, lane, scr, self_row_bytes, nbr_row_bytes);
+        write_item_ptrs(p, nxt, nids, dec, lane, scr, self_row_bytes, nbr_row_bytes);
         __syncwarp();
       }
       it = nit; item = nitem; cur = nxt; valid = nvalid;
@@ -604,7 +634,7 @@ int64_t sage_pad_k(int64_t d) { return pad_k((int)d); }
 
 // dynamic shared memory of the persistent kernel: A tile + W image + per-warp pointer scratch + bias + control + alignment slack
 int64_t sage_smem_bytes(int64_t k_total, int64_t N) {
-  return 1024 + kABufs * (k_total / 64) * (kTileM * 128) + (k_total / 64) * N * 128 + kGatherWarps * kScrCap * 8 + 256 * 4 + (kNumBars + 2) * 8;
+  return 1024 + kABufs * (k_total / 64) * (kTileM * 128) + (k_total / 64) * N * 128 + kMaxGatherWarps * kScrCap * 8 + 256 * 4 + (kNumBars + 2) * 8;
 }
 
 int sm_count() {
@@ -690,24 +720,38 @@ static void plan_tiles(SageParams& p, int64_t rows_forced) {
   p.total_tiles = tiles;
 }
 
+static int g_variant = 2;      // role layout of the persistent kernel (see the table at the top): (4, 19) measured fastest
+                               // at 1 and 2 GPUs (profiles/r2_role_layouts.txt); sage_set_variant / GLB_SAGE_VARIANT override
+void sage_set_variant(int64_t v) { TORCH_CHECK(v >= 0 && v <= 2, "variant 0..2"); g_variant = (int)v; }
+
 static void launch_persist(SageParams& p, size_t smem, cudaStream_t stream) {
   if (p.total_tiles == 0) return;
   const unsigned grid = (unsigned)(p.n_imgs * std::min<int>(std::max(1, usable_sms() / p.n_imgs), p.total_tiles));
   int kmax = 1;
   for (int s = 0; s < p.nseg; ++s) kmax = std::max(kmax, p.seg[s].k);
-  const int u = kmax <= 4 ? 4 : (kmax % 5 == 0 || kmax > 12) ? 5 : 6;
   const int dt = p.tnbr.dtype;
-#define LAUNCH(UU, DD)                                                                                     \
+#define LAUNCH(UU, DD, EW, GW)                                                                             \
   do {                                                                                                     \
     static bool attr_done = false;                                                                         \
     if (!attr_done) {                                                                                      \
-      C10_CUDA_CHECK(cudaFuncSetAttribute(sage_persist_kernel<UU, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit)); \
+      C10_CUDA_CHECK(cudaFuncSetAttribute(sage_persist_kernel<UU, DD, EW, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit)); \
       attr_done = true;                                                                                    \
     }                                                                                                      \
-    sage_persist_kernel<UU, DD><<<grid, kThreads, smem, stream>>>(p);                                      \
+    sage_persist_kernel<UU, DD, EW, GW><<<grid, (EW + 1 + GW) * 32, smem, stream>>>(p);                    \
   } while (0)
-  if (dt == 0) { if (u == 4) LAUNCH(4, 0); else if (u == 5) LAUNCH(5, 0); else LAUNCH(6, 0); }
-  else         { if (u == 4) LAUNCH(4, 1); else if (u == 5) LAUNCH(5, 1); else LAUNCH(6, 1); }
+#define LAUNCH_DT(UU, EW, GW) do { if (dt == 0) LAUNCH(UU, 0, EW, GW); else LAUNCH(UU, 1, EW, GW); } while (0)
+  if (g_variant == 1) {
+    // 512 threads x 128 registers: a whole neighbour list (or half of a long one) in flight per lane
+    const int u = kmax <= 5 ? 5 : kmax <= 10 ? 10 : 13;
+    if (u == 5) LAUNCH_DT(5, 4, 11); else if (u == 10) LAUNCH_DT(10, 4, 11); else LAUNCH_DT(13, 4, 11);
+  } else if (g_variant == 2) {
+    const int u = kmax <= 4 ? 4 : (kmax % 5 == 0 || kmax > 12) ? 5 : 6;
+    if (u == 4) LAUNCH_DT(4, 4, 19); else if (u == 5) LAUNCH_DT(5, 4, 19); else LAUNCH_DT(6, 4, 19);
+  } else {
+    const int u = kmax <= 4 ? 4 : (kmax % 5 == 0 || kmax > 12) ? 5 : 6;
+    if (u == 4) LAUNCH_DT(4, 8, 23); else if (u == 5) LAUNCH_DT(5, 8, 23); else LAUNCH_DT(6, 8, 23);
+  }
+#undef LAUNCH_DT
 #undef LAUNCH
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

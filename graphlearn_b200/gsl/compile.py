@@ -176,8 +176,35 @@ class CompiledQuery(object):
     # ------------------------------------------------------------------ iteration
     def next_seeds(self) -> torch.Tensor:
         """host vids of the next seed batch (raises OutOfRangeError at the end of an epoch)"""
+        if _config.get().actor_enabled and self.rt.world > 1 and self.plan.traverse in ("shuffle", "by_order"):
+            return self._next_dispatched()
         idx = self.iter.next_index()
         return self.seed_vids[idx]
+
+    def _next_dispatched(self) -> torch.Tensor:
+        """``gl.enable_actor()``: at every epoch start the ranks pool their seed batches and the balanced plan of
+        engine/dispatch.py gives each rank the same number of (work-balanced) batches - one collective per epoch."""
+        from ..engine.dispatch import BalancedSeedDispatcher
+        if getattr(self, "_planned", None) is None:
+            vids = self.seed_vids
+            if self.plan.traverse == "shuffle":
+                g = torch.Generator(device="cpu").manual_seed(_config.get().seed * 7919 + 31 * self.rt.rank + self.iter.epoch)
+                vids = vids[torch.randperm(int(vids.numel()), generator=g)]
+            dv = vids.to(self.rt.device)
+            weights = None
+            tab = self.store.nodes[self.plan.base_type]
+            et = self.plan.hops[0].edge_type
+            if self.plan.hops[0].direction == "out" and et in tab.out_degrees:
+                weights = tab.out_degrees[et][dv // self.rt.world].float() + 1.0
+            self._planned = BalancedSeedDispatcher(self.rt, self.B).plan(dv, weights).cpu()
+            self._plan_iter = SeedIterator(int(self._planned.numel()), self.B, "by_order", "cpu")
+        try:
+            idx = self._plan_iter.next_index()
+        except errors.OutOfRangeError:
+            self._planned = None
+            self.iter.epoch += 1
+            raise
+        return self._planned[idx]
 
     def launch(self):
         """Stage the next seed batch and replay the hop-chain graph of the next ring slot.  Returns (slot, n_real)."""

@@ -23,7 +23,16 @@ _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.int64: 2, torch.int32:
 
 def native():
     """The compiled extension (raises loudly when it is missing)."""
-    return _build.load()
+    global _NATIVE
+    if _NATIVE is None:
+        _NATIVE = _build.load()
+        v = os.environ.get("GLB_SAGE_VARIANT")          # role layout of the persistent fused kernel (csrc/sage_fused.cu)
+        if v is not None:
+            _NATIVE.sage_set_variant(int(v))
+    return _NATIVE
+
+
+_NATIVE = None
 
 
 class SymmTensor:
