@@ -41,6 +41,12 @@ def main(args):
     import torch.nn.functional as F
 
     small = getattr(args, "small", False)
+    if getattr(args, "config", "") == "taobao_gat":
+        # the reference's bipartite GAT (graphlearn/examples/tf/ego_bipartite_*) is a TF1 model and TensorFlow is not in
+        # this image; a torch re-implementation of it would be OUR model on the reference path, which the arm forbids
+        print(json.dumps({"impl": "reference", "unavailable": "reference bipartite GAT is TF1-only (graphlearn/examples/tf); no TensorFlow "
+                                                                "offline - only the sampling half could run unmodified"}))
+        return
     cfg = getattr(args, "cfg", None) or {"shape": dict(num_nodes=2_449_029, num_edges=123_718_280, feat_dim=100, num_classes=47),
                                          "fanouts": [25, 10], "hidden": 256,
                                          "metric": "sampled-subgraph train steps/sec (2-layer GraphSAGE fanout 25,10, ogbn-products-shaped synthetic)",

@@ -65,11 +65,27 @@ class Config:
     feature_dtype: str = "fp32"          # fp32 | bf16   storage dtype of float attribute tables in HBM
     loader_threads: int = 0           # 0 = auto: all cores divided by the number of ranks on the box
     use_peer_kernels: bool = True        # False -> torch.distributed (NCCL/gloo) baseline path
+    feature_row_align: int = 128         # bytes: feature rows wider than half of this start on such a boundary (16 = dense rows)
     seed: int = 0
     actor_enabled: bool = False
 
 
-_CFG = Config()
+def _from_env(cfg: "Config") -> "Config":
+    """GLB_<FIELD> environment variables override the int / bool / float / str defaults (e.g. GLB_FEATURE_ROW_ALIGN=16)"""
+    import os
+    for f in dataclasses.fields(cfg):
+        v = os.environ.get("GLB_" + f.name.upper())
+        if v is None:
+            continue
+        cur = getattr(cfg, f.name)
+        if isinstance(cur, bool):
+            setattr(cfg, f.name, v.lower() not in ("0", "false", "no", ""))
+        elif isinstance(cur, (int, float, str)):
+            setattr(cfg, f.name, type(cur)(v))
+    return cfg
+
+
+_CFG = _from_env(Config())
 
 
 def get() -> Config:
@@ -78,7 +94,7 @@ def get() -> Config:
 
 def reset():
     global _CFG
-    _CFG = Config()
+    _CFG = _from_env(Config())
     return _CFG
 
 
@@ -128,6 +144,7 @@ set_vineyard_ipc_socket = _setter("vineyard_ipc_socket", str)
 set_feature_dtype = _setter("feature_dtype", str)
 set_loader_threads = _setter("loader_threads", int)
 set_use_peer_kernels = _setter("use_peer_kernels", bool)
+set_feature_row_align = _setter("feature_row_align", int)
 set_seed = _setter("seed", int)
 
 

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const AllReduceP
     g.x *= p.scale; g.y *= p.scale; g.z *= p.scale; g.w *= p.scale;
     *reinterpret_cast<float4*>(my_stage + i) = g;
   }
-  __threadfence_system();
+  // (no per-thread system fence: the CTA barrier + the flag writers' st.release.sys order the staging stores, see adam_pack_kernel)
   __syncthreads();
 
   // phase 1: block-level cross-GPU barrier (block b of every rank)
@@ -280,7 +280,9 @@ __global__ void __launch_bounds__(128) adam_pack_kernel(const __grid_constant__ 
         }
       }
     }
-    __threadfence_system();
+    // No per-thread system fence here: 128 x blocks fence.sc.sys per step cost tens of microseconds on an NVSwitch box.
+    // The CTA barrier orders every thread's staging stores before the flag writers, and their st.release.sys is
+    // cumulative over everything that happens-before it (PTX memory model: causality order through bar.sync).
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();

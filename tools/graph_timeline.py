@@ -29,7 +29,24 @@ evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.Device
 ends = [i for i, e in enumerate(evs) if "adam_pack" in e.name]
 lo, hi = ends[2] + 1, ends[3] + 1
 t0 = evs[lo].time_range.start
-print("timeline of replay 4 (%s), %d kernels, span %.1f us" % ("e2e" if e2e else "device", hi - lo,
-      evs[hi - 1].time_range.end - t0))
-for e in evs[lo:hi]:
-    print("%8.1f +%6.1f us  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:70]))
+span = evs[hi - 1].time_range.end - t0
+if rt.rank == 0:
+    print("timeline of replay 4 (%s), %d kernels, span %.1f us%s" % ("e2e" if e2e else "device", hi - lo, span,
+          "" if rt.world == 1 else "  [rank 0 of %d]" % rt.world))
+    for e in evs[lo:hi]:
+        print("%8.1f +%6.1f us  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:70]))
+if rt.world > 1:
+    # per-rank summary: where the step's time goes on every GPU (adam_pack = fused peer all-reduce + Adam: its duration
+    # includes the wait for the slowest rank's gradients)
+    dur = {}
+    for e in evs[lo:hi]:
+        k = e.name.split("(")[0].replace("void ", "").replace("glb::", "")[:28]
+        dur[k] = dur.get(k, 0.0) + (e.time_range.end - e.time_range.start)
+    rows = rt.all_gather_object((rt.rank, span, dur))
+    if rt.rank == 0:
+        keys = sorted({k for _, _, d in rows for k in d})
+        print("per-rank kernel time (us) in one replay:")
+        print("rank  span   " + "  ".join("%-28s" % k for k in keys))
+        for r, sp, d in rows:
+            print("%4d %6.1f  " % (r, sp) + "  ".join("%-28.1f" % d.get(k, 0.0) for k in keys))
+rt.barrier()
