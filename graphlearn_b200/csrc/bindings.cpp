@@ -21,6 +21,8 @@ at::Tensor negative_sample(const at::Tensor&, const at::Tensor&, int64_t, const 
 at::Tensor gather_rows(const at::Tensor&, const at::Tensor&, bool, double);
 at::Tensor gather_agg(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int64_t, int64_t);
 void scatter_add_rows(const at::Tensor&, const at::Tensor&, const at::Tensor&, double);
+void sparse_adam_rows(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, double, double, double,
+                      double, int64_t);
 void gather_copy16(const at::Tensor&, const at::Tensor&, int64_t, const at::Tensor&, bool, int64_t);
 // sage_fused.cu
 int64_t sage_pad_k(int64_t);
@@ -162,6 +164,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gather_agg", &glb::gather_agg);
   m.def("scatter_add_rows", &glb::scatter_add_rows);
   m.def("gather_copy16", &glb::gather_copy16);
+  m.def("sparse_adam_rows", &glb::sparse_adam_rows);
   m.def("sage_pad_k", &glb::sage_pad_k);
   m.def("sage_smem_bytes", &glb::sage_smem_bytes);
   m.def("pack_weight_sw128", &glb::pack_weight_sw128);

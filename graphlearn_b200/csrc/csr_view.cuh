@@ -18,6 +18,8 @@ struct CsrView {
                        //                 sampling weight    (may be null)
   PeerTable ts;        // const int64_t*  edge timestamps, rows sorted asc
                        //                                   (may be null)
+  PeerTable sorted;    // const int64_t*  destination vids of every row sorted ASCENDING (same indptr; may be null):
+                       //                 membership tests by binary search (node2vec "is x a neighbour of the parent")
   int64_t nrows[kMaxWorld];
   int world;
 };
@@ -27,6 +29,7 @@ struct RowRef {
   const int64_t* eids;
   const float* cumw;
   const int64_t* ts;
+  const int64_t* sorted;
   int64_t beg;
   int64_t deg;
 };
@@ -36,7 +39,7 @@ struct RowRef {
 // id that is not a source vertex.
 __device__ __forceinline__ RowRef csr_row(const CsrView& g, int64_t vid) {
   RowRef r;
-  r.indices = nullptr; r.eids = nullptr; r.cumw = nullptr; r.ts = nullptr;
+  r.indices = nullptr; r.eids = nullptr; r.cumw = nullptr; r.ts = nullptr; r.sorted = nullptr;
   r.beg = 0; r.deg = 0;
   if (vid < 0) return r;
   int owner = (int)(vid % g.world);
@@ -51,6 +54,7 @@ __device__ __forceinline__ RowRef csr_row(const CsrView& g, int64_t vid) {
   r.eids = reinterpret_cast<const int64_t*>(g.eids.p[owner]);
   r.cumw = reinterpret_cast<const float*>(g.cumw.p[owner]);
   r.ts = reinterpret_cast<const int64_t*>(g.ts.p[owner]);
+  r.sorted = reinterpret_cast<const int64_t*>(g.sorted.p[owner]);
   return r;
 }
 

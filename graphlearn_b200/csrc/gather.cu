@@ -11,6 +11,7 @@
 // Aggregation semantics follow graphlearn/src/core/operator/aggregator/*
 // (sum / mean / min / max / prod segment reduce of float attributes).
 #include <torch/extension.h>
+#include <cmath>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cfloat>
@@ -239,6 +240,53 @@ void scatter_add_rows(const at::Tensor& table_desc, const at::Tensor& vids, cons
   unsigned blocks = (unsigned)((n * 32 + 255) / 256);
   scatter_add_rows_kernel<<<blocks, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
       t, v.data_ptr<int64_t>(), n, g.data_ptr<float>(), (int64_t)t.dim, (float)scale);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------
+// K9: sparse Adam on sharded embedding tables.  One warp per touched row (ids unique within the call): the row of the
+// weight table and of both moment tables lives on the owner GPU and is updated in place through the peer pointers -
+// the asynchronous parameter-server update of the reference's AdamAsyncOptimizer (examples/tf/trainer.py:111-116)
+// without a server: no dense gradient, no all-reduce.  Rows touched by two ranks at once race like they do on a PS.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sparse_adam_rows_kernel(const TableView w, const TableView m, const TableView v, const int64_t* __restrict__ vids, int64_t n,
+                        const float* __restrict__ grad, int64_t grad_stride, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const int64_t vid = __ldg(vids + r);
+  float* wp = const_cast<float*>(reinterpret_cast<const float*>(row_ptr(w, vid)));
+  float* mp = const_cast<float*>(reinterpret_cast<const float*>(row_ptr(m, vid)));
+  float* vp = const_cast<float*>(reinterpret_cast<const float*>(row_ptr(v, vid)));
+  if (!wp || !mp || !vp) return;
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int f = lane; f < w.dim; f += 32) {
+    const float g = grad[r * grad_stride + f];
+    const float mm = b1 * mp[f] + (1.f - b1) * g;
+    const float vv = b2 * vp[f] + (1.f - b2) * g * g;
+    mp[f] = mm; vp[f] = vv;
+    wp[f] -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+  }
+}
+
+void sparse_adam_rows(const at::Tensor& w_desc, const at::Tensor& m_desc, const at::Tensor& v_desc, const at::Tensor& vids,
+                      const at::Tensor& grad, double lr, double b1, double b2, double eps, int64_t step) {
+  check_cuda_i64(vids, "vids");
+  c10::cuda::CUDAGuard guard(vids.device());
+  TableView w = table_from_desc(w_desc), m = table_from_desc(m_desc), v = table_from_desc(v_desc);
+  TORCH_CHECK(w.dtype == 0 && m.dtype == 0 && v.dtype == 0 && m.dim == w.dim && v.dim == w.dim, "sparse_adam_rows needs fp32 tables of one width");
+  w.cmap = m.cmap = v.cmap = nullptr;        // updates always go to the owner
+  auto ids = vids.contiguous();
+  auto g = grad.contiguous();
+  TORCH_CHECK(g.is_cuda() && g.scalar_type() == at::kFloat && g.dim() == 2 && g.size(1) == w.dim && g.size(0) == ids.numel(),
+              "grad must be fp32 [n, dim]");
+  const int64_t n = ids.numel();
+  if (n == 0) return;
+  TORCH_CHECK(step >= 1, "Adam step counts from 1");
+  const float bc1 = 1.f - std::pow((float)b1, (float)step), bc2 = 1.f - std::pow((float)b2, (float)step);
+  sparse_adam_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      w, m, v, ids.data_ptr<int64_t>(), n, g.data_ptr<float>(), (int64_t)w.dim, (float)lr, (float)b1, (float)b2, (float)eps, bc1, bc2);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

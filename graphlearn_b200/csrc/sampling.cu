@@ -212,8 +212,10 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += 
 // host launchers
 // ---------------------------------------------------------------------------
 CsrView csr_from_desc(const at::Tensor& desc) {
-  TORCH_CHECK(desc.device().is_cpu() && desc.scalar_type() == at::kLong && desc.numel() == 1 + 6 * kMaxWorld,
-              "csr desc must be a CPU int64 tensor of 49 entries");
+  TORCH_CHECK(desc.device().is_cpu() && desc.scalar_type() == at::kLong &&
+                  (desc.numel() == 1 + 6 * kMaxWorld || desc.numel() == 1 + 7 * kMaxWorld),
+              "csr desc must be a CPU int64 tensor of 49 (or 57: + sorted rows) entries");
+  const bool has_sorted = desc.numel() == 1 + 7 * kMaxWorld;
   const int64_t* d = desc.data_ptr<int64_t>();
   CsrView g;
   g.world = (int)d[0];
@@ -225,6 +227,7 @@ CsrView csr_from_desc(const at::Tensor& desc) {
     g.eids.p[r] = reinterpret_cast<const void*>(d[1 + 3 * kMaxWorld + r]);
     g.cumw.p[r] = reinterpret_cast<const void*>(d[1 + 4 * kMaxWorld + r]);
     g.ts.p[r] = reinterpret_cast<const void*>(d[1 + 5 * kMaxWorld + r]);
+    g.sorted.p[r] = has_sorted ? reinterpret_cast<const void*>(d[1 + 6 * kMaxWorld + r]) : nullptr;
   }
   return g;
 }

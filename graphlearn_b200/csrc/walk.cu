@@ -9,7 +9,8 @@
 // current vertex on whichever GPU owns it (ld.global on the IPC-mapped peer
 // pointer over NVLink), so there is no per-step collective at all.  The
 // second-order bias uses rejection sampling; "is x a neighbour of the parent"
-// is a scan of the parent's row capped at `full_nbr_num` like the reference.
+// looks at the parent's first `full_nbr_num` neighbours like the reference: a binary search in the
+// id-sorted copy of the row (CsrView::sorted) when the whole row is inside the cap, a capped scan otherwise.
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -32,7 +33,7 @@ random_walk_kernel(const CsrView g, const int64_t* __restrict__ src, int64_t B, 
   int64_t cur = __ldg(src + b);
   int64_t prev = -1;
   RowRef prow;
-  prow.deg = 0; prow.beg = 0; prow.indices = nullptr;
+  prow.deg = 0; prow.beg = 0; prow.indices = nullptr; prow.sorted = nullptr;
   for (int step = 0; step < L; ++step) {
     RowRef r = csr_row(g, cur);
     int64_t nxt = default_id;
@@ -58,9 +59,15 @@ random_walk_kernel(const CsrView g, const int64_t* __restrict__ src, int64_t B, 
           if (x == prev) w = inv_p;
           else {
             bool nb = false;
-            int64_t lim = prow.deg < full_nbr_num ? prow.deg : full_nbr_num;
-            for (int64_t i = 0; i < lim; ++i)
-              if (__ldg(prow.indices + prow.beg + i) == x) { nb = true; break; }
+            if (prow.sorted != nullptr && prow.deg > 8 && prow.deg <= full_nbr_num) {
+              int64_t lo = 0, hi = prow.deg - 1;          // <= 7 dependent probes instead of up to 100
+              while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(prow.sorted + prow.beg + mid) < x) lo = mid + 1; else hi = mid; }
+              nb = __ldg(prow.sorted + prow.beg + lo) == x;
+            } else {
+              int64_t lim = prow.deg < full_nbr_num ? prow.deg : full_nbr_num;
+              for (int64_t i = 0; i < lim; ++i)
+                if (__ldg(prow.indices + prow.beg + i) == x) { nb = true; break; }
+            }
             w = nb ? 1.f : inv_q;
           }
           nxt = x;

@@ -98,3 +98,57 @@ class FileLoader(object):
             service.apply_updates(b.finish())
         self.batch_size = base_bs
         return n
+
+
+class GroupProducer(object):
+    """The data-loader SDK's producer (dataloader/include/dataloader/group_producer.h: ``AddVertex`` / ``AddEdge`` /
+    ``FlushAll`` batch records per DATA PARTITION and produce one Kafka message per full batch; ``dataloader.h``
+    ``SetBarrier``).  Here the sink is a :class:`~graphlearn_b200.dgs.workers.StreamingCluster` (its ingest ``LogChannel``
+    is the topic) or a plain service (``apply_updates``): records are grouped by the owner of their key, a partition's
+    builder is flushed when it holds ``max_batch_size`` records, and ``set_barrier`` marks "everything produced so far"
+    on the coordinator."""
+
+    def __init__(self, sink, max_batch_size: int = 4096, num_partitions: int = None):
+        self.sink, self.max_batch = sink, int(max_batch_size)
+        self.P = int(num_partitions or getattr(sink, "P", 1))
+        self.builders = [RecordBatchBuilder() for _ in range(self.P)]
+        self.produced = 0
+
+    def _part(self, key: int) -> int:
+        return abs(int(key)) % self.P
+
+    def add_vertex(self, vtype, vid, ts, feat):
+        p = self._part(vid)
+        self.builders[p].add_vertex(vtype, vid, ts, feat)
+        if self.builders[p].size >= self.max_batch:
+            self.flush(p)
+
+    def add_edge(self, etype, src, dst, ts, weight=1.0):
+        p = self._part(src)
+        self.builders[p].add_edge(etype, src, dst, ts, weight)
+        if self.builders[p].size >= self.max_batch:
+            self.flush(p)
+
+    def flush(self, p: int):
+        b = self.builders[p]
+        if b.size == 0:
+            return
+        n = b.size
+        batch = b.finish()
+        if hasattr(self.sink, "ingest") and hasattr(self.sink, "produced"):      # StreamingCluster: straight into the partition's log
+            self.sink.ingest.produce(p, batch, n)
+            self.sink.produced += n
+        elif hasattr(self.sink, "produce"):
+            self.sink.produce(batch)
+        else:
+            self.sink.apply_updates(batch)
+        self.produced += n
+
+    def flush_all(self):
+        for p in range(self.P):
+            self.flush(p)
+
+    def set_barrier(self, coordinator, name: str):
+        """flush, then ask the coordinator to report READY once everything produced so far is sampled and published"""
+        self.flush_all()
+        coordinator.set_barrier(name)

@@ -202,7 +202,15 @@ class FastSageTrainer:
         """Per-epoch seed order: the root traversal's permutation applied to this rank's vids once per epoch, so that a
         step only slices it (host work per step stays at a few microseconds)."""
         it = self._q_iter
-        if it.strategy == "shuffle":
+        th = getattr(self, "_q_thread", None)
+        if th is not None:
+            th.join()
+            self._q_thread = None
+        nxt = getattr(self, "_q_next", None)
+        self._q_next = None
+        if it.strategy == "shuffle" and nxt is not None and nxt[0] == it.epoch and it._perm is None:
+            it._perm, self._q_order = nxt[1], nxt[2]      # permutation of this epoch, prepared by the background thread
+        elif it.strategy == "shuffle":
             self._q_order = self._q_vids[it.prime()]
         elif it.strategy == "by_order":
             self._q_order = self._q_vids
@@ -220,7 +228,22 @@ class FastSageTrainer:
             return self.step(self._q_vids[it.next_index()])
         lo = it.cursor
         it.next_index()                                  # advances the cursor / raises OutOfRangeError at the epoch end
+        if it.strategy == "shuffle" and lo * 2 > it.n and getattr(self, "_q_thread", None) is None and getattr(self, "_q_next", None) is None:
+            self._q_prefetch_epoch(it.epoch + 1)         # randperm of millions of rows costs ~20 ms: off the step path
         return self.step(self._q_order[lo:lo + self.B])
+
+    def _q_prefetch_epoch(self, epoch: int):
+        """build the NEXT epoch's permutation (same generator seeding as SeedIterator) on a host thread"""
+        import threading
+        it = self._q_iter
+
+        def work():
+            g = torch.Generator()
+            g.manual_seed(it.seed * 1000003 + epoch)
+            perm = torch.randperm(it.n, generator=g)
+            self._q_next = (epoch, perm, self._q_vids[perm])
+        self._q_thread = threading.Thread(target=work, daemon=True)
+        self._q_thread.start()
 
     @property
     def epoch(self) -> int:

@@ -21,6 +21,8 @@ def random_walk(csr, src_vids: torch.Tensor, walk_len: int, p: float = 1.0, q: f
     src = src_vids.reshape(-1).to(torch.int64)
     rng = rng or _rng.default_rng(csr.rt)
     if csr.rt.is_cuda and cfg.use_peer_kernels:
+        if not (p == 1.0 and q == 1.0):
+            csr.ensure_sorted_rows()            # node2vec: binary-search membership in the parent's (id-sorted) row
         return native().random_walk(csr.desc, src, int(walk_len), float(p), float(q), int(cfg.default_neighbor_id),
                                     int(cfg.default_full_nbr_num), rng.state, int(salt))
     B = int(src.numel())

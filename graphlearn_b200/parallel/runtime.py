@@ -209,11 +209,14 @@ def _pad8(xs, fill=0):
     return xs + [fill] * (MAX_WORLD - len(xs))
 
 
-def make_csr_desc(world, nrows, indptr, indices, eids=None, cumw=None, ts=None) -> torch.Tensor:
-    """CPU int64[49] descriptor consumed by the sampling kernels (see csrc/sampling.cu)."""
+def make_csr_desc(world, nrows, indptr, indices, eids=None, cumw=None, ts=None, sorted_idx=None) -> torch.Tensor:
+    """CPU int64[49] descriptor consumed by the sampling kernels (see csrc/sampling.cu); 57 entries when the id-sorted
+    copy of the rows (``sorted_idx``, node2vec membership tests) is present."""
     z = [0] * world
     vals = [world] + _pad8(nrows) + _pad8(indptr) + _pad8(indices) + _pad8(eids or z) + \
         _pad8(cumw or z) + _pad8(ts or z)
+    if sorted_idx is not None:
+        vals += _pad8(sorted_idx)
     return torch.tensor(vals, dtype=torch.int64)
 
 

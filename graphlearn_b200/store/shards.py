@@ -459,13 +459,29 @@ class CsrShard:
         self.cumw_indeg = self.rt.symm_from(self._row_cumsum(w, self.indptr.local, self._row_of_edge))
         self._make_desc()
 
+    def ensure_sorted_rows(self):
+        """id-sorted copy of every adjacency row (same indptr), peer mapped: the walk kernel's node2vec membership test
+        becomes a binary search.  Collective (symmetric allocation); built once, on first use."""
+        if getattr(self, "sorted_idx", None) is None:
+            idx = self.indices.local
+            if idx.numel():
+                key = self._row_of_edge * (int(idx.max().item()) + 2) + (idx + 1)       # (row, dst) lexicographic
+                srt = idx[torch.argsort(key)]
+            else:
+                srt = idx.clone()
+            self.sorted_idx = self.rt.symm_from(srt)
+            self._make_desc()
+        return self.sorted_idx
+
     def _make_desc(self):
         W = self.rt.world
+        srt = getattr(self, "sorted_idx", None)
         self.desc = make_csr_desc(
             W, self.indptr.nrows and [n - 1 for n in self.indptr.nrows], self.indptr.ptrs, self.indices.ptrs,
             self.eids.ptrs if getattr(self, "eids", None) is not None else None,
             self.cumw.ptrs if self.cumw is not None else None,
-            self.ts.ptrs if self.ts is not None else None)
+            self.ts.ptrs if self.ts is not None else None,
+            srt.ptrs if srt is not None else None)
         if self.cumw_indeg is not None:
             self.desc_indeg = make_csr_desc(
                 W, [n - 1 for n in self.indptr.nrows], self.indptr.ptrs, self.indices.ptrs, None,

@@ -261,3 +261,31 @@ def test_streaming_cluster_subscriptions_match_single_store(tmp_path):
     cl2.pump()                                                             # replays the batch from the checkpointed offsets
     a, c = one.run_query(0, q), cl2.run_query(q)
     assert torch.equal(a["hops"][1]["ids"], c["hops"][1]["ids"]) and torch.equal(a["hops"][0]["ids"], c["hops"][0]["ids"])
+
+
+def test_group_producer_sdk(tmp_path):
+    """D13 data-loader SDK: per-partition batching into the cluster's ingest log + barrier through the coordinator"""
+    from graphlearn_b200.dgs import Coordinator, GroupProducer, StreamingCluster
+    schema = {"vertices": {"u": {"count": 8, "feat_dim": 0}, "i": {"count": 8, "feat_dim": 2}},
+              "edges": {"click": {"src": "u", "dst": "i"}}}
+    plan = QueryPlan("u").out("click", 2)
+    cl = StreamingCluster(schema, num_sampling=2, num_serving=1, sampling_devices=["cpu"] * 2, serving_devices=["cpu"])
+    cl.install_query(plan)
+    co = Coordinator(cl)
+    one = DynamicGraphService(schema, device="cpu")
+    one.install_query(0, plan)
+    gp = GroupProducer(cl, max_batch_size=5)
+    ref = GroupProducer(one, max_batch_size=1000, num_partitions=1)
+    rs = np.random.RandomState(0)
+    for t in range(37):
+        s, d = int(rs.randint(0, 12)), int(rs.randint(0, 9))
+        gp.add_edge("click", s, d, t); ref.add_edge("click", s, d, t)
+    assert cl.ingest.end_offset(0) + cl.ingest.end_offset(1) >= 6          # full batches were produced on the fly
+    gp.set_barrier(co, "all")
+    ref.flush_all()
+    assert gp.produced == 37 and cl.produced == 37 and co.barrier_status("all") == "PRODUCED"
+    cl.pump()
+    assert co.barrier_status("all") == "READY"
+    q = list(range(12))
+    a, c = one.run_query(0, q), cl.run_query(q)
+    assert torch.equal(a["hops"][0]["ids"], c["hops"][0]["ids"])

@@ -155,6 +155,81 @@ def test_id_filter(rt, graph):
                 assert (nb[b] != first[b].cpu()).all(), (strat, b)
 
 
+def test_timestamp_filter_kernel(rt):
+    """FILTER_TS on the kernel path: only edges with ts < bound are eligible (rows are ts-ascending), for every strategy."""
+    from graphlearn_b200.ops import sampling as S
+    from graphlearn_b200.store.shards import CsrShard
+    g = torch.Generator(device=rt.device).manual_seed(4)
+    n, E = 600, 12000
+    src = torch.randint(0, n, (E,), device=rt.device, generator=g)
+    dst = torch.randint(0, n, (E,), device=rt.device, generator=g)
+    ts = torch.randint(0, 1000, (E,), device=rt.device, generator=g)
+    csr = CsrShard.from_coo(rt, "e", "v", "v", src, dst, n, ts=ts)
+    ip, idx, tsl = csr.indptr.local.cpu(), csr.indices.local.cpu(), csr.ts.local.cpu()
+    q = torch.arange(0, n, device=rt.device)
+    bound = torch.randint(0, 1000, (n,), device=rt.device, generator=g)
+    for strat in ("random", "random_without_replacement", "topk"):
+        nbr, eid = S.sample_neighbors(csr, q, 5, strat, filter_mode=S.FILTER_TS, filter_values=bound)
+        nb, ei, bd = nbr.cpu(), eid.cpu(), bound.cpu()
+        for b in range(n):
+            a, e = int(ip[b]), int(ip[b + 1])
+            ok = [(int(idx[p]), p) for p in range(a, e) if int(tsl[p]) < int(bd[b])]
+            if not ok:
+                assert (nb[b] == 0).all(), (strat, b)                    # default neighbour id
+                continue
+            allowed = {v for v, _ in ok}
+            assert all(int(x) in allowed for x in nb[b]), (strat, b)
+            assert all(a <= int(p) < e and int(tsl[int(p)]) < int(bd[b]) for p in ei[b] if int(p) >= 0), (strat, b)
+            if strat == "random_without_replacement" and len(ok) >= 5:
+                assert len(set(ei[b].tolist())) == 5, b
+
+
+def test_in_degree_strategy_distribution(rt):
+    """strategy 'in_degree': neighbour j of a row is drawn with probability ~ in-degree(dst_j) (chi-square)."""
+    from graphlearn_b200.ops import sampling as S
+    from graphlearn_b200.store.shards import CsrShard
+    n = 64
+    # vertex 0 points at 1..8; the in-degree of target t is made t (other sources point at it t - 1 more times)
+    src, dst = [0] * 8, list(range(1, 9))
+    for t in range(1, 9):
+        src += [10 + i for i in range(t - 1)]
+        dst += [t] * (t - 1)
+    src_t, dst_t = torch.tensor(src, device=rt.device), torch.tensor(dst, device=rt.device)
+    csr = CsrShard.from_coo(rt, "e", "v", "v", src_t, dst_t, n)
+    indeg = torch.bincount(dst_t, minlength=n)
+    csr.set_indegree_weights(indeg[csr.indices.local])
+    draws = 40000
+    nbr, _ = S.sample_neighbors(csr, torch.zeros(draws // 8, dtype=torch.int64, device=rt.device), 8, "in_degree")
+    cnt = torch.bincount(nbr.reshape(-1).cpu(), minlength=9)[1:9].double()
+    assert int(cnt.sum()) == draws
+    expect = torch.arange(1, 9).double() / 36.0 * draws
+    chi2 = float(((cnt - expect) ** 2 / expect).sum())
+    assert chi2 < 24.3, (chi2, cnt.tolist())          # 7 d.o.f., p = 0.001
+
+
+def test_node2vec_bias_distribution(rt):
+    """second step of a node2vec walk on a small graph: return / common-neighbour / outward candidates are taken with
+    probabilities ~ 1/p : 1 : 1/q (rejection sampling in the walk kernel)."""
+    from graphlearn_b200.ops import walk as WK
+    from graphlearn_b200.store.shards import CsrShard
+    # 0 -> 1 ; 1 -> {0 (return), 2 (also a neighbour of 0: distance 1), 3 (distance 2)} ; 0 -> 2 as well
+    edges = [(0, 1), (0, 2), (1, 0), (1, 2), (1, 3), (2, 0), (3, 1)]
+    src = torch.tensor([e[0] for e in edges], device=rt.device)
+    dst = torch.tensor([e[1] for e in edges], device=rt.device)
+    csr = CsrShard.from_coo(rt, "e", "v", "v", src, dst, 4)
+    p, q = 0.25, 4.0
+    walks = WK.random_walk(csr, torch.zeros(60000, dtype=torch.int64, device=rt.device), 2, p, q).cpu()
+    via1 = walks[walks[:, 0] == 1]
+    assert via1.size(0) > 20000
+    cnt = torch.bincount(via1[:, 1], minlength=4).double()
+    w = torch.tensor([1.0 / p, 0.0, 1.0, 1.0 / q]).double()          # to 0 (return), -, to 2 (common), to 3 (outward)
+    expect = w / w.sum() * via1.size(0)
+    assert cnt[1] == 0
+    m = expect > 0
+    chi2 = float((((cnt - expect) ** 2)[m] / expect[m]).sum())
+    assert chi2 < 13.8, (chi2, cnt.tolist(), expect.tolist())          # 2 d.o.f., p = 0.001
+
+
 def test_gather_rows_and_agg(rt, graph):
     from graphlearn_b200.ops import gather as G
     nodes, csr = graph
@@ -572,6 +647,40 @@ def test_sharded_embedding_gpu(rt):
     w1 = emb.local_weight()
     assert torch.allclose(w1[3], w0[3] - 0.2, atol=1e-6) and torch.allclose(w1[10], w0[10] - 0.1, atol=1e-6)
     assert torch.equal(w1[11], w0[11])
+
+
+def _lazy_adam_reference(w, steps, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """Adam applied to the touched rows only, duplicates summed, global step for the bias correction"""
+    w = w.clone().double()
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    for t, (ids, g) in enumerate(steps, 1):
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        gs = torch.zeros(uniq.numel(), w.size(1), dtype=torch.float64).index_add_(0, inv, g.double())
+        m[uniq] = b1 * m[uniq] + (1 - b1) * gs
+        v[uniq] = b2 * v[uniq] + (1 - b2) * gs * gs
+        w[uniq] -= lr / (1 - b1 ** t) * m[uniq] / (v[uniq].sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+    return w.float()
+
+
+def test_sharded_embedding_sparse_adam_kernel(rt):
+    """K9: sparse_adam_rows_kernel (touched rows of weight + moment tables updated in place) vs a lazy-Adam reference"""
+    from graphlearn_b200 import nn as glnn
+    emb = glnn.ShardedEmbedding(rt, 500, 24, lr=0.01, optimizer="adam")
+    w0 = emb.local_weight().clone().cpu()
+    g = torch.Generator().manual_seed(2)
+    steps = []
+    for _ in range(6):
+        ids = torch.randint(0, 500, (64,), generator=g)
+        grad = torch.randn(64, 24, generator=g)
+        steps.append((ids, grad))
+        out = emb(ids.to(rt.device))
+        out.backward(grad.to(rt.device))
+    ref = _lazy_adam_reference(w0, steps, 0.01)
+    assert torch.allclose(emb.local_weight().cpu(), ref, rtol=1e-4, atol=1e-6), float((emb.local_weight().cpu() - ref).abs().max())
+    untouched = torch.ones(500, dtype=torch.bool)
+    for ids, _ in steps:
+        untouched[ids] = False
+    assert torch.equal(emb.local_weight().cpu()[untouched], w0[untouched])
 
 
 def test_relabel_hash_table_kernel(rt):

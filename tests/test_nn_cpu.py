@@ -222,6 +222,29 @@ def test_sharded_embedding_sparse_sgd():
     assert torch.allclose(w1[1], w0[1] - 0.5) and torch.allclose(w1[2], w0[2] - 1.0) and torch.allclose(w1[3], w0[3])
 
 
+
+def test_sharded_embedding_sparse_adam_cpu():
+    """portable path of the sparse Adam update (touched rows only, duplicates summed, global-step bias correction)"""
+    import torch
+    from graphlearn_b200 import nn as glnn
+    from graphlearn_b200.parallel.runtime import init
+    rt = init(device="cpu")
+    emb = glnn.ShardedEmbedding(rt, 50, 8, lr=0.01, optimizer="adam")
+    w = emb.local_weight().clone().double()
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    g = torch.Generator().manual_seed(1)
+    for t in range(1, 6):
+        ids = torch.randint(0, 50, (16,), generator=g)
+        grad = torch.randn(16, 8, generator=g)
+        emb(ids).backward(grad)
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        gs = torch.zeros(uniq.numel(), 8, dtype=torch.float64).index_add_(0, inv, grad.double())
+        m[uniq] = 0.9 * m[uniq] + 0.1 * gs
+        v[uniq] = 0.999 * v[uniq] + 0.001 * gs * gs
+        w[uniq] -= 0.01 / (1 - 0.9 ** t) * m[uniq] / (v[uniq].sqrt() / (1 - 0.999 ** t) ** 0.5 + 1e-8)
+    assert torch.allclose(emb.local_weight(), w.float(), rtol=1e-4, atol=1e-6)
+
+
 def test_pyg_style_loader_and_cluster_helpers(tmp_path):
     """P8: TorchDataset + induce_func -> list of subgraphs -> PyGDataLoader -> collated Batch."""
     import graphlearn_b200 as gl

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/o_tests.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/o_tests.log
+timeout 600 python bench.py --steps 6000 --warmup 20 --no-secondary > gpurun_out/o_bench1.log 2>&1; tail -1 gpurun_out/o_bench1.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value', d['value'], 'e2e', d['e2e']['value'])"
