@@ -184,7 +184,7 @@ def build_trainer(args, rt, shape, feature_dtype, cache_rows_arg):
             q = q.outV("e").sample(k).by("random").alias("h%d" % (i + 1))
         q = q.values()
     else:
-        fdt = torch.bfloat16 if feature_dtype == "bf16" else torch.float32
+        fdt = {"bf16": torch.bfloat16, "fp8": torch.float8_e4m3fn}.get(feature_dtype, torch.float32)
         nodes, csr = make_sharded_graph(rt, feature_dtype=fdt, seed=0, **shape)
     # N17 replica cache of remote feature rows in local HBM (the reference's set_local_node_cache_capacity, default 0 =
     # off there and here): -1 = as many remote rows as fit in 25% of the free HBM
@@ -298,7 +298,9 @@ def run_ours(args):
     ms_dev, ms_e2e, final_loss = time_trainer(args, rt, tr, nodes, args.steps, clocks)
     clk = clocks.stop() if clocks else None
     own, lib, names = count_own_launches(tr)
-    row_bytes = int(nodes.feats.local.size(1)) * nodes.feats.local.element_size()
+    # payload bytes of a feature row (the 128-byte aligned stride adds padding that is never read)
+    row_bytes = (nodes.float_dim + 2 * ((nodes.float_dim + 31) // 32)) if nodes.feats.local.dtype == torch.uint8 \
+        else nodes.float_dim * nodes.feats.local.element_size()
     rows_per_step, m_ = 0, args.batch
     for k_ in FANOUTS:                      # layer 1 gathers (1 + k_i) rows per destination of every hop pair
         rows_per_step += m_ * (1 + k_)
@@ -321,19 +323,22 @@ def run_ours(args):
                                       "steps": sec_steps}
         del tr2, nodes2
     elif W == 1 and not args.no_secondary:
-        other = "fp32" if args.feature_dtype == "bf16" else "bf16"
         del tr
         torch.cuda.empty_cache()
-        tr2, nodes2, _, _, _, _ = build_trainer(args, rt, shape, other, 0)
-        d2, e2, _ = time_trainer(args, rt, tr2, nodes2, sec_steps)
-        extra["%s_feature_rows_run" % other] = {"what": "same job with %s feature rows in HBM (compute stays bf16)" % other,
-                                                "value": sec_steps / (d2 / 1e3), "e2e_value": sec_steps / (e2 / 1e3),
-                                                "unit": "steps/s", "steps": sec_steps}
-        del tr2, nodes2
+        for other in [o for o in ("fp32", "bf16", "fp8") if o != args.feature_dtype]:
+            what = ("same job with %s feature rows in HBM (compute stays bf16)" % other) if other != "fp8" else \
+                "same job with fp8 (e4m3, one bf16 scale per 32 elements) feature rows - storage precision BELOW the reference's: " \
+                "capacity / bandwidth data point, never the headline"
+            tr2, nodes2, _, _, _, _ = build_trainer(args, rt, shape, other, 0)
+            d2, e2, _ = time_trainer(args, rt, tr2, nodes2, sec_steps)
+            extra["%s_feature_rows_run" % other] = {"what": what, "value": sec_steps / (d2 / 1e3), "e2e_value": sec_steps / (e2 / 1e3),
+                                                    "unit": "steps/s", "steps": sec_steps}
+            del tr2, nodes2
+            torch.cuda.empty_cache()
     if rt.rank == 0:
         steps_per_s = W * args.steps / (ms_dev / 1e3)
         e2e_steps_per_s = W * args.steps / (ms_e2e / 1e3)
-        fbytes = 2 if args.feature_dtype == "bf16" else 4
+        fbytes = {"bf16": 2, "fp8": 1}.get(args.feature_dtype, 4)
         out = {
             "metric": args.cfg["metric"],
             "value": steps_per_s, "unit": "steps/s", "n_gpus": W, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -606,7 +611,7 @@ def main():
     ap.add_argument("--config", default="products_sage2", choices=sorted(CONFIGS),
                     help="BASELINE.json config: products_sage2 (headline, default) | sage3 | deepwalk | taobao_gat")
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--feature-dtype", default="bf16", choices=["fp32", "bf16"],
+    ap.add_argument("--feature-dtype", default="bf16", choices=["fp32", "bf16", "fp8"],
                     help="HBM storage dtype of the float attribute table (compute is bf16 either way; bf16 halves NVLink bytes)")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-graph", action="store_true")

@@ -62,7 +62,7 @@ class Config:
     server_count: int = 1
     server_hosts: str = ""
     # --- B200 engine specific
-    feature_dtype: str = "fp32"          # fp32 | bf16   storage dtype of float attribute tables in HBM
+    feature_dtype: str = "fp32"          # fp32 | bf16 | fp8 (e4m3, bf16 scale per 32 elements)   storage of float tables in HBM
     loader_threads: int = 0           # 0 = auto: all cores divided by the number of ranks on the box
     use_peer_kernels: bool = True        # False -> torch.distributed (NCCL/gloo) baseline path
     feature_row_align: int = 128         # bytes: feature rows wider than half of this start on such a boundary (16 = dense rows)

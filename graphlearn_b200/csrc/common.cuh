@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace glb {
@@ -180,6 +181,19 @@ __device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ uint32_t ld_nc_u16(const uint16_t* p) {
+  uint16_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return (uint32_t)r;
+}
+// two e4m3 values (low byte first) -> fp32 pair
+__device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t two_bytes) {
+  uint32_t h2;
+  const uint16_t in = (uint16_t)two_bytes;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(in));
+  return __half22float2(*reinterpret_cast<__half2*>(&h2));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

@@ -23,9 +23,15 @@ enum AggMode : int { kSum = 0, kMean = 1, kMax = 2, kMin = 3, kProd = 4 };
 
 // load 4 consecutive features [4c, 4c+4) of a row as fp32
 template <int DTYPE>
-__device__ __forceinline__ float4 load4(const void* row, int c) {
+__device__ __forceinline__ float4 load4(const void* row, int c, int scale_off = 0) {
   if constexpr (DTYPE == 0) {
     return ld_nc_f4(reinterpret_cast<const float4*>(row) + c);
+  } else if constexpr (DTYPE == 2) {
+    // fp8 block-scaled row: 4 e4m3 bytes + the bf16 scale of their 32-element block
+    const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(row) + c);
+    const float s = __uint_as_float(ld_nc_u16(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(row) + scale_off) + (c >> 3)) << 16);
+    const float2 a = e4m3x2_to_float2(q), b = e4m3x2_to_float2(q >> 16);
+    return make_float4(a.x * s, a.y * s, b.x * s, b.y * s);
   } else {
     uint2 u = ld_nc_u2(reinterpret_cast<const uint2*>(row) + c);
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
@@ -38,7 +44,7 @@ __device__ __forceinline__ const void* row_ptr(const TableView& t, int64_t vid) 
   int owner = (int)(vid % t.world);
   int64_t row = vid / t.world;
   if (row >= t.nrows[owner]) return nullptr;
-  size_t esz = t.dtype == 0 ? 4 : 2;
+  size_t esz = (size_t)table_esize(t.dtype);
   if (t.cmap != nullptr && owner != t.self) {   // replica cache of remote rows (read paths only)
     const int s = __ldg(t.cmap + vid);
     if (s >= 0) return t.cbase + (size_t)s * (size_t)t.stride * esz;
@@ -82,8 +88,9 @@ gather_rows_kernel(const TableView t, const int64_t* __restrict__ vids, int64_t 
   const void* rp = row_ptr(t, __ldg(vids + w));
   int chunks = (t.dim + 3) >> 2;
   OutT* o = out + w * out_stride;
+  const int soff = fp8_scale_offset(t.dim);
   for (int c = lane; c < chunks; c += 32) {
-    float4 v = rp ? load4<DTYPE>(rp, c) : make_float4(fill, fill, fill, fill);
+    float4 v = rp ? load4<DTYPE>(rp, c, soff) : make_float4(fill, fill, fill, fill);
     store4<OutT>(o, c, t.dim, v);
   }
 }
@@ -183,7 +190,9 @@ at::Tensor gather_rows(const at::Tensor& table_desc, const at::Tensor& vids, boo
   const int64_t* vp = v.data_ptr<int64_t>();
 #define LAUNCH(DT, OT, optr) \
   gather_rows_kernel<DT, OT><<<blocks, 256, 0, stream>>>(t, vp, n, optr, (int64_t)t.dim, (float)fill)
-  if (t.dtype == 0 && !out_bf16) LAUNCH(0, float, out.data_ptr<float>());
+  if (t.dtype == 2 && !out_bf16) LAUNCH(2, float, out.data_ptr<float>());
+  else if (t.dtype == 2) LAUNCH(2, __nv_bfloat16, reinterpret_cast<__nv_bfloat16*>(out.data_ptr()));
+  else if (t.dtype == 0 && !out_bf16) LAUNCH(0, float, out.data_ptr<float>());
   else if (t.dtype == 0 && out_bf16) LAUNCH(0, __nv_bfloat16, reinterpret_cast<__nv_bfloat16*>(out.data_ptr()));
   else if (t.dtype == 1 && !out_bf16) LAUNCH(1, float, out.data_ptr<float>());
   else LAUNCH(1, __nv_bfloat16, reinterpret_cast<__nv_bfloat16*>(out.data_ptr()));
@@ -197,6 +206,7 @@ at::Tensor gather_agg(const at::Tensor& table_desc, const at::Tensor& vids,
   check_cuda_i64(vids, "vids");
   c10::cuda::CUDAGuard guard(vids.device());
   TableView t = table_from_desc(table_desc);
+  TORCH_CHECK(t.dtype != 2, "gather_agg: fp8 tables are served by gather_rows and the fused layer kernel");
   auto v = vids.contiguous();
   int64_t S;
   const int64_t* op = nullptr;

@@ -36,6 +36,31 @@ template <> struct Chunk<1> {
   }
 };
 
+// fp8 (e4m3) rows with one bf16 scale per 32-element block: a chunk is 8 elements = 8 bytes + the block's scale
+template <> struct Chunk<2> {
+  static constexpr int kVec = 8;
+  uint2 v;
+  float s;
+  __device__ __forceinline__ void load_row(const char* row, int chunk, int scale_off) {
+    v = ld_nc_u2(reinterpret_cast<const uint2*>(row) + chunk);
+    s = __uint_as_float(ld_nc_u16(reinterpret_cast<const uint16_t*>(row + scale_off) + (chunk >> 2)) << 16);
+  }
+  __device__ __forceinline__ void add_to(float (&a)[8]) const {
+    float2 x;
+    x = e4m3x2_to_float2(v.x);       a[0] = fmaf(x.x, s, a[0]); a[1] = fmaf(x.y, s, a[1]);
+    x = e4m3x2_to_float2(v.x >> 16); a[2] = fmaf(x.x, s, a[2]); a[3] = fmaf(x.y, s, a[3]);
+    x = e4m3x2_to_float2(v.y);       a[4] = fmaf(x.x, s, a[4]); a[5] = fmaf(x.y, s, a[5]);
+    x = e4m3x2_to_float2(v.y >> 16); a[6] = fmaf(x.x, s, a[6]); a[7] = fmaf(x.y, s, a[7]);
+  }
+};
+
+// uniform loader: 16-byte chunk `chunk` of a fp32 / bf16 row, or 8-element chunk + block scale of an fp8 row
+template <int DT>
+__device__ __forceinline__ void load_chunk(Chunk<DT>& c, const char* row, int chunk, int scale_off) {
+  if constexpr (DT == 2) c.load_row(row, chunk, scale_off);
+  else c.load(row + (size_t)chunk * 16);
+}
+
 // locator of a table row packed into 32 bits: (row << 3) | owner, 0xFFFFFFFF = missing
 __device__ __forceinline__ uint32_t make_loc(const TableView& t, int64_t vid, int wshift) {
   if (vid < 0) return 0xFFFFFFFFu;

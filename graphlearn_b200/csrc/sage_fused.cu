@@ -450,8 +450,10 @@ __global__ void __launch_bounds__((EW + 1 + GW) * 32, 1) sage_persist_kernel(con
     const bool has_self = p.kp_self > 0;
     const bool has_nbr = p.kp_nbr > 0;
     const bool need_self = has_self || p.mode == kGcnMean;
-    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * (DT == 0 ? 4u : 2u);
-    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * (DT == 0 ? 4u : 2u);
+    constexpr uint32_t kEsz = DT == 0 ? 4u : DT == 1 ? 2u : 1u;
+    const uint32_t nbr_row_bytes = (uint32_t)p.tnbr.stride * kEsz;
+    const uint32_t self_row_bytes = (uint32_t)p.tself.stride * kEsz;
+    const int soff_self = fp8_scale_offset(d_self), soff_nbr = fp8_scale_offset(d_nbr);     // fp8 rows: where the block scales start
     const char** scr = sScr + gw * kScrCap;
     const int n_tiles_cta = (p.total_tiles - tile_first + tile_stride - 1) / tile_stride;
 
@@ -501,7 +503,6 @@ __global__ void __launch_bounds__((EW + 1 + GW) * 32, 1) sage_persist_kernel(con
       const bool row_ok = r < cur.rows;
       const int chunk = gg.lig + 32 * sl;                 // this lane's 16-byte chunk of the row
       const int f0 = chunk * VEC;                         // first feature of the chunk
-      const size_t coff = (size_t)chunk * 16;
       float acc[VEC], sv[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; sv[i] = 0.f; }
@@ -511,20 +512,20 @@ __global__ void __launch_bounds__((EW + 1 + GW) * 32, 1) sage_persist_kernel(con
         const char* const* ptrs = scr + gg.sub * (k + 1);
         const bool self_ld = need_self && f0 < d_self;
         Chunk<DT> sraw;
-        if (self_ld) sraw.load(ptrs[k] + coff);
+        if (self_ld) load_chunk<DT>(sraw, ptrs[k], chunk, soff_self);
         if (has_nbr && f0 < d_nbr) {
           int j0 = 0;
           for (; j0 + U <= k; j0 += U) {                  // full batches: U unconditional loads, then U adds
             Chunk<DT> raw[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) raw[u].load(ptrs[j0 + u] + coff);
+            for (int u = 0; u < U; ++u) load_chunk<DT>(raw[u], ptrs[j0 + u], chunk, soff_nbr);
 #pragma unroll
             for (int u = 0; u < U; ++u) raw[u].add_to(acc);
           }
           if (j0 < k) {                                   // remainder batch (k % U rows)
             Chunk<DT> raw[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) raw[u].load(ptrs[j0 + u < k ? j0 + u : k - 1] + coff);
+            for (int u = 0; u < U; ++u) load_chunk<DT>(raw[u], ptrs[j0 + u < k ? j0 + u : k - 1], chunk, soff_nbr);
 #pragma unroll
             for (int u = 0; u < U; ++u)
               if (j0 + u < k) raw[u].add_to(acc);
@@ -740,17 +741,20 @@ static void launch_persist(SageParams& p, size_t smem, cudaStream_t stream) {
     sage_persist_kernel<UU, DD, EW, GW><<<grid, (EW + 1 + GW) * 32, smem, stream>>>(p);                    \
   } while (0)
 #define LAUNCH_DT(UU, EW, GW) do { if (dt == 0) LAUNCH(UU, 0, EW, GW); else LAUNCH(UU, 1, EW, GW); } while (0)
+#define LAUNCH_DT3(UU, EW, GW) do { if (dt == 2) LAUNCH(UU, 2, EW, GW); else LAUNCH_DT(UU, EW, GW); } while (0)
+  TORCH_CHECK(dt != 2 || g_variant == 2, "fp8 feature rows are built for the default role layout only");
   if (g_variant == 1) {
     // 512 threads x 128 registers: a whole neighbour list (or half of a long one) in flight per lane
     const int u = kmax <= 5 ? 5 : kmax <= 10 ? 10 : 13;
     if (u == 5) LAUNCH_DT(5, 4, 11); else if (u == 10) LAUNCH_DT(10, 4, 11); else LAUNCH_DT(13, 4, 11);
   } else if (g_variant == 2) {
     const int u = kmax <= 4 ? 4 : (kmax % 5 == 0 || kmax > 12) ? 5 : 6;
-    if (u == 4) LAUNCH_DT(4, 4, 19); else if (u == 5) LAUNCH_DT(5, 4, 19); else LAUNCH_DT(6, 4, 19);
+    if (u == 4) LAUNCH_DT3(4, 4, 19); else if (u == 5) LAUNCH_DT3(5, 4, 19); else LAUNCH_DT3(6, 4, 19);
   } else {
     const int u = kmax <= 4 ? 4 : (kmax % 5 == 0 || kmax > 12) ? 5 : 6;
     if (u == 4) LAUNCH_DT(4, 8, 23); else if (u == 5) LAUNCH_DT(5, 8, 23); else LAUNCH_DT(6, 8, 23);
   }
+#undef LAUNCH_DT3
 #undef LAUNCH_DT
 #undef LAUNCH
   C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -799,10 +803,9 @@ void sage_fused_multi(const at::Tensor& tself_desc, const at::Tensor& tnbr_desc,
   TORCH_CHECK((reinterpret_cast<uintptr_t>(w_img.data_ptr()) & 15) == 0, "weight image must be 16 B aligned");
   const size_t smem = (size_t)sage_smem_bytes(k_total, N);
   TORCH_CHECK(smem <= kSmemLimit, "tile does not fit in shared memory (", smem, " B); use the unfused path");
-  TORCH_CHECK(p.tself.dtype == p.tnbr.dtype && (p.tself.dtype == 0 || p.tself.dtype == 1),
-              "fused SAGE layer needs fp32 or bf16 self / neighbour tables of the same dtype");
+  TORCH_CHECK(p.tself.dtype == p.tnbr.dtype, "fused SAGE layer needs self / neighbour tables of the same storage dtype");
   TORCH_CHECK(p.kp_self == 0 || p.kp_nbr == 0 || p.kp_self == p.kp_nbr, "fused SAGE layer needs equally padded self / neighbour dims");
-  TORCH_CHECK((p.tself.stride * (p.tself.dtype == 0 ? 4 : 2)) % 16 == 0 && (p.tnbr.stride * (p.tnbr.dtype == 0 ? 4 : 2)) % 16 == 0,
+  TORCH_CHECK((p.tself.stride * table_esize(p.tself.dtype)) % 16 == 0 && (p.tnbr.stride * table_esize(p.tnbr.dtype)) % 16 == 0,
               "table rows must be 16-byte aligned (stride multiple of 4 fp32 / 8 bf16 elements)");
   {
     const int vec = p.tnbr.dtype == 0 ? 4 : 8;

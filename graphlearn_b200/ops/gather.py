@@ -42,6 +42,11 @@ def gather_rows(rt: Runtime, st: SymmTensor, desc: Optional[torch.Tensor], vids:
     v = vids.reshape(-1).to(torch.int64)
     if rt.is_cuda and _config.get().use_peer_kernels and desc is not None:
         return native().gather_rows(desc, v, out_dtype == torch.bfloat16, float(fill))
+    if st.local.dtype == torch.uint8:
+        # fp8 block-scaled table on the portable path: fetch the raw byte rows, dequantise here
+        from ..store.shards import NodeTable
+        (raw,) = part.remote_apply(v, lambda x: (_local_rows(st, x, rt.world, 0),), rt.world)
+        return NodeTable.dequantize_fp8_rows(raw, dim).to(out_dtype)
     cmap = getattr(st, "cache_map", None)
     if cmap is not None and rt.world > 1:
         # replica cache (N17): hits are served from local HBM, only misses travel

@@ -187,7 +187,9 @@ def sage_layer(weight_p: torch.Tensor, bias: Optional[torch.Tensor], *, k: int, 
     dt_self = x_self.dtype if x_self is not None else self_table.feats.local.dtype
     dt_nbr = x_nbr.dtype if x_nbr is not None else nbr_table.feats.local.dtype
     kp_s, kp_n = padded_dims(d_self, d_nbr, mode)
-    compatible = dt_self == dt_nbr and dt_self in (torch.float32, torch.bfloat16) and (kp_s == 0 or kp_s == kp_n)
+    # torch.uint8 = fp8 block-scaled table storage (store/shards.py): only as (table, vids) operands
+    ok_dt = (torch.float32, torch.bfloat16) + ((torch.uint8,) if x_self is None and x_nbr is None else ())
+    compatible = dt_self == dt_nbr and dt_self in ok_dt and (kp_s == 0 or kp_s == kp_n)
     if use_cuda and compatible and fused_supported(d_self, d_nbr, weight_p.size(0), mode, k, dt_self):
         return _SageFusedFn.apply(weight_p, bias, x_self, x_nbr,
                                   None if self_table is None else self_table.feat_desc, self_vids,

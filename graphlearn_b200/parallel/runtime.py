@@ -223,7 +223,8 @@ def make_csr_desc(world, nrows, indptr, indices, eids=None, cumw=None, ts=None, 
 def make_table_desc(world, dim, stride, dtype, nrows, ptrs, cache=None) -> torch.Tensor:
     """CPU int64[20] descriptor of a row-sharded dense table (see csrc/host_utils.h);
     ``cache=(rank, cache_map_ptr, cache_rows_ptr)`` appends the replica-cache triple (23 entries)."""
-    code = 0 if dtype == torch.float32 else 1
+    # 2 = fp8 e4m3 block-scaled rows (byte table; `stride` counts bytes, see csrc/host_utils.h)
+    code = 0 if dtype == torch.float32 else 2 if dtype in (torch.float8_e4m3fn, torch.uint8) else 1
     vals = [world, dim, stride, code] + _pad8(nrows) + _pad8(ptrs)
     if cache is not None:
         vals += [int(cache[0]), int(cache[1]), int(cache[2])]

@@ -180,7 +180,7 @@ class GraphStore(object):
         rt, W, r = self.rt, self.rt.world, self.rt.rank
         dev = rt.device
         cfg = _config.get()
-        fdt = torch.bfloat16 if cfg.feature_dtype == "bf16" else torch.float32
+        fdt = {"bf16": torch.bfloat16, "fp8": torch.float8_e4m3fn}.get(cfg.feature_dtype, torch.float32)
         # ---- load + keep what this rank owns
         # File sources: every rank parses 1/W of the bytes and one all-to-all-v per column moves the
         # rows to their owners (N10 + C4).  In-memory sources are identical on every rank -> filter.

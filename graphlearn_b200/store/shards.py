@@ -176,10 +176,59 @@ class NodeTable:
     def nrows(self):
         return self.idmap.nrows
 
+    FP8_BLOCK = 32
+
+    @staticmethod
+    def quantize_fp8_rows(x: torch.Tensor, stride: int) -> torch.Tensor:
+        """fp32 [n, d] -> uint8 [n, stride] rows ``[d e4m3 bytes | pad to 16][one bf16 scale per 32 elements][pad]`` with
+        value = q * scale and scale = bf16(amax(block) / 448) (448 = largest e4m3 magnitude)."""
+        n, d = int(x.size(0)), int(x.size(1))
+        B = NodeTable.FP8_BLOCK
+        nb = (d + B - 1) // B
+        xp = torch.zeros(n, nb * B, dtype=torch.float32, device=x.device)
+        xp[:, :d] = x.float()
+        blocks = xp.view(n, nb, B)
+        scale = (blocks.abs().amax(2) / 448.0).to(torch.bfloat16)
+        scale = torch.where(scale.float() > 0, scale, torch.ones_like(scale))
+        # the bf16 rounding of the scale may push |x / scale| just above 448: clamp before the cast (e4m3fn has no inf)
+        q = (blocks / scale.float().unsqueeze(2)).clamp_(-448.0, 448.0).to(torch.float8_e4m3fn)
+        out = torch.zeros(n, stride, dtype=torch.uint8, device=x.device)
+        out[:, :d] = q.view(n, nb * B)[:, :d].view(torch.uint8)
+        soff = _round_up(d, 16)
+        out[:, soff:soff + 2 * nb] = scale.contiguous().view(torch.uint8).view(n, 2 * nb)
+        return out
+
+    @staticmethod
+    def dequantize_fp8_rows(t: torch.Tensor, d: int) -> torch.Tensor:
+        """uint8 [n, stride] fp8 rows -> fp32 [n, d]"""
+        B = NodeTable.FP8_BLOCK
+        nb = (d + B - 1) // B
+        soff = _round_up(d, 16)
+        q = t[:, :d].contiguous().view(torch.float8_e4m3fn).float()
+        scale = t[:, soff:soff + 2 * nb].contiguous().view(torch.bfloat16).float()
+        return q * scale.repeat_interleave(B, dim=1)[:, :d]
+
+    def dequantize_local(self, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 values of (a subset of) the local rows of an fp8 table - oracle / portable path"""
+        return NodeTable.dequantize_fp8_rows(self.feats.local if rows is None else self.feats.local[rows], self.float_dim)
+
     def set_float(self, x: torch.Tensor, dtype: torch.dtype = torch.float32):
-        """x: [n_local, d] on the runtime device."""
+        """x: [n_local, d] on the runtime device.  dtype: torch.float32 / torch.bfloat16 / torch.float8_e4m3fn (block-scaled
+        fp8 storage: half the bytes of bf16 - read by the fused layer kernel and by lookups, dequantised on the fly)."""
         d = int(x.size(1))
         self.float_dim = d
+        if dtype == torch.float8_e4m3fn:
+            nb = (d + NodeTable.FP8_BLOCK - 1) // NodeTable.FP8_BLOCK
+            stride = _round_up(_round_up(d, 16) + 2 * nb, 16)
+            align = int(getattr(_config.get(), "feature_row_align", 128))
+            if align > 16 and stride > align // 2:
+                stride = _round_up(stride, align)
+            st = self.rt.symm_empty((self.n_local, stride), torch.uint8)
+            st.local.copy_(NodeTable.quantize_fp8_rows(x, stride))
+            self.feats = st
+            self.rt.barrier()
+            self.feat_desc = make_table_desc(self.rt.world, d, stride, torch.float8_e4m3fn, st.nrows, st.ptrs)
+            return
         esz = 4 if dtype == torch.float32 else 2
         stride = _round_up(max(d, 1), 16 // esz)
         # rows wider than one 128-byte line start on a line boundary: a 200-byte row then touches exactly 2 lines instead
@@ -210,6 +259,8 @@ class NodeTable:
         rt, W = self.rt, self.rt.world
         if W == 1 or self.feats is None or capacity <= 0:
             return 0
+        if self.feats.local.dtype == torch.uint8:
+            raise NotImplementedError("the replica cache copies rows through the float gather: not wired for fp8 tables yet")
         dev = rt.device
         max_vid = max(int(n) for n in self.nrows) * W
         vid = torch.arange(max_vid, device=dev, dtype=torch.int64)

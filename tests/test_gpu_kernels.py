@@ -327,6 +327,62 @@ def test_sage_fused_exact_rows(rt, M, k, d, n_out, dtype):
     assert torch.equal(y, ref), float((y - ref).abs().max())
 
 
+@pytest.mark.parametrize("d,k,M", [(100, 10, 3000), (64, 25, 500), (37, 3, 77)])
+def test_fp8_block_scaled_feature_rows(rt, d, k, M):
+    """fp8 (e4m3, one bf16 scale per 32 elements) feature storage: the lookup kernel returns exactly the dequantised values and
+    the fused layer equals the same layer fed with the dequantised rows."""
+    from graphlearn_b200.ops import gather as G
+    from graphlearn_b200.ops import sage as SG
+    from graphlearn_b200.store.shards import IdMap, NodeTable
+    n, n_out = 20000, 128
+    g = torch.Generator(device=rt.device).manual_seed(7)
+    x = torch.randn(n, d, device=rt.device, generator=g) * torch.rand(n, 1, device=rt.device, generator=g) * 4
+    t8 = NodeTable(rt, "t8", IdMap(rt, torch.arange(n, device=rt.device), dense=True))
+    t8.set_float(x, torch.float8_e4m3fn)
+    deq = t8.dequantize_local()
+    assert t8.feats.local.dtype == torch.uint8 and float(((deq - x).abs() / x.abs().amax(1, keepdim=True).clamp(min=1e-6)).max()) < 0.07
+    q = torch.randint(-1, n + 5, (4000,), device=rt.device, generator=g)
+    got = G.gather_rows(rt, t8.feats, t8.feat_desc, q, d)
+    ok = (q >= 0) & (q < n)
+    want = torch.where(ok[:, None], deq[q.clamp(0, n - 1)], torch.zeros(1, device=rt.device))
+    assert torch.equal(got, want)
+    # fused layer: fp8 table vs a bf16 table that stores the dequantised values (exact in bf16: 4-bit mantissa x bf16 scale)
+    tb = NodeTable(rt, "tb", IdMap(rt, torch.arange(n, device=rt.device), dense=True))
+    tb.set_float(deq, torch.bfloat16)
+    sv = torch.randint(0, n, (M,), device=rt.device, generator=g)
+    nv = torch.randint(-1, n, (M * k,), device=rt.device, generator=g)
+    w = torch.randn(n_out, 2 * d, device=rt.device, generator=g) / math.sqrt(2 * d)
+    b = torch.randn(n_out, device=rt.device, generator=g)
+    wp = SG.pad_weight(w, d, d, "mean")
+    y8 = SG.sage_layer(wp, b, k=k, mode="mean", relu=True, out_bf16=False, self_table=t8, self_vids=sv, nbr_table=t8, nbr_vids=nv)
+    yb = SG.sage_layer(wp, b, k=k, mode="mean", relu=True, out_bf16=False, self_table=tb, self_vids=sv, nbr_table=tb, nbr_vids=nv)
+    xn = torch.where((nv >= 0)[:, None], deq[nv.clamp(min=0)], torch.zeros(1, device=rt.device))
+    ref = SG.sage_layer_reference(w, b, deq[sv], xn, k, "mean", True)
+    assert (y8 - ref).abs().max() < 0.03 * max(float(ref.abs().max()), 1.0)
+    # same products, same fp32 accumulation order up to the fma contraction of the dequantisation: tiny differences only
+    assert (y8 - yb).abs().max() < 2e-2 * max(float(ref.abs().max()), 1.0), float((y8 - yb).abs().max())
+
+
+def test_fp8_feature_rows_train(rt):
+    """the hand-scheduled engine trains from an fp8 feature table (layer 1 dequantises inside the fused kernel)"""
+    from graphlearn_b200.engine.fast_sage import FastSageTrainer
+    from graphlearn_b200.models.graphsage import EgoGraphSAGE
+    from graphlearn_b200.store.synthetic import make_sharded_graph
+    nodes, csr = make_sharded_graph(rt, 20000, 300000, 100, 16, seed=3, feature_dtype=torch.float8_e4m3fn)
+    assert nodes.feats.local.dtype == torch.uint8 and nodes.feats.local.size(1) == 128
+    torch.manual_seed(0)
+    model = EgoGraphSAGE(100, 256, 16, 2).to(rt.device)
+    tr = FastSageTrainer(rt, nodes, csr, model, [10, 5], 512, lr=5e-3)
+    tr.seeds.copy_(torch.randint(0, 20000, (512,), device=rt.device))
+    tr.capture()
+    losses = []
+    for _ in range(40):
+        tr.step_device(torch.randint(0, 20000, (512,), device=rt.device))
+        torch.cuda.synchronize()
+        losses.append(float(tr.loss_out))
+    assert all(l == l for l in losses) and sum(losses[-5:]) < 0.8 * sum(losses[:5]), losses
+
+
 def test_sage_fused_multi_segment_and_ce(rt):
     """One persistent launch over two segments (k = 25 and k = 10, the flagship's layer 1) equals two single
     launches bit for bit; the fused cross-entropy epilogue matches torch."""
