@@ -524,32 +524,57 @@ def run_bipartite_gat(args, rt):
     if W > 1:
         for p_ in model.parameters():
             dist.broadcast(p_.data, src=0)
-    opt = torch.optim.Adam(model.parameters(), lr=3e-3, fused=True)
+    use_graph = not args.no_graph and W == 1
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3, fused=True, capturable=use_graph)
     tu, ti = g.store.nodes["u"], g.store.nodes["i"]
     h_loss = torch.zeros(1).pin_memory()
+    names = ("u", "u1", "u2", "i", "i1", "i2", "neg", "n1", "n2")
 
-    def step():
+    def next_batch():
         while True:
             try:
                 r = ds.next()
-                break
+                return {a: r[a].vids_t for a in names}
             except gl.OutOfRangeError:
                 continue
-        v = lambda a: r[a].vids_t          # noqa: E731
-        ue, ie = model.forward_store([tu, ti, tu], [v("u"), v("u1"), v("u2")], [ti, tu, ti], [v("i"), v("i1"), v("i2")], [K1, K2], [K1, K2])
-        ne = model.item_tower.forward_store([ti, tu, ti], [v("neg"), v("n1"), v("n2")], [K1, K2])
-        loss = model.in_batch_negative_loss(ue, ie) + model.loss(ue, ie, ne, kind="sigmoid")
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if W > 1:
-            flat = torch.cat([p_.grad.reshape(-1) for p_ in model.parameters()])
-            dist.all_reduce(flat)
-            flat /= W
-            o = 0
-            for p_ in model.parameters():
-                p_.grad.copy_(flat[o:o + p_.numel()].view_as(p_)); o += p_.numel()
-        opt.step()
-        h_loss.copy_(loss.detach(), non_blocking=True)
+
+    def loss_fn(v):
+        ue, ie = model.forward_store([tu, ti, tu], [v["u"], v["u1"], v["u2"]], [ti, tu, ti], [v["i"], v["i1"], v["i2"]], [K1, K2], [K1, K2])
+        ne = model.item_tower.forward_store([ti, tu, ti], [v["neg"], v["n1"], v["n2"]], [K1, K2])
+        return model.in_batch_negative_loss(ue, ie) + model.loss(ue, ie, ne, kind="sigmoid")
+
+    def allreduce_grads():
+        flat = torch.cat([p_.grad.reshape(-1) for p_ in model.parameters()])
+        dist.all_reduce(flat)
+        flat /= W
+        o = 0
+        for p_ in model.parameters():
+            p_.grad.copy_(flat[o:o + p_.numel()].view_as(p_)); o += p_.numel()
+
+    graphed = None
+    if use_graph:
+        # forward + loss + backward + Adam of the two towers as ONE CUDA graph over static id buffers (engine/graphed.py)
+        from graphlearn_b200.engine.graphed import GraphedTrainStep
+        try:
+            graphed = GraphedTrainStep(loss_fn, opt, next_batch())
+        except Exception as e:      # a non-capturable op in the model path: keep the eager step, say so in the JSON line
+            print("graph capture of the GAT step failed, running eagerly: %r" % (e,), file=sys.stderr)
+            graphed = None
+            opt = torch.optim.Adam(model.parameters(), lr=3e-3, fused=True)
+
+    def step():
+        v = next_batch()
+        if graphed is not None:
+            loss = graphed(v)
+        else:
+            loss = loss_fn(v)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if W > 1:
+                allreduce_grads()
+            opt.step()
+            loss = loss.detach()
+        h_loss.copy_(loss, non_blocking=True)
         return h_loss
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -579,6 +604,8 @@ def run_bipartite_gat(args, rt):
             "config": {"name": args.config, "model": cfg["model"], "global_batch": B * W, "fanout": cfg["fanouts"], "heads": cfg["heads"],
                        "negatives": "in-batch softmax + %d in-degree-weighted sampled negatives per user (item tower applied to them)" % NEG,
                        "api": "gsl (in-memory sources -> gl.Graph -> GSL E() query -> interpreter -> fused GAT kernels + autograd)",
+                       "cuda_graph": ("model step (forward + loss + backward + Adam) captured as one CUDA graph, %d replays / %d eager"
+                                      % (graphed.replays, graphed.eager_steps)) if graphed is not None else "no (eager autograd)",
                        "num_users": NU, "num_items": NI, "num_edges": NE, "feat_dim": D, "parallelism": "dp%d+graph-partition%d" % (W, W),
                        "graph_build_s": round(build_s, 2)},
             "e2e": {"value": v_, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,

@@ -2,25 +2,26 @@
 //
 //     out[m, :] = act( [ x_self[m] || agg_j x_nbr[m, j] ] . W^T + b )
 //
-// One CTA per SM stays resident and walks a static list of row tiles (<= 128 destination rows each)
+// One CTA per SM stays resident and walks a static list of row tiles (<= 64 destination rows each)
 // that may span SEVERAL segments of the ego graph (e.g. seeds<-hop1 with k=25 and hop1<-hop2 with
 // k=10 of a 2-layer GraphSAGE): the tile height of every segment is chosen on the host so that all
 // tiles cost about the same number of row fetches and the tile count is a multiple of the SM count.
 // Inside the CTA the phases of a tile overlap instead of running back to back:
 //
-//   warps 9-31  gather        each warp owns work items (1-4 destination rows x one 512-byte slice): it
+//   gather warps (GW, default 19)   each warp owns work items (1-4 destination rows x one 512-byte slice): it
 //                             translates the item's ids into row pointers (local HBM, a peer GPU's HBM over
 //                             NVLink, or the local replica cache) in a private SMEM scratch - the ids of the
 //                             NEXT item are prefetched while the current rows are in flight -, pulls the self
 //                             row and the k neighbour rows with batches of 16-byte loads, reduces in fp32
 //                             registers and writes the bf16 A tile in the UMMA K-major SWIZZLE_128B layout
 //                             (and row-major to global for the backward pass); items are dealt round-robin
-//                             ACROSS tile boundaries so no warp idles
-//   warp 8      MMA           W image fetched ONCE per CTA by the TMA engine (cp.async.bulk); one
-//                             elected thread issues tcgen05.mma (M=128, N<=256, K=16) into one of two
+//                             ACROSS tile boundaries so no warp idles; the A tile is double buffered; rows may be
+//                             fp32, bf16 or block-scaled fp8 (dequantised while accumulating)
+//   MMA warp (1)              W image fetched ONCE per CTA by the TMA engine (cp.async.bulk); one
+//                             elected thread issues tcgen05.mma (M=64, N<=256, K=16) into one of two
 //                             TMEM accumulators; tcgen05.commit frees the A tile and publishes the
 //                             accumulator through mbarriers
-//   warps 0-7   epilogue      tcgen05.ld -> bias -> ReLU -> bf16/fp32 store of tile t while the gather
+//   epilogue warps (EW, default 4)  tcgen05.ld -> bias -> ReLU -> bf16/fp32 store of tile t while the gather
 //                             warps are already loading tile t+1; for the top layer a second, coalesced
 //                             phase (one warp per row, one lane per class) computes the softmax
 //                             cross-entropy loss, dlogits and the bias gradient (fused CE)

@@ -4,18 +4,15 @@ Same math as ``models.graphsage.EgoGraphSAGE`` + ``SageTrainer``'s autograd
 path, but forward and backward are an explicit, minimal kernel chain over
 pre-allocated buffers (static shapes -> CUDA graph friendly):
 
-  memset(flat grads)
-  K1  sample hop 1..L                                    (L launches)
-      pack W_l fp32 -> bf16 SW128 image (+ row-major)    (L launches)
-  K6+K7 fused gather/aggregate/tcgen05 GEMM per (layer, hop pair)
-      loss + dlogits + bias grad                         (1 launch)
-  for l = L..1:  dW_l = dZ_l^T A_l        (library GEMM, fp32 accumulate straight into the flat grad buffer)
-                 dA_l = dZ_l W_l          (library GEMM)      [l > 1]
-                 dZ_{l-1} = relu'(H_{l-1}) * (self + nbr/k contributions of dA_l)   (1 launch, bias grad fused)
-  K8  peer-memory all-reduce of the flat gradient (world > 1)
-      RNG/step advance + fused Adam                       (2 launches)
+  K1    sample hop 1..L of the NEXT batch (parallel branch)            (L launches + 1 counter kernel)
+  K6+K7 ONE persistent launch per layer: gather / aggregate / tcgen05 GEMM of every hop pair of the layer
+        (multi-segment); the top layer's launch also computes softmax-CE, dlogits and the bias gradient
+  for l = L..1:  dW_l = dZ_l^T A_l   split-K tcgen05 kernel, fp32 accumulation straight into the flat gradient buffer;
+                                     for l < L, dZ_l = relu'(H_l) * (self + nbr/k rows of dA_{l+1}) is computed by its producers
+                 dA_l = dZ_l W_l     the forward kernel with a K-major image of W_l^T                      [l > 1]
+  K8    ONE kernel: peer-memory all-reduce (world > 1) + Adam + gradient zeroing + bf16 weight images of the next step
 
-18 launches for the 2-layer flagship instead of ~60 on the autograd path.
+9 launches of this repo's kernels (0 library kernels) for the 2-layer flagship instead of ~60 on the autograd path.
 Layer l consumes hop pairs (i, i+1) for i in 0..L-l, exactly the EgoGNN
 recursion of graphlearn/python/nn/tf/model/ego_gnn.py:58-110.
 
@@ -23,7 +20,8 @@ Scheduling (see ``_step_body`` / ``capture``): the launches above form a DAG, no
 run on forked streams, which become parallel branches of the captured CUDA graph; under capture the step is
 additionally software pipelined: graph replay t trains on the batch that replay t-1 staged (pinned host ->
 device) and sampled on a side branch, and the loss leaves through another branch.  Public API: ``capture()``,
-``step(seed_ids_host)`` (end to end), ``step_device()`` (no host traffic), ``predict``, ``state_dict``.
+``step(seed_ids_host)`` (end to end), ``step_device()`` (no host traffic), ``from_query`` / ``step_query`` (driven by a
+compiled GSL query), ``predict``, ``state_dict``.
 """
 from __future__ import annotations
 
@@ -263,12 +261,11 @@ class FastSageTrainer:
     def _step_body(self, pipe=None):
         """One training step as a small DAG of launches.  Independent work runs on forked streams (graph
         branches under capture) so that kernel-boundary latencies overlap instead of adding up:
-            side B : zero grads || side C : pack W_2..W_L || main : pack W_1 (bf16 SW128 images)
-            sampling: on main (plain schedule) or, under graph capture, the NEXT batch on its own branch
-            side B / sampling branch : rng + optimiser step counters (after the sampling kernels)
-            side A : layer-l segment 0                                  || segments >= 1 (main)
-            side A : dW_l GEMM                                          || dA_l GEMM + input-gradient kernels (main)
-        everything joins before the gradient all-reduce + Adam."""
+            sampling: on main (plain schedule) or, under graph capture, the NEXT batch on its own branch, followed by
+                      the rng + optimiser step counters
+            main    : one persistent launch per layer (all hop pairs of the layer; the top layer also computes the loss)
+            side A  : dW_L GEMM   ||   main : dA_L (forward kernel with the W^T image) -> dW_{L-1} (dZ computed on the fly) ...
+        everything joins before ONE fused kernel: gradient all-reduce + Adam + grad zeroing + next step's weight images."""
         C, L = self.C, self.L
         main = torch.cuda.current_stream()
         sA, sB = self._sides

@@ -237,3 +237,41 @@ def test_gat_fused_kernels(dtype, d, H, k):
     y = conv.forward_store(t, sv, nv, k)
     y_ref = conv.forward_reference(feats[sv], feats[nv], k)
     assert (y - y_ref).abs().max() < 3e-2 * max(1.0, float(y_ref.abs().max()))
+
+
+def test_graphed_train_step_matches_eager(rt):
+    """engine/graphed.py: forward + loss + backward + Adam captured once; replays train exactly like the eager step."""
+    from graphlearn_b200.engine.graphed import GraphedTrainStep
+    from graphlearn_b200.nn.conv import EgoGATConv
+    from graphlearn_b200.store.shards import IdMap, NodeTable
+    n, d, k = 3000, 32, 6
+    g = torch.Generator(device=rt.device).manual_seed(0)
+    tab = NodeTable(rt, "t", IdMap(rt, torch.arange(n, device=rt.device), dense=True))
+    tab.set_float(torch.randn(n, d, device=rt.device, generator=g), torch.bfloat16)
+    target = torch.randn(n, 16, device=rt.device, generator=g)
+
+    def make():
+        torch.manual_seed(1)
+        conv = EgoGATConv(d, 16, num_head=2).to(rt.device)
+        opt = torch.optim.Adam(conv.parameters(), lr=1e-2, capturable=True)
+
+        def loss_fn(v):
+            out = conv.forward_store(tab, v["s"], v["n"], k)
+            return ((out.float() - target[v["s"]]) ** 2).mean()
+        return conv, opt, loss_fn
+
+    batches = [{"s": torch.randint(0, n, (256,), device=rt.device, generator=g),
+                "n": torch.randint(0, n, (256 * k,), device=rt.device, generator=g)} for _ in range(8)]
+    conv_e, opt_e, loss_e = make()
+    eager = []
+    for b in batches[:1] * 3 + batches:             # the graphed step warms up 3x on its example batch
+        opt_e.zero_grad(set_to_none=True)
+        l = loss_e(b); l.backward(); opt_e.step()
+        eager.append(float(l))
+    conv_g, opt_g, loss_g = make()
+    step = GraphedTrainStep(loss_g, opt_g, batches[0], warmup=3)
+    got = [float(step(b)) for b in batches]
+    assert step.replays == 8 and step.eager_steps == 0
+    assert torch.allclose(torch.tensor(got), torch.tensor(eager[3:]), rtol=2e-3, atol=1e-5), (got, eager[3:])
+    short = {"s": batches[0]["s"][:100], "n": batches[0]["n"][:100 * k]}
+    assert float(step(short)) > 0 and step.eager_steps == 1          # other shapes fall back to the eager step
