@@ -30,7 +30,7 @@ The Java client and the Helm chart are deployment glue around this core and are 
 dicts of arrays (``LogChannel`` persists them as torch segments instead of Kafka/FlatBuffers).
 """
 from .coordinator import BarrierMonitor, CheckpointManager, Coordinator, WorkerRegistry  # noqa: F401
-from .file_loader import FileLoader, GroupProducer, RecordBatchBuilder  # noqa: F401
+from .file_loader import FileLoader, GroupProducer, RecordBatchBuilder, decode_record_batch, encode_record_batch  # noqa: F401
 from .http_server import HttpFrontEnd  # noqa: F401
 from .partitioned import PartitionedGraphService, Partitioner  # noqa: F401
 from .plan import PlanNode, QueryPlan  # noqa: F401

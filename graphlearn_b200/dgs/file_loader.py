@@ -152,3 +152,57 @@ class GroupProducer(object):
         """flush, then ask the coordinator to report READY once everything produced so far is sampled and published"""
         self.flush_all()
         coordinator.set_barrier(name)
+
+
+# ---------------------------------------------------------------------------------------------------- D2 wire format
+_MAGIC = b"GLBR1\x00"
+_DT = {"i8": np.int64, "f4": np.float32, "f8": np.float64, "i4": np.int32}
+
+
+def encode_record_batch(batch: dict) -> bytes:
+    """Record batch -> bytes.  The reference ships FlatBuffers ``RecordBatch`` tables (fbs/record.fbs) through Kafka; the
+    batches here are columnar dicts, so the wire form is columnar too: a JSON header (kind / type name / column / dtype /
+    shape / byte range) followed by the raw little-endian column buffers - zero parsing on the consumer side
+    (``np.frombuffer`` views).  Used for HTTP ingest bodies and for persisted ``LogChannel`` segments."""
+    import json
+    cols, blobs, off = [], [], 0
+    for kind in ("edges", "vertices"):
+        for name, rec in batch.get(kind, {}).items():
+            for col, arr in rec.items():
+                if arr is None:
+                    continue
+                a = np.ascontiguousarray(arr.detach().cpu().numpy() if hasattr(arr, "detach") else np.asarray(arr))
+                if a.dtype.kind == "i" and a.dtype != np.int64:
+                    a = a.astype(np.int64)
+                if a.dtype.kind == "f" and a.dtype not in (np.float32, np.float64):
+                    a = a.astype(np.float32)
+                code = {np.dtype(np.int64): "i8", np.dtype(np.float32): "f4", np.dtype(np.float64): "f8"}[a.dtype]
+                b = a.tobytes()
+                cols.append({"k": kind, "t": name, "c": col, "d": code, "s": list(a.shape), "o": off, "n": len(b)})
+                blobs.append(b)
+                off += len(b)
+    head = json.dumps({"cols": cols, "n": int(batch.get("_n", 0))}).encode()
+    return _MAGIC + len(head).to_bytes(4, "little") + head + b"".join(blobs)
+
+
+def decode_record_batch(buf: bytes) -> dict:
+    """inverse of :func:`encode_record_batch`; columns are numpy views of ONE writable copy of ``buf`` (torch wants writable
+    memory), pass a ``bytearray`` to decode in place"""
+    import json
+    if not isinstance(buf, bytearray):
+        buf = bytearray(buf)
+    if bytes(buf[:len(_MAGIC)]) != _MAGIC:
+        raise ValueError("not a graphlearn_b200 record batch")
+    p = len(_MAGIC)
+    hl = int.from_bytes(buf[p:p + 4], "little")
+    head = json.loads(bytes(buf[p + 4:p + 4 + hl]).decode())
+    base = p + 4 + hl
+    out: dict = {}
+    for c in head["cols"]:
+        if c["d"] not in _DT or c["k"] not in ("edges", "vertices"):
+            raise ValueError("bad column descriptor in record batch")
+        a = np.frombuffer(buf, dtype=_DT[c["d"]], count=int(np.prod(c["s"])) if c["s"] else 1, offset=base + c["o"]).reshape(c["s"])
+        out.setdefault(c["k"], {}).setdefault(c["t"], {})[c["c"]] = a
+    if head.get("n"):
+        out["_n"] = int(head["n"])
+    return out

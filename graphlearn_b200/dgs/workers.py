@@ -66,8 +66,18 @@ class LogChannel(object):
                     self._base[p] = int(f.read().strip() or 0)
             if offs:
                 self._base[p] = offs[0]
-                self._logs[p] = [torch.load(os.path.join(d, "%d.pt" % o), weights_only=True) for o in offs]
+                self._logs[p] = [self._load_segment(os.path.join(d, "%d.pt" % o)) for o in offs]
                 self._records[p] = sum(int(b.get("_n", 0)) for b in self._logs[p])
+
+    @staticmethod
+    def _load_segment(path: str) -> dict:
+        with open(path, "rb") as f:
+            head = f.read(6)
+        if head == b"GLBR1\x00":
+            from .file_loader import decode_record_batch
+            with open(path, "rb") as f:
+                return decode_record_batch(f.read())
+        return torch.load(path, weights_only=True)
 
     def end_offset(self, p: int) -> int:
         return self._base[p] + len(self._logs[p])
@@ -82,7 +92,12 @@ class LogChannel(object):
             self._records[p] += int(n_records)
             if self.path:
                 tmp = os.path.join(self.path, "p%d" % p, "%d.tmp" % off)
-                torch.save(batch, tmp)
+                if "edges" in batch or "vertices" in batch:          # record batches: columnar wire format (file_loader.py)
+                    from .file_loader import encode_record_batch
+                    with open(tmp, "wb") as f:
+                        f.write(encode_record_batch(batch))
+                else:                                                # published sample rows (device tensors)
+                    torch.save(batch, tmp)
                 os.replace(tmp, os.path.join(self.path, "p%d" % p, "%d.pt" % off))
             self._cv.notify_all()
             return off

@@ -289,3 +289,28 @@ def test_group_producer_sdk(tmp_path):
     q = list(range(12))
     a, c = one.run_query(0, q), cl.run_query(q)
     assert torch.equal(a["hops"][0]["ids"], c["hops"][0]["ids"])
+
+
+def test_record_batch_wire_format_roundtrip():
+    """D2: columnar binary record batches (header + raw column buffers)"""
+    from graphlearn_b200.dgs import decode_record_batch, encode_record_batch
+    rs = np.random.RandomState(0)
+    b = {"edges": {"click": {"src": rs.randint(0, 9, 7), "dst": rs.randint(0, 9, 7), "ts": np.arange(7), "weight": rs.rand(7).astype(np.float32)},
+                   "sim": {"src": torch.arange(3), "dst": torch.arange(3) + 1, "ts": torch.arange(3), "weight": None}},
+         "vertices": {"i": {"id": np.arange(4), "ts": np.arange(4), "feat": rs.randn(4, 3).astype(np.float32)}}, "_n": 14}
+    buf = encode_record_batch(b)
+    d = decode_record_batch(buf)
+    assert d["_n"] == 14 and set(d["edges"]) == {"click", "sim"} and "weight" not in d["edges"]["sim"]
+    assert np.array_equal(d["edges"]["click"]["src"], b["edges"]["click"]["src"]) and d["edges"]["click"]["weight"].dtype == np.float32
+    assert np.array_equal(d["edges"]["sim"]["dst"], np.arange(3) + 1)
+    assert np.array_equal(d["vertices"]["i"]["feat"], b["vertices"]["i"]["feat"]) and d["vertices"]["i"]["feat"].shape == (4, 3)
+    svc = DynamicGraphService({"vertices": {"u": {"count": 16, "feat_dim": 0}, "i": {"count": 16, "feat_dim": 3}},
+                               "edges": {"click": {"src": "u", "dst": "i"}, "sim": {"src": "i", "dst": "i"}}}, device="cpu")
+    svc.install_query(0, QueryPlan("u").out("click", 2))
+    svc.apply_updates(d)                                   # decoded (read-only) views feed the service directly
+    assert svc.ingested == 7
+    try:
+        decode_record_batch(b"nonsense")
+        assert False
+    except ValueError:
+        pass

@@ -239,9 +239,11 @@ def test_gat_fused_kernels(dtype, d, H, k):
     assert (y - y_ref).abs().max() < 3e-2 * max(1.0, float(y_ref.abs().max()))
 
 
-def test_graphed_train_step_matches_eager(rt):
+def test_graphed_train_step_matches_eager():
     """engine/graphed.py: forward + loss + backward + Adam captured once; replays train exactly like the eager step."""
     from graphlearn_b200.engine.graphed import GraphedTrainStep
+    from graphlearn_b200.parallel.runtime import init
+    rt = init()
     from graphlearn_b200.nn.conv import EgoGATConv
     from graphlearn_b200.store.shards import IdMap, NodeTable
     n, d, k = 3000, 32, 6
