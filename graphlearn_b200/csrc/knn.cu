@@ -173,28 +173,46 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_flat_kernel(const __grid_c
       umma::mbar_wait(t_free + b, (uint32_t)(((s >> 1) & 1) ^ 1));     // the top-k warps have consumed the norm slice
       const int64_t base = r_begin + (int64_t)s * kKnnSlab;
       uint8_t* dst = sX + (size_t)b * tile_bytes;
-      for (int i = pt; i < per_slab; i += kKnnProdWarps * 32) {
-        const int r = i / chunks_row, c = i - r * chunks_row;
-        const int64_t li = base + r;
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (li < r_end && c * 8 < p.dim) {
-          const int64_t row = p.row_list ? __ldg(p.row_list + li) : li;
-          if (p.x_dtype == 1) {
-            val = ld_nc_u4(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.x_stride) + c);
-            if (c * 8 + 8 > p.dim) {                          // mask the tail beyond the real dimension
-              __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&val);
-              for (int j = 0; j < 8; ++j) if (c * 8 + j >= p.dim) e[j] = __float2bfloat16(0.f);
-            }
-          } else {
-            const float* src = reinterpret_cast<const float*>(p.x) + row * p.x_stride + c * 8;
-            float f[8];
+      // batches of 8 chunks per thread: all loads of a batch are issued before the first store (one DRAM round trip per
+      // batch instead of one per chunk - the slab loop is latency bound otherwise)
+      constexpr int kPB = 8, kPT = kKnnProdWarps * 32;
+      for (int i0 = pt; i0 < per_slab; i0 += kPB * kPT) {
+        uint4 vals[kPB];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (c * 8 + j < p.dim) ? __ldg(src + j) : 0.f;
-            val.x = pack_bf16x2(f[0], f[1]); val.y = pack_bf16x2(f[2], f[3]); val.z = pack_bf16x2(f[4], f[5]); val.w = pack_bf16x2(f[6], f[7]);
+        for (int u = 0; u < kPB; ++u) {
+          const int i = i0 + u * kPT;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (i < per_slab) {
+            const int r = i / chunks_row, c = i - r * chunks_row;
+            const int64_t li = base + r;
+            if (li < r_end && c * 8 < p.dim) {
+              const int64_t row = p.row_list ? __ldg(p.row_list + li) : li;
+              if (p.x_dtype == 1) {
+                val = ld_nc_u4(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.x_stride) + c);
+                if (c * 8 + 8 > p.dim) {                          // mask the tail beyond the real dimension
+                  __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&val);
+                  for (int j = 0; j < 8; ++j) if (c * 8 + j >= p.dim) e[j] = __float2bfloat16(0.f);
+                }
+              } else {
+                const float* src = reinterpret_cast<const float*>(p.x) + row * p.x_stride + c * 8;
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = (c * 8 + j < p.dim) ? __ldg(src + j) : 0.f;
+                val.x = pack_bf16x2(f[0], f[1]); val.y = pack_bf16x2(f[2], f[3]); val.z = pack_bf16x2(f[4], f[5]); val.w = pack_bf16x2(f[6], f[7]);
+              }
+            }
+          }
+          vals[u] = val;
+        }
+#pragma unroll
+        for (int u = 0; u < kPB; ++u) {
+          const int i = i0 + u * kPT;
+          if (i < per_slab) {
+            const int r = i / chunks_row, c = i - r * chunks_row;
+            const int kcol = c * 8;
+            *reinterpret_cast<uint4*>(dst + (size_t)(kcol >> 6) * (128 * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63))) = vals[u];
           }
         }
-        const int kcol = c * 8;
-        *reinterpret_cast<uint4*>(dst + (size_t)(kcol >> 6) * (128 * 128) + umma::sw128_offset((uint32_t)r, (uint32_t)(kcol & 63))) = val;
       }
       if (p.x_norm && pt < kKnnSlab) {
         const int64_t li = base + pt;
@@ -220,47 +238,165 @@ struct KnnMergeParams {
   float* out_s; int64_t* out_i;    // [B, k], best first
 };
 
-__global__ void knn_merge_kernel(const KnnMergeParams p) {
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (q >= p.B) return;
+// One CTA per query: the candidate scores of every list are staged in shared memory once (coalesced over the lists), then k
+// selection passes (thread-local scan -> warp shuffle -> cross-warp reduce) pick the best remaining candidate each.
+__global__ void __launch_bounds__(256) knn_merge_kernel(const KnnMergeParams p) {
+  extern __shared__ float sc[];                 // [total] candidate scores, -FLT_MAX = invalid / already taken
+  __shared__ float red_s[8];
+  __shared__ int red_c[8];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per_src = p.n_lists * p.k;
   const int total = p.n_src * per_src;
-  float last = FLT_MAX;
-  long long last_key = -1;                                   // (position) tie-breaker so equal scores are not repeated
+  auto offset_of = [&](int c, int& src) -> size_t {
+    src = c / per_src;
+    const int rem = c - src * per_src;
+    const int l = rem / p.k, e = rem - l * p.k;
+    return ((size_t)l * p.qstride + q) * p.k + e;
+  };
+  for (int c = tid; c < total; c += 256) {
+    int src;
+    const size_t off = offset_of(c, src);
+    const float s = reinterpret_cast<const float*>(p.cand_s.p[src])[off];
+    const long long id = reinterpret_cast<const int64_t*>(p.cand_i.p[src])[off];
+    sc[c] = id < 0 ? -FLT_MAX : s;
+  }
+  __syncthreads();
   for (int j = 0; j < p.k; ++j) {
     float best = -FLT_MAX;
-    long long best_pos = -1;
-    for (int c = lane; c < total; c += 32) {
-      const int src = c / per_src, rem = c - src * per_src;
-      const int l = rem / p.k, e = rem - l * p.k;
-      const size_t off = ((size_t)l * p.qstride + q) * p.k + e;
-      const float s = reinterpret_cast<const float*>(p.cand_s.p[src])[off];
-      const long long id = reinterpret_cast<const int64_t*>(p.cand_i.p[src])[off];
-      if (id < 0) continue;
-      const bool after_last = s < last || (s == last && (long long)c > last_key);
-      if (after_last && (s > best || (s == best && (long long)c < best_pos))) { best = s; best_pos = c; }
+    int best_c = -1;
+    for (int c = tid; c < total; c += 256) {
+      const float s = sc[c];
+      if (s > best) { best = s; best_c = c; }            // ascending c inside a thread: the lowest position wins ties
     }
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const long long op = __shfl_xor_sync(0xffffffffu, best_pos, o);
-      if (op >= 0 && (best_pos < 0 || ob > best || (ob == best && op < best_pos))) { best = ob; best_pos = op; }
+      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+      if (oc >= 0 && (best_c < 0 || ob > best || (ob == best && oc < best_c))) { best = ob; best_c = oc; }
     }
-    if (lane == 0) {
-      if (best_pos < 0) { p.out_s[(size_t)q * p.k + j] = -FLT_MAX; p.out_i[(size_t)q * p.k + j] = -1; }
+    if (lane == 0) { red_s[warp] = best; red_c[warp] = best_c; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (red_c[w] >= 0 && (best_c < 0 || red_s[w] > best || (red_s[w] == best && red_c[w] < best_c))) { best = red_s[w]; best_c = red_c[w]; }
+      if (best_c < 0 || best == -FLT_MAX) { p.out_s[(size_t)q * p.k + j] = -FLT_MAX; p.out_i[(size_t)q * p.k + j] = -1; }
       else {
-        const int c = (int)best_pos;
-        const int src = c / per_src, rem = c - src * per_src;
-        const int l = rem / p.k, e = rem - l * p.k;
-        const size_t off = ((size_t)l * p.qstride + q) * p.k + e;
+        int src;
+        const size_t off = offset_of(best_c, src);
         const long long id = reinterpret_cast<const int64_t*>(p.cand_i.p[src])[off];
         p.out_s[(size_t)q * p.k + j] = best;
         p.out_i[(size_t)q * p.k + j] = p.id_scale > 0 ? id * p.id_scale + (long long)src * p.id_add : id;
+        sc[best_c] = -FLT_MAX;                               // taken
       }
     }
-    last = best; last_key = best_pos;
-    if (best_pos < 0) { last = -FLT_MAX; }
+    __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IVF-flat list scan: one CTA per (query, probed list).  The work per pair is tiny (a few thousand rows x d) and every
+// query probes different lists, so this is a CUDA-core kernel, exact in fp32: half-warps (fp32: whole warps for d > 128)
+// stream the list's rows with 16-byte loads, reduce the squared distance / inner product by shuffles, and each warp keeps
+// its k best in shared memory behind a threshold.  Output: [nprobe * 4 warps, B, k] candidate lists for knn_merge_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct KnnIvfParams {
+  const void* x; int x_dtype; int64_t x_stride; int dim;
+  const int64_t* order;        // rows grouped by list
+  const int64_t* offsets;      // [nlist + 1]
+  const float* q;              // [B, dim] fp32
+  const int64_t* probes;       // [B, nprobe]
+  int B, nprobe, k, metric;    // metric 0: -|q - x|^2, 1: <q, x>
+  float* out_s; int64_t* out_i;   // [nprobe * 4, B, k]
+};
+
+constexpr int kIvfWarps = 4;
+
+__global__ void __launch_bounds__(kIvfWarps * 32) knn_ivf_scan_kernel(const KnnIvfParams p) {
+  extern __shared__ float ivf_smem[];
+  float* sq = ivf_smem;                                   // [dim] the query
+  float* tv = sq + ((p.dim + 3) & ~3);                    // [warps][k] kept scores
+  int* ti = reinterpret_cast<int*>(tv + kIvfWarps * p.k); // [warps][k] kept positions inside the list
+  const int probe = blockIdx.x, qi = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int f = tid; f < p.dim; f += blockDim.x) sq[f] = p.q[(size_t)qi * p.dim + f];
+  for (int e = tid; e < kIvfWarps * p.k; e += blockDim.x) { tv[e] = -FLT_MAX; ti[e] = -1; }
+  __syncthreads();
+  const int64_t l = p.probes[(size_t)qi * p.nprobe + probe];
+  const int64_t lo = p.offsets[l], hi = p.offsets[l + 1];
+  const int vec = p.x_dtype == 0 ? 4 : 8;                  // elements per 16-byte chunk
+  const int chunks = (p.dim + vec - 1) / vec;
+  // lanes per row: the smallest power of two >= chunks (<= 32); wider rows loop over chunk groups
+  int lpr = 1;
+  while (lpr < chunks && lpr < 32) lpr <<= 1;
+  const int rows_per_iter = 32 / lpr;
+  const int sub = lane / lpr, lig = lane % lpr;
+  float* mv = tv + warp * p.k;
+  int* mi = ti + warp * p.k;
+  float thr = -FLT_MAX;
+  int thr_pos = 0;
+  for (int64_t base = lo + (int64_t)warp * rows_per_iter; base < hi; base += (int64_t)kIvfWarps * rows_per_iter) {
+    const int64_t pos = base + sub;
+    float acc = 0.f;
+    if (pos < hi) {
+      const int64_t row = __ldg(p.order + pos);
+      for (int c = lig; c < chunks; c += lpr) {
+        float xv[8];
+        const int f0 = c * vec;
+        if (p.x_dtype == 0) {
+          const float4 t = ld_nc_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + row * p.x_stride) + c);
+          xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        } else {
+          const uint4 t = ld_nc_u4(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.x_stride) + c);
+          float2 a;
+          a = unpack_bf16x2(t.x); xv[0] = a.x; xv[1] = a.y; a = unpack_bf16x2(t.y); xv[2] = a.x; xv[3] = a.y;
+          a = unpack_bf16x2(t.z); xv[4] = a.x; xv[5] = a.y; a = unpack_bf16x2(t.w); xv[6] = a.x; xv[7] = a.y;
+        }
+        for (int i = 0; i < vec; ++i) {
+          if (f0 + i < p.dim) {
+            const float qv = sq[f0 + i];
+            if (p.metric == 1) acc = fmaf(qv, xv[i], acc);
+            else { const float dlt = qv - xv[i]; acc = fmaf(-dlt, dlt, acc); }
+          }
+        }
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // the group leaders hold the scores of this iteration's rows: lane 0 folds them into the warp's list
+    for (int g = 0; g < rows_per_iter; ++g) {
+      const float sc = __shfl_sync(0xffffffffu, acc, g * lpr);
+      const int64_t pg = base + g;
+      if (pg < hi && sc > thr) {                            // warp-uniform branch
+        if (lane == 0) { mv[thr_pos] = sc; mi[thr_pos] = (int)(pg - lo); }
+        __syncwarp();
+        float m = FLT_MAX; int mp = 0;                      // new threshold = smallest kept score
+        for (int e = lane; e < p.k; e += 32) { const float v = mv[e]; if (v < m) { m = v; mp = e; } }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, m, o);
+          const int op = __shfl_xor_sync(0xffffffffu, mp, o);
+          if (om < m || (om == m && op < mp)) { m = om; mp = op; }
+        }
+        thr = m; thr_pos = mp;
+      }
+    }
+  }
+  __syncwarp();
+  const size_t ob = (((size_t)probe * kIvfWarps + warp) * p.B + qi) * p.k;
+  for (int e = lane; e < p.k; e += 32) {
+    const int pi = mi[e];
+    p.out_s[ob + e] = mv[e];
+    p.out_i[ob + e] = pi >= 0 ? __ldg(p.order + lo + pi) : -1;
+  }
+}
+
+static void launch_merge(const KnnMergeParams& m, cudaStream_t stream) {
+  const size_t smem = (size_t)m.n_src * m.n_lists * m.k * sizeof(float);
+  TORCH_CHECK(smem <= 200 * 1024, "too many candidates for the merge kernel's shared-memory stage");
+  static bool attr_done = false;
+  if (!attr_done) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  knn_merge_kernel<<<(unsigned)m.B, 256, smem, stream>>>(m);
 }
 
 // scores / rows of the k best database rows for up to 128 queries.  x: local [n, stride] fp32|bf16; q: bf16 [128, dpad].
@@ -309,7 +445,7 @@ std::vector<at::Tensor> knn_flat_topk(const at::Tensor& x, int64_t dim, const c1
   m.cand_s.p[0] = part_s.data_ptr(); m.cand_i.p[0] = part_i.data_ptr();
   m.n_src = 1; m.n_lists = grid; m.qstride = kKnnQ; m.k = (int)k; m.B = (int)B; m.id_scale = 0;
   m.out_s = out_s.data_ptr<float>(); m.out_i = out_i.data_ptr<int64_t>();
-  knn_merge_kernel<<<(unsigned)((B * 32 + 127) / 128), 128, 0, stream>>>(m);
+  launch_merge(m, stream);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out_s, out_i};
 }
@@ -327,7 +463,44 @@ std::vector<at::Tensor> knn_merge_peers(const at::Tensor& ptrs, int64_t world, i
   auto out_s = at::empty({B, k}, like.options().dtype(at::kFloat));
   auto out_i = at::empty({B, k}, like.options().dtype(at::kLong));
   m.out_s = out_s.data_ptr<float>(); m.out_i = out_i.data_ptr<int64_t>();
-  knn_merge_kernel<<<(unsigned)((B * 32 + 127) / 128), 128, 0, at::cuda::getCurrentCUDAStream()>>>(m);
+  launch_merge(m, at::cuda::getCurrentCUDAStream());
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {out_s, out_i};
+}
+
+// IVF-flat search: (scores [B, k] best first, rows [B, k]) over the probed lists of every query, exact in fp32.
+std::vector<at::Tensor> knn_ivf_search(const at::Tensor& x, int64_t dim, const at::Tensor& order, const at::Tensor& offsets, const at::Tensor& q,
+                                       const at::Tensor& probes, int64_t k, int64_t metric) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1 && (x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16));
+  TORCH_CHECK((x.stride(0) * x.element_size()) % 16 == 0 && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0, "rows must be 16-byte aligned");
+  check_cuda_i64(order, "order"); check_cuda_i64(offsets, "offsets"); check_cuda_i64(probes, "probes");
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kFloat && q.dim() == 2 && q.size(1) == dim && q.is_contiguous());
+  TORCH_CHECK(probes.dim() == 2 && probes.size(0) == q.size(0) && probes.is_contiguous() && order.is_contiguous() && offsets.is_contiguous());
+  TORCH_CHECK(k >= 1 && k <= kKnnMaxK);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t B = q.size(0), nprobe = probes.size(1);
+  auto of = x.options().dtype(at::kFloat);
+  auto oi = x.options().dtype(at::kLong);
+  auto out_s = at::empty({B, k}, of);
+  auto out_i = at::empty({B, k}, oi);
+  if (B == 0) return {out_s, out_i};
+  auto part_s = at::empty({nprobe * kIvfWarps, B, k}, of);
+  auto part_i = at::empty({nprobe * kIvfWarps, B, k}, oi);
+  KnnIvfParams p;
+  p.x = x.data_ptr(); p.x_dtype = x.scalar_type() == at::kFloat ? 0 : 1; p.x_stride = x.stride(0); p.dim = (int)dim;
+  p.order = order.data_ptr<int64_t>(); p.offsets = offsets.data_ptr<int64_t>(); p.q = q.data_ptr<float>();
+  p.probes = probes.data_ptr<int64_t>(); p.B = (int)B; p.nprobe = (int)nprobe; p.k = (int)k; p.metric = (int)metric;
+  p.out_s = part_s.data_ptr<float>(); p.out_i = part_i.data_ptr<int64_t>();
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const size_t smem = (((size_t)dim + 3) & ~(size_t)3) * 4 + (size_t)kIvfWarps * k * 8;
+  knn_ivf_scan_kernel<<<dim3((unsigned)nprobe, (unsigned)B), kIvfWarps * 32, smem, stream>>>(p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  KnnMergeParams m;
+  std::memset(&m, 0, sizeof(m));
+  m.cand_s.p[0] = part_s.data_ptr(); m.cand_i.p[0] = part_i.data_ptr();
+  m.n_src = 1; m.n_lists = (int)(nprobe * kIvfWarps); m.qstride = (int)B; m.k = (int)k; m.B = (int)B; m.id_scale = 0;
+  m.out_s = out_s.data_ptr<float>(); m.out_i = out_i.data_ptr<int64_t>();
+  launch_merge(m, stream);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out_s, out_i};
 }

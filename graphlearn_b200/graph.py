@@ -288,8 +288,8 @@ class Graph(object):
         out = V_.Nodes(ids_t, node_type, shape=shape, graph=self, vids=v)
         out._inited = True
         if dec.float_attr_num > 0 and tab.feats is not None:
-            out._t["float_attrs"] = G.gather_rows(rt, tab.feats, tab.feat_desc, v, tab.float_dim,
-                                                  fill=cfg.default_float_attribute)
+            pull = G.gather_rows_dedup if cfg.dedup_feature_pull else G.gather_rows
+            out._t["float_attrs"] = pull(rt, tab.feats, tab.feat_desc, v, tab.float_dim, fill=cfg.default_float_attribute)
         if dec.int_attr_num > 0 and tab.ints is not None:
             out._t["int_attrs"] = G.gather_any(rt, tab.ints, v, fill=cfg.default_int_attribute)
         if dec.labeled and tab.labels is not None:

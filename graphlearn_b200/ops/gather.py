@@ -61,6 +61,25 @@ def gather_rows(rt: Runtime, st: SymmTensor, desc: Optional[torch.Tensor], vids:
     return rows.to(out_dtype)
 
 
+def gather_rows_dedup(rt: Runtime, st: SymmTensor, desc: Optional[torch.Tensor], vids: torch.Tensor, dim: int,
+                      out_dtype: torch.dtype = torch.float32, fill: float = 0.0) -> torch.Tensor:
+    """Dedup before the pull: relabel the requested ids (K4 hash table, first-occurrence order), fetch
+    every DISTINCT row once - over NVLink when it is remote - and expand by index.  Pays off when a frontier repeats ids
+    (power-law graphs: a hub is sampled by many seeds; multi-hop ego networks of one batch); on the uniform synthetic
+    benchmark graph only ~6 % of the 282 K ids of a batch repeat, so the fused engine does not use it."""
+    from .sparse import Relabel
+    v = vids.reshape(-1).to(torch.int64)
+    if v.numel() == 0:
+        return gather_rows(rt, st, desc, v, dim, out_dtype, fill)
+    rl = Relabel(v)
+    uniq_rows = gather_rows(rt, st, desc, rl.uniq, dim, out_dtype, fill)
+    inv = rl.inverse.reshape(-1)
+    out = uniq_rows[inv.clamp(min=0)]
+    if bool((inv < 0).any()):                       # negative (padding) ids are not part of the table
+        out = torch.where((inv >= 0)[:, None], out, torch.full_like(out, fill))
+    return out
+
+
 def gather_any(rt: Runtime, st: SymmTensor, vids: torch.Tensor, fill) -> torch.Tensor:
     """Generic (int64 / float / 1-D or 2-D) sharded lookup.  On CUDA, 8-byte rows are
     moved bit-exactly by the float gather kernel (pure copies, no arithmetic)."""

@@ -124,6 +124,13 @@ class IvfFlatIndex(object):
         # nearest lists per query (always by L2 to the centroids, like faiss' IndexIVFFlat quantiser)
         d = torch.cdist(q.float(), self.centroids)
         probes = d.topk(self.nprobe, dim=1, largest=False).indices      # [B, nprobe]
+        if use_kernel and self.x.dtype in (torch.float32, torch.bfloat16):
+            # one launch: a CTA per (query, probed list) scans the list exactly in fp32, then the shared-memory merge
+            from ..parallel.runtime import native
+            s, r = native().knn_ivf_search(self.x, self.dim, self.order, self.offsets, q.float().contiguous(), probes.contiguous(),
+                                           int(k), int(self.metric))
+            s = torch.where(r >= 0, s, torch.full_like(s, float("-inf")))
+            return s, r
         best_s = torch.full((B, k), float("-inf"), device=q.device)
         best_i = torch.full((B, k), -1, dtype=torch.int64, device=q.device)
         offs = self.offsets.tolist()

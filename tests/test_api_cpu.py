@@ -557,3 +557,26 @@ def test_server_mode_clients_drive_queries_on_a_server(tmp_path):
         assert sorted(ids.tolist()) == list(range(fixtures.N_USER))           # every client traverses the server's users once
         ok = iid >= 0
         assert np.allclose(fa[..., 1][ok], iid[ok] + 0.25)                      # item_float(i, 1) = i + 0.25
+
+
+def test_dedup_before_pull_lookup(tmp_path):
+    """gl.set_dedup_feature_pull(True): attribute lookups fetch distinct rows once and expand by index - same answers"""
+    import numpy as np
+    import graphlearn_b200 as gl
+    from graphlearn_b200.ops import gather as G
+    from tests import fixtures as fx
+    d = fx.write_graph(str(tmp_path))
+    g = fx.build_graph(d)
+    ids = np.array([[3, 3, 7], [7, 3, 1]])
+    a = g.get_nodes("item", ids).float_attrs
+    gl.set_dedup_feature_pull(True)
+    try:
+        b = g.get_nodes("item", ids).float_attrs
+        tab = g.store.nodes["item"]
+        v = tab.idmap.to_vid(__import__("torch").tensor([5, -1, 5, 2, -1]))
+        x = G.gather_rows_dedup(g.runtime, tab.feats, tab.feat_desc, v, tab.float_dim, fill=9.0)
+        y = G.gather_rows(g.runtime, tab.feats, tab.feat_desc, v, tab.float_dim, fill=9.0)
+    finally:
+        gl.set_dedup_feature_pull(False)
+    assert np.array_equal(a, b) and bool((x == y).all())
+    g.close()
