@@ -41,8 +41,9 @@ from . import nn  # noqa: E402,F401  (gl.nn, like the reference's `import graphl
 
 class IndexOption(object):
     """KNN index options of the reference (graphlearn/python/c/py_export.cc): ``index_type`` in
-    flat | ivfflat | ivfpq (+ the ``gpu_`` variants); flat = fused tcgen05 scan, ivfflat = k-means lists probed
-    with the same kernel, ivfpq falls back to ivfflat (ops/knn.py)."""
+    flat | ivfflat | ivfpq (+ the ``gpu_`` variants); flat = fused tcgen05 scan, ivfflat = k-means lists scanned
+    exactly, ivfpq = the same lists with ``m`` one-byte product-quantiser codes per row, scored by look-up tables and
+    re-ranked exactly (ops/knn.py)."""
 
     def __init__(self):
         self.name = "knn"

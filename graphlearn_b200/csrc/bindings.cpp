@@ -94,6 +94,8 @@ std::vector<at::Tensor> knn_flat_topk(const at::Tensor&, int64_t, const c10::opt
 std::vector<at::Tensor> knn_ivf_search(const at::Tensor&, int64_t, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, int64_t,
                                        int64_t);
 std::vector<at::Tensor> knn_merge_peers(const at::Tensor&, int64_t, int64_t, int64_t, const at::Tensor&);
+std::vector<at::Tensor> knn_ivfpq_search(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
+                                         const at::Tensor&, int64_t, int64_t);
 // dgs.cu
 void dgs_apply_edges(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
                      const at::Tensor&, const c10::optional<at::Tensor>&);
@@ -203,6 +205,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("knn_flat_topk", &glb::knn_flat_topk);
   m.def("knn_merge_peers", &glb::knn_merge_peers);
   m.def("knn_ivf_search", &glb::knn_ivf_search);
+  m.def("knn_ivfpq_search", &glb::knn_ivfpq_search);
   m.def("dgs_apply_edges", &glb::dgs_apply_edges);
   m.def("dgs_lookup", &glb::dgs_lookup);
   m.def("load_table", &glb::load_table);

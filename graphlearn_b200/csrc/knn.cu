@@ -505,4 +505,166 @@ std::vector<at::Tensor> knn_ivf_search(const at::Tensor& x, int64_t dim, const a
   return {out_s, out_i};
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// IVF-PQ list scan (index_factory.cc:40-50 'ivfpq'): one CTA per (query, probed list).  Rows are stored as M one-byte
+// codes of their residual to the list centroid; the CTA first builds the asymmetric-distance table
+// LUT[m][c] = -|r_m - codebook[m][c]|^2 (L2, r = q - centroid) or <q_m, codebook[m][c]> (inner product, plus the constant
+// <q, centroid>) in shared memory, then every lane scores one row per iteration with M shared-memory look-ups and the
+// warps keep their k best behind a threshold exactly like the IVF-flat scan.  Output: [nprobe * 8 warps, B, k].
+// ---------------------------------------------------------------------------------------------------------------
+struct KnnPqParams {
+  const uint8_t* codes;        // [n, M] in list order (position-indexed)
+  const int64_t* order;        // position -> row
+  const int64_t* offsets;      // [nlist + 1]
+  const float* q;              // [B, dim]  (dim = M * dsub, zero padded)
+  const int64_t* probes;       // [B, nprobe]
+  const float* centroids;      // [nlist, dim]
+  const float* codebooks;      // [M, 256, dsub]
+  int B, nprobe, k, metric, M, dsub;
+  float* out_s; int64_t* out_i;   // [nprobe * 8, B, k]
+};
+
+constexpr int kPqWarps = 8;
+
+__global__ void __launch_bounds__(kPqWarps * 32) knn_ivfpq_scan_kernel(const KnnPqParams p) {
+  extern __shared__ float pq_smem[];
+  const int dim = p.M * p.dsub;
+  float* lut = pq_smem;                                   // [M][256]
+  float* sr = lut + p.M * 256;                            // [dim] residual (L2) or the query (inner product)
+  float* tv = sr + ((dim + 3) & ~3);                      // [warps][k]
+  int* ti = reinterpret_cast<int*>(tv + kPqWarps * p.k);  // [warps][k]
+  __shared__ float s_bias;
+  const int probe = blockIdx.x, qi = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t l = p.probes[(size_t)qi * p.nprobe + probe];
+  const int64_t lo = p.offsets[l], hi = p.offsets[l + 1];
+  const float* cen = p.centroids + (size_t)l * dim;
+  for (int f = tid; f < dim; f += blockDim.x) {
+    const float qv = p.q[(size_t)qi * dim + f];
+    sr[f] = p.metric == 1 ? qv : qv - __ldg(cen + f);
+  }
+  for (int e = tid; e < kPqWarps * p.k; e += blockDim.x) { tv[e] = -FLT_MAX; ti[e] = -1; }
+  if (warp == 0) {                                         // <q, centroid>: the part of an inner product the codes do not carry
+    float b = 0.f;
+    if (p.metric == 1) for (int f = lane; f < dim; f += 32) b = fmaf(p.q[(size_t)qi * dim + f], __ldg(cen + f), b);
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (lane == 0) s_bias = b;
+  }
+  __syncthreads();
+  if (hi > lo) {
+    for (int e = tid; e < p.M * 256; e += blockDim.x) {
+      const int m = e >> 8;
+      const float* cb = p.codebooks + (size_t)e * p.dsub;
+      const float* r = sr + m * p.dsub;
+      float acc = 0.f;
+      for (int d = 0; d < p.dsub; ++d) {
+        const float c = __ldg(cb + d);
+        if (p.metric == 1) acc = fmaf(r[d], c, acc);
+        else { const float dlt = r[d] - c; acc = fmaf(-dlt, dlt, acc); }
+      }
+      lut[e] = acc;
+    }
+  }
+  __syncthreads();
+  const float bias = s_bias;
+  float* mv = tv + warp * p.k;
+  int* mi = ti + warp * p.k;
+  float thr = -FLT_MAX;
+  int thr_pos = 0;
+  const bool words = (p.M & 3) == 0;
+  for (int64_t base = lo + (int64_t)warp * 32; base < hi; base += (int64_t)kPqWarps * 32) {
+    const int64_t pos = base + lane;
+    float acc = bias;
+    if (pos < hi) {
+      const uint8_t* code = p.codes + (size_t)pos * p.M;
+      if (words) {
+        const uint32_t* cw = reinterpret_cast<const uint32_t*>(code);
+        for (int m = 0; m < p.M; m += 4) {
+          const uint32_t w = __ldg(cw + (m >> 2));
+          acc += lut[(m + 0) * 256 + (w & 255u)];
+          acc += lut[(m + 1) * 256 + ((w >> 8) & 255u)];
+          acc += lut[(m + 2) * 256 + ((w >> 16) & 255u)];
+          acc += lut[(m + 3) * 256 + (w >> 24)];
+        }
+      } else {
+        for (int m = 0; m < p.M; ++m) acc += lut[m * 256 + __ldg(code + m)];
+      }
+    }
+    unsigned cand = __ballot_sync(0xffffffffu, pos < hi && acc > thr);
+    while (cand) {                                          // warp-uniform: lanes whose score beats the threshold
+      const int g = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float sc = __shfl_sync(0xffffffffu, acc, g);
+      if (sc > thr) {
+        if (lane == 0) { mv[thr_pos] = sc; mi[thr_pos] = (int)(base + g - lo); }
+        __syncwarp();
+        float mn = FLT_MAX; int mp = 0;
+        for (int e = lane; e < p.k; e += 32) { const float v = mv[e]; if (v < mn) { mn = v; mp = e; } }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, mn, o);
+          const int op = __shfl_xor_sync(0xffffffffu, mp, o);
+          if (om < mn || (om == mn && op < mp)) { mn = om; mp = op; }
+        }
+        thr = mn; thr_pos = mp;
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+  const size_t ob = (((size_t)probe * kPqWarps + warp) * p.B + qi) * p.k;
+  for (int e = lane; e < p.k; e += 32) {
+    const int pi = mi[e];
+    p.out_s[ob + e] = mv[e];
+    p.out_i[ob + e] = pi >= 0 ? __ldg(p.order + lo + pi) : -1;
+  }
+}
+
+// IVF-PQ search: (approximate scores [B, k] best first, rows [B, k]) over the probed lists of every query.
+std::vector<at::Tensor> knn_ivfpq_search(const at::Tensor& codes, const at::Tensor& order, const at::Tensor& offsets, const at::Tensor& q,
+                                         const at::Tensor& probes, const at::Tensor& centroids, const at::Tensor& codebooks, int64_t k,
+                                         int64_t metric) {
+  TORCH_CHECK(codes.is_cuda() && codes.scalar_type() == at::kByte && codes.dim() == 2 && codes.is_contiguous(), "codes must be uint8 [n, M]");
+  TORCH_CHECK(codebooks.is_cuda() && codebooks.scalar_type() == at::kFloat && codebooks.dim() == 3 && codebooks.size(1) == 256 &&
+              codebooks.is_contiguous() && codebooks.size(0) == codes.size(1), "codebooks must be fp32 [M, 256, dsub]");
+  const int64_t M = codes.size(1), dsub = codebooks.size(2), dim = M * dsub;
+  check_cuda_i64(order, "order"); check_cuda_i64(offsets, "offsets"); check_cuda_i64(probes, "probes");
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kFloat && q.dim() == 2 && q.size(1) == dim && q.is_contiguous(), "q must be fp32 [B, M * dsub]");
+  TORCH_CHECK(centroids.is_cuda() && centroids.scalar_type() == at::kFloat && centroids.dim() == 2 && centroids.size(1) == dim &&
+              centroids.is_contiguous() && centroids.size(0) + 1 == offsets.numel());
+  TORCH_CHECK(probes.dim() == 2 && probes.size(0) == q.size(0) && probes.is_contiguous() && order.is_contiguous() && offsets.is_contiguous());
+  TORCH_CHECK(order.numel() == codes.size(0));
+  TORCH_CHECK(k >= 1 && k <= kKnnMaxK && M >= 1 && M <= 128);
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(codes.data_ptr()) & 3) == 0);
+  c10::cuda::CUDAGuard guard(codes.device());
+  const int64_t B = q.size(0), nprobe = probes.size(1);
+  auto of = q.options().dtype(at::kFloat);
+  auto oi = q.options().dtype(at::kLong);
+  auto out_s = at::empty({B, k}, of);
+  auto out_i = at::empty({B, k}, oi);
+  if (B == 0) return {out_s, out_i};
+  auto part_s = at::empty({nprobe * kPqWarps, B, k}, of);
+  auto part_i = at::empty({nprobe * kPqWarps, B, k}, oi);
+  KnnPqParams p;
+  p.codes = codes.data_ptr<uint8_t>(); p.order = order.data_ptr<int64_t>(); p.offsets = offsets.data_ptr<int64_t>();
+  p.q = q.data_ptr<float>(); p.probes = probes.data_ptr<int64_t>(); p.centroids = centroids.data_ptr<float>();
+  p.codebooks = codebooks.data_ptr<float>();
+  p.B = (int)B; p.nprobe = (int)nprobe; p.k = (int)k; p.metric = (int)metric; p.M = (int)M; p.dsub = (int)dsub;
+  p.out_s = part_s.data_ptr<float>(); p.out_i = part_i.data_ptr<int64_t>();
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const size_t smem = (size_t)M * 256 * 4 + (((size_t)dim + 3) & ~(size_t)3) * 4 + (size_t)kPqWarps * k * 8;
+  TORCH_CHECK(smem <= 200 * 1024, "PQ look-up table too large for shared memory");
+  static size_t attr = 48 * 1024;
+  if (smem > attr) { C10_CUDA_CHECK(cudaFuncSetAttribute(knn_ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  knn_ivfpq_scan_kernel<<<dim3((unsigned)nprobe, (unsigned)B), kPqWarps * 32, smem, stream>>>(p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  KnnMergeParams m;
+  std::memset(&m, 0, sizeof(m));
+  m.cand_s.p[0] = part_s.data_ptr(); m.cand_i.p[0] = part_i.data_ptr();
+  m.n_src = 1; m.n_lists = (int)(nprobe * kPqWarps); m.qstride = (int)B; m.k = (int)k; m.B = (int)B; m.id_scale = 0;
+  m.out_s = out_s.data_ptr<float>(); m.out_i = out_i.data_ptr<int64_t>();
+  launch_merge(m, stream);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {out_s, out_i};
+}
+
 }  // namespace glb

@@ -9,6 +9,10 @@ broadcast to every server and the per-server top-k lists are merged with a k-hea
   candidates (2k, scored from bf16 operands) are re-ranked in fp32 so the result equals an fp32 brute force;
 * **ivfflat** - k-means coarse quantiser at build time, inverted lists = a row permutation; a query probes its
   ``nprobe`` nearest lists with the same kernel (row-index-list mode);
+* **ivfpq** - the same coarse quantiser, rows stored as ``m`` one-byte product-quantiser codes of their residual to
+  the list centroid; ``knn_ivfpq_scan_kernel`` builds the asymmetric-distance table of a (query, list) pair in shared
+  memory and scores a row with ``m`` look-ups; the best candidates are re-ranked with the exact rows (they stay in
+  HBM anyway), so reported distances are exact;
 * multi-GPU: every rank searches its shard, writes its list into a symmetric buffer and merges all peers' lists
   with peer loads over NVLink (no NCCL on the data path).
 
@@ -156,14 +160,131 @@ class IvfFlatIndex(object):
         return best_s, best_i
 
 
+def _kmeans(x: torch.Tensor, k: int, iters: int, g: torch.Generator) -> torch.Tensor:
+    """plain Lloyd iterations on the rows of x -> [k, d] centroids (empty clusters keep their previous centre)."""
+    n = x.size(0)
+    if n == 0:
+        return torch.zeros(k, x.size(1), device=x.device)
+    pick = torch.randperm(n, device=x.device, generator=g)[:k]
+    cent = x[pick].clone()
+    if cent.size(0) < k:                                                 # fewer points than centres: repeat points
+        cent = torch.cat([cent, x[torch.randint(0, n, (k - cent.size(0),), device=x.device, generator=g)]])
+    for _ in range(iters):
+        a = torch.cdist(x, cent).argmin(1)
+        cnt = torch.bincount(a, minlength=k)
+        sums = torch.zeros_like(cent).index_add_(0, a, x)
+        cent = torch.where((cnt > 0).unsqueeze(1), sums / cnt.clamp(min=1).unsqueeze(1), cent)
+    return cent
+
+
+class IvfPqIndex(IvfFlatIndex):
+    """IVF-PQ (index_factory.cc:40-50 'ivfpq' / 'gpu_ivfpq', ``IndexOption.m`` sub-quantisers of 8 bits): the coarse
+    quantiser and inverted lists of :class:`IvfFlatIndex`; every row is stored as ``m`` bytes - the nearest of 256
+    codewords per sub-space of its residual to the list centroid.  A search scores rows by asymmetric distance
+    computation (query-side look-up table, one table per (query, list)), keeps ``refine * k`` candidates and re-ranks
+    them with the exact rows (``refine = 0``: return the quantised scores like a plain faiss IndexIVFPQ)."""
+
+    def __init__(self, table, x: torch.Tensor, dim: int, nlist: int, nprobe: int, metric: int, m: int = 0, iters: int = 8,
+                 seed: int = 0, refine: int = 4):
+        super().__init__(table, x, dim, nlist, nprobe, metric, iters=iters, seed=seed)
+        n = x.size(0)
+        m = int(m) if m else max(1, min(64, dim // 4))
+        self.m = max(1, min(m, dim, 128))
+        self.dsub = (dim + self.m - 1) // self.m
+        self.dimp = self.m * self.dsub                                  # dim padded to a multiple of m
+        self.refine = int(refine)
+        g = torch.Generator(device=x.device).manual_seed(seed + 1)
+        cent = self._pad(self.centroids)
+        self.centroids_p = cent.contiguous()
+        # assignment of every row (list order is a stable sort of it): recover it from the offsets
+        assign_sorted = torch.repeat_interleave(torch.arange(self.nlist, device=x.device), self.offsets[1:] - self.offsets[:-1])
+        # residuals in LIST ORDER, chunked
+        books = torch.zeros(self.m, 256, self.dsub, device=x.device)
+        n_train = min(n, 256 * 64)
+        if n > 0:
+            tp = torch.randperm(n, device=x.device, generator=g)[:n_train]
+            tr = self._pad(x[self.order[tp], :dim].float()) - cent[assign_sorted[tp]]
+            for j in range(self.m):
+                books[j] = _kmeans(tr[:, j * self.dsub:(j + 1) * self.dsub].contiguous(), 256, iters, g)
+        self.codebooks = books.contiguous()
+        codes = torch.empty(n, self.m, dtype=torch.uint8, device=x.device)
+        for s in range(0, n, 1 << 16):
+            pos = slice(s, min(n, s + (1 << 16)))
+            r = self._pad(x[self.order[pos], :dim].float()) - cent[assign_sorted[pos]]
+            for j in range(self.m):
+                codes[pos, j] = torch.cdist(r[:, j * self.dsub:(j + 1) * self.dsub], books[j]).argmin(1).to(torch.uint8)
+        self.codes = codes.contiguous()
+
+    def _pad(self, v: torch.Tensor) -> torch.Tensor:
+        if v.size(1) == self.dimp:
+            return v
+        return torch.cat([v, torch.zeros(v.size(0), self.dimp - v.size(1), device=v.device, dtype=v.dtype)], 1)
+
+    def code_bytes(self) -> int:
+        return int(self.codes.numel())
+
+    def _adc_portable(self, q: torch.Tensor, probes: torch.Tensor, kk: int):
+        """torch oracle of the scan kernel: same tables, same codes."""
+        B = q.size(0)
+        best_s = torch.full((B, kk), float("-inf"), device=q.device)
+        best_i = torch.full((B, kk), -1, dtype=torch.int64, device=q.device)
+        offs = self.offsets.tolist()
+        ar = torch.arange(self.m, device=q.device)
+        for b in range(B):
+            cs, ci = [best_s[b]], [best_i[b]]
+            for l in probes[b].tolist():
+                lo, hi = offs[l], offs[l + 1]
+                if hi == lo:
+                    continue
+                if self.metric == 1:
+                    r = q[b].view(self.m, 1, self.dsub)
+                    lut = (r * self.codebooks).sum(2)                                      # [m, 256]
+                    bias = (q[b] * self.centroids_p[l]).sum()
+                else:
+                    r = (q[b] - self.centroids_p[l]).view(self.m, 1, self.dsub)
+                    lut = -((r - self.codebooks) ** 2).sum(2)
+                    bias = 0.0
+                sc = lut[ar[None, :], self.codes[lo:hi].long()].sum(1) + bias
+                cs.append(sc); ci.append(self.order[lo:hi])
+            cs, ci = torch.cat(cs), torch.cat(ci)
+            v, j = torch.topk(cs, min(kk, cs.numel()))
+            best_s[b, :v.numel()], best_i[b, :v.numel()] = v, ci[j]
+        best_i = torch.where(torch.isinf(best_s), torch.full_like(best_i, -1), best_i)
+        return best_s, best_i
+
+    def search(self, q: torch.Tensor, k: int, use_kernel: bool):
+        qf = q.float()
+        probes = torch.cdist(qf, self.centroids).topk(self.nprobe, dim=1, largest=False).indices.contiguous()
+        qp = self._pad(qf).contiguous()
+        kk = k if self.refine <= 0 else min(64, max(k, self.refine * k))
+        if use_kernel and kk <= 64:
+            from ..parallel.runtime import native
+            s, r = native().knn_ivfpq_search(self.codes, self.order, self.offsets, qp, probes, self.centroids_p, self.codebooks,
+                                             int(kk), int(self.metric))
+            s = torch.where(r >= 0, s, torch.full_like(s, float("-inf")))
+        else:
+            s, r = self._adc_portable(qp, probes, kk)
+        if self.refine <= 0:
+            return s, r
+        # exact re-rank of the kk candidates
+        ok = r >= 0
+        xr = self.x[r.clamp(min=0), :self.dim].float()                                     # [B, kk, d]
+        ip = torch.einsum("bd,bkd->bk", qf, xr)
+        sc = ip if self.metric == 1 else -((qf ** 2).sum(1, keepdim=True) - 2 * ip + (xr ** 2).sum(2))
+        sc = torch.where(ok, sc, torch.full_like(sc, float("-inf")))
+        v, j = torch.topk(sc, min(k, kk), dim=1)
+        rows = torch.gather(r, 1, j)
+        rows = torch.where(torch.isinf(v), torch.full_like(rows, -1), rows)
+        return v, rows
+
+
 def build_index(table, option) -> None:
     """``g.node(..., option=gl.IndexOption())``: attach the requested index to the node table
     (graphlearn/src/contrib/knn/builder.cc:23-52, local_noder.cc:44-51)."""
     itype = getattr(option, "index_type", "flat") or "flat"
     itype = itype.replace("gpu_", "")
-    if itype == "ivfpq":
-        itype = "ivfflat"       # product quantisation is not implemented: the exact-list index is the stand-in
-    table._knn_option = (itype, int(getattr(option, "nlist", 0) or 0), int(getattr(option, "nprobe", 0) or 0))
+    table._knn_option = (itype, int(getattr(option, "nlist", 0) or 0), int(getattr(option, "nprobe", 0) or 0),
+                         int(getattr(option, "m", 0) or 0))
     table._knn_index = None
 
 
@@ -175,11 +296,15 @@ def search(rt, table, queries: torch.Tensor, k: int, metric: int = 0):
     x_full = table.feats.local
     x = x_full[:, :dim]
     kern = _use_kernel(rt, x) and k <= 64
-    itype, nlist, nprobe = getattr(table, "_knn_option", ("flat", 0, 0))
-    if itype == "ivfflat":
+    itype, nlist, nprobe, pq_m = (tuple(getattr(table, "_knn_option", ("flat", 0, 0, 0))) + (0,))[:4]
+    if itype in ("ivfflat", "ivfpq"):
         idx = getattr(table, "_knn_index", None)
         if idx is None or idx.x.data_ptr() != x_full.data_ptr() or idx.metric != metric:
-            idx = IvfFlatIndex(table, x_full, dim, nlist or max(1, int(x.size(0) ** 0.5)), nprobe, metric)
+            nl = nlist or max(1, int(x.size(0) ** 0.5))
+            if itype == "ivfpq" and x_full.dtype in (torch.float32, torch.bfloat16):
+                idx = IvfPqIndex(table, x_full, dim, nl, nprobe, metric, m=pq_m)
+            else:
+                idx = IvfFlatIndex(table, x_full, dim, nl, nprobe, metric)
             table._knn_index = idx
         s, rows = idx.search(q, k, kern)
     elif kern:

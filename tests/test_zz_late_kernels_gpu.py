@@ -1,0 +1,49 @@
+"""Kernels added late in round 2 (collected last on purpose: their first driver-side run must not hide the rest of the
+suite behind ``-x``).  Every test compares a CUDA kernel with a plain PyTorch oracle of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(rt, x, dtype=torch.float32):
+    from graphlearn_b200.store.shards import IdMap, NodeTable
+    t = NodeTable(rt, "t", IdMap(rt, torch.arange(x.size(0), device=rt.device), dense=True))
+    t.set_float(x, dtype)
+    return t
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("m,d", [(8, 64), (5, 30)])
+def test_knn_ivfpq_scan_kernel(metric, m, d):
+    """csrc/knn.cu knn_ivfpq_scan_kernel vs the torch ADC oracle on the SAME codes / tables (word and byte code loads,
+    padded dims), then the public path: IVF-PQ + exact re-rank finds the true neighbours of clustered data."""
+    import graphlearn_b200 as gl
+    from graphlearn_b200.ops import knn
+    from graphlearn_b200.parallel.runtime import init
+    rt = init()
+    g = torch.Generator(device=rt.device).manual_seed(11)
+    n, B, k = 20000, 70, 10
+    centres = torch.randn(50, d, device=rt.device, generator=g) * 4
+    x = centres[torch.randint(0, 50, (n,), device=rt.device, generator=g)] + 0.3 * torch.randn(n, d, device=rt.device, generator=g)
+    t = _table(rt, x)
+    q = x[:B] + 0.01 * torch.randn(B, d, device=rt.device, generator=g)
+    idx = knn.IvfPqIndex(t, t.feats.local, d, 32, 8, metric, m=m, refine=0)
+    s_k, r_k = idx.search(q, k, True)
+    s_o, r_o = idx.search(q, k, False)
+    assert torch.allclose(s_k, s_o, rtol=1e-4, atol=1e-3)
+    # ids may differ only where scores tie (identical codes): compare as sets wherever the k-th score is separated
+    same = (torch.sort(r_k, 1).values == torch.sort(r_o, 1).values).all(1)
+    assert same.float().mean() > 0.9
+    # through the public search with the exact re-rank
+    opt = gl.IndexOption(); opt.index_type = "gpu_ivfpq"; opt.nlist = 32; opt.nprobe = 16; opt.m = m
+    knn.build_index(t, opt)
+    ids, dist = knn.search(rt, t, q, k, metric)
+    xs = t.feats.local[:, :d].float()
+    sc = q @ xs.t() if metric == 1 else -torch.cdist(q, xs) ** 2
+    ref_s, ref_i = torch.topk(sc, k, dim=1)
+    hit = (ids[:, :, None] == ref_i[:, None, :]).any(2).float().mean()
+    assert hit > (0.8 if metric == 0 else 0.5), float(hit)
+    if metric == 0:
+        assert (ids[:, 0] == torch.arange(B, device=rt.device)).all()
+        assert torch.allclose(dist[:, 0], -ref_s[:, 0], atol=1e-2)
