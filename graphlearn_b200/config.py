@@ -66,6 +66,7 @@ class Config:
     loader_threads: int = 0           # 0 = auto: all cores divided by the number of ranks on the box
     use_peer_kernels: bool = True        # False -> torch.distributed (NCCL/gloo) baseline path
     dedup_feature_pull: bool = False     # attribute lookups of GSL results fetch every distinct row once (ops/gather.py)
+    native_csr_build: bool = True        # CUDA shards: counting build (csrc/csr_build.cu) instead of two global stable sorts
     feature_row_align: int = 128         # bytes: feature rows wider than half of this start on such a boundary (16 = dense rows)
     seed: int = 0
     actor_enabled: bool = False
@@ -146,6 +147,7 @@ set_feature_dtype = _setter("feature_dtype", str)
 set_loader_threads = _setter("loader_threads", int)
 set_use_peer_kernels = _setter("use_peer_kernels", bool)
 set_feature_row_align = _setter("feature_row_align", int)
+set_native_csr_build = _setter("native_csr_build", bool)
 set_dedup_feature_pull = _setter("dedup_feature_pull", bool)
 set_seed = _setter("seed", int)
 

@@ -88,6 +88,8 @@ std::vector<at::Tensor> gat_agg_backward(const at::Tensor&, const at::Tensor&, c
                                          const at::Tensor&, bool);
 // idmap.cu
 at::Tensor idmap_translate(const at::Tensor&, const at::Tensor&, bool);
+// csr_build.cu
+std::vector<at::Tensor> csr_build(const at::Tensor&, int64_t, const c10::optional<at::Tensor>&, int64_t);
 // knn.cu
 std::vector<at::Tensor> knn_flat_topk(const at::Tensor&, int64_t, const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&,
                                       const at::Tensor&, int64_t, int64_t);
@@ -202,6 +204,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gat_agg_forward", &glb::gat_agg_forward);
   m.def("gat_agg_backward", &glb::gat_agg_backward);
   m.def("idmap_translate", &glb::idmap_translate);
+  m.def("csr_build", &glb::csr_build);
   m.def("knn_flat_topk", &glb::knn_flat_topk);
   m.def("knn_merge_peers", &glb::knn_merge_peers);
   m.def("knn_ivf_search", &glb::knn_ivf_search);

@@ -26,8 +26,12 @@ state in HBM tables:
                       ``LogChannel`` topics (workers.py), driven by ``Coordinator`` (worker registry, barriers,
                       consistent cluster checkpoints)
 
-The Java client and the Helm chart are deployment glue around this core and are out of scope; record batches are
-dicts of arrays (``LogChannel`` persists them as torch segments instead of Kafka/FlatBuffers).
+* ``client``            GSL client for Python programs (the role of the reference's Java client: ``Graph.connect`` /
+                      fluent traversal -> install-query JSON / ``install`` / ``run`` / ``EgoGraph`` hop tensors), client.py
+* ``python -m graphlearn_b200.dgs``   service process entry point (restore -> install -> load -> serve -> final checkpoint),
+                      scheduled by the Helm chart in ``deploy/dgs``
+
+Record batches are dicts of arrays (``LogChannel`` persists them as columnar binary segments instead of Kafka/FlatBuffers).
 """
 from .coordinator import BarrierMonitor, CheckpointManager, Coordinator, WorkerRegistry  # noqa: F401
 from .file_loader import FileLoader, GroupProducer, RecordBatchBuilder, decode_record_batch, encode_record_batch  # noqa: F401

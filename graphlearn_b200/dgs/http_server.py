@@ -10,6 +10,8 @@ device stream by a lock.
   POST /admin/checkpoint               -> {"checkpoint_id": n}
   POST /admin/barrier/set?name=x[&produced=n]     GET /admin/barrier/status?name=x
   GET  /admin/stats                    liveness + counters (k8s probes)
+  GET  /admin/schema                   the graph schema (reference JSON)        GET /admin/query[?qid=n]  an installed query
+The Python GSL client (``dgs/client.py``, the role of the reference's Java client) speaks exactly this surface.
 """
 from __future__ import annotations
 
@@ -40,6 +42,7 @@ class HttpFrontEnd(object):
         self.ckpt = CheckpointManager(service, checkpoint_dir) if checkpoint_dir else None
         self.barriers = BarrierMonitor(service)
         self._lock = threading.Lock()
+        self.installed = {}                 # qid -> install-query JSON (+ node_ids), answered by /admin/query
         front = self
 
         class Handler(BaseHTTPRequestHandler):
@@ -71,6 +74,14 @@ class HttpFrontEnd(object):
                         self._send(200, front.service.stats())
                     elif u.path == "/admin/barrier/status":
                         self._send(200, {"status": front.barriers.status(q["name"][0])})
+                    elif u.path == "/admin/schema":
+                        self._send(200, front.schema.raw if front.schema is not None else {})
+                    elif u.path == "/admin/query":
+                        if not front.installed:
+                            self._send(404, {"error": "no query installed"})
+                        else:
+                            qid = int(q["qid"][0]) if "qid" in q else max(front.installed)
+                            self._send(200, front.installed[qid])
                     else:
                         self._send(404, {"error": "unknown path"})
                 except Exception as e:  # noqa: BLE001
@@ -86,7 +97,9 @@ class HttpFrontEnd(object):
                         qid = int(d.get("query_id", len(front.service.queries)))
                         with front._lock:
                             front.service.install_query(qid, plan)
-                        self._send(200, {"query_id": qid})
+                        node_ids = {str(k): int(v) for k, v in getattr(plan, "json_ids", {}).items()}
+                        front.installed[qid] = {**d, "query_id": qid, "node_ids": node_ids}
+                        self._send(200, {"query_id": qid, "node_ids": node_ids})
                     elif u.path == "/admin/ingest":
                         with front._lock:
                             front.service.apply_updates(self._body())

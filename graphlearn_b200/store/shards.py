@@ -451,21 +451,29 @@ class CsrShard:
         E = int(src_rows.numel())
         dev = src_rows.device
         order = torch.arange(E, device=dev)
-        if E > 0:
+        indptr = None
+        grouped = E > 0 and ts is None and weights is None and bool((src_rows[1:] >= src_rows[:-1]).all())
+        if E > 0 and not grouped and dev.type == "cuda" and _config.get().native_csr_build:
+            # counting build (csrc/csr_build.cu): histogram -> prefix sum -> scatter -> per-row sort; the same permutation
+            # as the two stable sorts below, without sorting E keys globally
+            from ..parallel.runtime import native
+            if ts is not None:
+                indptr, order = native().csr_build(src_rows.contiguous(), n_src_rows, ts.to(torch.int64), 1)
+            elif weights is not None:
+                indptr, order = native().csr_build(src_rows.contiguous(), n_src_rows, weights.to(torch.float32), 2)
+            else:
+                indptr, order = native().csr_build(src_rows.contiguous(), n_src_rows, None, 0)
+        elif E > 0 and not grouped:
             if ts is not None:
                 order = torch.argsort(ts, stable=True)
             elif weights is not None:
                 order = torch.argsort(weights, descending=True, stable=True)
-            elif bool((src_rows[1:] >= src_rows[:-1]).all()):
-                order = None                      # already grouped by source row (the common file layout)
-            if order is None:
-                order = torch.arange(E, device=dev)
-            else:
-                order = order[torch.argsort(src_rows[order], stable=True)]
+            order = order[torch.argsort(src_rows[order], stable=True)]
         srt = src_rows[order]
-        counts = torch.bincount(srt, minlength=n_src_rows) if E > 0 else torch.zeros(n_src_rows, dtype=torch.int64, device=dev)
-        indptr = torch.zeros(n_src_rows + 1, dtype=torch.int64, device=dev)
-        indptr[1:] = torch.cumsum(counts, 0)
+        if indptr is None:
+            counts = torch.bincount(srt, minlength=n_src_rows) if E > 0 else torch.zeros(n_src_rows, dtype=torch.int64, device=dev)
+            indptr = torch.zeros(n_src_rows + 1, dtype=torch.int64, device=dev)
+            indptr[1:] = torch.cumsum(counts, 0)
         self.n_src_rows = n_src_rows
         self.n_edges = E
         self.indptr = rt.symm_from(indptr)

@@ -1,5 +1,6 @@
 """Streaming sampler service (GPU-native DGS analogue) - semantics vs a Python oracle."""
 import numpy as np
+import pytest
 import torch
 
 from graphlearn_b200.dgs import AdaptiveRateLimiter, DynamicGraphService, QueryPlan
@@ -125,6 +126,71 @@ def test_reference_config_formats_file_loader_http_and_checkpoints(tmp_path):
     assert CheckpointManager(svc2, str(tmp_path / "ck")).restore_latest() == 1
     a, b = svc.run_query(7, [1, 3]), svc2.run_query(7, [1, 3])
     assert torch.equal(a["hops"][0]["ids"], b["hops"][0]["ids"]) and torch.equal(a["hops"][1]["ids"], b["hops"][1]["ids"])
+
+
+def test_gsl_client_over_http(tmp_path):
+    """dgs/client.py (the role of the reference's Java GSL client): fluent traversal -> install-query JSON -> /admin/init,
+    run -> alias-keyed numpy results, EgoGraph hop tensors, barrier / schema / registered-query calls, error paths."""
+    import numpy as np
+    from graphlearn_b200.dgs import HttpFrontEnd, Schema
+    from graphlearn_b200.dgs import client as C
+    schema = Schema({
+        "attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}, {"type": 2, "name": "feature", "value_type": "FLOAT32_LIST"}],
+        "vertex_defs": [{"vtype": 0, "name": "user", "attr_types": [0, 2]}, {"vtype": 1, "name": "item", "attr_types": [0, 2]}],
+        "edge_defs": [{"etype": 2, "name": "u2i", "attr_types": [0]}, {"etype": 3, "name": "i2i", "attr_types": [0]}],
+        "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}, {"etype": 3, "src_vtype": 1, "dst_vtype": 1}]})
+    svc = DynamicGraphService(schema.to_service_schema(capacity=64, feat_dims={"user": 2, "item": 3}), device="cpu")
+    front = HttpFrontEnd(svc, schema).start()
+    try:
+        g = C.Graph.connect("127.0.0.1:%d" % front.port)
+        assert g.get_schema()["relations"] == {"u2i": ("user", "item"), "i2i": ("item", "item")}
+        with pytest.raises(C.UserException):
+            g.V("nobody")
+        with pytest.raises(C.UserException):
+            g.V("user").outV("i2i")                      # i2i starts at items
+        with pytest.raises(C.UserException):
+            g.V("user").outV("u2i").sample(3).by("random")
+        with pytest.raises(C.UserException):
+            g.V("user").outV("u2i").sample(3).values()   # no data source
+        src = C.DataSource([3, 4, 5], batch=2)
+        q = (g.V("user").feed(src).properties(1).alias("seed")
+              .outV("u2i").sample(3).by("topk_by_timestamp").properties(1).alias("hop1")
+              .outV("i2i").sample(2).by("topk_by_timestamp").alias("hop2").values())
+        kinds = [n["kind"] for n in q.to_json()["query_plan"]["plan_nodes"]]
+        assert kinds == ["SOURCE", "VERTEX_SAMPLER", "EDGE_SAMPLER", "VERTEX_SAMPLER", "EDGE_SAMPLER"]
+        with pytest.raises(C.UserException):
+            g.run(q)                                     # not installed yet
+        assert g.install_async(q).result(timeout=10).ok() and q.id is not None
+        svc.apply_updates({"vertices": {"user": {"id": list(range(8)), "ts": [1] * 8, "feat": [[u, 0.5] for u in range(8)]},
+                                        "item": {"id": list(range(20)), "ts": [1] * 20, "feat": [[i, 1.0, 2.0] for i in range(20)]}},
+                           "edges": {"u2i": {"src": [3, 3, 3, 3, 4], "dst": [10, 11, 12, 13, 14], "ts": [5, 6, 7, 8, 9]},
+                                     "i2i": {"src": [13, 13, 12], "dst": [1, 2, 3], "ts": [1, 2, 3]}}})
+        v = g.run(q)                                     # ids 3, 4 from the data source
+        assert v["seed"]["ids"].tolist() == [3, 4] and np.allclose(v["seed"]["features"], [[3, 0.5], [4, 0.5]])
+        assert v["hop1"]["ids"].tolist() == [[13, 12, 11], [14, -1, -1]]
+        assert v["hop1"]["features"].shape == (2, 3, 3) and v["hop1"]["features"][0, 0].tolist() == [13.0, 1.0, 2.0]
+        assert v["hop2"]["ids"].reshape(2, 3, 2)[0].tolist() == [[2, 1], [3, -1], [-1, -1]]
+        ego = v.ego_graph()
+        assert ego.num_hops() == 2 and ego.fanouts == [3, 2] and ego.get_vtype(1) == 1
+        xs = ego.hop_tensors()
+        assert [x.shape for x in xs] == [(2, 2), (6, 3), (12, 3)] and xs[1][4].tolist() == [0, 0, 0]
+        v2 = g.run_async(q).result(timeout=10)           # the last id of the source
+        assert v2["seed"]["ids"].tolist() == [5] and not src.has_next()
+        with pytest.raises(C.UserException):
+            g.run(q)                                     # source exhausted
+        assert g.run(q, [3])["hop1"]["ids"].tolist() == [[13, 12, 11]]
+        back = g.get_query()
+        assert back.id == q.id and back.aliases() == q.aliases()
+        front.barriers.set("b", svc.ingested + 100)
+        assert g.check_barrier("b").code == C.Status.NOT_READY
+        front.barriers.set("b2", 0)
+        assert g.check_barrier("b2").ok()
+        assert g.stats()["served"] >= 4
+        bad = C.Query.from_json({"query_plan": {"plan_nodes": [{"id": 0, "kind": "SOURCE", "params": [{"key": "vtype", "value": 9}]}]}})
+        assert not g.install(bad).ok()
+        g.close()
+    finally:
+        front.stop()
 
 
 def test_partitioned_service_matches_single_store():
@@ -314,3 +380,60 @@ def test_record_batch_wire_format_roundtrip():
         assert False
     except ValueError:
         pass
+
+
+def test_service_process_entry_point(tmp_path):
+    """``python -m graphlearn_b200.dgs`` (what the Helm chart in deploy/dgs runs): starts from schema + install-query files,
+    serves, writes a final checkpoint on SIGTERM and restores it (query included) on the next start."""
+    import json
+    import os
+    import signal
+    import subprocess
+    import sys
+    import time
+    from graphlearn_b200.dgs import client as C
+    schema = {"attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}],
+              "vertex_defs": [{"vtype": 0, "name": "user", "attr_types": [0]}, {"vtype": 1, "name": "item", "attr_types": [0]}],
+              "edge_defs": [{"etype": 2, "name": "u2i", "attr_types": [0]}],
+              "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}]}
+    (tmp_path / "schema.json").write_text(json.dumps(schema))
+    install = {"query_id": 3, "query_plan": {"plan_nodes": [
+        {"id": 0, "kind": "SOURCE", "links": [{"node": 1}], "params": [{"key": "vtype", "value": 0}]},
+        {"id": 1, "kind": "EDGE_SAMPLER", "links": [], "params": [{"key": "vtype", "value": 0}, {"key": "etype", "value": 2},
+                                                                   {"key": "fanout", "value": 2}, {"key": "strategy", "value": 0}]}]}}
+    (tmp_path / "q.json").write_text(json.dumps(install))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+
+    def start(extra=()):
+        pf = tmp_path / "port"
+        if pf.exists():
+            pf.unlink()
+        p = subprocess.Popen([sys.executable, "-m", "graphlearn_b200.dgs", "--schema", str(tmp_path / "schema.json"), "--device", "cpu",
+                              "--host", "127.0.0.1", "--port", "0", "--capacity", "16", "--checkpoint-dir", str(tmp_path / "ck"),
+                              "--port-file", str(pf)] + list(extra), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        t0 = time.time()
+        while not pf.exists() and time.time() - t0 < 120 and p.poll() is None:
+            time.sleep(0.2)
+        assert pf.exists(), p.communicate(timeout=5)[0]
+        return p, int(pf.read_text())
+    p, port = start(["--install-query", str(tmp_path / "q.json")])
+    try:
+        g = C.Graph.connect("127.0.0.1:%d" % port)
+        g._http("POST", "/admin/ingest", {"edges": {"u2i": {"src": [1, 1, 1], "dst": [4, 5, 6], "ts": [10, 11, 12]}}})
+        q = g.get_query(3) if False else C.Query.from_json(install)
+        q.id = 3
+        assert g.run(q, [1]).node(1)["ids"].tolist() == [[6, 5]]
+    finally:
+        p.send_signal(signal.SIGTERM)
+        out = p.communicate(timeout=60)[0].decode()
+    assert "final checkpoint 1" in out, out
+    p, port = start()                                    # no --install-query: the checkpoint carries it
+    try:
+        g = C.Graph.connect("127.0.0.1:%d" % port)
+        assert g.run(q, [1]).node(1)["ids"].tolist() == [[6, 5]]
+        assert g.stats()["ingested"] == 3
+    finally:
+        p.send_signal(signal.SIGTERM)
+        out = p.communicate(timeout=60)[0].decode()
+    assert "restored checkpoint 1" in out, out

@@ -47,3 +47,45 @@ def test_knn_ivfpq_scan_kernel(metric, m, d):
     if metric == 0:
         assert (ids[:, 0] == torch.arange(B, device=rt.device)).all()
         assert torch.allclose(dist[:, 0], -ref_s[:, 0], atol=1e-2)
+
+
+@pytest.mark.parametrize("mode", ["none", "ts", "weight"])
+def test_csr_build_kernel_matches_stable_sorts(mode):
+    """csrc/csr_build.cu (count -> scan -> scatter -> per-row bitonic sort, warp rows and CTA hub rows) must produce
+    EXACTLY the permutation of the two stable global sorts of the portable build, ties included."""
+    import graphlearn_b200 as gl
+    from graphlearn_b200.parallel.runtime import init
+    from graphlearn_b200.store.shards import CsrShard
+    rt = init()
+    g = torch.Generator(device=rt.device).manual_seed(3)
+    n_rows, E = 5000, 400000
+    src = torch.randint(0, n_rows, (E,), device=rt.device, generator=g)
+    src[:3000] = 7                                  # a hub (CTA sort, not a power of two) ...
+    src[3000:3300] = 11                             # ... and a row just above the warp limit
+    src[src == 13] = 14                             # an empty row
+    dst = torch.randint(0, 1 << 20, (E,), device=rt.device, generator=g)
+    ts = torch.randint(-50, 50, (E,), device=rt.device, generator=g) if mode == "ts" else None          # many ties, negative values
+    w = None
+    if mode == "weight":
+        w = torch.randint(-3, 4, (E,), device=rt.device, generator=g).float() * 0.5
+        w[::7] = -0.0
+    shards = []
+    for native in (True, False):
+        gl.set_native_csr_build(native)
+        shards.append(CsrShard.from_coo(rt, "e", "a", "b", src, dst, n_rows, weights=w, ts=ts))
+    a, b = shards
+    assert torch.equal(a.indptr.local, b.indptr.local)
+    assert torch.equal(a._order, b._order)
+    assert torch.equal(a.indices.local, b.indices.local)
+    if ts is not None:
+        assert torch.equal(a.ts.local, b.ts.local)
+    if w is not None:
+        assert torch.equal(a.weights.local, b.weights.local) and torch.allclose(a.cumw.local, b.cumw.local)
+    # empty input and a single edge
+    z = torch.zeros(0, dtype=torch.int64, device=rt.device)
+    gl.set_native_csr_build(True)
+    e0 = CsrShard.from_coo(rt, "e", "a", "b", z, z, 4)
+    assert e0.indptr.local.tolist() == [0, 0, 0, 0, 0]
+    one = CsrShard.from_coo(rt, "e", "a", "b", torch.tensor([2], device=rt.device), torch.tensor([9], device=rt.device), 4,
+                            weights=torch.tensor([1.5], device=rt.device))
+    assert one.indptr.local.tolist() == [0, 0, 0, 1, 1] and one.indices.local.tolist() == [9]
