@@ -23,21 +23,19 @@ class MultivalSpec(object):
         self.delimiter = delimiter
 
 
-class DynamicSparseSpec(object):
-    """Embedding column without a fixed bucket count (PAI-TF dynamic embedding in the reference,
-    feature_spec.py); accepted for script parity, ``nn.FeatureEncoder`` needs a bucket size."""
+class DynamicSparseSpec(SparseSpec):
+    """Embedding column without a fixed bucket count (PAI-TF dynamic embedding variables in the reference,
+    feature_spec.py:28-31): every distinct key owns a row (``nn.DynamicEmbedding``)."""
 
     def __init__(self, dimension, need_hash=True):
-        self.bucket_size = None
-        self.dimension = dimension
-        self.need_hash = need_hash
+        super().__init__(None, dimension, need_hash)
 
 
-class DynamicMultivalSpec(object):
+class DynamicMultivalSpec(MultivalSpec):
+    """Multi-value string column over an unbounded vocabulary (feature_spec.py:43-46)."""
+
     def __init__(self, dimension, delimiter=","):
-        self.bucket_size = None
-        self.dimension = dimension
-        self.delimiter = delimiter
+        super().__init__(None, dimension, delimiter)
 
 
 class FeatureSpec(object):
@@ -52,16 +50,26 @@ class FeatureSpec(object):
         (self.float_specs if is_float else self.int_specs).append(s)
         self.specs.append(s)
 
-    def append_sparse(self, bucket_size, dimension, need_hash):
-        s = SparseSpec(bucket_size, dimension, need_hash)
-        # hashed strings are stored as int attributes by the loader
-        self.int_specs.append(s)
+    def append_sparse(self, bucket_size, dimension, need_hash=False):
+        """bucket_size None = dynamic vocabulary: hashed (int) keys stay int attributes, raw strings are string
+        attributes (feature_spec.py:96-107)."""
+        if bucket_size is not None:
+            s = SparseSpec(bucket_size, dimension, need_hash)
+            self.int_specs.append(s)                  # hashed strings are stored as int attributes by the loader
+        else:
+            s = DynamicSparseSpec(dimension, need_hash)
+            (self.int_specs if need_hash else self.string_specs).append(s)
         self.specs.append(s)
 
     def append_multival(self, bucket_size, dimension, delimiter=","):
-        s = MultivalSpec(bucket_size, dimension, delimiter)
+        s = MultivalSpec(bucket_size, dimension, delimiter) if bucket_size is not None else DynamicMultivalSpec(dimension, delimiter)
         self.string_specs.append(s)
         self.specs.append(s)
+
+    @property
+    def dimension(self):
+        """width of the encoded feature vector (feature_spec.py:93-94)"""
+        return sum(int(s.dimension) for s in self.specs)
 
     @property
     def num_int(self):

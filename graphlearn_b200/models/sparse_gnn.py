@@ -52,3 +52,50 @@ class SEAL(nn.Module):
         h = torch.cat([x.float(), self.label_emb(z)], 1) if x is not None and x.numel() else self.label_emb(z)
         h = self.gnn(h, edge_index)
         return self.mlp(torch.cat([h[0], h[1]], -1)).squeeze(-1)     # src is node 0, dst is node 1
+
+
+class _BatchGraphModel(nn.Module):
+    """SubGraph-based link model of the reference (nn/tf/model/{gcn,sage,gat}.py): stacks sparse convs over a ``BatchGraph`` and
+    returns the embeddings of the first two nodes of every subgraph (the (src, dst) pair the sub-graph was induced around)."""
+
+    kind = "gcn"
+
+    def __init__(self, batch_size, input_dim, hidden_dim, output_dim, depth=2, drop_rate=0.0, encoder=None, **kw):
+        super().__init__()
+        self.batch_size, self.depth, self.encoder = batch_size, depth, encoder
+        self.gnn = SparseGNN(self.kind, input_dim, hidden_dim, output_dim, num_layers=depth, dropout=drop_rate, **kw)
+
+    def forward(self, batchgraph):
+        bg = batchgraph.transform(self.encoder)
+        h = self.gnn(bg.nodes, bg.edge_index)
+        off = bg.graph_node_offsets[:-1] if bg.graph_node_offsets.numel() > bg.num_graphs else bg.graph_node_offsets
+        return h[off], h[off + 1]
+
+
+class GCN(_BatchGraphModel):
+    kind = "gcn"
+
+
+class GraphSAGE(_BatchGraphModel):
+    """``agg_type`` in mean | sum (sage.py:29-60)"""
+    kind = "sage"
+
+    def __init__(self, batch_size, input_dim, hidden_dim, output_dim, depth=2, drop_rate=0.0, agg_type="mean", **kw):
+        super().__init__(batch_size, input_dim, hidden_dim, output_dim, depth, drop_rate, agg_type=agg_type, **kw)
+
+
+class GAT(_BatchGraphModel):
+    """``attn_heads`` on the hidden layers, one head on the output layer (gat.py:29-66)."""
+    kind = "gat"
+
+    def __init__(self, batch_size, input_dim, hidden_dim, output_dim, depth=2, drop_rate=0.0, attn_heads=1, attn_drop=0.0, **kw):
+        nn.Module.__init__(self)
+        self.batch_size, self.depth, self.encoder = batch_size, depth, kw.pop("encoder", None)
+        dims = [input_dim] + [hidden_dim] * (depth - 1) + [output_dim]
+        convs = []
+        for i in range(depth):
+            last = i == depth - 1 and depth != 1
+            convs.append(GATConv(dims[i], dims[i + 1], num_heads=1 if last else attn_heads, concat=False, attn_drop=attn_drop))
+        self.gnn = SparseGNN.__new__(SparseGNN)
+        nn.Module.__init__(self.gnn)
+        self.gnn.convs, self.gnn.dropout = nn.ModuleList(convs), drop_rate

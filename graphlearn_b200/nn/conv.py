@@ -256,3 +256,35 @@ class EgoTGATConv(nn.Module):
         xs = torch.cat([x.float(), self.time(torch.zeros_like(t_self))], 1)
         xn = torch.cat([neighbor.float(), self.time(dt)], 1)
         return self.att(xs, xn, expand)
+
+
+class EgoConv(nn.Module):
+    """Abstract EgoGraph convolution (ego_layer.py:25-39): ``forward(x [n, d_x], neighbor [n * expand, d_n], expand)`` ->
+    [n, out].  ``EgoSAGEConv / EgoGATConv / EgoGINConv / EgoRGCNConv`` follow this contract; subclass it for custom layers
+    that ``EgoLayer`` can stack."""
+
+    def forward(self, x, neighbor, expand):
+        raise NotImplementedError
+
+
+class SubConv(nn.Module):
+    """Abstract SubGraph convolution (sub_conv.py:25-37): ``forward(edge_index [2, m], node_vec [n, d])`` -> [n, out]
+    (``GCNConv / SAGEConv / GATConv`` in ``nn.sparse_conv`` take ``(x, edge_index)``; ``HeteroConv`` accepts both orders)."""
+
+    def forward(self, edge_index, node_vec, **kwargs):
+        raise NotImplementedError
+
+
+class LinearLayer(nn.Module):
+    """``y = act(x W + b)`` with lazily inferred input width (linear_layer.py:29-75: ``LinearLayer(name, input_dim,
+    output_dim, use_bias)``)."""
+
+    def __init__(self, name="linear", input_dim=None, output_dim=1, use_bias=True, activation=None):
+        super().__init__()
+        self.name = name
+        self.lin = nn.Linear(int(input_dim), int(output_dim), bias=use_bias) if input_dim else nn.LazyLinear(int(output_dim), bias=use_bias)
+        self.activation = activation
+
+    def forward(self, x):
+        y = self.lin(x)
+        return self.activation(y) if self.activation is not None else y

@@ -30,6 +30,11 @@ class Data(object):
         return Data(ids.reshape(-1) if flatten else ids, t("int_attrs"), t("float_attrs"), v._t.get("string_attrs"),
                     t("labels"), t("weights"))
 
+    # the reference's attribute names (nn/data.py Data: int_attrs / float_attrs / string_attrs)
+    int_attrs = property(lambda self: self.ints)
+    float_attrs = property(lambda self: self.floats)
+    string_attrs = property(lambda self: self.strings)
+
     def to(self, device):
         for k, v in list(self.__dict__.items()):
             if isinstance(v, torch.Tensor):
@@ -117,7 +122,7 @@ class BatchGraph(object):
 
     @property
     def num_nodes(self):
-        return int(self.nodes.ids.numel())
+        return int(self.nodes.size(0)) if isinstance(self.nodes, torch.Tensor) else int(self.nodes.ids.numel())
 
     @property
     def num_edges(self):
@@ -131,6 +136,26 @@ class BatchGraph(object):
     def graph_assign(self):
         n = self.graph_node_offsets[1:] - self.graph_node_offsets[:-1]
         return torch.repeat_interleave(torch.arange(n.numel(), device=n.device), n)
+
+    def transform(self, encoder=None) -> "BatchGraph":
+        """BatchGraph whose ``nodes`` is the dense feature matrix the sparse convs consume (batchgraph.py ``transform``):
+        ``encoder`` is a ``FeatureHandler`` / ``FeatureEncoder`` (or any callable on ``Data``); None = the float attributes."""
+        if isinstance(self.nodes, torch.Tensor):
+            return self
+        if encoder is None:
+            x = self.nodes.floats.float()
+        elif hasattr(encoder, "_fspec"):                                   # FeatureHandler: takes the Data object
+            x = encoder(self.nodes)
+        else:
+            try:
+                x = encoder(self.nodes.floats, self.nodes.ints, self.nodes.strings)
+            except TypeError:
+                x = encoder(self.nodes)
+        extra = {k: getattr(self, k) for k in self.additional_keys if hasattr(self, k)}
+        out = BatchGraph(self.edge_index, x, self.node_schema, self.graph_node_offsets, self.edges, self.graph_edge_offsets,
+                         self.additional_keys, **extra)
+        out.raw_nodes = self.nodes
+        return out
 
     @staticmethod
     def from_graphs(graphs, additional_keys=()) -> "BatchGraph":

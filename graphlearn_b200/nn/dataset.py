@@ -147,3 +147,90 @@ class PyGDataLoader(object):
 
     def __len__(self):
         return self.length if self.length is not None else 0
+
+
+class Collater(object):
+    """Collate the item list of one GSL batch (pyg_dataloader.py:47-68): sub-graph items become one ``Batch``, tensors are
+    stacked."""
+
+    def collate(self, batch):
+        if isinstance(batch, (list, tuple)) and len(batch) == 1 and isinstance(batch[0], (list, tuple)):
+            batch = batch[0]                                      # DataLoader(batch_size=1) wraps the GSL batch once more
+        elem = batch[0]
+        if isinstance(elem, SubGraphData):
+            return Batch.from_data_list(batch)
+        if isinstance(elem, torch.Tensor):
+            return torch.stack(list(batch))
+        raise TypeError("PyGDataLoader found invalid type: {}".format(type(elem)))
+
+    def __call__(self, batch):
+        return self.collate(batch)
+
+
+def worker_init_fn(worker_id):
+    """DataLoader worker hook of the reference (pyg_dataloader.py:42-45: each worker becomes GL client
+    ``worker_id + rank * num_client``).  Batches are sampled on the GPU of the owning process here, so worker processes are
+    not used; the hook only records the id for scripts that read it."""
+    from .utils import get_num_client, get_rank
+    info = torch.utils.data.get_worker_info()
+    if info is not None:
+        info.dataset.client_id = worker_id + get_rank() * get_num_client()
+
+
+class TemporalData(object):
+    """A batch of timestamped events: ``src, dst, t, msg`` (the PyG ``TemporalData`` the reference's TGN example consumes)."""
+
+    def __init__(self, src, dst, t, msg=None, **kw):
+        self.src, self.dst, self.t, self.msg = src, dst, t, msg
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def num_events(self):
+        return int(self.src.numel())
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, v.to(device))
+        return self
+
+
+class TemporalDataset(TorchDataset):
+    """Edge-rooted query -> stream of ``TemporalData`` (temporal_dataset.py:31-47): the alias ``event_name`` must name a
+    timestamped ``E(...)`` traversal; ``msg`` carries the edge weights (or float attributes when the edges have them)."""
+
+    def __init__(self, query, window=10, event_name="event", length: Optional[int] = None):
+        def induce(data_dict_raw):
+            if event_name not in data_dict_raw:
+                raise ValueError("Event name {} not exist.".format(event_name))
+            ev = data_dict_raw[event_name]
+            msg = ev.tensor("float_attrs")
+            if not isinstance(msg, torch.Tensor):
+                msg = ev.tensor("weights")
+            return TemporalData(ev.tensor("src_ids").reshape(-1), ev.tensor("dst_ids").reshape(-1),
+                                ev.tensor("timestamps").reshape(-1), msg if isinstance(msg, torch.Tensor) else None)
+        super().__init__(query, window=window, length=length)
+        self._induce = induce
+
+    def __iter__(self):
+        n = 0
+        while self._length is None or n < self._length:
+            try:
+                res = self._nn.next()
+            except errors.OutOfRangeError:
+                return
+            n += 1
+            yield self._induce(res)
+
+
+class TemporalDataLoader(object):
+    """Iterates a ``TemporalDataset`` as is (temporal_dataloader.py:31-45: batch size, shuffling and collation are fixed by
+    the GSL query, the loader only forwards)."""
+
+    def __init__(self, dataset: TemporalDataset, **_ignored):
+        assert isinstance(dataset, TemporalDataset), "TemporalDataLoader only accepts GraphLearn TemporalDataset"
+        self.dataset = dataset
+
+    def __iter__(self):
+        return iter(self.dataset)

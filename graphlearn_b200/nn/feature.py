@@ -68,7 +68,7 @@ class DynamicEmbedding(nn.Module):
         self.keys, self.rows = keys[order], rows[order]
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
-        flat = ids.reshape(-1).to(torch.int64).to(self.weight.device)
+        flat = ids.reshape(-1).to(torch.int64).to(self.weight.device).contiguous()
         if self.keys.device != flat.device:
             self.keys, self.rows = self.keys.to(flat.device), self.rows.to(flat.device)
         if self.training:

@@ -380,3 +380,136 @@ def test_stall_detector_fires_once_and_rearms():
     sd.tick(); time.sleep(1.5)               # re-armed by the next step
     assert len(hits) == 2
     sd.stop()
+
+
+def test_feature_columns_groups_and_handler():
+    """nn/feature_column.py (feature_column.py / feature_handler.py of the reference): every column kind, the spec-driven
+    grouping (per-feature, fused by width, dynamic, multi-value strings) and the concatenation order."""
+    torch.manual_seed(0)
+    num = glnn.NumericColumn("x", normalizer_func=lambda v: v / 10)
+    assert num(torch.tensor([10, 20])).tolist() == [1.0, 2.0]
+    emb = glnn.EmbeddingColumn("e", 7, 3)
+    assert torch.equal(emb(torch.tensor([2, 99])), emb.table.weight[[2, 6]])              # out-of-range ids clamp
+    hashed = glnn.EmbeddingColumn("h", 7, 3, need_hash=True)
+    assert hashed(torch.tensor([123456789, 5])).shape == (2, 3)
+    fused = glnn.FusedEmbeddingColumn("f", [4, 6], 2)
+    out = fused([torch.tensor([1, 3]), torch.tensor([0, 5])])
+    assert out.shape == (2, 4) and torch.equal(out[1], torch.cat([fused.table.weight[3], fused.table.weight[4 + 5]]))
+    sp = glnn.SparseEmbeddingColumn("s", 50, 4, delimiter=",")
+    o = sp(np.array(["a,b", "", "b"], dtype=object))
+    assert torch.allclose(o[1], torch.zeros(4)) and not torch.allclose(o[2], torch.zeros(4))
+    assert torch.allclose(o[0] - o[2], sp(np.array(["a"], dtype=object))[0], atol=1e-6)
+    dyn = glnn.DynamicEmbeddingColumn("d", 3, is_string=True)
+    a = dyn(["tok1", "tok2", "tok1"])
+    assert torch.equal(a[0], a[2]) and dyn.table.num_keys == 2
+    dyn.eval()
+    assert torch.allclose(dyn(["never seen"]), torch.zeros(1, 3)) and dyn.table.num_keys == 2
+    dsp = glnn.DynamicSparseEmbeddingColumn("ds", 2, delimiter="|")
+    assert dsp(["x|y", "y"]).shape == (2, 2) and dsp.table.num_keys == 2
+    grp = glnn.FeatureGroup([glnn.NumericColumn("a"), glnn.EmbeddingColumn("b", 5, 2)])
+    assert grp([torch.tensor([1.0, 2.0]), torch.tensor([0, 4])]).shape == (2, 3) and len(grp) == 2
+    with pytest.raises(ValueError):
+        grp([torch.tensor([1.0])])
+
+    spec = gl.FeatureSpec(8)
+    spec.append_dense()                       # float 0
+    spec.append_dense()                       # float 1
+    spec.append_dense(is_float=False)         # int 0: integer treated like a float
+    spec.append_sparse(10, 4, False)          # int 1: fused (width 4)
+    spec.append_sparse(20, 4, False)          # int 2: fused (width 4)
+    spec.append_sparse(30, 3, True)           # int 3: hashed, own table
+    spec.append_sparse(None, 5, True)         # int 4: dynamic vocabulary of hashed keys
+    spec.append_multival(40, 2, ":")          # string 0
+    spec.append_multival(None, 6, ":")        # string 1: dynamic multi-value
+    assert spec.dimension == 1 + 1 + 1 + 4 + 4 + 3 + 5 + 2 + 6
+    assert isinstance(spec.int_specs[4], gl.DynamicSparseSpec) and isinstance(spec.string_specs[1], gl.DynamicMultivalSpec)
+    fh = glnn.FeatureHandler("item", spec)
+    assert fh.output_dim == spec.dimension
+    n = 6
+    data = glnn.Data(ids=torch.arange(n), floats=torch.rand(n, 2),
+                     ints=torch.stack([torch.arange(n), torch.arange(n) % 10, torch.arange(n) % 20, torch.arange(n) * 7919,
+                                       torch.arange(n) * 104729], 1),
+                     strings=np.array([["a:b", "p:q:r"]] * n, dtype=object))
+    y = fh(data)
+    assert y.shape == (n, spec.dimension)
+    assert torch.allclose(y[:, :2], data.floats) and torch.allclose(y[:, 2], torch.arange(n).float())     # floats, then dense int
+    # order after the per-feature int columns [dense(1) | hashed(3) | dynamic(5)]: the fused group, then the strings
+    fcol = fh._fused_int_fg[0]
+    want = torch.cat([fcol.table.weight[data.ints[:, 1]], fcol.table.weight[10 + data.ints[:, 2]]], 1)
+    assert torch.allclose(y[:, 2 + 1 + 3 + 5:2 + 1 + 3 + 5 + 8], want)
+    y.sum().backward()
+    assert fcol.table.weight.grad is not None and fh._string_fg[1].table.weight.grad is not None
+    # without fusing every sparse column owns its table
+    assert len(glnn.FeatureHandler("x", spec, fuse_embedding=False)._fused_int_fg) == 0
+
+
+def test_reference_named_models_base_classes_and_torch_utils(tmp_path):
+    """Names a reference user expects: nn.Module / EgoConv / SubConv / LinearLayer, models.GCN / GraphSAGE / GAT over a
+    BatchGraph, unsorted_segment_softmax, the nn.pytorch data utils and the end-of-training barrier hook."""
+    from graphlearn_b200.nn import utils as U
+    assert issubclass(glnn.EgoSAGEConv, glnn.Module) and glnn.unsorted_segment_softmax is glnn.segment_softmax
+
+    class MyConv(glnn.EgoConv):
+        def forward(self, x, neighbor, expand):
+            return x + neighbor.reshape(x.size(0), expand, -1).mean(1)
+    layer = glnn.EgoLayer([MyConv()])
+    out = layer([torch.ones(2, 3), torch.ones(8, 3)], [4])
+    assert torch.allclose(out[0], torch.full((2, 3), 2.0))
+    with pytest.raises(NotImplementedError):
+        glnn.SubConv()(None, None)
+    lin = glnn.LinearLayer("l", 3, 5, activation=torch.relu)
+    assert lin(torch.randn(4, 3)).shape == (4, 5) and glnn.LinearLayer("lazy", None, 2)(torch.randn(4, 7)).shape == (4, 2)
+    # a BatchGraph of 3 path graphs with 4 nodes each
+    ei = torch.cat([torch.tensor([[0, 1, 2], [1, 2, 3]]) + 4 * i for i in range(3)], 1)
+    bg = glnn.BatchGraph(ei, glnn.Data(ids=torch.arange(12), floats=torch.randn(12, 6)), graph_node_offsets=torch.tensor([0, 4, 8, 12]))
+    for cls, kw in ((models.GCN, {}), (models.GraphSAGE, {"agg_type": "sum"}), (models.GAT, {"attn_heads": 2})):
+        m = cls(3, 6, 8, 5, depth=2, drop_rate=0.1, **kw)
+        src, dst = m(bg)
+        assert src.shape == (3, 5) and dst.shape == (3, 5)
+        (src * dst).sum().backward()
+    assert bg.transform().nodes.shape == (12, 6) and bg.transform().num_nodes == 12
+    # process-level helpers
+    U._reset_for_tests()
+    assert U.get_world_size() == 1 and U.get_rank() == 0 and U.get_num_client() == 1
+    U._reset_for_tests()
+    U.set_client_num(3)
+    assert U.get_num_client() == 3
+    spec = U.get_cluster_spec()
+    host, port = spec["server"].split(":")
+    assert int(port) > 0 and spec["client_count"] == 3 and not U.is_server_launched()
+    hook = glnn.SyncBarrierHook()
+    with hook:
+        pass                                            # no process group: returns at once
+    hook.end()
+    U._reset_for_tests()
+    # Collater / worker_init_fn
+    items = [glnn.SubGraphData(torch.ones(2, 3), torch.tensor([[0], [1]])), glnn.SubGraphData(torch.ones(3, 3), torch.tensor([[0, 1], [1, 2]]))]
+    b = glnn.Collater()([items])
+    assert b.num_graphs == 2 and b.x.shape == (5, 3) and b.edge_index.tolist() == [[0, 2, 3], [1, 3, 4]]
+    assert glnn.Collater()([torch.ones(2), torch.zeros(2)]).shape == (2, 2)
+    glnn.worker_init_fn(0)                              # outside a worker: no-op
+
+
+def test_temporal_dataset_and_loader(tmp_path):
+    """nn.TemporalDataset / TemporalDataLoader (nn/pytorch/data/temporal_dataset.py): an edge-rooted query streams
+    TemporalData(src, dst, t, msg) batches for one epoch."""
+    d = str(tmp_path)
+    with open(d + "/n.tsv", "w") as f:
+        f.write("id:int64\tfeature:string\n" + "".join("%d\t%d\n" % (i, i) for i in range(10)))
+    with open(d + "/e.tsv", "w") as f:
+        f.write("src_id:int64\tdst_id:int64\tweight:float\ttimestamp:int64\n")
+        for i in range(23):
+            f.write("%d\t%d\t%.1f\t%d\n" % (i % 10, (i * 3) % 10, 0.5 * i, 1000 + i))
+    g = gl.Graph().node(d + "/n.tsv", "n", decoder=gl.Decoder(attr_types=["float"])) \
+        .edge(d + "/e.tsv", ("n", "n", "e"), decoder=gl.Decoder(weighted=True, timestamped=True)).init(device="cpu")
+    q = g.E("e").batch(8).alias("event").values()
+    loader = glnn.TemporalDataLoader(glnn.TemporalDataset(q, event_name="event"), batch_size=99, shuffle=True)
+    batches = list(loader)
+    assert [b.num_events for b in batches] == [8, 8, 7]
+    t = torch.cat([b.t for b in batches])
+    assert sorted(t.tolist()) == list(range(1000, 1023))
+    b0 = batches[0]
+    assert torch.equal(b0.dst, (3 * (b0.t - 1000)) % 10) and torch.allclose(b0.msg.reshape(-1), 0.5 * (b0.t - 1000).float())
+    with pytest.raises(ValueError):
+        next(iter(glnn.TemporalDataset(g.E("e").batch(4).alias("x").values(), event_name="event")))
+    g.close()
