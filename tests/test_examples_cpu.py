@@ -91,3 +91,27 @@ def test_export_serving_model_and_online_inference(tmp_path):
 def test_subgraph_sage_edge_inducer():
     first, last = _run("train_subgraph_sage", ["--device", "cpu", "--epochs", "2", "--nodes", "500"])
     assert last < first
+
+
+def test_basic_queries_tour(tmp_path):
+    """examples/basic_queries.py (the reference's examples/basic): traversal epochs, edge iteration, multi-hop shapes, every
+    sampling strategy, negatives, look-ups, sub-graphs, walks and KNN on the generated toy graph."""
+    import numpy as np
+    out = _run("basic_queries", ["--device", "cpu", "--data", str(tmp_path)])
+    for epoch in out["node_epochs"]:
+        assert epoch.tolist() == list(range(100))                     # every user exactly once per epoch
+    assert out["edges"] == 1000
+    assert out["multi_hop"] == {"src": (8,), "h1": (8, 3), "h2": (24, 2), "h1_float": (8, 3, 4)}
+    st = out["strategies"]
+    assert (st["topk"] == np.array([[109, 108, 107, 106]] * 5)).all()              # heaviest edges first
+    assert all(len(set(r)) == 4 for r in st["random_without_replacement"].tolist())
+    assert st["full_offsets"].tolist() == [3] * 5
+    neg, cond = out["negatives"]
+    assert neg.shape == (6, 4) and cond.shape == (6, 2) and ((cond >= 100) & (cond < 110)).all()
+    assert out["lookups"]["int"] == [100, 105] and out["lookups"]["string"] == ["100s", "105s"] and out["lookups"]["deg"] == [10, 10, 10]
+    assert out["lookups"]["stats"]["relation"] == [720]                # undirected: both directions stored
+    ei_shape, walks = out["subgraph_walks"]
+    assert ei_shape[0] == 2 and walks.shape == (4, 5)
+    step = np.abs(np.diff(np.concatenate([walks[:, :1], walks], 1)[:, 1:], axis=1)) % 120
+    assert np.isin(np.minimum(step, 120 - step), [1, 2, 3]).all()      # every hop follows a ring edge
+    assert out["knn"][0][0] == 5 and abs(out["knn"][1][0]) < 1e-5

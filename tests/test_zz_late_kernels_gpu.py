@@ -32,9 +32,16 @@ def test_knn_ivfpq_scan_kernel(metric, m, d):
     s_k, r_k = idx.search(q, k, True)
     s_o, r_o = idx.search(q, k, False)
     assert torch.allclose(s_k, s_o, rtol=1e-4, atol=1e-3)
-    # ids may differ only where scores tie (identical codes): compare as sets wherever the k-th score is separated
-    same = (torch.sort(r_k, 1).values == torch.sort(r_o, 1).values).all(1)
-    assert same.float().mean() > 0.9
+    # rows with identical codes tie, so the two top-k id sets may differ at the boundary: every id the kernel returns must
+    # appear in the oracle's (4x deeper) list with the score the kernel reported
+    s_d, r_d = idx.search(q, 4 * k, False)
+    match = r_k[:, :, None] == r_d[:, None, :]
+    found = match.any(2) | (r_k < 0)
+    assert found.float().mean() > 0.99, float(found.float().mean())
+    s_at = torch.gather(s_d, 1, match.float().argmax(2))
+    ok = found & (r_k >= 0) & match.any(2)
+    assert torch.allclose(s_at[ok], s_k[ok], rtol=1e-4, atol=1e-3)
+    assert (torch.sort(r_k, 1).values == torch.sort(r_o, 1).values).all(1).float().mean() > 0.5
     # through the public search with the exact re-rank
     opt = gl.IndexOption(); opt.index_type = "gpu_ivfpq"; opt.nlist = 32; opt.nprobe = 16; opt.m = m
     knn.build_index(t, opt)
