@@ -132,11 +132,15 @@ class SyncBarrierHook(object):
     queue is a ``torch.distributed`` store counter; without a process group the hook is a no-op.  Use ``hook.end()`` after the
     training loop, or as a context manager around it."""
 
+    _instances = 0          # hooks are created in the same order on every rank: the sequence number keys the store counter
+
     def __init__(self, num_worker: Optional[int] = None, is_chief: Optional[bool] = None, timeout_s: float = 3600.0,
-                 key: str = "glb_sync_barrier"):
+                 key: Optional[str] = None):
         self._n = num_worker if num_worker is not None else get_world_size()
         self._chief = is_chief if is_chief is not None else get_rank() == 0
-        self._timeout, self._key, self._done = timeout_s, key, False
+        SyncBarrierHook._instances += 1
+        self._timeout, self._done = timeout_s, False
+        self._key = key or "glb_sync_barrier_%d" % SyncBarrierHook._instances
 
     def begin(self):
         return self

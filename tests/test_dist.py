@@ -39,6 +39,10 @@ def test_sharded_embedding_two_ranks_cpu_gloo():
     _run(2, 29650, {"CUDA_VISIBLE_DEVICES": ""}, "dist_embedding_worker.py", [], "EMB_ALL_OK")
 
 
+def test_nn_utils_two_ranks_cpu_gloo():
+    _run(2, 29653, {"CUDA_VISIBLE_DEVICES": ""}, "dist_nn_utils_worker.py", [], "NN_UTILS_OK")
+
+
 def test_data_parallel_example_two_ranks_cpu_gloo():
     """examples/train_gcn_sparse.py under torchrun: masks + full neighbourhoods + generic Trainer (flat gradients,
     all-reduce, lock-step epochs) - replicas must end with identical parameters."""
