@@ -27,8 +27,8 @@ from .sampler.negative_sampler import (ConditionalNegativeSampler, InDegreeNegat
 from .sampler.neighbor_sampler import (EdgeWeightNeighborSampler, FullNeighborSampler,  # noqa: F401
                                        InDegreeNeighborSampler, NeighborSampler, RandomNeighborSampler,
                                        RandomWithoutReplacementNeighborSampler, TopkNeighborSampler)
-from .sampler.node_sampler import (ByOrderEdgeSampler, ByOrderNodeSampler, EdgeSampler, NodeSampler,  # noqa: F401
-                                   RandomEdgeSampler, RandomNodeSampler, ShuffleEdgeSampler, ShuffleNodeSampler)
+from .sampler.edge_sampler import ByOrderEdgeSampler, EdgeSampler, RandomEdgeSampler, ShuffleEdgeSampler  # noqa: F401
+from .sampler.node_sampler import ByOrderNodeSampler, NodeSampler, RandomNodeSampler, ShuffleNodeSampler  # noqa: F401
 from .sampler.subgraph_sampler import SubGraphSampler  # noqa: F401
 from .utils import deprecated  # noqa: F401
 from .store.graph_store import Topology  # noqa: F401

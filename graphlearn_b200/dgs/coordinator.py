@@ -38,11 +38,36 @@ class CheckpointManager(object):
                 json.dump({"id": cid, "ingested": self.service.ingested}, f)
             return cid
 
+    # ---- backup-engine surface (the reference keeps RocksDB BackupEngine backups per store partition and restores a chosen
+    # backup id: sample_store.h StorePartitionBackupInfo / Backup() / PartitionedDB::Restore)
+    def list_backups(self):
+        """[{"id", "time", "bytes"}] of the retained checkpoints, oldest first"""
+        out = []
+        for cid in self._list():
+            f = os.path.join(self.path, "ckpt.%d.pt" % cid)
+            out.append({"id": cid, "time": os.path.getmtime(f), "bytes": os.path.getsize(f)})
+        return out
+
+    def purge(self, keep: Optional[int] = None) -> int:
+        """delete all but the newest ``keep`` checkpoints; returns how many were removed"""
+        keep = self.keep if keep is None else int(keep)
+        with self._lock:
+            old = self._list()[:-keep] if keep > 0 else self._list()
+            for cid in old:
+                os.remove(os.path.join(self.path, "ckpt.%d.pt" % cid))
+            return len(old)
+
     def restore_latest(self) -> Optional[int]:
         ids = self._list()
-        if not ids:
-            return None
-        ck = torch.load(os.path.join(self.path, "ckpt.%d.pt" % ids[-1]), weights_only=True)
+        return self.restore(ids[-1]) if ids else None
+
+    def restore(self, cid: int) -> int:
+        """restore the service (stores + installed queries) from checkpoint ``cid``"""
+        f = os.path.join(self.path, "ckpt.%d.pt" % int(cid))
+        if not os.path.exists(f):
+            raise FileNotFoundError("no checkpoint %d under %s (have %s)" % (cid, self.path, self._list()))
+        ids = [int(cid)]
+        ck = torch.load(f, weights_only=True)
         from .plan import PlanNode, QueryPlan
         for q, d in ck["queries"].items():
             plan = QueryPlan(d["source"])

@@ -126,12 +126,49 @@ class SampleStore(object):
         order = order[:, :k]
         return (torch.gather(self.nbr[vids], 1, order), t[:, :k], torch.gather(self.w[vids], 1, order))
 
+    # ---- key-level access (the reference's KV surface: sample_store.h GetEdgesByPrefix / GetVertex / Delete*ByPrefix)
+    def get(self, vid: int):
+        """kept samples of ONE vertex, most recent first: (nbr [c], ts [c], w [c]) with c = number of kept samples."""
+        if not 0 <= int(vid) < self.n:
+            e = torch.zeros(0, dtype=torch.int64, device=self.device)
+            return e, e.clone(), torch.zeros(0, device=self.device)
+        ok = self.nbr[vid] >= 0
+        t, order = torch.sort(self.ts[vid][ok], descending=True)
+        return self.nbr[vid][ok][order], t, self.w[vid][ok][order]
+
+    def get_vertex(self, vid: int):
+        """(feature row, its timestamp) of one vertex, or None when nothing was stored for it."""
+        if self.feat is None or not 0 <= int(vid) < self.n or int(self.feat_ts[vid]) == -(2 ** 62):
+            return None
+        return self.feat[vid].clone(), int(self.feat_ts[vid])
+
+    def delete(self, vids: torch.Tensor) -> int:
+        """drop every kept sample (and the stored feature version) of the given vertices; returns the number of samples
+        dropped (DeleteEdgesByPrefix / DeleteVerticesByPrefix: a vertex left the subscribed set or was deleted upstream)."""
+        vids = torch.as_tensor(vids, dtype=torch.int64).to(self.device).reshape(-1)
+        vids = torch.unique(vids[(vids >= 0) & (vids < self.n)])
+        if vids.numel() == 0:
+            return 0
+        dropped = int((self.nbr[vids] >= 0).sum().item())
+        self.nbr[vids] = -1
+        self.ts[vids] = -(2 ** 62)
+        self.w[vids] = 0
+        self.count[vids] = 0
+        if self.feat is not None:
+            self.feat[vids] = 0
+            self.feat_ts[vids] = -(2 ** 62)
+        return dropped
+
     def state_dict(self):
         return {k: getattr(self, k).clone() for k in ("nbr", "ts", "w", "count") } | \
                ({"feat": self.feat.clone(), "feat_ts": self.feat_ts.clone()} if self.feat is not None else {})
 
     def load_state_dict(self, sd):
         self.ensure(int(sd["nbr"].size(0)))
+        # rows the tables grew by since the snapshot must not survive a restore
+        self.nbr.fill_(-1); self.ts.fill_(-(2 ** 62)); self.w.zero_(); self.count.zero_()
+        if self.feat is not None:
+            self.feat.zero_(); self.feat_ts.fill_(-(2 ** 62))
         for k, v in sd.items():
             getattr(self, k)[:v.size(0)].copy_(v)
 
@@ -259,6 +296,18 @@ class DynamicGraphService(object):
     def expire(self, before_ts: int) -> int:
         """apply the sample TTL to every edge store (timestamps are whatever unit the records use)"""
         return sum(st.expire(before_ts) for st in self.stores.values())
+
+    def delete_vertices(self, vtype: str, ids) -> int:
+        """a vertex was deleted upstream: drop its feature version and the samples of every edge type that starts at it"""
+        n = self.vstores[vtype].delete(ids) if vtype in self.vstores else 0
+        for et, info in self.schema["edges"].items():
+            if info["src"] == vtype and et in self.stores:
+                n += self.stores[et].delete(ids)
+        return n
+
+    def delete_edges(self, etype: str, src_ids) -> int:
+        """drop the kept samples of ``etype`` of the given source vertices"""
+        return self.stores[etype].delete(src_ids) if etype in self.stores else 0
 
     def stats(self) -> dict:
         return {"ingested": self.ingested, "served": self.served, "queries": sorted(self.queries),

@@ -1,6 +1,6 @@
-"""Imperative seed samplers (graphlearn/python/sampler/node_sampler.py:85-117,
-edge_sampler.py): ``get()`` returns the next batch of Nodes / Edges of the LOCAL
-shard and raises ``OutOfRangeError`` at the end of an epoch."""
+"""Imperative node traversal (graphlearn/python/sampler/node_sampler.py:85-117): ``get()`` returns the next batch of Nodes of
+the LOCAL shard - node tables, or the source / destination ends of an edge table - and raises ``OutOfRangeError`` at the end
+of an epoch."""
 from __future__ import annotations
 
 import torch
@@ -55,35 +55,15 @@ class NodeSampler(object):
         self._it.load_state_dict(sd)
 
 
-class EdgeSampler(object):
-    def __init__(self, graph, edge_type, batch_size, strategy="by_order"):
-        assert strategy in ("by_order", "random", "shuffle")
-        self._g, self._type = graph, edge_type
-        self._csr = graph.store.edges[edge_type]
-        self._rt = graph.runtime
-        self._it = SeedIterator(self._csr.n_edges, batch_size, strategy, self._rt.device,
-                                seed=_config.get().seed + 37 * self._rt.rank)
-
-    def get(self):
-        csr = self._csr
-        idx = csr.insertion_pos()[self._it.next_index()]     # insertion (edge id) order, like the reference
-        W, r = self._rt.world, self._rt.rank
-        src_v = csr._row_of_edge[idx] * W + r
-        dst_v = csr.indices.local[idx]
-        src = self._g.to_ids(csr.src_type, src_v)
-        dst = self._g.to_ids(csr.dst_type, dst_v)
-        return V_.Edges(src, csr.src_type, dst, csr.dst_type, self._type, idx, graph=self._g, src_vids=src_v)
-
-    @property
-    def epoch(self):
-        return self._it.epoch
-
-
 from .neighbor_sampler import _fixed_strategy  # noqa: E402
 
 RandomNodeSampler = _fixed_strategy(NodeSampler, "random", "RandomNodeSampler")
 ByOrderNodeSampler = _fixed_strategy(NodeSampler, "by_order", "ByOrderNodeSampler")
 ShuffleNodeSampler = _fixed_strategy(NodeSampler, "shuffle", "ShuffleNodeSampler")
-RandomEdgeSampler = _fixed_strategy(EdgeSampler, "random", "RandomEdgeSampler")
-ByOrderEdgeSampler = _fixed_strategy(EdgeSampler, "by_order", "ByOrderEdgeSampler")
-ShuffleEdgeSampler = _fixed_strategy(EdgeSampler, "shuffle", "ShuffleEdgeSampler")
+
+
+def __getattr__(name):          # the edge samplers lived here once; keep the old import path working
+    if name in ("EdgeSampler", "RandomEdgeSampler", "ByOrderEdgeSampler", "ShuffleEdgeSampler"):
+        from . import edge_sampler
+        return getattr(edge_sampler, name)
+    raise AttributeError(name)

@@ -437,3 +437,36 @@ def test_service_process_entry_point(tmp_path):
         p.send_signal(signal.SIGTERM)
         out = p.communicate(timeout=60)[0].decode()
     assert "restored checkpoint 1" in out, out
+
+
+def test_key_level_ops_and_backup_engine(tmp_path):
+    """SampleStore get / get_vertex / delete (the reference's KV surface), vertex deletion cascading to the edge stores,
+    CheckpointManager as a backup engine: list, restore a chosen id (newer rows must vanish), purge."""
+    from graphlearn_b200.dgs import CheckpointManager
+    schema = {"vertices": {"u": {"count": 8, "feat_dim": 2}, "i": {"count": 8, "feat_dim": 0}},
+              "edges": {"click": {"src": "u", "dst": "i"}}}
+    svc = DynamicGraphService(schema, device="cpu")
+    svc.install_query(0, QueryPlan("u").out("click", 3))
+    svc.apply_updates({"vertices": {"u": {"id": [1, 2], "ts": [5, 6], "feat": [[1.0, 1.5], [2.0, 2.5]]}},
+                       "edges": {"click": {"src": [1, 1, 1, 1, 2], "dst": [3, 4, 5, 6, 7], "ts": [10, 40, 20, 30, 50], "weight": [1, 2, 3, 4, 5]}}})
+    st = svc.stores["click"]
+    nbr, ts, w = st.get(1)
+    assert nbr.tolist() == [4, 6, 5] and ts.tolist() == [40, 30, 20] and w.tolist() == [2.0, 4.0, 3.0]   # newest first, oldest evicted
+    assert st.get(5)[0].numel() == 0 and st.get(10 ** 9)[0].numel() == 0
+    f, fts = svc.vstores["u"].get_vertex(2)
+    assert f.tolist() == [2.0, 2.5] and fts == 6 and svc.vstores["u"].get_vertex(3) is None
+    ck = CheckpointManager(svc, str(tmp_path / "bk"), keep=5)
+    assert ck.save() == 1
+    svc.apply_updates({"edges": {"click": {"src": [30], "dst": [1], "ts": [99]}}})        # grows the table past the snapshot
+    assert ck.save() == 2
+    assert svc.delete_vertices("u", [1]) == 3 + 0 and st.get(1)[0].numel() == 0 and svc.vstores["u"].get_vertex(1) is None
+    assert svc.run_query(0, [1])["hops"][0]["ids"].tolist() == [[-1, -1, -1]]
+    assert svc.delete_edges("click", [2, 2, 777]) == 1
+    assert [b["id"] for b in ck.list_backups()] == [1, 2] and all(b["bytes"] > 0 for b in ck.list_backups())
+    assert ck.restore(1) == 1
+    assert st.get(1)[0].tolist() == [4, 6, 5] and st.get(2)[0].tolist() == [7] and st.get(30)[0].numel() == 0
+    assert ck.restore_latest() == 2 and st.get(30)[0].tolist() == [1]
+    import pytest as _pt
+    with _pt.raises(FileNotFoundError):
+        ck.restore(9)
+    assert ck.purge(keep=1) == 1 and [b["id"] for b in ck.list_backups()] == [2]
