@@ -103,6 +103,10 @@ void dgs_apply_edges(const at::Tensor&, const at::Tensor&, const at::Tensor&, co
                      const at::Tensor&, const c10::optional<at::Tensor>&);
 std::vector<at::Tensor> dgs_lookup(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, int64_t);
 // host_loader.cpp
+std::vector<at::Tensor> parse_records(const std::string&, int64_t, int64_t, const std::string&, const std::string&, const std::vector<std::string>&,
+                                      const std::vector<int64_t>&, const std::vector<int64_t>&, const std::vector<int64_t>&,
+                                      const std::vector<int64_t>&, const std::vector<int64_t>&, const std::vector<int64_t>&,
+                                      const std::vector<int64_t>&, int64_t);
 std::vector<at::Tensor> load_table(const std::string&, bool, bool, bool, bool, std::vector<int64_t>,
                                    std::vector<int64_t>, const std::string&, const std::string&, int64_t,
                                    int64_t, int64_t);
@@ -212,5 +216,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dgs_apply_edges", &glb::dgs_apply_edges);
   m.def("dgs_lookup", &glb::dgs_lookup);
   m.def("load_table", &glb::load_table);
+  m.def("parse_records", &glb::parse_records);
   m.def("save_embeddings", &glb::save_embeddings);
 }

@@ -335,4 +335,136 @@ void save_embeddings(const std::string& path, const at::Tensor& ids, const at::T
   std::fclose(fp);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming-record parser of the dynamic graph service's file loader (dgs/file_loader.py; reference: the C++ data-loader
+// SDK + apps/file_loader, dynamic_graph_service/dataloader/apps/file_loader/loader.cc).  A data line is
+//     <type name><delim><field 1><delim>...                e.g.  "u2i,3,17,1001,0.5"   /   "item,17,1000,0.1:0.2:0.3"
+// with the field order given per type by a pattern file.  One call parses up to `max_records` records starting at byte
+// `offset` and returns them as COLUMNS per type, ready for `apply_updates`:
+//     vertex type: ids int64 [n], ts int64 [n], feat fp32 [n, d]          edge type: src, dst, ts int64 [n], w fp32 [n]
+// (4 tensor slots per type, in `names` order; unused slots are empty) + meta int64 [next_offset, records, skipped_lines, eof].
+// Lines of unknown types or with a wrong field count are skipped like the Python loader does; malformed numbers are errors.
+// ---------------------------------------------------------------------------------------------------------------
+std::vector<at::Tensor> parse_records(const std::string& path, int64_t offset, int64_t max_records, const std::string& delim,
+                                      const std::string& list_delim, const std::vector<std::string>& names,
+                                      const std::vector<int64_t>& kinds,          // 0 vertex, 1 edge
+                                      const std::vector<int64_t>& n_fields,       // fields after the type name
+                                      const std::vector<int64_t>& ts_idx,         // field index of the timestamp or -1
+                                      const std::vector<int64_t>& w_idx,          // field index of the weight or -1 (edges)
+                                      const std::vector<int64_t>& feat_off,       // [types + 1] ranges into the two lists below
+                                      const std::vector<int64_t>& feat_field,     // field indices forming the feature row, in order
+                                      const std::vector<int64_t>& feat_is_list,   // 1: list_delim separated values
+                                      int64_t window_bytes) {
+  const size_t T = names.size();
+  TORCH_CHECK(delim.size() == 1 && list_delim.size() == 1, "single-character delimiters only");
+  TORCH_CHECK(kinds.size() == T && n_fields.size() == T && ts_idx.size() == T && w_idx.size() == T && feat_off.size() == T + 1 &&
+              feat_field.size() == feat_is_list.size() && (int64_t)feat_field.size() == feat_off[T], "inconsistent record specs");
+  TORCH_CHECK(max_records > 0 && offset >= 0 && window_bytes >= 4096);
+  const char dl = delim[0], ldl = list_delim[0];
+  FILE* fp = std::fopen(path.c_str(), "rb");
+  TORCH_CHECK(fp != nullptr, "cannot open ", path);
+  std::fseek(fp, 0, SEEK_END);
+  const long sz = std::ftell(fp);
+  std::vector<char> buf;
+  long got = 0;
+  bool window_hits_eof = false;
+  // read a window; grow it until it holds at least one complete line (or the rest of the file)
+  for (int64_t want = window_bytes;; want *= 4) {
+    const long n = (long)std::min<int64_t>(want, std::max<long>(0, sz - (long)offset));
+    buf.resize((size_t)n);
+    std::fseek(fp, (long)offset, SEEK_SET);
+    got = n > 0 ? (long)std::fread(buf.data(), 1, (size_t)n, fp) : 0;
+    window_hits_eof = (long)offset + got >= sz;
+    if (window_hits_eof || got == 0 || memchr(buf.data(), '\n', (size_t)got) != nullptr) break;
+  }
+  std::fclose(fp);
+  const char* base = buf.data();
+  const char* end = base + got;
+  if (!window_hits_eof) {                        // cut at the last complete line
+    const char* q = end;
+    while (q > base && q[-1] != '\n') --q;
+    end = q;
+  }
+  struct Col { std::vector<int64_t> a, b, ts; std::vector<float> w, feat; int64_t d = -1; };
+  std::vector<Col> cols(T);
+  int64_t records = 0, skipped = 0;
+  std::vector<std::pair<const char*, const char*>> f;
+  const char* p = base;
+  while (p < end && records < max_records) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* next = eol ? eol + 1 : end;
+    const char* le = eol ? eol : end;
+    if (le > p && le[-1] == '\r') --le;
+    if (le == p) { p = next; continue; }
+    // split
+    f.clear();
+    const char* fs = p;
+    for (const char* c = p; c <= le; ++c) {
+      if (c == le || *c == dl) { f.emplace_back(fs, c); fs = c + 1; }
+    }
+    size_t t = T;
+    for (size_t i = 0; i < T; ++i)
+      if (names[i].size() == (size_t)(f[0].second - f[0].first) && std::memcmp(names[i].data(), f[0].first, names[i].size()) == 0) { t = i; break; }
+    if (t == T || (int64_t)f.size() - 1 != n_fields[t] || n_fields[t] < (kinds[t] == 1 ? 2 : 1)) { ++skipped; p = next; continue; }
+    Col& c = cols[t];
+    auto fld = [&](int64_t i) { return f[(size_t)i + 1]; };
+    auto fail = [&](const char* what) {
+      TORCH_CHECK(false, path, ": bad ", what, " in record at byte ", (long long)(offset + (p - base)), ": ", std::string(p, (size_t)std::min<long>(le - p, 120)));
+    };
+    int64_t ts = 0;
+    if (ts_idx[t] >= 0 && !parse_i64(fld(ts_idx[t]).first, fld(ts_idx[t]).second, &ts)) fail("timestamp");
+    int64_t k0 = 0, k1 = 0;
+    if (!parse_i64(fld(0).first, fld(0).second, &k0)) fail("id");
+    if (kinds[t] == 1) {
+      if (n_fields[t] < 2 || !parse_i64(fld(1).first, fld(1).second, &k1)) fail("destination id");
+      float w = 1.f;
+      if (w_idx[t] >= 0 && !parse_f32(fld(w_idx[t]).first, fld(w_idx[t]).second, &w)) fail("weight");
+      c.a.push_back(k0); c.b.push_back(k1); c.ts.push_back(ts); c.w.push_back(w);
+    } else {
+      const size_t before = c.feat.size();
+      for (int64_t j = feat_off[t]; j < feat_off[t + 1]; ++j) {
+        const auto fv = fld(feat_field[(size_t)j]);
+        if (feat_is_list[(size_t)j]) {
+          const char* vs = fv.first;
+          for (const char* q = fv.first; q <= fv.second; ++q) {
+            if (q == fv.second || *q == ldl) {
+              if (q > vs) { float v; if (!parse_f32(vs, q, &v)) fail("list attribute"); c.feat.push_back(v); }
+              vs = q + 1;
+            }
+          }
+        } else if (fv.second > fv.first) {
+          float v;
+          if (!parse_f32(fv.first, fv.second, &v)) fail("attribute");
+          c.feat.push_back(v);
+        }
+      }
+      const int64_t d = (int64_t)(c.feat.size() - before);
+      if (c.d < 0) c.d = d;
+      if (d != c.d) fail("feature width (ragged rows)");
+      c.a.push_back(k0); c.ts.push_back(ts);
+    }
+    ++records;
+    p = next;
+  }
+  const int64_t consumed = (int64_t)(p - base);
+  auto i64 = [](const std::vector<int64_t>& v) { return at::from_blob((void*)v.data(), {(int64_t)v.size()}, at::kLong).clone(); };
+  auto f32 = [](const std::vector<float>& v) { return at::from_blob((void*)v.data(), {(int64_t)v.size()}, at::kFloat).clone(); };
+  std::vector<at::Tensor> out;
+  out.reserve(T * 4 + 1);
+  for (size_t t = 0; t < T; ++t) {
+    const Col& c = cols[t];
+    if (kinds[t] == 1) { out.push_back(i64(c.a)); out.push_back(i64(c.b)); out.push_back(i64(c.ts)); out.push_back(f32(c.w)); }
+    else {
+      out.push_back(i64(c.a)); out.push_back(i64(c.ts));
+      out.push_back(f32(c.feat).reshape({(int64_t)c.a.size(), c.d < 0 ? 0 : c.d}));
+      out.push_back(at::empty({0}, at::kFloat));
+    }
+  }
+  const bool eof = (long)(offset + consumed) >= sz;
+  auto meta = at::empty({4}, at::kLong);
+  meta[0] = offset + consumed; meta[1] = records; meta[2] = skipped; meta[3] = eof ? 1 : 0;
+  out.push_back(meta);
+  return out;
+}
+
 }  // namespace glb

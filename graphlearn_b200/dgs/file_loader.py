@@ -42,8 +42,12 @@ class RecordBatchBuilder(object):
 
 class FileLoader(object):
     def __init__(self, pattern_file: str, schema, delimiter: str = ",", list_delimiter: str = ":",
-                 batch_size: int = 4096, reverse_edges: Dict[str, str] = None):
+                 batch_size: int = 4096, reverse_edges: Dict[str, str] = None, native: bool = True):
+        """``native``: parse with the C++ record parser (``csrc/host_loader.cpp parse_records``: columnar batches straight from
+        the file, ~two orders of magnitude faster than the line-by-line Python path below, which stays as the oracle and the
+        fallback when the extension is not built)."""
         self.schema, self.delim, self.ldelim, self.batch_size = schema, delimiter, list_delimiter, batch_size
+        self.native = native
         self.patterns: Dict[str, tuple] = {}
         self.reverse_edges = reverse_edges or {}      # etype -> reversed etype fed with (dst, src)
         with open(pattern_file) as f:
@@ -51,9 +55,10 @@ class FileLoader(object):
                 parts = line.strip().split(delimiter)
                 if not parts or not parts[0].startswith("#"):
                     continue
-                kind, name = parts[0][1:].split(":")
-                if kind not in ("VERTEX", "EDGE"):
-                    continue
+                head = parts[0][1:].split(":")
+                if len(head) != 2 or head[0] not in ("VERTEX", "EDGE"):
+                    continue                                  # a comment line
+                kind, name = head
                 self.patterns[name] = (kind, parts[1:])
 
     def _feat(self, fields: Dict[str, str], attrs) -> List[float]:
@@ -69,6 +74,10 @@ class FileLoader(object):
         """Stream one file into the service; returns the number of records applied.  ``adaptive=True`` scales the
         ingest batch size with the service's ``AdaptiveRateLimiter`` (record-polling concurrency in the reference:
         the limiter shrinks ingest when query latencies miss their P99 target and restores it when stable)."""
+        if self.native and len(self.delim) == 1 and len(self.ldelim) == 1:
+            C = _native_or_none()
+            if C is not None:
+                return self._load_native(C, path, service, adaptive)
         b, n = RecordBatchBuilder(), 0
         base_bs = self.batch_size
         with open(path) as f:
@@ -98,6 +107,67 @@ class FileLoader(object):
             service.apply_updates(b.finish())
         self.batch_size = base_bs
         return n
+
+
+    def _specs(self):
+        names = list(self.patterns)
+        kinds, n_fields, ts_idx, w_idx, feat_off, feat_field, feat_is_list = [], [], [], [], [0], [], []
+        for name in names:
+            kind, fields = self.patterns[name]
+            kinds.append(0 if kind == "VERTEX" else 1)
+            n_fields.append(len(fields))
+            ts_idx.append(fields.index("timestamp") if "timestamp" in fields else -1)
+            w_idx.append(fields.index("weight") if kind == "EDGE" and "weight" in fields else -1)
+            if kind == "VERTEX":
+                for a in self.schema.vertex_attrs.get(name, []):
+                    if a.name in ("timestamp", "weight") or a.name not in fields:
+                        continue
+                    feat_field.append(fields.index(a.name))
+                    feat_is_list.append(1 if a.is_list else 0)
+            feat_off.append(len(feat_field))
+        return names, kinds, n_fields, ts_idx, w_idx, feat_off, feat_field, feat_is_list
+
+    def _load_native(self, C, path: str, service, adaptive: bool) -> int:
+        names, kinds, n_fields, ts_idx, w_idx, feat_off, feat_field, feat_is_list = self._specs()
+        base_bs, off, total = self.batch_size, 0, 0
+        while True:
+            out = C.parse_records(path, off, max(1, self.batch_size), self.delim, self.ldelim, names, kinds, n_fields, ts_idx, w_idx,
+                                  feat_off, feat_field, feat_is_list, 8 << 20)
+            off, n, _, eof = (int(x) for x in out[-1].tolist())
+            if n:
+                batch = {"edges": {}, "vertices": {}}
+                for t, name in enumerate(names):
+                    a, b_, c, d = out[4 * t:4 * t + 4]
+                    if a.numel() == 0:
+                        continue
+                    if kinds[t] == 0:
+                        batch["vertices"][name] = {"id": a.numpy(), "ts": b_.numpy(), "feat": c.numpy()}
+                    else:
+                        batch["edges"].setdefault(name, []).append((a, b_, c, d))
+                        if name in self.reverse_edges:
+                            batch["edges"].setdefault(self.reverse_edges[name], []).append((b_, a, c, d))
+                batch["edges"] = {k: {"src": np.concatenate([p[0].numpy() for p in v]), "dst": np.concatenate([p[1].numpy() for p in v]),
+                                      "ts": np.concatenate([p[2].numpy() for p in v]),
+                                      "weight": np.concatenate([p[3].numpy() for p in v]).astype(np.float64)}
+                                  for k, v in batch["edges"].items()}
+                service.apply_updates(batch)
+                total += n
+                if adaptive and hasattr(service, "limiter"):
+                    c_ = service.limiter.tick()
+                    self.batch_size = max(1, base_bs * c_ // max(service.limiter.max_c, 1))
+            if eof or (n == 0 and off == 0 and eof):
+                break
+        self.batch_size = base_bs
+        return total
+
+
+def _native_or_none():
+    try:
+        from ..parallel.runtime import native
+        C = native()
+        return C if hasattr(C, "parse_records") else None
+    except Exception:  # noqa: BLE001  (extension not built: the Python path is complete)
+        return None
 
 
 class GroupProducer(object):

@@ -470,3 +470,70 @@ def test_key_level_ops_and_backup_engine(tmp_path):
     with _pt.raises(FileNotFoundError):
         ck.restore(9)
     assert ck.purge(keep=1) == 1 and [b["id"] for b in ck.list_backups()] == [2]
+
+
+def test_native_record_parser_matches_python_loader(tmp_path):
+    """csrc/host_loader.cpp parse_records (columnar batches straight from the file) vs the line-by-line Python loader: same
+    service state for vertices with list + scalar attributes, weighted / unweighted and reversed edges, skipped lines, CRLF
+    line ends, a missing final newline and batch sizes that cut the file into many windows."""
+    from graphlearn_b200.dgs import FileLoader, Schema
+    schema = Schema({
+        "attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}, {"type": 1, "name": "weight", "value_type": "FLOAT32"},
+                      {"type": 2, "name": "feature", "value_type": "FLOAT32_LIST"}, {"type": 3, "name": "age", "value_type": "FLOAT32"}],
+        "vertex_defs": [{"vtype": 0, "name": "user", "attr_types": [0, 3, 2]}, {"vtype": 1, "name": "item", "attr_types": [0, 2]}],
+        "edge_defs": [{"etype": 2, "name": "u2i", "attr_types": [0, 1]}, {"etype": 3, "name": "i2u", "attr_types": [0, 1]},
+                      {"etype": 4, "name": "i2i", "attr_types": [0]}],
+        "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}, {"etype": 3, "src_vtype": 1, "dst_vtype": 0},
+                               {"etype": 4, "src_vtype": 1, "dst_vtype": 1}]})
+    (tmp_path / "pattern").write_text("#VERTEX:user,vid,timestamp,feature,age\n#VERTEX:item,vid,feature,timestamp\n"
+                                      "#EDGE:u2i,src,dst,timestamp,weight\n#EDGE:i2i,src,dst,timestamp\n# a comment\n")
+    rs = np.random.RandomState(1)
+    lines = []
+    for i in range(700):
+        r = rs.randint(0, 6)
+        if r == 0:
+            lines.append("user,%d,%d,%.3f:%.3f:%.3f,%d" % (rs.randint(0, 50), i, rs.rand(), rs.rand(), rs.rand(), rs.randint(18, 80)))
+        elif r == 1:
+            lines.append("item,%d,%.2f:%.2f,%d" % (rs.randint(0, 80), rs.rand(), rs.rand(), i))
+        elif r in (2, 3):
+            lines.append("u2i,%d,%d,%d,%.2f" % (rs.randint(0, 50), rs.randint(0, 80), rs.randint(0, 5000), rs.rand()))
+        elif r == 4:
+            lines.append("i2i,%d,%d,%d" % (rs.randint(0, 80), rs.randint(0, 80), rs.randint(0, 5000)))
+        else:
+            lines.append(["unknown,1,2,3", "u2i,1,2", "", "item,3,0.5:0.5,7,extra"][rs.randint(0, 4)])      # all skipped
+    data = tmp_path / "data"
+    data.write_bytes(("\r\n".join(lines[:350]) + "\r\n" + "\n".join(lines[350:])).encode())               # CRLF half, no final newline
+
+    def build(native, bs):
+        svc = DynamicGraphService(schema.to_service_schema(capacity=8, feat_dims={"user": 4, "item": 2}), device="cpu")
+        svc.install_query(0, QueryPlan("user").out("u2i", 4).out("i2u", 3))
+        svc.install_query(1, QueryPlan("item").out("i2i", 5))
+        n = FileLoader(str(tmp_path / "pattern"), schema, batch_size=bs, reverse_edges={"u2i": "i2u"}, native=native).load(str(data), svc)
+        return svc, n
+    ref, n_ref = build(False, 64)
+    want = {"user": 5, "item": 4, "u2i": 5, "i2i": 4}
+    assert n_ref == sum(1 for l in lines if want.get(l.split(",")[0]) == len(l.split(",")))
+    for bs in (64, 7, 100000):
+        nat, n_nat = build(True, bs)
+        assert n_nat == n_ref
+        for et in ("u2i", "i2u", "i2i"):
+            a, b = ref.stores[et], nat.stores[et]
+            m = min(a.n, b.n)
+            assert torch.equal(a.count[:m], b.count[:m]) and int(a.count[m:].sum()) == 0 and int(b.count[m:].sum()) == 0
+            # same kept (timestamp, neighbour, weight) multisets per vertex; ties may sit in different slots
+            for v in range(m):
+                ka = sorted(zip(*(x.tolist() for x in a.get(v))))
+                kb = sorted(zip(*(x.tolist() for x in b.get(v))))
+                assert [x[1] for x in ka] == [x[1] for x in kb], (et, v)
+        for vt in ("user", "item"):
+            a, b = ref.vstores[vt], nat.vstores[vt]
+            m = min(a.n, b.n)
+            assert torch.equal(a.feat_ts[:m], b.feat_ts[:m])
+            assert torch.allclose(a.feat[:m], b.feat[:m]) and float(a.feat[:m].abs().sum()) > 0       # vertex timestamps are unique
+            if vt == "user":                                        # schema order (age, feature), not pattern order
+                v = int((a.feat_ts > -(2 ** 61)).nonzero()[0])
+                assert float(a.feat[v, 0]) >= 18
+    # malformed numbers are errors, not silently dropped records
+    (tmp_path / "bad").write_text("u2i,1,x,3,0.5\n")
+    with pytest.raises(RuntimeError):
+        FileLoader(str(tmp_path / "pattern"), schema, native=True).load(str(tmp_path / "bad"), ref)
