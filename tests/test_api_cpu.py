@@ -621,3 +621,21 @@ def test_dedup_before_pull_lookup(tmp_path):
         gl.set_dedup_feature_pull(False)
     assert np.array_equal(a, b) and bool((x == y).all())
     g.close()
+
+
+def test_cpp_api_example_builds(tmp_path):
+    """L7: a plain C++ program written against include/glb/api.h compiles and links against the in-tree _C.so + libtorch
+    (examples/cpp; running it needs a GPU - the same entry points run under tests/test_cpp_api_gpu.py through pybind)."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None or shutil.which("python3-config") is None or not os.path.exists(os.path.join(root, "graphlearn_b200", "_C.so")):
+        pytest.skip("needs g++, python3-config and the built extension")
+    out = str(tmp_path / "sample_and_lookup")
+    p = subprocess.run(["make", "-C", os.path.join(root, "examples", "cpp"), "OUT=" + out, "PY=" + sys.executable],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and os.path.exists(out), (p.stdout + p.stderr)[-3000:]
+    sym = subprocess.run(["nm", "-D", "--undefined-only", out], capture_output=True, text=True).stdout
+    assert "glb3api5Graph" in sym and "glb3api7Dataset" in sym          # resolved from _C.so at load time
