@@ -99,3 +99,19 @@ class Trainer(object):
             state["opt"] = self.opt.state_dict()
         save_checkpoint(path, extra=state, datasets={"train": self.dataset} if hasattr(self.dataset, "state_dict") else None,
                         rank=self.rt.rank)
+
+    def load(self, path: str) -> bool:
+        """Restore what ``save`` wrote for this rank (parameters, optimiser moments, step counter, traversal cursor);
+        False when there is no checkpoint."""
+        import os
+        from ..utils.checkpoint import load_checkpoint
+        if not os.path.exists("%s.rank%d" % (path, self.rt.rank)):
+            return False
+        st = load_checkpoint(path, datasets={"train": self.dataset} if hasattr(self.dataset, "load_state_dict") else None,
+                             rank=self.rt.rank, map_location=self.flat_p.device)
+        with torch.no_grad():
+            self.flat_p.copy_(st["model"].to(self.flat_p.device))
+        if self._flat_opt and "opt" in st:
+            self.opt.load_state_dict(st["opt"])
+        self.global_step = int(st["step"])
+        return True

@@ -542,3 +542,48 @@ def test_eval_metrics_recall_ndcg_f1():
     emb = lab.astype(np.float64) + 0.05 * rs.randn(300, 4)
     f1 = M.multilabel_f1(emb, lab, train_ratios=(0.5,), shuffles=1)
     assert f1[0.5]["micro"] > 0.95 and f1[0.5]["macro"] > 0.95
+
+
+def test_local_and_dist_trainer_reference_surface(tmp_path):
+    """engine/trainers.py: LocalTrainer / DistTrainer with the reference trainers' method names - train (periodic checkpoints,
+    resume), test, train_and_evaluate, save_node_embedding(_bigdata), join."""
+    from graphlearn_b200.engine.trainers import DistTrainer, LocalTrainer
+    g = fx.build_graph(fx.write_graph(str(tmp_path / "g")))
+
+    def make_ds():
+        return gl.Dataset(g.V("user").batch(8).shuffle(traverse=True).alias("u").outV("buy").sample(3).by("edge_weight").alias("i").values())
+
+    def step(m, b):
+        return F.cross_entropy(m(b["i"].tensor("float_attrs").mean(1)), b["u"].tensor("labels"))
+
+    def acc(m, b):
+        return (m(b["i"].tensor("float_attrs").mean(1)).argmax(1) == b["u"].tensor("labels")).float().mean()
+
+    def embed(m, b):
+        return b["u"].ids_t, m(b["i"].tensor("float_attrs").mean(1))
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    ck = str(tmp_path / "ckpt")
+    tr = LocalTrainer(ckpt_dir=ck, save_checkpoint_secs=None, save_checkpoint_steps=4, progress_steps=1000)
+    first = tr.train(make_ds(), model, step, learning_rate=2e-2, epochs=1)
+    loss, metric = tr.train_and_evaluate(make_ds(), make_ds(), model, step, acc, learning_rate=2e-2, epochs=10)
+    assert loss < first and 0.0 <= metric <= 1.0
+    steps_per_epoch = fx.N_USER // 8
+    assert tr.global_step == 11 * steps_per_epoch                 # the second call resumed from the first one's checkpoint
+    assert os.path.exists(os.path.join(ck, "model.ckpt.rank0"))
+    # a fresh trainer + fresh model pick the checkpoint up (parameters and step counter)
+    model2 = torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    tr2 = LocalTrainer(ckpt_dir=ck, save_checkpoint_secs=0.0001, progress_steps=1000)        # time-based checkpoints: step-wise loop
+    tr2.train(make_ds(), model2, step, learning_rate=2e-2, epochs=1)
+    assert tr2.global_step == 12 * steps_per_epoch
+    assert abs(tr2.test(make_ds(), model2, acc) - tr.test(make_ds(), model, acc)) < 0.35
+    out = str(tmp_path / "emb.txt")
+    tr2.save_node_embedding(out, make_ds(), model2, embed)
+    lines = open(out + ".rank0").read().strip().split("\n")
+    assert lines[0] == "id:int64\temb:string" and len(lines) == 1 + fx.N_USER
+    tr2.save_node_embedding_bigdata(str(tmp_path / "big.txt"), make_ds(), model2, embed, block_max_lines=20)
+    assert len([f for f in os.listdir(str(tmp_path)) if f.startswith("big")]) == (fx.N_USER + 19) // 20
+    dt = DistTrainer(cluster_spec={"worker": ["a"]}, job_name="worker", ckpt_dir=None, progress_steps=1000)
+    assert dt.is_chief and dt.worker_count == 1 and not dt.is_local
+    dt.train(make_ds(), model, step, learning_rate=1e-2, epochs=1)
+    dt.join()
