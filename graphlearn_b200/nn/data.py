@@ -11,6 +11,10 @@ import torch
 
 class Data(object):
     def __init__(self, ids=None, ints=None, floats=None, strings=None, labels=None, weights=None, **kwargs):
+        # the reference's constructor names (nn/data.py Data(ids, int_attrs, float_attrs, string_attrs, ...)) are accepted too
+        ints = kwargs.pop("int_attrs", ints)
+        floats = kwargs.pop("float_attrs", floats)
+        strings = kwargs.pop("string_attrs", strings)
         self.ids, self.ints, self.floats, self.strings = ids, ints, floats, strings
         self.labels, self.weights = labels, weights
         for k, v in kwargs.items():
