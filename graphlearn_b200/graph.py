@@ -106,22 +106,31 @@ class Graph(object):
         self._edge_decoders[met] = decoder
         self._topology.add(met, st, dt)
 
-        def add(types, direction):
-            if isinstance(source, dict):
-                self._edge_sources.append(Source("edge", None, types, decoder, direction, option, data=source))
-            else:
-                self._edge_sources.append(Source("edge", source, types, decoder, direction, option))
-
-        add((st, dt, met), ORIGIN)
+        self._add_edge_source(source, (st, dt, met), decoder, ORIGIN, option)
         if not directed:
-            self._undirected_edges.append(et)
-            if st != dt:
-                rt_ = et + "_reverse"
-                self._edge_decoders[rt_] = decoder
-                self._topology.add(rt_, dt, st)
-                add((dt, st, rt_), REVERSED)
-            else:
-                add((st, dt, met), REVERSED)
+            self.add_reverse_edges((st, dt, met) if st == dt else (st, dt, et), source, decoder, option)
+        return self
+
+    def _add_edge_source(self, source, types, decoder, direction, option):
+        if isinstance(source, dict):
+            self._edge_sources.append(Source("edge", None, types, decoder, direction, option, data=source))
+        else:
+            self._edge_sources.append(Source("edge", source, types, decoder, direction, option))     # comma lists / dirs: the loader expands them
+
+    def add_reverse_edges(self, edge_type, source, decoder, option=None):
+        """Load ``source`` a second time with the end points swapped (graph.py:357-381): into the same edge type when
+        src_type == dst_type, otherwise as ``<edge_type>_reverse``.  ``edge(..., directed=False)`` calls this."""
+        st, dt, et = edge_type
+        raw = et[len("MASK"):].split("_", 1)[1] if et.startswith("MASK") and "_" in et else et
+        if raw not in self._undirected_edges:
+            self._undirected_edges.append(raw)
+        if st != dt:
+            rt_ = et + "_reverse"
+            self._edge_decoders[rt_] = decoder
+            self._topology.add(rt_, dt, st)
+            self._add_edge_source(source, (dt, st, rt_), decoder, REVERSED, option)
+        else:
+            self._add_edge_source(source, (st, dt, et), decoder, REVERSED, option)
         return self
 
     @property
@@ -175,6 +184,67 @@ class Graph(object):
             self._server = GraphServer(self, address=_parse(addrs[int(task_index) % len(addrs)]),
                                        client_count=int(spec.get("client_count", 1))).start()
         return self
+
+    # ---- the reference's deployment entry points (graph.py:439-511); ``init`` picks one of them from its arguments
+    def deploy_in_local_mode(self, task_index=0):
+        """one process, one shard (``g.init()`` without a cluster)"""
+        return self.init(task_index=task_index)
+
+    def deploy_in_worker_mode(self, tracker=None, hosts=None, task_index=0, task_count=1):
+        """every process owns a shard AND trains (``torchrun``): the tracker directory / host list of the reference are not
+        needed - the ranks rendezvous through ``torch.distributed`` (RANK / WORLD_SIZE); a mismatching ``task_count`` is an error"""
+        import os as _os
+        world = int(_os.environ.get("WORLD_SIZE", "1"))
+        n = len(hosts.split(",")) if hosts else int(task_count)
+        if n != world:
+            raise ValueError("worker mode with %d tasks needs a %d-process torchrun job (WORLD_SIZE is %d)" % (n, n, world))
+        return self.init(task_index=task_index, task_count=n)
+
+    def deploy_in_server_mode(self, task_index, cluster, job_name):
+        """``job_name`` 'server': build this shard and serve it; 'client': connect to the servers of ``cluster``"""
+        if job_name not in ("server", "client"):
+            raise ValueError("job_name must be 'server' or 'client'")
+        if not isinstance(cluster, (dict, str)):
+            raise ValueError("cluster must be dict or json string.")
+        return self.init(task_index=task_index, cluster=cluster, job_name=job_name)
+
+    def node_attributes(self, node_type, attrs, n_int=0, n_float=0, n_string=0):
+        """Keep only the named attribute columns of a node source (the reference offers this for Vineyard property graphs,
+        graph.py:265-277): ``attrs`` are 0-based positions (or 'a<i>' names) into the source's attribute list, in the order
+        int, float, string; the decoder is rewritten accordingly."""
+        return self._select_attrs(self._node_sources, self._node_decoders, node_type, attrs, n_int, n_float, n_string, "Node")
+
+    def edge_attributes(self, edge_type, attrs, n_int=0, n_float=0, n_string=0):
+        return self._select_attrs(self._edge_sources, self._edge_decoders, edge_type, attrs, n_int, n_float, n_string, "edge")
+
+    def _select_attrs(self, sources, decoders, type_name, attrs, n_int, n_float, n_string, what):
+        srcs = [s for s in sources if (s.types if isinstance(s.types, str) else s.types[2]) == type_name]
+        if not srcs:
+            raise ValueError('%s type "%s" doesn\'t exist.' % (what, type_name))
+        dec = decoders[type_name]
+        idx = [int(a[1:]) if isinstance(a, str) and a[:1] == "a" and a[1:].isdigit() else int(a) for a in attrs]
+        if len(idx) != n_int + n_float + n_string:
+            raise ValueError("%d attributes selected, but n_int + n_float + n_string = %d" % (len(idx), n_int + n_float + n_string))
+        from .store.graph_store import storage_kinds
+        kinds = storage_kinds(dec)
+        for i, t in zip(idx, ["int"] * n_int + ["float"] * n_float + ["string"] * n_string):
+            have = kinds[i] if 0 <= i < len(kinds) else None
+            if have != t:
+                raise ValueError("attribute %d of %s is stored as %r, selected as %r" % (i, type_name, have, t))
+        new = Decoder(weighted=dec.weighted, labeled=dec.labeled, timestamped=dec.timestamped,
+                      attr_types=[dec.attr_types[i] for i in idx], attr_delimiter=dec.attr_delimiter)
+        for s in srcs:
+            s.use_attrs = list(idx)
+            s.decoder_full, s.decoder = dec, new
+        decoders[type_name] = new
+        return self
+
+    def vineyard(self, handle, nodes=None, edges=None):
+        """Vineyard object stores are not part of this runtime: load the graph from files / arrays instead."""
+        raise errors.UnimplementedError("vineyard sources are not supported: use node() / edge() with files or in-memory arrays")
+
+    def init_vineyard(self, server_index=None, worker_index=None, worker_count=None, standalone=False):
+        raise ValueError("Not a vineyard graph")
 
     @property
     def remote(self) -> bool:

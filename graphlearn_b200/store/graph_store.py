@@ -96,13 +96,45 @@ def _loader_threads(ranks_on_box: int) -> int:
     return n if n > 0 else max(1, (os.cpu_count() or 8) // max(int(ranks_on_box), 1))
 
 
+def storage_kinds(dec: Decoder) -> List[str]:
+    """per attribute position: the column group it is stored in ('int' | 'float' | 'string'; hashed strings are ints)"""
+    out = []
+    for name, bucket, multival in dec._parsed:
+        out.append("int" if name == "int" or (name == "string" and bucket is not None and not multival) else name)
+    return out
+
+
 def _load_source(src: Source, part_index: int = 0, part_count: int = 1) -> Dict[str, object]:
+    """``Graph.node_attributes / edge_attributes`` selections (``src.use_attrs``: attribute positions of the FULL decoder
+    ``src.decoder_full``) are applied after parsing: the unselected columns are dropped here and never reach the device."""
+    use = getattr(src, "use_attrs", None)
+    if use is None:
+        return _load_source_all(src, src.decoder, part_index, part_count)
+    full: Decoder = src.decoder_full
+    out = _load_source_all(src, full, part_index, part_count)
+    kinds = storage_kinds(full)
+    col = {}
+    seen = {"int": 0, "float": 0, "string": 0}
+    for i, k in enumerate(kinds):
+        col[i] = seen[k]
+        seen[k] += 1
+    pick = {"int": [col[i] for i in use if kinds[i] == "int"], "float": [col[i] for i in use if kinds[i] == "float"],
+            "string": [col[i] for i in use if kinds[i] == "string"]}
+    if out["ia"] is not None:
+        out["ia"] = out["ia"][:, pick["int"]] if pick["int"] else None
+    if out["fa"] is not None:
+        out["fa"] = out["fa"][:, pick["float"]] if pick["float"] else None
+    if out["strs"] is not None:
+        out["strs"] = np.asarray(out["strs"], dtype=object)[:, pick["string"]] if pick["string"] else None
+    return out
+
+
+def _load_source_all(src: Source, dec: Decoder, part_index: int = 0, part_count: int = 1) -> Dict[str, object]:
     """-> dict(a, b, w, label, ts, ia, fa, strs) of CPU tensors.
 
     ``part_count > 1`` reads only this rank's share (SliceReader, graphlearn/src/core/io/
     slice_reader.h:60-86,137-157): a single file is cut into ``part_count`` contiguous record
     ranges; the files of a directory are dealt round-robin, whole, to the parts."""
-    dec: Decoder = src.decoder
     if src.data is not None:
         d = src.data
         g = lambda k: (None if d.get(k) is None else torch.as_tensor(np.asarray(d[k]) if not isinstance(d[k], torch.Tensor) else d[k]))  # noqa: E731

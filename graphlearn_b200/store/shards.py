@@ -458,11 +458,11 @@ class CsrShard:
             # as the two stable sorts below, without sorting E keys globally
             from ..parallel.runtime import native
             if ts is not None:
-                indptr, order = native().csr_build(src_rows.contiguous(), n_src_rows, ts.to(torch.int64), 1)
+                indptr, order = native().csr_build(src_rows.to(torch.int64).contiguous(), n_src_rows, ts.to(torch.int64), 1)
             elif weights is not None:
-                indptr, order = native().csr_build(src_rows.contiguous(), n_src_rows, weights.to(torch.float32), 2)
+                indptr, order = native().csr_build(src_rows.to(torch.int64).contiguous(), n_src_rows, weights.to(torch.float32), 2)
             else:
-                indptr, order = native().csr_build(src_rows.contiguous(), n_src_rows, None, 0)
+                indptr, order = native().csr_build(src_rows.to(torch.int64).contiguous(), n_src_rows, None, 0)
         elif E > 0 and not grouped:
             if ts is not None:
                 order = torch.argsort(ts, stable=True)

@@ -1,6 +1,8 @@
 """CPU tests of the public API (Graph / GSL / Dataset / samplers) on closed-form
 fixtures.  They exercise the portable torch path of every op - the same path that
 serves as the oracle for the CUDA kernels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -639,3 +641,36 @@ def test_cpp_api_example_builds(tmp_path):
     assert p.returncode == 0 and os.path.exists(out), (p.stdout + p.stderr)[-3000:]
     sym = subprocess.run(["nm", "-D", "--undefined-only", out], capture_output=True, text=True).stdout
     assert "glb3api5Graph" in sym and "glb3api7Dataset" in sym          # resolved from _C.so at load time
+
+
+def test_graph_deploy_modes_reverse_edges_and_attribute_selection(tmp_path):
+    """Reference Graph methods beyond node/edge/init: add_reverse_edges (what directed=False does), deploy_in_*_mode,
+    node_attributes / edge_attributes column selection (decoder rewritten, unselected columns never loaded), vineyard stubs."""
+    d = fx.write_graph(str(tmp_path))
+    g = gl.Graph()
+    g.node(os.path.join(d, "item.tsv"), "item", decoder=gl.Decoder(attr_types=["float"] * 4))
+    g.edge(os.path.join(d, "i2i.tsv"), ("item", "item", "sim"), decoder=gl.Decoder(labeled=True, timestamped=True))
+    g.add_reverse_edges(("item", "item", "sim"), os.path.join(d, "i2i.tsv"), gl.Decoder(labeled=True, timestamped=True), None)
+    assert g.undirected_edges == ["sim"] and not g.is_directed("sim")
+    g.node_attributes("item", [2, 0], n_float=2)                   # keep float columns 2 and 0, in that order
+    assert g.get_node_decoder("item").float_attr_num == 2
+    with pytest.raises(ValueError):
+        g.node_attributes("nobody", [0], n_float=1)
+    with pytest.raises(ValueError):
+        g.node_attributes("item", [0], n_int=1)                    # column 0 is a float
+    with pytest.raises(ValueError):
+        g.deploy_in_worker_mode(hosts="a:1,b:2", task_index=0)      # 2 tasks but a 1-process job
+    with pytest.raises(ValueError):
+        g.deploy_in_server_mode(0, {"server": "127.0.0.1:1"}, "trainer")
+    with pytest.raises(gl.UnimplementedError):
+        g.vineyard({"server": "x"})
+    with pytest.raises(ValueError):
+        g.init_vineyard(standalone=True)
+    g.deploy_in_local_mode(0) if False else g.init(device="cpu")
+    ids = np.array([0, 3, 7])
+    fa = g.get_nodes("item", ids).float_attrs
+    want = np.array([[fx.item_float(i, 2), fx.item_float(i, 0)] for i in ids], dtype=np.float32)
+    assert fa.shape == (3, 2) and np.allclose(fa, want, atol=1e-5)
+    # both directions of every edge are stored once add_reverse_edges ran
+    assert g.get_stats()["sim"][0] == 2 * sum(1 for _ in open(os.path.join(d, "i2i.tsv"))) - 2
+    g.close()
