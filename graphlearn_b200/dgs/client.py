@@ -376,5 +376,28 @@ class Graph(object):
     def stats(self) -> dict:
         return self._http("GET", "/admin/stats")
 
+    # ---- data-loader side (the reference's dataloader SDK talks to the same service: records + barriers)
+    def load_file(self, pattern_file: str, data_file: str, reverse_edges: Optional[Dict[str, str]] = None) -> int:
+        """ask the service to bulk-load a record file IT can read (pattern-file format of the file-loader app)"""
+        body = {"pattern": pattern_file, "data": data_file}
+        if reverse_edges:
+            body["reverse_edges"] = reverse_edges
+        return int(self._http("POST", "/admin/load", body)["records"])
+
+    def ingest(self, batch: dict) -> int:
+        """push one record batch: {"edges": {etype: {"src", "dst", "ts"[, "weight"]}}, "vertices": {vtype: {"id", "ts", "feat"}}}"""
+        def plain(x):
+            if isinstance(x, dict):
+                return {k: plain(v) for k, v in x.items()}
+            return x.tolist() if hasattr(x, "tolist") else x
+        return int(self._http("POST", "/admin/ingest", plain(batch))["ingested"])
+
+    def set_barrier(self, name: str, after_records: Optional[int] = None):
+        """mark "everything produced so far" (``after_records`` None = the service's current ingest count)"""
+        params = {"name": name}
+        if after_records is not None:
+            params["produced"] = int(after_records)
+        self._http("POST", "/admin/barrier/set", None, **params)
+
     def close(self):
         self._pool.shutdown(wait=False)

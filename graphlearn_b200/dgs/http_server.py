@@ -7,6 +7,8 @@ device stream by a lock.
   GET  /infer?qid=0&vid=12[,13,...]   -> {"src": [...], "nodes": {plan_node_id: {...}}}
   POST /admin/init                     body = install-query JSON (reference format)   -> {"query_id": n}
   POST /admin/ingest                   body = {"edges": {...}, "vertices": {...}}     (testing / small feeds)
+  POST /admin/load                     body = {"pattern": path, "data": path[, "reverse_edges": {etype: reversed etype}]}: bulk-load a
+                                       record file that the SERVICE can read (the file-loader app; native record parser)
   POST /admin/checkpoint               -> {"checkpoint_id": n}
   POST /admin/barrier/set?name=x[&produced=n]     GET /admin/barrier/status?name=x
   GET  /admin/stats                    liveness + counters (k8s probes)
@@ -104,6 +106,13 @@ class HttpFrontEnd(object):
                         with front._lock:
                             front.service.apply_updates(self._body())
                         self._send(200, {"ingested": front.service.ingested})
+                    elif u.path == "/admin/load":
+                        from .file_loader import FileLoader
+                        d = self._body()
+                        fl = FileLoader(d["pattern"], front.schema, reverse_edges=d.get("reverse_edges"))
+                        with front._lock:
+                            n = fl.load(d["data"], front.service)
+                        self._send(200, {"records": n, "ingested": front.service.ingested})
                     elif u.path == "/admin/checkpoint":
                         with front._lock:
                             cid = front.ckpt.save()

@@ -115,3 +115,11 @@ def test_basic_queries_tour(tmp_path):
     step = np.abs(np.diff(np.concatenate([walks[:, :1], walks], 1)[:, 1:], axis=1)) % 120
     assert np.isin(np.minimum(step, 120 - step), [1, 2, 3]).all()      # every hop follows a ring edge
     assert out["knn"][0][0] == 5 and abs(out["knn"][1][0]) < 1e-5
+
+
+def test_u2i_online_pipeline_service_process_and_client():
+    """examples/u2i_online_pipeline.py: offline training on static tables, the streaming service as its own process, query built
+    and installed by the GSL client, record file bulk-loaded through /admin/load (native parser), barrier, online inference on
+    EgoGraph hop tensors - the served neighbourhoods must carry enough signal to recover every user's preferred category."""
+    acc, n, served = _run("u2i_online_pipeline", ["--epochs", "6"])
+    assert n == 67 and served == 67 and acc > 0.85
