@@ -28,6 +28,7 @@ def main(argv=None) -> int:
     ap.add_argument("--checkpoint-interval", type=float, default=0.0, help="seconds between periodic checkpoints (0 = only on demand / exit)")
     ap.add_argument("--install-query", default="", help="install-query JSON to install at start-up")
     ap.add_argument("--load", nargs=2, action="append", default=[], metavar=("PATTERN", "DATA"), help="bulk-load a record file described by a pattern file (repeatable)")
+    ap.add_argument("--admin-token-file", default="", help="file holding the bearer token required on POST /admin/* (default: $GLB_DGS_ADMIN_TOKEN, empty = open)")
     ap.add_argument("--port-file", default="", help="write the bound port here once the service answers (scripts / probes)")
     a = ap.parse_args(argv)
 
@@ -40,8 +41,10 @@ def main(argv=None) -> int:
         dims[k] = int(v)
     svc = DynamicGraphService(schema.to_service_schema(capacity=a.capacity, feat_dims=dims), device=a.device)
     ckpt_dir = a.checkpoint_dir or ""
+    import os
+    token = open(a.admin_token_file).read().strip() if a.admin_token_file else os.environ.get("GLB_DGS_ADMIN_TOKEN", "")
     front = HttpFrontEnd(svc, schema, checkpoint_dir=ckpt_dir, host=a.host,
-                         port=a.port if a.port is not None else int(opt.get("http-port", 0) or 0))
+                         port=a.port if a.port is not None else int(opt.get("http-port", 0) or 0), admin_token=token)
     if front.ckpt is not None:
         front.ckpt.keep = int(opt.get("checkpoint.keep", 3))
         cid = front.ckpt.restore_latest()

@@ -280,10 +280,11 @@ class EgoGraph(object):
 class Graph(object):
     """Connection to a service front end (Graph.java / impl/GraphImpl.java)."""
 
-    def __init__(self, server_addr: str, timeout: float = 30.0, workers: int = 4):
+    def __init__(self, server_addr: str, timeout: float = 30.0, workers: int = 4, admin_token: str = ""):
         if "://" not in server_addr:
             server_addr = "http://" + server_addr
         self._base, self._timeout = server_addr.rstrip("/"), timeout
+        self._token = admin_token          # sent as ``Authorization: Bearer`` on admin calls when the service asks for one
         self._schema: Optional[dict] = None
         self._pool = ThreadPoolExecutor(max_workers=workers)
         self._query: Optional[Query] = None
@@ -296,7 +297,10 @@ class Graph(object):
     def _http(self, method: str, path: str, body: Optional[dict] = None, **params) -> dict:
         url = self._base + path + (("?" + urllib.parse.urlencode(params)) if params else "")
         data = json.dumps(body).encode() if body is not None else (b"" if method == "POST" else None)
-        req = urllib.request.Request(url, data=data, method=method, headers={"Content-Type": "application/json"})
+        headers = {"Content-Type": "application/json"}
+        if self._token and path.startswith("/admin/"):
+            headers["Authorization"] = "Bearer " + self._token
+        req = urllib.request.Request(url, data=data, method=method, headers=headers)
         try:
             with urllib.request.urlopen(req, timeout=self._timeout) as r:
                 return json.loads(r.read() or b"{}")

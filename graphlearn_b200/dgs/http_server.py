@@ -39,8 +39,12 @@ def _jsonable(x):
 
 
 class HttpFrontEnd(object):
-    def __init__(self, service, schema=None, checkpoint_dir: str = "", host: str = "127.0.0.1", port: int = 0):
+    def __init__(self, service, schema=None, checkpoint_dir: str = "", host: str = "127.0.0.1", port: int = 0,
+                 admin_token: str = ""):
+        """``admin_token``: when set, every POST /admin/* call must carry ``Authorization: Bearer <token>`` (the admin surface
+        installs queries, ingests records and reads server-side files; ``/infer`` and the read-only GETs stay open)."""
         self.service, self.schema = service, schema
+        self.admin_token = admin_token or ""
         self.ckpt = CheckpointManager(service, checkpoint_dir) if checkpoint_dir else None
         self.barriers = BarrierMonitor(service)
         self._lock = threading.Lock()
@@ -92,6 +96,13 @@ class HttpFrontEnd(object):
             def do_POST(self):
                 u = urlparse(self.path)
                 q = parse_qs(u.query)
+                if front.admin_token and u.path.startswith("/admin/"):
+                    import hmac
+                    got = self.headers.get("Authorization", "")
+                    if not hmac.compare_digest(got, "Bearer " + front.admin_token):
+                        self._body()
+                        self._send(401, {"error": "admin token required"})
+                        return
                 try:
                     if u.path == "/admin/init":
                         d = self._body()

@@ -537,3 +537,37 @@ def test_native_record_parser_matches_python_loader(tmp_path):
     (tmp_path / "bad").write_text("u2i,1,x,3,0.5\n")
     with pytest.raises(RuntimeError):
         FileLoader(str(tmp_path / "pattern"), schema, native=True).load(str(tmp_path / "bad"), ref)
+
+
+def test_admin_token_and_service_side_load(tmp_path):
+    """POST /admin/* needs the bearer token when the front end has one; /infer and read-only GETs stay open; the client sends
+    the token; /admin/load bulk-loads a server-side record file; client.ingest / set_barrier round trip."""
+    from graphlearn_b200.dgs import HttpFrontEnd, Schema
+    from graphlearn_b200.dgs import client as C
+    schema = Schema({"attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}],
+                     "vertex_defs": [{"vtype": 0, "name": "u", "attr_types": [0]}, {"vtype": 1, "name": "i", "attr_types": [0]}],
+                     "edge_defs": [{"etype": 2, "name": "e", "attr_types": [0]}],
+                     "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}]})
+    svc = DynamicGraphService(schema.to_service_schema(capacity=16), device="cpu")
+    front = HttpFrontEnd(svc, schema, admin_token="s3cret").start()
+    try:
+        anon = C.Graph.connect("127.0.0.1:%d" % front.port)
+        q = anon.V("u").feed(C.DataSource([1])).outV("e").sample(2).by("topk_by_timestamp").alias("h").values()
+        st = anon.install(q)
+        assert not st.ok() and "401" in st.message
+        with pytest.raises(C.UserException):
+            anon.ingest({"edges": {"e": {"src": [1], "dst": [2], "ts": [3]}}})
+        assert anon.stats()["ingested"] == 0                             # open read-only surface
+        g = C.Graph.connect("127.0.0.1:%d" % front.port, admin_token="s3cret")
+        assert g.install(q).ok()
+        (tmp_path / "pattern").write_text("#EDGE:e,src,dst,timestamp\n")
+        (tmp_path / "data").write_text("e,1,5,10\ne,1,6,11\ne,1,7,12\n")
+        assert g.load_file(str(tmp_path / "pattern"), str(tmp_path / "data")) == 3
+        assert g.ingest({"edges": {"e": {"src": np.array([1]), "dst": np.array([9]), "ts": np.array([13])}}}) == 4
+        g.set_barrier("b")
+        assert g.check_barrier("b").ok()
+        g.set_barrier("later", after_records=100)
+        assert not anon.check_barrier("later").ok()
+        assert anon.run(q)["h"]["ids"].tolist() == [[9, 7]]              # inference needs no token
+    finally:
+        front.stop()
