@@ -25,10 +25,34 @@ def _scratch_cwd():
     return d
 
 
+def _ensure_installed(rank: int) -> bool:
+    """baseline/_ref is git-ignored: when the working tree was re-created from the repository it is gone.  The wheel of the
+    UNMODIFIED reference that baseline/build_reference.sh produced is kept under baseline/dist/ - install it (offline, no
+    dependencies, a few seconds) so that the reference arm survives; other ranks wait for rank 0."""
+    marker = os.path.join(REF, "graphlearn", "__init__.py")
+    if os.path.exists(marker):
+        return True
+    import glob
+    wheels = sorted(glob.glob(os.path.join(HERE, "dist", "graph_learn-*.whl")))
+    if not wheels:
+        return False
+    if int(os.environ.get("LOCAL_RANK", rank)) == 0:
+        import subprocess
+        tmp = REF + ".installing"
+        subprocess.run([sys.executable, "-m", "pip", "install", "--no-index", "--no-deps", "--quiet", "--target", tmp, wheels[-1]],
+                       check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if os.path.exists(os.path.join(tmp, "graphlearn", "__init__.py")) and not os.path.exists(REF):
+            os.replace(tmp, REF)                      # publish atomically: waiting ranks never see a half-installed tree
+    t0 = time.time()
+    while not os.path.exists(marker) and time.time() - t0 < 300:
+        time.sleep(0.5)
+    return os.path.exists(marker)
+
+
 def main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not os.path.isdir(os.path.join(REF, "graphlearn")):
+    if not _ensure_installed(rank):
         if rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed (see DESIGN.md)"}))
         return
