@@ -571,3 +571,71 @@ def test_admin_token_and_service_side_load(tmp_path):
         assert anon.run(q)["h"]["ids"].tolist() == [[9, 7]]              # inference needs no token
     finally:
         front.stop()
+
+
+def test_native_record_parser_fuzz_matches_python(tmp_path):
+    """Randomised record files (signed / huge ids, '+' prefixes, exponent and bare-dot floats, empty list tokens, junk and
+    short lines, CRLF or LF, with / without a final newline, batch sizes 1 / 3 / 1000): the native parser and the Python
+    loader must produce identical batches - or fail alike."""
+    import random
+    from graphlearn_b200.dgs import FileLoader, Schema
+    schema = Schema({
+        "attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}, {"type": 1, "name": "weight", "value_type": "FLOAT32"},
+                      {"type": 2, "name": "feature", "value_type": "FLOAT32_LIST"}, {"type": 3, "name": "age", "value_type": "FLOAT32"}],
+        "vertex_defs": [{"vtype": 0, "name": "user", "attr_types": [0, 3, 2]}, {"vtype": 1, "name": "item", "attr_types": [0, 2]}],
+        "edge_defs": [{"etype": 2, "name": "u2i", "attr_types": [0, 1]}, {"etype": 4, "name": "i2i", "attr_types": [0]}],
+        "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}, {"etype": 4, "src_vtype": 1, "dst_vtype": 1}]})
+
+    class Rec(object):
+        def __init__(self):
+            self.b = []
+
+        def apply_updates(self, batch):
+            self.b.append(batch)
+
+    def flat(batches):
+        out = {}
+        for b in batches:
+            for k, e in b["edges"].items():
+                for s, d_, t, w in zip(e["src"], e["dst"], e["ts"], e["weight"]):
+                    out.setdefault(("E", k), []).append((int(s), int(d_), int(t), round(float(w), 5)))
+            for k, v in b["vertices"].items():
+                for i, t, f in zip(v["id"], v["ts"], v["feat"]):
+                    out.setdefault(("V", k), []).append((int(i), int(t), tuple(round(float(x), 4) for x in f)))
+        return out
+    d = str(tmp_path)
+    with open(d + "/pattern", "w") as f:
+        f.write("#VERTEX:user,vid,timestamp,feature,age\n#VERTEX:item,vid,feature,timestamp\n#EDGE:u2i,src,dst,timestamp,weight\n#EDGE:i2i,src,dst,timestamp\n")
+    for seed in range(80):
+        rs = random.Random(seed)
+        num = lambda: rs.choice(["%d" % rs.randint(-5, 50), "+%d" % rs.randint(0, 9), "%d" % rs.randint(0, 10 ** 12)])  # noqa: E731
+        fl = lambda: rs.choice(["%.3f" % rs.uniform(-2, 2), "1e-3", "+0.5", "%d" % rs.randint(0, 9), ".5", "5."])  # noqa: E731
+        lines = []
+        for _ in range(rs.randint(0, 60)):
+            r = rs.randint(0, 7)
+            if r == 0:
+                lines.append("user,%s,%s,%s:%s:%s,%s" % (num(), num(), fl(), fl(), fl(), fl()))
+            elif r == 1:
+                lines.append("item,%s,%s:%s,%s" % (num(), fl(), fl(), num()))
+            elif r in (2, 3):
+                lines.append("u2i,%s,%s,%s,%s" % (num(), num(), num(), fl()))
+            elif r == 4:
+                lines.append("i2i,%s,%s,%s" % (num(), num(), num()))
+            elif r == 5:
+                lines.append(rs.choice(["", "junk", "u2i,1", "item,1,2,3,4,5", ",,,", "user", " "]))
+            elif r == 6:
+                lines.append("item,%s,%s::%s,%s" % (num(), fl(), fl(), num()))
+            else:
+                lines.append("u2i,%s,%s,%s,%s " % (num(), num(), num(), fl()))
+        eol = rs.choice(["\n", "\r\n"])
+        with open(d + "/data", "wb") as f:
+            f.write((eol.join(lines) + (eol if rs.random() < 0.5 else "")).encode())
+        res = []
+        for native in (False, True):
+            rec = Rec()
+            try:
+                n = FileLoader(d + "/pattern", schema, batch_size=rs.choice([1, 3, 1000]), native=native).load(d + "/data", rec)
+                res.append((n, flat(rec.b)))
+            except Exception as e:  # noqa: BLE001
+                res.append(("ERR", type(e).__name__ in ("ValueError", "RuntimeError")))
+        assert res[0] == res[1], (seed, lines)
