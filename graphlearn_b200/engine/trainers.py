@@ -59,6 +59,12 @@ class _ExampleTrainer(object):
         return min(rt.all_gather_object(int(n)))
 
     def _build(self, dataset, model, step_fn, optimizer, learning_rate):
+        tr = self._trainer
+        if tr is not None and tr.model is model and tr.dataset is dataset and optimizer is None and tr._flat_opt:
+            tr.step_fn = step_fn                      # another train() call on the same job: keep parameters AND Adam moments
+            if learning_rate is not None:
+                tr.opt.lr = learning_rate
+            return tr
         rt = self._runtime()
         if self.ckpt_dir:
             os.makedirs(self.ckpt_dir, exist_ok=True)
@@ -172,3 +178,65 @@ class DistTrainer(_ExampleTrainer):
     def join(self):
         """block until every worker has finished training (call after ``train``)"""
         self.sync_barrier.end()
+
+
+class LinkDistTrainer(DistTrainer):
+    """Link-prediction driver of the reference's SEAL / ogbl-collab examples (examples/tf/link_trainer.py:38-176): trains on a
+    positive/negative edge stream, evaluates Hits@K on held-out positive and negative edges after every epoch, writes scored
+    edges with ``predict``."""
+
+    def eval(self, dataset, model, score_fn: Callable):
+        """all scores ``score_fn(model, batch) -> [n]`` of one pass over ``dataset`` (numpy)"""
+        import numpy as np
+        from .. import errors as _errors
+        model.eval()
+        outs = []
+        with torch.no_grad():
+            while True:
+                try:
+                    batch = dataset.next()
+                except _errors.OutOfRangeError:
+                    break
+                outs.append(score_fn(model, batch).detach().float().reshape(-1).cpu().numpy())
+        model.train()
+        return np.concatenate(outs) if outs else np.zeros(0, dtype=np.float32)
+
+    @staticmethod
+    def eval_hits(y_pred_pos, y_pred_neg, k: int) -> dict:
+        from ..utils.metrics import hits_at_k
+        return {"hits@{}".format(k): hits_at_k(y_pred_pos, y_pred_neg, k)}
+
+    def train_and_eval(self, train_dataset, model, step_fn: Callable, test_dataset, test_neg_dataset, score_fn: Callable,
+                       learning_rate: float = 1e-2, epochs: int = 10, hit_K: int = 50, optimizer=None):
+        """-> list of per-epoch {"loss", "hits@K"}; ``step_fn(model, batch) -> loss`` consumes whatever ``train_dataset``
+        yields (positive + negative edges of one query, or a pair zipped by the caller)"""
+        history = []
+        for epoch in range(epochs):
+            loss = self.train(train_dataset, model, step_fn, optimizer=optimizer, learning_rate=learning_rate, epochs=1)
+            pos = self.eval(test_dataset, model, score_fn)
+            neg = self.eval(test_neg_dataset, model, score_fn)
+            rec = {"loss": loss, **self.eval_hits(pos, neg, hit_K)}
+            log.info("Epoch %d: loss %.5f  Test hits@%d: %.4f", epoch, loss, hit_K, rec["hits@{}".format(hit_K)])
+            history.append(rec)
+        self.join()
+        return history
+
+    def predict(self, dataset, model, edge_score_fn: Callable, path: str) -> int:
+        """``edge_score_fn(model, batch) -> (src_ids, dst_ids, scores)``; rows ``src \t dst \t score`` in ``<path>.rank<r>``"""
+        from .. import errors as _errors
+        rt = self._runtime()
+        n = 0
+        model.eval()
+        with open("%s.rank%d" % (path, rt.rank), "w") as f, torch.no_grad():
+            f.write("src_id:int64\tdst_id:int64\tscore:float\n")
+            while True:
+                try:
+                    batch = dataset.next()
+                except _errors.OutOfRangeError:
+                    break
+                s, d, sc = edge_score_fn(model, batch)
+                for a, b, c in zip(s.reshape(-1).tolist(), d.reshape(-1).tolist(), sc.reshape(-1).tolist()):
+                    f.write("%d\t%d\t%.6f\n" % (a, b, c))
+                    n += 1
+        model.train()
+        return n

@@ -31,9 +31,30 @@ class Dataset(object):
         res = self._ds.next()
         return {k: Data.from_values(v) for k, v in res.items() if hasattr(v, "_t")}
 
-    def get_egograph(self, source: str, neighbors: Sequence[str], nbr_nums: Optional[Sequence[int]] = None,
+    def _default_neighbors(self, source: str) -> List[str]:
+        """hop aliases below ``source`` when every hop has exactly ONE positive downstream (the reference's
+        ``get_egograph(source, neighbors=None)``, nn/tf/data/dataset.py:95-150); edge hops (outE) are skipped - their vertex
+        ends (inV / outV) are the neighbours"""
+        from ..gsl.dag_node import TraverseEdgeDagNode
+        pre = self._query.get_node(source)
+        out: List[str] = []
+        recepts = pre.pos_downstreams
+        while recepts:
+            if len(recepts) > 1:
+                raise ValueError("Can't automatically find neighbors for {}, which has multiple downstreams. You should assign "
+                                 "specific neighbors for {}.".format(pre.get_alias(), source))
+            cur = recepts[0]
+            if not isinstance(cur, TraverseEdgeDagNode):
+                out.append(cur.get_alias())
+            pre, recepts = cur, cur.pos_downstreams
+        return out
+
+    def get_egograph(self, source: str, neighbors: Optional[Sequence[str]] = None, nbr_nums: Optional[Sequence[int]] = None,
                      res=None) -> EgoGraph:
-        """EgoGraph rooted at alias `source` with hop aliases `neighbors` (in hop order)."""
+        """EgoGraph rooted at alias `source` with hop aliases `neighbors` (in hop order; None = follow the single positive
+        downstream chain of `source` in the query)."""
+        if neighbors is None:
+            neighbors = self._default_neighbors(source)
         res = res if res is not None else self._ds.next()
         src = Data.from_values(res[source])
         hops = [Data.from_values(res[a]) for a in neighbors]

@@ -4,6 +4,7 @@
   batch like eval_rec_metric.py:23-55 (divide by the number of triggers at the end);
 * ``recall_metrics_at_k``               the same three metrics for a whole evaluation set in one vectorised call (device tensors);
 * ``evaluate_recall``                   embeddings -> KNN recall (``Graph.search`` / ``ops.knn``) -> metrics, the test_rec.py flow;
+* ``hits_at_k``                         OGB link-prediction Hits@K (link_trainer.py ``eval_hits``);
 * ``multilabel_f1``                     micro / macro F1 of a one-vs-rest logistic regression on frozen embeddings with the
   "predict as many labels as the node has" protocol (blogcatelog_eval.py:41-104; needs scikit-learn).
 """
@@ -54,6 +55,17 @@ def evaluate_recall(graph, item_type: str, query_vectors, gt_items: Sequence[Seq
     r, n, h = eval_metrics(gt_items, ids)
     m = max(len(gt_items), 1)
     return {"recall": r / m, "ndcg": n / m, "hit_rate": h / m, "k": top_k}
+
+
+def hits_at_k(y_pred_pos, y_pred_neg, k: int) -> float:
+    """OGB-style Hits@K (examples/tf/link_trainer.py:162-173): the share of positive scores that beat the k-th best negative
+    score; 1.0 when there are fewer than k negatives or no positives."""
+    pos = np.asarray(y_pred_pos, dtype=np.float64).reshape(-1)
+    neg = np.asarray(y_pred_neg, dtype=np.float64).reshape(-1)
+    if neg.size < k or pos.size == 0:
+        return 1.0
+    kth = np.sort(neg)[-k]
+    return float((pos > kth).sum()) / pos.size
 
 
 def multilabel_f1(embeddings: np.ndarray, labels: np.ndarray, train_ratios: Sequence[float] = (0.5, 0.9), shuffles: int = 2,

@@ -123,3 +123,31 @@ def test_u2i_online_pipeline_service_process_and_client():
     EgoGraph hop tensors - the served neighbourhoods must carry enough signal to recover every user's preferred category."""
     acc, n, served = _run("u2i_online_pipeline", ["--epochs", "6"])
     assert n == 67 and served == 67 and acc > 0.85
+
+
+def test_ego_data_loaders(tmp_path):
+    """examples/ego_data_loader.py: the reference's supervised / unsupervised EgoSAGE loaders - one epoch per iteration, ego
+    graphs by alias with the hop chain read off the query."""
+    if EX not in sys.path:
+        sys.path.insert(0, EX)
+    import graphlearn_b200 as gl
+    from common import write_citation_like
+    from ego_data_loader import EgoSAGESupervisedDataLoader, EgoSAGEUnsupervisedDataLoader
+    node_f, edge_f, dim, classes = write_citation_like(str(tmp_path), n=300)
+    g = gl.Graph().node(node_f, "i", decoder=gl.Decoder(labeled=True, attr_types=["float"] * dim)) \
+        .edge(edge_f, ("i", "i", "e"), decoder=gl.Decoder(weighted=True)).init(device="cpu")
+    sup = EgoSAGESupervisedDataLoader(g, gl.Mask.NONE, "random", batch_size=64, node_type="i", edge_type="e", nbrs_num=[4, 3])
+    for epoch in range(2):
+        seen = 0
+        for ego in sup:
+            assert ego.nbr_nums == [4, 3] and ego.hop_node(1).floats.shape == (ego.src.ids.numel() * 12, dim)
+            assert ego.src.labels.shape == ego.src.ids.shape
+            seen += ego.src.ids.numel()
+        assert seen == 300
+    uns = EgoSAGEUnsupervisedDataLoader(g, gl.Mask.NONE, "random", "random", batch_size=32, node_type="i", edge_type="e", nbrs_num=[3], neg_num=2)
+    uns.next()
+    s, d, n = uns.src_ego, uns.dst_ego, uns.neg_dst_ego
+    assert s.src.ids.shape == d.src.ids.shape == (32,) and n.src.ids.numel() == 64
+    assert s.nbr_nums == d.nbr_nums == n.nbr_nums == [3] and n.hop_node(0).ids.numel() == 64 * 3
+    assert uns["src"].floats.shape == (32, dim) and set(uns.data_dict) >= {"src", "dst", "neg_dst"}
+    g.close()

@@ -128,6 +128,17 @@ def test_nn_dataset_egograph(tmp_path):
     m = models.EgoGraphSAGE(4, 8, 3, 2, bf16_activations=False)
     out = m([h.floats for h in ego.hops()], ego.nbr_nums)
     assert out.shape == (5, 3)
+    # neighbors=None: the hop chain is read off the query (single positive downstream per hop); edge hops are skipped
+    auto = glnn.Dataset(q).get_egograph("s")
+    assert auto.nbr_nums == [2, 2] and auto.hop_node(1).floats.shape == (20, 4)
+    src = g.V("item").batch(5).alias("r")
+    src.outE("sim").sample(2).by("topk").alias("e1").inV().alias("n1")
+    assert glnn.Dataset(src.values()).get_egograph("r").nbr_nums == [2]
+    fork = g.V("item").batch(5).alias("f")
+    fork.outV("sim").sample(2).by("topk").alias("a")
+    fork.outV("sim").sample(3).by("random").alias("b")
+    with pytest.raises(ValueError):
+        glnn.Dataset(fork.values()).get_egograph("f")
 
 
 def test_checkpoint_resume_is_deterministic(tmp_path):
@@ -587,3 +598,56 @@ def test_local_and_dist_trainer_reference_surface(tmp_path):
     assert dt.is_chief and dt.worker_count == 1 and not dt.is_local
     dt.train(make_ds(), model, step, learning_rate=1e-2, epochs=1)
     dt.join()
+
+
+def test_link_dist_trainer_hits_and_predict(tmp_path):
+    """engine/trainers.LinkDistTrainer (examples/tf/link_trainer.py): dot-product link model on the user-item fixture - trained
+    on positive edges + sampled negatives, Hits@K on held-out positive / negative streams rises above the untrained model,
+    predict writes scored edges; hits_at_k matches its definition on a hand example."""
+    from graphlearn_b200.engine.trainers import LinkDistTrainer
+    from graphlearn_b200.utils.metrics import hits_at_k
+    assert hits_at_k([0.9, 0.2, 0.5], [0.1, 0.3, 0.6, 0.4], 2) == pytest.approx(2 / 3)      # 2nd best negative = 0.4
+    assert hits_at_k([0.9], [0.1], 5) == 1.0 and hits_at_k([], [0.1, 0.2], 1) == 1.0
+    g = fx.build_graph(fx.write_graph(str(tmp_path / "g")))
+    torch.manual_seed(0)
+
+    class Dot(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.u = torch.nn.Embedding(fx.N_USER, 8)
+            self.i = torch.nn.Embedding(fx.N_ITEM, 8)
+
+        def score(self, u, i):
+            return (self.u(u) * self.i(i)).sum(-1)
+    model = Dot()
+
+    def train_ds():
+        return gl.Dataset(g.E("buy").batch(16).shuffle(traverse=True).alias("pos").outV().alias("u").outNeg("buy").sample(4).by("random").alias("neg").values())
+
+    def pos_ds():
+        return gl.Dataset(g.E("buy").batch(32).alias("pos").values())
+
+    def neg_ds():
+        return gl.Dataset(g.V("user").batch(16).alias("u").outNeg("buy").sample(3).by("random").alias("neg").values())
+
+    def step(m, b):
+        e = b["pos"]
+        u, i = e.tensor("src_ids"), e.tensor("dst_ids")
+        neg = b["neg"].tensor("ids")
+        pos_s = m.score(u, i)
+        neg_s = m.score(u[:, None].expand_as(neg), neg)
+        return F.softplus(-pos_s).mean() + F.softplus(neg_s).mean()
+
+    def score(m, b):
+        if "pos" in b:
+            return m.score(b["pos"].tensor("src_ids"), b["pos"].tensor("dst_ids"))
+        neg = b["neg"].tensor("ids")
+        return m.score(b["u"].tensor("ids")[:, None].expand_as(neg), neg)
+    tr = LinkDistTrainer(progress_steps=10000)
+    before = tr.eval_hits(tr.eval(pos_ds(), model, score), tr.eval(neg_ds(), model, score), 10)["hits@10"]
+    hist = tr.train_and_eval(train_ds(), model, step, pos_ds(), neg_ds(), score, learning_rate=5e-2, epochs=6, hit_K=10)
+    assert len(hist) == 6 and hist[-1]["loss"] < hist[0]["loss"] and hist[-1]["hits@10"] > before + 0.15
+    n = tr.predict(pos_ds(), model, lambda m, b: (b["pos"].tensor("src_ids"), b["pos"].tensor("dst_ids"),
+                                                   m.score(b["pos"].tensor("src_ids"), b["pos"].tensor("dst_ids"))), str(tmp_path / "pred"))
+    lines = open(str(tmp_path / "pred") + ".rank0").read().strip().split("\n")
+    assert n == len(lines) - 1 == g.get_stats()["buy"][0] and lines[0].startswith("src_id:int64")
