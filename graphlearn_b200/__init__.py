@@ -30,6 +30,7 @@ from .sampler.neighbor_sampler import (EdgeWeightNeighborSampler, FullNeighborSa
 from .sampler.edge_sampler import ByOrderEdgeSampler, EdgeSampler, RandomEdgeSampler, ShuffleEdgeSampler  # noqa: F401
 from .sampler.node_sampler import ByOrderNodeSampler, NodeSampler, RandomNodeSampler, ShuffleNodeSampler  # noqa: F401
 from .sampler.subgraph_sampler import SubGraphSampler  # noqa: F401
+from .ops.sampling import LocalAdjacency, register_sampler, registered_samplers, unregister_sampler  # noqa: F401
 from .utils import deprecated  # noqa: F401
 from .store.graph_store import Topology  # noqa: F401
 from .utils import Mask, get_mask_type, strategy2op  # noqa: F401

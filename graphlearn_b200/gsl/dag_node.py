@@ -99,6 +99,9 @@ class DagNode(object):
     def by(self, strategy):
         neg = bool(self._params.get("negative"))
         allowed = NEGATIVE_STRATEGIES if neg else NEIGHBOR_STRATEGIES
+        if not neg:
+            from ..ops.sampling import registered_samplers
+            allowed = tuple(allowed) + tuple(registered_samplers())            # gl.register_sampler
         if strategy not in allowed:
             raise ValueError("strategy must be one of {}, got {!r}".format(allowed, strategy))
         self._params["strategy"] = strategy

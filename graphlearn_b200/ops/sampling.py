@@ -157,6 +157,83 @@ def _local_sample_idfilter(csr, vids, k, strategy, fvals, circular, default_id, 
     return nbr.to(vids.device), eid
 
 
+# ---------------------------------------------------------------------- user-defined samplers
+# The reference lets users add operators in C++: subclass Operator / Sampler, implement the LOCAL ``Process`` and
+# ``REGISTER_OPERATOR("xxxSampler", ...)``; the framework partitions the request over the servers and stitches the answers
+# (docs/en/gl/developer/operator.md, src/core/operator/operator.h, op_registry).  The same contract here: register the local
+# rule, ``g.V(..).outV(e).sample(k).by("xxx")`` / ``g.neighbor_sampler(e, k, strategy="xxx")`` run it on the owner of every
+# source row (Partition -> all-to-all -> local rule -> Stitch on multi-rank jobs).
+_CUSTOM_SAMPLERS = {}
+
+
+class LocalAdjacency(object):
+    """What a custom sampling rule sees: this rank's CSR shard.  Row r holds positions ``indptr[r] .. indptr[r + 1] - 1`` of
+    ``indices`` (destination ids in the engine's virtual-id space), ``weights`` / ``timestamps`` (or None); rows are ordered by
+    weight descending, or by timestamp ascending for timestamped edge types."""
+
+    def __init__(self, csr: CsrShard):
+        self.edge_type, self.num_rows, self.num_edges = csr.type, csr.n_src_rows, csr.n_edges
+        self.indptr, self.indices = csr.indptr.local, csr.indices.local
+        self.weights = csr.weights.local if csr.weights is not None else None
+        self.timestamps = csr.ts.local if csr.ts is not None else None
+
+    def degrees(self, rows: torch.Tensor) -> torch.Tensor:
+        return self.indptr[rows + 1] - self.indptr[rows]
+
+
+def register_sampler(name: str, fn, overwrite: bool = False):
+    """Register a neighbour-sampling strategy ``name``.
+
+    ``fn(adj: LocalAdjacency, rows: int64 [n], k: int, generator: torch.Generator | None) -> int64 [n, k]`` returns, for every
+    local source row, k POSITIONS into ``adj.indices`` taken from that row's range (``-1`` = no neighbour: the slot gets the
+    default neighbour id).  Positions outside the row are treated as -1, so a rule can never fabricate an edge."""
+    if not callable(fn):
+        raise ValueError("fn must be callable")
+    if name in STRATEGY or name == "full":
+        raise ValueError("%r is a built-in strategy" % (name,))
+    if name in _CUSTOM_SAMPLERS and not overwrite:
+        raise ValueError("sampler %r is already registered" % (name,))
+    _CUSTOM_SAMPLERS[name] = fn
+    return fn
+
+
+def unregister_sampler(name: str):
+    _CUSTOM_SAMPLERS.pop(name, None)
+
+
+def registered_samplers():
+    return sorted(_CUSTOM_SAMPLERS)
+
+
+def _custom_sample(csr: CsrShard, src: torch.Tensor, k: int, strategy: str, gen, default_id: int):
+    fn = _CUSTOM_SAMPLERS[strategy]
+    W = csr.rt.world
+    adj = LocalAdjacency(csr)
+
+    def run(v):
+        rows = torch.div(v, W, rounding_mode="floor")
+        ok = (v >= 0) & (rows < csr.n_src_rows)
+        rows = torch.where(ok, rows, torch.zeros_like(rows))
+        n = int(v.numel())
+        if n == 0 or csr.n_src_rows == 0:
+            return (torch.full((n, k), default_id, dtype=torch.int64, device=v.device),
+                    torch.full((n, k), -1, dtype=torch.int64, device=v.device))
+        pos = torch.as_tensor(fn(adj, rows, int(k), gen)).to(torch.int64).to(v.device)
+        if tuple(pos.shape) != (n, k):
+            raise ValueError("sampler %r returned shape %s, expected %s" % (strategy, tuple(pos.shape), (n, k)))
+        beg, end = adj.indptr[rows], adj.indptr[rows + 1]
+        valid = ok[:, None] & (pos >= beg[:, None]) & (pos < end[:, None])
+        p = pos.clamp(min=0, max=max(csr.n_edges - 1, 0))
+        if csr.n_edges == 0:
+            valid = torch.zeros_like(valid)
+            nbr_raw = torch.zeros_like(p)
+            eid_raw = torch.zeros_like(p)
+        else:
+            nbr_raw, eid_raw = adj.indices[p], _eid_of(csr, p)
+        return (torch.where(valid, nbr_raw, torch.full_like(p, default_id)), torch.where(valid, eid_raw, torch.full_like(p, -1)))
+    return part.remote_apply(src, run, W, ())
+
+
 def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: str = "random",
                      filter_mode: int = FILTER_NONE, filter_values: Optional[torch.Tensor] = None,
                      want_eids: bool = True, rng: Optional["_rng.DeviceRng"] = None, salt: int = 0,
@@ -168,10 +245,18 @@ def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: st
     circular = (cfg.padding_mode == _config.PADDING_CIRCULAR) if padding_circular is None else padding_circular
     if strategy == "full":
         raise ValueError("use sample_full for the 'full' strategy")
-    if strategy not in STRATEGY:
-        raise ValueError("unknown sampling strategy %r" % (strategy,))
     src = src_vids.reshape(-1).to(torch.int64)
     rng = rng or _rng.default_rng(csr.rt)
+    if strategy in _CUSTOM_SAMPLERS:
+        if filter_mode != FILTER_NONE:
+            raise ValueError("filters are not available for user-defined samplers (filter inside the rule)")
+        nbr, eid = _custom_sample(csr, src, int(k), strategy, rng.torch_generator(salt), int(cfg.default_neighbor_id))
+        if out is not None:
+            out.view(-1).copy_(nbr.reshape(-1))
+        return nbr, (eid if want_eids else None)
+    if strategy not in STRATEGY:
+        raise ValueError("unknown sampling strategy %r (built-in: %s; registered: %s)" % (strategy, ", ".join(STRATEGY),
+                                                                                          ", ".join(registered_samplers()) or "-"))
     if csr.rt.is_cuda and cfg.use_peer_kernels:
         desc = csr.desc_indeg if strategy == "in_degree" else csr.desc
         if strategy == "in_degree" and desc is None:

@@ -47,6 +47,19 @@ def main():
         dd = (n2 - n1.reshape(-1)[:, None]) % fx.N_ITEM
         assert ((dd >= 1) & (dd <= 3)).all()
     assert g.out_degrees(ids, "buy").tolist() == [len(adj[u]) for u in ids]
+    # a user-defined sampler (gl.register_sampler): the local rule runs on the OWNER of every source row, the framework
+    # partitions the request and stitches the answers (seeds of all ranks' users asked from every rank)
+
+    def lightest(adj_, rows, k, gen):
+        end = adj_.indptr[rows + 1]
+        pos = end[:, None] - 1 - torch.arange(k, device=rows.device)[None, :]
+        return torch.where(pos >= adj_.indptr[rows][:, None], pos, torch.full_like(pos, -1))
+    gl.register_sampler("lightest", lightest, overwrite=True)
+    light = g.neighbor_sampler("buy", 2, strategy="lightest").get(ids).layer_nodes(1).ids
+    for u in ids:
+        by_w = sorted(adj[u], key=lambda tw: tw[1])
+        pad = gl.get_config().default_neighbor_id
+        assert light[u].tolist() == [t for t, _ in by_w[:2]] + [pad] * (2 - min(2, len(by_w))), (u, light[u])
     exp = np.zeros(fx.N_ITEM, int)
     for u in adj:
         for i, _ in adj[u]:

@@ -674,3 +674,46 @@ def test_graph_deploy_modes_reverse_edges_and_attribute_selection(tmp_path):
     # both directions of every edge are stored once add_reverse_edges ran
     assert g.get_stats()["sim"][0] == 2 * sum(1 for _ in open(os.path.join(d, "i2i.tsv"))) - 2
     g.close()
+
+
+def test_user_defined_sampler(tmp_path):
+    """gl.register_sampler (the reference's REGISTER_OPERATOR + .by("xxx"), docs/en/gl/developer/operator.md): a local rule
+    returning positions into the shard's CSR is usable from GSL and from the imperative sampler; slots the rule leaves empty
+    or points outside the row get the default neighbour id; built-in names cannot be overridden."""
+    import torch
+    g = fx.build_graph(fx.write_graph(str(tmp_path)))
+
+    def lightest(adj, rows, k, gen):
+        # rows are weight-descending: the LAST k positions of a row are its lightest edges (none left: -1)
+        end = adj.indptr[rows + 1]
+        pos = end[:, None] - 1 - torch.arange(k, device=rows.device)[None, :]
+        return torch.where(pos >= adj.indptr[rows][:, None], pos, torch.full_like(pos, -1))
+    gl.register_sampler("lightest", lightest)
+    try:
+        assert "lightest" in gl.registered_samplers()
+        with pytest.raises(ValueError):
+            gl.register_sampler("lightest", lightest)
+        with pytest.raises(ValueError):
+            gl.register_sampler("topk", lightest)
+        gl.set_default_neighbor_id(-7)
+        users = np.array([1, 2, 6])
+        nb = g.neighbor_sampler("buy", expand_factor=3, strategy="lightest").get(users).layer_nodes(1)
+        adj = fx.u2i_adj()
+        for u, row, er in zip(users.tolist(), nb.ids.tolist(), g.neighbor_sampler("buy", 3, strategy="lightest").get(users).layer_edges(1).weights.tolist()):
+            by_w = sorted(adj[u], key=lambda tw: tw[1])                # (item, weight) ascending weight
+            want = [t for t, _ in by_w[:3]] + [-7] * (3 - min(3, len(by_w)))
+            assert row == want, (u, row, want)
+        q = g.V("user").batch(4).alias("u").outV("buy").sample(2).by("lightest").alias("i").values()
+        res = gl.Dataset(q).next()
+        for u, row in zip(res["u"].ids.tolist(), res["i"].ids.tolist()):
+            by_w = sorted(adj[u], key=lambda tw: tw[1])
+            assert row == ([t for t, _ in by_w[:2]] + [-7] * (2 - min(2, len(by_w))))
+        # a rule that points outside its rows cannot fabricate edges
+        gl.register_sampler("rogue", lambda adj, rows, k, gen: torch.zeros(rows.numel(), k, dtype=torch.int64) + 10 ** 6)
+        assert (g.neighbor_sampler("buy", 2, strategy="rogue").get(users).layer_nodes(1).ids == -7).all()
+        with pytest.raises(ValueError):
+            g.V("user").batch(2).outV("buy").sample(2).by("nobody")
+    finally:
+        gl.unregister_sampler("lightest")
+        gl.unregister_sampler("rogue")
+    g.close()
