@@ -32,6 +32,7 @@ from .sampler.node_sampler import ByOrderNodeSampler, NodeSampler, RandomNodeSam
 from .sampler.subgraph_sampler import SubGraphSampler  # noqa: F401
 from .ops.sampling import LocalAdjacency, register_sampler, registered_samplers, unregister_sampler  # noqa: F401
 from .utils import deprecated  # noqa: F401
+from . import io  # noqa: F401  (gl.io.register_file_system, read_table, save_embeddings)
 from .store.graph_store import Topology  # noqa: F401
 from .utils import Mask, get_mask_type, strategy2op  # noqa: F401
 
