@@ -11,6 +11,11 @@ from ..nn.sparse_conv import GATConv, GCNConv, SAGEConv
 _CONV = {"gcn": GCNConv, "sage": SAGEConv, "gat": GATConv}
 
 
+def _nn_conf():
+    from ..nn.utils import conf          # the reference's tfg.conf.training switch
+    return conf
+
+
 class SparseGNN(nn.Module):
     def __init__(self, kind, in_dim, hidden, out_dim, num_layers=2, dropout=0.0, **kw):
         super().__init__()
@@ -23,7 +28,7 @@ class SparseGNN(nn.Module):
             x = conv(x, edge_index)
             if i < len(self.convs) - 1:
                 x = F.relu(x)
-                if self.training and self.dropout:
+                if self.training and self.dropout and _nn_conf().training:
                     x = F.dropout(x, self.dropout)
         return x
 

@@ -18,5 +18,6 @@ from .hetero import (BipartiteSAGEConv, HeteroConv, HeteroSubGraph, LinkPredicto
                      SubGraphProcessor)
 from .sparse_conv import GATConv, GCNConv, SAGEConv, segment_softmax  # noqa: F401
 from .sparse_conv import segment_softmax as unsorted_segment_softmax  # noqa: F401  (nn/tf/utils/softmax.py name)
+from .utils import Config, conf  # noqa: F401  (nn/tf/config.py)
 from .utils import (SyncBarrierHook, bootstrap, get_cluster_spec, get_counts, get_num_client, get_rank, get_world_size,  # noqa: F401
                     is_server_launched, launch_server, set_client_num)

@@ -120,6 +120,23 @@ def is_server_launched() -> bool:
     return SERVER_LAUNCHED
 
 
+class Config(object):
+    """Model-layer switches of the reference (nn/tf/config.py): ``conf.training`` (dropout / attention dropout of the layers that
+    read it - torch modules normally use ``module.train()`` / ``.eval()``, the flag is honoured by ``models.SparseGNN`` and the
+    EgoDataLoader example), the embedding partitioning knobs (kept for scripts; big tables are sharded over GPUs by
+    ``nn.ShardedEmbedding``) and ``emb_live_steps`` (``DynamicEmbedding`` rows never expire here)."""
+
+    def __init__(self):
+        self.training = True
+        self.partitioner = "min_max"
+        self.emb_max_partitions = None
+        self.emb_min_slice_size = 128 * 1024
+        self.emb_live_steps = None
+
+
+conf = Config()
+
+
 def _reset_for_tests():
     global SERVER_LAUNCHED, CLUSTER_SPEC, WORLD_SIZE, RANK, NUM_CLIENT
     SERVER_LAUNCHED, CLUSTER_SPEC, WORLD_SIZE, RANK, NUM_CLIENT = False, None, None, None, None
