@@ -405,3 +405,29 @@ class Graph(object):
 
     def close(self):
         self._pool.shutdown(wait=False)
+
+
+class HttpSink(object):
+    """Sink of a ``GroupProducer`` that talks to a REMOTE service: every flushed record batch becomes one ``/admin/ingest`` call."""
+
+    P = 1
+
+    def __init__(self, graph: Graph):
+        self.graph = graph
+
+    def apply_updates(self, batch: dict):
+        self.graph.ingest(batch)
+
+    def set_barrier(self, name: str):
+        self.graph.set_barrier(name)
+
+
+def data_loader(dgs_host: str, max_batch_size: int = 4096, admin_token: str = ""):
+    """The data-loader SDK entry point (dataloader/dataloader.h ``Initialize(dgs_host)`` + ``GroupProducer``): connects to the
+    service, reads its schema and returns ``(producer, graph)`` - ``producer.add_vertex / add_edge`` batch records per type and
+    flush them to the service when a batch is full, ``producer.flush_all()``, ``producer.set_barrier(producer.sink, name)``
+    marks "everything produced so far", ``graph.check_barrier(name)`` polls it."""
+    from .file_loader import GroupProducer            # numpy-only module
+    g = Graph.connect(dgs_host, admin_token=admin_token)
+    g.get_schema()
+    return GroupProducer(HttpSink(g), max_batch_size=max_batch_size, num_partitions=1), g

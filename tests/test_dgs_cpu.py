@@ -639,3 +639,32 @@ def test_native_record_parser_fuzz_matches_python(tmp_path):
             except Exception as e:  # noqa: BLE001
                 res.append(("ERR", type(e).__name__ in ("ValueError", "RuntimeError")))
         assert res[0] == res[1], (seed, lines)
+
+
+def test_remote_data_loader_sdk():
+    """dgs.client.data_loader (the reference's data-loader SDK: Initialize(dgs_host) + GroupProducer): records added on the client
+    are batched, shipped to the service over HTTP, and become visible to queries once the barrier is READY."""
+    from graphlearn_b200.dgs import HttpFrontEnd, Schema
+    from graphlearn_b200.dgs import client as C
+    schema = Schema({"attr_defs": [{"type": 0, "name": "timestamp", "value_type": "INT64"}, {"type": 1, "name": "f", "value_type": "FLOAT32_LIST"}],
+                     "vertex_defs": [{"vtype": 0, "name": "u", "attr_types": [0, 1]}, {"vtype": 1, "name": "i", "attr_types": [0, 1]}],
+                     "edge_defs": [{"etype": 2, "name": "e", "attr_types": [0]}],
+                     "edge_relation_defs": [{"etype": 2, "src_vtype": 0, "dst_vtype": 1}]})
+    svc = DynamicGraphService(schema.to_service_schema(capacity=16, feat_dims={"u": 2, "i": 2}), device="cpu")
+    front = HttpFrontEnd(svc, schema).start()
+    try:
+        producer, g = C.data_loader("127.0.0.1:%d" % front.port, max_batch_size=5)
+        q = g.V("u").feed(C.DataSource([2])).properties(1).alias("s").outV("e").sample(3).by("topk_by_timestamp").properties(1).alias("h").values()
+        assert g.install(q).ok()
+        producer.add_vertex("u", 2, 1, [0.5, 1.5])
+        for i in range(7):
+            producer.add_vertex("i", i, 1, [float(i), 0.0])
+            producer.add_edge("e", 2, i, 100 + i)
+        assert 0 < svc.ingested < 15 and producer.produced >= 10            # full batches already left the client
+        producer.set_barrier(producer.sink, "all")
+        assert g.check_barrier("all").ok() and svc.ingested == 7            # edges counted by the service (vertices are upserts)
+        v = g.run(q)
+        assert v["h"]["ids"].tolist() == [[6, 5, 4]] and v["h"]["features"][0, 0].tolist() == [6.0, 0.0]
+        assert v["s"]["features"].tolist() == [[0.5, 1.5]]
+    finally:
+        front.stop()
