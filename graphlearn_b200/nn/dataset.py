@@ -14,10 +14,50 @@ from .data import BatchGraph, Data, EgoGraph, TemporalGraph
 
 
 class Dataset(object):
-    def __init__(self, query, window=10, induce_func: Optional[Callable] = None, **kwargs):
+    def __init__(self, query, window=10, induce_func: Optional[Callable] = None, batch_size: int = 1, drop_last: bool = False,
+                 **kwargs):
+        """``batch_size`` / ``drop_last`` only matter for ``get_subgraphs_v2`` (how many SubGraph samples form one batch,
+        nn/dataset.py:44-58 of the reference); GSL batches are sized by the query's ``.batch(n)``."""
         self._query = query
         self._ds = _GslDataset(query, window=window, **kwargs)
         self._induce = induce_func
+        self.batch_size, self.drop_last = int(batch_size), bool(drop_last)
+
+    def __iter__(self):
+        """one epoch of ``get_data_dict()`` results"""
+        while True:
+            try:
+                yield self.get_data_dict()
+            except errors.OutOfRangeError:
+                return
+
+    @property
+    def iterator(self):
+        return iter(self)
+
+    def get_subgraphs(self, inducer):
+        """``inducer.induce_func(query result) -> (positive subgraphs, negative subgraphs | None)`` for the next GSL batch
+        (nn/dataset.py:124-136; ``nn.SubGraphInducer``)"""
+        return inducer.induce_func(self._ds.next())
+
+    def get_subgraphs_v2(self, processor):
+        """``batch_size`` processed SubGraph samples of a ``g.SubGraph(...)`` query (nn/dataset.py:138-157;
+        ``nn.SubGraphProcessor``); raises OutOfRangeError at the end of the epoch - a short tail is returned unless
+        ``drop_last``"""
+        if getattr(self, "_sg_epoch_end", False):          # the previous call returned the short tail of the epoch
+            self._sg_epoch_end = False
+            raise errors.OutOfRangeError("OutOfRange")
+        rets = []
+        alias = self._query.list_alias()[-1]
+        while len(rets) < self.batch_size:
+            try:
+                rets.append(processor.process_func(self._ds.next()[alias]))
+            except errors.OutOfRangeError:
+                if rets and not self.drop_last:
+                    self._sg_epoch_end = True
+                    return rets
+                raise
+        return rets
 
     @property
     def raw(self):
@@ -94,13 +134,52 @@ class TorchDataset(torch.utils.data.IterableDataset):
     """Iterate one epoch of a query; every item is a dict alias -> Data (or the output of
     ``transform``).  Use with ``DataLoader(ds, batch_size=None)`` or iterate directly."""
 
-    def __init__(self, query, window=10, transform: Optional[Callable] = None, length: Optional[int] = None):
+    def __init__(self, query, window=10, transform: Optional[Callable] = None, length: Optional[int] = None,
+                 induce_func: Optional[Callable] = None, graph=None, cluster=None):
+        """``induce_func`` is the reference's name for ``transform`` (nn/pytorch/data/dataset.py:31-60: data dict -> list of
+        sub-graphs).  ``graph`` / ``cluster``: lazy client-mode initialisation - the dataset connects ``graph`` to the servers
+        of ``cluster`` (default: ``nn.get_cluster_spec()``) on first iteration, as DataLoader workers do in the reference."""
         super().__init__()
-        self._nn = Dataset(query, window=window)
-        self._transform = transform
+        self._query, self._window = query, window
+        self._graph, self._cluster = graph, cluster
+        self._lazy = graph is not None
+        if self._lazy:
+            from .utils import is_server_launched
+            if not is_server_launched():
+                raise RuntimeError("graph learn server should be running firstly when using lazy init dataset")
+        self._nn = None if self._lazy else Dataset(query, window=window)
+        self._transform = transform if transform is not None else induce_func
         self._length = length
+        self._as_dict = False
+        self._client_id = 0
+
+    def lazy_init(self) -> bool:
+        return self._lazy
+
+    @property
+    def client_id(self) -> int:
+        return self._client_id
+
+    @client_id.setter
+    def client_id(self, value):
+        if not isinstance(value, int):
+            raise ValueError("client_id must be an int")
+        self._client_id = value
+
+    def as_dict(self):
+        """yield plain dicts of tensors instead of ``Data`` objects (for torch's default collate; dataset.py:86-93)"""
+        self._as_dict = True
+        return self
+
+    def _ensure(self):
+        if self._nn is None:
+            from .utils import get_cluster_spec
+            self._graph.init(cluster=self._cluster or get_cluster_spec(), job_name="client", task_index=self._client_id)
+            q = self._query(self._graph) if callable(self._query) else self._query
+            self._nn = Dataset(q, window=self._window)
 
     def __iter__(self):
+        self._ensure()
         n = 0
         while self._length is None or n < self._length:
             try:
@@ -108,7 +187,12 @@ class TorchDataset(torch.utils.data.IterableDataset):
             except errors.OutOfRangeError:
                 return
             n += 1
-            yield self._transform(d) if self._transform else d
+            if self._transform:
+                yield self._transform(d)
+            elif self._as_dict:
+                yield {k: {a: b for a, b in v.__dict__.items() if b is not None} for k, v in d.items()}
+            else:
+                yield d
 
 
 class SubGraphData(object):

@@ -651,3 +651,47 @@ def test_link_dist_trainer_hits_and_predict(tmp_path):
                                                    m.score(b["pos"].tensor("src_ids"), b["pos"].tensor("dst_ids"))), str(tmp_path / "pred"))
     lines = open(str(tmp_path / "pred") + ".rank0").read().strip().split("\n")
     assert n == len(lines) - 1 == g.get_stats()["buy"][0] and lines[0].startswith("src_id:int64")
+
+
+def test_nn_dataset_reference_methods(tmp_path):
+    """nn.Dataset iteration / get_subgraphs(inducer) / get_subgraphs_v2(processor) and the TorchDataset compat surface of the
+    reference's nn/pytorch Dataset (induce_func, as_dict, client_id, lazy_init)."""
+    g = fx.build_graph(fx.write_graph(str(tmp_path)))
+    q = g.V("item").batch(8).alias("s").outV("sim").sample(2).by("topk").alias("n").values()
+    n_batches = sum(1 for _ in glnn.Dataset(q))
+    assert n_batches == (fx.N_ITEM + 7) // 8
+    first = next(glnn.Dataset(q).iterator)
+    assert set(first) == {"s", "n"} and first["n"].floats.shape == (16, 4)
+
+    class PairInducer(glnn.SubGraphInducer):
+        def induce_func(self, values):
+            src, nbr = values["s"], values["n"]
+            pos = [(int(a), [int(x) for x in row]) for a, row in zip(src.ids.tolist(), nbr.ids.tolist())]
+            return pos, None
+    pos, neg = glnn.Dataset(q).get_subgraphs(PairInducer(use_neg=False))
+    assert neg is None and len(pos) == 8 and all(len(r) == 2 for _, r in pos)
+
+    class CountProcessor(glnn.SubGraphProcessor):
+        def process_func(self, subgraph):
+            return int(subgraph.num_nodes), tuple(subgraph.edge_index.shape)
+    sq = g.SubGraph("item", "sim", batch_size=6).alias("sg").values()
+    ds = glnn.Dataset(sq, batch_size=3)
+    got = ds.get_subgraphs_v2(CountProcessor())
+    assert len(got) == 3 and all(n == 6 and e[0] == 2 for n, e in got)
+    total = 3
+    with pytest.raises(gl.OutOfRangeError):
+        while True:
+            total += len(ds.get_subgraphs_v2(CountProcessor()))
+    assert total == (fx.N_ITEM + 5) // 6
+    # TorchDataset compat
+    td = glnn.TorchDataset(q, induce_func=lambda d: [d["s"].ids.numel()])
+    assert next(iter(td)) == [8] and not td.lazy_init()
+    td.client_id = 3
+    assert td.client_id == 3
+    with pytest.raises(ValueError):
+        td.client_id = "x"
+    dd = next(iter(glnn.TorchDataset(q).as_dict()))
+    assert isinstance(dd["s"], dict) and dd["s"]["ids"].shape == (8,) and "floats" in dd["n"]
+    with pytest.raises(RuntimeError):
+        glnn.TorchDataset(q, graph=gl.Graph())           # lazy client mode needs a launched server
+    g.close()
