@@ -459,3 +459,10 @@ class SubGraph(object):
     @property
     def num_edges(self):
         return int(self._edge_index.size(1))
+
+    @property
+    def keys(self):
+        """names of the attributes that are set: edge_index, nodes, edges and any extras such as dist_to_src / dist_to_dst
+        (nn/subgraph.py ``keys``)"""
+        base = ["edge_index", "nodes"] + (["edges"] if self._edges is not None else [])
+        return base + [k for k, v in self.__dict__.items() if not k.startswith("_") and v is not None]

@@ -221,6 +221,11 @@ class EgoLayer(nn.Module):
         super().__init__()
         self.convs = nn.ModuleList(convs)
 
+    def append(self, conv):
+        """add the conv of one more hop pair (ego_layer.py:94-95)"""
+        self.convs.append(conv)
+        return self
+
     def forward(self, x_list, expands):
         assert len(self.convs) == len(x_list) - 1
         return [self.convs[i](x_list[i], x_list[i + 1], expands[i]) for i in range(len(x_list) - 1)]

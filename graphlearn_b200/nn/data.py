@@ -96,6 +96,15 @@ class TemporalGraph(object):
         self.nbr_nodes, self.nbr_t, self.nbr_edges = list(nbr_nodes), list(nbr_t), list(nbr_edges or [])
         self.nbr_nums, self.node_schema, self.edge_schema, self.time_dim = list(nbr_nums), node_schema, edge_schema, time_dim
 
+    def hop_node(self, i) -> Data:
+        return self.nbr_nodes[i]
+
+    def hop_edge(self, i) -> Data:
+        return self.nbr_edges[i]
+
+    def hop_t(self, i) -> torch.Tensor:
+        return self.nbr_t[i]
+
     def time_spans(self):
         """per hop: (time of the hop's parent element) - (edge time), flattened like the hop."""
         spans, parent_t = [], self.src_t.reshape(-1)
@@ -161,6 +170,21 @@ class BatchGraph(object):
         out.raw_nodes = self.nodes
         return out
 
+    def to_graphs(self):
+        """split the batch back into per-graph ``(edge_index [2, m_i] with local node numbering, node ``Data`` slice)`` pairs
+        (batchgraph.py ``to_graphs``)"""
+        off = self.graph_node_offsets.tolist()
+        out = []
+        row = self.edge_index[0]
+        for i in range(len(off) - 1):
+            lo, hi = off[i], off[i + 1]
+            m = (row >= lo) & (row < hi)
+            nodes = self.nodes[lo:hi] if isinstance(self.nodes, torch.Tensor) else Data(
+                *[None if v is None else v[lo:hi] for v in (self.nodes.ids, self.nodes.ints, self.nodes.floats, self.nodes.strings,
+                                                            self.nodes.labels, self.nodes.weights)])
+            out.append((self.edge_index[:, m] - lo, nodes))
+        return out
+
     @staticmethod
     def from_graphs(graphs, additional_keys=()) -> "BatchGraph":
         """graphs: list of ``SubGraph`` results."""
@@ -194,9 +218,77 @@ class BatchGraph(object):
 class HeteroBatchGraph(object):
     """dict-of-types variant: edge_index_dict[(src_t, edge_t, dst_t)], nodes_dict[type]."""
 
-    def __init__(self, edge_index_dict: Dict, nodes_dict: Dict[str, Data], graph_node_offsets_dict=None):
+    def __init__(self, edge_index_dict: Dict, nodes_dict: Dict[str, Data], graph_node_offsets_dict=None, edges_dict=None,
+                 graph_edge_offsets_dict=None, node_schema_dict=None, edge_schema_dict=None):
         self.edge_index_dict, self.nodes_dict = edge_index_dict, nodes_dict
         self.graph_node_offsets_dict = graph_node_offsets_dict or {}
+        self.edges_dict, self.graph_edge_offsets_dict = edges_dict or {}, graph_edge_offsets_dict or {}
+        self.node_schema_dict, self.edge_schema_dict = node_schema_dict, edge_schema_dict
+
+    @property
+    def node_types(self):
+        return list(self.nodes_dict)
+
+    @property
+    def edge_types(self):
+        return list(self.edge_index_dict)
+
+    def num_edges(self, key):
+        return int(self.edge_index_dict[key].size(1))
+
+    @property
+    def num_graphs(self):
+        for off in self.graph_node_offsets_dict.values():
+            return int(off.numel()) - 1
+        return 0
+
+    def transform(self, encoders=None) -> "HeteroBatchGraph":
+        """HeteroBatchGraph whose ``nodes_dict`` holds dense feature matrices: ``encoders`` = {node type: FeatureHandler /
+        FeatureEncoder / callable on Data}; types without an encoder keep their float attributes (hetero_batchgraph.py:113-152)"""
+        encoders = encoders or {}
+        out = {}
+        for t, d in self.nodes_dict.items():
+            if isinstance(d, torch.Tensor):
+                out[t] = d
+                continue
+            enc = encoders.get(t)
+            if enc is None:
+                out[t] = d.floats.float()
+            elif hasattr(enc, "_fspec"):
+                out[t] = enc(d)
+            else:
+                try:
+                    out[t] = enc(d.floats, d.ints, d.strings)
+                except TypeError:
+                    out[t] = enc(d)
+        return HeteroBatchGraph(self.edge_index_dict, out, self.graph_node_offsets_dict, self.edges_dict, self.graph_edge_offsets_dict,
+                                self.node_schema_dict, self.edge_schema_dict)
+
+    @staticmethod
+    def from_graphs(graphs) -> "HeteroBatchGraph":
+        """stack ``nn.HeteroSubGraph`` objects: per node type the ``Data`` rows are concatenated, every ``edge_index_dict[(h, r, t)]``
+        is shifted by the per-graph offsets of its two end types (row -> t, col -> h, the HeteroSubGraph convention)"""
+        types = list(graphs[0].nodes_dict)
+        offs = {t: [0] for t in types}
+        for g in graphs:
+            for t in types:
+                offs[t].append(offs[t][-1] + int(g.nodes_dict[t].ids.numel()))
+        nodes = {}
+        for t in types:
+            ds = [g.nodes_dict[t] for g in graphs]
+            cat = lambda name: (torch.cat([getattr(d, name) for d in ds]) if all(isinstance(getattr(d, name), torch.Tensor) for d in ds) else None)  # noqa: E731
+            nodes[t] = Data(cat("ids"), cat("ints"), cat("floats"), None, cat("labels"), cat("weights"))
+        ei = {}
+        for key in graphs[0].edge_index_dict:
+            h, _, tt = key
+            parts = []
+            for i, g in enumerate(graphs):
+                e = g.edge_index_dict[key]
+                shift = torch.tensor([[offs[tt][i]], [offs[h][i]]], device=e.device, dtype=e.dtype)
+                parts.append(e + shift)
+            ei[key] = torch.cat(parts, 1)
+        dev = next(iter(ei.values())).device if ei else torch.device("cpu")
+        return HeteroBatchGraph(ei, nodes, {t: torch.tensor(o, device=dev) for t, o in offs.items()})
 
     def num_nodes(self, t):
         return int(self.nodes_dict[t].ids.numel())

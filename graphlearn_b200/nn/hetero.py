@@ -124,6 +124,11 @@ class HeteroSubGraph(object):
     def num_edges(self, key):
         return int(self.edge_index_dict[key].size(1))
 
+    @property
+    def keys(self):
+        """names of the attributes that are set (hetero_subgraph.py ``keys``)"""
+        return [k for k, v in self.__dict__.items() if v is not None and not k.startswith("_")]
+
 
 class SubGraphInducer(object):
     """Subclass and implement ``induce_func(data_dict) -> (pos_subgraphs, neg_subgraphs | None)``."""

@@ -695,3 +695,32 @@ def test_nn_dataset_reference_methods(tmp_path):
     with pytest.raises(RuntimeError):
         glnn.TorchDataset(q, graph=gl.Graph())           # lazy client mode needs a launched server
     g.close()
+
+
+def test_container_parity_methods():
+    """BatchGraph.to_graphs, HeteroBatchGraph.from_graphs / transform / num_graphs / num_edges, TemporalGraph.hop_*, EgoLayer.append,
+    SubGraph / HeteroSubGraph keys, GLError.message - method-level parity with the reference's containers."""
+    ei = torch.cat([torch.tensor([[0, 1], [1, 2]]) + 3 * i for i in range(2)], 1)
+    bg = glnn.BatchGraph(ei, glnn.Data(ids=torch.arange(6), floats=torch.arange(12.).reshape(6, 2)), graph_node_offsets=torch.tensor([0, 3, 6]))
+    parts = bg.to_graphs()
+    assert len(parts) == 2 and parts[1][0].tolist() == [[0, 1], [1, 2]] and parts[1][1].ids.tolist() == [3, 4, 5]
+    assert bg.transform().to_graphs()[0][1].shape == (3, 2)
+    hs = []
+    for i in range(3):
+        nodes = {"u": glnn.Data(ids=torch.arange(2) + 10 * i, floats=torch.ones(2, 3) * i), "v": glnn.Data(ids=torch.arange(4) + 100 * i, floats=torch.ones(4, 5))}
+        hs.append(glnn.HeteroSubGraph({("u", "r", "v"): torch.tensor([[0, 3], [1, 0]])}, nodes))
+    assert set(hs[0].keys) >= {"edge_index_dict", "nodes_dict"}
+    hb = glnn.HeteroBatchGraph.from_graphs(hs)
+    assert hb.num_graphs == 3 and hb.num_edges(("u", "r", "v")) == 6 and hb.num_nodes("v") == 12 and hb.node_types == ["u", "v"]
+    # rows index the tail type (v: 4 per graph), cols the head type (u: 2 per graph)
+    assert hb.edge_index_dict[("u", "r", "v")].tolist() == [[0, 3, 4, 7, 8, 11], [1, 0, 3, 2, 5, 4]]
+    tr = hb.transform({"u": lambda d: d.floats * 2})
+    assert tr.nodes_dict["u"].shape == (6, 3) and float(tr.nodes_dict["u"][4, 0]) == 4.0 and tr.nodes_dict["v"].shape == (12, 5)
+    tg = glnn.TemporalGraph(glnn.Data(ids=torch.arange(2)), torch.tensor([5, 6]), [glnn.Data(ids=torch.arange(4))], [torch.tensor([1, 2, 3, 4])],
+                            [glnn.Data(ids=torch.arange(4))], [2])
+    assert tg.hop_node(0).ids.numel() == 4 and tg.hop_t(0).tolist() == [1, 2, 3, 4] and tg.hop_edge(0).ids.numel() == 4
+    layer = glnn.EgoLayer([glnn.EgoSAGEConv(4, 8)])
+    layer.append(glnn.EgoSAGEConv(4, 8))
+    assert len(layer.convs) == 2
+    err = gl.NotFoundError("no such node")
+    assert err.message == "no such node" and isinstance(err, gl.BaseError)
