@@ -429,5 +429,7 @@ def data_loader(dgs_host: str, max_batch_size: int = 4096, admin_token: str = ""
     marks "everything produced so far", ``graph.check_barrier(name)`` polls it."""
     from .file_loader import GroupProducer            # numpy-only module
     g = Graph.connect(dgs_host, admin_token=admin_token)
+    info = g._http("GET", "/admin/init-info/dataloader")          # Initialize(dgs_host): endpoints, partitions, schema
+    g.loader_info = info
     g.get_schema()
     return GroupProducer(HttpSink(g), max_batch_size=max_batch_size, num_partitions=1), g

@@ -13,6 +13,7 @@ device stream by a lock.
   POST /admin/barrier/set?name=x[&produced=n]     GET /admin/barrier/status?name=x
   GET  /admin/stats                    liveness + counters (k8s probes)
   GET  /admin/schema                   the graph schema (reference JSON)        GET /admin/query[?qid=n]  an installed query
+  GET  /admin/init-info/dataloader     what a data loader needs: ingest endpoints, data partition count, schema
 The Python GSL client (``dgs/client.py``, the role of the reference's Java client) speaks exactly this surface.
 """
 from __future__ import annotations
@@ -82,6 +83,13 @@ class HttpFrontEnd(object):
                         self._send(200, {"status": front.barriers.status(q["name"][0])})
                     elif u.path == "/admin/schema":
                         self._send(200, front.schema.raw if front.schema is not None else {})
+                    elif u.path == "/admin/init-info/dataloader":
+                        # what a data loader needs before producing (the reference hands out the Kafka brokers / topic /
+                        # partition count + the schema, coordinator/http_service.py:95-103): here records go to /admin/ingest
+                        # (or /admin/load), one data partition per service process
+                        parts = int(getattr(front.service, "P", 1))
+                        self._send(200, {"downstream": {"transport": "http", "ingest": "/admin/ingest", "load": "/admin/load"},
+                                         "data_partition_num": parts, "schema": front.schema.raw if front.schema is not None else {}})
                     elif u.path == "/admin/query":
                         if not front.installed:
                             self._send(404, {"error": "no query installed"})
