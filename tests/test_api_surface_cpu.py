@@ -299,3 +299,24 @@ def test_graph_and_dag_node_methods():
     for c in DagNode.__subclasses__():
         have |= set(dir(c))
     assert not [m for m in REF["dag_node_methods"] if m not in have and m not in INTERNAL_DAG]
+
+
+def test_reference_import_paths():
+    """``graphlearn.python.nn.tf`` / ``.pytorch`` style imports work after renaming the package, with the same flat name sets as
+    the reference's __init__ files."""
+    import graphlearn_b200.python.nn as gnn
+    import graphlearn_b200.python.nn.pytorch as thg
+    import graphlearn_b200.python.nn.tf as tfg
+    tf_names = ["conf", "Dataset", "FeatureColumn", "EmbeddingColumn", "DynamicEmbeddingColumn", "NumericColumn", "FusedEmbeddingColumn",
+                "SparseEmbeddingColumn", "DynamicSparseEmbeddingColumn", "FeatureGroup", "FeatureHandler", "sigmoid_cross_entropy_loss",
+                "unsupervised_softmax_cross_entropy_loss", "triplet_margin_loss", "triplet_softplus_loss", "Module", "EgoGraph",
+                "EgoGATConv", "EgoGINConv", "EgoLayer", "EgoRGCNConv", "EgoSAGEConv", "LinearLayer", "EgoGNN", "LinkPredictor",
+                "BatchGraph", "HeteroBatchGraph", "SubGraphInducer", "SubGraphProcessor", "GATConv", "GCNConv", "HeteroConv", "SAGEConv",
+                "SubConv", "GAT", "GCN", "GraphSAGE", "SEAL", "compute_norm", "unsorted_segment_softmax", "SyncBarrierHook"]
+    assert not [n for n in tf_names if not hasattr(tfg, n)]
+    th_names = ["Dataset", "get_cluster_spec", "get_counts", "launch_server", "set_client_num", "PyGDataLoader", "TemporalDataset",
+                "TemporalDataLoader"]
+    assert not [n for n in th_names if not hasattr(thg, n)]
+    assert not [n for n in ("Data", "Dataset", "SubGraph", "HeteroSubGraph") if not hasattr(gnn, n)]
+    import graphlearn_b200.python as glp
+    assert glp.Graph is gl.Graph and glp.nn is nn
