@@ -319,4 +319,4 @@ def test_reference_import_paths():
     assert not [n for n in th_names if not hasattr(thg, n)]
     assert not [n for n in ("Data", "Dataset", "SubGraph", "HeteroSubGraph") if not hasattr(gnn, n)]
     import graphlearn_b200.python as glp
-    assert glp.Graph is gl.Graph and glp.nn is nn
+    assert glp.Graph is gl.Graph and glp.nn.Data is nn.Data
