@@ -558,9 +558,17 @@ class Graph(object):
             return ConditionalNegativeSampler(self, object_type, expand_factor, strategy, **kwargs)
         return NegativeSampler(self, object_type, expand_factor, strategy)
 
-    def subgraph_sampler(self, seed_type, nbr_type, batch_size=64, strategy="random_node", num_nbrs=None,
+    def subgraph_sampler(self, seed_type=None, nbr_type=None, batch_size=64, strategy="random_node", num_nbrs=None,
                          need_dist=False):
+        """``seed_type`` defaults to the source node type of ``nbr_type`` (the reference's own tests call
+        ``g.subgraph_sampler(nbr_type="relation")``)."""
         from .sampler.subgraph_sampler import SubGraphSampler
+        if nbr_type is None and seed_type is not None and seed_type in self._store.edges:
+            seed_type, nbr_type = None, seed_type
+        if nbr_type is None:
+            raise ValueError("subgraph_sampler needs the neighbour (edge) type")
+        if seed_type is None:
+            seed_type = self._store.edges[nbr_type].src_type
         return SubGraphSampler(self, seed_type, nbr_type, batch_size, strategy, num_nbrs, need_dist)
 
     def search(self, node_type, inputs, option):

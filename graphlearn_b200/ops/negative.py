@@ -196,13 +196,26 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
     (conditional_negative_sampler.cc:37-156).  True neighbours of src and (unique=True)
     duplicates are avoided on a best-effort basis like the reference."""
     cfg = _config.get()
-    csr = store.edges[etype]
-    tab = store.nodes[csr.dst_type]
+    is_edge = etype in store.edges
+    if not is_edge and etype not in store.nodes:
+        raise KeyError("conditional negative sampling: %r is neither an edge type nor a node type" % (etype,))
+    csr = store.edges[etype] if is_edge else None
+    dst_type = csr.dst_type if is_edge else etype
+    tab = store.nodes[dst_type]
     rt = store.rt
     B = int(src_v.numel())
     dev = src_v.device
     base_strategy = strategy if strategy in ("random", "in_degree") else "random"
-    out = edge_negative(store, etype, src_v, k, base_strategy, gen)
+    if is_edge:
+        def _base():
+            return edge_negative(store, etype, src_v, k, base_strategy, gen)
+    else:
+        # object = a NODE type (``negative_sampler(node_type, strategy="node_weight", conditional=True)``): candidates are the
+        # nodes of that type drawn by weight (uniformly when the table has no weights); there is no neighbourhood to avoid,
+        # only the positive ids
+        def _base():
+            return node_weight_negative(store, etype, dst_v, k, gen)
+    out = _base()
     cols = [("int", c, p) for c, p in zip(cond.get("int_cols", []), cond.get("int_props", []))] + \
            [("float", c, p) for c, p in zip(cond.get("float_cols", []), cond.get("float_props", []))] + \
            [("str", c, p) for c, p in zip(cond.get("str_cols", []), cond.get("str_props", []))]
@@ -216,10 +229,13 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
             pos = torch.searchsorted(pos_sorted, cand.reshape(-1)).clamp_(max=max(pos_sorted.numel() - 1, 0))
             return (pos_sorted[pos] == cand.reshape(-1)).reshape(cand.shape)
         for _ in range(max(1, int(cfg.neg_sampling_retry_times))):       # strictness is dropped after the retries
-            out = torch.where(_excluded(out), edge_negative(store, etype, src_v, k, base_strategy, gen), out)
-    else:
+            out = torch.where(_excluded(out), _base(), out)
+    elif is_edge:
         def _excluded(cand):
             return _is_neighbor(csr, src_v, cand) | (cand == dst_v[:, None])
+    else:
+        def _excluded(cand):
+            return cand == dst_v[:, None]
     if not cols:
         return out
     slot = 0
@@ -233,7 +249,7 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
             # positives' values into integer codes, then reuse the sorted-run index below
             import numpy as np
             if tab.str_dim == 0:
-                raise ValueError("conditional negative sampling: node type %r has no string attributes" % (csr.dst_type,))
+                raise ValueError("conditional negative sampling: node type %r has no string attributes" % (dst_type,))
             # factorise the LOCAL column and the positives' values (fetched from their owners) with one shared
             # vocabulary, then reuse the sorted-run index below
             col = np.asarray(tab.strings[:, c], dtype=object).astype(str) if tab.strings is not None and tab.n_local else \
@@ -244,13 +260,13 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
             dstv = torch.as_tensor(codes[len(col):], device=dev).long()
         elif kind == "int":
             if tab.ints is None:
-                raise ValueError("conditional negative sampling: node type %r has no int attributes" % (csr.dst_type,))
+                raise ValueError("conditional negative sampling: node type %r has no int attributes" % (dst_type,))
             attr_all = tab.ints
             dstv = G.gather_any(rt, attr_all, dst_v, fill=0)[:, c]
             local_vals = attr_all.local[:, c]
         else:
             if tab.feats is None:
-                raise ValueError("conditional negative sampling: node type %r has no float attributes" % (csr.dst_type,))
+                raise ValueError("conditional negative sampling: node type %r has no float attributes" % (dst_type,))
             dstv = G.gather_rows(rt, tab.feats, tab.feat_desc, dst_v, tab.float_dim)[:, c]
             local_vals = tab.feats.local[:, c].float()
         # inverted index over the LOCAL shard: sort rows by attribute value, pick uniformly inside
@@ -291,6 +307,6 @@ def conditional_negative(store, etype: str, src_v: torch.Tensor, dst_v: torch.Te
         dup = torch.zeros_like(out, dtype=torch.bool)
         dup[:, 1:] = srt[:, 1:] == srt[:, :-1]
         dup = torch.zeros_like(out, dtype=torch.bool).scatter(1, idx, dup)
-        fresh = edge_negative(store, etype, src_v, k, base_strategy, gen)
+        fresh = _base()
         out = torch.where(dup, fresh, out)
     return out

@@ -254,6 +254,8 @@ def sample_neighbors(csr: CsrShard, src_vids: torch.Tensor, k: int, strategy: st
         if out is not None:
             out.view(-1).copy_(nbr.reshape(-1))
         return nbr, (eid if want_eids else None)
+    if strategy == "edge_weight" and csr.cumw is None:
+        strategy = "random"        # unweighted edge type: every edge carries the same default weight (the reference's behaviour)
     if strategy not in STRATEGY:
         raise ValueError("unknown sampling strategy %r (built-in: %s; registered: %s)" % (strategy, ", ".join(STRATEGY),
                                                                                           ", ".join(registered_samplers()) or "-"))

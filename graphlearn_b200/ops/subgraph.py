@@ -77,9 +77,13 @@ def induce_subgraph(store, etype: str, seeds: torch.Tensor, num_nbrs: List[int],
     cidx = rl.lookup(vals)     # membership test + local index in one table probe
     hit = cidx >= 0
     r, c, e = rows[hit], cidx[hit], eids[hit]
-    row = torch.cat([r, c])
-    col = torch.cat([c, r])
-    eid = torch.cat([e, e])
+    # the reference's order (subgraph_sampler.cc / its python checks): stored edges by (row index, col index), each followed
+    # by its mirrored entry
+    order = torch.argsort(r * max(n, 1) + c, stable=True)
+    r, c, e = r[order], c[order], e[order]
+    row = torch.stack([r, c], 1).reshape(-1)
+    col = torch.stack([c, r], 1).reshape(-1)
+    eid = torch.stack([e, e], 1).reshape(-1)
     out = {"nodes": nodes, "row": row, "col": col, "eids": eid, "dist_to_src": None, "dist_to_dst": None}
     if need_dist and n >= 2:
         d_dst = _bfs(n, row, col, start=1, removed=0)

@@ -51,14 +51,21 @@ class ConditionalNegativeSampler(object):
         self._rng = rng_ops.DeviceRng(graph.runtime, 223)
 
     def get(self, src_ids, dst_ids):
+        """``object_type`` is an edge type (negatives for (src, dst) pairs of that type) or - with ``strategy="node_weight"`` - a
+        NODE type: candidates are that type's nodes, ``src_ids`` only fix the batch shape (conditional_negative_sampler.cc)."""
         g = self._g
-        csr = g.store.edges[self._type]
-        s = g.to_vids(csr.src_type, _t(src_ids, g.device))
-        d = g.to_vids(csr.dst_type, _t(dst_ids, g.device))
+        if self._type in g.store.edges:
+            csr = g.store.edges[self._type]
+            src_type, dst_type = csr.src_type, csr.dst_type
+            s = g.to_vids(src_type, _t(src_ids, g.device))
+        else:
+            dst_type = self._type
+            s = _t(src_ids, g.device).reshape(-1)                       # not looked up: ids of whatever type the caller pairs with
+        d = g.to_vids(dst_type, _t(dst_ids, g.device))
         neg = NEG.conditional_negative(g.store, self._type, s, d, self._k, self._strategy, self._cond,
                                        self._rng.torch_generator(2))
         self._rng.advance(1)
-        return V_.Nodes(g.to_ids(csr.dst_type, neg), csr.dst_type, shape=(int(s.numel()), self._k), graph=g, vids=neg)
+        return V_.Nodes(g.to_ids(dst_type, neg), dst_type, shape=(int(s.numel()), self._k), graph=g, vids=neg)
 
 
 from .neighbor_sampler import _fixed_strategy  # noqa: E402

@@ -1,0 +1,119 @@
+"""Conformance run: the REFERENCE's own Python unit tests (graphlearn/python/{tests,sampler/tests,gsl/tests}/test_*.py) executed
+against this package.  Nothing is copied: the test files and their helper (python/tests/utils.py) are loaded from the reference
+checkout at run time, with ``graphlearn`` aliased to ``graphlearn_b200`` in ``sys.modules`` - exactly what a user does who
+switches the import.
+
+    python tools/run_reference_pytests.py [--ref /root/reference] [--pattern test_node] [-v]
+
+Every test file runs in its own process (the reference's tests share global flags and tracker directories), on the CPU.
+Prints one line per file and a summary; exit code 0 when everything that ran passed.
+"""
+import argparse
+import glob
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+RUNNER = r'''
+import importlib.util, os, sys, types, unittest
+sys.path.insert(0, {root!r})
+import graphlearn_b200 as gl
+import graphlearn_b200.python as glp
+sys.modules["graphlearn"] = gl
+sys.modules["graphlearn.python"] = glp
+for sub in ("nn", "nn.tf", "nn.pytorch"):
+    sys.modules["graphlearn.python." + sub] = importlib.import_module("graphlearn_b200.python." + sub)
+for name, mod in (("errors", "errors"), ("utils", "utils"), ("config", "config"), ("data", "data"), ("sampler", "sampler"), ("gsl", "gsl")):
+    sys.modules["graphlearn.python." + name] = importlib.import_module("graphlearn_b200." + mod)
+    setattr(glp, name, sys.modules["graphlearn.python." + name])
+ref = {ref!r}
+def attach(modname, m):
+    sys.modules[modname] = m
+    parent, _, leaf = modname.rpartition(".")
+    if parent in sys.modules:
+        try:
+            setattr(sys.modules[parent], leaf, m)
+        except Exception:
+            pass
+def load(modname, path):
+    spec = importlib.util.spec_from_file_location(modname, path)
+    m = importlib.util.module_from_spec(spec)
+    attach(modname, m)
+    spec.loader.exec_module(m)
+    return m
+for name in ("graphlearn.python.tests", "graphlearn.python.sampler.tests", "graphlearn.python.gsl.tests"):
+    pkg = types.ModuleType(name); pkg.__path__ = []
+    attach(name, pkg)
+load("graphlearn.python.tests.utils", os.path.join(ref, "graphlearn/python/tests/utils.py"))
+# other test files import their base classes as graphlearn.python.<dir>.tests.<module>: resolve those names to the reference files
+import importlib.abc, importlib.machinery
+class RefTests(importlib.abc.MetaPathFinder):
+    DIRS = {{"graphlearn.python.tests": "graphlearn/python/tests", "graphlearn.python.sampler.tests": "graphlearn/python/sampler/tests",
+            "graphlearn.python.gsl.tests": "graphlearn/python/gsl/tests"}}
+    def find_spec(self, fullname, path, target=None):
+        parent, _, leaf = fullname.rpartition(".")
+        d = self.DIRS.get(parent)
+        if d is None:
+            return None
+        f = os.path.join(ref, d, leaf + ".py")
+        return importlib.util.spec_from_file_location(fullname, f) if os.path.exists(f) else None
+sys.meta_path.insert(0, RefTests())
+os.chdir({cwd!r})
+gl.set_default_neighbor_id(0) if False else None
+m = load("ref_test_module", {test!r})
+suite = unittest.defaultTestLoader.loadTestsFromModule(m)
+res = unittest.TextTestRunner(verbosity={verbosity}, stream=sys.stdout).run(suite)
+print("RESULT run=%d failures=%d errors=%d skipped=%d" % (res.testsRun, len(res.failures), len(res.errors), len(res.skipped)))
+'''
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--pattern", default="")
+    ap.add_argument("-v", action="store_true")
+    ap.add_argument("--timeout", type=int, default=300)
+    a = ap.parse_args()
+    py = os.path.join(a.ref, "graphlearn", "python")
+    if not os.path.isdir(py):
+        print("no reference checkout at", a.ref)
+        return 0
+    files = sorted(glob.glob(py + "/tests/test_*.py") + glob.glob(py + "/sampler/tests/test_*.py") + glob.glob(py + "/gsl/tests/test_*.py"))
+    files = [f for f in files if a.pattern in os.path.basename(f)]
+    import tempfile
+    tot = {"run": 0, "failures": 0, "errors": 0, "skipped": 0}
+    bad_files = []
+    for f in files:
+        cwd = tempfile.mkdtemp(prefix="glb_reftest_")
+        code = RUNNER.format(root=ROOT, ref=a.ref, cwd=cwd, test=f, verbosity=2 if a.v else 0)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="", GLB_TEST_DEVICE="cpu")
+        try:
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=a.timeout, env=env)
+            out = p.stdout + p.stderr
+        except subprocess.TimeoutExpired:
+            out = "TIMEOUT"
+        line = [l for l in out.splitlines() if l.startswith("RESULT")]
+        rel = os.path.relpath(f, py)
+        if line:
+            kv = dict(x.split("=") for x in line[-1].split()[1:])
+            for k in tot:
+                tot[k] += int(kv[k])
+            ok = int(kv["failures"]) == 0 and int(kv["errors"]) == 0
+            print("%-55s %s  %s" % (rel, "ok  " if ok else "FAIL", line[-1][7:]))
+            if not ok:
+                bad_files.append(rel)
+                if a.v:
+                    print(out[-3000:])
+        else:
+            print("%-55s CRASH %s" % (rel, out.strip().splitlines()[-1][:160] if out.strip() else ""))
+            bad_files.append(rel)
+            if a.v:
+                print(out[-3000:])
+    print("TOTAL files=%d %s  not-clean: %s" % (len(files), tot, bad_files))
+    return 0 if not bad_files else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
