@@ -190,7 +190,8 @@ class TorchDataset(torch.utils.data.IterableDataset):
             if self._transform:
                 yield self._transform(d)
             elif self._as_dict:
-                yield {k: {a: b for a, b in v.__dict__.items() if b is not None} for k, v in d.items()}
+                names = {"ints": "int_attrs", "floats": "float_attrs", "strings": "string_attrs"}      # the reference's field names
+                yield {k: {names.get(a, a): b for a, b in v.__dict__.items() if isinstance(b, torch.Tensor)} for k, v in d.items()}
             else:
                 yield d
 

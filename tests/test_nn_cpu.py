@@ -691,7 +691,7 @@ def test_nn_dataset_reference_methods(tmp_path):
     with pytest.raises(ValueError):
         td.client_id = "x"
     dd = next(iter(glnn.TorchDataset(q).as_dict()))
-    assert isinstance(dd["s"], dict) and dd["s"]["ids"].shape == (8,) and "floats" in dd["n"]
+    assert isinstance(dd["s"], dict) and dd["s"]["ids"].shape == (8,) and dd["n"]["float_attrs"].shape == (16, 4)
     with pytest.raises(RuntimeError):
         glnn.TorchDataset(q, graph=gl.Graph())           # lazy client mode needs a launched server
     g.close()

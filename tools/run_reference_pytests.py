@@ -80,7 +80,8 @@ def main():
     if not os.path.isdir(py):
         print("no reference checkout at", a.ref)
         return 0
-    files = sorted(glob.glob(py + "/tests/test_*.py") + glob.glob(py + "/sampler/tests/test_*.py") + glob.glob(py + "/gsl/tests/test_*.py"))
+    files = sorted(glob.glob(py + "/tests/test_*.py") + glob.glob(py + "/sampler/tests/test_*.py") + glob.glob(py + "/gsl/tests/test_*.py") +
+                   glob.glob(py + "/nn/pytorch/data/test/test_*.py"))        # nn/tf tests need TensorFlow
     files = [f for f in files if a.pattern in os.path.basename(f)]
     import tempfile
     tot = {"run": 0, "failures": 0, "errors": 0, "skipped": 0}
