@@ -243,6 +243,10 @@ class QueryExecutor(object):
         direction = p.get("direction", "out")
         strategy = p.get("strategy", "random")
         k = int(p.get("neighbor_count", 1))
+        if direction == "in" and (et + "_reverse") in self.store.edges:
+            # an undirected heterogeneous edge type stores its mirrored rows as '<type>_reverse': the reference defines
+            # inV / inE(type) as outV / outE(type + '_reverse') (gsl/dag_node.py:470-492), results carry that type name
+            et, direction = et + "_reverse", "out"
         if direction == "in":
             csr = self.store.reverse_csr(et)
             dst_t = self.store.edges[et].src_type

@@ -112,6 +112,31 @@ def main():
             bad_files.append(rel)
             if a.v:
                 print(out[-3000:])
+    # the reference's examples/basic walkthrough (gen_test_data.py + test_local.py: node / edge iteration over 2-hop queries,
+    # truncated full sampling, conditional negatives, stats) - executed from a scratch copy because it writes next to itself
+    basic = os.path.join(a.ref, "graphlearn", "examples", "basic")
+    if not a.pattern or a.pattern in "examples_basic_test_local":
+        import shutil
+        d = tempfile.mkdtemp(prefix="glb_refbasic_")
+        w = os.path.join(d, "basic")
+        shutil.copytree(basic, w)
+        os.makedirs(os.path.join(w, "data"), exist_ok=True)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="", GLB_TEST_DEVICE="cpu")
+        code = ("import sys, os, runpy\nsys.path.insert(0, %r)\nimport graphlearn_b200 as gl, graphlearn_b200.python as glp\n"
+                "sys.modules['graphlearn'] = gl; sys.modules['graphlearn.python'] = glp\nsys.path.insert(0, %r); os.chdir(%r)\n"
+                "runpy.run_path('gen_test_data.py', run_name='__main__')\nsys.argv = ['test_local.py']\n"
+                "runpy.run_path('test_local.py', run_name='__main__')\nprint('BASIC_OK')\n" % (ROOT, w, w))
+        try:
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=a.timeout, env=env)
+            ok = p.returncode == 0 and "BASIC_OK" in p.stdout
+            out = p.stdout + p.stderr
+        except subprocess.TimeoutExpired:
+            ok, out = False, "TIMEOUT"
+        print("%-55s %s" % ("examples/basic/test_local.py", "ok" if ok else "FAIL"))
+        if not ok:
+            bad_files.append("examples/basic/test_local.py")
+            if a.v:
+                print(out[-3000:])
     print("TOTAL files=%d %s  not-clean: %s" % (len(files), tot, bad_files))
     return 0 if not bad_files else 1
 
