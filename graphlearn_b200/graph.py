@@ -563,6 +563,8 @@ class Graph(object):
         """``seed_type`` defaults to the source node type of ``nbr_type`` (the reference's own tests call
         ``g.subgraph_sampler(nbr_type="relation")``)."""
         from .sampler.subgraph_sampler import SubGraphSampler
+        if isinstance(nbr_type, (list, tuple)):                  # g.subgraph_sampler('relation', [10, 10]): the class-level signature
+            num_nbrs, nbr_type = list(nbr_type), None
         if nbr_type is None and seed_type is not None and seed_type in self._store.edges:
             seed_type, nbr_type = None, seed_type
         if nbr_type is None:

@@ -21,10 +21,12 @@ import importlib.util, os, sys, types, unittest
 sys.path.insert(0, {root!r})
 import graphlearn_b200 as gl
 import graphlearn_b200.python as glp
-sys.modules["graphlearn"] = gl
-sys.modules["graphlearn.python"] = glp
-for sub in ("nn", "nn.tf", "nn.pytorch"):
-    sys.modules["graphlearn.python." + sub] = importlib.import_module("graphlearn_b200.python." + sub)
+import graphlearn_b200.python.nn.tf, graphlearn_b200.python.nn.pytorch
+# alias every loaded module of the package: 'graphlearn.x.y' must be THE SAME module object as 'graphlearn_b200.x.y' (a second
+# copy would break isinstance checks)
+for name, mod in list(sys.modules.items()):
+    if name == "graphlearn_b200" or name.startswith("graphlearn_b200."):
+        sys.modules["graphlearn" + name[len("graphlearn_b200"):]] = mod
 for name, mod in (("errors", "errors"), ("utils", "utils"), ("config", "config"), ("data", "data"), ("sampler", "sampler"), ("gsl", "gsl")):
     sys.modules["graphlearn.python." + name] = importlib.import_module("graphlearn_b200." + mod)
     setattr(glp, name, sys.modules["graphlearn.python." + name])
@@ -112,29 +114,39 @@ def main():
             bad_files.append(rel)
             if a.v:
                 print(out[-3000:])
-    # the reference's examples/basic walkthrough (gen_test_data.py + test_local.py: node / edge iteration over 2-hop queries,
-    # truncated full sampling, conditional negatives, stats) - executed from a scratch copy because it writes next to itself
+    # the reference's examples/basic scripts (gen_test_data.py + test_local.py: node / edge iteration over 2-hop queries, truncated
+    # full sampling, conditional negatives, stats; test_subgraph.py: SEAL-style sub-graph sampler + GSL SubGraph;
+    # test_local_temporal_{sampler,loader}.py on examples/data/gen_temporal_data.py; test_actor_local.py) - executed from a scratch
+    # copy because they write next to themselves
     basic = os.path.join(a.ref, "graphlearn", "examples", "basic")
-    if not a.pattern or a.pattern in "examples_basic_test_local":
+    scripts = [("test_local.py", "gen_test_data.py"), ("test_subgraph.py", "gen_test_data.py"), ("test_actor_local.py", "gen_test_data.py"),
+               ("test_local_temporal_sampler.py", "gen_temporal_data.py"), ("test_local_temporal_loader.py", "gen_temporal_data.py")]
+    for script, gen in scripts:
+        label = "examples/basic/" + script
+        if a.pattern and a.pattern not in label.replace("/", "_"):
+            continue
         import shutil
         d = tempfile.mkdtemp(prefix="glb_refbasic_")
         w = os.path.join(d, "basic")
         shutil.copytree(basic, w)
+        shutil.copy(os.path.join(a.ref, "graphlearn", "examples", "data", "gen_temporal_data.py"), w)
         os.makedirs(os.path.join(w, "data"), exist_ok=True)
         env = dict(os.environ, CUDA_VISIBLE_DEVICES="", GLB_TEST_DEVICE="cpu")
         code = ("import sys, os, runpy\nsys.path.insert(0, %r)\nimport graphlearn_b200 as gl, graphlearn_b200.python as glp\n"
-                "sys.modules['graphlearn'] = gl; sys.modules['graphlearn.python'] = glp\nsys.path.insert(0, %r); os.chdir(%r)\n"
-                "runpy.run_path('gen_test_data.py', run_name='__main__')\nsys.argv = ['test_local.py']\n"
-                "runpy.run_path('test_local.py', run_name='__main__')\nprint('BASIC_OK')\n" % (ROOT, w, w))
+                "import graphlearn_b200.python.nn.tf, graphlearn_b200.python.nn.pytorch\n"
+                "for n, m in list(sys.modules.items()):\n    if n == 'graphlearn_b200' or n.startswith('graphlearn_b200.'): sys.modules['graphlearn' + n[15:]] = m\n"
+                "sys.path.insert(0, %r); os.chdir(%r)\n"
+                "runpy.run_path(%r, run_name='__main__')\nsys.argv = [%r]\n"
+                "runpy.run_path(%r, run_name='__main__')\nprint('BASIC_OK')\n" % (ROOT, w, w, gen, script, script))
         try:
             p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=a.timeout, env=env)
             ok = p.returncode == 0 and "BASIC_OK" in p.stdout
             out = p.stdout + p.stderr
         except subprocess.TimeoutExpired:
             ok, out = False, "TIMEOUT"
-        print("%-55s %s" % ("examples/basic/test_local.py", "ok" if ok else "FAIL"))
+        print("%-55s %s" % (label, "ok" if ok else "FAIL"))
         if not ok:
-            bad_files.append("examples/basic/test_local.py")
+            bad_files.append(label)
             if a.v:
                 print(out[-3000:])
     print("TOTAL files=%d %s  not-clean: %s" % (len(files), tot, bad_files))
