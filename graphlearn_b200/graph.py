@@ -165,6 +165,13 @@ class Graph(object):
             self._remote_node_types = set(meta["node_types"])
             self._inited = True
             return self
+        import os as _os
+        if kwargs.get("hosts") and int(task_count or 1) <= 1:
+            task_count = len([h for h in str(kwargs["hosts"]).split(",") if h.strip()])      # rpc tracker: one host per worker
+        if int(task_count or 1) > 1 and "WORLD_SIZE" not in _os.environ and not (spec and job_name):
+            # the reference's worker-mode launch: N plain processes, each with its task index and a shared tracker directory
+            # (or a host list) - no torchrun.  Form the process group from those arguments.
+            _rt.bootstrap_cluster(int(task_index), int(task_count), kwargs.get("tracker"), kwargs.get("hosts"), device)
         self._rt = _rt.init(device=device)
         self._store = GraphStore(self._rt)
         self._store.node_decoders = self._node_decoders

@@ -203,6 +203,33 @@ def init(device: Optional[str] = None, backend: Optional[str] = None) -> Runtime
     return Runtime.get().init(device=device, backend=backend)
 
 
+def bootstrap_cluster(task_index: int, task_count: int, tracker: Optional[str] = None, hosts: Optional[str] = None,
+                      device: Optional[str] = None, timeout_s: float = 600.0) -> None:
+    """Form the process group WITHOUT torchrun, the way the reference's worker mode is launched: N independent processes call
+    ``g.init(task_index=i, task_count=N, tracker=<shared dir>)`` (file-system tracker, graph.py:445-464 /
+    fs_coordinator.cc) or ``g.init(..., hosts="ip:port,ip:port")`` (RPC tracker with an explicit host list).  The tracker
+    directory becomes a ``torch.distributed`` file-store rendezvous, the first host a TCP rendezvous; like the reference, a
+    tracker directory must be fresh for every job."""
+    if dist.is_available() and dist.is_initialized():
+        return
+    import datetime
+    use_cuda = torch.cuda.is_available() and device != "cpu"
+    os.environ["RANK"], os.environ["WORLD_SIZE"] = str(int(task_index)), str(int(task_count))
+    os.environ.setdefault("LOCAL_RANK", str(int(task_index)))
+    if hosts:
+        first = hosts.split(",")[0].strip()
+        method = "tcp://" + first
+    else:
+        d = os.path.abspath(tracker or "/tmp/graphlearn")
+        os.makedirs(d, exist_ok=True)
+        method = "file://" + os.path.join(d, "glb_rendezvous_%d" % int(task_count))
+    if use_cuda:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl" if use_cuda else "gloo", init_method=method, rank=int(task_index), world_size=int(task_count),
+                            timeout=datetime.timedelta(seconds=timeout_s))
+    Runtime.get().owns_pg = True
+
+
 # ---------------------------------------------------------------------- descriptors
 def _pad8(xs, fill=0):
     xs = list(xs)

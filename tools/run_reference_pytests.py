@@ -149,6 +149,55 @@ def main():
             bad_files.append(label)
             if a.v:
                 print(out[-3000:])
+    # the reference's DISTRIBUTED worker-mode launch (run_dist_worker_mode_{fs,rpc}_tracker.sh): two plain processes, no torchrun -
+    # each calls g.init(task_index=i, task_count=2, tracker=dir) or g.init(task_index=i, hosts="h:p,h:p")
+    import socket
+
+    def free_port():
+        sk = socket.socket()
+        sk.bind(("127.0.0.1", 0))
+        pt = sk.getsockname()[1]
+        sk.close()
+        return pt
+    for script, mk_args in (("test_dist_worker_mode_fs_tracker.py", lambda i, w, hp: ["--task_index=%d" % i, "--task_count=2", "--tracker=" + os.path.join(w, "tracker")]),
+                            ("test_dist_worker_mode_rpc_tracker.py", lambda i, w, hp: ["--task_index=%d" % i, "--hosts=" + hp])):
+        label = "examples/basic/" + script + " (2 workers)"
+        if a.pattern and a.pattern not in label.replace("/", "_"):
+            continue
+        import shutil
+        d = tempfile.mkdtemp(prefix="glb_refdist_")
+        w = os.path.join(d, "basic")
+        shutil.copytree(basic, w)
+        os.makedirs(os.path.join(w, "data"), exist_ok=True)
+        os.makedirs(os.path.join(w, "tracker"), exist_ok=True)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="", GLB_TEST_DEVICE="cpu")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        pre = ("import sys, os, runpy\nsys.path.insert(0, %r)\nimport graphlearn_b200 as gl, graphlearn_b200.python as glp\n"
+               "import graphlearn_b200.python.nn.tf, graphlearn_b200.python.nn.pytorch\n"
+               "for n, m in list(sys.modules.items()):\n    if n == 'graphlearn_b200' or n.startswith('graphlearn_b200.'): sys.modules['graphlearn' + n[15:]] = m\n"
+               "sys.path.insert(0, %r); os.chdir(%r)\n" % (ROOT, w, w))
+        subprocess.run([sys.executable, "-c", pre + "runpy.run_path('gen_test_data.py', run_name='__main__')\n"], capture_output=True, env=env, timeout=a.timeout)
+        hp = "127.0.0.1:%d,127.0.0.1:%d" % (free_port(), free_port())
+        procs = []
+        for i in range(2):
+            code = pre + "sys.argv = %r\nrunpy.run_path(%r, run_name='__main__')\nprint('WORKER_OK')\n" % ([script] + mk_args(i, w, hp), script)
+            procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        outs = []
+        ok = True
+        for pr in procs:
+            try:
+                o = pr.communicate(timeout=a.timeout)[0]
+            except subprocess.TimeoutExpired:
+                pr.kill()
+                o = "TIMEOUT"
+            outs.append(o)
+            ok = ok and pr.returncode == 0 and "WORKER_OK" in o
+        print("%-55s %s" % (label, "ok" if ok else "FAIL"))
+        if not ok:
+            bad_files.append(label)
+            if a.v:
+                print("\n".join(x[-2000:] for x in outs))
     print("TOTAL files=%d %s  not-clean: %s" % (len(files), tot, bad_files))
     return 0 if not bad_files else 1
 
