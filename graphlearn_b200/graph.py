@@ -198,14 +198,14 @@ class Graph(object):
         return self.init(task_index=task_index)
 
     def deploy_in_worker_mode(self, tracker=None, hosts=None, task_index=0, task_count=1):
-        """every process owns a shard AND trains (``torchrun``): the tracker directory / host list of the reference are not
-        needed - the ranks rendezvous through ``torch.distributed`` (RANK / WORLD_SIZE); a mismatching ``task_count`` is an error"""
+        """every process owns a shard AND trains.  Under ``torchrun`` the ranks already know each other (a mismatching task count
+        is an error); launched as N plain processes (the reference's way) the tracker directory or the host list is the
+        rendezvous (``parallel/runtime.py:bootstrap_cluster``)."""
         import os as _os
-        world = int(_os.environ.get("WORLD_SIZE", "1"))
-        n = len(hosts.split(",")) if hosts else int(task_count)
-        if n != world:
-            raise ValueError("worker mode with %d tasks needs a %d-process torchrun job (WORLD_SIZE is %d)" % (n, n, world))
-        return self.init(task_index=task_index, task_count=n)
+        n = len([h for h in hosts.split(",") if h.strip()]) if hosts else int(task_count)
+        if "WORLD_SIZE" in _os.environ and n != int(_os.environ["WORLD_SIZE"]):
+            raise ValueError("worker mode with %d tasks inside a %s-process torchrun job" % (n, _os.environ["WORLD_SIZE"]))
+        return self.init(task_index=task_index, task_count=n, tracker=tracker, hosts=hosts)
 
     def deploy_in_server_mode(self, task_index, cluster, job_name):
         """``job_name`` 'server': build this shard and serve it; 'client': connect to the servers of ``cluster``"""

@@ -658,8 +658,12 @@ def test_graph_deploy_modes_reverse_edges_and_attribute_selection(tmp_path):
         g.node_attributes("nobody", [0], n_float=1)
     with pytest.raises(ValueError):
         g.node_attributes("item", [0], n_int=1)                    # column 0 is a float
-    with pytest.raises(ValueError):
-        g.deploy_in_worker_mode(hosts="a:1,b:2", task_index=0)      # 2 tasks but a 1-process job
+    os.environ["WORLD_SIZE"] = "1"
+    try:
+        with pytest.raises(ValueError):
+            g.deploy_in_worker_mode(hosts="a:1,b:2", task_index=0)      # 2 tasks inside a 1-process torchrun job
+    finally:
+        del os.environ["WORLD_SIZE"]
     with pytest.raises(ValueError):
         g.deploy_in_server_mode(0, {"server": "127.0.0.1:1"}, "trainer")
     with pytest.raises(gl.UnimplementedError):

@@ -39,6 +39,21 @@ def test_sharded_embedding_two_ranks_cpu_gloo():
     _run(2, 29650, {"CUDA_VISIBLE_DEVICES": ""}, "dist_embedding_worker.py", [], "EMB_ALL_OK")
 
 
+def test_worker_mode_with_tracker_directory_no_torchrun(tmp_path):
+    """The reference's worker-mode launch: N PLAIN processes, each calling g.init(task_index=i, task_count=N, tracker=dir) - the
+    tracker directory is the rendezvous (parallel/runtime.py:bootstrap_cluster), no torchrun, no RANK / WORLD_SIZE variables."""
+    from tests import fixtures as fx
+    d = fx.write_graph(str(tmp_path / "g"))
+    tracker = str(tmp_path / "tracker")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env.update(PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "tracker_worker.py"), d, tracker, str(i), "2"], env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for i in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for i, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "TRACKER_WORKER_OK %d" % i in o, o[-3000:]
+
+
 def test_nn_utils_two_ranks_cpu_gloo():
     _run(2, 29653, {"CUDA_VISIBLE_DEVICES": ""}, "dist_nn_utils_worker.py", [], "NN_UTILS_OK")
 
