@@ -153,8 +153,26 @@ class Graph(object):
             spec = _json.loads(cluster) if isinstance(cluster, str) else dict(cluster)
         self._remote = None
         self._server = None
+        ep_dir = None
+        if spec and job_name in ("server", "client") and not spec.get("server"):
+            # FS-tracker server mode: no host list, the servers publish "ip:port" under <tracker>/endpoints/<index> and the
+            # clients read them (the reference's FS naming engine, fs_naming_engine.cc:80-153)
+            import os as _os
+            ep_dir = _os.path.join(_os.path.abspath(spec.get("tracker") or kwargs.get("tracker") or "/tmp/graphlearn"), "endpoints")
+            _os.makedirs(ep_dir, exist_ok=True)
         if spec and job_name == "client":
             from .service import RemoteGraphClient
+            if ep_dir is not None:
+                import os as _os
+                import time as _time
+                S = int(spec.get("server_count", 1))
+                t0 = _time.time()
+                while len([f for f in _os.listdir(ep_dir) if f.isdigit()]) < S:
+                    if _time.time() - t0 > float(_config.get().timeout or 60) * 5:
+                        raise errors.DeadlineExceededError("only %d of %d servers published an endpoint under %s" %
+                                                           (len(_os.listdir(ep_dir)), S, ep_dir))
+                    _time.sleep(0.1)
+                spec["server"] = ",".join(open(_os.path.join(ep_dir, str(i))).read().strip() for i in range(S))
             self._remote = RemoteGraphClient(spec["server"], client_id=int(task_index), client_count=int(spec.get("client_count", 1)))
             meta = self._remote.meta
             self._node_decoders, self._edge_decoders = dict(meta["node_decoders"]), dict(meta["edge_decoders"])
@@ -187,9 +205,23 @@ class Graph(object):
         if spec and job_name == "server":
             from .service import GraphServer
             from .service.client import _parse
-            addrs = [a for a in str(spec["server"]).split(",") if a]
-            self._server = GraphServer(self, address=_parse(addrs[int(task_index) % len(addrs)]),
-                                       client_count=int(spec.get("client_count", 1))).start()
+            import os as _os
+            addrs = [a for a in str(spec.get("server") or "").split(",") if a]
+            S = len(addrs) or int(spec.get("server_count", 1))
+            if S > 1 and self._rt.world == 1:
+                # several server PROCESSES that are not one process group (the reference's launch: plain processes + tracker):
+                # every server holds the whole graph and TRAVERSES its hash share of the ids; look-ups / sampling of any id
+                # are local.  (Under torchrun the servers form one sharded group instead.)
+                self._traverse_shard = (int(task_index), S)
+            address = _parse(addrs[int(task_index) % len(addrs)]) if addrs else ("127.0.0.1", 0)
+            self._server = GraphServer(self, address=address, client_count=int(spec.get("client_count", 1)),
+                                       server_index=int(task_index), server_count=S).start()
+            if ep_dir is not None:
+                host, port = self._server.address[0], self._server.address[1]
+                tmp = _os.path.join(ep_dir, ".%d.tmp" % int(task_index))
+                with open(tmp, "w") as f:
+                    f.write("%s:%d" % (host, port))
+                _os.replace(tmp, _os.path.join(ep_dir, str(int(task_index))))
         return self
 
     # ---- the reference's deployment entry points (graph.py:439-511); ``init`` picks one of them from its arguments
@@ -326,6 +358,8 @@ class Graph(object):
     def get_stats(self):
         """{type: [count on rank 0, count on rank 1, ...]} (GetStats)."""
         self._check_inited()
+        if self.remote:                                   # server-mode client: ask the servers this client talks to
+            return dict(self._remote.conns[0].call("stats")[1])
         return dict(self._store.stats)
 
     server_get_stats = get_stats

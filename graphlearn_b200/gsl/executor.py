@@ -116,11 +116,24 @@ class QueryExecutor(object):
                                       dev, seed=seed)
         elif isinstance(node, TraverseSourceEdgeDagNode) or p.get("node_from", NODE) != NODE:
             csr = self.store.edges[p["edge_type"]]
-            self._iter = SeedIterator(csr.n_edges, int(p.get("batch_size", 64)), p.get("strategy", "by_order"), dev,
+            n_edges = csr.n_edges
+            self._edge_sel = None
+            shard = getattr(self.g, "_traverse_shard", None)
+            if shard is not None and n_edges > 0:
+                # replicated multi-server mode: this server traverses the edges whose SOURCE id hashes to it
+                pos = csr.insertion_pos()
+                src_ids = self.g.to_ids(csr.src_type, csr._row_of_edge[pos] * self.rt.world + r)
+                self._edge_sel = (src_ids.abs() % shard[1] == shard[0]).nonzero().flatten()
+                n_edges = int(self._edge_sel.numel())
+            self._iter = SeedIterator(n_edges, int(p.get("batch_size", 64)), p.get("strategy", "by_order"), dev,
                                       seed=seed, drop_last=self.drop_last)
         else:
             tab = self.store.nodes[node.type]
             rows = tab.present.nonzero().flatten() if tab.present is not None else torch.arange(tab.n_local, device=dev)
+            shard = getattr(self.g, "_traverse_shard", None)
+            if shard is not None and rows.numel() > 0:
+                ids_ = tab.idmap.to_id(rows * self.rt.world + r) if not tab.idmap.dense else rows * self.rt.world + r
+                rows = rows[ids_.abs() % shard[1] == shard[0]]         # this server's share of the node ids
             self._rows = rows
             self._iter = SeedIterator(int(rows.numel()), int(p.get("batch_size", 64)), p.get("strategy", "by_order"), dev,
                                       seed=seed, drop_last=self.drop_last)
@@ -172,7 +185,8 @@ class QueryExecutor(object):
         # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
         # index, memory_edge_storage.cc; GetEdges by_order walks edge ids) - chronological event
         # files therefore yield chronological batches although the CSR is row-major
-        idx = csr.insertion_pos()[self._iter.next_index()]
+        nxt = self._iter.next_index()
+        idx = csr.insertion_pos()[nxt if getattr(self, "_edge_sel", None) is None else self._edge_sel[nxt]]
         if p["node_from"] == EDGE_SRC:
             vids = csr._row_of_edge[idx] * W + r
             t = csr.src_type
@@ -222,7 +236,8 @@ class QueryExecutor(object):
         # traversal follows the INSERTION order of the edges (the reference's edge id = insertion
         # index, memory_edge_storage.cc; GetEdges by_order walks edge ids) - chronological event
         # files therefore yield chronological batches although the CSR is row-major
-        idx = csr.insertion_pos()[self._iter.next_index()]
+        nxt = self._iter.next_index()
+        idx = csr.insertion_pos()[nxt if getattr(self, "_edge_sel", None) is None else self._edge_sel[nxt]]
         src_v = csr._row_of_edge[idx] * W + r
         dst_v = csr.indices.local[idx]
         src_ids = self.g.to_ids(csr.src_type, src_v)

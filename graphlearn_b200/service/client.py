@@ -36,6 +36,18 @@ class _Conn(object):
 
 
 def decode_value(d: dict, graph=None):
+    sp = d.get("sparse")
+    attrs = dict(int_attrs=d.get("int_attrs"), float_attrs=d.get("float_attrs"), string_attrs=d.get("string_attrs"),
+                 weights=d.get("weights"), labels=d.get("labels"), timestamps=d.get("timestamps"))
+    if sp is not None and d["kind"] == "nodes":
+        v = V_.SparseNodes(d["ids"], sp["offsets"], tuple(sp["dense_shape"]), d["type"], graph=graph, **attrs)
+        v._inited = True
+        return v
+    if sp is not None:
+        v = V_.SparseEdges(d["src_ids"], d["src_type"], d["dst_ids"], d["dst_type"], d["edge_type"], sp["offsets"],
+                           tuple(sp["dense_shape"]), edge_ids=d["edge_ids"], graph=graph, **attrs)
+        v._inited = True
+        return v
     if d["kind"] == "nodes":
         v = V_.Nodes(d["ids"], d["type"], int_attrs=d.get("int_attrs"), float_attrs=d.get("float_attrs"),
                      string_attrs=d.get("string_attrs"), weights=d.get("weights"), labels=d.get("labels"),

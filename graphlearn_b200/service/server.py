@@ -20,8 +20,11 @@ def _np(x):
 def encode_value(v, no_property: bool = False) -> dict:
     """Nodes / Edges -> plain dict of numpy arrays (ids + every attribute the decoder declares: the reference ships the
     LookupNodes / LookupEdges results inside the tape, dag_node.py:558-564,595-610)."""
-    if isinstance(v, (V_.SparseNodes, V_.SparseEdges, V_.SubGraph)):
-        raise errors.UnimplementedError("server mode streams dense Nodes / Edges values (sparse / sub-graph queries run in worker mode)")
+    if isinstance(v, V_.SubGraph):
+        raise errors.UnimplementedError("server mode streams Nodes / Edges values (sub-graph queries run in worker mode)")
+    sparse = None
+    if isinstance(v, (V_.SparseNodes, V_.SparseEdges)):      # 'full' neighbourhoods: values + per-row counts + dense shape
+        sparse = {"offsets": _np(v.offsets), "dense_shape": tuple(v.dense_shape)}
     if isinstance(v, V_.Edges):
         d = {"kind": "edges", "edge_type": v.edge_type, "src_type": v.src_type, "dst_type": v.dst_type, "shape": tuple(v.shape),
              "src_ids": _np(v.src_ids), "dst_ids": _np(v.dst_ids), "edge_ids": _np(v.edge_ids)}
@@ -31,6 +34,8 @@ def encode_value(v, no_property: bool = False) -> dict:
         dec = v._get_decoder()
     else:
         raise errors.UnimplementedError("cannot ship %r" % (type(v),))
+    if sparse is not None:
+        d["sparse"] = sparse
     if not no_property:
         if dec.float_attr_num:
             d["float_attrs"] = _np(v.float_attrs)
@@ -48,12 +53,18 @@ def encode_value(v, no_property: bool = False) -> dict:
 
 
 class GraphServer(object):
-    def __init__(self, graph, address: Tuple[str, int] = ("127.0.0.1", 0), client_count: int = 1, authkey: bytes = AUTHKEY):
+    def __init__(self, graph, address: Tuple[str, int] = ("127.0.0.1", 0), client_count: int = 1, authkey: bytes = AUTHKEY,
+                 server_index: int = 0, server_count: int = 1):
         graph._check_inited()
         self.g = graph
         self._listener = Listener(address, authkey=authkey)
         self.address = self._listener.address
-        self.client_count = int(client_count)
+        # how many clients will say STOP to THIS server: the same round-robin deal the clients apply
+        # (service/client.py RemoteGraphClient: S >= C -> client c owns servers {s : s % C == c}; else client c uses server c % S)
+        S, C = max(1, int(server_count)), max(1, int(client_count))
+        self.client_count = 1 if S >= C else len([c for c in range(C) if c % S == int(server_index)])
+        if S == 1:
+            self.client_count = C
         self._stops = 0
         self._lock = threading.Lock()
         self._done = threading.Event()
@@ -71,6 +82,8 @@ class GraphServer(object):
             self._listener.close()
         except Exception:
             pass
+        for t in list(self._threads):          # let the connection threads close their datasets before the process exits
+            t.join(timeout=10)
 
     # ------------------------------------------------------------------ internals
     def _accept_loop(self):

@@ -212,6 +212,51 @@ def main():
             bad_files.append(label)
             if a.v:
                 print("\n".join(x[-2000:] for x in outs))
+    # the reference's SERVER-mode launch (run_dist_server_mode_{fs,rpc}_tracker.sh): 2 graph servers + 3 clients as plain processes
+    for script, mk_args in (("test_dist_server_mode_fs_tracker.py",
+                             lambda job, i, w, hp: ["--server_count=2", "--client_count=3", "--tracker=" + os.path.join(w, "tracker"),
+                                                    "--job_name=" + job, "--task_index=%d" % i]),
+                            ("test_dist_server_mode_rpc_tracker.py",
+                             lambda job, i, w, hp: ["--server=" + hp, "--client_count=3", "--job_name=" + job, "--task_index=%d" % i])):
+        label = "examples/basic/" + script + " (2 servers + 3 clients)"
+        if (a.pattern and a.pattern not in label.replace("/", "_")) or (a.quick and "rpc" in script):
+            continue
+        import shutil
+        d = tempfile.mkdtemp(prefix="glb_refsrv_")
+        w = os.path.join(d, "basic")
+        shutil.copytree(basic, w)
+        os.makedirs(os.path.join(w, "data"), exist_ok=True)
+        os.makedirs(os.path.join(w, "tracker"), exist_ok=True)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="", GLB_TEST_DEVICE="cpu")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        pre = ("import sys, os, runpy\nsys.path.insert(0, %r)\nimport graphlearn_b200 as gl, graphlearn_b200.python as glp\n"
+               "import graphlearn_b200.python.nn.tf, graphlearn_b200.python.nn.pytorch\n"
+               "for n, m in list(sys.modules.items()):\n    if n == 'graphlearn_b200' or n.startswith('graphlearn_b200.'): sys.modules['graphlearn' + n[15:]] = m\n"
+               "sys.path.insert(0, %r); os.chdir(%r)\n" % (ROOT, w, w))
+        subprocess.run([sys.executable, "-c", pre + "runpy.run_path('gen_test_data.py', run_name='__main__')\n"], capture_output=True, env=env, timeout=a.timeout)
+        hp = "127.0.0.1:%d,127.0.0.1:%d" % (free_port(), free_port())
+        procs = []
+        for job, i in (("server", 0), ("server", 1), ("client", 0), ("client", 1), ("client", 2)):
+            code = pre + "sys.argv = %r\nrunpy.run_path(%r, run_name='__main__')\nprint('PROC_OK')\n" % ([script] + mk_args(job, i, w, hp), script)
+            procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+            if job == "server":
+                import time as _t
+                _t.sleep(0.5)
+        outs, ok = [], True
+        for pr in procs:
+            try:
+                o = pr.communicate(timeout=a.timeout)[0]
+            except subprocess.TimeoutExpired:
+                pr.kill()
+                o = "TIMEOUT"
+            outs.append(o)
+            ok = ok and pr.returncode == 0 and "PROC_OK" in o
+        print("%-55s %s" % (label, "ok" if ok else "FAIL"))
+        if not ok:
+            bad_files.append(label)
+            if a.v:
+                print("\n".join(x[-1500:] for x in outs))
     print("TOTAL files=%d %s  not-clean: %s" % (len(files), tot, bad_files))
     return 0 if not bad_files else 1
 
