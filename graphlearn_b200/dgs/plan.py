@@ -66,7 +66,17 @@ class QueryPlan(object):
                 par.setdefault(l["node"], n["id"])
         params = lambda n: {p["key"]: p["value"] for p in n.get("params", [])}  # noqa: E731
         src = [n for n in d["plan_nodes"] if n["kind"] == "SOURCE"][0]
-        plan = QueryPlan(schema.vertex_name[params(src)["vtype"]])
+        src_vtype = params(src).get("vtype")
+        if src_vtype is None:
+            # some install-query files (conf/dblp) leave the SOURCE node without parameters: its vertex type is the one its
+            # first downstream sampler starts from
+            for l in src.get("links", []):
+                src_vtype = params(raw[l["node"]]).get("vtype")
+                if src_vtype is not None:
+                    break
+        if src_vtype is None:
+            raise ValueError("install query: cannot determine the vertex type of the SOURCE node")
+        plan = QueryPlan(schema.vertex_name[src_vtype])
         remap = {src["id"]: 0}
         for nid in sorted(raw):
             n = raw[nid]

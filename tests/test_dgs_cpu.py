@@ -668,3 +668,30 @@ def test_remote_data_loader_sdk():
         assert v["s"]["features"].tolist() == [[0.5, 1.5]]
     finally:
         front.stop()
+
+
+def test_reference_dgs_conf_files_load():
+    """The reference's own service configuration files (dynamic_graph_service/conf/{u2i,dblp,ut}: schema JSON, install-query JSON incl.
+    the parameter-less SOURCE node of conf/dblp, YAML option files) drive this service unchanged.  Skipped without a checkout."""
+    import glob
+    import json
+    import os
+    from graphlearn_b200.dgs import Options, Schema
+    base = os.path.join(os.environ.get("GLB_REFERENCE_DIR", "/root/reference"), "dynamic_graph_service", "conf")
+    if not os.path.isdir(base):
+        pytest.skip("no reference checkout")
+    want = {"u2i": [("u2i", 10), ("i2i", 5)], "dblp": [("published", 5), ("written", 5)]}
+    for name in ("u2i", "dblp", "ut"):
+        sch = Schema.from_json(os.path.join(base, name, "schema.%s.json" % name))
+        iq = json.load(open(os.path.join(base, name, "install_query.%s.json" % name)))
+        plan = QueryPlan.from_json(iq, sch)
+        svc = DynamicGraphService(sch.to_service_schema(capacity=8), device="cpu")
+        svc.install_query(int(iq.get("query_id", 0)), plan)
+        if name in want:
+            assert plan.hops == want[name]
+        src_type = plan.source_type
+        first = plan.edge_nodes()[0].etype
+        svc.apply_updates({"edges": {first: {"src": [1, 1], "dst": [2, 3], "ts": [5, 6]}}})
+        assert svc.run_query(int(iq.get("query_id", 0)), [1])["hops"][0]["ids"][0, 0].item() == 3 and src_type in sch.vertex_id
+    for y in glob.glob(os.path.join(base, "ut", "*.yml")):
+        assert Options.from_yaml(y).get("http-port") is not None
