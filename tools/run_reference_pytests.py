@@ -257,6 +257,32 @@ def main():
             bad_files.append(label)
             if a.v:
                 print("\n".join(x[-1500:] for x in outs))
+    # the reference's DGS tutorial data: its u2i generator (python/data/u2i/u2i_generator.py -> /tmp/u2i_gen) + its conf/u2i schema and
+    # install-query files drive THIS service through the pattern-file loader (native parser and Python loader must agree)
+    label = "dynamic_graph_service u2i generator + conf -> service"
+    gen = os.path.join(a.ref, "dynamic_graph_service", "python", "data", "u2i", "u2i_generator.py")
+    if os.path.exists(gen) and (not a.pattern or a.pattern in "dgs_u2i") and not a.quick:
+        code = ("import json, sys, runpy\nsys.path.insert(0, %r)\nrunpy.run_path(%r, run_name='__main__')\n"
+                "from graphlearn_b200.dgs import Schema, QueryPlan, DynamicGraphService, FileLoader\nbase = %r\n"
+                "sch = Schema.from_json(base + '/schema.u2i.json'); iq = json.load(open(base + '/install_query.u2i.json'))\nres = []\n"
+                "for native in (True, False):\n"
+                "    svc = DynamicGraphService(sch.to_service_schema(capacity=64, feat_dims={'user': 10, 'item': 10}), device='cpu')\n"
+                "    svc.install_query(0, QueryPlan.from_json(iq, sch))\n"
+                "    n = FileLoader('/tmp/u2i_gen/streaming/u2i.pattern', sch, native=native).load('/tmp/u2i_gen/streaming/u2i.streaming', svc)\n"
+                "    r = svc.run_query(0, [0, 1, 2])\n    res.append((n, r['hops'][0]['ids'].tolist(), r['hops'][1]['ids'][:3].tolist()))\n"
+                "assert res[0] == res[1] and res[0][0] > 10000 and all(x >= 0 for x in res[0][1][0])\nprint('DGS_U2I_OK')\n"
+                % (ROOT, gen, os.path.join(a.ref, "dynamic_graph_service", "conf", "u2i")))
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        try:
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=a.timeout, env=env, cwd=tempfile.mkdtemp())
+            ok, out = p.returncode == 0 and "DGS_U2I_OK" in p.stdout, p.stdout + p.stderr
+        except subprocess.TimeoutExpired:
+            ok, out = False, "TIMEOUT"
+        print("%-55s %s" % (label, "ok" if ok else "FAIL"))
+        if not ok:
+            bad_files.append(label)
+            if a.v:
+                print(out[-2000:])
     print("TOTAL files=%d %s  not-clean: %s" % (len(files), tot, bad_files))
     return 0 if not bad_files else 1
 
