@@ -17,9 +17,21 @@ def _parse(addr) -> Tuple[str, int]:
 
 
 class _Conn(object):
-    def __init__(self, addr, authkey=AUTHKEY):
+    def __init__(self, addr, authkey=AUTHKEY, connect_timeout: float = None):
+        """A server that is still loading its graph does not listen yet: retry the connection until ``gl.set_timeout`` seconds
+        have passed (the reference's channel manager re-resolves broken channels every second, channel_manager.cc:151-170)."""
+        import time
+        from .. import config as _config
         self.addr = _parse(addr)
-        self._c = Client(self.addr, authkey=authkey)
+        deadline = time.time() + float(connect_timeout if connect_timeout is not None else (_config.get().timeout or 60))
+        while True:
+            try:
+                self._c = Client(self.addr, authkey=authkey)
+                break
+            except (ConnectionRefusedError, ConnectionResetError, FileNotFoundError):
+                if time.time() >= deadline:
+                    raise errors.UnavailableError("graph server %s:%d is not reachable" % self.addr)
+                time.sleep(0.2)
 
     def call(self, *req):
         self._c.send(tuple(req))
