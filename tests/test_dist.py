@@ -54,6 +54,36 @@ def test_worker_mode_with_tracker_directory_no_torchrun(tmp_path):
         assert p.returncode == 0 and "TRACKER_WORKER_OK %d" % i in o, o[-3000:]
 
 
+def test_server_mode_two_independent_servers_with_tracker(tmp_path):
+    """Server mode launched the reference's way: 2 server + 2 client PLAIN processes, cluster = {server_count, client_count,
+    tracker}.  The servers publish their endpoints under the tracker directory, hold the whole graph and traverse their hash
+    share of the ids: the union of what the two clients see is every user / every edge exactly once; look-ups of any id and
+    full-neighbour (sparse) values work on either server."""
+    import json
+    from tests import fixtures as fx
+    d = fx.write_graph(str(tmp_path / "g"))
+    tracker = str(tmp_path / "tracker")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env.update(PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    procs = []
+    for job, i in (("server", 0), ("server", 1), ("client", 0), ("client", 1)):
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "server_mode_proc.py"), d, tracker, job, str(i),
+                                       str(tmp_path / ("out_%s_%d.json" % (job, i)))], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "SERVER_MODE_PROC_OK" in o, o[-3000:]
+    res = [json.load(open(str(tmp_path / ("out_client_%d.json" % i)))) for i in range(2)]
+    users = res[0]["users"] + res[1]["users"]
+    assert sorted(users) == list(range(fx.N_USER))                                     # every user exactly once over the clients
+    assert set(res[0]["users"]) == {u for u in range(fx.N_USER) if u % 2 == 0}        # client 0 <-> server 0 <-> even ids
+    adj = fx.u2i_adj()
+    want_edges = sorted((u, i) for u in adj for i, _ in adj[u])
+    assert sorted(map(tuple, res[0]["edges"] + res[1]["edges"])) == want_edges
+    assert res[0]["full"] == [len(adj[u]) for u in res[0]["users"][:5]]
+    assert res[0]["stats"]["user"] == [fx.N_USER]
+
+
 def test_nn_utils_two_ranks_cpu_gloo():
     _run(2, 29653, {"CUDA_VISIBLE_DEVICES": ""}, "dist_nn_utils_worker.py", [], "NN_UTILS_OK")
 
