@@ -222,7 +222,22 @@ def bootstrap_cluster(task_index: int, task_count: int, tracker: Optional[str] =
     else:
         d = os.path.abspath(tracker or "/tmp/graphlearn")
         os.makedirs(d, exist_ok=True)
-        method = "file://" + os.path.join(d, "glb_rendezvous_%d" % int(task_count))
+        path = os.path.join(d, "glb_rendezvous_%d" % int(task_count))
+        # a file store removes its file when the job ends cleanly; one left behind by a CRASHED job would poison this one:
+        # task 0 deletes a rendezvous file that is older than two minutes, the others wait until it is gone or fresh
+        import time as _time
+        stale = lambda: os.path.exists(path) and _time.time() - os.path.getmtime(path) > 120     # noqa: E731
+        if int(task_index) == 0:
+            if stale():
+                try:
+                    os.remove(path)
+                except OSError:
+                    pass
+        else:
+            t0 = _time.time()
+            while stale() and _time.time() - t0 < timeout_s:
+                _time.sleep(0.2)
+        method = "file://" + path
     if use_cuda:
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl" if use_cuda else "gloo", init_method=method, rank=int(task_index), world_size=int(task_count),
