@@ -320,6 +320,15 @@ def test_reference_import_paths():
     assert not [n for n in ("Data", "Dataset", "SubGraph", "HeteroSubGraph") if not hasattr(gnn, n)]
     import graphlearn_b200.python as glp
     assert glp.Graph is gl.Graph and glp.nn.Data is nn.Data
+    # the deep module paths the reference's own examples import from
+    import importlib
+    for mod, names in (("nn.data", ["Data"]), ("nn.subgraph", ["SubGraph"]), ("nn.hetero_subgraph", ["HeteroSubGraph"]),
+                       ("nn.dataset", ["Dataset"]), ("nn.tf.module", ["Module"]), ("nn.tf.config", ["conf"]),
+                       ("nn.tf.layers.sage_conv", ["SAGEConv"]), ("nn.tf.layers.linear_layer", ["LinearLayer"]),
+                       ("nn.tf.layers.hetero_conv", ["HeteroConv"]), ("nn.tf.layers.ego_layer", ["EgoLayer", "EgoConv"]),
+                       ("nn.tf.layers.ego_sage_conv", ["EgoSAGEConv"]), ("nn.tf.layers.gat_conv", ["GATConv"])):
+        m = importlib.import_module("graphlearn_b200.python." + mod)
+        assert all(hasattr(m, n) for n in names), mod
 
 
 def test_reference_unit_tests_pass_against_this_package():
